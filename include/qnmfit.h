@@ -1,0 +1,182 @@
+/*
+ * qnmfit.h — C ABI of libqnmfit.so: batched complex least-squares ringdown fits on
+ * one NVIDIA B200 (sm_100a).
+ *
+ * The reference (eliotfinch/qnmfits) has no FFI: its boundary is a set of Python
+ * functions.  This library sits *underneath* that surface.  Each entry point names
+ * the reference code it replaces (paths relative to the reference checkout):
+ *
+ *   qnmfit_fit_batch   one launch = B independent fits, each doing what the body of
+ *                      ringdown_fit (qnmfits/qnmfits.py:274-293) or
+ *                      multimode_ringdown_fit (qnmfits/qnmfits.py:606-652) does for
+ *                      ONE grid point / start time: form the frequencies
+ *                      (qnmfits/qnm.py:235,272-280; qnmfits.py:274), build the design
+ *                      matrix a[k,j] = coef * exp(-i w_j (t_k - t0))
+ *                      (qnmfits.py:280-283, :628-631), solve min ||a C - d||_2
+ *                      (qnmfits.py:287, :635 -> LAPACK zgelsd), evaluate the model
+ *                      (qnmfits.py:290, :639) and the trapezoid mismatch
+ *                      (qnmfits.py:90-97, :123-139).  The B-loop replaces the serial
+ *                      Python loops of mismatch_t0_array (qnmfits.py:1271-1281) and
+ *                      mismatch_M_chi_grid (qnmfits.py:1391-1410).
+ *   qnmfit_eval_batch  the model + mismatch half only, for caller-supplied
+ *                      amplitudes (qnmfits.py:290-293, :639-652).
+ *
+ * All pointers in qnmfit_batch are DEVICE pointers (the Python wrapper passes
+ * torch tensors' data_ptr()); complex128 arrays are interleaved (re, im) doubles,
+ * layout-compatible with numpy complex128 and CUDA double2.  The caller owns every
+ * buffer and must keep it alive until the stream has been synchronised.  No C++
+ * types, exceptions or torch types cross this boundary.
+ *
+ * Return value of every call: 0 on success; QNMFIT_E_* (< 0) for argument errors;
+ * > 0 is a cudaError_t passed through.  qnmfit_last_error() gives the message.
+ * Numerical conditions of individual fits never fail a batch: they are reported
+ * per fit in status[] (QNMFIT_ST_* bits).
+ */
+#ifndef QNMFIT_H
+#define QNMFIT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QNMFIT_ABI_VERSION 1
+
+/* limits of the compiled kernels */
+#define QNMFIT_MAX_MODES_SMALL 8     /* register-resident TSQR kernel (K1)   */
+#define QNMFIT_MAX_MODES 64          /* CTA-cooperative general kernel (K2)  */
+
+/* argument errors */
+#define QNMFIT_E_NULL      (-1)      /* required pointer is NULL                  */
+#define QNMFIT_E_SHAPE     (-2)      /* sizes out of range / inconsistent         */
+#define QNMFIT_E_WINDOW    (-3)      /* shared window empty or outside the series */
+#define QNMFIT_E_ABI       (-4)      /* struct_size does not match this library   */
+#define QNMFIT_E_NOGPU     (-5)      /* no usable sm_100 device                   */
+
+/* per-fit status bits */
+#define QNMFIT_ST_OK            0
+#define QNMFIT_ST_RANK_DEFICIENT 1   /* |R_jj| <= eps*max(M,N)*max|R_jj| for some j:
+                                        numpy.linalg.lstsq(rcond=None) may truncate
+                                        (numpy/linalg/_linalg.py:2553) — amplitudes are
+                                        a basic, not the minimum-norm, solution     */
+#define QNMFIT_ST_NONFINITE     2    /* non-finite value met in inputs or outputs  */
+#define QNMFIT_ST_UNDERDETERMINED 4  /* rows <= columns                            */
+
+/* kernel selection (qnmfit_batch.kernel) */
+#define QNMFIT_KERNEL_AUTO    0
+#define QNMFIT_KERNEL_SMALL   1      /* K1: n_series == 1 and n_modes <= 8         */
+#define QNMFIT_KERNEL_GENERAL 2      /* K2: any n_series, n_modes <= 64            */
+
+typedef struct qnmfit_ctx qnmfit_ctx;
+
+typedef struct qnmfit_batch {
+    int32_t struct_size;      /* sizeof(qnmfit_batch), checked                         */
+    int32_t kernel;           /* QNMFIT_KERNEL_*                                       */
+
+    /* ---- problem sizes ---- */
+    int32_t n_fits;           /* B: fits in this launch                                */
+    int32_t n_modes;          /* N: columns (QNMs)                                     */
+    int32_t n_series;         /* L: stacked spherical-harmonic series (1 = single)     */
+    int32_t n_times;          /* K_tot: samples of the full time series                */
+    int64_t series_stride;    /* complex elements between consecutive series in data   */
+    int64_t first_fit;        /* global flat index of fit 0 (index sharding over GPUs) */
+
+    /* ---- shared inputs ---- */
+    const double *times;      /* f64 [n_times], ascending                              */
+    const double *data;       /* c128[n_series][series_stride]                         */
+
+    /* ---- analysis window and start time: per fit, or shared when NULL ---- */
+    const int32_t *row_begin; /* i32 [B] or NULL -> row_begin_all                      */
+    const int32_t *row_end;   /* i32 [B] or NULL -> row_end_all   (half open)          */
+    const double  *t0;        /* f64 [B] or NULL -> t0_all                             */
+    int32_t row_begin_all;
+    int32_t row_end_all;
+    double  t0_all;
+
+    /* ---- frequencies: explicit, or factored (table x 1/Mf x delta) ---- */
+    const double  *omega;        /* c128[B][N] or NULL                                 */
+    const double  *omega_tilde;  /* c128[n_chi][n_constituents]  (Mf = 1 values)       */
+    const int32_t *mode_ptr;     /* i32 [N+1] constituent range of each mode           */
+    const double  *inv_Mf;       /* f64 [n_mf]  1.0/Mf                                 */
+    const double  *delta_factor; /* f64 [N] or NULL (= 1)                              */
+    const int32_t *chi_index;    /* i32 [B] or NULL -> (first_fit + i) % n_chi         */
+    const int32_t *mf_index;     /* i32 [B] or NULL -> (first_fit + i) / n_chi         */
+    int32_t n_chi;
+    int32_t n_mf;
+    int32_t n_constituents;
+    int32_t omega_shared;        /* 1: omega is c128[1][N], the same for every fit     */
+
+    /* ---- per-series column coefficients (mu / identity); NULL = all ones ---- */
+    const double  *coef;         /* c128[n_coef][L][N]                                 */
+    const int32_t *coef_index;   /* i32 [B] or NULL -> the fit's chi index             */
+    int32_t n_coef;
+
+    /* ---- design-matrix generator ---- */
+    int32_t anchor_rows;      /* direct cexp every this many rows (multiple of 4);
+                                 0 -> library default (32)                             */
+    double  dt_nominal;       /* > 0: nearly uniform grid, rows advance by the
+                                 recurrence z *= exp(-i w dt) with first-order
+                                 correction for the deviation of each sample from the
+                                 nominal grid; 0: direct cexp for every element        */
+
+    /* ---- amplitudes in (eval) / out (fit) ---- */
+    double  *C;               /* c128[B][N]; may be NULL for fit                       */
+
+    /* ---- outputs (each may be NULL except mismatch) ---- */
+    double  *mismatch;        /* f64 [B]                                               */
+    double  *residual;        /* f64 [B]  sum |model - data|^2                         */
+    double  *R;               /* c128[B][N][N+1] upper-triangular factor, last column
+                                 = Q^H d (for rank / singular values on the host)      */
+    int32_t *status;          /* i32 [B] QNMFIT_ST_* bits                              */
+    double  *model;           /* c128[B][model_stride]: best-fit model, series-major
+                                 ((i, k) -> i*rows + k, rows = the fit's window length)  */
+    int64_t model_stride;     /* complex elements between consecutive fits in model    */
+} qnmfit_batch;
+
+/* Create / destroy a context bound to one CUDA device (one process per GPU). */
+int qnmfit_create(int device, qnmfit_ctx **out);
+int qnmfit_destroy(qnmfit_ctx *ctx);
+
+/* Message for the most recent non-zero return on this ctx (never NULL).
+ * ctx may be NULL: returns the message of the last failed qnmfit_create. */
+const char *qnmfit_last_error(const qnmfit_ctx *ctx);
+
+/* Launch the fits of *b asynchronously on `stream` (a cudaStream_t; NULL = legacy
+ * default stream).  Replaces the loop bodies cited at the top of this file. */
+int qnmfit_fit_batch(qnmfit_ctx *ctx, const qnmfit_batch *b, void *stream);
+
+/* Model + mismatch (+ residual) only, with amplitudes read from b->C. */
+int qnmfit_eval_batch(qnmfit_ctx *ctx, const qnmfit_batch *b, void *stream);
+
+/* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
+int64_t qnmfit_launch_count(const qnmfit_ctx *ctx);
+
+/* What qnmfit_fit_batch would launch for *b: kernel id, lanes per fit, grid and
+ * block size, dynamic shared memory bytes, registers per thread. */
+typedef struct qnmfit_plan {
+    int32_t kernel;
+    int32_t lanes_per_fit;
+    int32_t grid;
+    int32_t block;
+    int32_t smem_bytes;
+    int32_t regs_per_thread;
+    int32_t staged;           /* waveform window staged in shared memory */
+    int32_t reserved;
+} qnmfit_plan;
+int qnmfit_plan_batch(qnmfit_ctx *ctx, const qnmfit_batch *b, qnmfit_plan *plan);
+
+/* FP64 peak micro-benchmark on the ctx's device: kind 0 = DFMA (vector pipe),
+ * kind 1 = DMMA m8n8k4 (tensor pipe).  Writes TFLOP/s (2 flops per FMA). */
+int qnmfit_fp64_peak(qnmfit_ctx *ctx, int kind, int iters, double *tflops);
+
+/* Algorithmic FP64 flops credited to one fit (DESIGN.md "flop accounting"):
+ * F = 8 M N^2 + 30 M N + 20 M - (8/3) N^3 - 4 N^2 with M = n_series * rows. */
+double qnmfit_flops_per_fit(int rows, int n_modes, int n_series);
+
+int qnmfit_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QNMFIT_H */

@@ -1,0 +1,78 @@
+"""
+TEST INFRASTRUCTURE — loads the *unmodified* reference modules from /root/reference.
+
+Only usable in the build container (the GPU box has no /root/reference).  Used by
+``tests/golden/make_golden.py`` to generate the committed fixtures and by the CPU
+tests (when the path exists) to pin ``oracle/qnmfits_oracle.py`` against the real
+thing.  Nothing in ``qnmfits_b200/`` may import this module.
+
+Recipe: the reference's ``qnmfits/qnmfits.py`` and
+``qnmfits/qnm.py`` import matplotlib, mpl_toolkits, h5py and the ``qnm`` PyPI
+package at module scope (reference qnmfits/qnmfits.py:2,8; qnmfits/qnm.py:2,8).
+None is installed here, and none is on the hot path, so they are replaced by empty
+stubs; ``qnm.modes_cache`` is served by the synthetic table provider.  The package
+``__init__`` (which imports sxs/spherical) is bypassed by registering a bare
+package object whose ``__path__`` points at the reference directory.
+"""
+import importlib
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("QNMFITS_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available():
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "qnmfits", "qnmfits.py"))
+
+
+def _stub(name, **attrs):
+    mod = types.ModuleType(name)
+    mod.__dict__.update(attrs)
+    sys.modules[name] = mod
+    return mod
+
+
+_loaded = None
+
+
+def load_reference(modes_cache=None):
+    """Return the reference's ``qnmfits.qnmfits`` module (functions + ``qnm`` instance)."""
+    global _loaded
+    if _loaded is not None:
+        return _loaded
+    if not reference_available():
+        raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
+    if modes_cache is None:
+        here = os.path.dirname(os.path.abspath(__file__))
+        sys.path.insert(0, os.path.dirname(here))
+        from qnmfits_b200.synthetic import modes_cache as _mc
+        modes_cache = _mc
+
+    saved = {k: sys.modules.get(k) for k in
+             ("matplotlib", "matplotlib.pyplot", "mpl_toolkits",
+              "mpl_toolkits.axes_grid1", "h5py", "qnm", "qnmfits",
+              "qnmfits.qnm", "qnmfits.qnmfits")}
+    try:
+        if "matplotlib" not in sys.modules:
+            mpl = _stub("matplotlib")
+            mpl.pyplot = _stub("matplotlib.pyplot")
+        if "mpl_toolkits.axes_grid1" not in sys.modules:
+            _stub("mpl_toolkits")
+            _stub("mpl_toolkits.axes_grid1", make_axes_locatable=lambda ax: None)
+        if "h5py" not in sys.modules:
+            _stub("h5py", File=None)
+        _stub("qnm", modes_cache=modes_cache)
+        pkg = types.ModuleType("qnmfits")
+        pkg.__path__ = [os.path.join(REFERENCE_ROOT, "qnmfits")]
+        sys.modules["qnmfits"] = pkg
+        ref = importlib.import_module("qnmfits.qnmfits")
+    finally:
+        # Leave no stubs behind: the reference module keeps its own references.
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _loaded = ref
+    return ref

@@ -1,0 +1,166 @@
+"""
+ctypes binding of ``libqnmfit.so`` (C ABI declared in ``include/qnmfit.h``).
+
+There is deliberately no fallback: if the shared library is missing or has no
+usable sm_100 device the functions here raise, they never compute on the CPU.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqnmfit.so")
+
+ABI_VERSION = 1
+MAX_MODES_SMALL = 8
+MAX_MODES = 64
+
+KERNEL_AUTO, KERNEL_SMALL, KERNEL_GENERAL = 0, 1, 2
+
+ST_RANK_DEFICIENT, ST_NONFINITE, ST_UNDERDETERMINED = 1, 2, 4
+
+_dp = C.c_void_p  # device (or, for the test harness, host) pointer
+
+
+class Batch(C.Structure):
+    """Mirror of ``struct qnmfit_batch`` — field order and types must match the header."""
+    _fields_ = [
+        ("struct_size", C.c_int32), ("kernel", C.c_int32),
+        ("n_fits", C.c_int32), ("n_modes", C.c_int32),
+        ("n_series", C.c_int32), ("n_times", C.c_int32),
+        ("series_stride", C.c_int64), ("first_fit", C.c_int64),
+        ("times", _dp), ("data", _dp),
+        ("row_begin", _dp), ("row_end", _dp), ("t0", _dp),
+        ("row_begin_all", C.c_int32), ("row_end_all", C.c_int32),
+        ("t0_all", C.c_double),
+        ("omega", _dp), ("omega_tilde", _dp), ("mode_ptr", _dp),
+        ("inv_Mf", _dp), ("delta_factor", _dp),
+        ("chi_index", _dp), ("mf_index", _dp),
+        ("n_chi", C.c_int32), ("n_mf", C.c_int32),
+        ("n_constituents", C.c_int32), ("omega_shared", C.c_int32),
+        ("coef", _dp), ("coef_index", _dp),
+        ("n_coef", C.c_int32), ("anchor_rows", C.c_int32),
+        ("dt_nominal", C.c_double),
+        ("C", _dp),
+        ("mismatch", _dp), ("residual", _dp), ("R", _dp), ("status", _dp),
+        ("model", _dp), ("model_stride", C.c_int64),
+    ]
+
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        self.struct_size = C.sizeof(Batch)
+
+
+class Plan(C.Structure):
+    _fields_ = [
+        ("kernel", C.c_int32), ("lanes_per_fit", C.c_int32),
+        ("grid", C.c_int32), ("block", C.c_int32),
+        ("smem_bytes", C.c_int32), ("regs_per_thread", C.c_int32),
+        ("staged", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+#: every symbol include/qnmfit.h declares (checked by tests/test_cabi_symbols.py)
+EXPORTS = (
+    "qnmfit_create", "qnmfit_destroy", "qnmfit_last_error", "qnmfit_fit_batch",
+    "qnmfit_eval_batch", "qnmfit_launch_count", "qnmfit_plan_batch",
+    "qnmfit_fp64_peak", "qnmfit_flops_per_fit", "qnmfit_abi_version",
+)
+
+_lib = None
+
+
+class QnmfitError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"libqnmfit error {code}: {message}")
+        self.code = code
+
+
+def load_library(path=None):
+    """dlopen the CUDA library and declare prototypes.  Raises if it is not built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.isfile(path):
+        raise ImportError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (nvcc, sm_100a). qnmfits_b200 has no CPU fallback.")
+    lib = C.CDLL(path)
+    lib.qnmfit_abi_version.restype = C.c_int
+    lib.qnmfit_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.qnmfit_create.restype = C.c_int
+    lib.qnmfit_destroy.argtypes = [C.c_void_p]
+    lib.qnmfit_destroy.restype = C.c_int
+    lib.qnmfit_last_error.argtypes = [C.c_void_p]
+    lib.qnmfit_last_error.restype = C.c_char_p
+    for name in ("qnmfit_fit_batch", "qnmfit_eval_batch"):
+        fn = getattr(lib, name)
+        fn.argtypes = [C.c_void_p, C.POINTER(Batch), C.c_void_p]
+        fn.restype = C.c_int
+    lib.qnmfit_launch_count.argtypes = [C.c_void_p]
+    lib.qnmfit_launch_count.restype = C.c_int64
+    lib.qnmfit_plan_batch.argtypes = [C.c_void_p, C.POINTER(Batch), C.POINTER(Plan)]
+    lib.qnmfit_plan_batch.restype = C.c_int
+    lib.qnmfit_fp64_peak.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    lib.qnmfit_fp64_peak.restype = C.c_int
+    lib.qnmfit_flops_per_fit.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.qnmfit_flops_per_fit.restype = C.c_double
+    if lib.qnmfit_abi_version() != ABI_VERSION:
+        raise ImportError(
+            f"{path}: ABI version {lib.qnmfit_abi_version()} != binding {ABI_VERSION}; rebuild")
+    if path == LIB_PATH:
+        _lib = lib
+    return lib
+
+
+class Context:
+    """Owns one ``qnmfit_ctx`` (one CUDA device).  Not thread-safe, like the reference."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        handle = C.c_void_p()
+        rc = self.lib.qnmfit_create(int(device), C.byref(handle))
+        if rc != 0:
+            raise QnmfitError(rc, self.lib.qnmfit_last_error(None).decode())
+        self.handle = handle
+        self.device = int(device)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise QnmfitError(rc, self.lib.qnmfit_last_error(self.handle).decode())
+
+    def fit_batch(self, batch, stream=0):
+        self._check(self.lib.qnmfit_fit_batch(self.handle, C.byref(batch), C.c_void_p(stream)))
+
+    def eval_batch(self, batch, stream=0):
+        self._check(self.lib.qnmfit_eval_batch(self.handle, C.byref(batch), C.c_void_p(stream)))
+
+    def plan(self, batch):
+        plan = Plan()
+        self._check(self.lib.qnmfit_plan_batch(self.handle, C.byref(batch), C.byref(plan)))
+        return plan
+
+    def launch_count(self):
+        return int(self.lib.qnmfit_launch_count(self.handle))
+
+    def fp64_peak(self, kind=0, iters=4096):
+        out = C.c_double()
+        self._check(self.lib.qnmfit_fp64_peak(self.handle, int(kind), int(iters), C.byref(out)))
+        return out.value
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.qnmfit_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def flops_per_fit(rows, n_modes, n_series=1):
+    """Algorithmic FP64 flops credited to one fit (same formula as the C library)."""
+    M, N = float(rows) * n_series, float(n_modes)
+    return 8 * M * N * N + 30 * M * N + 20 * M - (8.0 / 3.0) * N ** 3 - 4 * N * N

@@ -1,0 +1,476 @@
+// fit_small.cuh — K1: single-series fits with N <= 8 columns.
+//
+// Replaces, for one grid point / start time, the body of the reference's
+// ringdown_fit (qnmfits/qnmfits.py:274-293): frequencies -> design matrix ->
+// least squares -> model -> mismatch.  Nothing of the M x N design matrix ever
+// reaches HBM (or even shared memory):
+//
+//   * a fit is owned by `lpf` (lanes per fit, 1..32, power of two) adjacent lanes
+//     of one warp; lane l owns a contiguous slice of the window's rows;
+//   * each lane streams its rows four at a time through registers
+//     (B: 4 x (N+1) complex, last column = data), generating row k+1 from row k by
+//     the recurrence z <- z * exp(-i w dt) (first-order corrected for the deviation
+//     of every sample from the nominal grid) and re-anchoring with a direct
+//     exp/sincos every `anchor_rows` rows;
+//   * every 4-row block is folded into the lane's private upper-triangular factor
+//     [R | Q^H d] by N Householder reflections of the stacked matrix [R; B]
+//     (sequential TSQR).  R lives in shared memory, laid out [entry][lane] so that
+//     every access is a conflict-free LDS.128/STS.128; each entry is touched once
+//     per block;
+//   * the lpf factors of a fit are merged by a binary tree of the same Householder
+//     step (the partner's triangle plays the role of B) — the "R-combine";
+//   * lane 0 back-substitutes, then all lanes regenerate their rows once more to
+//     accumulate the three trapezoid-weighted inner products of the mismatch
+//     (qnmfits.py:90-97) and |model - data|^2; a fixed-order butterfly adds the lane
+//     partials, so results do not depend on how fits are distributed over CTAs/GPUs.
+//
+// Householder QR, not normal equations: overtone bases have cond ~ 1e5 (8 overtones)
+// and the reference solves by SVD (LAPACK zgelsd).
+#pragma once
+#include "qnmfit_common.cuh"
+
+template <int N>
+struct SmallLayout {
+    static constexpr int MB = 4;                      // rows per register block
+    static constexpr int NC = N + 1;                  // columns incl. right-hand side
+    static constexpr int NP = N * (N + 1) / 2;        // strictly-upper entries incl. rhs column
+    // index of R[j][k], j < k <= N (k == N is the rhs column)
+    QF_MEMBOTH static constexpr int pair(int j, int k) { return j * N - j * (j - 1) / 2 + (k - j - 1); }
+};
+
+// Views into the CTA's shared memory.
+template <int N, int THREADS>
+struct SmallSmem {
+    double2 *Ro;        // [NP][THREADS]   off-diagonal + rhs
+    double2 *om;        // [N][fpc]        frequencies of the CTA's fits
+    double2 *qq;        // [N][fpc]        exp(-i w dt)
+    double2 *qw;        // [N][fpc]        exp(-i w dt) * (-i w)
+    const double2 *ds;  // [stage_rows]    staged data window (or global data)
+    double *Rd;         // [N][THREADS]    real diagonal
+    const double *ts;   // [stage_rows]    staged times (or global times)
+    int fpc;            // fits per CTA
+    int t_off;          // subtract from a row index before indexing ts/ds
+
+    QF_MEMBOTH static size_t bytes(int fpc, int stage_rows)
+    {
+        return sizeof(double2) * (size_t)(SmallLayout<N>::NP * THREADS + 3 * N * fpc + stage_rows)
+             + sizeof(double) * (size_t)(N * THREADS + stage_rows);
+    }
+    QF_MEM void carve(void *base, int fpc_, int stage_rows)
+    {
+        fpc = fpc_;
+        double2 *p2 = (double2 *)base;
+        Ro = p2; p2 += SmallLayout<N>::NP * THREADS;
+        om = p2; p2 += N * fpc;
+        qq = p2; p2 += N * fpc;
+        qw = p2; p2 += N * fpc;
+        ds = p2; p2 += stage_rows;
+        double *p1 = (double *)p2;
+        Rd = p1; p1 += N * THREADS;
+        ts = p1;
+    }
+};
+
+// Per-lane description of its share of one fit.
+struct SmallLane {
+    int fit;        // index within the launch, -1 if the lane has no fit
+    int slot;       // fit slot within the CTA
+    int lf;         // lane index within the fit
+    int rb, re;     // window rows of the fit
+    int lo, hi;     // rows of this lane
+    int nblk;       // 4-row blocks of this lane (same for all lanes of a fit)
+    double t0;
+};
+
+QF_HD SmallLane small_lane_setup(const FitParams &p, int cta, int tid, int threads)
+{
+    SmallLane L;
+    const int lpf = p.lanes_per_fit;
+    const int fpc = threads / lpf;
+    L.slot = tid / lpf;
+    L.lf = tid % lpf;
+    int fit = cta * fpc + L.slot;
+    L.fit = fit < p.n_fits ? fit : -1;
+    L.rb = L.re = L.lo = L.hi = 0;
+    L.nblk = 0;
+    L.t0 = 0.0;
+    if (L.fit >= 0) {
+        L.rb = p.row_begin ? p.row_begin[fit] : p.row_begin_all;
+        L.re = p.row_end ? p.row_end[fit] : p.row_end_all;
+        L.t0 = p.t0 ? p.t0[fit] : p.t0_all;
+        if (L.rb < 0) L.rb = 0;
+        if (L.re > p.n_times) L.re = p.n_times;
+        if (L.re < L.rb) L.re = L.rb;
+        int M = L.re - L.rb;
+        int rpl = (M + lpf - 1) / lpf;
+        rpl = (rpl + 3) / 4 * 4;
+        L.nblk = rpl / 4;
+        L.lo = L.rb + L.lf * rpl;
+        if (L.lo > L.re) L.lo = L.re;
+        L.hi = L.lo + rpl;
+        if (L.hi > L.re) L.hi = L.re;
+    }
+    return L;
+}
+
+// Row generator state of one lane.
+template <int N>
+struct SmallGen {
+    double2 z[N];     // exp(-i w_j tau) of the row about to be emitted
+    double tau_a;     // tau of the current anchor row
+    double eps;       // deviation of the current row from the nominal grid
+    int n;            // rows since the anchor
+};
+
+// Emit 4 rows [row0, row0+4) into B (zero rows beyond the lane's range) and advance.
+template <int N, int THREADS>
+QF_HD void small_generate(const FitParams &p, const SmallSmem<N, THREADS> &sm, const SmallLane &L,
+                          SmallGen<N> &g, int blk, int ablk, double2 (&B)[4][N + 1])
+{
+    const int row0 = L.lo + blk * 4;
+    const bool direct = !(p.dt_nominal > 0.0);
+    if ((direct || blk % ablk == 0) && row0 < L.hi) {
+        g.tau_a = qf_sub_rn(sm.ts[row0 - sm.t_off], L.t0);
+#pragma unroll
+        for (int j = 0; j < N; ++j) g.z[j] = design_entry(sm.om[j * sm.fpc + L.slot], g.tau_a);
+        g.eps = 0.0;
+        g.n = 0;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = row0 + i;
+        const bool valid = r < L.hi;
+        const double2 zero = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int j = 0; j < N; ++j) B[i][j] = valid ? g.z[j] : zero;
+        B[i][N] = valid ? sm.ds[r - sm.t_off] : zero;
+        // advance to row r + 1 (clamped to the window; values past L.hi are unused)
+        int rn = r + 1;
+        if (rn > L.re - 1) rn = L.re - 1;
+        if (rn < L.rb) rn = L.rb;
+        const double tau_n = qf_sub_rn(sm.ts[rn - sm.t_off], L.t0);
+        if (direct) {
+            if (rn < L.hi && i < 3) {
+#pragma unroll
+                for (int j = 0; j < N; ++j) g.z[j] = design_entry(sm.om[j * sm.fpc + L.slot], tau_n);
+            }
+        } else {
+            g.n += 1;
+            const double eps_n = fma(-(double)g.n, p.dt_nominal, tau_n - g.tau_a);
+            const double de = eps_n - g.eps;
+            g.eps = eps_n;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const double2 q = sm.qq[j * sm.fpc + L.slot];
+                const double2 w = sm.qw[j * sm.fpc + L.slot];
+                const double2 qe = make_double2(fma(w.x, de, q.x), fma(w.y, de, q.y));
+                g.z[j] = c_mul(g.z[j], qe);
+            }
+        }
+    }
+}
+
+// Fold the 4 x (N+1) block B into the lane's factor: N Householder reflections of
+// [R; B], columns JSTART..N-1 (columns below JSTART of B must be zero).
+template <int N, int THREADS, int JSTART>
+QF_HD void small_absorb(double2 (&B)[4][N + 1], double *Rd, double2 *Ro)
+{
+    typedef SmallLayout<N> LY;
+#pragma unroll
+    for (int j = JSTART; j < N; ++j) {
+        const double r = Rd[j * THREADS];
+        double sig0 = B[0][j].x * B[0][j].x, sig1 = B[1][j].x * B[1][j].x;
+        sig0 = fma(B[0][j].y, B[0][j].y, sig0);
+        sig1 = fma(B[1][j].y, B[1][j].y, sig1);
+        sig0 = fma(B[2][j].x, B[2][j].x, sig0);
+        sig1 = fma(B[3][j].x, B[3][j].x, sig1);
+        sig0 = fma(B[2][j].y, B[2][j].y, sig0);
+        sig1 = fma(B[3][j].y, B[3][j].y, sig1);
+        const double t = fma(r, r, sig0 + sig1);
+        // norm of the stacked column; a column that is negligible down to the
+        // underflow range is left alone (H = I) and shows up as a zero pivot.
+        const bool ok = t > 1e-280;
+        const double y = qf_rsqrt(ok ? t : 1.0);
+        const double nrm = ok ? t * y : 0.0;
+        const double ar = fabs(r);
+        const double v0 = copysign(ar + nrm, r);          // v = [v0; b]
+        const double den = nrm * (ar + nrm);              // v^H v / 2
+        const double beta = ok ? qf_rcp(den) : 0.0;
+        if (ok) Rd[j * THREADS] = -copysign(nrm, r);
+#pragma unroll
+        for (int k = j + 1; k <= N; ++k) {
+            double2 Rjk = Ro[LY::pair(j, k) * THREADS];
+            // s = v^H [R_jk; B_k]
+            double sr = v0 * Rjk.x, si = v0 * Rjk.y;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                sr = fma(B[i][j].x, B[i][k].x, sr);
+                si = fma(B[i][j].x, B[i][k].y, si);
+                sr = fma(B[i][j].y, B[i][k].y, sr);
+                si = fma(-B[i][j].y, B[i][k].x, si);
+            }
+            sr *= beta;
+            si *= beta;
+            Rjk.x = fma(-v0, sr, Rjk.x);
+            Rjk.y = fma(-v0, si, Rjk.y);
+            Ro[LY::pair(j, k) * THREADS] = Rjk;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double bx = B[i][k].x, by = B[i][k].y;
+                bx = fma(-sr, B[i][j].x, bx);
+                by = fma(-sr, B[i][j].y, by);
+                bx = fma(si, B[i][j].y, bx);
+                by = fma(-si, B[i][j].x, by);
+                B[i][k].x = bx;
+                B[i][k].y = by;
+            }
+        }
+    }
+}
+
+// Zero the lane's factor.
+template <int N, int THREADS>
+QF_HD void small_clear(const SmallSmem<N, THREADS> &sm, int tid)
+{
+#pragma unroll
+    for (int j = 0; j < N; ++j) sm.Rd[j * THREADS + tid] = 0.0;
+#pragma unroll
+    for (int e = 0; e < SmallLayout<N>::NP; ++e) sm.Ro[e * THREADS + tid] = make_double2(0.0, 0.0);
+}
+
+// Leaf stage: sequential TSQR over the lane's rows.
+template <int N, int THREADS>
+QF_HD void small_leaf(const FitParams &p, const SmallSmem<N, THREADS> &sm, const SmallLane &L, int tid)
+{
+    if (L.fit < 0) return;
+    int ablk = (p.anchor_rows > 0 ? p.anchor_rows : 32) / 4;
+    if (ablk < 1) ablk = 1;
+    SmallGen<N> g;
+#pragma unroll
+    for (int j = 0; j < N; ++j) g.z[j] = make_double2(0.0, 0.0);
+    g.tau_a = 0.0; g.eps = 0.0; g.n = 0;
+    double2 B[4][N + 1];
+#pragma unroll 1
+    for (int blk = 0; blk < L.nblk; ++blk) {
+        if (L.lo + blk * 4 >= L.hi) break;
+        small_generate<N, THREADS>(p, sm, L, g, blk, ablk, B);
+        small_absorb<N, THREADS, 0>(B, sm.Rd + tid, sm.Ro + tid);
+    }
+}
+
+// One level of the R-combine: lanes with lf % (2 s) == 0 absorb the factor of lane lf + s.
+template <int N, int THREADS>
+QF_HD void small_tree_level(const FitParams &p, const SmallSmem<N, THREADS> &sm, const SmallLane &L,
+                            int tid, int s)
+{
+    typedef SmallLayout<N> LY;
+    if (L.fit < 0 || (L.lf % (2 * s)) != 0) return;
+    const int pt = tid + s;   // partner lane (same warp, same fit)
+    double2 B[4][N + 1];
+#pragma unroll 1
+    for (int b0 = 0; b0 < N; b0 += 4) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = b0 + i;
+#pragma unroll
+            for (int k = 0; k <= N; ++k) {
+                double2 v = make_double2(0.0, 0.0);
+                if (row < N) {
+                    if (k == row) v = make_double2(sm.Rd[row * THREADS + pt], 0.0);
+                    else if (k > row) v = sm.Ro[(row * N - row * (row - 1) / 2 + (k - row - 1)) * THREADS + pt];
+                }
+                B[i][k] = v;
+            }
+        }
+        small_absorb<N, THREADS, 0>(B, sm.Rd + tid, sm.Ro + tid);
+    }
+}
+
+// Back-substitution by lane 0 of the fit; leaves C in the rhs slots of lane 0.
+template <int N, int THREADS>
+QF_HD void small_backsub(const FitParams &p, const SmallSmem<N, THREADS> &sm, const SmallLane &L, int tid,
+                         int &status)
+{
+    typedef SmallLayout<N> LY;
+    if (L.fit < 0 || L.lf != 0) return;
+    const int M = L.re - L.rb;
+    double dmax = 0.0, dmin = 1e300;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        double a = fabs(sm.Rd[j * THREADS + tid]);
+        dmax = a > dmax ? a : dmax;
+        dmin = a < dmin ? a : dmin;
+    }
+    const double cut = 2.220446049250313e-16 * (double)(M > N ? M : N) * dmax;
+    if (!(dmin > cut)) status |= QNMFIT_ST_RANK_DEFICIENT_;
+    if (M <= N) status |= QNMFIT_ST_UNDERDETERMINED_;
+    if (p.R) {
+        double2 *Rout = p.R + (long long)L.fit * N * (N + 1);
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+#pragma unroll
+            for (int k = 0; k <= N; ++k) {
+                double2 v = make_double2(0.0, 0.0);
+                if (k == j) v = make_double2(sm.Rd[j * THREADS + tid], 0.0);
+                else if (k > j) v = sm.Ro[LY::pair(j, k) * THREADS + tid];
+                Rout[j * (N + 1) + k] = v;
+            }
+    }
+    double2 C[N];
+#pragma unroll
+    for (int j = N - 1; j >= 0; --j) {
+        double2 acc = sm.Ro[LY::pair(j, N) * THREADS + tid];
+#pragma unroll
+        for (int k = j + 1; k < N; ++k) {
+            const double2 Rjk = sm.Ro[LY::pair(j, k) * THREADS + tid];
+            acc.x = fma(-Rjk.x, C[k].x, acc.x);
+            acc.x = fma(Rjk.y, C[k].y, acc.x);
+            acc.y = fma(-Rjk.x, C[k].y, acc.y);
+            acc.y = fma(-Rjk.y, C[k].x, acc.y);
+        }
+        const double d = sm.Rd[j * THREADS + tid];
+        if (d != 0.0) { C[j].x = acc.x / d; C[j].y = acc.y / d; }
+        else C[j] = make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        sm.Ro[LY::pair(j, N) * THREADS + tid] = C[j];
+        if (p.C) p.C[(long long)L.fit * N + j] = C[j];
+        if (!(fabs(C[j].x) < 1e300) || !(fabs(C[j].y) < 1e300)) status |= QNMFIT_ST_NONFINITE_;
+    }
+}
+
+// Second pass: model rows and the trapezoid-weighted inner products.
+//   sums[0] = Re <model, data>_w   sums[1] = <model, model>_w
+//   sums[2] = <data, data>_w       sums[3] = sum |model - data|^2
+template <int N, int THREADS>
+QF_HD void small_eval(const FitParams &p, const SmallSmem<N, THREADS> &sm, const SmallLane &L, int tid,
+                      double (&sums)[4])
+{
+    typedef SmallLayout<N> LY;
+    sums[0] = sums[1] = sums[2] = sums[3] = 0.0;
+    if (L.fit < 0) return;
+    double2 C[N];
+    if (p.eval_only) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) C[j] = p.C[(long long)L.fit * N + j];
+    } else {
+        const int t0lane = tid - L.lf;
+#pragma unroll
+        for (int j = 0; j < N; ++j) C[j] = sm.Ro[LY::pair(j, N) * THREADS + t0lane];
+    }
+    int ablk = (p.anchor_rows > 0 ? p.anchor_rows : 32) / 4;
+    if (ablk < 1) ablk = 1;
+    SmallGen<N> g;
+#pragma unroll
+    for (int j = 0; j < N; ++j) g.z[j] = make_double2(0.0, 0.0);
+    g.tau_a = 0.0; g.eps = 0.0; g.n = 0;
+    double2 B[4][N + 1];
+#pragma unroll 1
+    for (int blk = 0; blk < L.nblk; ++blk) {
+        const int row0 = L.lo + blk * 4;
+        if (row0 >= L.hi) break;
+        small_generate<N, THREADS>(p, sm, L, g, blk, ablk, B);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = row0 + i;
+            if (r < L.hi) {
+                double mx = 0.0, my = 0.0;
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    mx = fma(B[i][j].x, C[j].x, mx);
+                    my = fma(B[i][j].x, C[j].y, my);
+                    mx = fma(-B[i][j].y, C[j].y, mx);
+                    my = fma(B[i][j].y, C[j].x, my);
+                }
+                const double dx = B[i][N].x, dy = B[i][N].y;
+                if (p.model) p.model[(long long)L.fit * p.model_stride + (r - L.rb)] = make_double2(mx, my);
+                int rm = r - 1 < L.rb ? L.rb : r - 1;
+                int rp = r + 1 > L.re - 1 ? L.re - 1 : r + 1;
+                const double w = 0.5 * (sm.ts[rp - sm.t_off] - sm.ts[rm - sm.t_off]);
+                sums[0] = fma(w, fma(mx, dx, my * dy), sums[0]);
+                sums[1] = fma(w, fma(mx, mx, my * my), sums[1]);
+                sums[2] = fma(w, fma(dx, dx, dy * dy), sums[2]);
+                const double ex = mx - dx, ey = my - dy;
+                sums[3] += fma(ex, ex, ey * ey);
+            }
+        }
+    }
+}
+
+// Lane 0 of the fit, with the fit's total sums: write the outputs.
+QF_HD void small_finalize(const FitParams &p, const SmallLane &L, const double (&sums)[4], int status)
+{
+    if (L.fit < 0 || L.lf != 0) return;
+    const double mm = 1.0 - sums[0] / sqrt(sums[1] * sums[2]);
+    p.mismatch[L.fit] = mm;
+    if (p.residual) p.residual[L.fit] = sums[3];
+    if (p.status) p.status[L.fit] = status;
+}
+
+#ifndef QNMFIT_HOSTSIM
+// ---------------------------------------------------------------------------
+// The kernel.  STAGED: the union of all windows (times + data, 24 B/row) is copied
+// into shared memory once per CTA and reused by every fit the CTA handles.
+template <int N, int THREADS, bool STAGED>
+__global__ void __launch_bounds__(THREADS, 1) fit_small_kernel(const FitParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmallSmem<N, THREADS> sm;
+    const int lpf = p.lanes_per_fit;
+    const int fpc = THREADS / lpf;
+    const int tid = threadIdx.x;
+    sm.carve(smem_raw, fpc, STAGED ? p.stage_rows : 0);
+    if (STAGED) {
+        double *ts_w = const_cast<double *>(sm.ts);
+        double2 *ds_w = const_cast<double2 *>(sm.ds);
+        for (int r = tid; r < p.stage_rows; r += THREADS) {
+            ts_w[r] = p.times[p.stage_begin + r];
+            ds_w[r] = p.data[p.stage_begin + r];
+        }
+        sm.t_off = p.stage_begin;
+    } else {
+        sm.ts = p.times;
+        sm.ds = p.data;
+        sm.t_off = 0;
+    }
+    // frequency tables of the CTA's fits
+    const int cta_first = blockIdx.x * fpc;
+    for (int idx = tid; idx < fpc * N; idx += THREADS) {
+        const int slot = idx / N, j = idx - slot * N;
+        const int fit = cta_first + slot;
+        if (fit < p.n_fits) {
+            const double2 w = fit_omega(p, fit, j);
+            sm.om[j * fpc + slot] = w;
+            if (p.dt_nominal > 0.0) {
+                const double2 q = design_entry(w, p.dt_nominal);
+                sm.qq[j * fpc + slot] = q;
+                sm.qw[j * fpc + slot] = c_mul(q, make_double2(w.y, -w.x));
+            }
+        }
+    }
+    const SmallLane L = small_lane_setup(p, blockIdx.x, tid, THREADS);
+    small_clear<N, THREADS>(sm, tid);
+    __syncthreads();
+
+    int status = 0;
+    if (!p.eval_only) {
+        small_leaf<N, THREADS>(p, sm, L, tid);
+        for (int s = 1; s < lpf; s <<= 1) {
+            __syncwarp();
+            small_tree_level<N, THREADS>(p, sm, L, tid, s);
+        }
+        __syncwarp();
+        small_backsub<N, THREADS>(p, sm, L, tid, status);
+        __syncwarp();
+    }
+    double sums[4];
+    small_eval<N, THREADS>(p, sm, L, tid, sums);
+    // fixed-order butterfly over the lanes of the fit
+    for (int s = 1; s < lpf; s <<= 1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sums[q] += __shfl_xor_sync(0xffffffffu, sums[q], s);
+    }
+    small_finalize(p, L, sums, status);
+}
+#endif  // !QNMFIT_HOSTSIM

@@ -1,0 +1,403 @@
+// qnmfit_api.cu — the C ABI of libqnmfit.so (see include/qnmfit.h).
+//
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo
+//        -Xcompiler -fPIC -shared -Iinclude -o qnmfits_b200/libqnmfit.so qnmfit_api.cu
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "qnmfit.h"
+#include "fit_small.cuh"
+#include "fit_general.cuh"
+
+#define K1_THREADS 256
+
+struct qnmfit_ctx {
+    int device;
+    int sm_count;
+    int smem_optin;          // max dynamic shared memory per block
+    long long launches;
+    char err[512];
+};
+
+static char g_create_err[512] = "";
+
+static int fail(qnmfit_ctx *ctx, int code, const char *fmt, ...)
+{
+    char *dst = ctx ? ctx->err : g_create_err;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static int cuda_fail(qnmfit_ctx *ctx, cudaError_t e, const char *what)
+{
+    return fail(ctx, (int)e, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+// ---------------------------------------------------------------------------
+// kernel tables
+
+typedef void (*small_kernel_t)(const FitParams);
+
+template <int N>
+static small_kernel_t small_kernel_for(bool staged)
+{
+    return staged ? (small_kernel_t)fit_small_kernel<N, K1_THREADS, true>
+                  : (small_kernel_t)fit_small_kernel<N, K1_THREADS, false>;
+}
+
+static small_kernel_t small_kernel(int N, bool staged)
+{
+    switch (N) {
+    case 1: return small_kernel_for<1>(staged);
+    case 2: return small_kernel_for<2>(staged);
+    case 3: return small_kernel_for<3>(staged);
+    case 4: return small_kernel_for<4>(staged);
+    case 5: return small_kernel_for<5>(staged);
+    case 6: return small_kernel_for<6>(staged);
+    case 7: return small_kernel_for<7>(staged);
+    case 8: return small_kernel_for<8>(staged);
+    }
+    return nullptr;
+}
+
+static size_t small_smem_bytes(int N, int fpc, int stage_rows)
+{
+    switch (N) {
+    case 1: return SmallSmem<1, K1_THREADS>::bytes(fpc, stage_rows);
+    case 2: return SmallSmem<2, K1_THREADS>::bytes(fpc, stage_rows);
+    case 3: return SmallSmem<3, K1_THREADS>::bytes(fpc, stage_rows);
+    case 4: return SmallSmem<4, K1_THREADS>::bytes(fpc, stage_rows);
+    case 5: return SmallSmem<5, K1_THREADS>::bytes(fpc, stage_rows);
+    case 6: return SmallSmem<6, K1_THREADS>::bytes(fpc, stage_rows);
+    case 7: return SmallSmem<7, K1_THREADS>::bytes(fpc, stage_rows);
+    case 8: return SmallSmem<8, K1_THREADS>::bytes(fpc, stage_rows);
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// context
+
+extern "C" int qnmfit_abi_version(void) { return QNMFIT_ABI_VERSION; }
+
+extern "C" int qnmfit_create(int device, qnmfit_ctx **out)
+{
+    if (!out) return fail(nullptr, QNMFIT_E_NULL, "qnmfit_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, QNMFIT_E_NOGPU, "qnmfit_create: no CUDA device (%s)",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "count = 0");
+    if (device < 0 || device >= count)
+        return fail(nullptr, QNMFIT_E_SHAPE, "qnmfit_create: device %d out of range [0, %d)", device, count);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        return fail(nullptr, QNMFIT_E_NOGPU,
+                    "qnmfit_create: device %d is sm_%d%d; this library contains sm_100a code only",
+                    device, prop.major, prop.minor);
+    qnmfit_ctx *ctx = new qnmfit_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    ctx->launches = 0;
+    ctx->err[0] = 0;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaSetDevice"); delete ctx; return r; }
+    // opt every kernel in to the full shared-memory carve-out once
+    for (int N = 1; N <= QNMFIT_MAX_MODES_SMALL; ++N)
+        for (int st = 0; st < 2; ++st) {
+            e = cudaFuncSetAttribute((const void *)small_kernel(N, st != 0),
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+            if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaFuncSetAttribute(K1)"); delete ctx; return r; }
+        }
+    e = cudaFuncSetAttribute((const void *)fit_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             ctx->smem_optin);
+    if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaFuncSetAttribute(K2)"); delete ctx; return r; }
+    *out = ctx;
+    return 0;
+}
+
+extern "C" int qnmfit_destroy(qnmfit_ctx *ctx)
+{
+    delete ctx;
+    return 0;
+}
+
+extern "C" const char *qnmfit_last_error(const qnmfit_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
+
+extern "C" int64_t qnmfit_launch_count(const qnmfit_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" double qnmfit_flops_per_fit(int rows, int n_modes, int n_series)
+{
+    const double M = (double)rows * (double)n_series, N = (double)n_modes;
+    return 8.0 * M * N * N + 30.0 * M * N + 20.0 * M - (8.0 / 3.0) * N * N * N - 4.0 * N * N;
+}
+
+// ---------------------------------------------------------------------------
+// planning
+
+struct Plan {
+    int kernel;
+    int lpf;
+    int grid, block;
+    size_t smem;
+    bool staged;
+    int stage_begin, stage_rows;
+    int TR, TK;
+};
+
+static int validate(qnmfit_ctx *ctx, const qnmfit_batch *b, bool eval)
+{
+    if (!ctx) return QNMFIT_E_NULL;
+    if (!b) return fail(ctx, QNMFIT_E_NULL, "batch is NULL");
+    if (b->struct_size != (int32_t)sizeof(qnmfit_batch))
+        return fail(ctx, QNMFIT_E_ABI, "struct_size %d != sizeof(qnmfit_batch) %d (ABI %d)", b->struct_size,
+                    (int)sizeof(qnmfit_batch), QNMFIT_ABI_VERSION);
+    if (b->n_fits < 0 || b->n_modes < 1 || b->n_modes > QNMFIT_MAX_MODES || b->n_series < 1 || b->n_times < 1)
+        return fail(ctx, QNMFIT_E_SHAPE, "bad sizes: n_fits=%d n_modes=%d (1..%d) n_series=%d n_times=%d",
+                    b->n_fits, b->n_modes, QNMFIT_MAX_MODES, b->n_series, b->n_times);
+    if (b->n_series > 1 && b->series_stride < b->n_times)
+        return fail(ctx, QNMFIT_E_SHAPE, "series_stride %lld < n_times %d", (long long)b->series_stride, b->n_times);
+    if (!b->times || !b->data || !b->mismatch) return fail(ctx, QNMFIT_E_NULL, "times, data and mismatch are required");
+    if (eval && !b->C) return fail(ctx, QNMFIT_E_NULL, "qnmfit_eval_batch needs C");
+    if (!b->omega) {
+        if (!b->omega_tilde || !b->mode_ptr || !b->inv_Mf)
+            return fail(ctx, QNMFIT_E_NULL, "give omega, or omega_tilde + mode_ptr + inv_Mf");
+        if (b->n_chi < 1 || b->n_mf < 1 || b->n_constituents < b->n_modes)
+            return fail(ctx, QNMFIT_E_SHAPE, "bad table sizes: n_chi=%d n_mf=%d n_constituents=%d", b->n_chi, b->n_mf,
+                        b->n_constituents);
+        if ((!b->chi_index || !b->mf_index)
+            && b->first_fit + b->n_fits > (int64_t)b->n_chi * b->n_mf)
+            return fail(ctx, QNMFIT_E_SHAPE, "implicit grid indexing: first_fit + n_fits = %lld exceeds n_mf*n_chi = %lld",
+                        (long long)(b->first_fit + b->n_fits), (long long)b->n_chi * b->n_mf);
+    }
+    if (b->model && b->model_stride < (int64_t)b->n_series * (b->row_end_all - b->row_begin_all))
+        return fail(ctx, QNMFIT_E_SHAPE, "model_stride %lld too small for n_series * longest window", (long long)b->model_stride);
+    if (b->coef && b->n_coef < 1) return fail(ctx, QNMFIT_E_SHAPE, "coef given but n_coef = %d", b->n_coef);
+    if (b->row_begin_all < 0 || b->row_end_all > b->n_times || b->row_end_all <= b->row_begin_all)
+        return fail(ctx, QNMFIT_E_WINDOW,
+                    "window [%d, %d) (shared window, or union of the per-fit windows) is empty or outside [0, %d)",
+                    b->row_begin_all, b->row_end_all, b->n_times);
+    if ((b->row_begin == nullptr) != (b->row_end == nullptr))
+        return fail(ctx, QNMFIT_E_NULL, "row_begin and row_end must both be given or both be NULL");
+    if (b->anchor_rows < 0 || (b->anchor_rows % 4) != 0)
+        return fail(ctx, QNMFIT_E_SHAPE, "anchor_rows %d must be a non-negative multiple of 4", b->anchor_rows);
+    if (!(b->dt_nominal >= 0.0)) return fail(ctx, QNMFIT_E_SHAPE, "dt_nominal must be >= 0");
+    return 0;
+}
+
+static int ilog2(int v) { int l = 0; while ((1 << (l + 1)) <= v) ++l; return l; }
+
+static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
+{
+    memset(pl, 0, sizeof(*pl));
+    int kernel = b->kernel;
+    const bool small_ok = b->n_series == 1 && b->n_modes <= QNMFIT_MAX_MODES_SMALL && !b->coef;
+    if (kernel == QNMFIT_KERNEL_AUTO) kernel = small_ok ? QNMFIT_KERNEL_SMALL : QNMFIT_KERNEL_GENERAL;
+    if (kernel == QNMFIT_KERNEL_SMALL && !small_ok)
+        return fail(ctx, QNMFIT_E_SHAPE, "K1 needs n_series == 1, n_modes <= %d and no coef table",
+                    QNMFIT_MAX_MODES_SMALL);
+    if (kernel != QNMFIT_KERNEL_SMALL && kernel != QNMFIT_KERNEL_GENERAL)
+        return fail(ctx, QNMFIT_E_SHAPE, "unknown kernel id %d", b->kernel);
+    pl->kernel = kernel;
+    const int N = b->n_modes;
+    const int Mmax = b->row_end_all - b->row_begin_all;   // longest possible window
+    if (kernel == QNMFIT_KERNEL_SMALL) {
+        const int stage_rows = Mmax;
+        double best = 1e300;
+        for (int lpf = 1; lpf <= 32; lpf *= 2) {
+            const int fpc = K1_THREADS / lpf;
+            size_t smem = small_smem_bytes(N, fpc, stage_rows);
+            bool staged = true;
+            if (smem > (size_t)ctx->smem_optin) { staged = false; smem = small_smem_bytes(N, fpc, 0); }
+            if (smem > (size_t)ctx->smem_optin) continue;
+            const int ctas = (b->n_fits + fpc - 1) / fpc;
+            const int waves = (ctas + ctx->sm_count - 1) / ctx->sm_count;
+            const int rpl = ((Mmax + lpf - 1) / lpf + 3) / 4;
+            const double blocks = rpl * (1.0 + 0.2) /* second pass ~ 20% of a first-pass block */
+                                + ilog2(lpf) * ((N + 3) / 4);
+            const double cost = (double)(waves > 0 ? waves : 1) * blocks * (staged ? 1.0 : 1.03);
+            if (cost < best) {
+                best = cost;
+                pl->lpf = lpf; pl->grid = ctas; pl->block = K1_THREADS; pl->smem = smem; pl->staged = staged;
+                pl->stage_begin = b->row_begin_all; pl->stage_rows = staged ? stage_rows : 0;
+            }
+        }
+        if (best >= 1e300) return fail(ctx, QNMFIT_E_SHAPE, "K1: no lanes-per-fit choice fits shared memory");
+    } else {
+        const int L = b->n_series;
+        int TR = 128;
+        while (TR >= 32) {
+            if (TR >= L) {
+                const int TK = TR / L > 0 ? TR / L : 1;
+                size_t smem = GeneralSmem::bytes(N, L, TR, TK);
+                if (smem <= (size_t)ctx->smem_optin) {
+                    pl->TR = TR; pl->TK = TK; pl->smem = smem;
+                    break;
+                }
+            }
+            TR /= 2;
+        }
+        if (pl->TR == 0)
+            return fail(ctx, QNMFIT_E_SHAPE, "K2: n_modes=%d with n_series=%d does not fit shared memory", N, L);
+        pl->grid = b->n_fits; pl->block = K2_THREADS; pl->lpf = K2_THREADS;
+    }
+    return 0;
+}
+
+static void fill_params(const qnmfit_batch *b, const Plan &pl, bool eval, FitParams *p)
+{
+    memset(p, 0, sizeof(*p));
+    p->n_fits = b->n_fits; p->n_modes = b->n_modes; p->n_series = b->n_series; p->n_times = b->n_times;
+    p->series_stride = b->series_stride; p->first_fit = b->first_fit;
+    p->times = b->times; p->data = (const double2 *)b->data;
+    p->row_begin = b->row_begin; p->row_end = b->row_end; p->t0 = b->t0;
+    p->row_begin_all = b->row_begin_all; p->row_end_all = b->row_end_all; p->t0_all = b->t0_all;
+    p->omega = (const double2 *)b->omega; p->omega_tilde = b->omega_tilde; p->mode_ptr = b->mode_ptr;
+    p->inv_Mf = b->inv_Mf; p->delta_factor = b->delta_factor; p->chi_index = b->chi_index;
+    p->mf_index = b->mf_index; p->n_chi = b->n_chi > 0 ? b->n_chi : 1; p->n_mf = b->n_mf;
+    p->n_constituents = b->n_constituents;
+    p->coef = (const double2 *)b->coef; p->coef_index = b->coef_index; p->n_coef = b->n_coef;
+    p->anchor_rows = b->anchor_rows > 0 ? b->anchor_rows : 32;
+    p->dt_nominal = b->dt_nominal;
+    p->C = (double2 *)b->C; p->mismatch = b->mismatch; p->residual = b->residual;
+    p->R = (double2 *)b->R; p->status = b->status;
+    p->model = (double2 *)b->model; p->model_stride = b->model_stride; p->omega_shared = b->omega_shared;
+    p->lanes_per_fit = pl.lpf; p->eval_only = eval ? 1 : 0;
+    p->stage_begin = pl.stage_begin; p->stage_rows = pl.stage_rows;
+}
+
+static int launch(qnmfit_ctx *ctx, const qnmfit_batch *b, void *stream, bool eval)
+{
+    int rc = validate(ctx, b, eval);
+    if (rc) return rc;
+    if (b->n_fits == 0) return 0;
+    Plan pl;
+    if ((rc = make_plan(ctx, b, &pl))) return rc;
+    FitParams p;
+    fill_params(b, pl, eval, &p);
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pl.kernel == QNMFIT_KERNEL_SMALL) {
+        small_kernel_t k = small_kernel(b->n_modes, pl.staged);
+        k<<<pl.grid, pl.block, pl.smem, st>>>(p);
+    } else {
+        fit_general_kernel<<<pl.grid, pl.block, pl.smem, st>>>(p, pl.TR, pl.TK);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "kernel launch");
+    ctx->launches += 1;
+    return 0;
+}
+
+extern "C" int qnmfit_fit_batch(qnmfit_ctx *ctx, const qnmfit_batch *b, void *stream)
+{
+    return launch(ctx, b, stream, false);
+}
+
+extern "C" int qnmfit_eval_batch(qnmfit_ctx *ctx, const qnmfit_batch *b, void *stream)
+{
+    return launch(ctx, b, stream, true);
+}
+
+extern "C" int qnmfit_plan_batch(qnmfit_ctx *ctx, const qnmfit_batch *b, qnmfit_plan *out)
+{
+    if (!out) return fail(ctx, QNMFIT_E_NULL, "plan is NULL");
+    int rc = validate(ctx, b, false);
+    if (rc) return rc;
+    Plan pl;
+    if ((rc = make_plan(ctx, b, &pl))) return rc;
+    memset(out, 0, sizeof(*out));
+    out->kernel = pl.kernel; out->lanes_per_fit = pl.lpf; out->grid = pl.grid; out->block = pl.block;
+    out->smem_bytes = (int32_t)pl.smem; out->staged = pl.staged ? 1 : 0;
+    cudaFuncAttributes fa;
+    const void *fn = pl.kernel == QNMFIT_KERNEL_SMALL ? (const void *)small_kernel(b->n_modes, pl.staged)
+                                                      : (const void *)fit_general_kernel;
+    cudaError_t e = cudaFuncGetAttributes(&fa, fn);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaFuncGetAttributes");
+    out->regs_per_thread = fa.numRegs;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// FP64 peak micro-benchmarks (the roofline denominator; MEASURED_PEAKS.json has no
+// FP64 entry).  Eight independent dependent-FMA chains per thread / four MMA
+// accumulators per warp; results are stored so nothing is optimised away.
+
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double b, double c)
+{
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+           a6 = a0 + 6, a7 = a0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+            a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double *out, int iters, double b, double c)
+{
+    double a = threadIdx.x * 1e-3 + 0.5, bb = b;
+    double c00 = c, c01 = c, c10 = c + 1, c11 = c + 1, c20 = c + 2, c21 = c + 2, c30 = c + 3, c31 = c + 3;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c00), "+d"(c01) : "d"(a), "d"(bb));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c10), "+d"(c11) : "d"(a), "d"(bb));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c20), "+d"(c21) : "d"(a), "d"(bb));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c30), "+d"(c31) : "d"(a), "d"(bb));
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((c00 + c01) + (c10 + c11)) + ((c20 + c21) + (c30 + c31));
+}
+
+extern "C" int qnmfit_fp64_peak(qnmfit_ctx *ctx, int kind, int iters, double *tflops)
+{
+    if (!ctx || !tflops) return fail(ctx, QNMFIT_E_NULL, "qnmfit_fp64_peak: NULL argument");
+    if (iters < 1) iters = 1;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
+    const int block = 256, grid = ctx->sm_count * 8;
+    double *out = nullptr;
+    if ((e = cudaMalloc(&out, sizeof(double) * (size_t)grid * block)) != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc");
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {   // first reps warm up; best of the rest
+        cudaEventRecord(ev0, 0);
+        if (kind == 0) dfma_peak_kernel<<<grid, block>>>(out, iters, 0.999999, 1e-9);
+        else dmma_peak_kernel<<<grid, block>>>(out, iters, 0.999999, 1e-9);
+        cudaEventRecord(ev1, 0);
+        e = cudaEventSynchronize(ev1);
+        if (e != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        if (rep >= 2 && ms < best_ms) best_ms = ms;
+        ctx->launches += 1;
+    }
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    cudaFree(out);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "fp64 peak kernel");
+    double flops;
+    if (kind == 0) flops = 2.0 * 64.0 * (double)iters * (double)grid * block;            // 8 chains x 8 unroll
+    else flops = 2.0 * 256.0 * 32.0 * (double)iters * (double)grid * (block / 32);        // 32 MMAs x 256 FMA
+    *tflops = flops / (best_ms * 1e-3) * 1e-12;
+    return 0;
+}

@@ -1,0 +1,227 @@
+"""
+QNM table provider — host side of the drop-in boundary.
+
+Mirrors the interface of the reference's ``qnmfits.qnm.qnm`` class (reference
+``qnmfits/qnm.py:36-393``): ``omega``, ``omega_list``, ``mu``, ``mu_list`` with the
+same argument order, label conventions and return types.  Tabulation stays on the
+host (as BASELINE.json's north_star asks): cubic interpolating splines in spin built
+by the same SciPy call the reference makes, so label -> value resolution is
+bit-identical; what this module adds is the *factored, vectorised* form the device
+kernels consume (``constituent_table``): the spline values for the few unique spins
+of a sweep instead of one Python call per grid point.
+
+Label semantics kept from the reference:
+
+* ``(ell, m, n, sign)``; ``sign=-1`` selects the mirror mode: the sequence loaded is
+  ``(ell, -m, n)`` and the value is ``-conj(omega)`` (reference qnm.py:220,232-233).
+* a mode tuple of length 4p is a p-th order (quadratic, cubic, ...) QNM whose
+  frequency is the Python ``sum`` of its constituents, each already divided by
+  ``Mf`` (reference qnm.py:235,272-280).
+* ``mu`` is the int ``0`` when ``m' != m`` — tested *before* the mirror sign flip
+  (reference qnm.py:336-341); the ell column is ``ell - max(|m|, |s|)`` evaluated
+  after the flip (reference qnm.py:345-348); mirror value
+  ``(-1)**(ell+ell') * conj(mu)`` (reference qnm.py:358-359).
+* overtone re-indexing around the Cook-Zalutskiy multiplets: for (2,0), (2,1),
+  (2,2) a request ``n > 9`` loads sequence ``n - 1`` (reference qnm.py:128-134);
+  the n = 8, 9 multiplet members themselves come from ``KerrQNM_08.h5`` /
+  ``KerrQNM_09.h5`` when present (reference qnm.py:60-122).
+"""
+from pathlib import Path
+
+import numpy as np
+from scipy.interpolate import UnivariateSpline
+
+_table_provider = None
+
+
+def set_table_provider(modes_cache):
+    """Install the callable used in place of ``qnm.modes_cache(s, l, m, n)``.
+
+    ``modes_cache`` must return an object with ``.a``, ``.omega`` and ``.C`` (see
+    reference qnmfits/qnm.py:134-141).  Passing ``None`` restores the default (the
+    ``qnm`` PyPI package).  Existing ``qnm`` instances drop their spline caches.
+    """
+    global _table_provider
+    _table_provider = modes_cache
+    for inst in list(qnm._instances):
+        inst._reset_sequences()
+
+
+def _default_provider():
+    if _table_provider is not None:
+        return _table_provider
+    try:
+        import qnm as qnm_loader  # the PyPI package (Stein 2019)
+    except ImportError as exc:  # pragma: no cover - depends on environment
+        raise ImportError(
+            "The 'qnm' package (Kerr QNM tables) is not installed. Install it, or "
+            "call qnmfits_b200.set_table_provider(modes_cache) with a callable "
+            "returning objects with .a, .omega, .C (e.g. "
+            "qnmfits_b200.synthetic.modes_cache for benchmarks)."
+        ) from exc
+    return qnm_loader.modes_cache
+
+
+def _spline_pair(x, values):
+    """Interpolating cubic splines for real and imaginary part (qnm.py:144-155)."""
+    return (UnivariateSpline(x, np.real(values), s=0),
+            UnivariateSpline(x, np.imag(values), s=0))
+
+
+class qnm:
+    """Frequencies and spherical-spheroidal mixing coefficients of Kerr QNMs."""
+
+    _instances = []
+
+    #: multiplets that the Leaver solver of the ``qnm`` package cannot follow
+    #: (reference qnm.py:67), as (ell, m, n, s)
+    multiplet_list = [(2, 0, 8, -2), (2, 1, 8, -2), (2, 2, 8, -2)]
+
+    def __init__(self, data_dir=None):
+        self._qnm_funcs = {}
+        self._interpolated_qnm_funcs = {}
+        self.download_check = {}
+        self._data_dir = Path(data_dir) if data_dir is not None \
+            else Path(__file__).parent / 'Data'
+        self._load_cook_multiplets()
+        qnm._instances.append(self)
+
+    # ------------------------------------------------------------------ tables
+
+    def _reset_sequences(self):
+        self._interpolated_qnm_funcs = {}
+        self._load_cook_multiplets()
+
+    def _load_cook_multiplets(self):
+        """Cook & Zalutskiy n=8,9 multiplet data, if the HDF5 files are present.
+
+        Dataset path ``n08/m+02/{2,2,{8,0}}``; columns
+        ``[chi, Re w, Im w, Re A, Im A, Re mu_0, Im mu_0, ...]`` (reference
+        qnm.py:79-98).
+        """
+        for ell, m, n, s in self.multiplet_list:
+            path = self._data_dir / f'KerrQNM_{n:02}.h5'
+            self.download_check[n] = path.exists()
+            if not self.download_check[n]:
+                continue
+            import h5py
+            with h5py.File(path, 'r') as f:
+                for i in (0, 1):
+                    name = f'n{n:02}/m{m:+03}/{{{ell},{m},{{{n},{i}}}}}'
+                    table = np.array(f[name])
+                    spins = table[:, 0]
+                    w = _spline_pair(spins, table[:, 1] + 1j * table[:, 2])
+                    mus = [
+                        _spline_pair(spins, re + 1j * im)
+                        for re, im in zip(table[:, 5::2].T, table[:, 6::2].T)
+                    ]
+                    self._interpolated_qnm_funcs[(ell, m, n + i, s)] = [w, mus]
+
+    def _interpolate(self, ell, m, n, s=-2):
+        n_load = n
+        for ellp, mp, nprime, sp in self.multiplet_list:
+            if (ell == ellp) and (m == mp) and (n > nprime + 1):
+                n_load -= 1
+        seq = _default_provider()(s, ell, m, n_load)
+        spins = seq.a
+        w = _spline_pair(spins, seq.omega)
+        mus = [_spline_pair(spins, col) for col in np.asarray(seq.C).T]
+        self._interpolated_qnm_funcs[ell, m, n, s] = [w, mus]
+
+    def _funcs(self, ell, m, n, s):
+        key = (ell, m, n, s)
+        if key not in self._interpolated_qnm_funcs:
+            self._interpolate(ell, m, n, s)
+        return self._interpolated_qnm_funcs[key]
+
+    # ----------------------------------------------------------- reference API
+
+    def omega(self, ell, m, n, sign, chif, Mf=1, s=-2):
+        """Complex frequency omega_{ell m n}(Mf, chif) (reference qnm.py:162-235)."""
+        m = m * sign
+        re_f, im_f = self._funcs(ell, m, n, s)[0]
+        omega = re_f(chif) + 1j * im_f(chif)
+        if sign == -1:
+            omega = -np.conjugate(omega)
+        return omega / Mf
+
+    def omega_list(self, modes, chif, Mf=1, s=-2):
+        """List of mode frequencies; 4p-tuples sum p constituents (qnm.py:237-280)."""
+        out = []
+        for mode in modes:
+            parts = [
+                self.omega(*mode[i:i + 4], chif, Mf, s)
+                for i in range(0, len(mode), 4)
+            ]
+            out.append(sum(parts))
+        return out
+
+    def mu(self, ell, m, ellp, mp, nprime, sign, chif, s=-2):
+        """Spherical-spheroidal mixing coefficient (reference qnm.py:293-361)."""
+        if mp != m:
+            return 0
+        m = m * sign
+        mp = mp * sign
+        index = ell - max(abs(m), abs(s))
+        re_f, im_f = self._funcs(ellp, mp, nprime, s)[1][index]
+        mu = re_f(chif) + 1j * im_f(chif)
+        if sign == -1:
+            mu = (-1) ** (ell + ellp) * np.conjugate(mu)
+        return mu
+
+    def mu_list(self, indices, chif, s=-2):
+        """Mixing coefficients for (ell, m, ell', m', n', sign) tuples (qnm.py:363-393)."""
+        return [
+            self.mu(ell, m, ellp, mp, nprime, sign, chif, s)
+            for ell, m, ellp, mp, nprime, sign in indices
+        ]
+
+    # ------------------------------------------------- factored device tables
+
+    def constituent_table(self, modes, chif_values, s=-2):
+        """Mf-independent frequency table for a sweep over spins.
+
+        Returns ``(table, mode_ptr)``: ``table`` is complex128 of shape
+        ``(len(chif_values), P)`` holding, for every unique spin, the mirror-resolved
+        dimensionless frequency of each of the ``P`` constituents of ``modes`` (a
+        linear mode has one, a quadratic mode two, ...); ``mode_ptr`` is int32 of
+        length ``len(modes)+1`` with the constituent range of each mode.  The device
+        forms ``omega_j = delta_factor_j * sum_p(table[c, p] * (1/Mf))`` with the
+        rounding order of the reference (qnm.py:235 then the Python ``sum`` of
+        qnm.py:272-280 then qnmfits.py:274), so the per-point frequencies match it
+        bit for bit.
+        """
+        chif_values = np.atleast_1d(np.asarray(chif_values, dtype=float))
+        cols = []
+        mode_ptr = [0]
+        for mode in modes:
+            if len(mode) == 0 or len(mode) % 4 != 0:
+                raise ValueError(
+                    f"mode label {mode!r} must have a multiple of 4 entries")
+            for i in range(0, len(mode), 4):
+                ell, m, n, sign = mode[i:i + 4]
+                cols.append(np.asarray(
+                    self.omega(ell, m, n, sign, chif_values, 1.0, s),
+                    dtype=complex))
+            mode_ptr.append(len(cols))
+        table = np.ascontiguousarray(np.stack(cols, axis=1)) if cols else \
+            np.zeros((len(chif_values), 0), dtype=complex)
+        return table, np.asarray(mode_ptr, dtype=np.int32)
+
+    def mu_table(self, spherical_modes, modes, chif_values, s=-2):
+        """Mixing coefficients mu[c, i, j] for spins c, spherical modes i, QNMs j.
+
+        Entry rules follow ``mu`` exactly (int 0 -> 0+0j).  Only 4-tuples are valid
+        here: the reference raises for nonlinear labels in the multimode fit
+        (qnm.py:390 unpacks six indices); see ``multimode_ringdown_fit`` for the
+        documented superset.
+        """
+        chif_values = np.atleast_1d(np.asarray(chif_values, dtype=float))
+        out = np.zeros((len(chif_values), len(spherical_modes), len(modes)),
+                       dtype=complex)
+        for i, (ell, m) in enumerate(spherical_modes):
+            for j, mode in enumerate(modes):
+                ellp, mp, nprime, sign = mode
+                out[:, i, j] = self.mu(ell, m, ellp, mp, nprime, sign,
+                                       chif_values, s)
+        return out

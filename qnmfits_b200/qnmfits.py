@@ -1,0 +1,564 @@
+"""
+Public fitting API — drop-in for the hot path of the reference's
+``qnmfits/qnmfits.py``: ``ringdown``, ``mismatch``, ``multimode_mismatch``,
+``ringdown_fit``, ``multimode_ringdown_fit``, ``mismatch_t0_array``,
+``mismatch_M_chi_grid`` keep their names, positional order, defaults, label
+conventions and return types (reference qnmfits/qnmfits.py:15,73,100,142,478,1183,
+1304).  ``calculate_mismatch`` is named by BASELINE.json but does not exist in the
+reference; it is provided as an alias that dispatches on dict vs array.
+
+Host Python does exactly the discrete work of the reference — window selection with
+the same numpy expressions, label -> table resolution through the provider, result
+dict assembly — and hands the arithmetic (design matrix, least squares, model,
+mismatch) to the sm_100a kernels of ``libqnmfit.so`` through ``_cabi``.  There is no
+CPU implementation of that arithmetic in this package.
+
+Deliberate supersets of the reference (documented in DESIGN.md):
+
+* an invalid ``t0_method`` or ``delta`` raises ``ValueError`` up front (the reference
+  prints and then dies with ``UnboundLocalError``, qnmfits.py:246-248,270-271);
+* Python ints are accepted for ``Mf`` / ``chif`` in ``mismatch_t0_array`` (the
+  reference routes them to the dynamic branch and raises, qnmfits.py:1268);
+* time-dependent ``Mf`` / ``chif`` arrays (the dynamic-spectrum fits,
+  qnmfits.py:318-475,676-911) are not part of this hot path: NotImplementedError.
+"""
+import numpy as np
+
+from . import _cabi, _dist
+from ._engine import get_engine, nominal_step
+from .qnm import qnm as _qnm_class
+
+# Module-level provider *instance* that shadows the class, exactly like the
+# reference (qnmfits/qnmfits.py:11-12): ``qnmfits.qnm.omega_list(...)`` is an
+# instance call in user code.
+qnm = _qnm_class()
+
+_EPS = float(np.finfo(np.float64).eps)
+
+
+# --------------------------------------------------------------------------
+# host utilities (not on the device path)
+
+def ringdown(time, start_time, complex_amplitudes, frequencies):
+    """Sum of damped sinusoids, zero before ``start_time`` (reference qnmfits.py:15-70).
+
+    Model evaluator used to make injections and plots; O(K N) host numpy, not part
+    of the fitting path.
+    """
+    time = np.asarray(time)
+    h = np.zeros(len(time), dtype=complex)
+    keep = time >= start_time
+    tau = (time - start_time)[keep]
+    h[keep] = np.sum([
+        complex_amplitudes[n] * np.exp(-1j * frequencies[n] * tau)
+        for n in range(len(frequencies))], axis=0)
+    return h
+
+
+def mismatch(times, wf_1, wf_2):
+    """Mismatch of two complex series with trapezoid weights (reference qnmfits.py:73-97).
+
+    Stand-alone utility for arbitrary user waveforms (three O(K) sums on the host).
+    The fit functions do not call it: their mismatch is fused into the kernels.
+    """
+    num = np.real(np.trapezoid(wf_1 * np.conjugate(wf_2), x=times))
+    den = np.sqrt(np.trapezoid(np.real(wf_1 * np.conjugate(wf_1)), x=times)
+                  * np.trapezoid(np.real(wf_2 * np.conjugate(wf_2)), x=times))
+    return 1 - (num / den)
+
+
+def multimode_mismatch(times, wf_dict_1, wf_dict_2):
+    """Sky-averaged mismatch over the keys of the first dict (reference qnmfits.py:100-139)."""
+    keys = list(wf_dict_1.keys())
+    num = np.real(sum([
+        np.trapezoid(wf_dict_1[k] * np.conjugate(wf_dict_2[k]), x=times) for k in keys]))
+    n1 = sum([np.trapezoid(np.real(wf_dict_1[k] * np.conjugate(wf_dict_1[k])), x=times)
+              for k in keys])
+    n2 = sum([np.trapezoid(np.real(wf_dict_2[k] * np.conjugate(wf_dict_2[k])), x=times)
+              for k in keys])
+    return 1 - (num / np.sqrt(n1 * n2))
+
+
+def calculate_mismatch(times, wf_1, wf_2):
+    """Alias named in BASELINE.json; the reference has ``mismatch`` / ``multimode_mismatch``."""
+    if isinstance(wf_1, dict):
+        return multimode_mismatch(times, wf_1, wf_2)
+    return mismatch(times, wf_1, wf_2)
+
+
+# --------------------------------------------------------------------------
+# discrete host logic shared by the fit functions
+
+def _window(times, t0, T, t0_method):
+    """Selection of the analysis window — the reference's own expressions
+    (qnmfits.py:231-244), so the retained rows are bit-exact."""
+    if t0_method == 'geq':
+        return (times >= t0) & (times < t0 + T)
+    if t0_method == 'closest':
+        start_index = np.argmin((times - t0) ** 2)
+        end_index = np.argmin((times - t0 - T) ** 2)
+        return slice(start_index, end_index)
+    raise ValueError(
+        "Requested t0_method is not valid. Please choose between 'geq' and 'closest'")
+
+
+def _window_rows(times, t0, T, t0_method):
+    """[begin, end) row range of the window for ascending ``times``.
+
+    'geq': the mask ``(times >= t0) & (times < t0 + T)`` of an ascending array is the
+    contiguous range between two left bisections; 'closest': the reference's argmin
+    slice (an empty slice when end <= start).
+    """
+    if t0_method == 'geq':
+        begin = int(np.searchsorted(times, t0, side='left'))
+        end = int(np.searchsorted(times, t0 + T, side='left'))
+        return begin, max(end, begin)
+    if t0_method == 'closest':
+        begin = int(np.argmin((times - t0) ** 2))
+        end = int(np.argmin((times - t0 - T) ** 2))
+        return begin, max(end, begin)
+    raise ValueError(
+        "Requested t0_method is not valid. Please choose between 'geq' and 'closest'")
+
+
+def _delta_factor(delta, n_modes):
+    """``delta + 1`` with the reference's accepted input forms (qnmfits.py:256-271)."""
+    if type(delta) is int:
+        delta = float(delta)
+    if type(delta) is list and len(delta) == n_modes:
+        delta = np.array(delta)
+    if (isinstance(delta, np.ndarray) and len(delta) == n_modes) or type(delta) is float \
+            or isinstance(delta, np.floating):
+        return delta + 1
+    raise ValueError("delta must be a float or an array with length len(modes)")
+
+
+def _is_scalar(x):
+    return isinstance(x, (int, float, np.integer, np.floating)) and not isinstance(x, bool)
+
+
+def _check_modes(modes):
+    for mode in modes:
+        if len(mode) == 0 or len(mode) % 4 != 0:
+            raise ValueError(f"mode label {mode!r} must have a multiple of 4 entries")
+
+
+def _rank_and_singular_values(R, M):
+    """numpy.linalg.lstsq's ``rank`` and ``s`` from the device's triangular factor.
+
+    A = Q R with orthonormal Q, so the singular values of the M x N design matrix are
+    those of the N x N factor.  ``rcond=None`` means cutoff ``eps * max(M, N)`` relative
+    to the largest singular value (numpy/linalg/_linalg.py:2553-2554).
+    """
+    N = R.shape[0]
+    s = np.linalg.svd(R[:, :N], compute_uv=False)
+    cutoff = _EPS * max(M, N) * (s[0] if s.size else 0.0)
+    rank = np.int32(np.count_nonzero(s > cutoff))
+    return rank, s
+
+
+def _minimum_norm_from_factor(R, M):
+    """Amplitudes numpy.linalg.lstsq would return when it truncates singular values.
+
+    min ||A x - d|| = min ||R x - Q^H d||; the truncated-SVD minimum-norm solution of
+    the small N x N system equals that of the M x N one.  Host post-processing of the
+    device factor for the rare rank-deficient fit (e.g. duplicated overtone labels);
+    the model and mismatch are then evaluated on the device with these amplitudes.
+    """
+    N = R.shape[0]
+    U, s, Vh = np.linalg.svd(R[:, :N])
+    cutoff = _EPS * max(M, N) * (s[0] if s.size else 0.0)
+    keep = s > cutoff
+    c = U.conj().T @ R[:, N]
+    return Vh.conj().T[:, keep] @ (c[keep] / s[keep])
+
+
+def _single_fit_on_device(times_m, data_rows, frequencies, t0, coef):
+    """One fit on the device: ``data_rows`` is (L, K) — the masked series.
+
+    Returns dict with C, mismatch, residual, model (L, K), rank, s.
+    """
+    import torch
+    eng = get_engine()
+    L, K = data_rows.shape
+    N = len(frequencies)
+    if N > _cabi.MAX_MODES:
+        raise ValueError(f"at most {_cabi.MAX_MODES} modes are supported, got {N}")
+    if K < 1:
+        raise ValueError("the analysis window is empty")
+    wmax = float(np.max(np.abs(frequencies))) if N else 0.0
+    times_d = eng.to_device(times_m, np.float64)
+    data_d = eng.to_device(data_rows, np.complex128)
+    omega_d = eng.to_device(np.asarray(frequencies, dtype=complex).reshape(1, N), np.complex128)
+    coef_d = None if coef is None else eng.to_device(
+        np.asarray(coef, dtype=complex).reshape(1, L, N), np.complex128)
+    C_d = eng.empty((1, N), torch.complex128)
+    mm_d = eng.empty((1,), torch.float64)
+    res_d = eng.empty((1,), torch.float64)
+    R_d = eng.empty((1, N, N + 1), torch.complex128)
+    st_d = eng.empty((1,), torch.int32)
+    model_d = eng.empty((1, L * K), torch.complex128)
+    common = dict(
+        times_d=times_d, data_d=data_d, n_fits=1, n_modes=N, n_series=L,
+        row_begin_all=0, row_end_all=K, t0_all=float(t0),
+        omega_d=omega_d, omega_shared=True, coef_d=coef_d, n_coef=0 if coef is None else 1,
+        coef_index_d=None if coef is None else eng.to_device(np.zeros(1, np.int32), np.int32),
+        dt_nominal=nominal_step(times_m, wmax),
+        C_d=C_d, mismatch_d=mm_d, residual_d=res_d, status_d=st_d,
+        model_d=model_d, model_stride=L * K)
+    eng.fit(eng.make_batch(R_d=R_d, **common))
+    R = eng.to_host(R_d)[0]
+    rank, s = _rank_and_singular_values(R, L * K)
+    if rank < N:
+        # numpy truncates here: complete the minimum-norm solution from the factor
+        # and re-evaluate model / mismatch on the device with it.
+        C_min = _minimum_norm_from_factor(R, L * K)
+        C_d.copy_(torch.from_numpy(np.ascontiguousarray(C_min.reshape(1, N))))
+        eng.evaluate(eng.make_batch(**common))
+    return {
+        'C': eng.to_host(C_d)[0], 'mismatch': np.float64(eng.to_host(mm_d)[0]),
+        'residual': eng.to_host(res_d)[0], 'model': eng.to_host(model_d)[0].reshape(L, K),
+        'rank': rank, 's': s, 'status': int(eng.to_host(st_d)[0]),
+    }
+
+
+def _numpy_residual(out, M, N):
+    """Shape (1,) sum of squared residuals, or empty when rank < N or M <= N
+    (numpy/linalg/_linalg.py:2580-2581)."""
+    if out['rank'] == N and M > N:
+        return np.array([out['residual']])
+    return np.array([], dtype=np.float64)
+
+
+# --------------------------------------------------------------------------
+# single fits
+
+def ringdown_fit(times, data, modes, Mf, chif, t0, t0_method='geq', T=100,
+                 delta=0.0):
+    """Least-squares fit of a ringdown model to one series (reference qnmfits.py:142-315).
+
+    Same arguments and the same 12-key result dict as the reference: 'residual',
+    'rank', 's', 'mismatch', 'C', 'data', 'model', 'model_times', 't0', 'modes',
+    'mode_labels', 'frequencies'.  Amplitudes are referenced to ``t0`` itself, not to
+    the first retained sample (qnmfits.py:281).
+    """
+    times = np.asarray(times)
+    data = np.asarray(data)
+    _check_modes(modes)
+    sel = _window(times, t0, T, t0_method)
+    times_masked = times[sel]
+    data_masked = data[sel]
+    delta_factor = _delta_factor(delta, len(modes))
+    frequencies = delta_factor * np.array(qnm.omega_list(modes, chif, Mf))
+
+    out = _single_fit_on_device(
+        np.asarray(times_masked, dtype=float),
+        np.asarray(data_masked, dtype=complex).reshape(1, -1), frequencies, t0, None)
+
+    return {
+        'residual': _numpy_residual(out, len(times_masked), len(modes)),
+        'rank': out['rank'],
+        's': out['s'],
+        'mismatch': out['mismatch'],
+        'C': out['C'],
+        'data': data_masked,
+        'model': out['model'][0],
+        'model_times': times_masked,
+        't0': t0,
+        'modes': modes,
+        'mode_labels': [str(mode) for mode in modes],
+        'frequencies': frequencies,
+    }
+
+
+def _mu_lists(spherical_modes, modes, chif):
+    """The reference's list-of-lists of mixing coefficients (qnmfits.py:618-622)."""
+    for mode in modes:
+        if len(mode) != 4:
+            # the reference unpacks exactly six indices (qnm.py:390) and raises
+            raise ValueError(
+                "multimode fits take (ell, m, n, sign) labels only: the reference has no "
+                "definition of mixing coefficients for nonlinear QNMs (too many values "
+                "to unpack (expected 6))")
+    return [qnm.mu_list([tuple(lm) + tuple(mode) for mode in modes], chif)
+            for lm in spherical_modes]
+
+
+def multimode_ringdown_fit(times, data_dict, modes, Mf, chif, t0,
+                           t0_method='geq', T=100, spherical_modes=None):
+    """Fit several spherical-harmonic series at once with spheroidal mixing
+    (reference qnmfits.py:478-673).  Returns the reference's 11-key dict incl.
+    'weighted_C' (mu_i * C per spherical mode) and per-mode 'model' / 'data' dicts.
+    """
+    times = np.asarray(times)
+    if spherical_modes is None:
+        spherical_modes = list(data_dict.keys())
+    sel = _window(times, t0, T, t0_method)
+    times_masked = times[sel]
+    data_dict_mask = {lm: np.asarray(data_dict[lm])[sel] for lm in spherical_modes}
+    frequencies = np.array(qnm.omega_list(modes, chif, Mf))
+    mu_lists = _mu_lists(spherical_modes, modes, chif)
+    coef = np.array([[complex(v) for v in row] for row in mu_lists], dtype=complex)
+    coef = coef.reshape(len(spherical_modes), len(modes))
+    rows = np.stack([np.asarray(data_dict_mask[lm], dtype=complex) for lm in spherical_modes]) \
+        if spherical_modes else np.zeros((0, len(times_masked)), dtype=complex)
+
+    out = _single_fit_on_device(np.asarray(times_masked, dtype=float), rows, frequencies, t0, coef)
+
+    model_dict = {}
+    weighted_C = {}
+    for i, lm in enumerate(spherical_modes):
+        model_dict[lm] = out['model'][i]
+        weighted_C[lm] = np.array(mu_lists[i]) * out['C']
+    M = rows.shape[0] * rows.shape[1]
+    return {
+        'residual': _numpy_residual(out, M, len(modes)),
+        'mismatch': out['mismatch'],
+        'C': out['C'],
+        'weighted_C': weighted_C,
+        'data': data_dict_mask,
+        'model': model_dict,
+        'model_times': times_masked,
+        't0': t0,
+        'modes': modes,
+        'mode_labels': [str(mode) for mode in modes],
+        'frequencies': frequencies,
+    }
+
+
+# --------------------------------------------------------------------------
+# sweeps
+
+def _series_rows(data, spherical_modes):
+    """(L, K_tot) complex array of the series to fit and the list of keys (or None)."""
+    if type(data) is dict:
+        keys = list(data.keys()) if spherical_modes is None else list(spherical_modes)
+        return np.stack([np.asarray(data[lm], dtype=complex) for lm in keys]), keys
+    return np.asarray(data, dtype=complex).reshape(1, -1), None
+
+
+class _Sweep:
+    """A sweep whose inputs are resident on the device: upload once, launch many times.
+
+    ``windows`` is (begin[n], end[n]) int32 arrays or a single (begin, end) pair; ``t0s``
+    is float64[n] or a scalar.  With torch.distributed initialised the flat fit index is
+    split into one contiguous slab per rank (``_dist.shard_bounds``); ``launch`` runs
+    this rank's slab and all-gathers the mismatches.
+    """
+
+    def __init__(self, times, rows, *, n_fits, n_modes, windows, t0s, freq_kwargs, coef,
+                 coef_per_chi, wmax):
+        import torch
+        eng = self.eng = get_engine()
+        self.n_fits = n_fits
+        self.rank, self.ws = _dist.world()
+        lo, hi, per = _dist.shard_bounds(n_fits, self.rank, self.ws)
+        self.lo, self.hi, self.per = lo, hi, per
+        n_local = hi - lo
+        L = rows.shape[0]
+
+        times_d = eng.to_device(times, np.float64)
+        data_d = eng.to_device(rows, np.complex128)
+        shared_window = not isinstance(windows[0], np.ndarray)
+        if shared_window:
+            rb_all, re_all = int(windows[0]), int(windows[1])
+            rb_d = re_d = None
+        else:
+            rb_all, re_all = int(windows[0].min()), int(windows[1].max())
+            rb_d = eng.to_device(windows[0][lo:hi], np.int32)
+            re_d = eng.to_device(windows[1][lo:hi], np.int32)
+        if re_all <= rb_all:
+            raise ValueError("the analysis window is empty")
+        if np.ndim(t0s) == 0:
+            t0_d, t0_all = None, float(t0s)
+        else:
+            t0_d, t0_all = eng.to_device(np.asarray(t0s, dtype=float)[lo:hi], np.float64), 0.0
+
+        kw = {k: (eng.to_device(v[0], v[1]) if isinstance(v, tuple) else v)
+              for k, v in freq_kwargs.items()}
+        coef_d = coef_index_d = None
+        n_coef = 0
+        if coef is not None:
+            coef_d = eng.to_device(coef, np.complex128)
+            n_coef = coef.shape[0]
+            if not coef_per_chi:
+                coef_index_d = torch.zeros(max(n_local, 1), dtype=torch.int32, device=eng.device)
+
+        self.mm_d = torch.full((max(per, 1),), float('nan'), dtype=torch.float64,
+                               device=eng.device)
+        self.st_d = torch.zeros((max(per, 1),), dtype=torch.int32, device=eng.device)
+        self.mm_all, self.st_all = self.mm_d[:n_fits], self.st_d[:n_fits]
+        self.batch = None
+        if n_local > 0:
+            self.batch = eng.make_batch(
+                times_d=times_d, data_d=data_d, n_fits=n_local, n_modes=n_modes, n_series=L,
+                first_fit=lo, row_begin_all=rb_all, row_end_all=re_all, t0_all=t0_all,
+                row_begin_d=rb_d, row_end_d=re_d, t0_d=t0_d,
+                coef_d=coef_d, coef_index_d=coef_index_d, n_coef=n_coef,
+                dt_nominal=nominal_step(times[rb_all:re_all], wmax),
+                mismatch_d=self.mm_d, status_d=self.st_d, **kw)
+        # keep every device buffer alive as long as the descriptor
+        self._keep = (times_d, data_d, rb_d, re_d, t0_d, kw, coef_d, coef_index_d)
+        self.rows_max = re_all - rb_all
+
+    def launch(self, gather_status=True):
+        """Asynchronous: the fit kernel on this rank's slab, then the all-gather."""
+        if self.batch is not None:
+            self.eng.fit(self.batch)
+        if self.ws > 1:
+            self.mm_all = _dist.all_gather_slabs(self.mm_d, self.n_fits)
+            if gather_status:
+                self.st_all = _dist.all_gather_slabs(self.st_d, self.n_fits)
+
+    def fetch(self):
+        """Mismatch of every fit (float64[n_fits]) and the status words, on the host."""
+        return self.eng.to_host(self.mm_all), self.eng.to_host(self.st_all)
+
+
+def _sweep_on_device(*args, **kwargs):
+    sweep = _Sweep(*args, **kwargs)
+    sweep.launch()
+    return sweep.fetch()
+
+
+def _warn_status(status, what):
+    bad = np.count_nonzero(status & (_cabi.ST_RANK_DEFICIENT | _cabi.ST_UNDERDETERMINED))
+    if bad:
+        import warnings
+        warnings.warn(
+            f"{what}: {bad} fit(s) are numerically rank deficient by numpy's "
+            "eps*max(M,N) criterion; numpy.linalg.lstsq would truncate singular values "
+            "there, the device returns the basic QR solution (mismatch may differ).",
+            RuntimeWarning, stacklevel=3)
+
+
+def mismatch_t0_array(times, data, modes, Mf, chif, t0_array, t0_method='geq',
+                      T_array=100, spherical_modes=None, delta=0.0):
+    """Mismatch for an array of start times (reference qnmfits.py:1183-1301).
+
+    Returns a Python list of np.float64 like the reference (its docstring says
+    ndarray; the code returns a list, qnmfits.py:1259,1301).  ``delta`` is ignored for
+    dict data, as in the reference (qnmfits.py:1251).
+    """
+    times = np.asarray(times)
+    t0_array = np.asarray(t0_array, dtype=float)
+    if type(T_array) != np.ndarray:
+        T_array = T_array * np.ones(len(t0_array))
+    if not (_is_scalar(Mf) and _is_scalar(chif)):
+        raise NotImplementedError(
+            "time-dependent Mf/chif (dynamic_ringdown_fit, reference qnmfits.py:1286-1299) "
+            "is outside the B200 hot path")
+    _check_modes(modes)
+    if t0_method not in ('geq', 'closest'):
+        raise ValueError(
+            "Requested t0_method is not valid. Please choose between 'geq' and 'closest'")
+    n = len(t0_array)
+    if n == 0:
+        return []
+
+    if np.any(np.diff(times) < 0):
+        # Unsorted time arrays make the 'geq' mask non-contiguous: fit one by one.
+        fit = multimode_ringdown_fit if type(data) is dict else ringdown_fit
+        out = []
+        for t0, T in zip(t0_array, T_array):
+            if type(data) is dict:
+                out.append(fit(times, data, modes, Mf, chif, t0, t0_method, T,
+                               spherical_modes)['mismatch'])
+            else:
+                out.append(fit(times, data, modes, Mf, chif, t0, t0_method, T,
+                               delta)['mismatch'])
+        return out
+
+    rows, keys = _series_rows(data, spherical_modes)
+    begin = np.empty(n, np.int32)
+    end = np.empty(n, np.int32)
+    for i, (t0, T) in enumerate(zip(t0_array, T_array)):
+        begin[i], end[i] = _window_rows(times, t0, T, t0_method)
+    if np.any(end <= begin):
+        raise ValueError("an analysis window is empty")
+
+    if keys is None:
+        frequencies = _delta_factor(delta, len(modes)) * np.array(
+            qnm.omega_list(modes, chif, Mf))
+        coef = None
+    else:
+        frequencies = np.array(qnm.omega_list(modes, chif, Mf))
+        mu_lists = _mu_lists(keys, modes, chif)
+        coef = np.array([[complex(v) for v in row] for row in mu_lists],
+                        dtype=complex).reshape(1, len(keys), len(modes))
+    freq_kwargs = dict(omega_d=(frequencies.reshape(1, -1), np.complex128), omega_shared=True)
+    mm, status = _sweep_on_device(
+        np.asarray(times, dtype=float), rows, n_fits=n, n_modes=len(modes),
+        windows=(begin, end), t0s=t0_array, freq_kwargs=freq_kwargs, coef=coef,
+        coef_per_chi=False, wmax=float(np.max(np.abs(frequencies))))
+    _warn_status(status, "mismatch_t0_array")
+    return [np.float64(v) for v in mm]
+
+
+def _prepare_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0, t0_method='geq',
+                        T=100, res=50, spherical_modes=None, delta=0.0):
+    """Host tabulation + upload for the grid sweep; returns (sweep, shape)."""
+    times = np.asarray(times)
+    _check_modes(modes)
+    Mf_array = np.linspace(Mf_minmax[0], Mf_minmax[1], res)
+    chif_array = np.linspace(chif_minmax[0], chif_minmax[1], res)
+    shape = (len(Mf_array), len(chif_array))
+    n = shape[0] * shape[1]
+    if n == 0:
+        return None, shape
+    if np.any(np.diff(times) < 0):
+        raise ValueError("times must be ascending")
+    window = _window_rows(times, t0, T, t0_method)
+    if window[1] <= window[0]:
+        raise ValueError("the analysis window is empty")
+    rows, keys = _series_rows(data, spherical_modes)
+
+    # Frequencies are tabulated for the `res` unique spins only and shipped factored:
+    # the device forms omega = delta_factor * sum(table[chi] * (1/Mf)) per grid point
+    # with the reference's rounding (qnm.py:235,272-280; qnmfits.py:274).
+    table, mode_ptr = qnm.constituent_table(modes, chif_array)
+    inv_Mf = 1.0 / Mf_array
+    if keys is None:
+        df = _delta_factor(delta, len(modes))
+        df = np.broadcast_to(np.asarray(df, dtype=float), (len(modes),)).copy()
+        coef = None
+    else:
+        for mode in modes:
+            if len(mode) != 4:
+                raise ValueError("multimode fits take (ell, m, n, sign) labels only")
+        df = None
+        coef = qnm.mu_table(keys, modes, chif_array)
+    wmax = float(np.max(np.abs(table)) * np.max(np.abs(inv_Mf))
+                 * (1.0 if df is None else np.max(np.abs(df)))) * max(
+                     len(m) // 4 for m in modes)
+    freq_kwargs = dict(
+        omega_tilde_d=(table, np.complex128), mode_ptr_d=(mode_ptr, np.int32),
+        inv_Mf_d=(inv_Mf, np.float64), n_chi=len(chif_array), n_mf=len(Mf_array),
+        n_constituents=table.shape[1])
+    if df is not None:
+        freq_kwargs['delta_factor_d'] = (df, np.float64)
+    sweep = _Sweep(
+        np.asarray(times, dtype=float), rows, n_fits=n, n_modes=len(modes),
+        windows=window, t0s=float(t0), freq_kwargs=freq_kwargs, coef=coef,
+        coef_per_chi=True, wmax=wmax)
+    return sweep, shape
+
+
+def mismatch_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0,
+                        t0_method='geq', T=100, res=50, spherical_modes=None,
+                        delta=0.0):
+    """Mismatch on a res x res grid of remnant mass and spin (reference
+    qnmfits.py:1304-1415).  Returns float64 (res, res) indexed [iMf, ichif].
+
+    The flat index i = iMf * res + ichif of the reference's loop (qnmfits.py:1393-1394,
+    1404-1405) is the sharding axis: each rank of an initialised torch.distributed job
+    fits one contiguous slab and the mismatches are all-gathered.
+    """
+    sweep, shape = _prepare_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0,
+                                       t0_method, T, res, spherical_modes, delta)
+    if sweep is None:
+        return np.reshape(np.array([]), shape)
+    sweep.launch()
+    mm, status = sweep.fetch()
+    _warn_status(status, "mismatch_M_chi_grid")
+    return np.reshape(mm, shape)

@@ -1,0 +1,130 @@
+"""
+Synthetic injected-QNM workloads of BASELINE.json's configs.
+
+Input generators only (seeded, deterministic): used by bench.py, the tests and
+``__graft_entry__.smoke()`` so that every arm — reference, oracle, CUDA — is fed the
+same arrays.  ``times = np.arange(-500, 1501) * 0.1`` (dt = 0.1 M, K_tot = 2001); truth
+(Mf, chif) = (0.95, 0.69); amplitudes from ``default_rng(0)``; complex white noise of
+sigma 1e-6 from ``default_rng(1)``; the signal is zero before t = 0
+(reference ``ringdown``, qnmfits/qnmfits.py:15-70).
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import synthetic
+from .qnm import set_table_provider
+from .qnmfits import qnm, ringdown
+
+MF_TRUE, CHIF_TRUE = 0.95, 0.69
+
+
+def use_synthetic_tables():
+    """Serve ``qnm.modes_cache`` from the closed-form synthetic provider."""
+    set_table_provider(synthetic.modes_cache)
+
+
+def synthetic_modes_cache():
+    return synthetic.modes_cache
+
+
+@dataclass
+class Workload:
+    name: str
+    times: np.ndarray
+    data: object                     # ndarray (single series) or dict {(l, m): ndarray}
+    modes: list
+    t0: float = 0.0
+    T: float = 100.0
+    Mf: float = MF_TRUE
+    chif: float = CHIF_TRUE
+    Mf_minmax: tuple = (0.85, 1.05)
+    chif_minmax: tuple = (0.59, 0.79)
+    res: int = 256
+    t0_array: np.ndarray = None
+    spherical_modes: list = None
+    extra: dict = field(default_factory=dict)
+
+
+def default_times():
+    return np.arange(-500, 1501) * 0.1
+
+
+def overtone_modes(n_overtones=8, ell=2, m=2):
+    return [(ell, m, n, 1) for n in range(n_overtones)]
+
+
+def _noise(rng, n, sigma):
+    return sigma * (rng.normal(size=n) + 1j * rng.normal(size=n))
+
+
+def injected_series(times, modes, Mf=MF_TRUE, chif=CHIF_TRUE, sigma=1e-6):
+    """h(t) = sum_j C_j exp(-i w_j t) for t >= 0, plus noise (single series)."""
+    omega = np.array(qnm.omega_list(modes, chif, Mf))
+    rng = np.random.default_rng(0)
+    C = rng.normal(size=len(modes)) + 1j * rng.normal(size=len(modes))
+    h = ringdown(times, 0.0, C, omega)
+    return h + _noise(np.random.default_rng(1), len(times), sigma), C
+
+
+def config1(n_overtones=8):
+    """ringdown_fit of h22 with (2,2,n,+1), n < n_overtones, t0 = 0, T = 100."""
+    times = default_times()
+    modes = overtone_modes(n_overtones)
+    data, C = injected_series(times, modes)
+    return Workload("cfg1_ringdown_fit", times, data, modes, extra={"C_true": C})
+
+
+def config2(n_t0=1000, n_overtones=8):
+    """mismatch_t0_array: start times linspace(-10, 60, n_t0)."""
+    wl = config1(n_overtones)
+    wl.name = "cfg2_mismatch_t0_array"
+    wl.t0_array = np.linspace(-10.0, 60.0, n_t0)
+    return wl
+
+
+def config3(res=256, n_overtones=8):
+    """mismatch_M_chi_grid: res x res grid around the truth, 8 overtones on h22."""
+    wl = config1(n_overtones)
+    wl.name = "cfg3_mismatch_M_chi_grid"
+    wl.res = res
+    return wl
+
+
+def multimode_labels():
+    """21 spherical modes (ell = 2..4) and 40 QNMs: regular and mirror, three m's."""
+    spherical = [(ell, m) for ell in (2, 3, 4) for m in range(-ell, ell + 1)]
+    modes = []
+    for m in (2, -2):
+        for ell in (2, 3, 4):
+            ell_eff = max(ell, abs(m))
+            modes += [(ell_eff, m, n, 1) for n in range(4)]
+        for ell in (2, 3):
+            modes += [(ell, m, n, -1) for n in range(2)]
+    for ell, n_max in ((2, 4), (3, 2), (4, 2)):
+        modes += [(ell, 0, n, 1) for n in range(n_max)]
+    return spherical, modes
+
+
+def config4(n_t0=500, spherical=None, modes=None, sigma=1e-6):
+    """multimode sweep: 21 series x 40 QNMs with spheroidal mixing and mirror modes.
+
+    Nonlinear (quadratic) labels are not included: the reference's
+    multimode_ringdown_fit cannot express them (qnm.py:390 raises), so there is no
+    reference result to be faithful to.
+    """
+    if spherical is None or modes is None:
+        spherical, modes = multimode_labels()
+    times = default_times()
+    omega = np.array(qnm.omega_list(modes, CHIF_TRUE, MF_TRUE))
+    rng = np.random.default_rng(0)
+    C = rng.normal(size=len(modes)) + 1j * rng.normal(size=len(modes))
+    noise_rng = np.random.default_rng(1)
+    data = {}
+    for lm in spherical:
+        mu = np.array([complex(v) for v in
+                       qnm.mu_list([lm + mode for mode in modes], CHIF_TRUE)])
+        data[lm] = ringdown(times, 0.0, mu * C, omega) + _noise(noise_rng, len(times), sigma)
+    return Workload("cfg4_multimode_t0_sweep", times, data, modes,
+                    t0_array=np.linspace(0.0, 50.0, n_t0), spherical_modes=spherical,
+                    extra={"C_true": C})

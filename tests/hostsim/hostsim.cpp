@@ -1,0 +1,114 @@
+// hostsim.cpp — TEST HARNESS ONLY.  Compiles the K1 device code (fit_small.cuh) as
+// plain host C++ (-DQNMFIT_HOSTSIM) and runs the lanes of each CTA one after another,
+// phase by phase, exactly as the CUDA kernel orders them.  It lets the CPU-only test
+// tier check the kernel's arithmetic (streamed TSQR, anchored recurrence, R-combine,
+// back-substitution, mismatch sums) against the oracle.  It is never loaded by the
+// qnmfits_b200 package.
+//
+// Build: g++ -O2 -std=c++17 -mfma -ffp-contract=off -fPIC -shared -DQNMFIT_HOSTSIM
+//        -Iinclude -Iqnmfits_b200/csrc -o tests/hostsim/libqnmfit_hostsim.so hostsim.cpp
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "qnmfit.h"
+#include "fit_small.cuh"
+
+#define HS_THREADS 256
+
+static void fill_params(const qnmfit_batch *b, int lpf, bool eval, FitParams *p)
+{
+    memset(p, 0, sizeof(*p));
+    p->n_fits = b->n_fits; p->n_modes = b->n_modes; p->n_series = b->n_series; p->n_times = b->n_times;
+    p->series_stride = b->series_stride; p->first_fit = b->first_fit;
+    p->times = b->times; p->data = (const double2 *)b->data;
+    p->row_begin = b->row_begin; p->row_end = b->row_end; p->t0 = b->t0;
+    p->row_begin_all = b->row_begin_all; p->row_end_all = b->row_end_all; p->t0_all = b->t0_all;
+    p->omega = (const double2 *)b->omega; p->omega_tilde = b->omega_tilde; p->mode_ptr = b->mode_ptr;
+    p->inv_Mf = b->inv_Mf; p->delta_factor = b->delta_factor; p->chi_index = b->chi_index;
+    p->mf_index = b->mf_index; p->n_chi = b->n_chi > 0 ? b->n_chi : 1; p->n_mf = b->n_mf;
+    p->n_constituents = b->n_constituents;
+    p->anchor_rows = b->anchor_rows > 0 ? b->anchor_rows : 32;
+    p->dt_nominal = b->dt_nominal;
+    p->C = (double2 *)b->C; p->mismatch = b->mismatch; p->residual = b->residual;
+    p->R = (double2 *)b->R; p->status = b->status;
+    p->model = (double2 *)b->model; p->model_stride = b->model_stride; p->omega_shared = b->omega_shared;
+    p->lanes_per_fit = lpf; p->eval_only = eval ? 1 : 0;
+}
+
+template <int N>
+static void run(const qnmfit_batch *b, int lpf, bool eval)
+{
+    FitParams p;
+    fill_params(b, lpf, eval, &p);
+    const int fpc = HS_THREADS / lpf;
+    const int ctas = (b->n_fits + fpc - 1) / fpc;
+    std::vector<unsigned char> smem(SmallSmem<N, HS_THREADS>::bytes(fpc, 0) + 64);
+    for (int cta = 0; cta < ctas; ++cta) {
+        SmallSmem<N, HS_THREADS> sm;
+        sm.carve(smem.data(), fpc, 0);
+        sm.ts = p.times; sm.ds = p.data; sm.t_off = 0;
+        for (int idx = 0; idx < fpc * N; ++idx) {
+            const int slot = idx / N, j = idx - slot * N;
+            const int fit = cta * fpc + slot;
+            if (fit < p.n_fits) {
+                const double2 w = fit_omega(p, fit, j);
+                sm.om[j * fpc + slot] = w;
+                if (p.dt_nominal > 0.0) {
+                    const double2 q = design_entry(w, p.dt_nominal);
+                    sm.qq[j * fpc + slot] = q;
+                    sm.qw[j * fpc + slot] = c_mul(q, make_double2(w.y, -w.x));
+                }
+            }
+        }
+        std::vector<SmallLane> lanes(HS_THREADS);
+        std::vector<int> status(HS_THREADS, 0);
+        for (int tid = 0; tid < HS_THREADS; ++tid) {
+            lanes[tid] = small_lane_setup(p, cta, tid, HS_THREADS);
+            small_clear<N, HS_THREADS>(sm, tid);
+        }
+        if (!eval) {
+            for (int tid = 0; tid < HS_THREADS; ++tid) small_leaf<N, HS_THREADS>(p, sm, lanes[tid], tid);
+            for (int s = 1; s < lpf; s <<= 1)
+                for (int tid = 0; tid < HS_THREADS; ++tid) small_tree_level<N, HS_THREADS>(p, sm, lanes[tid], tid, s);
+            for (int tid = 0; tid < HS_THREADS; ++tid) small_backsub<N, HS_THREADS>(p, sm, lanes[tid], tid, status[tid]);
+        }
+        std::vector<double> sums(HS_THREADS * 4), tmp(HS_THREADS * 4);
+        for (int tid = 0; tid < HS_THREADS; ++tid) {
+            double s4[4];
+            small_eval<N, HS_THREADS>(p, sm, lanes[tid], tid, s4);
+            for (int q = 0; q < 4; ++q) sums[tid * 4 + q] = s4[q];
+        }
+        for (int s = 1; s < lpf; s <<= 1) {   // the __shfl_xor butterfly
+            for (int tid = 0; tid < HS_THREADS; ++tid)
+                for (int q = 0; q < 4; ++q) tmp[tid * 4 + q] = sums[tid * 4 + q] + sums[(tid ^ s) * 4 + q];
+            sums.swap(tmp);
+        }
+        for (int tid = 0; tid < HS_THREADS; ++tid) {
+            double s4[4];
+            for (int q = 0; q < 4; ++q) s4[q] = sums[tid * 4 + q];
+            small_finalize(p, lanes[tid], s4, status[tid]);
+        }
+    }
+}
+
+extern "C" int hostsim_sizeof_batch(void) { return (int)sizeof(qnmfit_batch); }
+
+// All pointers in *b are HOST pointers here.
+extern "C" int hostsim_fit_small(const qnmfit_batch *b, int lpf, int eval)
+{
+    if (!b || b->struct_size != (int)sizeof(qnmfit_batch)) return QNMFIT_E_ABI;
+    if (b->n_series != 1 || b->n_modes < 1 || b->n_modes > QNMFIT_MAX_MODES_SMALL) return QNMFIT_E_SHAPE;
+    if (lpf < 1 || lpf > 32 || (lpf & (lpf - 1))) return QNMFIT_E_SHAPE;
+    switch (b->n_modes) {
+    case 1: run<1>(b, lpf, eval); break;
+    case 2: run<2>(b, lpf, eval); break;
+    case 3: run<3>(b, lpf, eval); break;
+    case 4: run<4>(b, lpf, eval); break;
+    case 5: run<5>(b, lpf, eval); break;
+    case 6: run<6>(b, lpf, eval); break;
+    case 7: run<7>(b, lpf, eval); break;
+    case 8: run<8>(b, lpf, eval); break;
+    }
+    return 0;
+}

@@ -1,0 +1,82 @@
+"""Drive the K1 lane-emulation harness (tests/hostsim) with numpy host arrays through
+the same qnmfit_batch descriptor the CUDA library takes."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from qnmfits_b200 import _cabi
+from qnmfits_b200._engine import nominal_step
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_hs = None
+
+
+def lib():
+    global _hs
+    if _hs is None:
+        _hs = C.CDLL(os.path.join(ROOT, "tests", "hostsim", "libqnmfit_hostsim.so"))
+        _hs.hostsim_fit_small.argtypes = [C.POINTER(_cabi.Batch), C.c_int, C.c_int]
+    return _hs
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def run(times, data, *, n_fits, n_modes, window, t0, lpf=4, eval_only=False, dt=None,
+        anchor_rows=0, omega=None, omega_shared=False, table=None, mode_ptr=None, inv_Mf=None,
+        delta_factor=None, n_chi=0, n_mf=0, first_fit=0, C_in=None, want_model=False):
+    times = np.ascontiguousarray(times, dtype=float)
+    data = np.ascontiguousarray(data, dtype=complex)
+    keep = [times, data]
+    kw = {}
+    if isinstance(window[0], np.ndarray):
+        rb = np.ascontiguousarray(window[0], np.int32)
+        re = np.ascontiguousarray(window[1], np.int32)
+        keep += [rb, re]
+        kw.update(row_begin=_p(rb), row_end=_p(re), row_begin_all=int(rb.min()),
+                  row_end_all=int(re.max()))
+    else:
+        kw.update(row_begin_all=int(window[0]), row_end_all=int(window[1]))
+    if np.ndim(t0) == 0:
+        kw.update(t0_all=float(t0))
+    else:
+        t0a = np.ascontiguousarray(t0, dtype=float)
+        keep.append(t0a)
+        kw.update(t0=_p(t0a))
+    if omega is not None:
+        om = np.ascontiguousarray(omega, dtype=complex)
+        keep.append(om)
+        kw.update(omega=_p(om), omega_shared=1 if omega_shared else 0)
+        wmax = float(np.max(np.abs(om)))
+    else:
+        tab = np.ascontiguousarray(table, dtype=complex)
+        mp = np.ascontiguousarray(mode_ptr, np.int32)
+        inv = np.ascontiguousarray(inv_Mf, dtype=float)
+        keep += [tab, mp, inv]
+        kw.update(omega_tilde=_p(tab), mode_ptr=_p(mp), inv_Mf=_p(inv), n_chi=n_chi, n_mf=n_mf,
+                  n_constituents=tab.shape[1])
+        wmax = float(np.max(np.abs(tab)) * np.max(inv)) * 3
+        if delta_factor is not None:
+            df = np.ascontiguousarray(delta_factor, dtype=float)
+            keep.append(df)
+            kw.update(delta_factor=_p(df))
+    if dt is None:
+        dt = nominal_step(times[kw["row_begin_all"]:kw["row_end_all"]], wmax)
+    Mmax = kw["row_end_all"] - kw["row_begin_all"]
+    Cbuf = np.zeros((n_fits, n_modes), complex) if C_in is None else \
+        np.ascontiguousarray(C_in, dtype=complex)
+    mm = np.zeros(n_fits)
+    res = np.zeros(n_fits)
+    R = np.zeros((n_fits, n_modes, n_modes + 1), complex)
+    st = np.zeros(n_fits, np.int32)
+    model = np.zeros((n_fits, Mmax), complex) if want_model else None
+    b = _cabi.Batch(n_fits=n_fits, n_modes=n_modes, n_series=1, n_times=len(times),
+                    series_stride=len(times), first_fit=first_fit, times=_p(times), data=_p(data),
+                    dt_nominal=float(dt), anchor_rows=anchor_rows, C=_p(Cbuf), mismatch=_p(mm),
+                    residual=_p(res), R=_p(R), status=_p(st), model=_p(model),
+                    model_stride=Mmax if want_model else 0, **kw)
+    rc = lib().hostsim_fit_small(C.byref(b), int(lpf), 1 if eval_only else 0)
+    assert rc == 0, rc
+    return dict(C=Cbuf, mismatch=mm, residual=res, R=R, status=st, model=model, dt=dt)

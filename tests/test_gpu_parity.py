@@ -1,0 +1,233 @@
+"""Parity of the CUDA path (through the public API -> ctypes -> libqnmfit.so) with the
+oracle (numpy lstsq restatement of the reference) and with the golden fixtures the
+unmodified reference produced.  Tolerances (BASELINE.json north_star):
+amplitudes max(1e-8, 100*cond*eps) relative, mismatch 1e-10 absolute, discrete
+choices (frequencies, window rows, rank) exact."""
+import warnings
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import qnmfits_oracle as orc
+from qnmfits_b200 import _cabi, workloads
+
+pytestmark = pytest.mark.gpu
+
+MM_TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def eng(qf):
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    from qnmfits_b200._engine import get_engine
+    return get_engine()
+
+
+def test_library_is_loaded_and_device_is_blackwell(eng):
+    import torch
+    assert torch.cuda.get_device_capability(0)[0] == 10
+    assert eng.ctx.handle
+
+
+def test_ringdown_fit_cases_vs_golden(qf, eng, golden):
+    g = golden("cfg1")
+    wl, cs = cases.cfg1_cases()
+    for name, kw in cs.items():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            fit = qf.ringdown_fit(wl.times, wl.data, **kw)
+        assert list(fit.keys()) == ['residual', 'rank', 's', 'mismatch', 'C', 'data', 'model',
+                                    'model_times', 't0', 'modes', 'mode_labels', 'frequencies']
+        assert np.array_equal(fit["frequencies"], g[name + "__frequencies"]), name
+        assert np.array_equal(fit["model_times"], g[name + "__model_times"]), name
+        assert int(fit["rank"]) == int(g[name + "__rank"]), name
+        assert fit["residual"].shape == g[name + "__residual"].shape, name
+        s = g[name + "__s"]
+        np.testing.assert_allclose(fit["s"], s, rtol=1e-8, atol=1e-12 * s[0], err_msg=name)
+        C_ref = g[name + "__C"]
+        if int(g[name + "__rank"]) == len(C_ref):
+            err = np.max(np.abs(fit["C"] - C_ref)) / np.max(np.abs(C_ref))
+            assert err < cases.amp_tol(s), (name, err)
+        else:
+            # numpy truncated a singular value: the host completes the minimum-norm
+            # solution from the device factor; compare what is well defined
+            assert abs(np.linalg.norm(fit["C"]) - np.linalg.norm(C_ref)) < 1e-6 * np.linalg.norm(C_ref)
+        assert abs(fit["mismatch"] - float(g[name + "__mismatch"])) < MM_TOL, name
+        scale = np.max(np.abs(g[name + "__model"]))
+        np.testing.assert_allclose(fit["model"], g[name + "__model"], rtol=0, atol=1e-8 * scale,
+                                   err_msg=name)
+        if fit["residual"].size:
+            np.testing.assert_allclose(fit["residual"], g[name + "__residual"], rtol=1e-7)
+
+
+def test_g1_injection_recovery(qf, eng, golden):
+    g = golden("g1")
+    f0 = qf.ringdown_fit(g["times"], g["data"], [(2, 2, 0, 1)], 1, 0.7, 0)
+    f10 = qf.ringdown_fit(g["times"], g["data"], [(2, 2, 0, 1)], 1, 0.7, 10)
+    assert abs(f0["C"][0] - (1 - 1j)) < 1e-12 and abs(f0["mismatch"]) < 1e-13
+    np.testing.assert_allclose(f10["C"], g["C10"], rtol=1e-11)
+
+
+def test_nonuniform_grid_direct_path(qf, eng, golden):
+    g = golden("nonuniform")
+    fit = qf.ringdown_fit(g["times"], g["data"], workloads.overtone_modes(5), 0.95, 0.69, 1.0, T=60)
+    assert cases.rel_err(fit["C"], g["fit__C"]) < 1e-8
+    assert abs(fit["mismatch"] - float(g["fit__mismatch"])) < MM_TOL
+
+
+def test_t0_sweep_vs_golden_and_oracle(qf, eng, golden, oracle_tables):
+    g = golden("cfg2")
+    wl = workloads.config2(n_t0=40)
+    mm = qf.mismatch_t0_array(wl.times, wl.data, wl.modes, 0.95, 0.69, wl.t0_array)
+    assert isinstance(mm, list) and isinstance(mm[0], np.float64)
+    np.testing.assert_allclose(mm, g["mismatch"], rtol=0, atol=MM_TOL)
+    mmc = qf.mismatch_t0_array(wl.times, wl.data, wl.modes[:4], 0.95, 0.69, wl.t0_array[:10],
+                               t0_method="closest", T_array=np.linspace(50, 80, 10))
+    np.testing.assert_allclose(mmc, g["mismatch_closest"], rtol=0, atol=MM_TOL)
+    # config 2 at full size: 1000 start times vs the oracle
+    wl = workloads.config2()
+    mm = qf.mismatch_t0_array(wl.times, wl.data, wl.modes, wl.Mf, wl.chif, wl.t0_array)
+    want = orc.mismatch_t0_array(oracle_tables, wl.times, wl.data, wl.modes, wl.Mf, wl.chif,
+                                 wl.t0_array)
+    np.testing.assert_allclose(mm, want, rtol=0, atol=MM_TOL)
+
+
+def test_grid_vs_golden(qf, eng, golden):
+    g = golden("cfg3")
+    wl = workloads.config3(res=12)
+    grid = qf.mismatch_M_chi_grid(wl.times, wl.data, wl.modes, wl.Mf_minmax, wl.chif_minmax, wl.t0,
+                                  T=wl.T, res=12)
+    assert grid.shape == (12, 12) and grid.dtype == np.float64
+    np.testing.assert_allclose(grid, g["grid"], rtol=0, atol=MM_TOL)
+    gq = qf.mismatch_M_chi_grid(wl.times, wl.data, [(2, 2, 0, 1), (2, 2, 1, 1), (2, 2, 0, 1, 2, 2, 0, 1)],
+                                wl.Mf_minmax, wl.chif_minmax, 15.0, T=60, res=5,
+                                delta=[0.0, 0.01, 0.0])
+    np.testing.assert_allclose(gq, g["grid_quadratic"], rtol=0, atol=MM_TOL)
+
+
+def test_full_size_grid_properties(qf, eng, oracle_tables):
+    """Config 3 at BASELINE size (256 x 256 = 65 536 fits): spot checks against the
+    oracle at random grid points, orientation [iMf, ichi], minimum near the truth, and
+    index-sharding invariance (slabs computed separately are bit-identical)."""
+    wl = workloads.config3(res=256)
+    grid = qf.mismatch_M_chi_grid(wl.times, wl.data, wl.modes, wl.Mf_minmax, wl.chif_minmax, wl.t0,
+                                  T=wl.T, res=256)
+    assert grid.shape == (256, 256) and np.all(np.isfinite(grid))
+    rng = np.random.default_rng(5)
+    idx = rng.choice(256 * 256, size=96, replace=False)
+    want = orc.mismatch_M_chi_grid(oracle_tables, wl.times, wl.data, wl.modes, wl.Mf_minmax,
+                                   wl.chif_minmax, wl.t0, T=wl.T, res=256, flat_indices=idx)
+    np.testing.assert_allclose(grid.reshape(-1)[idx], want, rtol=0, atol=MM_TOL)
+    i, j = np.unravel_index(np.argmin(grid), grid.shape)
+    Mf = np.linspace(*wl.Mf_minmax, 256)[i]
+    chi = np.linspace(*wl.chif_minmax, 256)[j]
+    assert abs(Mf - workloads.MF_TRUE) < 2e-3 and abs(chi - workloads.CHIF_TRUE) < 2e-3
+    again = qf.mismatch_M_chi_grid(wl.times, wl.data, wl.modes, wl.Mf_minmax, wl.chif_minmax,
+                                   wl.t0, T=wl.T, res=256)
+    assert np.array_equal(grid, again)          # deterministic
+
+
+def test_slab_launches_are_bit_identical_to_one_launch(qf, eng):
+    """What each rank of an N-GPU job computes (first_fit offset) equals the
+    corresponding slab of the single launch, for several lanes-per-fit choices."""
+    import torch
+    from qnmfits_b200 import qnmfits as api
+    res = 24
+    wl = workloads.config3(res=res)
+    Mf = np.linspace(*wl.Mf_minmax, res)
+    chi = np.linspace(*wl.chif_minmax, res)
+    table, ptr = qf.qnm.constituent_table(wl.modes, chi)
+    win = api._window_rows(wl.times, 0.0, 100, "geq")
+    d = dict(times_d=eng.to_device(wl.times, np.float64),
+             data_d=eng.to_device(wl.data.reshape(1, -1), np.complex128),
+             omega_tilde_d=eng.to_device(table, np.complex128), mode_ptr_d=eng.to_device(ptr, np.int32),
+             inv_Mf_d=eng.to_device(1.0 / Mf, np.float64), n_chi=res, n_mf=res,
+             n_constituents=table.shape[1], n_modes=8, row_begin_all=win[0], row_end_all=win[1],
+             t0_all=0.0, dt_nominal=0.1)
+    n = res * res
+    full = eng.empty((n,), torch.float64)
+    eng.fit(eng.make_batch(n_fits=n, mismatch_d=full, **d))
+    parts = eng.empty((n,), torch.float64)
+    for lo, hi in ((0, 100), (100, 101), (101, 400), (400, n)):
+        eng.fit(eng.make_batch(n_fits=hi - lo, first_fit=lo, mismatch_d=parts[lo:hi], **d))
+    eng.synchronize()
+    assert torch.equal(full, parts)
+
+
+def test_general_kernel_matches_small_kernel_and_oracle(qf, eng, oracle_tables):
+    """K2 (CTA per fit) forced on a K1-sized problem."""
+    import torch
+    from qnmfits_b200 import qnmfits as api
+    wl = workloads.config1()
+    freq = np.array(qf.qnm.omega_list(wl.modes, 0.69, 0.95))
+    win = api._window_rows(wl.times, 0.0, 100, "geq")
+    d = dict(times_d=eng.to_device(wl.times, np.float64),
+             data_d=eng.to_device(wl.data.reshape(1, -1), np.complex128),
+             omega_d=eng.to_device(freq.reshape(1, -1), np.complex128), omega_shared=True,
+             n_fits=1, n_modes=8, row_begin_all=win[0], row_end_all=win[1], t0_all=0.0)
+    outs = {}
+    for name, kernel, dt in (("k1", _cabi.KERNEL_SMALL, 0.1), ("k2", _cabi.KERNEL_GENERAL, 0.0)):
+        C_d = eng.empty((1, 8), torch.complex128)
+        mm_d = eng.empty((1,), torch.float64)
+        eng.fit(eng.make_batch(kernel=kernel, dt_nominal=dt, C_d=C_d, mismatch_d=mm_d, **d))
+        outs[name] = (eng.to_host(C_d)[0], float(eng.to_host(mm_d)[0]))
+    want = orc.ringdown_fit(oracle_tables, wl.times, wl.data, wl.modes, 0.95, 0.69, 0.0)
+    for name, (C, mm) in outs.items():
+        err = np.max(np.abs(C - want["C"])) / np.max(np.abs(want["C"]))
+        assert err < cases.amp_tol(want["s"]), (name, err)
+        assert abs(mm - want["mismatch"]) < MM_TOL, name
+
+
+def test_multimode_vs_golden(qf, eng, golden):
+    g = golden("cfg4")
+    wl = cases.cfg4_small()
+    fit = qf.multimode_ringdown_fit(wl.times, wl.data, cases.MM_MODES, 0.95, 0.69, 5.0, T=80)
+    assert list(fit.keys()) == ['residual', 'mismatch', 'C', 'weighted_C', 'data', 'model',
+                                'model_times', 't0', 'modes', 'mode_labels', 'frequencies']
+    assert np.array_equal(fit["frequencies"], g["frequencies"])
+    err = np.max(np.abs(fit["C"] - g["C"])) / np.max(np.abs(g["C"]))
+    assert err < 1e-8, err
+    assert abs(fit["mismatch"] - float(g["mismatch"])) < MM_TOL
+    np.testing.assert_allclose(fit["residual"], g["residual"], rtol=1e-7)
+    for lm in cases.MM_SPH:
+        m_ref = g[f"model_{lm[0]}_{lm[1]}"]
+        np.testing.assert_allclose(fit["model"][lm], m_ref, rtol=0, atol=1e-8 * np.max(np.abs(g["C"])))
+        np.testing.assert_allclose(fit["weighted_C"][lm], g[f"weighted_C_{lm[0]}_{lm[1]}"],
+                                   rtol=0, atol=1e-8 * np.max(np.abs(g["C"])))
+    sub = qf.multimode_ringdown_fit(wl.times, wl.data, cases.MM_MODES[:4], 0.95, 0.69, 5.0, T=80,
+                                    spherical_modes=[(2, 2), (3, 2)])
+    assert np.max(np.abs(sub["C"] - g["sub_C"])) / np.max(np.abs(g["sub_C"])) < 1e-8
+    assert abs(sub["mismatch"] - float(g["sub_mismatch"])) < MM_TOL
+    sweep = qf.mismatch_t0_array(wl.times, wl.data, cases.MM_MODES, 0.95, 0.69, wl.t0_array,
+                                 T_array=70)
+    np.testing.assert_allclose(sweep, g["t0_sweep"], rtol=0, atol=MM_TOL)
+    grid = qf.mismatch_M_chi_grid(wl.times, wl.data, cases.MM_MODES, (0.9, 1.0), (0.6, 0.75), 5.0,
+                                  T=80, res=4)
+    np.testing.assert_allclose(grid, g["grid"], rtol=0, atol=MM_TOL)
+    with pytest.raises(ValueError):
+        qf.multimode_ringdown_fit(wl.times, wl.data, [(2, 2, 0, 1, 2, 2, 0, 1)], 0.95, 0.69, 5.0)
+
+
+def test_config4_shape_vs_oracle(qf, eng, oracle_tables):
+    """21 spherical modes x 40 QNMs (config 4's shape), three start times vs the oracle."""
+    wl = workloads.config4(n_t0=3)
+    got = qf.mismatch_t0_array(wl.times, wl.data, wl.modes, wl.Mf, wl.chif, wl.t0_array,
+                               T_array=wl.T, spherical_modes=wl.spherical_modes)
+    want = orc.mismatch_t0_array(oracle_tables, wl.times, wl.data, wl.modes, wl.Mf, wl.chif,
+                                 wl.t0_array, T_array=wl.T, spherical_modes=wl.spherical_modes)
+    np.testing.assert_allclose(got, want, rtol=0, atol=MM_TOL)
+
+
+def test_errors_are_reported_not_swallowed(qf, eng):
+    import torch
+    b = eng.make_batch(times_d=eng.empty((4,), torch.float64), data_d=eng.empty((1, 4), torch.complex128),
+                       n_fits=1, n_modes=99, row_begin_all=0, row_end_all=4,
+                       mismatch_d=eng.empty((1,), torch.float64))
+    with pytest.raises(_cabi.QnmfitError) as e:
+        eng.fit(b)
+    assert e.value.code == -2 and "n_modes" in str(e.value)
+    with pytest.raises(ValueError):
+        qf.ringdown_fit(np.linspace(0, 1, 5), np.ones(5, complex), [(2, 2, 0, 1)], 1.0, 0.5, 0.0,
+                        t0_method="nearest")

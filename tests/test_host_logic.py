@@ -1,0 +1,90 @@
+"""Host logic of the public API that needs no GPU: windows, delta, errors, no fallback."""
+import numpy as np
+import pytest
+
+from qnmfits_b200 import qnmfits as api
+from qnmfits_b200 import _dist, _engine, _cabi
+
+
+def test_window_rows_equal_reference_mask():
+    times = np.arange(-500, 1501) * 0.1
+    rng = np.random.default_rng(0)
+    for t0, T in zip(rng.uniform(-20, 80, 200), rng.uniform(1, 120, 200)):
+        mask = (times >= t0) & (times < t0 + T)
+        idx = np.nonzero(mask)[0]
+        b, e = api._window_rows(times, t0, T, 'geq')
+        assert (b, e) == (idx[0], idx[-1] + 1)
+        s = api._window(times, t0, T, 'closest')
+        assert api._window_rows(times, t0, T, 'closest') == (s.start, max(s.stop, s.start))
+    # exact hits on samples
+    assert api._window_rows(times, times[600], 10.0, 'geq')[0] == 600
+
+
+def test_bad_arguments_raise_value_error():
+    times = np.linspace(0, 10, 11)
+    with pytest.raises(ValueError):
+        api._window(times, 0, 1, 'nearest')
+    with pytest.raises(ValueError):
+        api._delta_factor([0.1, 0.2], 3)
+    with pytest.raises(ValueError):
+        api._delta_factor("x", 3)
+    assert api._delta_factor(0, 3) == 1.0
+    assert np.array_equal(api._delta_factor([0.0, 0.5], 2), np.array([1.0, 1.5]))
+    with pytest.raises(ValueError):
+        api._check_modes([(2, 2, 0)])
+
+
+def test_nominal_step_detection():
+    t = np.arange(-500, 1501) * 0.1
+    assert abs(_engine.nominal_step(t, 2.0) - 0.1) < 1e-12
+    assert _engine.nominal_step(np.sort(np.random.default_rng(0).random(100)), 2.0) == 0.0
+    assert _engine.nominal_step(np.array([0.0, 1.0]), 1.0) == 0.0
+
+
+def test_rank_and_min_norm_completion_match_numpy():
+    """Host completion for rank-deficient fits reproduces numpy.linalg.lstsq from the
+    triangular factor alone."""
+    rng = np.random.default_rng(1)
+    M, N = 200, 5
+    A = rng.normal(size=(M, N)) + 1j * rng.normal(size=(M, N))
+    A[:, 4] = A[:, 1]                     # exactly duplicated column
+    b = rng.normal(size=M) + 1j * rng.normal(size=M)
+    Q, R = np.linalg.qr(A)
+    Rfull = np.concatenate([R, (Q.conj().T @ b)[:, None]], axis=1)
+    x, res, rank, s = np.linalg.lstsq(A, b, rcond=None)
+    rk, sv = api._rank_and_singular_values(Rfull, M)
+    assert rk == rank == 4
+    np.testing.assert_allclose(sv, s, rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(api._minimum_norm_from_factor(Rfull, M), x, rtol=1e-10, atol=1e-12)
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 7, 1000, 65536):
+        for ws in (1, 2, 3, 8):
+            spans = [_dist.shard_bounds(n, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for a, b in zip(spans, spans[1:]):
+                assert a[1] == b[0]
+            assert all(hi - lo <= per for lo, hi, per in spans)
+
+
+def test_no_cpu_fallback_without_gpu(qf):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from qnmfits_b200 import workloads
+    wl = workloads.config1()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        qf.ringdown_fit(wl.times, wl.data, wl.modes, 0.95, 0.69, 0.0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        qf.mismatch_M_chi_grid(wl.times, wl.data, wl.modes, (0.9, 1.0), (0.6, 0.7), 0.0, res=4)
+
+
+def test_dynamic_spectrum_is_not_implemented(qf):
+    t = np.linspace(0, 10, 101)
+    with pytest.raises(NotImplementedError):
+        qf.mismatch_t0_array(t, np.ones(101, complex), [(2, 2, 0, 1)], np.ones(101), 0.7, [0.0])
+
+
+def test_flops_formula():
+    assert abs(_cabi.flops_per_fit(1000, 8) - 770378.67) < 1.0

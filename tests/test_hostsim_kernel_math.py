@@ -1,0 +1,151 @@
+"""CPU check of the K1 kernel's arithmetic: tests/hostsim compiles the device code of
+csrc/fit_small.cuh for the host and steps the lanes in the kernel's order.  Compared
+with the oracle (numpy lstsq) on the golden cases.  (The CUDA build itself is checked
+by the -m gpu tests.)"""
+import numpy as np
+import pytest
+
+import cases
+import hostsim_driver as hs
+from oracle import qnmfits_oracle as orc
+from qnmfits_b200 import qnmfits as api
+from qnmfits_b200 import workloads
+
+
+def _single(qf, wl, kw, lpf, **extra):
+    kw = dict(kw)
+    modes = kw.pop("modes")
+    Mf, chif, t0 = kw.pop("Mf"), kw.pop("chif"), kw.pop("t0")
+    T = kw.pop("T", 100)
+    method = kw.pop("t0_method", "geq")
+    delta = kw.pop("delta", 0.0)
+    sel = api._window(wl.times, t0, T, method)
+    tm, dm = wl.times[sel], wl.data[sel]
+    freq = api._delta_factor(delta, len(modes)) * np.array(qf.qnm.omega_list(modes, chif, Mf))
+    return hs.run(tm, dm, n_fits=1, n_modes=len(modes), window=(0, len(tm)), t0=t0, lpf=lpf,
+                  omega=freq.reshape(1, -1), omega_shared=True, **extra), freq
+
+
+@pytest.mark.parametrize("lpf", [1, 4, 32])
+def test_single_fit_cases_vs_golden(qf, golden, lpf):
+    g = golden("cfg1")
+    wl, cs = cases.cfg1_cases()
+    for name, kw in cs.items():
+        if len(kw["modes"]) > 8 or name == "duplicate_label":
+            continue
+        out, freq = _single(qf, wl, kw, lpf)
+        C_ref, s = g[name + "__C"], g[name + "__s"]
+        assert np.array_equal(freq, g[name + "__frequencies"]), name
+        err = np.max(np.abs(out["C"][0] - C_ref)) / np.max(np.abs(C_ref))
+        assert err < cases.amp_tol(s), (name, err)
+        assert abs(out["mismatch"][0] - float(g[name + "__mismatch"])) < 1e-10, name
+        assert out["status"][0] == 0
+        np.testing.assert_allclose(out["residual"][0], g[name + "__residual"][0], rtol=1e-9)
+        sv = np.linalg.svd(out["R"][0][:, :len(s)], compute_uv=False)
+        np.testing.assert_allclose(sv, s, rtol=1e-9)
+
+
+def test_model_output_and_eval_only(qf, golden):
+    g = golden("cfg1")
+    wl, cs = cases.cfg1_cases()
+    out, freq = _single(qf, wl, cs["offgrid_geq"], 8, want_model=True)
+    M = len(g["offgrid_geq__model"])
+    np.testing.assert_allclose(out["model"][0][:M], g["offgrid_geq__model"], rtol=0,
+                               atol=1e-9 * np.max(np.abs(g["offgrid_geq__model"])))
+    # eval-only with the reference's amplitudes reproduces its mismatch
+    sel = api._window(wl.times, 3.37, 77.7, "geq")
+    ev = hs.run(wl.times[sel], wl.data[sel], n_fits=1, n_modes=8, window=(0, M), t0=3.37, lpf=4,
+                omega=freq.reshape(1, -1), omega_shared=True, eval_only=True,
+                C_in=g["offgrid_geq__C"].reshape(1, -1))
+    assert abs(ev["mismatch"][0] - float(g["offgrid_geq__mismatch"])) < 1e-13
+
+
+def test_direct_mode_on_nonuniform_grid(qf, golden):
+    g = golden("nonuniform")
+    t, d = g["times"], g["data"]
+    modes = workloads.overtone_modes(5)
+    sel = api._window(t, 1.0, 60, "geq")
+    freq = np.array(qf.qnm.omega_list(modes, 0.69, 0.95))
+    out = hs.run(t[sel], d[sel], n_fits=1, n_modes=5, window=(0, int(sel.sum())), t0=1.0, lpf=8,
+                 omega=freq.reshape(1, -1), omega_shared=True)
+    assert out["dt"] == 0.0            # direct evaluation selected
+    assert cases.rel_err(out["C"][0], g["fit__C"]) < 1e-8
+    assert abs(out["mismatch"][0] - float(g["fit__mismatch"])) < 1e-10
+
+
+def test_recurrence_needs_the_jitter_correction(qf, golden):
+    """np.arange(n)*0.1 is not bit-uniform; anchors + first-order correction keep the
+    generated rows within ~1e-15 of direct evaluation regardless of anchor spacing."""
+    g = golden("cfg1")
+    wl, cs = cases.cfg1_cases()
+    ref_direct, _ = _single(qf, wl, cs["base"], 4, dt=0.0)
+    for anchor in (8, 32, 128):
+        out, _ = _single(qf, wl, cs["base"], 4, anchor_rows=anchor)
+        err = np.max(np.abs(out["C"][0] - ref_direct["C"][0])) / np.max(np.abs(ref_direct["C"][0]))
+        assert err < 2e-9, (anchor, err)
+
+
+def test_t0_sweep_vs_golden(qf, golden):
+    g = golden("cfg2")
+    wl = workloads.config2(n_t0=40)
+    begin = np.empty(40, np.int32)
+    end = np.empty(40, np.int32)
+    for i, t0 in enumerate(wl.t0_array):
+        begin[i], end[i] = api._window_rows(wl.times, t0, 100.0, "geq")
+    freq = np.array(qf.qnm.omega_list(wl.modes, 0.95, 0.69)).reshape(1, -1)
+    freq = np.array(qf.qnm.omega_list(wl.modes, 0.69, 0.95)).reshape(1, -1)
+    for lpf in (2, 16):
+        out = hs.run(wl.times, wl.data, n_fits=40, n_modes=8, window=(begin, end), t0=wl.t0_array,
+                     lpf=lpf, omega=freq, omega_shared=True)
+        np.testing.assert_allclose(out["mismatch"], g["mismatch"], rtol=0, atol=1e-10)
+
+
+def test_grid_vs_golden_and_sharding_invariance(qf, golden):
+    g = golden("cfg3")
+    wl = workloads.config3(res=12)
+    Mf = np.linspace(0.85, 1.05, 12)
+    chi = np.linspace(0.59, 0.79, 12)
+    table, ptr = qf.qnm.constituent_table(wl.modes, chi)
+    win = api._window_rows(wl.times, 0.0, 100, "geq")
+    common = dict(n_modes=8, window=win, t0=0.0, table=table, mode_ptr=ptr, inv_Mf=1.0 / Mf,
+                  n_chi=12, n_mf=12)
+    full = hs.run(wl.times, wl.data, n_fits=144, lpf=4, **common)
+    np.testing.assert_allclose(full["mismatch"].reshape(12, 12), g["grid"], rtol=0, atol=1e-10)
+    # two slabs (as two ranks would compute them) are bit-identical to the full launch
+    a = hs.run(wl.times, wl.data, n_fits=72, first_fit=0, lpf=4, **common)
+    b = hs.run(wl.times, wl.data, n_fits=72, first_fit=72, lpf=4, **common)
+    assert np.array_equal(np.concatenate([a["mismatch"], b["mismatch"]]), full["mismatch"])
+
+
+def test_grid_with_quadratic_mode_and_delta(qf, golden):
+    g = golden("cfg3")
+    wl = workloads.config3(res=5)
+    modes = [(2, 2, 0, 1), (2, 2, 1, 1), (2, 2, 0, 1, 2, 2, 0, 1)]
+    Mf = np.linspace(0.85, 1.05, 5)
+    chi = np.linspace(0.59, 0.79, 5)
+    table, ptr = qf.qnm.constituent_table(modes, chi)
+    win = api._window_rows(wl.times, 15.0, 60, "geq")
+    out = hs.run(wl.times, wl.data, n_fits=25, n_modes=3, window=win, t0=15.0, lpf=8, table=table,
+                 mode_ptr=ptr, inv_Mf=1.0 / Mf, n_chi=5, n_mf=5,
+                 delta_factor=np.array([1.0, 1.01, 1.0]))
+    np.testing.assert_allclose(out["mismatch"].reshape(5, 5), g["grid_quadratic"], rtol=0,
+                               atol=1e-10)
+
+
+def test_ragged_and_tiny_windows(qf, oracle_tables):
+    """Windows that are not multiples of the block size, shorter than the lanes, and
+    barely overdetermined."""
+    wl = workloads.config1()
+    modes = wl.modes[:3]
+    freq = np.array(qf.qnm.omega_list(modes, 0.69, 0.95)).reshape(1, -1)
+    for M in (4, 5, 7, 33, 127):
+        for lpf in (1, 8, 32):
+            out = hs.run(wl.times, wl.data, n_fits=1, n_modes=3, window=(500, 500 + M), t0=0.0,
+                         lpf=lpf, omega=freq, omega_shared=True)
+            want = orc.ringdown_fit(oracle_tables, wl.times, wl.data, modes, 0.95, 0.69, 0.0,
+                                    T=wl.times[500 + M - 1] + 0.05)
+            assert len(want["model_times"]) == M
+            tol = cases.amp_tol(want["s"])
+            err = np.max(np.abs(out["C"][0] - want["C"])) / np.max(np.abs(want["C"]))
+            assert err < tol, (M, lpf, err)
+            assert abs(out["mismatch"][0] - want["mismatch"]) < 1e-10, (M, lpf)
