@@ -272,7 +272,8 @@ def run_gpu_arm(args):
 
     # ---- roofline ------------------------------------------------------------------
     rows = sweep.rows_max
-    flops_fit = _cabi.flops_per_fit(rows, len(wl.modes))
+    flops_fit = _cabi.flops_per_fit(rows, len(wl.modes), 1, bool(plan.fast_mismatch))
+    flops_fit_8d = _cabi.flops_per_fit(rows, len(wl.modes))
     fits_per_launch = sweep.hi - sweep.lo
     achieved = fits_per_launch * flops_fit / (kernel_ms * 1e-3) * 1e-12
     peak_dfma = eng.ctx.fp64_peak(0, 2048)
@@ -291,6 +292,10 @@ def run_gpu_arm(args):
         "peak_source": "measured live: dependent-free DFMA loop on all SMs (qnmfit_fp64_peak); "
                        "MEASURED_PEAKS.json has no FP64 entry; nominal 37.2 TFLOP/s",
         "dmma_peak": peak_dmma, "flops_per_fit": flops_fit, "fits_per_launch": fits_per_launch,
+        "flops_note": ("flops_per_fit counts what the launched algorithm needs (fast_mismatch: no "
+                       "model pass); frac_survey_8d uses SURVEY.md 8d's F(M,N) incl. model + "
+                       "trapezoid sums, which this path does not execute"),
+        "frac_survey_8d": fits_per_launch * flops_fit_8d / (kernel_ms * 1e-3) * 1e-12 / peak_dfma,
         "kernel_ms": kernel_ms,
         "hbm": {"algorithmic_bytes_per_launch": alg_bytes,
                 "achieved_gbs": alg_bytes / (kernel_ms * 1e-3) * 1e-9, "peak_gbs": hbm_peak,
@@ -310,7 +315,8 @@ def run_gpu_arm(args):
                        "kernel": {"id": plan.kernel, "lanes_per_fit": plan.lanes_per_fit,
                                   "grid": plan.grid, "block": plan.block,
                                   "smem_bytes": plan.smem_bytes, "regs": plan.regs_per_thread,
-                                  "staged": bool(plan.staged)}},
+                                  "staged": bool(plan.staged),
+                                  "fast_mismatch": bool(plan.fast_mismatch)}},
             "e2e": {"value": n_fits / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
                     "api": "qnmfits_b200.mismatch_M_chi_grid(host numpy arrays)"},

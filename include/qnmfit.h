@@ -114,7 +114,7 @@ typedef struct qnmfit_batch {
 
     /* ---- design-matrix generator ---- */
     int32_t anchor_rows;      /* direct cexp every this many rows (multiple of 4);
-                                 0 -> library default (32)                             */
+                                 0 -> library default (64)                             */
     double  dt_nominal;       /* > 0: nearly uniform grid, rows advance by the
                                  recurrence z *= exp(-i w dt) with first-order
                                  correction for the deviation of each sample from the
@@ -132,6 +132,16 @@ typedef struct qnmfit_batch {
     double  *model;           /* c128[B][model_stride]: best-fit model, series-major
                                  ((i, k) -> i*rows + k, rows = the fit's window length)  */
     int64_t model_stride;     /* complex elements between consecutive fits in model    */
+
+    /* ---- mismatch quadrature ---- */
+    int32_t uniform_weights;  /* 1: the caller guarantees that every step of the window
+                                 deviates from dt_nominal by < 1e-11 relative, so the
+                                 trapezoid weights are uniform to that level; K1 may then
+                                 take the mismatch from by-products of the factorisation
+                                 (||Q^H d||^2, ||d||^2, the two end rows) instead of a
+                                 second pass over the rows.  0: always the general
+                                 weighted second pass.                                  */
+    int32_t reserved1;
 } qnmfit_batch;
 
 /* Create / destroy a context bound to one CUDA device (one process per GPU). */
@@ -162,7 +172,7 @@ typedef struct qnmfit_plan {
     int32_t smem_bytes;
     int32_t regs_per_thread;
     int32_t staged;           /* waveform window staged in shared memory */
-    int32_t reserved;
+    int32_t fast_mismatch;    /* mismatch from factorisation by-products (no 2nd pass) */
 } qnmfit_plan;
 int qnmfit_plan_batch(qnmfit_ctx *ctx, const qnmfit_batch *b, qnmfit_plan *plan);
 
@@ -170,9 +180,14 @@ int qnmfit_plan_batch(qnmfit_ctx *ctx, const qnmfit_batch *b, qnmfit_plan *plan)
  * kind 1 = DMMA m8n8k4 (tensor pipe).  Writes TFLOP/s (2 flops per FMA). */
 int qnmfit_fp64_peak(qnmfit_ctx *ctx, int kind, int iters, double *tflops);
 
-/* Algorithmic FP64 flops credited to one fit (DESIGN.md "flop accounting"):
- * F = 8 M N^2 + 30 M N + 20 M - (8/3) N^3 - 4 N^2 with M = n_series * rows. */
-double qnmfit_flops_per_fit(int rows, int n_modes, int n_series);
+/* Algorithmic FP64 flops credited to one fit (DESIGN.md "flop accounting"), with
+ * M = n_series * rows:
+ *   fast_mismatch = 0:  F = 8 M N^2 + 30 M N + 20 M - (8/3) N^3 - 4 N^2
+ *                       (QR, Q^H d, back-substitution, row generation, model, three
+ *                        trapezoid inner products — SURVEY.md section 8d);
+ *   fast_mismatch = 1:  F = 8 M N^2 + 22 M N + 4 M - (8/3) N^3 - 4 N^2 + 28 N
+ *                       (no model pass: ||d||^2 and two end rows instead). */
+double qnmfit_flops_per_fit(int rows, int n_modes, int n_series, int fast_mismatch);
 
 int qnmfit_abi_version(void);
 

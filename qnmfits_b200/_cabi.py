@@ -43,6 +43,7 @@ class Batch(C.Structure):
         ("C", _dp),
         ("mismatch", _dp), ("residual", _dp), ("R", _dp), ("status", _dp),
         ("model", _dp), ("model_stride", C.c_int64),
+        ("uniform_weights", C.c_int32), ("reserved1", C.c_int32),
     ]
 
     def __init__(self, **kw):
@@ -55,7 +56,7 @@ class Plan(C.Structure):
         ("kernel", C.c_int32), ("lanes_per_fit", C.c_int32),
         ("grid", C.c_int32), ("block", C.c_int32),
         ("smem_bytes", C.c_int32), ("regs_per_thread", C.c_int32),
-        ("staged", C.c_int32), ("reserved", C.c_int32),
+        ("staged", C.c_int32), ("fast_mismatch", C.c_int32),
     ]
 
 
@@ -103,7 +104,7 @@ def load_library(path=None):
     lib.qnmfit_plan_batch.restype = C.c_int
     lib.qnmfit_fp64_peak.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
     lib.qnmfit_fp64_peak.restype = C.c_int
-    lib.qnmfit_flops_per_fit.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.qnmfit_flops_per_fit.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     lib.qnmfit_flops_per_fit.restype = C.c_double
     if lib.qnmfit_abi_version() != ABI_VERSION:
         raise ImportError(
@@ -160,7 +161,9 @@ class Context:
             pass
 
 
-def flops_per_fit(rows, n_modes, n_series=1):
-    """Algorithmic FP64 flops credited to one fit (same formula as the C library)."""
+def flops_per_fit(rows, n_modes, n_series=1, fast_mismatch=False):
+    """Algorithmic FP64 flops credited to one fit (same formulas as the C library)."""
     M, N = float(rows) * n_series, float(n_modes)
+    if fast_mismatch:
+        return 8 * M * N * N + 22 * M * N + 4 * M - (8.0 / 3.0) * N ** 3 - 4 * N * N + 28 * N
     return 8 * M * N * N + 30 * M * N + 20 * M - (8.0 / 3.0) * N ** 3 - 4 * N * N

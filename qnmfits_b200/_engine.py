@@ -50,6 +50,16 @@ def nominal_step(times, wmax):
     return 0.0
 
 
+def uniform_weights(times, dt):
+    """True when every step is within 1e-11 (relative) of ``dt``: the trapezoid weights
+    are then uniform to 1e-11 and K1 may take the mismatch from by-products of the
+    factorisation instead of a weighted second pass (changes it by < 1e-11)."""
+    times = np.asarray(times, dtype=float)
+    if not dt > 0.0 or times.size < 3:
+        return False
+    return bool(np.max(np.abs(np.diff(times) - dt)) <= 1e-11 * dt)
+
+
 class Engine:
     def __init__(self, device):
         import torch
@@ -92,7 +102,7 @@ class Engine:
                    coef_d=None, coef_index_d=None, n_coef=0,
                    dt_nominal=0.0, anchor_rows=0, kernel=_cabi.KERNEL_AUTO,
                    C_d=None, mismatch_d=None, residual_d=None, R_d=None, status_d=None,
-                   model_d=None, model_stride=0):
+                   model_d=None, model_stride=0, uniform_weights=False):
         def p(t):
             return None if t is None else t.data_ptr()
         n_times = int(times_d.numel())
@@ -109,7 +119,8 @@ class Engine:
             coef=p(coef_d), coef_index=p(coef_index_d), n_coef=int(n_coef),
             dt_nominal=float(dt_nominal), anchor_rows=int(anchor_rows),
             C=p(C_d), mismatch=p(mismatch_d), residual=p(residual_d), R=p(R_d),
-            status=p(status_d), model=p(model_d), model_stride=int(model_stride))
+            status=p(status_d), model=p(model_d), model_stride=int(model_stride),
+            uniform_weights=1 if uniform_weights else 0)
         return b
 
     def fit(self, batch):

@@ -134,9 +134,11 @@ extern "C" const char *qnmfit_last_error(const qnmfit_ctx *ctx) { return ctx ? c
 
 extern "C" int64_t qnmfit_launch_count(const qnmfit_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
-extern "C" double qnmfit_flops_per_fit(int rows, int n_modes, int n_series)
+extern "C" double qnmfit_flops_per_fit(int rows, int n_modes, int n_series, int fast_mismatch)
 {
     const double M = (double)rows * (double)n_series, N = (double)n_modes;
+    if (fast_mismatch)
+        return 8.0 * M * N * N + 22.0 * M * N + 4.0 * M - (8.0 / 3.0) * N * N * N - 4.0 * N * N + 28.0 * N;
     return 8.0 * M * N * N + 30.0 * M * N + 20.0 * M - (8.0 / 3.0) * N * N * N - 4.0 * N * N;
 }
 
@@ -265,12 +267,13 @@ static void fill_params(const qnmfit_batch *b, const Plan &pl, bool eval, FitPar
     p->mf_index = b->mf_index; p->n_chi = b->n_chi > 0 ? b->n_chi : 1; p->n_mf = b->n_mf;
     p->n_constituents = b->n_constituents;
     p->coef = (const double2 *)b->coef; p->coef_index = b->coef_index; p->n_coef = b->n_coef;
-    p->anchor_rows = b->anchor_rows > 0 ? b->anchor_rows : 32;
+    p->anchor_rows = b->anchor_rows > 0 ? b->anchor_rows : 64;
     p->dt_nominal = b->dt_nominal;
     p->C = (double2 *)b->C; p->mismatch = b->mismatch; p->residual = b->residual;
     p->R = (double2 *)b->R; p->status = b->status;
     p->model = (double2 *)b->model; p->model_stride = b->model_stride; p->omega_shared = b->omega_shared;
     p->lanes_per_fit = pl.lpf; p->eval_only = eval ? 1 : 0;
+    p->fast_mismatch = (pl.kernel == QNMFIT_KERNEL_SMALL && !eval && b->uniform_weights && b->dt_nominal > 0.0 && !b->model) ? 1 : 0;
     p->stage_begin = pl.stage_begin; p->stage_rows = pl.stage_rows;
 }
 
@@ -318,6 +321,7 @@ extern "C" int qnmfit_plan_batch(qnmfit_ctx *ctx, const qnmfit_batch *b, qnmfit_
     memset(out, 0, sizeof(*out));
     out->kernel = pl.kernel; out->lanes_per_fit = pl.lpf; out->grid = pl.grid; out->block = pl.block;
     out->smem_bytes = (int32_t)pl.smem; out->staged = pl.staged ? 1 : 0;
+    out->fast_mismatch = (pl.kernel == QNMFIT_KERNEL_SMALL && b->uniform_weights && b->dt_nominal > 0.0 && !b->model) ? 1 : 0;
     cudaFuncAttributes fa;
     const void *fn = pl.kernel == QNMFIT_KERNEL_SMALL ? (const void *)small_kernel(b->n_modes, pl.staged)
                                                       : (const void *)fit_general_kernel;

@@ -144,6 +144,7 @@ struct FitParams {
     // launch-time choices
     int lanes_per_fit;   // K1: power of two, 1..32
     int eval_only;       // 1: skip the solve, read C
+    int fast_mismatch;   // K1: mismatch from QR by-products (uniform grid, no model output)
     int stage_begin;     // K1 staged variant: first staged row
     int stage_rows;      //                    number of staged rows
 };

@@ -25,7 +25,7 @@ Deliberate supersets of the reference (documented in DESIGN.md):
 import numpy as np
 
 from . import _cabi, _dist
-from ._engine import get_engine, nominal_step
+from ._engine import get_engine, nominal_step, uniform_weights
 from .qnm import qnm as _qnm_class
 
 # Module-level provider *instance* that shadows the class, exactly like the
@@ -389,13 +389,14 @@ class _Sweep:
         self.st_d = torch.zeros((max(per, 1),), dtype=torch.int32, device=eng.device)
         self.mm_all, self.st_all = self.mm_d[:n_fits], self.st_d[:n_fits]
         self.batch = None
+        dt = nominal_step(times[rb_all:re_all], wmax)
         if n_local > 0:
             self.batch = eng.make_batch(
                 times_d=times_d, data_d=data_d, n_fits=n_local, n_modes=n_modes, n_series=L,
                 first_fit=lo, row_begin_all=rb_all, row_end_all=re_all, t0_all=t0_all,
                 row_begin_d=rb_d, row_end_d=re_d, t0_d=t0_d,
                 coef_d=coef_d, coef_index_d=coef_index_d, n_coef=n_coef,
-                dt_nominal=nominal_step(times[rb_all:re_all], wmax),
+                dt_nominal=dt, uniform_weights=uniform_weights(times[rb_all:re_all], dt),
                 mismatch_d=self.mm_d, status_d=self.st_d, **kw)
         # keep every device buffer alive as long as the descriptor
         self._keep = (times_d, data_d, rb_d, re_d, t0_d, kw, coef_d, coef_index_d)

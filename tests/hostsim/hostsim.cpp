@@ -28,12 +28,13 @@ static void fill_params(const qnmfit_batch *b, int lpf, bool eval, FitParams *p)
     p->inv_Mf = b->inv_Mf; p->delta_factor = b->delta_factor; p->chi_index = b->chi_index;
     p->mf_index = b->mf_index; p->n_chi = b->n_chi > 0 ? b->n_chi : 1; p->n_mf = b->n_mf;
     p->n_constituents = b->n_constituents;
-    p->anchor_rows = b->anchor_rows > 0 ? b->anchor_rows : 32;
+    p->anchor_rows = b->anchor_rows > 0 ? b->anchor_rows : 64;
     p->dt_nominal = b->dt_nominal;
     p->C = (double2 *)b->C; p->mismatch = b->mismatch; p->residual = b->residual;
     p->R = (double2 *)b->R; p->status = b->status;
     p->model = (double2 *)b->model; p->model_stride = b->model_stride; p->omega_shared = b->omega_shared;
     p->lanes_per_fit = lpf; p->eval_only = eval ? 1 : 0;
+    p->fast_mismatch = (!eval && b->uniform_weights && b->dt_nominal > 0.0 && !b->model) ? 1 : 0;
 }
 
 template <int N>
@@ -63,15 +64,42 @@ static void run(const qnmfit_batch *b, int lpf, bool eval)
         }
         std::vector<SmallLane> lanes(HS_THREADS);
         std::vector<int> status(HS_THREADS, 0);
+        std::vector<SmallAcc> acc(HS_THREADS);
+        for (auto &a : acc) a.sdd = a.res2 = a.cn2 = 0.0;
         for (int tid = 0; tid < HS_THREADS; ++tid) {
             lanes[tid] = small_lane_setup(p, cta, tid, HS_THREADS);
             small_clear<N, HS_THREADS>(sm, tid);
         }
         if (!eval) {
-            for (int tid = 0; tid < HS_THREADS; ++tid) small_leaf<N, HS_THREADS>(p, sm, lanes[tid], tid);
+            for (int tid = 0; tid < HS_THREADS; ++tid) small_leaf<N, HS_THREADS>(p, sm, lanes[tid], tid, acc[tid]);
             for (int s = 1; s < lpf; s <<= 1)
-                for (int tid = 0; tid < HS_THREADS; ++tid) small_tree_level<N, HS_THREADS>(p, sm, lanes[tid], tid, s);
-            for (int tid = 0; tid < HS_THREADS; ++tid) small_backsub<N, HS_THREADS>(p, sm, lanes[tid], tid, status[tid]);
+                for (int tid = 0; tid < HS_THREADS; ++tid)
+                    small_tree_level<N, HS_THREADS>(p, sm, lanes[tid], tid, s, acc[tid]);
+            for (int tid = 0; tid < HS_THREADS; ++tid)
+                small_backsub<N, HS_THREADS>(p, sm, lanes[tid], tid, status[tid], acc[tid]);
+        }
+        if (p.fast_mismatch) {
+            std::vector<double> part(HS_THREADS * 6), tmp6(HS_THREADS * 6);
+            for (int tid = 0; tid < HS_THREADS; ++tid) {
+                double p6[6];
+                small_fast_partials<N, HS_THREADS>(p, sm, lanes[tid], tid, acc[tid], p6);
+                for (int q = 0; q < 6; ++q) part[tid * 6 + q] = p6[q];
+            }
+            for (int s = 1; s < lpf; s <<= 1) {   // the __shfl_xor butterfly
+                for (int tid = 0; tid < HS_THREADS; ++tid)
+                    for (int q = 0; q < 6; ++q) tmp6[tid * 6 + q] = part[tid * 6 + q] + part[(tid ^ s) * 6 + q];
+                part.swap(tmp6);
+            }
+            for (int tid = 0; tid < HS_THREADS; ++tid) {
+                const SmallLane &L = lanes[tid];
+                if (L.fit >= 0 && L.lf == 0 && L.re > L.rb) {
+                    double p6[6];
+                    for (int q = 0; q < 6; ++q) p6[q] = part[tid * 6 + q];
+                    small_fast_finalize(p, L, sm.ds[L.rb - sm.t_off], sm.ds[L.re - 1 - sm.t_off], p6, acc[tid].cn2,
+                                        status[tid]);
+                }
+            }
+            continue;
         }
         std::vector<double> sums(HS_THREADS * 4), tmp(HS_THREADS * 4);
         for (int tid = 0; tid < HS_THREADS; ++tid) {

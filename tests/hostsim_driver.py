@@ -26,7 +26,8 @@ def _p(a):
 
 def run(times, data, *, n_fits, n_modes, window, t0, lpf=4, eval_only=False, dt=None,
         anchor_rows=0, omega=None, omega_shared=False, table=None, mode_ptr=None, inv_Mf=None,
-        delta_factor=None, n_chi=0, n_mf=0, first_fit=0, C_in=None, want_model=False):
+        delta_factor=None, n_chi=0, n_mf=0, first_fit=0, C_in=None, want_model=False,
+        uniform_weights=0):
     times = np.ascontiguousarray(times, dtype=float)
     data = np.ascontiguousarray(data, dtype=complex)
     keep = [times, data]
@@ -76,7 +77,7 @@ def run(times, data, *, n_fits, n_modes, window, t0, lpf=4, eval_only=False, dt=
                     series_stride=len(times), first_fit=first_fit, times=_p(times), data=_p(data),
                     dt_nominal=float(dt), anchor_rows=anchor_rows, C=_p(Cbuf), mismatch=_p(mm),
                     residual=_p(res), R=_p(R), status=_p(st), model=_p(model),
-                    model_stride=Mmax if want_model else 0, **kw)
+                    model_stride=Mmax if want_model else 0, uniform_weights=int(uniform_weights), **kw)
     rc = lib().hostsim_fit_small(C.byref(b), int(lpf), 1 if eval_only else 0)
     assert rc == 0, rc
     return dict(C=Cbuf, mismatch=mm, residual=res, R=R, status=st, model=model, dt=dt)

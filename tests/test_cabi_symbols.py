@@ -43,4 +43,6 @@ def test_create_fails_loudly_without_device():
 def test_flops_entry_point_matches_python():
     lib = _cabi.load_library()
     for rows, n, l in ((1000, 8, 1), (1000, 40, 21), (37, 3, 1)):
-        assert abs(lib.qnmfit_flops_per_fit(rows, n, l) - _cabi.flops_per_fit(rows, n, l)) < 1e-6
+        for fast in (0, 1):
+            assert abs(lib.qnmfit_flops_per_fit(rows, n, l, fast)
+                       - _cabi.flops_per_fit(rows, n, l, bool(fast))) < 1e-6

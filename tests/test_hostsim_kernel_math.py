@@ -149,3 +149,34 @@ def test_ragged_and_tiny_windows(qf, oracle_tables):
             err = np.max(np.abs(out["C"][0] - want["C"])) / np.max(np.abs(want["C"]))
             assert err < tol, (M, lpf, err)
             assert abs(out["mismatch"][0] - want["mismatch"]) < 1e-10, (M, lpf)
+
+
+def test_fast_mismatch_path_equals_general_path(qf, golden):
+    """uniform_weights=1: mismatch and residual from the by-products of the
+    factorisation (no second pass) agree with the weighted second pass and with the
+    reference to 1e-10, for full grids, ragged t0 windows and every lanes-per-fit."""
+    g2, g3 = golden("cfg2"), golden("cfg3")
+    wl = workloads.config3(res=12)
+    Mf = np.linspace(0.85, 1.05, 12)
+    chi = np.linspace(0.59, 0.79, 12)
+    table, ptr = qf.qnm.constituent_table(wl.modes, chi)
+    win = api._window_rows(wl.times, 0.0, 100, "geq")
+    common = dict(n_fits=144, n_modes=8, window=win, t0=0.0, table=table, mode_ptr=ptr,
+                  inv_Mf=1.0 / Mf, n_chi=12, n_mf=12)
+    slow = hs.run(wl.times, wl.data, lpf=4, uniform_weights=0, **common)
+    for lpf in (1, 4, 16):
+        fast = hs.run(wl.times, wl.data, lpf=lpf, uniform_weights=1, **common)
+        np.testing.assert_allclose(fast["mismatch"].reshape(12, 12), g3["grid"], rtol=0, atol=1e-10)
+        np.testing.assert_allclose(fast["mismatch"], slow["mismatch"], rtol=0, atol=1e-13)
+        np.testing.assert_allclose(fast["residual"], slow["residual"], rtol=1e-9)
+        assert np.array_equal(fast["C"], hs.run(wl.times, wl.data, lpf=lpf, uniform_weights=0,
+                                                **common)["C"])
+    wl2 = workloads.config2(n_t0=40)
+    begin = np.empty(40, np.int32)
+    end = np.empty(40, np.int32)
+    for i, t0 in enumerate(wl2.t0_array):
+        begin[i], end[i] = api._window_rows(wl2.times, t0, 100.0, "geq")
+    freq = np.array(qf.qnm.omega_list(wl2.modes, 0.69, 0.95)).reshape(1, -1)
+    fast = hs.run(wl2.times, wl2.data, n_fits=40, n_modes=8, window=(begin, end), t0=wl2.t0_array,
+                  lpf=8, omega=freq, omega_shared=True, uniform_weights=1)
+    np.testing.assert_allclose(fast["mismatch"], g2["mismatch"], rtol=0, atol=1e-10)
