@@ -176,8 +176,10 @@ typedef struct qnmfit_plan {
 } qnmfit_plan;
 int qnmfit_plan_batch(qnmfit_ctx *ctx, const qnmfit_batch *b, qnmfit_plan *plan);
 
-/* FP64 peak micro-benchmark on the ctx's device: kind 0 = DFMA (vector pipe),
- * kind 1 = DMMA m8n8k4 (tensor pipe).  Writes TFLOP/s (2 flops per FMA). */
+/* FP64 peak micro-benchmarks on the ctx's device.  kind 0 = DFMA, operands mostly from
+ * the reuse cache (vector pipe peak); 1 = DMMA m8n8k4 (tensor pipe); 2 = DFMA with three
+ * distinct register operands per instruction (register-file read bound); 3 = DFMA with
+ * two register reads + one reused operand.  Writes TFLOP/s (2 flops per FMA). */
 int qnmfit_fp64_peak(qnmfit_ctx *ctx, int kind, int iters, double *tflops);
 
 /* Algorithmic FP64 flops credited to one fit (DESIGN.md "flop accounting"), with

@@ -29,6 +29,12 @@
 #pragma once
 #include "qnmfit_common.cuh"
 
+// Columns left (N - j) at or below which the reflector dot products are accumulated
+// as two partial sums (more independent FMA chains when few columns remain).
+#ifndef QNMFIT_SPLIT_COLS
+#define QNMFIT_SPLIT_COLS 0   /* measured on B200: splitting costs registers and is slower */
+#endif
+
 template <int N>
 struct SmallLayout {
     static constexpr int MB = 4;                      // rows per register block
@@ -151,6 +157,7 @@ QF_HD void small_emit(const FitParams &p, const SmallSmem<N, THREADS> &sm, const
             const double eps_n = fma(-(double)g.n, p.dt_nominal, tau_n - g.tau_a);
             const double de = eps_n - g.eps;
             g.eps = eps_n;
+#ifndef QNMFIT_ABL_NOGEN
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 const double2 q = sm.qq[j * sm.fpc + L.slot];
@@ -158,6 +165,9 @@ QF_HD void small_emit(const FitParams &p, const SmallSmem<N, THREADS> &sm, const
                 const double2 qe = make_double2(fma(w.x, de, q.x), fma(w.y, de, q.y));
                 g.z[j] = c_mul(g.z[j], qe);
             }
+#else
+            g.z[0].x += de;
+#endif
         }
     }
 }
@@ -199,13 +209,21 @@ QF_HD void small_absorb(double2 (&B)[4][N + 1], double *Rd, double2 *Ro)
         // norm of the stacked column; a column that is negligible down to the
         // underflow range is left alone (H = I) and shows up as a zero pivot.
         const bool ok = t > 1e-280;
+#ifdef QNMFIT_ABL_NOSCALAR
+        const double y = 1.0;
+#else
         const double y = qf_rsqrt(ok ? t : 1.0);
+#endif
         const double nrm = ok ? t * y : 0.0;
         const double ar = fabs(r);
         const double v0 = copysign(ar + nrm, r);          // v = [v0; b]
         const double den = nrm * (ar + nrm);              // v^H v / 2
+#ifdef QNMFIT_ABL_NOSCALAR
+        const double beta = ok ? den : 0.0;
+#else
         const double beta = ok ? qf_rcp(den) : 0.0;
-        if (ok) Rd[j * THREADS] = -copysign(nrm, r);
+#endif
+        Rd[j * THREADS] = ok ? -copysign(nrm, r) : r;
 #pragma unroll
         for (int k = j + 1; k <= N; ++k) {
             double2 Rjk = Ro[LY::pair(j, k) * THREADS];
@@ -214,7 +232,7 @@ QF_HD void small_absorb(double2 (&B)[4][N + 1], double *Rd, double2 *Ro)
             // their rsqrt/rcp latency; near the end of the sweep (few columns left = few
             // independent chains) it is split in two partial sums.
             double sr, si;
-            if (N - j <= 4) {
+            if (N - j <= QNMFIT_SPLIT_COLS) {
                 double ar0 = B[0][j].x * B[0][k].x, ai0 = B[0][j].x * B[0][k].y;
                 double ar1 = B[2][j].x * B[2][k].x, ai1 = B[2][j].x * B[2][k].y;
                 ar0 = fma(B[0][j].y, B[0][k].y, ar0); ai0 = fma(-B[0][j].y, B[0][k].x, ai0);

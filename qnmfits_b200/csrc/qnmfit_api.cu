@@ -12,7 +12,9 @@
 #include "fit_small.cuh"
 #include "fit_general.cuh"
 
+#ifndef K1_THREADS
 #define K1_THREADS 256
+#endif
 
 struct qnmfit_ctx {
     int device;
@@ -54,6 +56,7 @@ static small_kernel_t small_kernel_for(bool staged)
 static small_kernel_t small_kernel(int N, bool staged)
 {
     switch (N) {
+#ifndef QNMFIT_ONLY_N8
     case 1: return small_kernel_for<1>(staged);
     case 2: return small_kernel_for<2>(staged);
     case 3: return small_kernel_for<3>(staged);
@@ -61,6 +64,7 @@ static small_kernel_t small_kernel(int N, bool staged)
     case 5: return small_kernel_for<5>(staged);
     case 6: return small_kernel_for<6>(staged);
     case 7: return small_kernel_for<7>(staged);
+#endif
     case 8: return small_kernel_for<8>(staged);
     }
     return nullptr;
@@ -113,6 +117,7 @@ extern "C" int qnmfit_create(int device, qnmfit_ctx **out)
     // opt every kernel in to the full shared-memory carve-out once
     for (int N = 1; N <= QNMFIT_MAX_MODES_SMALL; ++N)
         for (int st = 0; st < 2; ++st) {
+            if (!small_kernel(N, st != 0)) continue;
             e = cudaFuncSetAttribute((const void *)small_kernel(N, st != 0),
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
             if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaFuncSetAttribute(K1)"); delete ctx; return r; }
@@ -216,12 +221,16 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
         double best = 1e300;
         for (int lpf = 1; lpf <= 32; lpf *= 2) {
             const int fpc = K1_THREADS / lpf;
+            // CTAs that may be co-resident on an SM by thread count; staging the window
+            // must not reduce that (8 warps per SM are needed to keep the FP64 pipe fed)
+            const int want_cps = 256 / K1_THREADS > 0 ? 256 / K1_THREADS : 1;
+            const size_t per_cta = ((size_t)ctx->smem_optin + 1024) / want_cps - 1024;
             size_t smem = small_smem_bytes(N, fpc, stage_rows);
             bool staged = true;
-            if (smem > (size_t)ctx->smem_optin) { staged = false; smem = small_smem_bytes(N, fpc, 0); }
-            if (smem > (size_t)ctx->smem_optin) continue;
+            if (smem > per_cta) { staged = false; smem = small_smem_bytes(N, fpc, 0); }
+            if (smem > per_cta) continue;
             const int ctas = (b->n_fits + fpc - 1) / fpc;
-            const int waves = (ctas + ctx->sm_count - 1) / ctx->sm_count;
+            const int waves = (ctas + ctx->sm_count * want_cps - 1) / (ctx->sm_count * want_cps);
             const int rpl = ((Mmax + lpf - 1) / lpf + 3) / 4;
             const double blocks = rpl * (1.0 + 0.2) /* second pass ~ 20% of a first-pass block */
                                 + ilog2(lpf) * ((N + 3) / 4);
@@ -350,6 +359,56 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, 
     out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+// DFMA whose three source operands are all distinct registers and never repeat in the
+// same operand slot of consecutive instructions (no operand-reuse-cache hits): the rate
+// the register file can feed, which is what bounds register-blocked FP64 code like the
+// Householder updates of K1/K2.
+__global__ void __launch_bounds__(256) dfma_3op_kernel(double *out, int iters, double b, double c)
+{
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+           a6 = a0 + 6, a7 = a0 + 7;
+    double b0 = b, b1 = b + 1e-9, b2 = b + 2e-9, b3 = b + 3e-9, b4 = b + 4e-9, b5 = b + 5e-9, b6 = b + 6e-9,
+           b7 = b + 7e-9;
+    double c0 = c, c1 = c * 2, c2 = c * 3, c3 = c * 4, c4 = c * 5, c5 = c * 6, c6 = c * 7, c7 = c * 8;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a0) : "d"(b0), "d"(c0));
+            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a1) : "d"(b1), "d"(c1));
+            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a2) : "d"(b2), "d"(c2));
+            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a3) : "d"(b3), "d"(c3));
+            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a4) : "d"(b4), "d"(c4));
+            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a5) : "d"(b5), "d"(c5));
+            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a6) : "d"(b6), "d"(c6));
+            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a7) : "d"(b7), "d"(c7));
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+// Same, but the multiplier is shared by consecutive instructions (one operand served by
+// the reuse cache, two register reads per DFMA) — the pattern of a rank-1 update.
+__global__ void __launch_bounds__(256) dfma_2op_kernel(double *out, int iters, double b, double c)
+{
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+           a6 = a0 + 6, a7 = a0 + 7;
+    double c0 = c, c1 = c * 2, c2 = c * 3, c3 = c * 4, c4 = c * 5, c5 = c * 6, c6 = c * 7, c7 = c * 8;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a0) : "d"(b), "d"(c0));
+            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a1) : "d"(b), "d"(c1));
+            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a2) : "d"(b), "d"(c2));
+            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a3) : "d"(b), "d"(c3));
+            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a4) : "d"(b), "d"(c4));
+            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a5) : "d"(b), "d"(c5));
+            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a6) : "d"(b), "d"(c6));
+            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a7) : "d"(b), "d"(c7));
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 __global__ void __launch_bounds__(256) dmma_peak_kernel(double *out, int iters, double b, double c)
 {
     double a = threadIdx.x * 1e-3 + 0.5, bb = b;
@@ -376,7 +435,11 @@ extern "C" int qnmfit_fp64_peak(qnmfit_ctx *ctx, int kind, int iters, double *tf
     if (iters < 1) iters = 1;
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
-    const int block = 256, grid = ctx->sm_count * 8;
+    // kinds >= 10: the same kernels at the occupancy of K1 (one 256-thread CTA per SM,
+    // two warps per scheduler) to see what that occupancy can extract from the pipe
+    const bool low_occ = kind >= 10;
+    if (low_occ) kind -= 10;
+    const int block = 256, grid = ctx->sm_count * (low_occ ? 1 : 8);
     double *out = nullptr;
     if ((e = cudaMalloc(&out, sizeof(double) * (size_t)grid * block)) != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc");
     cudaEvent_t ev0, ev1;
@@ -386,6 +449,8 @@ extern "C" int qnmfit_fp64_peak(qnmfit_ctx *ctx, int kind, int iters, double *tf
     for (int rep = 0; rep < 6; ++rep) {   // first reps warm up; best of the rest
         cudaEventRecord(ev0, 0);
         if (kind == 0) dfma_peak_kernel<<<grid, block>>>(out, iters, 0.999999, 1e-9);
+        else if (kind == 2) dfma_3op_kernel<<<grid, block>>>(out, iters, 0.999999, 1e-9);
+        else if (kind == 3) dfma_2op_kernel<<<grid, block>>>(out, iters, 0.999999, 1e-9);
         else dmma_peak_kernel<<<grid, block>>>(out, iters, 0.999999, 1e-9);
         cudaEventRecord(ev1, 0);
         e = cudaEventSynchronize(ev1);
@@ -400,7 +465,7 @@ extern "C" int qnmfit_fp64_peak(qnmfit_ctx *ctx, int kind, int iters, double *tf
     cudaFree(out);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "fp64 peak kernel");
     double flops;
-    if (kind == 0) flops = 2.0 * 64.0 * (double)iters * (double)grid * block;            // 8 chains x 8 unroll
+    if (kind == 0 || kind == 2 || kind == 3) flops = 2.0 * 64.0 * (double)iters * (double)grid * block;   // 8 chains x 8 unroll
     else flops = 2.0 * 256.0 * 32.0 * (double)iters * (double)grid * (block / 32);        // 32 MMAs x 256 FMA
     *tflops = flops / (best_ms * 1e-3) * 1e-12;
     return 0;

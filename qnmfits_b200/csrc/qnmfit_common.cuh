@@ -36,31 +36,27 @@ QF_DEV double qf_mul_rn(double a, double b) { return __dmul_rn(a, b); }
 QF_DEV double qf_add_rn(double a, double b) { return __dadd_rn(a, b); }
 QF_DEV double qf_sub_rn(double a, double b) { return __dsub_rn(a, b); }
 
-// 1/sqrt(x), x > 0 and normal: MUFU.RSQ64H seed (rel. err 2^-22) + one cubically
-// convergent step  y <- y (1 + e/2 + 3 e^2/8),  e = 1 - x y^2   (err ~ 2^-60).
+// 1/sqrt(x), x > 0 and normal: MUFU.RSQ64H seed (PTX: max rel. err 2^-22) + one
+// cubically convergent step  y <- y (1 + e/2 + 3 e^2/8),  e = 1 - x y^2.  The error
+// after the step is ~ (5/16) e^3 < 2^-65, i.e. the result is correct to ~1 ulp of
+// rounding; the reflector only needs consistency to O(eps).  Five dependent FP64 ops.
 QF_DEV double qf_rsqrt(double x)
 {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double xy = x * y;
-    double e = fma(-xy, y, 1.0);
+    const double xy = x * y;
+    const double e = fma(-xy, y, 1.0);
     double p = fma(0.375, e, 0.5);
     p = p * e;
-    y = fma(y, p, y);
-    // one cheap polish (quadratic) keeps the result within ~1 ulp for all inputs
-    xy = x * y;
-    e = fma(-xy, y, 1.0);
-    return fma(0.5 * y, e, y);
+    return fma(y, p, y);
 }
 
-// 1/x, x normal: MUFU.RCP64H seed (2^-23) + two Newton steps.
+// 1/x, x normal: MUFU.RCP64H seed (2^-23) + two Newton steps (2^-46, 2^-92).
 QF_DEV double qf_rcp(double x)
 {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
     y = fma(y, e, y);
     e = fma(-x, y, 1.0);
     return fma(y, e, y);

@@ -1,0 +1,96 @@
+#!/usr/bin/env python
+"""Developer tool: build variants of libqnmfit.so with -D switches and time the cfg3 grid
+kernel with each (device-resident inputs, CUDA events).  Not part of the product.
+
+    python tools/k1_variants.py build          # here (nvcc cross-compiles)
+    python tools/k1_variants.py run            # on the GPU box
+"""
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "tools", "_variants")
+
+VARIANTS = {
+    "base": [],
+    "noscalar": ["-DQNMFIT_ABL_NOSCALAR"],
+    "nogen": ["-DQNMFIT_ABL_NOGEN"],
+    "nosplit": ["-DQNMFIT_SPLIT_COLS=0"],
+    "split8": ["-DQNMFIT_SPLIT_COLS=8"],
+    "t128": ["-DK1_THREADS=128"],
+}
+
+
+def build():
+    os.makedirs(OUT, exist_ok=True)
+    procs = []
+    for name, flags in VARIANTS.items():
+        cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+               "-Xcompiler", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"),
+               "-I" + os.path.join(ROOT, "qnmfits_b200", "csrc"), "-DQNMFIT_ONLY_N8", *flags,
+               "-o", os.path.join(OUT, f"libqnmfit_{name}.so"),
+               os.path.join(ROOT, "qnmfits_b200", "csrc", "qnmfit_api.cu")]
+        procs.append((name, subprocess.Popen(cmd, cwd=ROOT)))
+    for name, p in procs:
+        assert p.wait() == 0, name
+
+
+def run(steps=10):
+    import numpy as np
+    import torch
+    import qnmfits_b200 as qf
+    from qnmfits_b200 import _cabi, workloads
+    from qnmfits_b200 import qnmfits as api
+    from qnmfits_b200._engine import get_engine
+    workloads.use_synthetic_tables()
+    wl = workloads.config3(res=256)
+    eng = get_engine(0)
+    sweep, shape = api._prepare_M_chi_grid(wl.times, wl.data, wl.modes, wl.Mf_minmax, wl.chif_minmax,
+                                           wl.t0, T=wl.T, res=256)
+    stream = torch.cuda.current_stream()
+    results = {}
+    names = sys.argv[2:] or list(VARIANTS)
+    for name in names:
+        path = os.path.join(OUT, f"libqnmfit_{name}.so")
+        if not os.path.isfile(path):
+            continue
+        lib = _cabi.load_library(path)
+        h = C.c_void_p()
+        assert lib.qnmfit_create(0, C.byref(h)) == 0
+        for anchor in (64, 256):
+            for uw in (1, 0):
+                sweep.batch.anchor_rows = anchor
+                sweep.batch.uniform_weights = uw
+                for _ in range(3):
+                    rc = lib.qnmfit_fit_batch(h, C.byref(sweep.batch), C.c_void_p(stream.cuda_stream))
+                    assert rc == 0, lib.qnmfit_last_error(h)
+                torch.cuda.synchronize()
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(steps):
+                    lib.qnmfit_fit_batch(h, C.byref(sweep.batch), C.c_void_p(stream.cuda_stream))
+                e1.record(stream)
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / steps
+                plan = _cabi.Plan()
+                lib.qnmfit_plan_batch(h, C.byref(sweep.batch), C.byref(plan))
+                results[f"{name}/anchor{anchor}/fast{uw}"] = dict(
+                    ms=round(ms, 4), lpf=plan.lanes_per_fit, grid=plan.grid, block=plan.block,
+                    regs=plan.regs_per_thread, smem=plan.smem_bytes)
+                print(f"{name:10s} anchor={anchor:4d} fast={uw} {ms:8.4f} ms  lpf={plan.lanes_per_fit} "
+                      f"grid={plan.grid} block={plan.block} regs={plan.regs_per_thread}", flush=True)
+        lib.qnmfit_destroy(h)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(results, open(os.path.join(ROOT, "gpurun_out", "k1_variants.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "build":
+        build()
+    else:
+        run()
