@@ -231,7 +231,7 @@ def run_gpu_arm(args):
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=eng.device)
     stream = torch.cuda.current_stream()
     for _ in range(max(args.warmup, 3)):
-        sweep.launch(gather_status=False)
+        sweep.launch()
     barrier()
     launches0 = eng.ctx.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
@@ -241,10 +241,9 @@ def run_gpu_arm(args):
         for e0, e1, e2 in ev:
             flush.fill_(1.0)                       # evict L2 between steps (not timed)
             e0.record(stream)
-            sweep.eng.fit(sweep.batch)             # this rank's slab
+            sweep.launch_kernel()                  # this rank's slab
             e1.record(stream)
-            if world > 1:
-                sweep.mm_all = api._dist.all_gather_slabs(sweep.mm_d, n_fits)
+            sweep.gather()                         # NCCL all-gather of the slabs (N > 1)
             e2.record(stream)
         barrier()
     launches = eng.ctx.launch_count() - launches0

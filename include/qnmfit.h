@@ -142,6 +142,10 @@ typedef struct qnmfit_batch {
                                  second pass over the rows.  0: always the general
                                  weighted second pass.                                  */
     int32_t reserved1;
+
+    double  *flagged_count;   /* f64 [1] or NULL: incremented (atomicAdd) once per fit
+                                 whose status word is non-zero; lets a sweep detect
+                                 flagged fits without copying status[] back           */
 } qnmfit_batch;
 
 /* Create / destroy a context bound to one CUDA device (one process per GPU). */

@@ -44,6 +44,7 @@ class Batch(C.Structure):
         ("mismatch", _dp), ("residual", _dp), ("R", _dp), ("status", _dp),
         ("model", _dp), ("model_stride", C.c_int64),
         ("uniform_weights", C.c_int32), ("reserved1", C.c_int32),
+        ("flagged_count", _dp),
     ]
 
     def __init__(self, **kw):

@@ -69,6 +69,8 @@ class Engine:
         self.ctx = _cabi.Context(device)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self._pinned_bufs = {}
+        self._upload_event = None
 
     # ------------------------------------------------------------- transfers
 
@@ -91,6 +93,63 @@ class Engine:
     def stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
 
+    # ---------------------------------------- low-overhead packed transfers
+
+    def _pinned(self, name, nbytes):
+        """A cached pinned host buffer of at least nbytes (uint8)."""
+        buf = self._pinned_bufs.get(name)
+        if buf is None or buf.numel() < nbytes:
+            buf = self.torch.empty(max(nbytes, 1 << 16), dtype=self.torch.uint8, pin_memory=True)
+            self._pinned_bufs[name] = buf
+        return buf
+
+    def upload_packed(self, arrays):
+        """Copy several host arrays to the device with ONE cudaMemcpyAsync.
+
+        ``arrays`` is a list of C-contiguous numpy arrays (or None).  They are packed,
+        256-byte aligned, into a pinned staging buffer and copied into one freshly
+        allocated device buffer; returns (device_buffer, [device pointer or None, ...]).
+        The staging buffer is reused by the next call: the previous copy has completed
+        by then because every public API call ends with a stream synchronisation, and
+        an event guards the remaining cases.
+        """
+        torch = self.torch
+        offsets, total = [], 0
+        for a in arrays:
+            if a is None:
+                offsets.append(None)
+                continue
+            offsets.append(total)
+            total += (a.nbytes + 255) // 256 * 256
+        total = max(total, 256)
+        if self._upload_event is not None:
+            self._upload_event.synchronize()
+        stage = self._pinned("upload", total)
+        stage_np = stage.numpy()
+        for a, off in zip(arrays, offsets):
+            if a is not None and a.nbytes:
+                stage_np[off:off + a.nbytes] = a.reshape(-1).view(np.uint8)
+        dev = torch.empty(total, dtype=torch.uint8, device=self.device)
+        dev.copy_(stage[:total], non_blocking=True)
+        if self._upload_event is None:
+            self._upload_event = torch.cuda.Event()
+        self._upload_event.record(torch.cuda.current_stream(self.device))
+        self.h2d_bytes += sum(a.nbytes for a in arrays if a is not None)
+        base = dev.data_ptr()
+        return dev, [None if off is None else base + off for off in offsets]
+
+    def download(self, tensor):
+        """Device tensor -> new numpy array through a cached pinned buffer (one async
+        copy + one stream synchronisation)."""
+        torch = self.torch
+        nbytes = tensor.numel() * tensor.element_size()
+        stage = self._pinned("download", nbytes)
+        view = stage[:nbytes].view(tensor.dtype)
+        view.copy_(tensor.reshape(-1), non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        self.d2h_bytes += nbytes
+        return view.numpy().copy()
+
     # --------------------------------------------------------------- batches
 
     def make_batch(self, *, times_d, data_d, n_fits, n_modes, n_series=1, first_fit=0,
@@ -102,13 +161,19 @@ class Engine:
                    coef_d=None, coef_index_d=None, n_coef=0,
                    dt_nominal=0.0, anchor_rows=0, kernel=_cabi.KERNEL_AUTO,
                    C_d=None, mismatch_d=None, residual_d=None, R_d=None, status_d=None,
-                   model_d=None, model_stride=0, uniform_weights=False):
+                   model_d=None, model_stride=0, uniform_weights=False,
+                   n_times=None, series_stride=None, flagged_d=None):
         def p(t):
-            return None if t is None else t.data_ptr()
-        n_times = int(times_d.numel())
+            if t is None or isinstance(t, int):
+                return t
+            return t.data_ptr()
+        if n_times is None:
+            n_times = int(times_d.numel())
+        if series_stride is None:
+            series_stride = int(data_d.shape[-1])
         b = _cabi.Batch(
             kernel=kernel, n_fits=int(n_fits), n_modes=int(n_modes), n_series=int(n_series),
-            n_times=n_times, series_stride=int(data_d.shape[-1]), first_fit=int(first_fit),
+            n_times=int(n_times), series_stride=int(series_stride), first_fit=int(first_fit),
             times=p(times_d), data=p(data_d),
             row_begin=p(row_begin_d), row_end=p(row_end_d), t0=p(t0_d),
             row_begin_all=int(row_begin_all), row_end_all=int(row_end_all), t0_all=float(t0_all),
@@ -120,7 +185,7 @@ class Engine:
             dt_nominal=float(dt_nominal), anchor_rows=int(anchor_rows),
             C=p(C_d), mismatch=p(mismatch_d), residual=p(residual_d), R=p(R_d),
             status=p(status_d), model=p(model_d), model_stride=int(model_stride),
-            uniform_weights=1 if uniform_weights else 0)
+            uniform_weights=1 if uniform_weights else 0, flagged_count=p(flagged_d))
         return b
 
     def fit(self, batch):

@@ -296,6 +296,7 @@ fit_general_kernel(const FitParams p, const int TR, const int TK)
         p.mismatch[fit] = 1.0 - a0 / sqrt(a1 * a2);
         if (p.residual) p.residual[fit] = a3;
         if (p.status) p.status[fit] = status;
+        note_status(p, status);
     }
 }
 #endif  // !QNMFIT_HOSTSIM

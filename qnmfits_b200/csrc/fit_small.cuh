@@ -480,6 +480,7 @@ QF_HD void small_finalize(const FitParams &p, const SmallLane &L, const double (
     p.mismatch[L.fit] = mm;
     if (p.residual) p.residual[L.fit] = sums[3];
     if (p.status) p.status[L.fit] = status;
+    note_status(p, status);
 }
 
 // Fast path for (nearly) uniform grids — no second pass.  With m = A C = Q Q^H d:
@@ -525,6 +526,7 @@ QF_HD void small_fast_finalize(const FitParams &p, const SmallLane &L, const dou
     p.mismatch[L.fit] = 1.0 - num / sqrt(n1 * n2);
     if (p.residual) p.residual[L.fit] = tot[1];
     if (p.status) p.status[L.fit] = status;
+    note_status(p, status);
 }
 
 #ifndef QNMFIT_HOSTSIM

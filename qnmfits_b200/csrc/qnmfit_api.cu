@@ -281,6 +281,7 @@ static void fill_params(const qnmfit_batch *b, const Plan &pl, bool eval, FitPar
     p->C = (double2 *)b->C; p->mismatch = b->mismatch; p->residual = b->residual;
     p->R = (double2 *)b->R; p->status = b->status;
     p->model = (double2 *)b->model; p->model_stride = b->model_stride; p->omega_shared = b->omega_shared;
+    p->flagged_count = b->flagged_count;
     p->lanes_per_fit = pl.lpf; p->eval_only = eval ? 1 : 0;
     p->fast_mismatch = (pl.kernel == QNMFIT_KERNEL_SMALL && !eval && b->uniform_weights && b->dt_nominal > 0.0 && !b->model) ? 1 : 0;
     p->stage_begin = pl.stage_begin; p->stage_rows = pl.stage_rows;

@@ -136,6 +136,7 @@ struct FitParams {
     int *status;
     double2 *model;
     long long model_stride;
+    double *flagged_count;
     int omega_shared;
     // launch-time choices
     int lanes_per_fit;   // K1: power of two, 1..32
@@ -162,6 +163,18 @@ QF_HD double2 fit_omega(const FitParams &p, int fit, int j)
     double inv = p.inv_Mf[fit_mf_index(p, fit)];
     double df = p.delta_factor ? p.delta_factor[j] : 1.0;
     return form_omega(p.omega_tilde + 2ll * c * p.n_constituents, p.mode_ptr, j, inv, df);
+}
+
+// count a fit whose status word is non-zero
+QF_HD void note_status(const FitParams &p, int status)
+{
+    if (status != 0 && p.flagged_count) {
+#ifdef QNMFIT_HOSTSIM
+        *p.flagged_count += 1.0;
+#else
+        atomicAdd(p.flagged_count, 1.0);
+#endif
+    }
 }
 
 #define QNMFIT_ST_RANK_DEFICIENT_ 1

@@ -80,6 +80,7 @@ class qnm:
     def __init__(self, data_dir=None):
         self._qnm_funcs = {}
         self._interpolated_qnm_funcs = {}
+        self._tabulated = {}
         self.download_check = {}
         self._data_dir = Path(data_dir) if data_dir is not None \
             else Path(__file__).parent / 'Data'
@@ -90,6 +91,7 @@ class qnm:
 
     def _reset_sequences(self):
         self._interpolated_qnm_funcs = {}
+        self._tabulated = {}
         self._load_cook_multiplets()
 
     def _load_cook_multiplets(self):
@@ -178,6 +180,17 @@ class qnm:
 
     # ------------------------------------------------- factored device tables
 
+    def _memo(self, key, compute):
+        """Memoise a tabulated column per (label, spin array): the reference memoises its
+        splines the same way (qnm.py:225-226); a sweep repeated on the same spin grid
+        (other t0, other data) then skips the FITPACK evaluation."""
+        hit = self._tabulated.get(key)
+        if hit is None:
+            if len(self._tabulated) > 4096:
+                self._tabulated.clear()
+            hit = self._tabulated[key] = compute()
+        return hit
+
     def constituent_table(self, modes, chif_values, s=-2):
         """Mf-independent frequency table for a sweep over spins.
 
@@ -192,6 +205,7 @@ class qnm:
         bit for bit.
         """
         chif_values = np.atleast_1d(np.asarray(chif_values, dtype=float))
+        chi_key = chif_values.tobytes()
         cols = []
         mode_ptr = [0]
         for mode in modes:
@@ -199,10 +213,11 @@ class qnm:
                 raise ValueError(
                     f"mode label {mode!r} must have a multiple of 4 entries")
             for i in range(0, len(mode), 4):
-                ell, m, n, sign = mode[i:i + 4]
-                cols.append(np.asarray(
-                    self.omega(ell, m, n, sign, chif_values, 1.0, s),
-                    dtype=complex))
+                ell, m, n, sign = (int(v) for v in mode[i:i + 4])
+                cols.append(self._memo(
+                    ('w', ell, m, n, sign, s, chi_key),
+                    lambda: np.asarray(self.omega(ell, m, n, sign, chif_values, 1.0, s),
+                                       dtype=complex)))
             mode_ptr.append(len(cols))
         table = np.ascontiguousarray(np.stack(cols, axis=1)) if cols else \
             np.zeros((len(chif_values), 0), dtype=complex)
@@ -217,11 +232,16 @@ class qnm:
         documented superset.
         """
         chif_values = np.atleast_1d(np.asarray(chif_values, dtype=float))
+        chi_key = chif_values.tobytes()
         out = np.zeros((len(chif_values), len(spherical_modes), len(modes)),
                        dtype=complex)
         for i, (ell, m) in enumerate(spherical_modes):
             for j, mode in enumerate(modes):
-                ellp, mp, nprime, sign = mode
-                out[:, i, j] = self.mu(ell, m, ellp, mp, nprime, sign,
-                                       chif_values, s)
+                ellp, mp, nprime, sign = (int(v) for v in mode)
+                if mp != m:
+                    continue          # int 0 in the reference (qnm.py:336-337)
+                out[:, i, j] = self._memo(
+                    ('mu', int(ell), int(m), ellp, mp, nprime, sign, s, chi_key),
+                    lambda: np.asarray(self.mu(ell, m, ellp, mp, nprime, sign, chif_values, s),
+                                       dtype=complex))
         return out

@@ -344,10 +344,14 @@ class _Sweep:
     is float64[n] or a scalar.  With torch.distributed initialised the flat fit index is
     split into one contiguous slab per rank (``_dist.shard_bounds``); ``launch`` runs
     this rank's slab and all-gathers the mismatches.
+
+    Host overhead is kept small: every input goes to the device in ONE pinned-memory
+    copy (``Engine.upload_packed``); the kernels count flagged fits into one double
+    behind the mismatch slab, so the result comes back in ONE copy as well.
     """
 
-    def __init__(self, times, rows, *, n_fits, n_modes, windows, t0s, freq_kwargs, coef,
-                 coef_per_chi, wmax):
+    def __init__(self, times, rows, *, n_fits, n_modes, windows, t0s, freq_arrays, freq_scalars,
+                 coef, coef_per_chi, wmax):
         import torch
         eng = self.eng = get_engine()
         self.n_fits = n_fits
@@ -355,65 +359,78 @@ class _Sweep:
         lo, hi, per = _dist.shard_bounds(n_fits, self.rank, self.ws)
         self.lo, self.hi, self.per = lo, hi, per
         n_local = hi - lo
-        L = rows.shape[0]
+        L, K_tot = rows.shape
 
-        times_d = eng.to_device(times, np.float64)
-        data_d = eng.to_device(rows, np.complex128)
         shared_window = not isinstance(windows[0], np.ndarray)
         if shared_window:
             rb_all, re_all = int(windows[0]), int(windows[1])
-            rb_d = re_d = None
+            rb = re = None
         else:
             rb_all, re_all = int(windows[0].min()), int(windows[1].max())
-            rb_d = eng.to_device(windows[0][lo:hi], np.int32)
-            re_d = eng.to_device(windows[1][lo:hi], np.int32)
+            rb = np.ascontiguousarray(windows[0][lo:hi], dtype=np.int32)
+            re = np.ascontiguousarray(windows[1][lo:hi], dtype=np.int32)
         if re_all <= rb_all:
             raise ValueError("the analysis window is empty")
         if np.ndim(t0s) == 0:
-            t0_d, t0_all = None, float(t0s)
+            t0_arr, t0_all = None, float(t0s)
         else:
-            t0_d, t0_all = eng.to_device(np.asarray(t0s, dtype=float)[lo:hi], np.float64), 0.0
-
-        kw = {k: (eng.to_device(v[0], v[1]) if isinstance(v, tuple) else v)
-              for k, v in freq_kwargs.items()}
-        coef_d = coef_index_d = None
+            t0_arr, t0_all = np.ascontiguousarray(np.asarray(t0s, dtype=float)[lo:hi]), 0.0
+        coef_arr = coef_index = None
         n_coef = 0
         if coef is not None:
-            coef_d = eng.to_device(coef, np.complex128)
+            coef_arr = np.ascontiguousarray(coef, dtype=np.complex128)
             n_coef = coef.shape[0]
             if not coef_per_chi:
-                coef_index_d = torch.zeros(max(n_local, 1), dtype=torch.int32, device=eng.device)
+                coef_index = np.zeros(max(n_local, 1), np.int32)
 
-        self.mm_d = torch.full((max(per, 1),), float('nan'), dtype=torch.float64,
-                               device=eng.device)
-        self.st_d = torch.zeros((max(per, 1),), dtype=torch.int32, device=eng.device)
-        self.mm_all, self.st_all = self.mm_d[:n_fits], self.st_d[:n_fits]
+        names = list(freq_arrays)
+        host = [np.ascontiguousarray(times, dtype=np.float64),
+                np.ascontiguousarray(rows, dtype=np.complex128), rb, re, t0_arr, coef_arr,
+                coef_index] + [np.ascontiguousarray(freq_arrays[k][0], dtype=freq_arrays[k][1])
+                               for k in names]
+        self._inputs, ptrs = eng.upload_packed(host)
+        kw = dict(freq_scalars)
+        kw.update({k: ptr for k, ptr in zip(names, ptrs[7:])})
+
+        # output slab: per mismatches + one counter of flagged fits
+        self.out_d = torch.empty(max(per, 1) + 1, dtype=torch.float64, device=eng.device)
+        self.gathered = None
         self.batch = None
         dt = nominal_step(times[rb_all:re_all], wmax)
         if n_local > 0:
             self.batch = eng.make_batch(
-                times_d=times_d, data_d=data_d, n_fits=n_local, n_modes=n_modes, n_series=L,
+                times_d=ptrs[0], data_d=ptrs[1], n_times=K_tot, series_stride=K_tot,
+                n_fits=n_local, n_modes=n_modes, n_series=L,
                 first_fit=lo, row_begin_all=rb_all, row_end_all=re_all, t0_all=t0_all,
-                row_begin_d=rb_d, row_end_d=re_d, t0_d=t0_d,
-                coef_d=coef_d, coef_index_d=coef_index_d, n_coef=n_coef,
+                row_begin_d=ptrs[2], row_end_d=ptrs[3], t0_d=ptrs[4],
+                coef_d=ptrs[5], coef_index_d=ptrs[6], n_coef=n_coef,
                 dt_nominal=dt, uniform_weights=uniform_weights(times[rb_all:re_all], dt),
-                mismatch_d=self.mm_d, status_d=self.st_d, **kw)
-        # keep every device buffer alive as long as the descriptor
-        self._keep = (times_d, data_d, rb_d, re_d, t0_d, kw, coef_d, coef_index_d)
+                mismatch_d=self.out_d, flagged_d=self.out_d.data_ptr() + 8 * max(per, 1), **kw)
         self.rows_max = re_all - rb_all
 
-    def launch(self, gather_status=True):
-        """Asynchronous: the fit kernel on this rank's slab, then the all-gather."""
+    def launch_kernel(self):
+        """Asynchronous: the fit kernel on this rank's slab."""
+        self.out_d[-1:].zero_()
         if self.batch is not None:
             self.eng.fit(self.batch)
+
+    def gather(self):
+        """Asynchronous: all-gather of the slabs (NCCL); no-op on a single rank."""
         if self.ws > 1:
-            self.mm_all = _dist.all_gather_slabs(self.mm_d, self.n_fits)
-            if gather_status:
-                self.st_all = _dist.all_gather_slabs(self.st_d, self.n_fits)
+            self.gathered = _dist.all_gather_slabs(self.out_d, self.out_d.numel() * self.ws)
+
+    def launch(self):
+        self.launch_kernel()
+        self.gather()
 
     def fetch(self):
-        """Mismatch of every fit (float64[n_fits]) and the status words, on the host."""
-        return self.eng.to_host(self.mm_all), self.eng.to_host(self.st_all)
+        """(mismatch of every fit as float64[n_fits], number of flagged fits), on the host."""
+        per = max(self.per, 1)
+        if self.ws > 1:
+            full = self.eng.download(self.gathered).reshape(self.ws, per + 1)
+            return full[:, :per].reshape(-1)[:self.n_fits].copy(), int(full[:, per].sum())
+        out = self.eng.download(self.out_d)
+        return out[:self.n_fits], int(out[per])
 
 
 def _sweep_on_device(*args, **kwargs):
@@ -422,15 +439,34 @@ def _sweep_on_device(*args, **kwargs):
     return sweep.fetch()
 
 
-def _warn_status(status, what):
-    bad = np.count_nonzero(status & (_cabi.ST_RANK_DEFICIENT | _cabi.ST_UNDERDETERMINED))
-    if bad:
+def _warn_status(flagged, what):
+    if flagged:
         import warnings
         warnings.warn(
-            f"{what}: {bad} fit(s) are numerically rank deficient by numpy's "
-            "eps*max(M,N) criterion; numpy.linalg.lstsq would truncate singular values "
-            "there, the device returns the basic QR solution (mismatch may differ).",
+            f"{what}: {flagged} fit(s) were flagged by the device (numerically rank "
+            "deficient by numpy's eps*max(M,N) criterion, underdetermined or non-finite); "
+            "numpy.linalg.lstsq would truncate singular values there, the device returns "
+            "the basic QR solution (mismatch may differ).",
             RuntimeWarning, stacklevel=3)
+
+
+def _window_rows_many(times, t0_array, T_array, t0_method):
+    """Vectorised ``_window_rows``: identical arithmetic per element."""
+    if t0_method == 'geq':
+        begin = np.searchsorted(times, t0_array, side='left')
+        end = np.searchsorted(times, t0_array + T_array, side='left')
+    else:
+        begin = np.empty(len(t0_array), np.int64)
+        end = np.empty(len(t0_array), np.int64)
+        step = max(1, 2_000_000 // max(len(times), 1))
+        for s in range(0, len(t0_array), step):
+            t0 = t0_array[s:s + step, None]
+            T = T_array[s:s + step, None]
+            begin[s:s + step] = np.argmin((times[None, :] - t0) ** 2, axis=1)
+            end[s:s + step] = np.argmin((times[None, :] - t0 - T) ** 2, axis=1)
+    begin = begin.astype(np.int32)
+    end = np.maximum(end, begin).astype(np.int32)
+    return begin, end
 
 
 def mismatch_t0_array(times, data, modes, Mf, chif, t0_array, t0_method='geq',
@@ -471,10 +507,7 @@ def mismatch_t0_array(times, data, modes, Mf, chif, t0_array, t0_method='geq',
         return out
 
     rows, keys = _series_rows(data, spherical_modes)
-    begin = np.empty(n, np.int32)
-    end = np.empty(n, np.int32)
-    for i, (t0, T) in enumerate(zip(t0_array, T_array)):
-        begin[i], end[i] = _window_rows(times, t0, T, t0_method)
+    begin, end = _window_rows_many(times, t0_array, np.asarray(T_array, dtype=float), t0_method)
     if np.any(end <= begin):
         raise ValueError("an analysis window is empty")
 
@@ -487,10 +520,11 @@ def mismatch_t0_array(times, data, modes, Mf, chif, t0_array, t0_method='geq',
         mu_lists = _mu_lists(keys, modes, chif)
         coef = np.array([[complex(v) for v in row] for row in mu_lists],
                         dtype=complex).reshape(1, len(keys), len(modes))
-    freq_kwargs = dict(omega_d=(frequencies.reshape(1, -1), np.complex128), omega_shared=True)
     mm, status = _sweep_on_device(
         np.asarray(times, dtype=float), rows, n_fits=n, n_modes=len(modes),
-        windows=(begin, end), t0s=t0_array, freq_kwargs=freq_kwargs, coef=coef,
+        windows=(begin, end), t0s=t0_array,
+        freq_arrays=dict(omega_d=(frequencies.reshape(1, -1), np.complex128)),
+        freq_scalars=dict(omega_shared=True), coef=coef,
         coef_per_chi=False, wmax=float(np.max(np.abs(frequencies))))
     _warn_status(status, "mismatch_t0_array")
     return [np.float64(v) for v in mm]
@@ -532,16 +566,17 @@ def _prepare_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0, t0_metho
     wmax = float(np.max(np.abs(table)) * np.max(np.abs(inv_Mf))
                  * (1.0 if df is None else np.max(np.abs(df)))) * max(
                      len(m) // 4 for m in modes)
-    freq_kwargs = dict(
+    freq_arrays = dict(
         omega_tilde_d=(table, np.complex128), mode_ptr_d=(mode_ptr, np.int32),
-        inv_Mf_d=(inv_Mf, np.float64), n_chi=len(chif_array), n_mf=len(Mf_array),
-        n_constituents=table.shape[1])
+        inv_Mf_d=(inv_Mf, np.float64))
     if df is not None:
-        freq_kwargs['delta_factor_d'] = (df, np.float64)
+        freq_arrays['delta_factor_d'] = (df, np.float64)
     sweep = _Sweep(
         np.asarray(times, dtype=float), rows, n_fits=n, n_modes=len(modes),
-        windows=window, t0s=float(t0), freq_kwargs=freq_kwargs, coef=coef,
-        coef_per_chi=True, wmax=wmax)
+        windows=window, t0s=float(t0), freq_arrays=freq_arrays,
+        freq_scalars=dict(n_chi=len(chif_array), n_mf=len(Mf_array),
+                          n_constituents=table.shape[1]),
+        coef=coef, coef_per_chi=True, wmax=wmax)
     return sweep, shape
 
 
