@@ -198,7 +198,10 @@ QF_HD void small_absorb(double2 (&B)[4][N + 1], double *Rd, double2 *Ro)
 #pragma unroll
     for (int j = JSTART; j < N; ++j) {
         const double r = Rd[j * THREADS];
-        double sig0 = B[0][j].x * B[0][j].x, sig1 = B[1][j].x * B[1][j].x;
+        // |column|^2 of the stacked [r; b], seeded with 1e-300 so that an exactly zero column
+        // (then row j of R and b are all zero and the reflection changes nothing) needs no
+        // branch: the seed is below one ulp of any column with norm > 1e-142.
+        double sig0 = fma(B[0][j].x, B[0][j].x, 1e-300), sig1 = B[1][j].x * B[1][j].x;
         sig0 = fma(B[0][j].y, B[0][j].y, sig0);
         sig1 = fma(B[1][j].y, B[1][j].y, sig1);
         sig0 = fma(B[2][j].x, B[2][j].x, sig0);
@@ -206,24 +209,21 @@ QF_HD void small_absorb(double2 (&B)[4][N + 1], double *Rd, double2 *Ro)
         sig0 = fma(B[2][j].y, B[2][j].y, sig0);
         sig1 = fma(B[3][j].y, B[3][j].y, sig1);
         const double t = fma(r, r, sig0 + sig1);
-        // norm of the stacked column; a column that is negligible down to the
-        // underflow range is left alone (H = I) and shows up as a zero pivot.
-        const bool ok = t > 1e-280;
 #ifdef QNMFIT_ABL_NOSCALAR
         const double y = 1.0;
 #else
-        const double y = qf_rsqrt(ok ? t : 1.0);
+        const double y = qf_rsqrt(t);
 #endif
-        const double nrm = ok ? t * y : 0.0;
+        const double nrm = t * y;
         const double ar = fabs(r);
         const double v0 = copysign(ar + nrm, r);          // v = [v0; b]
         const double den = nrm * (ar + nrm);              // v^H v / 2
 #ifdef QNMFIT_ABL_NOSCALAR
-        const double beta = ok ? den : 0.0;
+        const double beta = den;
 #else
-        const double beta = ok ? qf_rcp(den) : 0.0;
+        const double beta = qf_rcp(den);
 #endif
-        Rd[j * THREADS] = ok ? -copysign(nrm, r) : r;
+        Rd[j * THREADS] = -copysign(nrm, r);
 #pragma unroll
         for (int k = j + 1; k <= N; ++k) {
             double2 Rjk = Ro[LY::pair(j, k) * THREADS];
@@ -304,13 +304,12 @@ QF_HD void small_acc_rhs(const double2 (&B)[4][N + 1], double &acc)
     }
 }
 
-// Leaf stage: sequential TSQR over the lane's rows.
+// Leaf stage, general form: any grid (direct evaluation of every element when
+// dt_nominal == 0), ragged blocks, per-block anchor test.
 template <int N, int THREADS>
-QF_HD void small_leaf(const FitParams &p, const SmallSmem<N, THREADS> &sm, const SmallLane &L, int tid,
-                      SmallAcc &acc)
+QF_HD void small_leaf_generic(const FitParams &p, const SmallSmem<N, THREADS> &sm, const SmallLane &L, int tid,
+                              SmallAcc &acc)
 {
-    acc.sdd = acc.res2 = acc.cn2 = 0.0;
-    if (L.fit < 0) return;
     int ablk = (p.anchor_rows > 0 ? p.anchor_rows : 64) / 4;
     if (ablk < 1) ablk = 1;
     SmallGen<N> g;
@@ -326,6 +325,109 @@ QF_HD void small_leaf(const FitParams &p, const SmallSmem<N, THREADS> &sm, const
         small_absorb<N, THREADS, 0>(B, sm.Rd + tid, sm.Ro + tid);
         small_acc_rhs<N>(B, acc.res2);
     }
+}
+
+// Leaf stage on a (nearly) uniform grid: the hot loop of the whole library.  The lane's
+// rows are cut into segments of `anchor_rows`; a segment starts with a direct
+// exp/sincos of its first row and then runs branch-free over its full 4-row blocks:
+// row k+1 = row k * (q + q(-i w) de_k), where de_k = (tau_{k+1} - tau_k) - dt is the
+// (tiny, exactly computed) deviation of that step from the nominal one.  The at most
+// three rows left over at the end of the lane are evaluated directly.
+template <int N, int THREADS>
+QF_HD void small_leaf_uniform(const FitParams &p, const SmallSmem<N, THREADS> &sm, const SmallLane &L, int tid,
+                              SmallAcc &acc)
+{
+    const double *ts = sm.ts - sm.t_off;
+    const double2 *ds = sm.ds - sm.t_off;
+    const double2 *om = sm.om + L.slot, *qq = sm.qq + L.slot, *qw = sm.qw + L.slot;
+    const int fpc = sm.fpc;
+    const double dt = p.dt_nominal, t0 = L.t0;
+    int ablk = (p.anchor_rows > 0 ? p.anchor_rows : 64) / 4;
+    if (ablk < 1) ablk = 1;
+    const int nfull = (L.hi - L.lo) >> 2;
+    const int last = L.re - 1;
+    int row0 = L.lo;
+    double2 z[N];
+    double2 B[4][N + 1];
+#pragma unroll 1
+    for (int blk = 0; blk < nfull;) {
+        const int nb = nfull - blk < ablk ? nfull - blk : ablk;
+        double tau = qf_sub_rn(ts[row0], t0);
+#pragma unroll
+        for (int j = 0; j < N; ++j) z[j] = design_entry(om[j * fpc], tau);
+#pragma unroll 1
+        for (int b = 0; b < nb; ++b) {
+            // all loads of the block up front: one exposed shared-memory latency per block
+            const int r4 = row0 + 4 < last ? row0 + 4 : last;   // clamps only in the window's last block,
+            double tn[4];                                        // whose advanced z is never used
+            tn[0] = ts[row0 + 1]; tn[1] = ts[row0 + 2]; tn[2] = ts[row0 + 3]; tn[3] = ts[r4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) B[i][N] = ds[row0 + i];
+            double de[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double tau_n = qf_sub_rn(tn[i], t0);
+                de[i] = qf_sub_rn(qf_sub_rn(tau_n, tau), dt);
+                tau = tau_n;
+            }
+#ifndef QNMFIT_ABL_NOGEN
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const double2 q = qq[j * fpc], w = qw[j * fpc];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    B[i][j] = z[j];
+                    z[j] = c_mul(z[j], make_double2(fma(w.x, de[i], q.x), fma(w.y, de[i], q.y)));
+                }
+            }
+#else
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { B[i][j] = z[j]; z[j].x += de[i]; }
+#endif
+            small_acc_rhs<N>(B, acc.sdd);
+            small_absorb<N, THREADS, 0>(B, sm.Rd + tid, sm.Ro + tid);
+            small_acc_rhs<N>(B, acc.res2);
+            row0 += 4;
+        }
+        blk += nb;
+    }
+    if (row0 < L.hi) {   // ragged tail (at most 3 rows): anchor, recurrence, zero rows beyond the lane's share
+        double tau = qf_sub_rn(ts[row0], t0);
+#pragma unroll
+        for (int j = 0; j < N; ++j) z[j] = design_entry(om[j * fpc], tau);
+        const double2 zero = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool valid = row0 + i < L.hi;
+            B[i][N] = valid ? ds[valid ? row0 + i : row0] : zero;
+            const int rn = row0 + i + 1 < last ? row0 + i + 1 : last;
+            const double tau_n = qf_sub_rn(ts[rn], t0);
+            const double de = qf_sub_rn(qf_sub_rn(tau_n, tau), dt);
+            tau = tau_n;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const double2 q = qq[j * fpc], w = qw[j * fpc];
+                B[i][j] = valid ? z[j] : zero;
+                z[j] = c_mul(z[j], make_double2(fma(w.x, de, q.x), fma(w.y, de, q.y)));
+            }
+        }
+        small_acc_rhs<N>(B, acc.sdd);
+        small_absorb<N, THREADS, 0>(B, sm.Rd + tid, sm.Ro + tid);
+        small_acc_rhs<N>(B, acc.res2);
+    }
+}
+
+// Leaf stage: sequential TSQR over the lane's rows.
+template <int N, int THREADS>
+QF_HD void small_leaf(const FitParams &p, const SmallSmem<N, THREADS> &sm, const SmallLane &L, int tid,
+                      SmallAcc &acc)
+{
+    acc.sdd = acc.res2 = acc.cn2 = 0.0;
+    if (L.fit < 0) return;
+    if (p.dt_nominal > 0.0) small_leaf_uniform<N, THREADS>(p, sm, L, tid, acc);
+    else small_leaf_generic<N, THREADS>(p, sm, L, tid, acc);
 }
 
 // One level of the R-combine: lanes with lf % (2 s) == 0 absorb the factor of lane lf + s.

@@ -223,12 +223,19 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
             const int fpc = K1_THREADS / lpf;
             // CTAs that may be co-resident on an SM by thread count; staging the window
             // must not reduce that (8 warps per SM are needed to keep the FP64 pipe fed)
+#ifdef K1_FORCE_CPS   /* developer experiments (tools/k1_variants.py) */
+            const int want_cps = K1_FORCE_CPS;
+#else
             const int want_cps = 256 / K1_THREADS > 0 ? 256 / K1_THREADS : 1;
+#endif
             const size_t per_cta = ((size_t)ctx->smem_optin + 1024) / want_cps - 1024;
             size_t smem = small_smem_bytes(N, fpc, stage_rows);
             bool staged = true;
             if (smem > per_cta) { staged = false; smem = small_smem_bytes(N, fpc, 0); }
             if (smem > per_cta) continue;
+#ifdef K1_FORCE_CPS
+            if (smem < per_cta * 6 / 10) smem = per_cta * 6 / 10;   // pad so that no more CTAs become resident
+#endif
             const int ctas = (b->n_fits + fpc - 1) / fpc;
             const int waves = (ctas + ctx->sm_count * want_cps - 1) / (ctx->sm_count * want_cps);
             const int rpl = ((Mmax + lpf - 1) / lpf + 3) / 4;
