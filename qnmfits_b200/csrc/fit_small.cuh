@@ -192,7 +192,7 @@ QF_HD void small_generate(const FitParams &p, const SmallSmem<N, THREADS> &sm, c
 // Fold the 4 x (N+1) block B into the lane's factor: N Householder reflections of
 // [R; B], columns JSTART..N-1 (columns below JSTART of B must be zero).
 template <int N, int THREADS, int JSTART>
-QF_HD void small_absorb(double2 (&B)[4][N + 1], double *Rd, double2 *Ro)
+QF_HD void small_absorb_v1(double2 (&B)[4][N + 1], double *Rd, double2 *Ro)
 {
     typedef SmallLayout<N> LY;
 #pragma unroll
@@ -275,6 +275,85 @@ QF_HD void small_absorb(double2 (&B)[4][N + 1], double *Rd, double2 *Ro)
     }
 }
 
+// Same reflections, written phase by phase so that the instruction stream the compiler
+// sees already interleaves independent chains: (A) the column norm and the raw dot
+// products b^H B_k of ALL trailing columns, rows outermost; (B) the reflector scalars,
+// whose rsqrt/rcp latency the dots cover; (C) the row of R and the rank-1 update.
+template <int N, int THREADS, int JSTART>
+QF_HD void small_absorb(double2 (&B)[4][N + 1], double *Rd, double2 *Ro)
+{
+#ifdef QNMFIT_ABSORB_V1
+    small_absorb_v1<N, THREADS, JSTART>(B, Rd, Ro);
+#else
+    typedef SmallLayout<N> LY;
+#pragma unroll
+    for (int j = JSTART; j < N; ++j) {
+        const double r = Rd[j * THREADS];
+        double sr[N + 1], si[N + 1];
+        // (A)
+        double sig0 = fma(B[0][j].x, B[0][j].x, 1e-300), sig1 = B[1][j].x * B[1][j].x;
+#pragma unroll
+        for (int k = j + 1; k <= N; ++k) { sr[k] = B[0][j].x * B[0][k].x; si[k] = B[0][j].x * B[0][k].y; }
+        sig0 = fma(B[0][j].y, B[0][j].y, sig0);
+        sig1 = fma(B[1][j].y, B[1][j].y, sig1);
+#pragma unroll
+        for (int k = j + 1; k <= N; ++k) { sr[k] = fma(B[0][j].y, B[0][k].y, sr[k]); si[k] = fma(-B[0][j].y, B[0][k].x, si[k]); }
+        sig0 = fma(B[2][j].x, B[2][j].x, sig0);
+        sig1 = fma(B[3][j].x, B[3][j].x, sig1);
+#pragma unroll
+        for (int k = j + 1; k <= N; ++k) { sr[k] = fma(B[1][j].x, B[1][k].x, sr[k]); si[k] = fma(B[1][j].x, B[1][k].y, si[k]); }
+        sig0 = fma(B[2][j].y, B[2][j].y, sig0);
+        sig1 = fma(B[3][j].y, B[3][j].y, sig1);
+#pragma unroll
+        for (int k = j + 1; k <= N; ++k) { sr[k] = fma(B[1][j].y, B[1][k].y, sr[k]); si[k] = fma(-B[1][j].y, B[1][k].x, si[k]); }
+        const double t = fma(r, r, sig0 + sig1);
+#pragma unroll
+        for (int i = 2; i < 4; ++i) {
+#pragma unroll
+            for (int k = j + 1; k <= N; ++k) { sr[k] = fma(B[i][j].x, B[i][k].x, sr[k]); si[k] = fma(B[i][j].x, B[i][k].y, si[k]); }
+#pragma unroll
+            for (int k = j + 1; k <= N; ++k) { sr[k] = fma(B[i][j].y, B[i][k].y, sr[k]); si[k] = fma(-B[i][j].y, B[i][k].x, si[k]); }
+        }
+        // (B)
+#ifdef QNMFIT_ABL_NOSCALAR
+        const double y = 1.0;
+#else
+        const double y = qf_rsqrt(t);
+#endif
+        const double nrm = t * y;
+        const double ar = fabs(r);
+        const double v0 = copysign(ar + nrm, r);          // v = [v0; b]
+        const double den = nrm * (ar + nrm);              // v^H v / 2
+#ifdef QNMFIT_ABL_NOSCALAR
+        const double beta = den;
+#else
+        const double beta = qf_rcp(den);
+#endif
+        Rd[j * THREADS] = -copysign(nrm, r);
+        // (C)
+#pragma unroll
+        for (int k = j + 1; k <= N; ++k) {
+            double2 Rjk = Ro[LY::pair(j, k) * THREADS];
+            const double pr = fma(v0, Rjk.x, sr[k]) * beta;
+            const double pi = fma(v0, Rjk.y, si[k]) * beta;
+            Rjk.x = fma(-v0, pr, Rjk.x);
+            Rjk.y = fma(-v0, pi, Rjk.y);
+            Ro[LY::pair(j, k) * THREADS] = Rjk;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double bx = B[i][k].x, by = B[i][k].y;
+                bx = fma(-pr, B[i][j].x, bx);
+                by = fma(-pr, B[i][j].y, by);
+                bx = fma(pi, B[i][j].y, bx);
+                by = fma(-pi, B[i][j].x, by);
+                B[i][k].x = bx;
+                B[i][k].y = by;
+            }
+        }
+    }
+#endif
+}
+
 // Zero the lane's factor.
 template <int N, int THREADS>
 QF_HD void small_clear(const SmallSmem<N, THREADS> &sm, int tid)
@@ -304,13 +383,23 @@ QF_HD void small_acc_rhs(const double2 (&B)[4][N + 1], double &acc)
     }
 }
 
+// Same, as two independent chains (rows 0-1 and rows 2-3).
+template <int N>
+QF_HD void small_acc_rhs2(const double2 (&B)[4][N + 1], double &a0, double &a1)
+{
+    a0 = fma(B[0][N].x, B[0][N].x, a0); a1 = fma(B[2][N].x, B[2][N].x, a1);
+    a0 = fma(B[0][N].y, B[0][N].y, a0); a1 = fma(B[2][N].y, B[2][N].y, a1);
+    a0 = fma(B[1][N].x, B[1][N].x, a0); a1 = fma(B[3][N].x, B[3][N].x, a1);
+    a0 = fma(B[1][N].y, B[1][N].y, a0); a1 = fma(B[3][N].y, B[3][N].y, a1);
+}
+
 // Leaf stage, general form: any grid (direct evaluation of every element when
 // dt_nominal == 0), ragged blocks, per-block anchor test.
 template <int N, int THREADS>
 QF_HD void small_leaf_generic(const FitParams &p, const SmallSmem<N, THREADS> &sm, const SmallLane &L, int tid,
                               SmallAcc &acc)
 {
-    int ablk = (p.anchor_rows > 0 ? p.anchor_rows : 64) / 4;
+    int ablk = (p.anchor_rows > 0 ? p.anchor_rows : QNMFIT_DEFAULT_ANCHOR_ROWS) / 4;
     if (ablk < 1) ablk = 1;
     SmallGen<N> g;
 #pragma unroll
@@ -342,13 +431,14 @@ QF_HD void small_leaf_uniform(const FitParams &p, const SmallSmem<N, THREADS> &s
     const double2 *om = sm.om + L.slot, *qq = sm.qq + L.slot, *qw = sm.qw + L.slot;
     const int fpc = sm.fpc;
     const double dt = p.dt_nominal, t0 = L.t0;
-    int ablk = (p.anchor_rows > 0 ? p.anchor_rows : 64) / 4;
+    int ablk = (p.anchor_rows > 0 ? p.anchor_rows : QNMFIT_DEFAULT_ANCHOR_ROWS) / 4;
     if (ablk < 1) ablk = 1;
     const int nfull = (L.hi - L.lo) >> 2;
     const int last = L.re - 1;
     int row0 = L.lo;
     double2 z[N];
     double2 B[4][N + 1];
+    double sdd1 = 0.0, res1 = 0.0;   // second accumulation chains
 #pragma unroll 1
     for (int blk = 0; blk < nfull;) {
         const int nb = nfull - blk < ablk ? nfull - blk : ablk;
@@ -386,9 +476,9 @@ QF_HD void small_leaf_uniform(const FitParams &p, const SmallSmem<N, THREADS> &s
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { B[i][j] = z[j]; z[j].x += de[i]; }
 #endif
-            small_acc_rhs<N>(B, acc.sdd);
+            small_acc_rhs2<N>(B, acc.sdd, sdd1);
             small_absorb<N, THREADS, 0>(B, sm.Rd + tid, sm.Ro + tid);
-            small_acc_rhs<N>(B, acc.res2);
+            small_acc_rhs2<N>(B, acc.res2, res1);
             row0 += 4;
         }
         blk += nb;
@@ -417,6 +507,8 @@ QF_HD void small_leaf_uniform(const FitParams &p, const SmallSmem<N, THREADS> &s
         small_absorb<N, THREADS, 0>(B, sm.Rd + tid, sm.Ro + tid);
         small_acc_rhs<N>(B, acc.res2);
     }
+    acc.sdd += sdd1;
+    acc.res2 += res1;
 }
 
 // Leaf stage: sequential TSQR over the lane's rows.
@@ -430,19 +522,16 @@ QF_HD void small_leaf(const FitParams &p, const SmallSmem<N, THREADS> &sm, const
     else small_leaf_generic<N, THREADS>(p, sm, L, tid, acc);
 }
 
-// One level of the R-combine: lanes with lf % (2 s) == 0 absorb the factor of lane lf + s.
-template <int N, int THREADS>
-QF_HD void small_tree_level(const FitParams &p, const SmallSmem<N, THREADS> &sm, const SmallLane &L,
-                            int tid, int s, SmallAcc &acc)
+// Absorb rows B0..B0+3 of the partner's triangle (rows >= N are zero rows).  Row r of a
+// triangle is zero left of column r, so the reflections can start at column B0.
+template <int N, int THREADS, int B0>
+QF_HD void small_tree_block(const SmallSmem<N, THREADS> &sm, int tid, int pt, SmallAcc &acc)
 {
-    if (L.fit < 0 || (L.lf % (2 * s)) != 0) return;
-    const int pt = tid + s;   // partner lane (same warp, same fit)
-    double2 B[4][N + 1];
-#pragma unroll 1
-    for (int b0 = 0; b0 < N; b0 += 4) {
+    if constexpr (B0 < N) {
+        double2 B[4][N + 1];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int row = b0 + i;
+            const int row = B0 + i;
 #pragma unroll
             for (int k = 0; k <= N; ++k) {
                 double2 v = make_double2(0.0, 0.0);
@@ -453,9 +542,20 @@ QF_HD void small_tree_level(const FitParams &p, const SmallSmem<N, THREADS> &sm,
                 B[i][k] = v;
             }
         }
-        small_absorb<N, THREADS, 0>(B, sm.Rd + tid, sm.Ro + tid);
+        small_absorb<N, THREADS, B0>(B, sm.Rd + tid, sm.Ro + tid);
         small_acc_rhs<N>(B, acc.res2);
+        small_tree_block<N, THREADS, B0 + 4>(sm, tid, pt, acc);
     }
+}
+
+// One level of the R-combine: lanes with lf % (2 s) == 0 absorb the factor of lane lf + s.
+template <int N, int THREADS>
+QF_HD void small_tree_level(const FitParams &p, const SmallSmem<N, THREADS> &sm, const SmallLane &L,
+                            int tid, int s, SmallAcc &acc)
+{
+    if (L.fit < 0 || (L.lf % (2 * s)) != 0) return;
+    const int pt = tid + s;   // partner lane (same warp, same fit)
+    small_tree_block<N, THREADS, 0>(sm, tid, pt, acc);
 }
 
 // Back-substitution by lane 0 of the fit; leaves C in the rhs slots of lane 0.
@@ -535,7 +635,7 @@ QF_HD void small_eval(const FitParams &p, const SmallSmem<N, THREADS> &sm, const
 #pragma unroll
         for (int j = 0; j < N; ++j) C[j] = sm.Ro[LY::pair(j, N) * THREADS + t0lane];
     }
-    int ablk = (p.anchor_rows > 0 ? p.anchor_rows : 64) / 4;
+    int ablk = (p.anchor_rows > 0 ? p.anchor_rows : QNMFIT_DEFAULT_ANCHOR_ROWS) / 4;
     if (ablk < 1) ablk = 1;
     SmallGen<N> g;
 #pragma unroll

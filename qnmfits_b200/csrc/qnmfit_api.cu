@@ -283,7 +283,7 @@ static void fill_params(const qnmfit_batch *b, const Plan &pl, bool eval, FitPar
     p->mf_index = b->mf_index; p->n_chi = b->n_chi > 0 ? b->n_chi : 1; p->n_mf = b->n_mf;
     p->n_constituents = b->n_constituents;
     p->coef = (const double2 *)b->coef; p->coef_index = b->coef_index; p->n_coef = b->n_coef;
-    p->anchor_rows = b->anchor_rows > 0 ? b->anchor_rows : 64;
+    p->anchor_rows = b->anchor_rows > 0 ? b->anchor_rows : QNMFIT_DEFAULT_ANCHOR_ROWS;
     p->dt_nominal = b->dt_nominal;
     p->C = (double2 *)b->C; p->mismatch = b->mismatch; p->residual = b->residual;
     p->R = (double2 *)b->R; p->status = b->status;

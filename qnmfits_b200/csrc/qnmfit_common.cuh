@@ -8,6 +8,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include "qnmfit.h"
 
 #ifdef QNMFIT_HOSTSIM
 struct double2 { double x, y; };

@@ -28,7 +28,7 @@ static void fill_params(const qnmfit_batch *b, int lpf, bool eval, FitParams *p)
     p->inv_Mf = b->inv_Mf; p->delta_factor = b->delta_factor; p->chi_index = b->chi_index;
     p->mf_index = b->mf_index; p->n_chi = b->n_chi > 0 ? b->n_chi : 1; p->n_mf = b->n_mf;
     p->n_constituents = b->n_constituents;
-    p->anchor_rows = b->anchor_rows > 0 ? b->anchor_rows : 64;
+    p->anchor_rows = b->anchor_rows > 0 ? b->anchor_rows : QNMFIT_DEFAULT_ANCHOR_ROWS;
     p->dt_nominal = b->dt_nominal;
     p->C = (double2 *)b->C; p->mismatch = b->mismatch; p->residual = b->residual;
     p->R = (double2 *)b->R; p->status = b->status;

@@ -17,8 +17,7 @@ OUT = os.path.join(ROOT, "tools", "_variants")
 
 VARIANTS = {
     "base": [],
-    "t128x1": ["-DK1_THREADS=128", "-DK1_FORCE_CPS=1"],
-    "t192x1": ["-DK1_THREADS=192", "-DK1_FORCE_CPS=1"],
+    "absv1": ["-DQNMFIT_ABSORB_V1"],
 }
 
 
