@@ -68,6 +68,7 @@ extern "C" {
 #define QNMFIT_KERNEL_AUTO    0
 #define QNMFIT_KERNEL_SMALL   1      /* K1: n_series == 1 and n_modes <= 8         */
 #define QNMFIT_KERNEL_GENERAL 2      /* K2: any n_series, n_modes <= 64            */
+#define QNMFIT_KERNEL_STRUCT  3      /* K3: n_modes + n_series <= 64, structured QR */
 
 typedef struct qnmfit_ctx qnmfit_ctx;
 

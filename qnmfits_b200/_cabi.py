@@ -14,7 +14,7 @@ ABI_VERSION = 1
 MAX_MODES_SMALL = 8
 MAX_MODES = 64
 
-KERNEL_AUTO, KERNEL_SMALL, KERNEL_GENERAL = 0, 1, 2
+KERNEL_AUTO, KERNEL_SMALL, KERNEL_GENERAL, KERNEL_STRUCT = 0, 1, 2, 3
 
 ST_RANK_DEFICIENT, ST_NONFINITE, ST_UNDERDETERMINED = 1, 2, 4
 

@@ -11,6 +11,7 @@
 #include "qnmfit.h"
 #include "fit_small.cuh"
 #include "fit_general.cuh"
+#include "fit_struct.cuh"
 
 #ifndef K1_THREADS
 #define K1_THREADS 256
@@ -70,6 +71,24 @@ static small_kernel_t small_kernel(int N, bool staged)
     return nullptr;
 }
 
+typedef void (*struct_kernel_t)(const FitParams);
+
+static int struct_group(int ncols)   // lanes per column of K3
+{
+    return ncols > 32 ? 4 : ncols > 16 ? 8 : ncols > 8 ? 16 : 32;
+}
+
+static struct_kernel_t struct_kernel(int G)
+{
+    switch (G) {
+    case 4: return fit_struct_kernel<4>;
+    case 8: return fit_struct_kernel<8>;
+    case 16: return fit_struct_kernel<16>;
+    case 32: return fit_struct_kernel<32>;
+    }
+    return nullptr;
+}
+
 static size_t small_smem_bytes(int N, int fpc, int stage_rows)
 {
     switch (N) {
@@ -125,6 +144,11 @@ extern "C" int qnmfit_create(int device, qnmfit_ctx **out)
     e = cudaFuncSetAttribute((const void *)fit_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              ctx->smem_optin);
     if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaFuncSetAttribute(K2)"); delete ctx; return r; }
+    for (int G = 4; G <= 32; G *= 2) {
+        e = cudaFuncSetAttribute((const void *)struct_kernel(G), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 ctx->smem_optin);
+        if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaFuncSetAttribute(K3)"); delete ctx; return r; }
+    }
     *out = ctx;
     return 0;
 }
@@ -207,11 +231,16 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
     memset(pl, 0, sizeof(*pl));
     int kernel = b->kernel;
     const bool small_ok = b->n_series == 1 && b->n_modes <= QNMFIT_MAX_MODES_SMALL && !b->coef;
-    if (kernel == QNMFIT_KERNEL_AUTO) kernel = small_ok ? QNMFIT_KERNEL_SMALL : QNMFIT_KERNEL_GENERAL;
+    const bool struct_ok = b->n_modes + b->n_series <= 64
+        && StructSmem::bytes(b->n_modes, b->n_series, K3_RPT * struct_group(b->n_modes + b->n_series)) <= (size_t)ctx->smem_optin;
+    if (kernel == QNMFIT_KERNEL_AUTO)
+        kernel = small_ok ? QNMFIT_KERNEL_SMALL : struct_ok ? QNMFIT_KERNEL_STRUCT : QNMFIT_KERNEL_GENERAL;
+    if (kernel == QNMFIT_KERNEL_STRUCT && !struct_ok)
+        return fail(ctx, QNMFIT_E_SHAPE, "K3 needs n_modes + n_series <= 64 (got %d + %d)", b->n_modes, b->n_series);
     if (kernel == QNMFIT_KERNEL_SMALL && !small_ok)
         return fail(ctx, QNMFIT_E_SHAPE, "K1 needs n_series == 1, n_modes <= %d and no coef table",
                     QNMFIT_MAX_MODES_SMALL);
-    if (kernel != QNMFIT_KERNEL_SMALL && kernel != QNMFIT_KERNEL_GENERAL)
+    if (kernel != QNMFIT_KERNEL_SMALL && kernel != QNMFIT_KERNEL_GENERAL && kernel != QNMFIT_KERNEL_STRUCT)
         return fail(ctx, QNMFIT_E_SHAPE, "unknown kernel id %d", b->kernel);
     pl->kernel = kernel;
     const int N = b->n_modes;
@@ -249,6 +278,11 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
             }
         }
         if (best >= 1e300) return fail(ctx, QNMFIT_E_SHAPE, "K1: no lanes-per-fit choice fits shared memory");
+    } else if (kernel == QNMFIT_KERNEL_STRUCT) {
+        const int G = struct_group(b->n_modes + b->n_series);
+        pl->lpf = G; pl->TR = K3_RPT * G;
+        pl->smem = StructSmem::bytes(b->n_modes, b->n_series, pl->TR);
+        pl->grid = b->n_fits; pl->block = K3_THREADS;
     } else {
         const int L = b->n_series;
         int TR = 128;
@@ -290,7 +324,7 @@ static void fill_params(const qnmfit_batch *b, const Plan &pl, bool eval, FitPar
     p->model = (double2 *)b->model; p->model_stride = b->model_stride; p->omega_shared = b->omega_shared;
     p->flagged_count = b->flagged_count;
     p->lanes_per_fit = pl.lpf; p->eval_only = eval ? 1 : 0;
-    p->fast_mismatch = (pl.kernel == QNMFIT_KERNEL_SMALL && !eval && b->uniform_weights && b->dt_nominal > 0.0 && !b->model) ? 1 : 0;
+    p->fast_mismatch = (pl.kernel != QNMFIT_KERNEL_GENERAL && !eval && b->uniform_weights && b->dt_nominal > 0.0 && !b->model) ? 1 : 0;
     p->stage_begin = pl.stage_begin; p->stage_rows = pl.stage_rows;
 }
 
@@ -308,6 +342,9 @@ static int launch(qnmfit_ctx *ctx, const qnmfit_batch *b, void *stream, bool eva
     cudaStream_t st = (cudaStream_t)stream;
     if (pl.kernel == QNMFIT_KERNEL_SMALL) {
         small_kernel_t k = small_kernel(b->n_modes, pl.staged);
+        k<<<pl.grid, pl.block, pl.smem, st>>>(p);
+    } else if (pl.kernel == QNMFIT_KERNEL_STRUCT) {
+        struct_kernel_t k = struct_kernel(pl.lpf);
         k<<<pl.grid, pl.block, pl.smem, st>>>(p);
     } else {
         fit_general_kernel<<<pl.grid, pl.block, pl.smem, st>>>(p, pl.TR, pl.TK);
@@ -338,10 +375,11 @@ extern "C" int qnmfit_plan_batch(qnmfit_ctx *ctx, const qnmfit_batch *b, qnmfit_
     memset(out, 0, sizeof(*out));
     out->kernel = pl.kernel; out->lanes_per_fit = pl.lpf; out->grid = pl.grid; out->block = pl.block;
     out->smem_bytes = (int32_t)pl.smem; out->staged = pl.staged ? 1 : 0;
-    out->fast_mismatch = (pl.kernel == QNMFIT_KERNEL_SMALL && b->uniform_weights && b->dt_nominal > 0.0 && !b->model) ? 1 : 0;
+    out->fast_mismatch = (pl.kernel != QNMFIT_KERNEL_GENERAL && b->uniform_weights && b->dt_nominal > 0.0 && !b->model) ? 1 : 0;
     cudaFuncAttributes fa;
     const void *fn = pl.kernel == QNMFIT_KERNEL_SMALL ? (const void *)small_kernel(b->n_modes, pl.staged)
-                                                      : (const void *)fit_general_kernel;
+                   : pl.kernel == QNMFIT_KERNEL_STRUCT ? (const void *)struct_kernel(pl.lpf)
+                                                       : (const void *)fit_general_kernel;
     cudaError_t e = cudaFuncGetAttributes(&fa, fn);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaFuncGetAttributes");
     out->regs_per_thread = fa.numRegs;

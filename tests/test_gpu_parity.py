@@ -231,3 +231,103 @@ def test_errors_are_reported_not_swallowed(qf, eng):
     with pytest.raises(ValueError):
         qf.ringdown_fit(np.linspace(0, 1, 5), np.ones(5, complex), [(2, 2, 0, 1)], 1.0, 0.5, 0.0,
                         t0_method="nearest")
+
+
+def _synthetic_stack(N, L, K_tot, seed, uniform=True):
+    """Well-separated damped sinusoids, random mixing table, injected model + noise."""
+    rng = np.random.default_rng(seed)
+    if uniform:
+        times = np.arange(K_tot) * 0.1
+    else:
+        times = np.cumsum(0.05 + 0.1 * rng.random(K_tot))
+    freq = np.linspace(-0.1 * N, 0.1 * N, N) + 0.013 * rng.standard_normal(N) - 1j * (0.02 + 0.06 * rng.random(N))
+    coef = rng.standard_normal((L, N)) + 1j * rng.standard_normal((L, N))
+    C = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    E = np.exp(-1j * np.outer(times - times[3], freq))
+    data = np.stack([E @ (coef[i] * C) for i in range(L)])
+    data += 1e-5 * (rng.standard_normal(data.shape) + 1j * rng.standard_normal(data.shape))
+    return times, data, freq, coef
+
+
+@pytest.mark.parametrize("N,L,use_coef", [(3, 2, True), (12, 1, False), (12, 1, True), (20, 5, True),
+                                           (40, 21, True), (63, 1, False), (9, 7, True)])
+def test_struct_kernel_vs_oracle_and_general_kernel(qf, eng, N, L, use_coef):
+    """K3 (structured two-phase QR) for every lanes-per-column variant, uniform (fast
+    mismatch and second pass) and non-uniform grids, against numpy lstsq on the explicit
+    stacked matrix and against K2."""
+    import torch
+    K_tot = 700
+    for uniform in (True, False):
+        times, data, freq, coef = _synthetic_stack(N, L, K_tot, seed=N * 100 + L, uniform=uniform)
+        rb, re, t0 = 3, 3 + 613, float(times[3])          # 613 rows: not a multiple of any tile height
+        a, C_ref, res_ref, rank, s, model = orc.lstsq_fit(times[rb:re], data[:, rb:re].reshape(-1), freq, t0,
+                                                          coef if (use_coef or L > 1) else None)
+        assert rank == N
+        d_m = {i: data[i, rb:re] for i in range(L)}
+        m_m = {i: model[i * (re - rb):(i + 1) * (re - rb)] for i in range(L)}
+        mm_ref = orc.multimode_mismatch(times[rb:re], m_m, d_m)
+        d = dict(times_d=eng.to_device(times, np.float64), data_d=eng.to_device(data, np.complex128),
+                 omega_d=eng.to_device(freq.reshape(1, -1), np.complex128), omega_shared=True,
+                 n_fits=1, n_modes=N, n_series=L, row_begin_all=rb, row_end_all=re, t0_all=t0)
+        if use_coef or L > 1:
+            d.update(coef_d=eng.to_device(coef.reshape(1, L, N), np.complex128), n_coef=1,
+                     coef_index_d=eng.to_device(np.zeros(1, np.int32), np.int32))
+        tol = cases.amp_tol(s)
+        variants = [("k3_second_pass", _cabi.KERNEL_STRUCT, False), ("k2", _cabi.KERNEL_GENERAL, False)]
+        if uniform:
+            variants.insert(0, ("k3_fast", _cabi.KERNEL_STRUCT, True))
+        for name, kernel, fast in variants:
+            C_d = eng.empty((1, N), torch.complex128)
+            mm_d = eng.empty((1,), torch.float64)
+            res_d = eng.empty((1,), torch.float64)
+            st_d = eng.empty((1,), torch.int32)
+            eng.fit(eng.make_batch(kernel=kernel, dt_nominal=0.1 if uniform else 0.0, uniform_weights=fast,
+                                   C_d=C_d, mismatch_d=mm_d, residual_d=res_d, status_d=st_d, **d))
+            C = eng.to_host(C_d)[0]
+            err = np.max(np.abs(C - C_ref)) / np.max(np.abs(C_ref))
+            assert err < tol, (name, uniform, err, tol)
+            assert abs(float(eng.to_host(mm_d)[0]) - mm_ref) < MM_TOL, (name, uniform)
+            np.testing.assert_allclose(eng.to_host(res_d)[0], res_ref[0], rtol=1e-6, err_msg=name)
+            assert int(eng.to_host(st_d)[0]) == 0, name
+        plan = eng.ctx.plan(eng.make_batch(kernel=_cabi.KERNEL_AUTO, mismatch_d=mm_d, **d))
+        assert plan.kernel == (_cabi.KERNEL_STRUCT if (N > 8 or L > 1 or use_coef) else _cabi.KERNEL_SMALL)
+
+
+def test_struct_kernel_many_fits_windows_and_eval(qf, eng):
+    """K3 on a sweep: per-fit windows and start times, model output, eval-only path."""
+    import torch
+    N, L, K_tot, B = 10, 3, 500, 37
+    times, data, freq, coef = _synthetic_stack(N, L, K_tot, seed=7)
+    rng = np.random.default_rng(3)
+    rb = rng.integers(0, 60, B).astype(np.int32)
+    re = (rb + rng.integers(200, 400, B)).astype(np.int32)
+    t0 = times[rb] - 0.03
+    Kmax = int(re.max() - rb.min())     # the library sizes model rows by the union window
+    d = dict(times_d=eng.to_device(times, np.float64), data_d=eng.to_device(data, np.complex128),
+             omega_d=eng.to_device(freq.reshape(1, -1), np.complex128), omega_shared=True,
+             coef_d=eng.to_device(coef.reshape(1, L, N), np.complex128), n_coef=1,
+             coef_index_d=eng.to_device(np.zeros(B, np.int32), np.int32),
+             n_fits=B, n_modes=N, n_series=L, row_begin_all=int(rb.min()), row_end_all=int(re.max()),
+             row_begin_d=eng.to_device(rb, np.int32), row_end_d=eng.to_device(re, np.int32),
+             t0_d=eng.to_device(t0, np.float64), dt_nominal=0.1, kernel=_cabi.KERNEL_STRUCT)
+    C_d = eng.empty((B, N), torch.complex128)
+    mm_d = eng.empty((B,), torch.float64)
+    model_d = eng.empty((B, L * Kmax), torch.complex128)
+    eng.fit(eng.make_batch(C_d=C_d, mismatch_d=mm_d, model_d=model_d, model_stride=L * Kmax, **d))
+    mm_fast = eng.empty((B,), torch.float64)
+    eng.fit(eng.make_batch(mismatch_d=mm_fast, uniform_weights=True, **d))
+    mm_eval = eng.empty((B,), torch.float64)
+    eng.evaluate(eng.make_batch(C_d=C_d, mismatch_d=mm_eval, **d))
+    C, mm, model = eng.to_host(C_d), eng.to_host(mm_d), eng.to_host(model_d)
+    for b in range(B):
+        sl = slice(rb[b], re[b])
+        K = re[b] - rb[b]
+        a, C_ref, res, rank, s, m_ref = orc.lstsq_fit(times[sl], data[:, sl].reshape(-1), freq, t0[b], coef)
+        assert np.max(np.abs(C[b] - C_ref)) / np.max(np.abs(C_ref)) < cases.amp_tol(s)
+        mm_ref = orc.multimode_mismatch(times[sl], {i: m_ref[i * K:(i + 1) * K] for i in range(L)},
+                                        {i: data[i, sl] for i in range(L)})
+        assert abs(mm[b] - mm_ref) < MM_TOL
+        got = np.concatenate([model[b, i * K:(i + 1) * K] for i in range(L)])
+        np.testing.assert_allclose(got, m_ref, rtol=0, atol=1e-8 * np.max(np.abs(C_ref)))
+    np.testing.assert_allclose(eng.to_host(mm_fast), mm, rtol=0, atol=1e-11)
+    np.testing.assert_allclose(eng.to_host(mm_eval), mm, rtol=0, atol=1e-12)
