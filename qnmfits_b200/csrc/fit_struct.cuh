@@ -23,14 +23,16 @@
 // Flops per fit: 8KN^2 + 16KNL (phase 1) + ~(8/3) L N^3 (phase 2) instead of 8 (LK) N^2
 // — 4.4e7 instead of 2.9e8 at L=21, K=1000, N=40.
 //
-// Mapping.  The CTA (256 threads) owns one fit.  A tile is TR = 16 G rows; thread
-// (column c, row group g) keeps rows 16g..16g+15 of column c in registers, G lanes of a
-// warp share a column (G = 4, 8, 16, 32 chosen so that (N + L) G <= 256).  Reflection j:
-// the owner lanes reduce the column norm (xor-shuffles inside the group), form the
-// reflector scalars and publish v through shared memory (double buffered: one
-// __syncthreads per reflection); every other column forms its dot product against v in
-// registers, reduces it over its G lanes, updates its entry of row j of R (shared
-// memory) and its 16 rows.  Warps whose columns are all retired only pass the barrier.
+// Mapping.  The CTA (256 threads) owns one fit.  A tile is TR = 8 G rows; thread
+// (column pair p, row group g) keeps rows 8g..8g+7 of columns 2p and 2p+1 in registers,
+// G lanes of a warp share a column pair (G = 8, 16, 32 chosen so that ceil((N+L)/2) G
+// <= 256).  Reflection j: the owner lanes reduce the column norm (xor-shuffles inside
+// the group), form the reflector scalars and publish v through shared memory (double
+// buffered: one __syncthreads per reflection); every thread loads its 8 rows of v ONCE
+// (128 B — shared-memory bandwidth, not FP64, bounded the first version, which re-read v
+// for a single column), forms the dot products of both its columns, reduces them over
+// the G lanes, updates its entries of row j of R (shared memory) and its rows.  Warps
+// whose columns are all retired only pass the barrier.
 #pragma once
 #include "qnmfit_common.cuh"
 #include "fit_general.cuh"
@@ -39,13 +41,14 @@
 
 #define K3_THREADS 256
 #define K3_WARPS (K3_THREADS / 32)
-#define K3_RPT 16                 // rows per thread
+#define K3_RPT 8                  // rows per thread
+#define K3_VST (K3_RPT + 1)       // row-group stride of the v buffer (double2): conflict-free LDS.128
 #define K3_TK 16                  // time chunk of the second pass
 
 struct StructSmem {
     double2 *R1;      // [N][NC]    R_E (strictly upper) | Y
     double2 *R2;      // [N][N+1]   second-phase factor | Q^H d   (aliases R1 when phase 2 is skipped)
-    double2 *vbuf;    // [2][TR]
+    double2 *vbuf;    // [2][G * K3_VST]
     double2 *om, *qq, *qw;   // [N]
     double2 *coef;    // [L][N]
     double2 *Cv;      // [N]
@@ -55,20 +58,20 @@ struct StructSmem {
     double *scal;     // [2][2]     v0, beta
     double *red;      // [K3_WARPS][8]
     double *ends;     // [64][3]     end-point terms per series
-    static size_t bytes(int N, int L, int TR)
+    static size_t bytes(int N, int L, int G)
     {
         const size_t NC = (size_t)N + L;
-        return sizeof(double2) * ((size_t)N * NC + (size_t)N * (N + 1) + 2 * (size_t)TR + 3 * (size_t)N
+        return sizeof(double2) * ((size_t)N * NC + (size_t)N * (N + 1) + 2 * (size_t)G * K3_VST + 3 * (size_t)N
                                   + 2 * (size_t)L * N + N + (size_t)K3_TK * N)
              + sizeof(double) * (2 * (size_t)N + 4 + K3_WARPS * 8 + 64 * 3);
     }
-    __device__ void carve(void *base, int N, int L, int TR)
+    __device__ void carve(void *base, int N, int L, int G)
     {
         const int NC = N + L;
         double2 *p = (double2 *)base;
         R1 = p; p += N * NC;
         R2 = p; p += N * (N + 1);
-        vbuf = p; p += 2 * TR;
+        vbuf = p; p += 2 * G * K3_VST;
         om = p; p += N; qq = p; p += N; qw = p; p += N;
         coef = p; p += L * N;
         Cv = p; p += N;
@@ -83,7 +86,7 @@ struct StructSmem {
     }
 };
 
-// sum of |x|^2 over the thread's rows, four chains
+// sum of |x|^2 over the thread's rows of one column, four chains
 __device__ __forceinline__ double k3_norm2(const double2 (&X)[K3_RPT])
 {
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -97,17 +100,47 @@ __device__ __forceinline__ double k3_norm2(const double2 (&X)[K3_RPT])
     return (a0 + a1) + (a2 + a3);
 }
 
-// Reflections jstart..N-1 of [R; tile].  X: the thread's 16 rows of column c (row group
-// g).  nrm2 must hold the thread's partial |column|^2 when its column is column jstart.
-// Columns >= ncols do not exist; columns < jstart of the tile must be zero.
-template <int G>
-__device__ __forceinline__ void k3_reflect(double2 (&X)[K3_RPT], double &nrm2, const int c, const int g,
-                                           const int warp, const int ncols, const int N, const int jstart,
-                                           double2 *Rm, const int ldr, double *diag, double2 *vbuf, double *scal,
-                                           int &buf)
+// conj(v) . x over the thread's rows, two complex chains
+__device__ __forceinline__ void k3_dot(const double2 (&v)[K3_RPT], const double2 (&X)[K3_RPT], double &sr, double &si)
 {
-    constexpr int CPW = 32 / G;          // columns per warp
-    constexpr int TR = K3_RPT * G;
+    double sr0 = 0.0, si0 = 0.0, sr1 = 0.0, si1 = 0.0;
+#pragma unroll
+    for (int r = 0; r < K3_RPT; r += 2) {
+        sr0 = fma(v[r].x, X[r].x, sr0); si0 = fma(v[r].x, X[r].y, si0);
+        sr1 = fma(v[r + 1].x, X[r + 1].x, sr1); si1 = fma(v[r + 1].x, X[r + 1].y, si1);
+        sr0 = fma(v[r].y, X[r].y, sr0); si0 = fma(-v[r].y, X[r].x, si0);
+        sr1 = fma(v[r + 1].y, X[r + 1].y, sr1); si1 = fma(-v[r + 1].y, X[r + 1].x, si1);
+    }
+    sr = sr0 + sr1;
+    si = si0 + si1;
+}
+
+// x -= (pr + i pi) v
+__device__ __forceinline__ void k3_axpy(const double2 (&v)[K3_RPT], double2 (&X)[K3_RPT], double pr, double pi)
+{
+#pragma unroll
+    for (int r = 0; r < K3_RPT; ++r) {
+        double bx = X[r].x, by = X[r].y;
+        bx = fma(-pr, v[r].x, bx);
+        by = fma(-pr, v[r].y, by);
+        bx = fma(pi, v[r].y, bx);
+        by = fma(-pi, v[r].x, by);
+        X[r].x = bx;
+        X[r].y = by;
+    }
+}
+
+// Reflections jstart..N-1 of [R; tile].  X0 / X1: the thread's 8 rows of columns c0 = 2p
+// and c0 + 1 (row group g).  nrm2 must hold the thread's partial |column jstart|^2 when
+// it owns that column.  Columns >= ncols do not exist; columns < jstart of the tile
+// must be zero.
+template <int G>
+__device__ __forceinline__ void k3_reflect(double2 (&X0)[K3_RPT], double2 (&X1)[K3_RPT], double &nrm2,
+                                           const int c0, const int g, const int warp, const int ncols,
+                                           const int N, const int jstart, double2 *Rm, const int ldr,
+                                           double *diag, double2 *vbuf, double *scal, int &buf)
+{
+    constexpr int CPW = 2 * (32 / G);    // columns per warp
     const int wfirst = warp * CPW, wlast = wfirst + CPW - 1;
 #pragma unroll 1
     for (int j = jstart; j < N; ++j) {
@@ -115,7 +148,7 @@ __device__ __forceinline__ void k3_reflect(double2 (&X)[K3_RPT], double &nrm2, c
             double sig = nrm2;
 #pragma unroll
             for (int s = 1; s < G; s <<= 1) sig += __shfl_xor_sync(0xffffffffu, sig, s);
-            if (c == j) {
+            if ((j >> 1) == (c0 >> 1)) {
                 const double r = diag[j];
                 const double t = fma(r, r, sig) + 1e-300;   // see fit_small.cuh: an all-zero column needs no branch
                 const double y = qf_rsqrt(t);
@@ -128,59 +161,117 @@ __device__ __forceinline__ void k3_reflect(double2 (&X)[K3_RPT], double &nrm2, c
                     scal[buf * 2] = v0;
                     scal[buf * 2 + 1] = beta;
                 }
-                double2 *vw = vbuf + buf * TR + K3_RPT * g;
+                double2 *vw = vbuf + buf * (G * K3_VST) + K3_VST * g;
+                if (j & 1) {
 #pragma unroll
-                for (int r2 = 0; r2 < K3_RPT; ++r2) vw[r2] = X[r2];
+                    for (int r2 = 0; r2 < K3_RPT; ++r2) vw[r2] = X1[r2];
+                } else {
+#pragma unroll
+                    for (int r2 = 0; r2 < K3_RPT; ++r2) vw[r2] = X0[r2];
+                }
             }
         }
         __syncthreads();
         if (wlast > j && wfirst < ncols) {           // warp still has trailing columns
-            const bool act = c > j && c < ncols;
-            const double2 *v = vbuf + buf * TR + K3_RPT * g;
-            double sr0 = 0.0, si0 = 0.0, sr1 = 0.0, si1 = 0.0, sr2 = 0.0, si2 = 0.0, sr3 = 0.0, si3 = 0.0;
+            const bool act0 = c0 > j && c0 < ncols, act1 = c0 + 1 > j && c0 + 1 < ncols;
+            const double2 *vs = vbuf + buf * (G * K3_VST) + K3_VST * g;
+            double2 v[K3_RPT];
 #pragma unroll
-            for (int r = 0; r < K3_RPT; r += 4) {
-                const double2 b0 = v[r], b1 = v[r + 1], b2 = v[r + 2], b3 = v[r + 3];
-                sr0 = fma(b0.x, X[r].x, sr0); si0 = fma(b0.x, X[r].y, si0);
-                sr1 = fma(b1.x, X[r + 1].x, sr1); si1 = fma(b1.x, X[r + 1].y, si1);
-                sr2 = fma(b2.x, X[r + 2].x, sr2); si2 = fma(b2.x, X[r + 2].y, si2);
-                sr3 = fma(b3.x, X[r + 3].x, sr3); si3 = fma(b3.x, X[r + 3].y, si3);
-                sr0 = fma(b0.y, X[r].y, sr0); si0 = fma(-b0.y, X[r].x, si0);
-                sr1 = fma(b1.y, X[r + 1].y, sr1); si1 = fma(-b1.y, X[r + 1].x, si1);
-                sr2 = fma(b2.y, X[r + 2].y, sr2); si2 = fma(-b2.y, X[r + 2].x, si2);
-                sr3 = fma(b3.y, X[r + 3].y, sr3); si3 = fma(-b3.y, X[r + 3].x, si3);
-            }
-            double sr = (sr0 + sr1) + (sr2 + sr3), si = (si0 + si1) + (si2 + si3);
+            for (int r = 0; r < K3_RPT; ++r) v[r] = vs[r];
+            double sr0, si0, sr1, si1;
+            k3_dot(v, X0, sr0, si0);
+            k3_dot(v, X1, sr1, si1);
 #pragma unroll
             for (int s = 1; s < G; s <<= 1) {
-                sr += __shfl_xor_sync(0xffffffffu, sr, s);
-                si += __shfl_xor_sync(0xffffffffu, si, s);
+                sr0 += __shfl_xor_sync(0xffffffffu, sr0, s);
+                si0 += __shfl_xor_sync(0xffffffffu, si0, s);
+                sr1 += __shfl_xor_sync(0xffffffffu, sr1, s);
+                si1 += __shfl_xor_sync(0xffffffffu, si1, s);
             }
-            if (act) {
-                const double v0 = scal[buf * 2], beta = scal[buf * 2 + 1];
-                double2 Rjc = Rm[j * ldr + c];
-                const double pr = fma(v0, Rjc.x, sr) * beta;
-                const double pi = fma(v0, Rjc.y, si) * beta;
-                if (g == 0) {
-                    Rjc.x = fma(-v0, pr, Rjc.x);
-                    Rjc.y = fma(-v0, pi, Rjc.y);
-                    Rm[j * ldr + c] = Rjc;
-                }
-#pragma unroll
-                for (int r = 0; r < K3_RPT; ++r) {
-                    const double2 b = v[r];
-                    double bx = X[r].x, by = X[r].y;
-                    bx = fma(-pr, b.x, bx);
-                    by = fma(-pr, b.y, by);
-                    bx = fma(pi, b.y, bx);
-                    by = fma(-pi, b.x, by);
-                    X[r].x = bx;
-                    X[r].y = by;
-                }
+            const double v0 = scal[buf * 2], beta = scal[buf * 2 + 1];
+            if (act0) {
+                double2 Rjc = Rm[j * ldr + c0];
+                const double pr = fma(v0, Rjc.x, sr0) * beta;
+                const double pi = fma(v0, Rjc.y, si0) * beta;
+                if (g == 0) Rm[j * ldr + c0] = make_double2(fma(-v0, pr, Rjc.x), fma(-v0, pi, Rjc.y));
+                k3_axpy(v, X0, pr, pi);
             }
-            if (wfirst <= j + 1 && j + 1 <= wlast) nrm2 = k3_norm2(X);   // look-ahead for the next pivot
+            if (act1) {
+                double2 Rjc = Rm[j * ldr + c0 + 1];
+                const double pr = fma(v0, Rjc.x, sr1) * beta;
+                const double pi = fma(v0, Rjc.y, si1) * beta;
+                if (g == 0) Rm[j * ldr + c0 + 1] = make_double2(fma(-v0, pr, Rjc.x), fma(-v0, pi, Rjc.y));
+                k3_axpy(v, X1, pr, pi);
+            }
+            if (wfirst <= j + 1 && j + 1 <= wlast)   // look-ahead for the next pivot
+                nrm2 = ((j + 1) & 1) ? k3_norm2(X1) : k3_norm2(X0);
         }
         buf ^= 1;
+    }
+}
+
+// Rows first..first+7 of column c of the phase-1 matrix [E | d_1..d_L] (zero outside the window).
+__device__ __forceinline__ void k3_load1(double2 (&X)[K3_RPT], const FitParams &p, const StructSmem &sm, const int c,
+                                         const int N, const int NC, const int first, const int re, const double t0,
+                                         double &sdd)
+{
+    const double2 zero = make_double2(0.0, 0.0);
+    if (c < N) {
+        if (p.dt_nominal > 0.0) {
+            if (first < re) {
+                const double dt = p.dt_nominal;
+                double tau = qf_sub_rn(p.times[first], t0);
+                double2 z = design_entry(sm.om[c], tau);
+                const double2 q = sm.qq[c], w = sm.qw[c];
+#pragma unroll
+                for (int r = 0; r < K3_RPT; ++r) {
+                    X[r] = first + r < re ? z : zero;
+                    const int kn = first + r + 1 < re ? first + r + 1 : re - 1;
+                    const double tau_n = qf_sub_rn(p.times[kn], t0);
+                    const double de = qf_sub_rn(qf_sub_rn(tau_n, tau), dt);
+                    tau = tau_n;
+                    z = c_mul(z, make_double2(fma(w.x, de, q.x), fma(w.y, de, q.y)));
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < K3_RPT; ++r) X[r] = zero;
+            }
+        } else {
+#pragma unroll 1
+            for (int r = 0; r < K3_RPT; ++r) {
+                double2 e = zero;
+                if (first + r < re) e = design_entry(sm.om[c], qf_sub_rn(p.times[first + r], t0));
+#pragma unroll
+                for (int q = 0; q < K3_RPT; ++q) if (q == r) X[q] = e;   // static register index
+            }
+        }
+    } else if (c < NC) {
+        const double2 *dsrc = p.data + (long long)(c - N) * p.series_stride;
+#pragma unroll
+        for (int r = 0; r < K3_RPT; ++r) X[r] = first + r < re ? dsrc[first + r] : zero;
+        sdd += k3_norm2(X);
+    } else {
+#pragma unroll
+        for (int r = 0; r < K3_RPT; ++r) X[r] = zero;
+    }
+}
+
+// Rows q0..q0+7 of column c of the phase-2 matrix: row q = rr * L + i is row rr of
+// [R_E D_i | Y_i]  (rr-major, so that a tile's rows share their leading zeros).
+__device__ __forceinline__ void k3_load2(double2 (&X)[K3_RPT], const StructSmem &sm, const int c, const int N,
+                                         const int L, const int NC, const int q0, const int rows2)
+{
+#pragma unroll
+    for (int r = 0; r < K3_RPT; ++r) {
+        const int q = q0 + r;
+        double2 v = make_double2(0.0, 0.0);
+        if (q < rows2 && c <= N) {
+            const int rr = q / L, i = q - rr * L;
+            if (c == N) v = sm.R1[rr * NC + N + i];
+            else if (c == rr) { const double2 cf = sm.coef[i * N + c]; const double d = sm.diag1[rr]; v = make_double2(cf.x * d, cf.y * d); }
+            else if (c > rr) v = c_mul(sm.coef[i * N + c], sm.R1[rr * NC + c]);
+        }
+        X[r] = v;
     }
 }
 
@@ -188,14 +279,14 @@ template <int G>
 __global__ void __launch_bounds__(K3_THREADS, 2) fit_struct_kernel(const FitParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int CPW = 32 / G;
+    constexpr int PPW = 32 / G;            // column pairs per warp
     constexpr int TR = K3_RPT * G;
     const int N = p.n_modes, L = p.n_series, NC = N + L;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c = warp * CPW + lane / G, g = lane % G;
+    const int c0 = 2 * (warp * PPW + lane / G), g = lane % G;
     const int fit = blockIdx.x;
     StructSmem sm;
-    sm.carve(smem_raw, N, L, TR);
+    sm.carve(smem_raw, N, L, G);
 
     int rb = p.row_begin ? p.row_begin[fit] : p.row_begin_all;
     int re = p.row_end ? p.row_end[fit] : p.row_end_all;
@@ -211,14 +302,12 @@ __global__ void __launch_bounds__(K3_THREADS, 2) fit_struct_kernel(const FitPara
         coef_g = p.coef + (long long)ci * L * N;
     }
     const bool two_phase = (coef_g != nullptr) || L > 1;
-    const bool uniform = p.dt_nominal > 0.0;
-    const double dt = p.dt_nominal;
 
     for (int j = tid; j < N; j += K3_THREADS) {
         const double2 w = fit_omega(p, fit, j);
         sm.om[j] = w;
-        if (uniform) {
-            const double2 q = design_entry(w, dt);
+        if (p.dt_nominal > 0.0) {
+            const double2 q = design_entry(w, p.dt_nominal);
             sm.qq[j] = q;
             sm.qw[j] = c_mul(q, make_double2(w.y, -w.x));
         }
@@ -233,7 +322,7 @@ __global__ void __launch_bounds__(K3_THREADS, 2) fit_struct_kernel(const FitPara
     int status = 0;
     double sdd = 0.0, res2 = 0.0;
     int buf = 0;
-    double2 X[K3_RPT];
+    double2 X0[K3_RPT], X1[K3_RPT];
 
     if (!p.eval_only) {
         // ---------------- phase 1: [E | d_1..d_L] ----------------
@@ -241,48 +330,12 @@ __global__ void __launch_bounds__(K3_THREADS, 2) fit_struct_kernel(const FitPara
 #pragma unroll 1
         for (int tile = 0; tile < ntiles; ++tile) {
             const int first = rb + tile * TR + K3_RPT * g;
-            if (c < N) {
-                if (uniform) {
-                    if (first < re) {
-                        double tau = qf_sub_rn(p.times[first], t0);
-                        double2 z = design_entry(sm.om[c], tau);
-                        const double2 q = sm.qq[c], w = sm.qw[c];
-#pragma unroll
-                        for (int r = 0; r < K3_RPT; ++r) {
-                            X[r] = first + r < re ? z : make_double2(0.0, 0.0);
-                            const int kn = first + r + 1 < re ? first + r + 1 : re - 1;
-                            const double tau_n = qf_sub_rn(p.times[kn], t0);
-                            const double de = qf_sub_rn(qf_sub_rn(tau_n, tau), dt);
-                            tau = tau_n;
-                            z = c_mul(z, make_double2(fma(w.x, de, q.x), fma(w.y, de, q.y)));
-                        }
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < K3_RPT; ++r) X[r] = make_double2(0.0, 0.0);
-                    }
-                } else {
-#pragma unroll 1
-                    for (int r = 0; r < K3_RPT; ++r) {
-                        double2 e = make_double2(0.0, 0.0);
-                        if (first + r < re) e = design_entry(sm.om[c], qf_sub_rn(p.times[first + r], t0));
-                        // static register index: select into every slot
-#pragma unroll
-                        for (int q = 0; q < K3_RPT; ++q) if (q == r) X[q] = e;
-                    }
-                }
-            } else if (c < NC) {
-                const double2 *dsrc = p.data + (long long)(c - N) * p.series_stride;
-#pragma unroll
-                for (int r = 0; r < K3_RPT; ++r)
-                    X[r] = first + r < re ? dsrc[first + r] : make_double2(0.0, 0.0);
-                sdd += k3_norm2(X);
-            } else {
-#pragma unroll
-                for (int r = 0; r < K3_RPT; ++r) X[r] = make_double2(0.0, 0.0);
-            }
-            double nrm2 = (c == 0) ? k3_norm2(X) : 0.0;
-            k3_reflect<G>(X, nrm2, c, g, warp, NC, N, 0, sm.R1, NC, sm.diag1, sm.vbuf, sm.scal, buf);
-            if (c >= N && c < NC) res2 += k3_norm2(X);
+            k3_load1(X0, p, sm, c0, N, NC, first, re, t0, sdd);
+            k3_load1(X1, p, sm, c0 + 1, N, NC, first, re, t0, sdd);
+            double nrm2 = (c0 == 0) ? k3_norm2(X0) : 0.0;
+            k3_reflect<G>(X0, X1, nrm2, c0, g, warp, NC, N, 0, sm.R1, NC, sm.diag1, sm.vbuf, sm.scal, buf);
+            if (c0 >= N && c0 < NC) res2 += k3_norm2(X0);
+            if (c0 + 1 >= N && c0 + 1 < NC) res2 += k3_norm2(X1);
         }
         __syncthreads();
 
@@ -298,21 +351,14 @@ __global__ void __launch_bounds__(K3_THREADS, 2) fit_struct_kernel(const FitPara
             for (int tile = 0; tile < ntiles2; ++tile) {
                 const int q0 = tile * TR + K3_RPT * g;
                 const int jstart = (tile * TR) / L;        // first non-zero column of the tile
-#pragma unroll
-                for (int r = 0; r < K3_RPT; ++r) {
-                    const int q = q0 + r;
-                    double2 v = make_double2(0.0, 0.0);
-                    if (q < rows2 && c <= N) {
-                        const int rr = q / L, i = q - rr * L;
-                        if (c == N) v = sm.R1[rr * NC + N + i];
-                        else if (c == rr) { const double2 cf = sm.coef[i * N + c]; const double d = sm.diag1[rr]; v = make_double2(cf.x * d, cf.y * d); }
-                        else if (c > rr) v = c_mul(sm.coef[i * N + c], sm.R1[rr * NC + c]);
-                    }
-                    X[r] = v;
-                }
-                double nrm2 = (c == jstart) ? k3_norm2(X) : 0.0;
-                k3_reflect<G>(X, nrm2, c, g, warp, N + 1, N, jstart, sm.R2, N + 1, sm.diag2, sm.vbuf, sm.scal, buf);
-                if (c == N) res2 += k3_norm2(X);
+                k3_load2(X0, sm, c0, N, L, NC, q0, rows2);
+                k3_load2(X1, sm, c0 + 1, N, L, NC, q0, rows2);
+                double nrm2 = 0.0;
+                if (c0 == (jstart & ~1)) nrm2 = (jstart & 1) ? k3_norm2(X1) : k3_norm2(X0);
+                k3_reflect<G>(X0, X1, nrm2, c0, g, warp, N + 1, N, jstart, sm.R2, N + 1, sm.diag2, sm.vbuf, sm.scal,
+                              buf);
+                if (c0 == N) res2 += k3_norm2(X0);
+                if (c0 + 1 == N) res2 += k3_norm2(X1);
             }
             __syncthreads();
         }

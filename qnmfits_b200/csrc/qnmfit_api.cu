@@ -73,15 +73,14 @@ static small_kernel_t small_kernel(int N, bool staged)
 
 typedef void (*struct_kernel_t)(const FitParams);
 
-static int struct_group(int ncols)   // lanes per column of K3
+static int struct_group(int ncols)   // lanes per column pair of K3
 {
-    return ncols > 32 ? 4 : ncols > 16 ? 8 : ncols > 8 ? 16 : 32;
+    return ncols > 32 ? 8 : ncols > 16 ? 16 : 32;
 }
 
 static struct_kernel_t struct_kernel(int G)
 {
     switch (G) {
-    case 4: return fit_struct_kernel<4>;
     case 8: return fit_struct_kernel<8>;
     case 16: return fit_struct_kernel<16>;
     case 32: return fit_struct_kernel<32>;
@@ -144,7 +143,7 @@ extern "C" int qnmfit_create(int device, qnmfit_ctx **out)
     e = cudaFuncSetAttribute((const void *)fit_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              ctx->smem_optin);
     if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaFuncSetAttribute(K2)"); delete ctx; return r; }
-    for (int G = 4; G <= 32; G *= 2) {
+    for (int G = 8; G <= 32; G *= 2) {
         e = cudaFuncSetAttribute((const void *)struct_kernel(G), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  ctx->smem_optin);
         if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaFuncSetAttribute(K3)"); delete ctx; return r; }
@@ -232,7 +231,7 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
     int kernel = b->kernel;
     const bool small_ok = b->n_series == 1 && b->n_modes <= QNMFIT_MAX_MODES_SMALL && !b->coef;
     const bool struct_ok = b->n_modes + b->n_series <= 64
-        && StructSmem::bytes(b->n_modes, b->n_series, K3_RPT * struct_group(b->n_modes + b->n_series)) <= (size_t)ctx->smem_optin;
+        && StructSmem::bytes(b->n_modes, b->n_series, struct_group(b->n_modes + b->n_series)) <= (size_t)ctx->smem_optin;
     if (kernel == QNMFIT_KERNEL_AUTO)
         kernel = small_ok ? QNMFIT_KERNEL_SMALL : struct_ok ? QNMFIT_KERNEL_STRUCT : QNMFIT_KERNEL_GENERAL;
     if (kernel == QNMFIT_KERNEL_STRUCT && !struct_ok)
@@ -281,7 +280,7 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
     } else if (kernel == QNMFIT_KERNEL_STRUCT) {
         const int G = struct_group(b->n_modes + b->n_series);
         pl->lpf = G; pl->TR = K3_RPT * G;
-        pl->smem = StructSmem::bytes(b->n_modes, b->n_series, pl->TR);
+        pl->smem = StructSmem::bytes(b->n_modes, b->n_series, G);
         pl->grid = b->n_fits; pl->block = K3_THREADS;
     } else {
         const int L = b->n_series;

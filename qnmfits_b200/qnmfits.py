@@ -469,6 +469,32 @@ def _window_rows_many(times, t0_array, T_array, t0_method):
     return begin, end
 
 
+def _prepare_t0_sweep(times, data, modes, Mf, chif, t0_array, t0_method, T_array,
+                      spherical_modes, delta):
+    """Host tabulation + upload for the start-time sweep; returns the device-resident sweep."""
+    n = len(t0_array)
+    rows, keys = _series_rows(data, spherical_modes)
+    begin, end = _window_rows_many(times, t0_array, np.asarray(T_array, dtype=float), t0_method)
+    if np.any(end <= begin):
+        raise ValueError("an analysis window is empty")
+
+    if keys is None:
+        frequencies = _delta_factor(delta, len(modes)) * np.array(
+            qnm.omega_list(modes, chif, Mf))
+        coef = None
+    else:
+        frequencies = np.array(qnm.omega_list(modes, chif, Mf))
+        mu_lists = _mu_lists(keys, modes, chif)
+        coef = np.array([[complex(v) for v in row] for row in mu_lists],
+                        dtype=complex).reshape(1, len(keys), len(modes))
+    return _Sweep(
+        np.asarray(times, dtype=float), rows, n_fits=n, n_modes=len(modes),
+        windows=(begin, end), t0s=t0_array,
+        freq_arrays=dict(omega_d=(frequencies.reshape(1, -1), np.complex128)),
+        freq_scalars=dict(omega_shared=True), coef=coef,
+        coef_per_chi=False, wmax=float(np.max(np.abs(frequencies))))
+
+
 def mismatch_t0_array(times, data, modes, Mf, chif, t0_array, t0_method='geq',
                       T_array=100, spherical_modes=None, delta=0.0):
     """Mismatch for an array of start times (reference qnmfits.py:1183-1301).
@@ -506,26 +532,10 @@ def mismatch_t0_array(times, data, modes, Mf, chif, t0_array, t0_method='geq',
                                delta)['mismatch'])
         return out
 
-    rows, keys = _series_rows(data, spherical_modes)
-    begin, end = _window_rows_many(times, t0_array, np.asarray(T_array, dtype=float), t0_method)
-    if np.any(end <= begin):
-        raise ValueError("an analysis window is empty")
-
-    if keys is None:
-        frequencies = _delta_factor(delta, len(modes)) * np.array(
-            qnm.omega_list(modes, chif, Mf))
-        coef = None
-    else:
-        frequencies = np.array(qnm.omega_list(modes, chif, Mf))
-        mu_lists = _mu_lists(keys, modes, chif)
-        coef = np.array([[complex(v) for v in row] for row in mu_lists],
-                        dtype=complex).reshape(1, len(keys), len(modes))
-    mm, status = _sweep_on_device(
-        np.asarray(times, dtype=float), rows, n_fits=n, n_modes=len(modes),
-        windows=(begin, end), t0s=t0_array,
-        freq_arrays=dict(omega_d=(frequencies.reshape(1, -1), np.complex128)),
-        freq_scalars=dict(omega_shared=True), coef=coef,
-        coef_per_chi=False, wmax=float(np.max(np.abs(frequencies))))
+    sweep = _prepare_t0_sweep(times, data, modes, Mf, chif, t0_array, t0_method, T_array,
+                              spherical_modes, delta)
+    sweep.launch()
+    mm, status = sweep.fetch()
     _warn_status(status, "mismatch_t0_array")
     return [np.float64(v) for v in mm]
 
