@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define QNMFIT_ABI_VERSION 1
+#define QNMFIT_ABI_VERSION 2
 
 /* limits of the compiled kernels */
 #define QNMFIT_MAX_MODES_SMALL 8     /* register-resident TSQR kernel (K1)   */
@@ -148,6 +148,13 @@ typedef struct qnmfit_batch {
     double  *flagged_count;   /* f64 [1] or NULL: incremented (atomicAdd) once per fit
                                  whose status word is non-zero; lets a sweep detect
                                  flagged fits without copying status[] back           */
+
+    const int32_t *series_index; /* i32 [B] or NULL.  K1 only (n_series == 1): fit b reads
+                                 its data from row series_index[b] of data[][] (row
+                                 stride series_stride) instead of row 0 — one launch
+                                 over many waveforms, as the batched free-frequency
+                                 search needs (reference qnmfits.py:1905-2043 calls the
+                                 fit once per waveform and optimiser step)             */
 } qnmfit_batch;
 
 /* Create / destroy a context bound to one CUDA device (one process per GPU). */

@@ -274,3 +274,24 @@ def mismatch_M_chi_grid(tables, times, data, modes, Mf_minmax, chif_minmax, t0,
     if flat_indices is None:
         out = np.reshape(out, (len(Mf_array), len(chif_array)))
     return out
+
+
+def free_frequency_fit(tables, times, data, t0, modes=(), Mf=None, chif=None, t0_method='geq',
+                       T=100, min_method='Nelder-Mead', return_result=False):
+    """qnmfits/qnmfits.py:1972-2043: scipy minimize over (Re w, Im w) of the mismatch of a
+    fit with the fixed modes plus one free frequency; x0 = [1, -0.5], bounds
+    [(0, 2), (-1, 0)], xatol = 1e-8."""
+    from scipy.optimize import minimize
+    sel = window(times, t0, T, t0_method)
+    t_m, d_m = times[sel], data[sel]
+    fixed = np.array(tables.omega_list(list(modes), chif, Mf)) if len(modes) else np.zeros(0, complex)
+
+    def mismatch_f_tau(x):
+        frequencies = np.hstack([fixed, x[0] + 1j * x[1]])
+        a, C, res, rank, s, model = lstsq_fit(t_m, d_m, frequencies, t0)
+        return mismatch(t_m, model, d_m)
+
+    res = minimize(mismatch_f_tau, [1, -0.5], method=min_method, bounds=[(0, 2), (-1, 0)],
+                   options={'xatol': 1e-8, 'disp': False})
+    omega = res.x[0] + 1j * res.x[1]
+    return (omega, res) if return_result else omega

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libqnmfit.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_MODES_SMALL = 8
 MAX_MODES = 64
 
@@ -45,6 +45,7 @@ class Batch(C.Structure):
         ("model", _dp), ("model_stride", C.c_int64),
         ("uniform_weights", C.c_int32), ("reserved1", C.c_int32),
         ("flagged_count", _dp),
+        ("series_index", _dp),
     ]
 
     def __init__(self, **kw):

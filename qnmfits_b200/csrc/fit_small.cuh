@@ -86,9 +86,10 @@ struct SmallLane {
     int lo, hi;     // rows of this lane
     int nblk;       // 4-row blocks of this lane (same for all lanes of a fit)
     double t0;
+    long long d_off;   // element offset of the fit's own data series (series_index; 0 when shared)
 };
 
-QF_HD SmallLane small_lane_setup(const FitParams &p, int cta, int tid, int threads)
+QF_HD SmallLane small_lane_setup(const FitParams &p, int cta, int tid, int threads, bool per_fit_data = true)
 {
     SmallLane L;
     const int lpf = p.lanes_per_fit;
@@ -100,7 +101,9 @@ QF_HD SmallLane small_lane_setup(const FitParams &p, int cta, int tid, int threa
     L.rb = L.re = L.lo = L.hi = 0;
     L.nblk = 0;
     L.t0 = 0.0;
+    L.d_off = 0;
     if (L.fit >= 0) {
+        if (per_fit_data && p.series_index) L.d_off = (long long)p.series_index[fit] * p.series_stride;
         L.rb = p.row_begin ? p.row_begin[fit] : p.row_begin_all;
         L.re = p.row_end ? p.row_end[fit] : p.row_end_all;
         L.t0 = p.t0 ? p.t0[fit] : p.t0_all;
@@ -141,7 +144,7 @@ QF_HD void small_emit(const FitParams &p, const SmallSmem<N, THREADS> &sm, const
         const double2 zero = make_double2(0.0, 0.0);
 #pragma unroll
         for (int j = 0; j < N; ++j) B[i][j] = valid ? g.z[j] : zero;
-        B[i][N] = valid ? sm.ds[r - sm.t_off] : zero;
+        B[i][N] = valid ? sm.ds[r - sm.t_off + L.d_off] : zero;
         // advance to row r + 1 (clamped to the window; values past L.hi are unused)
         int rn = r + 1;
         if (rn > L.re - 1) rn = L.re - 1;
@@ -427,7 +430,7 @@ QF_HD void small_leaf_uniform(const FitParams &p, const SmallSmem<N, THREADS> &s
                               SmallAcc &acc)
 {
     const double *ts = sm.ts - sm.t_off;
-    const double2 *ds = sm.ds - sm.t_off;
+    const double2 *ds = sm.ds - sm.t_off + L.d_off;
     const double2 *om = sm.om + L.slot, *qq = sm.qq + L.slot, *qw = sm.qw + L.slot;
     const int fpc = sm.fpc;
     const double dt = p.dt_nominal, t0 = L.t0;
@@ -772,7 +775,7 @@ __global__ void __launch_bounds__(THREADS, 1) fit_small_kernel(const FitParams p
             }
         }
     }
-    const SmallLane L = small_lane_setup(p, blockIdx.x, tid, THREADS);
+    const SmallLane L = small_lane_setup(p, blockIdx.x, tid, THREADS, !STAGED);
     small_clear<N, THREADS>(sm, tid);
     __syncthreads();
 
@@ -798,7 +801,8 @@ __global__ void __launch_bounds__(THREADS, 1) fit_small_kernel(const FitParams p
             for (int q = 0; q < 6; ++q) part[q] += __shfl_xor_sync(0xffffffffu, part[q], s);
         }
         if (L.fit >= 0 && L.lf == 0 && L.re > L.rb)
-            small_fast_finalize(p, L, sm.ds[L.rb - sm.t_off], sm.ds[L.re - 1 - sm.t_off], part, acc.cn2, status);
+            small_fast_finalize(p, L, sm.ds[L.rb - sm.t_off + L.d_off], sm.ds[L.re - 1 - sm.t_off + L.d_off], part, acc.cn2,
+                                status);
         return;
     }
     double sums[4];

@@ -193,6 +193,8 @@ static int validate(qnmfit_ctx *ctx, const qnmfit_batch *b, bool eval)
     if (b->n_fits < 0 || b->n_modes < 1 || b->n_modes > QNMFIT_MAX_MODES || b->n_series < 1 || b->n_times < 1)
         return fail(ctx, QNMFIT_E_SHAPE, "bad sizes: n_fits=%d n_modes=%d (1..%d) n_series=%d n_times=%d",
                     b->n_fits, b->n_modes, QNMFIT_MAX_MODES, b->n_series, b->n_times);
+    if (b->series_index && (b->n_series != 1 || b->series_stride < b->n_times))
+        return fail(ctx, QNMFIT_E_SHAPE, "series_index needs n_series == 1 and series_stride >= n_times");
     if (b->n_series > 1 && b->series_stride < b->n_times)
         return fail(ctx, QNMFIT_E_SHAPE, "series_stride %lld < n_times %d", (long long)b->series_stride, b->n_times);
     if (!b->times || !b->data || !b->mismatch) return fail(ctx, QNMFIT_E_NULL, "times, data and mismatch are required");
@@ -239,6 +241,9 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
     if (kernel == QNMFIT_KERNEL_SMALL && !small_ok)
         return fail(ctx, QNMFIT_E_SHAPE, "K1 needs n_series == 1, n_modes <= %d and no coef table",
                     QNMFIT_MAX_MODES_SMALL);
+    if (b->series_index && kernel != QNMFIT_KERNEL_SMALL)
+        return fail(ctx, QNMFIT_E_SHAPE, "series_index is supported by K1 only (n_modes <= %d, no coef table)",
+                    QNMFIT_MAX_MODES_SMALL);
     if (kernel != QNMFIT_KERNEL_SMALL && kernel != QNMFIT_KERNEL_GENERAL && kernel != QNMFIT_KERNEL_STRUCT)
         return fail(ctx, QNMFIT_E_SHAPE, "unknown kernel id %d", b->kernel);
     pl->kernel = kernel;
@@ -258,8 +263,9 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
 #endif
             const size_t per_cta = ((size_t)ctx->smem_optin + 1024) / want_cps - 1024;
             size_t smem = small_smem_bytes(N, fpc, stage_rows);
-            bool staged = true;
-            if (smem > per_cta) { staged = false; smem = small_smem_bytes(N, fpc, 0); }
+            bool staged = b->series_index == nullptr;   // per-fit series are read through L1/L2
+            if (!staged) smem = small_smem_bytes(N, fpc, 0);
+            if (staged && smem > per_cta) { staged = false; smem = small_smem_bytes(N, fpc, 0); }
             if (smem > per_cta) continue;
 #ifdef K1_FORCE_CPS
             if (smem < per_cta * 6 / 10) smem = per_cta * 6 / 10;   // pad so that no more CTAs become resident
@@ -316,6 +322,7 @@ static void fill_params(const qnmfit_batch *b, const Plan &pl, bool eval, FitPar
     p->mf_index = b->mf_index; p->n_chi = b->n_chi > 0 ? b->n_chi : 1; p->n_mf = b->n_mf;
     p->n_constituents = b->n_constituents;
     p->coef = (const double2 *)b->coef; p->coef_index = b->coef_index; p->n_coef = b->n_coef;
+    p->series_index = b->series_index;
     p->anchor_rows = b->anchor_rows > 0 ? b->anchor_rows : QNMFIT_DEFAULT_ANCHOR_ROWS;
     p->dt_nominal = b->dt_nominal;
     p->C = (double2 *)b->C; p->mismatch = b->mismatch; p->residual = b->residual;

@@ -127,6 +127,7 @@ struct FitParams {
     int n_chi, n_mf, n_constituents;
     const double2 *coef;
     const int *coef_index;
+    const int *series_index;   // K1: per-fit data series (row of data[][]) or NULL
     int n_coef;
     int anchor_rows;
     double dt_nominal;

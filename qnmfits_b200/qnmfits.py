@@ -608,3 +608,111 @@ def mismatch_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0,
     mm, status = sweep.fetch()
     _warn_status(status, "mismatch_M_chi_grid")
     return np.reshape(mm, shape)
+
+
+# --------------------------------------------------------------------------
+# free-frequency search (reference qnmfits.py:1905-2043)
+
+class _FreeFrequencyObjective:
+    """The reference's ``mismatch_f_tau`` (qnmfits.py:2003-2029) for S waveforms that
+    share ``times``, window and fixed modes, resident on the device: one call evaluates
+    one trial frequency for each of any subset of the waveforms in ONE launch (K1 with
+    per-fit explicit frequencies and per-fit data rows, ``series_index``)."""
+
+    def __init__(self, times, data, t0, fixed_frequencies, t0_method, T):
+        import torch
+        times = np.asarray(times, dtype=float)
+        data = np.atleast_2d(np.asarray(data, dtype=complex))
+        if t0_method not in ('geq', 'closest'):
+            raise ValueError(
+                "Requested t0_method is not valid. Please choose between 'geq' and 'closest'")
+        if np.any(np.diff(times) < 0):
+            raise ValueError("times must be ascending")
+        self.eng = eng = get_engine()
+        self.fixed = np.asarray(fixed_frequencies, dtype=complex).reshape(-1)
+        self.N = len(self.fixed) + 1
+        self.S, K_tot = data.shape
+        if self.N > _cabi.MAX_MODES_SMALL and self.S > 1:
+            raise NotImplementedError(
+                f"batched free-frequency fits support at most {_cabi.MAX_MODES_SMALL - 1} fixed modes")
+        self.window = _window_rows(times, t0, T, t0_method)
+        if self.window[1] <= self.window[0]:
+            raise ValueError("the analysis window is empty")
+        self.t0 = float(t0)
+        self._keep, ptrs = eng.upload_packed([np.ascontiguousarray(times),
+                                              np.ascontiguousarray(data)])
+        self.times_p, self.data_p = ptrs
+        self.K_tot = K_tot
+        tw = times[self.window[0]:self.window[1]]
+        wmax = max(float(np.max(np.abs(self.fixed))) if len(self.fixed) else 0.0, abs(2 - 1j))
+        self.dt = nominal_step(tw, wmax)
+        self.uniform = uniform_weights(tw, self.dt)
+        self.mm_d = torch.empty(self.S, dtype=torch.float64, device=eng.device)
+        self.launches = 0
+
+    def __call__(self, X, idx):
+        eng = self.eng
+        n = len(idx)
+        omega = np.empty((n, self.N), dtype=np.complex128)
+        omega[:, :-1] = self.fixed
+        omega[:, -1] = X[:, 0] + 1j * X[:, 1]
+        arrays = [omega, np.ascontiguousarray(idx, dtype=np.int32) if self.S > 1 else None]
+        keep, ptrs = eng.upload_packed(arrays)
+        batch = eng.make_batch(
+            times_d=self.times_p, data_d=self.data_p, n_times=self.K_tot, series_stride=self.K_tot,
+            n_fits=n, n_modes=self.N, row_begin_all=self.window[0], row_end_all=self.window[1],
+            t0_all=self.t0, omega_d=ptrs[0], series_index_d=ptrs[1], dt_nominal=self.dt,
+            uniform_weights=self.uniform, mismatch_d=self.mm_d)
+        eng.fit(batch)
+        self.launches += 1
+        out = eng.download(self.mm_d[:n])
+        del keep
+        return out
+
+
+def free_frequency_fit_batch(times, data, t0, modes=[], Mf=None, chif=None, t0_method='geq',
+                             T=100, xatol=1e-8, return_result=False):
+    """``free_frequency_fit`` for many waveforms at once: ``data`` is (S, len(times)).
+
+    Runs S bounded Nelder-Mead searches in lock step (``_neldermead.minimize_lockstep``,
+    a restatement of the scipy routine the reference calls with x0 = [1, -0.5], bounds
+    [(0, 2), (-1, 0)], xatol = 1e-8, qnmfits.py:1995-2038); every optimiser step is one
+    batched device launch.  Returns complex128 (S,) best-fit frequencies.
+    """
+    from ._neldermead import minimize_lockstep
+    _check_modes(modes)
+    fixed = np.array(qnm.omega_list(modes, chif, Mf)) if len(modes) else np.zeros(0, complex)
+    objective = _FreeFrequencyObjective(times, data, t0, fixed, t0_method, T)
+    x0 = np.tile(np.array([1.0, -0.5]), (objective.S, 1))
+    res = minimize_lockstep(objective, x0, [(0, 2), (-1, 0)], xatol=xatol)
+    omega = res.x[:, 0] + 1j * res.x[:, 1]
+    if return_result:
+        res.launches = objective.launches
+        return omega, res
+    return omega
+
+
+def free_frequency_fit(times, data, t0, modes=[], Mf=None, chif=None, t0_method='geq',
+                       T=100, min_method='Nelder-Mead'):
+    """Complex frequency minimising the mismatch, optionally next to fixed QNMs
+    (reference qnmfits.py:1905-2043: same signature, start point, bounds and options).
+
+    'Nelder-Mead' uses the lock-step restatement of scipy's routine (identical
+    trajectory when the objective returns the same floats; the device mismatch differs
+    from numpy's by ~1e-13, so the minimiser agrees to the optimiser's own resolution).
+    Any other ``min_method`` is handed to ``scipy.optimize.minimize`` with the device
+    objective, one launch per call, exactly like the reference.
+    """
+    data = np.asarray(data)
+    if min_method == 'Nelder-Mead':
+        return complex(free_frequency_fit_batch(times, data.reshape(1, -1), t0, modes, Mf, chif,
+                                                t0_method, T)[0])
+    from scipy.optimize import minimize
+    _check_modes(modes)
+    fixed = np.array(qnm.omega_list(modes, chif, Mf)) if len(modes) else np.zeros(0, complex)
+    objective = _FreeFrequencyObjective(times, data.reshape(1, -1), t0, fixed, t0_method, T)
+    zero = np.zeros(1, dtype=np.int64)
+    res = minimize(lambda x: float(objective(np.asarray(x, dtype=float).reshape(1, 2), zero)[0]),
+                   [1, -0.5], method=min_method, bounds=[(0, 2), (-1, 0)],
+                   options={'xatol': 1e-8, 'disp': False} if min_method == 'Nelder-Mead' else {'disp': False})
+    return res.x[0] + 1j * res.x[1]

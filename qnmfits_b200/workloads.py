@@ -128,3 +128,22 @@ def config4(n_t0=500, spherical=None, modes=None, sigma=1e-6):
     return Workload("cfg4_multimode_t0_sweep", times, data, modes,
                     t0_array=np.linspace(0.0, 50.0, n_t0), spherical_modes=spherical,
                     extra={"C_true": C})
+
+
+def config5(n_waveforms=4096, n_fixed=2, sigma=1e-6):
+    """Free-frequency fitting: n_waveforms series, each = n_fixed fixed Kerr modes
+    ((2,2,0,+1), (2,2,1,+1)) + one damped sinusoid whose frequency is drawn uniformly in
+    [0.3, 1.7] x [-0.9, -0.05] (inside the optimiser's box), default_rng(2), noise sigma.
+    t0 = 0, T = 100."""
+    times = default_times()
+    modes = overtone_modes(n_fixed)
+    fixed = np.array(qnm.omega_list(modes, CHIF_TRUE, MF_TRUE)) if n_fixed else np.zeros(0, complex)
+    rng = np.random.default_rng(2)
+    w_free = rng.uniform(0.3, 1.7, n_waveforms) + 1j * rng.uniform(-0.9, -0.05, n_waveforms)
+    amps = rng.normal(size=(n_waveforms, n_fixed + 1)) + 1j * rng.normal(size=(n_waveforms, n_fixed + 1))
+    noise_rng = np.random.default_rng(3)
+    data = np.empty((n_waveforms, len(times)), dtype=complex)
+    for b in range(n_waveforms):
+        om = np.concatenate([fixed, w_free[b:b + 1]])
+        data[b] = ringdown(times, 0.0, amps[b], om) + _noise(noise_rng, len(times), sigma)
+    return Workload("cfg5_free_frequency", times, data, modes, extra={"omega_free": w_free, "amps": amps})

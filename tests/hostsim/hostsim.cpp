@@ -34,6 +34,7 @@ static void fill_params(const qnmfit_batch *b, int lpf, bool eval, FitParams *p)
     p->R = (double2 *)b->R; p->status = b->status;
     p->model = (double2 *)b->model; p->model_stride = b->model_stride; p->omega_shared = b->omega_shared;
     p->flagged_count = b->flagged_count;
+    p->series_index = b->series_index;
     p->lanes_per_fit = lpf; p->eval_only = eval ? 1 : 0;
     p->fast_mismatch = (!eval && b->uniform_weights && b->dt_nominal > 0.0 && !b->model) ? 1 : 0;
 }
@@ -96,7 +97,7 @@ static void run(const qnmfit_batch *b, int lpf, bool eval)
                 if (L.fit >= 0 && L.lf == 0 && L.re > L.rb) {
                     double p6[6];
                     for (int q = 0; q < 6; ++q) p6[q] = part[tid * 6 + q];
-                    small_fast_finalize(p, L, sm.ds[L.rb - sm.t_off], sm.ds[L.re - 1 - sm.t_off], p6, acc[tid].cn2,
+                    small_fast_finalize(p, L, sm.ds[L.rb - sm.t_off + L.d_off], sm.ds[L.re - 1 - sm.t_off + L.d_off], p6, acc[tid].cn2,
                                         status[tid]);
                 }
             }

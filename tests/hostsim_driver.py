@@ -27,7 +27,7 @@ def _p(a):
 def run(times, data, *, n_fits, n_modes, window, t0, lpf=4, eval_only=False, dt=None,
         anchor_rows=0, omega=None, omega_shared=False, table=None, mode_ptr=None, inv_Mf=None,
         delta_factor=None, n_chi=0, n_mf=0, first_fit=0, C_in=None, want_model=False,
-        uniform_weights=0):
+        uniform_weights=0, series_index=None):
     times = np.ascontiguousarray(times, dtype=float)
     data = np.ascontiguousarray(data, dtype=complex)
     keep = [times, data]
@@ -63,6 +63,10 @@ def run(times, data, *, n_fits, n_modes, window, t0, lpf=4, eval_only=False, dt=
             df = np.ascontiguousarray(delta_factor, dtype=float)
             keep.append(df)
             kw.update(delta_factor=_p(df))
+    if series_index is not None:
+        si = np.ascontiguousarray(series_index, np.int32)
+        keep.append(si)
+        kw.update(series_index=_p(si))
     if dt is None:
         dt = nominal_step(times[kw["row_begin_all"]:kw["row_end_all"]], wmax)
     Mmax = kw["row_end_all"] - kw["row_begin_all"]
@@ -74,7 +78,7 @@ def run(times, data, *, n_fits, n_modes, window, t0, lpf=4, eval_only=False, dt=
     st = np.zeros(n_fits, np.int32)
     model = np.zeros((n_fits, Mmax), complex) if want_model else None
     b = _cabi.Batch(n_fits=n_fits, n_modes=n_modes, n_series=1, n_times=len(times),
-                    series_stride=len(times), first_fit=first_fit, times=_p(times), data=_p(data),
+                    series_stride=data.shape[-1], first_fit=first_fit, times=_p(times), data=_p(data),
                     dt_nominal=float(dt), anchor_rows=anchor_rows, C=_p(Cbuf), mismatch=_p(mm),
                     residual=_p(res), R=_p(R), status=_p(st), model=_p(model),
                     model_stride=Mmax if want_model else 0, uniform_weights=int(uniform_weights), **kw)

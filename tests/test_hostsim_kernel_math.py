@@ -180,3 +180,36 @@ def test_fast_mismatch_path_equals_general_path(qf, golden):
     fast = hs.run(wl2.times, wl2.data, n_fits=40, n_modes=8, window=(begin, end), t0=wl2.t0_array,
                   lpf=8, omega=freq, omega_shared=True, uniform_weights=1)
     np.testing.assert_allclose(fast["mismatch"], g2["mismatch"], rtol=0, atol=1e-10)
+
+
+def test_per_fit_data_series_for_the_free_frequency_search(qf, oracle_tables):
+    """series_index: each fit of one launch reads its own waveform (the batched
+    free-frequency objective), explicit per-fit frequencies."""
+    from oracle import qnmfits_oracle as orc
+    wl = workloads.config5(n_waveforms=7, n_fixed=2)
+    fixed = np.array(oracle_tables.omega_list(wl.modes, wl.chif, wl.Mf))
+    rng = np.random.default_rng(4)
+    pick = np.array([6, 2, 2, 5, 0], dtype=np.int32)
+    trial = rng.uniform(0.3, 1.7, len(pick)) - 1j * rng.uniform(0.05, 0.9, len(pick))
+    omega = np.column_stack([np.tile(fixed, (len(pick), 1)), trial])
+    win = (int(np.searchsorted(wl.times, 0.0)), int(np.searchsorted(wl.times, 100.0)))
+    for uw in (0, 1):
+        out = hs.run(wl.times, wl.data, n_fits=len(pick), n_modes=3, window=win, t0=0.0, lpf=8,
+                     omega=omega, series_index=pick, uniform_weights=uw)
+        for k, b in enumerate(pick):
+            sel = orc.window(wl.times, 0.0, 100, 'geq')
+            a, C, res, rank, s, model = orc.lstsq_fit(wl.times[sel], wl.data[b][sel], omega[k], 0.0)
+            assert np.max(np.abs(out["C"][k] - C)) / np.max(np.abs(C)) < 1e-9
+            assert abs(out["mismatch"][k] - orc.mismatch(wl.times[sel], model, wl.data[b][sel])) < 1e-11
+
+
+def test_oracle_free_frequency_fit_vs_reference_golden(golden, oracle_tables):
+    """The oracle's free_frequency_fit (scipy Nelder-Mead on the numpy mismatch) against
+    what the unmodified reference returned (tests/golden/make_golden_cfg5.py)."""
+    from oracle import qnmfits_oracle as orc
+    g = golden("cfg5")
+    wl = workloads.config5(n_waveforms=3, n_fixed=1)
+    for b in range(3):
+        w = orc.free_frequency_fit(oracle_tables, wl.times, wl.data[b], 0.0, modes=wl.modes, Mf=wl.Mf,
+                                   chif=wl.chif)
+        assert abs(w - g["fixed1_omega"][b]) < 1e-12
