@@ -295,3 +295,43 @@ def free_frequency_fit(tables, times, data, t0, modes=(), Mf=None, chif=None, t0
                    options={'xatol': 1e-8, 'disp': False})
     omega = res.x[0] + 1j * res.x[1]
     return (omega, res) if return_result else omega
+
+
+def mismatch_omega_grid(tables, times, data, modes, Mf, chif, re_minmax, im_minmax, t0,
+                        t0_method='geq', T=100, res=50):
+    """qnmfits/qnmfits.py:1745-1827, including its re-masking of the already masked arrays
+    inside the loop (:1759-1768; harmless for 'geq', drops the last sample per iteration
+    for 'closest') and the final transpose (:1825)."""
+    re_array = np.linspace(re_minmax[0], re_minmax[1], res)
+    im_array = np.linspace(im_minmax[0], im_minmax[1], res)
+    fixed = list(tables.omega_list(list(modes), chif, Mf)) if len(modes) else []
+    mm_list = []
+    for i in range(len(re_array) * len(im_array)):
+        re = re_array[int(i / len(re_array))]
+        im = im_array[i % len(im_array)]
+        sel = window(times, t0, T, t0_method)
+        times, data = times[sel], data[sel]
+        frequencies = np.array(fixed + [re + 1j * im])
+        a, C, r, rank, s, model = lstsq_fit(times, data, frequencies, t0)
+        mm_list.append(mismatch(times, model, data))
+    return np.reshape(np.array(mm_list), (len(re_array), len(im_array))).T
+
+
+def calculate_epsilon(tables, times, data, modes, Mf, chif, t0, t0_method='geq', T=100,
+                      spherical_modes=None, min_method='Nelder-Mead', delta=0.0, x0=None):
+    """qnmfits/qnmfits.py:1514-1594."""
+    from scipy.optimize import minimize
+    if x0 is None:
+        x0 = [Mf, chif]
+
+    def mismatch_M_chi(x):
+        c = min(max(x[1], 0), 0.99)
+        if type(data) == dict:
+            return multimode_ringdown_fit(tables, times, data, modes, x[0], c, t0, t0_method, T,
+                                          spherical_modes)['mismatch']
+        return ringdown_fit(tables, times, data, modes, x[0], c, t0, t0_method, T, delta)['mismatch']
+
+    res = minimize(mismatch_M_chi, x0, method=min_method, bounds=[(0, 2.0), (0, 0.99)],
+                   options={'xatol': 1e-6, 'disp': False})
+    dM, dc = res.x[0] - Mf, res.x[1] - chif
+    return np.sqrt(dM**2 + dc**2), res.x[0], res.x[1]

@@ -613,61 +613,93 @@ def mismatch_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0,
 # --------------------------------------------------------------------------
 # free-frequency search (reference qnmfits.py:1905-2043)
 
-class _FreeFrequencyObjective:
-    """The reference's ``mismatch_f_tau`` (qnmfits.py:2003-2029) for S waveforms that
-    share ``times``, window and fixed modes, resident on the device: one call evaluates
-    one trial frequency for each of any subset of the waveforms in ONE launch (K1 with
-    per-fit explicit frequencies and per-fit data rows, ``series_index``)."""
+class _ResidentData:
+    """``times`` and S data rows resident on the device for repeated launches with fresh
+    frequencies: the objective of the optimiser-driven entry points (free_frequency_fit,
+    calculate_epsilon) and the frequency grid (mismatch_omega_grid)."""
 
-    def __init__(self, times, data, t0, fixed_frequencies, t0_method, T):
+    def __init__(self, times, rows, t0, t0_method, T):
         import torch
         times = np.asarray(times, dtype=float)
-        data = np.atleast_2d(np.asarray(data, dtype=complex))
+        rows = np.atleast_2d(np.asarray(rows, dtype=complex))
         if t0_method not in ('geq', 'closest'):
             raise ValueError(
                 "Requested t0_method is not valid. Please choose between 'geq' and 'closest'")
         if np.any(np.diff(times) < 0):
             raise ValueError("times must be ascending")
         self.eng = eng = get_engine()
-        self.fixed = np.asarray(fixed_frequencies, dtype=complex).reshape(-1)
-        self.N = len(self.fixed) + 1
-        self.S, K_tot = data.shape
-        if self.N > _cabi.MAX_MODES_SMALL and self.S > 1:
-            raise NotImplementedError(
-                f"batched free-frequency fits support at most {_cabi.MAX_MODES_SMALL - 1} fixed modes")
+        self.S, self.K_tot = rows.shape
         self.window = _window_rows(times, t0, T, t0_method)
         if self.window[1] <= self.window[0]:
             raise ValueError("the analysis window is empty")
         self.t0 = float(t0)
-        self._keep, ptrs = eng.upload_packed([np.ascontiguousarray(times),
-                                              np.ascontiguousarray(data)])
+        self._keep, ptrs = eng.upload_packed([np.ascontiguousarray(times), np.ascontiguousarray(rows)])
         self.times_p, self.data_p = ptrs
-        self.K_tot = K_tot
         tw = times[self.window[0]:self.window[1]]
-        wmax = max(float(np.max(np.abs(self.fixed))) if len(self.fixed) else 0.0, abs(2 - 1j))
-        self.dt = nominal_step(tw, wmax)
-        self.uniform = uniform_weights(tw, self.dt)
-        self.mm_d = torch.empty(self.S, dtype=torch.float64, device=eng.device)
+        # nominal_step() with the frequency bound applied per launch
+        self._dt = nominal_step(tw, 0.0)
+        self._dev = float(np.max(np.abs(np.diff(tw) - self._dt))) if self._dt > 0.0 else np.inf
+        self.uniform = uniform_weights(tw, self._dt)
+        self.mm_d = torch.empty(1, dtype=torch.float64, device=eng.device)
         self.launches = 0
 
-    def __call__(self, X, idx):
+    def mismatches(self, omega, coef=None, series_index=None, n_series=1, row_end=None):
+        """One launch: fit b uses frequencies omega[b] (c128 (n, N)), mixing table coef[b]
+        (c128 (n, L, N)) or none, data row series_index[b] (single-series fits) or the
+        first n_series rows; optional per-fit window ends.  Returns float64 (n,)."""
+        import torch
         eng = self.eng
-        n = len(idx)
-        omega = np.empty((n, self.N), dtype=np.complex128)
-        omega[:, :-1] = self.fixed
-        omega[:, -1] = X[:, 0] + 1j * X[:, 1]
-        arrays = [omega, np.ascontiguousarray(idx, dtype=np.int32) if self.S > 1 else None]
+        omega = np.ascontiguousarray(omega, dtype=np.complex128)
+        n, N = omega.shape
+        if N > _cabi.MAX_MODES:
+            raise ValueError(f"at most {_cabi.MAX_MODES} modes are supported, got {N}")
+        if self.mm_d.numel() < n:
+            self.mm_d = torch.empty(n, dtype=torch.float64, device=eng.device)
+        finite = np.isfinite(omega).all()
+        wmax = float(np.max(np.abs(omega))) if (n and finite) else np.inf
+        dt = self._dt if self._dev * max(wmax, 1.0) <= 4e-10 else 0.0
+        rb = re = None
+        if row_end is not None:
+            re = np.ascontiguousarray(row_end, dtype=np.int32)
+            rb = np.full(n, self.window[0], dtype=np.int32)
+        arrays = [omega,
+                  None if series_index is None else np.ascontiguousarray(series_index, dtype=np.int32),
+                  None if coef is None else np.ascontiguousarray(coef, dtype=np.complex128),
+                  None if coef is None else np.arange(n, dtype=np.int32), rb, re]
         keep, ptrs = eng.upload_packed(arrays)
         batch = eng.make_batch(
             times_d=self.times_p, data_d=self.data_p, n_times=self.K_tot, series_stride=self.K_tot,
-            n_fits=n, n_modes=self.N, row_begin_all=self.window[0], row_end_all=self.window[1],
-            t0_all=self.t0, omega_d=ptrs[0], series_index_d=ptrs[1], dt_nominal=self.dt,
-            uniform_weights=self.uniform, mismatch_d=self.mm_d)
+            n_fits=n, n_modes=N, n_series=n_series, row_begin_all=self.window[0],
+            row_end_all=self.window[1], t0_all=self.t0, omega_d=ptrs[0], series_index_d=ptrs[1],
+            coef_d=ptrs[2], coef_index_d=ptrs[3], n_coef=0 if coef is None else n,
+            row_begin_d=ptrs[4], row_end_d=ptrs[5], dt_nominal=dt,
+            uniform_weights=self.uniform and dt > 0.0, mismatch_d=self.mm_d)
         eng.fit(batch)
         self.launches += 1
         out = eng.download(self.mm_d[:n])
         del keep
         return out
+
+
+class _FreeFrequencyObjective(_ResidentData):
+    """The reference's ``mismatch_f_tau`` (qnmfits.py:2003-2029) for S waveforms that
+    share ``times``, window and fixed modes: one call evaluates one trial frequency for
+    each of any subset of the waveforms in ONE launch (K1 with per-fit explicit
+    frequencies and per-fit data rows, ``series_index``)."""
+
+    def __init__(self, times, data, t0, fixed_frequencies, t0_method, T):
+        super().__init__(times, data, t0, t0_method, T)
+        self.fixed = np.asarray(fixed_frequencies, dtype=complex).reshape(-1)
+        self.N = len(self.fixed) + 1
+        if self.N > _cabi.MAX_MODES_SMALL and self.S > 1:
+            raise NotImplementedError(
+                f"batched free-frequency fits support at most {_cabi.MAX_MODES_SMALL - 1} fixed modes")
+
+    def __call__(self, X, idx):
+        omega = np.empty((len(idx), self.N), dtype=np.complex128)
+        omega[:, :-1] = self.fixed
+        omega[:, -1] = X[:, 0] + 1j * X[:, 1]
+        return self.mismatches(omega, series_index=idx if self.S > 1 else None)
 
 
 def free_frequency_fit_batch(times, data, t0, modes=[], Mf=None, chif=None, t0_method='geq',
@@ -716,3 +748,93 @@ def free_frequency_fit(times, data, t0, modes=[], Mf=None, chif=None, t0_method=
                    [1, -0.5], method=min_method, bounds=[(0, 2), (-1, 0)],
                    options={'xatol': 1e-8, 'disp': False} if min_method == 'Nelder-Mead' else {'disp': False})
     return res.x[0] + 1j * res.x[1]
+
+
+# --------------------------------------------------------------------------
+# frequency grid and remnant search (reference qnmfits.py:1679-1827, 1418-1594)
+
+def mismatch_omega_grid(times, data, modes, Mf, chif, re_minmax, im_minmax, t0,
+                        t0_method='geq', T=100, res=50):
+    """Mismatch on a res x res grid of one additional complex frequency next to the fixed
+    ``modes`` (reference qnmfits.py:1679-1827).  Returns float64 (res, res) indexed
+    [i_im, i_re] like the reference (its final ``.T``, qnmfits.py:1825) — one launch.
+
+    Reference quirk kept for parity: with ``t0_method='closest'`` the loop re-slices the
+    already sliced arrays every iteration (qnmfits.py:1759-1768), which drops the last
+    sample each time, so grid point i is fitted on a window that is i samples shorter;
+    when it runs out of rows (res^2 > window length + modes) the reference fails inside
+    LAPACK, here a ValueError is raised before any launch.
+    """
+    _check_modes(modes)
+    re_array = np.linspace(re_minmax[0], re_minmax[1], res)
+    im_array = np.linspace(im_minmax[0], im_minmax[1], res)
+    n = len(re_array) * len(im_array)
+    if n == 0:
+        return np.reshape(np.array([]), (len(re_array), len(im_array))).T
+    fixed = np.array(qnm.omega_list(modes, chif, Mf)) if len(modes) else np.zeros(0, complex)
+    i = np.arange(n)
+    omega = np.empty((n, len(fixed) + 1), dtype=np.complex128)
+    omega[:, :-1] = fixed
+    omega[:, -1] = re_array[(i / len(re_array)).astype(int)] + 1j * im_array[i % len(im_array)]
+    resident = _ResidentData(times, np.asarray(data).reshape(1, -1), t0, t0_method, T)
+    row_end = None
+    if t0_method == 'closest':
+        row_end = resident.window[1] - i
+        if row_end[-1] - resident.window[0] < 1:
+            raise ValueError(
+                "mismatch_omega_grid with t0_method='closest' shortens the window by one sample "
+                "per grid point (reference qnmfits.py:1759-1768) and runs out of rows")
+    mm = resident.mismatches(omega, row_end=row_end)
+    return np.reshape(mm, (len(re_array), len(im_array))).T
+
+
+class _RemnantObjective(_ResidentData):
+    """``mismatch_M_chi`` of calculate_epsilon (reference qnmfits.py:1523-1540, 1554-1571):
+    mismatch of the fit at (Mf, chif), chif clipped to [0, 0.99]."""
+
+    def __init__(self, times, data, modes, t0, t0_method, T, spherical_modes, delta):
+        rows, self.keys = _series_rows(data, spherical_modes)
+        super().__init__(times, rows, t0, t0_method, T)
+        self.modes = modes
+        self.df = None if self.keys is not None else _delta_factor(delta, len(modes))
+
+    def __call__(self, X, idx=None):
+        X = np.atleast_2d(X)
+        omega = np.empty((len(X), len(self.modes)), dtype=np.complex128)
+        coef = None if self.keys is None else np.empty((len(X), len(self.keys), len(self.modes)), complex)
+        for k, (Mf, chif) in enumerate(X):
+            chif = min(max(chif, 0), 0.99)
+            omega[k] = np.array(qnm.omega_list(self.modes, chif, Mf))
+            if self.keys is None:
+                omega[k] = self.df * omega[k]
+            else:
+                coef[k] = [[complex(v) for v in row] for row in _mu_lists(self.keys, self.modes, chif)]
+        return self.mismatches(omega, coef=coef, n_series=1 if self.keys is None else len(self.keys))
+
+
+def calculate_epsilon(times, data, modes, Mf, chif, t0, t0_method='geq', T=100,
+                      spherical_modes=None, min_method='Nelder-Mead', delta=0.0, x0=None):
+    """Remnant mass and spin minimising the mismatch and their distance epsilon from
+    (Mf, chif) (reference qnmfits.py:1418-1594: same start point, bounds [(0, 2), (0, 0.99)],
+    xatol = 1e-6).  Returns (epsilon, Mf_bestfit, chif_bestfit).
+
+    Each objective call is one device fit (K1 / K3), data resident; 'Nelder-Mead' runs the
+    restatement of scipy's routine in ``_neldermead``, other methods go through scipy.
+    """
+    _check_modes(modes)
+    if x0 is None:
+        x0 = [Mf, chif]
+    bounds = [(0, 2.0), (0, 0.99)]
+    objective = _RemnantObjective(times, data, modes, t0, t0_method, T, spherical_modes, delta)
+    if min_method == 'Nelder-Mead':
+        from ._neldermead import minimize_lockstep
+        res = minimize_lockstep(objective, np.asarray(x0, dtype=float).reshape(1, 2), bounds, xatol=1e-6)
+        Mf_bestfit, chif_bestfit = res.x[0]
+    else:
+        from scipy.optimize import minimize
+        res = minimize(lambda x: float(objective(np.asarray(x, dtype=float).reshape(1, 2))[0]), x0,
+                       method=min_method, bounds=bounds, options={'disp': False})
+        Mf_bestfit, chif_bestfit = res.x
+    delta_Mf = Mf_bestfit - Mf
+    delta_chif = chif_bestfit - chif
+    return np.sqrt(delta_Mf**2 + delta_chif**2), Mf_bestfit, chif_bestfit

@@ -380,3 +380,44 @@ def test_free_frequency_objective_matches_oracle_mismatch(qf, eng, oracle_tables
         a, C, res, rank, s, model = orc.lstsq_fit(wl.times[sel], wl.data[b][sel],
                                                   np.hstack([fixed, X[k, 0] + 1j * X[k, 1]]), 0.0)
         assert abs(got[k] - orc.mismatch(wl.times[sel], model, wl.data[b][sel])) < MM_TOL
+
+
+def test_omega_grid_vs_reference_golden(qf, eng, golden):
+    """mismatch_omega_grid (reference qnmfits.py:1679-1827): orientation [i_im, i_re], no
+    fixed modes, and the 'closest' window that loses one sample per grid point."""
+    g = golden("next")
+    wl = workloads.config1()
+    m2 = wl.modes[:2]
+    got = qf.mismatch_omega_grid(wl.times, wl.data, m2, 0.95, 0.69, (0.2, 0.9), (-0.9, -0.1), 5.0, T=80, res=7)
+    assert got.shape == (7, 7)
+    np.testing.assert_allclose(got, g["omega_grid_geq"], rtol=0, atol=MM_TOL)
+    got = qf.mismatch_omega_grid(wl.times, wl.data, [], 0.95, 0.69, (0.3, 0.8), (-0.3, -0.05), 20.0, res=4)
+    np.testing.assert_allclose(got, g["omega_grid_nofixed"], rtol=0, atol=MM_TOL)
+    got = qf.mismatch_omega_grid(wl.times, wl.data, m2, 0.95, 0.69, (0.2, 0.9), (-0.9, -0.1), 3.37,
+                                 t0_method='closest', T=60, res=5)
+    np.testing.assert_allclose(got, g["omega_grid_closest"], rtol=0, atol=MM_TOL)
+    with pytest.raises(ValueError):
+        qf.mismatch_omega_grid(wl.times, wl.data, m2, 0.95, 0.69, (0.2, 0.9), (-0.9, -0.1), 3.37,
+                               t0_method='closest', T=60, res=40)
+    # a grid with more than 8 columns goes through K3 (7 fixed + 1 free is still K1)
+    big = qf.mismatch_omega_grid(wl.times, wl.data, wl.modes, 0.95, 0.69, (0.2, 0.9), (-0.9, -0.1), 5.0, T=80, res=3)
+    assert big.shape == (3, 3) and np.all(np.isfinite(big)) and np.all(big < got.max() + 1)
+
+
+def test_calculate_epsilon_vs_reference_golden(qf, eng, golden):
+    """calculate_epsilon (reference qnmfits.py:1418-1594): Nelder-Mead over (Mf, chif),
+    single series (with delta and x0) and multimode.  xatol = 1e-6 and a mismatch floor of
+    ~1e-12 give best-fit values that agree to ~1e-6."""
+    import cases as cs
+    g = golden("next")
+    wl = workloads.config1()
+    eps, Mf, chi = qf.calculate_epsilon(wl.times, wl.data, wl.modes[:4], 0.95, 0.69, 10.0)
+    np.testing.assert_allclose([eps, Mf, chi], g["eps_single"], rtol=0, atol=3e-6)
+    got = qf.calculate_epsilon(wl.times, wl.data, wl.modes[:3], 0.95, 0.69, 15.0, T=70, delta=[0.0, 0.01, 0.0],
+                               x0=[1.0, 0.6])
+    np.testing.assert_allclose(got, g["eps_single_x0_delta"], rtol=0, atol=3e-6)
+    wl4 = cs.cfg4_small()
+    got = qf.calculate_epsilon(wl4.times, wl4.data, cs.MM_MODES, 0.95, 0.69, 5.0, T=80)
+    np.testing.assert_allclose(got, g["eps_multimode"], rtol=0, atol=3e-6)
+    got = qf.calculate_epsilon(wl4.times, wl4.data, cs.MM_MODES, 0.95, 0.69, 5.0, T=80, x0=[0.97, 0.65])
+    np.testing.assert_allclose(got, g["eps_multimode_x0"], rtol=0, atol=3e-6)

@@ -83,3 +83,25 @@ def test_oracle_against_live_reference(qf, oracle_tables, reference):
             assert np.array_equal(a["model_times"], b["model_times"])
             assert rel_err(b["C"], a["C"]) < 1e-13
             assert abs(a["mismatch"] - b["mismatch"]) < 1e-15
+
+
+def test_oracle_omega_grid_and_epsilon_vs_reference_golden(golden, oracle_tables):
+    """mismatch_omega_grid (incl. the 'closest' re-slicing quirk, reference
+    qnmfits.py:1759-1768) and calculate_epsilon restated in the oracle vs the unmodified
+    reference's outputs (tests/golden/make_golden_next.py)."""
+    from qnmfits_b200 import workloads
+    g = golden("next")
+    wl = workloads.config1()
+    m2 = wl.modes[:2]
+    got = orc.mismatch_omega_grid(oracle_tables, wl.times, wl.data, m2, 0.95, 0.69, (0.2, 0.9), (-0.9, -0.1),
+                                  5.0, T=80, res=7)
+    np.testing.assert_allclose(got, g["omega_grid_geq"], rtol=0, atol=1e-15)
+    got = orc.mismatch_omega_grid(oracle_tables, wl.times, wl.data, m2, 0.95, 0.69, (0.2, 0.9), (-0.9, -0.1),
+                                  3.37, t0_method='closest', T=60, res=5)
+    np.testing.assert_allclose(got, g["omega_grid_closest"], rtol=0, atol=1e-15)
+    eps = orc.calculate_epsilon(oracle_tables, wl.times, wl.data, wl.modes[:4], 0.95, 0.69, 10.0)
+    np.testing.assert_allclose(eps, g["eps_single"], rtol=0, atol=1e-12)
+    wl4 = cases.cfg4_small()
+    eps = orc.calculate_epsilon(oracle_tables, wl4.times, wl4.data, cases.MM_MODES, 0.95, 0.69, 5.0, T=80,
+                                x0=[0.97, 0.65])
+    np.testing.assert_allclose(eps, g["eps_multimode_x0"], rtol=0, atol=1e-12)
