@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define QNMFIT_ABI_VERSION 2
+#define QNMFIT_ABI_VERSION 3
 
 /* limits of the compiled kernels */
 #define QNMFIT_MAX_MODES_SMALL 8     /* register-resident TSQR kernel (K1)   */
@@ -155,6 +155,14 @@ typedef struct qnmfit_batch {
                                  over many waveforms, as the batched free-frequency
                                  search needs (reference qnmfits.py:1905-2043 calls the
                                  fit once per waveform and optimiser step)             */
+
+    /* ---- time-dependent spectrum (dynamic fits, reference qnmfits.py:318-475, 676-911):
+       one frequency / mixing coefficient per ROW, shared by every fit of the batch.
+       K3 takes omega_rows (single series or constant coef); coef_rows needs K2.       */
+    const double  *omega_rows;   /* c128[N][n_times] or NULL: w_j at sample k; replaces
+                                    omega / omega_tilde                                 */
+    const double  *coef_rows;    /* c128[L][N][n_times] or NULL: mu_ij at sample k;
+                                    replaces coef                                       */
 } qnmfit_batch;
 
 /* Create / destroy a context bound to one CUDA device (one process per GPU). */

@@ -335,3 +335,48 @@ def calculate_epsilon(tables, times, data, modes, Mf, chif, t0, t0_method='geq',
                    options={'xatol': 1e-6, 'disp': False})
     dM, dc = res.x[0] - Mf, res.x[1] - chif
     return np.sqrt(dM**2 + dc**2), res.x[0], res.x[1]
+
+
+def dynamic_ringdown_fit(tables, times, data, modes, Mf, chif, t0, t0_method='geq', T=100):
+    """qnmfits/qnmfits.py:396-475: per-sample Mf / chif, a = exp(-1j*frequencies*(times-t0)).T
+    with frequencies of shape (N, K)."""
+    sel = window(times, t0, T, t0_method)
+    t_m, d_m = times[sel], data[sel]
+    Mf = np.full(len(t_m), Mf) if type(Mf) in [float, np.float64] else Mf[sel]
+    chif = np.full(len(t_m), chif) if type(chif) in [float, np.float64] else chif[sel]
+    frequencies = np.array(tables.omega_list(modes, chif, Mf))
+    a = np.exp(-1j * frequencies * (t_m - t0)).T
+    C, res, rank, s = np.linalg.lstsq(a, d_m, rcond=None)
+    model = np.einsum('ij,j->i', a, C)
+    return {'residual': res, 'mismatch': mismatch(t_m, model, d_m), 'C': C, 'data': d_m, 'model': model,
+            'model_times': t_m, 't0': t0, 'modes': modes, 'mode_labels': [str(m) for m in modes],
+            'frequencies': frequencies}
+
+
+def dynamic_multimode_ringdown_fit(tables, times, data_dict, modes, Mf, chif, t0, t0_method='geq',
+                                   T=100, spherical_modes=None):
+    """qnmfits/qnmfits.py:773-911: a[(i,k), j] = mu_ij(chif_k) exp(-i w_j(Mf_k, chif_k) (t_k - t0))."""
+    if spherical_modes is None:
+        spherical_modes = list(data_dict.keys())
+    sel = window(times, t0, T, t0_method)
+    t_m = times[sel]
+    d_masked = {lm: data_dict[lm][sel] for lm in spherical_modes}
+    data = np.concatenate([d_masked[lm] for lm in spherical_modes])
+    Mf = Mf[sel]
+    chif = np.full(len(t_m), chif) if type(chif) in [float, np.float64] else chif[sel]
+    frequencies = np.array(tables.omega_list(modes, chif, Mf)).T
+    frequencies = np.vstack(len(spherical_modes) * [frequencies])
+    mu = np.vstack([np.array([np.broadcast_to(v, t_m.shape) for v in
+                              tables.mu_list([lm + mode for mode in modes], chif)]).T
+                    for lm in spherical_modes])
+    stacked_times = np.vstack(len(spherical_modes) * [t_m[:, None]])
+    a = mu * np.exp(-1j * frequencies * (stacked_times - t0))
+    C, res, rank, s = np.linalg.lstsq(a, data, rcond=None)
+    model = np.einsum('ij,j->i', a, C)
+    weighted = mu * C
+    K = len(t_m)
+    model_dict = {lm: model[i * K:(i + 1) * K] for i, lm in enumerate(spherical_modes)}
+    return {'residual': res, 'mismatch': multimode_mismatch(t_m, model_dict, d_masked), 'C': C,
+            'weighted_C': {lm: weighted[i * K:(i + 1) * K] for i, lm in enumerate(spherical_modes)},
+            'data': d_masked, 'model': model_dict, 'model_times': t_m, 't0': t0, 'modes': modes,
+            'mode_labels': [str(m) for m in modes], 'frequencies': frequencies}

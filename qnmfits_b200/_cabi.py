@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libqnmfit.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_MODES_SMALL = 8
 MAX_MODES = 64
 
@@ -46,6 +46,7 @@ class Batch(C.Structure):
         ("uniform_weights", C.c_int32), ("reserved1", C.c_int32),
         ("flagged_count", _dp),
         ("series_index", _dp),
+        ("omega_rows", _dp), ("coef_rows", _dp),
     ]
 
     def __init__(self, **kw):

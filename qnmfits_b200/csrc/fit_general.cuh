@@ -104,7 +104,7 @@ fit_general_kernel(const FitParams p, const int TR, const int TK)
             for (int e = tid; e < kn * N; e += K2_THREADS) {
                 const int kk = e / N, j = e - kk * N;
                 const double tau = qf_sub_rn(p.times[k0 + kk], t0);
-                sm.E[kk * N + j] = design_entry(sm.om[j], tau);
+                sm.E[kk * N + j] = design_entry(row_omega(p, sm.om, j, k0 + kk), tau);
             }
             __syncthreads();
             // 2. tile [coef (.) E | d], column-major, zero padded to TR rows
@@ -115,7 +115,8 @@ fit_general_kernel(const FitParams p, const int TR, const int TK)
                     const int i = r / kn, kk = r - i * kn;
                     if (k < N) {
                         v = sm.E[kk * N + k];
-                        if (coef) v = c_mul(coef[i * N + k], v);
+                        if (p.coef_rows) v = c_mul(p.coef_rows[((long long)i * N + k) * p.n_times + k0 + kk], v);
+                        else if (coef) v = c_mul(coef[i * N + k], v);
                     } else {
                         v = p.data[(long long)i * p.series_stride + k0 + kk];
                     }
@@ -253,7 +254,7 @@ fit_general_kernel(const FitParams p, const int TR, const int TK)
         for (int e = tid; e < kn * N; e += K2_THREADS) {
             const int kk = e / N, j = e - kk * N;
             const double tau = qf_sub_rn(p.times[k0 + kk], t0);
-            sm.E[kk * N + j] = design_entry(sm.om[j], tau);
+            sm.E[kk * N + j] = design_entry(row_omega(p, sm.om, j, k0 + kk), tau);
         }
         __syncthreads();
         for (int r = tid; r < rows; r += K2_THREADS) {
@@ -262,7 +263,9 @@ fit_general_kernel(const FitParams p, const int TR, const int TK)
             const double2 *ci = sm.cc + i * N;
             double mx = 0.0, my = 0.0;
             for (int j = 0; j < N; ++j) {
-                const double2 a = Er[j], c = ci[j];
+                const double2 a = Er[j];
+                const double2 c = p.coef_rows
+                    ? c_mul(p.coef_rows[((long long)i * N + j) * p.n_times + k0 + kk], sm.Cv[j]) : ci[j];
                 mx = fma(a.x, c.x, mx);
                 my = fma(a.x, c.y, my);
                 mx = fma(-a.y, c.y, mx);

@@ -217,7 +217,7 @@ __device__ __forceinline__ void k3_load1(double2 (&X)[K3_RPT], const FitParams &
 {
     const double2 zero = make_double2(0.0, 0.0);
     if (c < N) {
-        if (p.dt_nominal > 0.0) {
+        if (p.dt_nominal > 0.0 && !p.omega_rows) {
             if (first < re) {
                 const double dt = p.dt_nominal;
                 double tau = qf_sub_rn(p.times[first], t0);
@@ -240,7 +240,7 @@ __device__ __forceinline__ void k3_load1(double2 (&X)[K3_RPT], const FitParams &
 #pragma unroll 1
             for (int r = 0; r < K3_RPT; ++r) {
                 double2 e = zero;
-                if (first + r < re) e = design_entry(sm.om[c], qf_sub_rn(p.times[first + r], t0));
+                if (first + r < re) e = design_entry(row_omega(p, sm.om, c, first + r), qf_sub_rn(p.times[first + r], t0));
 #pragma unroll
                 for (int q = 0; q < K3_RPT; ++q) if (q == r) X[q] = e;   // static register index
             }
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(K3_THREADS, 2) fit_struct_kernel(const FitPara
             for (int e = tid; e < 2 * N; e += K3_THREADS) {
                 const int j = e % N;
                 const int row = e < N ? rb : re - 1;
-                sm.E[e] = design_entry(sm.om[j], qf_sub_rn(p.times[row], t0));
+                sm.E[e] = design_entry(row_omega(p, sm.om, j, row), qf_sub_rn(p.times[row], t0));
             }
             __syncthreads();
             double e0 = 0.0, e1 = 0.0, e2 = 0.0;      // end-point terms of the three sums
@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(K3_THREADS, 2) fit_struct_kernel(const FitPara
         __syncthreads();
         for (int e = tid; e < kn * N; e += K3_THREADS) {
             const int kk = e / N, j = e - kk * N;
-            sm.E[kk * N + j] = design_entry(sm.om[j], qf_sub_rn(p.times[k0 + kk], t0));
+            sm.E[kk * N + j] = design_entry(row_omega(p, sm.om, j, k0 + kk), qf_sub_rn(p.times[k0 + kk], t0));
         }
         __syncthreads();
         for (int r = tid; r < rows; r += K3_THREADS) {

@@ -199,7 +199,7 @@ static int validate(qnmfit_ctx *ctx, const qnmfit_batch *b, bool eval)
         return fail(ctx, QNMFIT_E_SHAPE, "series_stride %lld < n_times %d", (long long)b->series_stride, b->n_times);
     if (!b->times || !b->data || !b->mismatch) return fail(ctx, QNMFIT_E_NULL, "times, data and mismatch are required");
     if (eval && !b->C) return fail(ctx, QNMFIT_E_NULL, "qnmfit_eval_batch needs C");
-    if (!b->omega) {
+    if (!b->omega && !b->omega_rows) {
         if (!b->omega_tilde || !b->mode_ptr || !b->inv_Mf)
             return fail(ctx, QNMFIT_E_NULL, "give omega, or omega_tilde + mode_ptr + inv_Mf");
         if (b->n_chi < 1 || b->n_mf < 1 || b->n_constituents < b->n_modes)
@@ -231,13 +231,15 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
 {
     memset(pl, 0, sizeof(*pl));
     int kernel = b->kernel;
-    const bool small_ok = b->n_series == 1 && b->n_modes <= QNMFIT_MAX_MODES_SMALL && !b->coef;
-    const bool struct_ok = b->n_modes + b->n_series <= 64
+    const bool small_ok = b->n_series == 1 && b->n_modes <= QNMFIT_MAX_MODES_SMALL && !b->coef
+        && !b->omega_rows && !b->coef_rows;
+    const bool struct_ok = !b->coef_rows && b->n_modes + b->n_series <= 64
         && StructSmem::bytes(b->n_modes, b->n_series, struct_group(b->n_modes + b->n_series)) <= (size_t)ctx->smem_optin;
     if (kernel == QNMFIT_KERNEL_AUTO)
         kernel = small_ok ? QNMFIT_KERNEL_SMALL : struct_ok ? QNMFIT_KERNEL_STRUCT : QNMFIT_KERNEL_GENERAL;
     if (kernel == QNMFIT_KERNEL_STRUCT && !struct_ok)
-        return fail(ctx, QNMFIT_E_SHAPE, "K3 needs n_modes + n_series <= 64 (got %d + %d)", b->n_modes, b->n_series);
+        return fail(ctx, QNMFIT_E_SHAPE, "K3 needs n_modes + n_series <= 64 (got %d + %d) and no per-row coef table",
+                    b->n_modes, b->n_series);
     if (kernel == QNMFIT_KERNEL_SMALL && !small_ok)
         return fail(ctx, QNMFIT_E_SHAPE, "K1 needs n_series == 1, n_modes <= %d and no coef table",
                     QNMFIT_MAX_MODES_SMALL);
@@ -323,6 +325,7 @@ static void fill_params(const qnmfit_batch *b, const Plan &pl, bool eval, FitPar
     p->n_constituents = b->n_constituents;
     p->coef = (const double2 *)b->coef; p->coef_index = b->coef_index; p->n_coef = b->n_coef;
     p->series_index = b->series_index;
+    p->omega_rows = (const double2 *)b->omega_rows; p->coef_rows = (const double2 *)b->coef_rows;
     p->anchor_rows = b->anchor_rows > 0 ? b->anchor_rows : QNMFIT_DEFAULT_ANCHOR_ROWS;
     p->dt_nominal = b->dt_nominal;
     p->C = (double2 *)b->C; p->mismatch = b->mismatch; p->residual = b->residual;

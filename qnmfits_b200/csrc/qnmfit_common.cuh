@@ -128,6 +128,8 @@ struct FitParams {
     const double2 *coef;
     const int *coef_index;
     const int *series_index;   // K1: per-fit data series (row of data[][]) or NULL
+    const double2 *omega_rows; // [N][n_times] per-row frequencies (dynamic fits) or NULL
+    const double2 *coef_rows;  // [L][N][n_times] per-row mixing coefficients (K2) or NULL
     int n_coef;
     int anchor_rows;
     double dt_nominal;
@@ -160,11 +162,18 @@ QF_HD int fit_mf_index(const FitParams &p, int fit)
 }
 QF_HD double2 fit_omega(const FitParams &p, int fit, int j)
 {
+    if (p.omega_rows) return p.omega_rows[(long long)j * p.n_times];   // placeholder; rows use row_omega()
     if (p.omega) return p.omega[(p.omega_shared ? 0ll : (long long)fit * p.n_modes) + j];
     int c = fit_chi_index(p, fit);
     double inv = p.inv_Mf[fit_mf_index(p, fit)];
     double df = p.delta_factor ? p.delta_factor[j] : 1.0;
     return form_omega(p.omega_tilde + 2ll * c * p.n_constituents, p.mode_ptr, j, inv, df);
+}
+
+// frequency of mode j at sample k: the per-row table of a dynamic fit, else the fit's own
+QF_HD double2 row_omega(const FitParams &p, const double2 *om, int j, int k)
+{
+    return p.omega_rows ? p.omega_rows[(long long)j * p.n_times + k] : om[j];
 }
 
 // count a fit whose status word is non-zero

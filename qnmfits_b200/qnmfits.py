@@ -507,10 +507,7 @@ def mismatch_t0_array(times, data, modes, Mf, chif, t0_array, t0_method='geq',
     t0_array = np.asarray(t0_array, dtype=float)
     if type(T_array) != np.ndarray:
         T_array = T_array * np.ones(len(t0_array))
-    if not (_is_scalar(Mf) and _is_scalar(chif)):
-        raise NotImplementedError(
-            "time-dependent Mf/chif (dynamic_ringdown_fit, reference qnmfits.py:1286-1299) "
-            "is outside the B200 hot path")
+    dynamic = not (_is_scalar(Mf) and _is_scalar(chif))
     _check_modes(modes)
     if t0_method not in ('geq', 'closest'):
         raise ValueError(
@@ -518,6 +515,18 @@ def mismatch_t0_array(times, data, modes, Mf, chif, t0_array, t0_method='geq',
     n = len(t0_array)
     if n == 0:
         return []
+
+    if dynamic:
+        # time-dependent Kerr spectrum (reference qnmfits.py:1286-1299): the per-row
+        # frequency / mixing tables are shared by every start time, only the window moves
+        if np.any(np.diff(times) < 0):
+            raise ValueError("times must be ascending")
+        sweep = _prepare_dynamic_t0_sweep(times, data, modes, Mf, chif, t0_array, t0_method, T_array,
+                                          spherical_modes)
+        sweep.launch()
+        mm, status = sweep.fetch()
+        _warn_status(status, "mismatch_t0_array")
+        return [np.float64(v) for v in mm]
 
     if np.any(np.diff(times) < 0):
         # Unsorted time arrays make the 'geq' mask non-contiguous: fit one by one.
@@ -838,3 +847,127 @@ def calculate_epsilon(times, data, modes, Mf, chif, t0, t0_method='geq', T=100,
     delta_Mf = Mf_bestfit - Mf
     delta_chif = chif_bestfit - chif
     return np.sqrt(delta_Mf**2 + delta_chif**2), Mf_bestfit, chif_bestfit
+
+
+# --------------------------------------------------------------------------
+# time-dependent Kerr spectrum (reference qnmfits.py:318-475, 676-911)
+
+def _row_tables(times, modes, Mf, chif, keys):
+    """Per-sample frequency table (N, K) and, for dict data, mixing table (L, N, K) from
+    scalar-or-array Mf / chif, as the reference forms them (qnmfits.py:432-445, 806-833)."""
+    K = len(times)
+    Mf_rows = np.full(K, Mf) if _is_scalar(Mf) else np.asarray(Mf, dtype=float)
+    chif_rows = np.full(K, chif) if _is_scalar(chif) else np.asarray(chif, dtype=float)
+    if len(Mf_rows) != K or len(chif_rows) != K:
+        raise ValueError("time-dependent Mf / chif must have the length of times")
+    omega_rows = np.array([np.broadcast_to(w, (K,)) for w in qnm.omega_list(modes, chif_rows, Mf_rows)],
+                          dtype=complex)
+    coef_rows = None
+    if keys is not None:
+        coef_rows = np.array([[np.broadcast_to(np.asarray(v, dtype=complex), (K,))
+                               for v in qnm.mu_list([lm + mode for mode in modes], chif_rows)]
+                              for lm in keys], dtype=complex)
+    return omega_rows, coef_rows
+
+
+def _dynamic_fit_on_device(times_m, data_rows, omega_rows, coef_rows, t0):
+    """One fit with per-row tables: K3 (single series) or K2 (per-row mixing)."""
+    import torch
+    eng = get_engine()
+    L, K = data_rows.shape
+    N = omega_rows.shape[0]
+    if N > _cabi.MAX_MODES:
+        raise ValueError(f"at most {_cabi.MAX_MODES} modes are supported, got {N}")
+    if K < 1:
+        raise ValueError("the analysis window is empty")
+    C_d = eng.empty((1, N), torch.complex128)
+    mm_d = eng.empty((1,), torch.float64)
+    res_d = eng.empty((1,), torch.float64)
+    st_d = eng.empty((1,), torch.int32)
+    model_d = eng.empty((1, L * K), torch.complex128)
+    eng.fit(eng.make_batch(
+        times_d=eng.to_device(times_m, np.float64), data_d=eng.to_device(data_rows, np.complex128),
+        n_fits=1, n_modes=N, n_series=L, row_begin_all=0, row_end_all=K, t0_all=float(t0),
+        omega_rows_d=eng.to_device(omega_rows, np.complex128),
+        coef_rows_d=None if coef_rows is None else eng.to_device(coef_rows, np.complex128),
+        C_d=C_d, mismatch_d=mm_d, residual_d=res_d, status_d=st_d, model_d=model_d, model_stride=L * K))
+    status = int(eng.to_host(st_d)[0])
+    _warn_status(1 if status else 0, "dynamic fit")
+    residual = eng.to_host(res_d)
+    return {'C': eng.to_host(C_d)[0], 'mismatch': np.float64(eng.to_host(mm_d)[0]),
+            'residual': residual if (status & _cabi.ST_RANK_DEFICIENT) == 0 and L * K > N
+            else np.array([], dtype=np.float64),
+            'model': eng.to_host(model_d)[0].reshape(L, K)}
+
+
+def dynamic_ringdown_fit(times, data, modes, Mf, chif, t0, t0_method='geq', T=100):
+    """``ringdown_fit`` with remnant mass and spin given per time sample, so the Kerr
+    spectrum changes along the signal (reference qnmfits.py:318-475).  Same 10-key dict;
+    'frequencies' is (len(modes), len(model_times))."""
+    times = np.asarray(times)
+    data = np.asarray(data)
+    _check_modes(modes)
+    sel = _window(times, t0, T, t0_method)
+    times_masked, data_masked = times[sel], data[sel]
+    Mf_m = Mf if _is_scalar(Mf) else np.asarray(Mf)[sel]
+    chif_m = chif if _is_scalar(chif) else np.asarray(chif)[sel]
+    frequencies, _ = _row_tables(times_masked, modes, Mf_m, chif_m, None)
+    out = _dynamic_fit_on_device(np.asarray(times_masked, dtype=float),
+                                 np.asarray(data_masked, dtype=complex).reshape(1, -1), frequencies, None, t0)
+    return {
+        'residual': out['residual'], 'mismatch': out['mismatch'], 'C': out['C'], 'data': data_masked,
+        'model': out['model'][0], 'model_times': times_masked, 't0': t0, 'modes': modes,
+        'mode_labels': [str(mode) for mode in modes], 'frequencies': frequencies,
+    }
+
+
+def dynamic_multimode_ringdown_fit(times, data_dict, modes, Mf, chif, t0, t0_method='geq', T=100,
+                                   spherical_modes=None):
+    """``multimode_ringdown_fit`` with per-sample mass and spin (reference
+    qnmfits.py:676-911): frequencies and mixing coefficients follow the remnant along the
+    signal.  'weighted_C' holds (K, N) arrays and 'frequencies' the (L K, N) stack, like
+    the reference (:818, 877-887)."""
+    times = np.asarray(times)
+    _check_modes(modes)
+    for mode in modes:
+        if len(mode) != 4:
+            raise ValueError("multimode fits take (ell, m, n, sign) labels only")
+    if spherical_modes is None:
+        spherical_modes = list(data_dict.keys())
+    sel = _window(times, t0, T, t0_method)
+    times_masked = times[sel]
+    data_masked = {lm: np.asarray(data_dict[lm])[sel] for lm in spherical_modes}
+    rows = np.array([data_masked[lm] for lm in spherical_modes], dtype=complex)
+    Mf_m = Mf if _is_scalar(Mf) else np.asarray(Mf)[sel]
+    chif_m = chif if _is_scalar(chif) else np.asarray(chif)[sel]
+    omega_rows, coef_rows = _row_tables(times_masked, modes, Mf_m, chif_m, spherical_modes)
+    out = _dynamic_fit_on_device(np.asarray(times_masked, dtype=float), rows, omega_rows, coef_rows, t0)
+    C = out['C']
+    return {
+        'residual': out['residual'], 'mismatch': out['mismatch'], 'C': C,
+        'weighted_C': {lm: coef_rows[i].T * C for i, lm in enumerate(spherical_modes)},
+        'data': data_masked,
+        'model': {lm: out['model'][i] for i, lm in enumerate(spherical_modes)},
+        'model_times': times_masked, 't0': t0, 'modes': modes,
+        'mode_labels': [str(mode) for mode in modes],
+        'frequencies': np.vstack(len(spherical_modes) * [omega_rows.T]),
+    }
+
+
+def _prepare_dynamic_t0_sweep(times, data, modes, Mf, chif, t0_array, t0_method, T_array, spherical_modes):
+    n = len(t0_array)
+    rows, keys = _series_rows(data, spherical_modes)
+    if keys is not None:
+        for mode in modes:
+            if len(mode) != 4:
+                raise ValueError("multimode fits take (ell, m, n, sign) labels only")
+    begin, end = _window_rows_many(times, t0_array, np.asarray(T_array, dtype=float), t0_method)
+    if np.any(end <= begin):
+        raise ValueError("an analysis window is empty")
+    omega_rows, coef_rows = _row_tables(np.asarray(times, dtype=float), modes, Mf, chif, keys)
+    freq_arrays = dict(omega_rows_d=(omega_rows, np.complex128))
+    if coef_rows is not None:
+        freq_arrays['coef_rows_d'] = (coef_rows, np.complex128)
+    return _Sweep(np.asarray(times, dtype=float), rows, n_fits=n, n_modes=len(modes), windows=(begin, end),
+                  t0s=t0_array, freq_arrays=freq_arrays, freq_scalars={}, coef=None, coef_per_chi=False,
+                  wmax=float(np.max(np.abs(omega_rows))))

@@ -43,3 +43,14 @@ def cfg4_small():
 def rel_err(a, b):
     a, b = np.asarray(a), np.asarray(b)
     return float(np.max(np.abs(a - b) / np.abs(b)))
+
+
+# dynamic (time-dependent spectrum) cases of tests/golden/make_golden_dynamic.py
+DYN_SPH = [(2, 2), (3, 2), (4, 2)]
+DYN_MODES = [(2, 2, 0, 1), (2, 2, 1, 1), (3, 2, 0, 1), (2, 2, 0, -1), (4, 2, 0, 1)]
+
+
+def drift(times):
+    """Mf(t), chif(t) relaxing exponentially to (0.95, 0.69)."""
+    x = np.exp(-np.clip(times, 0, None) / 15.0)
+    return 0.95 - 0.03 * x, 0.69 - 0.05 * x

@@ -421,3 +421,47 @@ def test_calculate_epsilon_vs_reference_golden(qf, eng, golden):
     np.testing.assert_allclose(got, g["eps_multimode"], rtol=0, atol=3e-6)
     got = qf.calculate_epsilon(wl4.times, wl4.data, cs.MM_MODES, 0.95, 0.69, 5.0, T=80, x0=[0.97, 0.65])
     np.testing.assert_allclose(got, g["eps_multimode_x0"], rtol=0, atol=3e-6)
+
+
+def test_dynamic_fits_vs_reference_golden(qf, eng, golden):
+    """dynamic_ringdown_fit / dynamic_multimode_ringdown_fit and the dynamic branch of
+    mismatch_t0_array (reference qnmfits.py:318-475, 676-911, 1286-1299): per-row frequency
+    table through K3, per-row mixing table through K2."""
+    g = golden("dynamic")
+    wl = workloads.config1()
+    Mf_t, chi_t = cases.drift(wl.times)
+    fit = qf.dynamic_ringdown_fit(wl.times, wl.data, wl.modes[:5], Mf_t, chi_t, 2.0, T=70)
+    assert list(fit.keys()) == ['residual', 'mismatch', 'C', 'data', 'model', 'model_times', 't0', 'modes',
+                                'mode_labels', 'frequencies']
+    assert np.array_equal(fit["frequencies"], g["single_frequencies"])
+    assert np.max(np.abs(fit["C"] - g["single_C"])) / np.max(np.abs(g["single_C"])) < 1e-8
+    assert abs(fit["mismatch"] - float(g["single_mismatch"])) < MM_TOL
+    np.testing.assert_allclose(fit["residual"], g["single_residual"], rtol=1e-6)
+    np.testing.assert_allclose(fit["model"], g["single_model"], rtol=0, atol=1e-8 * np.max(np.abs(g["single_C"])))
+    fit = qf.dynamic_ringdown_fit(wl.times, wl.data, wl.modes[:3], 0.95, chi_t, 3.37, t0_method='closest', T=50)
+    assert np.max(np.abs(fit["C"] - g["single_closest_C"])) / np.max(np.abs(g["single_closest_C"])) < 1e-8
+    assert abs(fit["mismatch"] - float(g["single_closest_mismatch"])) < MM_TOL
+    mm = qf.mismatch_t0_array(wl.times, wl.data, wl.modes[:5], Mf_t, chi_t, g["t0s"], T_array=60)
+    assert isinstance(mm, list)
+    np.testing.assert_allclose(mm, g["sweep_single"], rtol=0, atol=MM_TOL)
+
+    wl4 = cases.cfg4_small()
+    Mf4, chi4 = cases.drift(wl4.times)
+    fit = qf.dynamic_multimode_ringdown_fit(wl4.times, wl4.data, cases.DYN_MODES, Mf4, chi4, 5.0, T=80,
+                                            spherical_modes=cases.DYN_SPH)
+    assert list(fit.keys()) == ['residual', 'mismatch', 'C', 'weighted_C', 'data', 'model', 'model_times', 't0',
+                                'modes', 'mode_labels', 'frequencies']
+    assert tuple(fit["frequencies"].shape) == tuple(g["multi_frequencies_shape"])
+    scale = np.max(np.abs(g["multi_C"]))
+    assert np.max(np.abs(fit["C"] - g["multi_C"])) / scale < 1e-8
+    assert abs(fit["mismatch"] - float(g["multi_mismatch"])) < MM_TOL
+    np.testing.assert_allclose(fit["residual"], g["multi_residual"], rtol=1e-6)
+    lm = cases.DYN_SPH[1]
+    np.testing.assert_allclose(fit["model"][lm], g["multi_model_1"], rtol=0, atol=1e-8 * scale)
+    np.testing.assert_allclose(fit["weighted_C"][lm], g["multi_weighted_1"], rtol=0, atol=1e-8 * scale)
+    mm = qf.mismatch_t0_array(wl4.times, wl4.data, cases.DYN_MODES, Mf4, chi4, wl4.t0_array, T_array=70,
+                              spherical_modes=cases.DYN_SPH)
+    np.testing.assert_allclose(mm, g["sweep_multi"], rtol=0, atol=MM_TOL)
+    # superset: coefficients that vanish identically (m' != m) — the reference cannot reshape them
+    fit = qf.dynamic_multimode_ringdown_fit(wl4.times, wl4.data, cases.MM_MODES, Mf4, chi4, 5.0, T=80)
+    assert np.isfinite(fit["mismatch"]) and fit["mismatch"] < 1e-3

@@ -80,10 +80,22 @@ def test_no_cpu_fallback_without_gpu(qf):
         qf.mismatch_M_chi_grid(wl.times, wl.data, wl.modes, (0.9, 1.0), (0.6, 0.7), 0.0, res=4)
 
 
-def test_dynamic_spectrum_is_not_implemented(qf):
+def test_dynamic_spectrum_tables_and_no_cpu_fallback(qf):
+    """Per-row tables of the dynamic fits (reference qnmfits.py:432-445, 806-833): scalar
+    entries are broadcast along time; without a GPU the fit itself raises."""
+    import torch
+    from qnmfits_b200 import qnmfits as api
     t = np.linspace(0, 10, 101)
-    with pytest.raises(NotImplementedError):
-        qf.mismatch_t0_array(t, np.ones(101, complex), [(2, 2, 0, 1)], np.ones(101), 0.7, [0.0])
+    Mf = np.linspace(0.9, 0.95, 101)
+    om, mu = api._row_tables(t, [(2, 2, 0, 1), (3, 2, 0, 1)], Mf, 0.7, [(2, 2), (2, 1)])
+    assert om.shape == (2, 101) and mu.shape == (2, 2, 101)
+    np.testing.assert_array_equal(om[0], np.array(qf.qnm.omega_list([(2, 2, 0, 1)], 0.7, 1.0))[0] / Mf)
+    assert np.all(mu[1] == 0)                      # m' != m: the scalar 0 of qnm.mu, broadcast
+    with pytest.raises(ValueError):
+        api._row_tables(t, [(2, 2, 0, 1)], Mf[:50], 0.7, None)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            qf.mismatch_t0_array(t, np.ones(101, complex), [(2, 2, 0, 1)], np.ones(101), 0.7, [0.0])
 
 
 def test_flops_formula():

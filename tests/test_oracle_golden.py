@@ -105,3 +105,23 @@ def test_oracle_omega_grid_and_epsilon_vs_reference_golden(golden, oracle_tables
     eps = orc.calculate_epsilon(oracle_tables, wl4.times, wl4.data, cases.MM_MODES, 0.95, 0.69, 5.0, T=80,
                                 x0=[0.97, 0.65])
     np.testing.assert_allclose(eps, g["eps_multimode_x0"], rtol=0, atol=1e-12)
+
+
+def test_oracle_dynamic_fits_vs_reference_golden(golden, oracle_tables):
+    """Time-dependent Kerr spectrum (reference qnmfits.py:318-475, 676-911) restated in the
+    oracle vs the unmodified reference's outputs (tests/golden/make_golden_dynamic.py)."""
+    from qnmfits_b200 import workloads
+    g = golden("dynamic")
+    wl = workloads.config1()
+    Mf_t, chi_t = cases.drift(wl.times)
+    fit = orc.dynamic_ringdown_fit(oracle_tables, wl.times, wl.data, wl.modes[:5], Mf_t, chi_t, 2.0, T=70)
+    assert np.array_equal(fit["frequencies"], g["single_frequencies"])
+    assert rel_err(fit["C"], g["single_C"]) < 1e-12
+    assert abs(fit["mismatch"] - float(g["single_mismatch"])) < 1e-15
+    wl4 = cases.cfg4_small()
+    Mf4, chi4 = cases.drift(wl4.times)
+    fit = orc.dynamic_multimode_ringdown_fit(oracle_tables, wl4.times, wl4.data, cases.DYN_MODES, Mf4, chi4, 5.0,
+                                             T=80, spherical_modes=cases.DYN_SPH)
+    assert rel_err(fit["C"], g["multi_C"]) < 1e-12
+    assert abs(fit["mismatch"] - float(g["multi_mismatch"])) < 1e-15
+    np.testing.assert_allclose(fit["weighted_C"][cases.DYN_SPH[1]], g["multi_weighted_1"], rtol=1e-12)
