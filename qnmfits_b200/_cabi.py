@@ -84,7 +84,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or LIB_PATH
+    path = path or os.environ.get("QNMFIT_LIB") or LIB_PATH   # QNMFIT_LIB: developer builds (tools/)
     if not os.path.isfile(path):
         raise ImportError(
             f"{path} not found: build it with `python -c 'import __graft_entry__ as g; "

@@ -12,12 +12,14 @@
 #include "fit_small.cuh"
 #include "fit_general.cuh"
 #include "fit_struct.cuh"
+#include <stdlib.h>
 
 #ifndef K1_THREADS
 #define K1_THREADS 256
 #endif
 
 struct qnmfit_ctx {
+    int k3_g, k3_rpt;        // K3: lanes per column, rows per thread (developer knob QNMFIT_K3G="G,RPT")
     int device;
     int sm_count;
     int smem_optin;          // max dynamic shared memory per block
@@ -73,18 +75,17 @@ static small_kernel_t small_kernel(int N, bool staged)
 
 typedef void (*struct_kernel_t)(const FitParams);
 
-static int struct_group(int ncols)   // lanes per column pair of K3
-{
-    return ncols > 32 ? 8 : ncols > 16 ? 16 : 32;
-}
+#define K3C_DEFAULT_G 4
+#define K3C_DEFAULT_RPT 16
 
-static struct_kernel_t struct_kernel(int G)
+static struct_kernel_t struct3_kernel(int G, int RPT)
 {
-    switch (G) {
-    case 8: return fit_struct_kernel<8>;
-    case 16: return fit_struct_kernel<16>;
-    case 32: return fit_struct_kernel<32>;
-    }
+    if (G == 1 && RPT == 32) return fit_struct3_kernel<1, 32>;
+    if (G == 2 && RPT == 16) return fit_struct3_kernel<2, 16>;
+    if (G == 2 && RPT == 32) return fit_struct3_kernel<2, 32>;
+    if (G == 4 && RPT == 8) return fit_struct3_kernel<4, 8>;
+    if (G == 4 && RPT == 16) return fit_struct3_kernel<4, 16>;
+    if (G == 8 && RPT == 8) return fit_struct3_kernel<8, 8>;
     return nullptr;
 }
 
@@ -131,6 +132,9 @@ extern "C" int qnmfit_create(int device, qnmfit_ctx **out)
     ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
     ctx->launches = 0;
     ctx->err[0] = 0;
+    ctx->k3_g = K3C_DEFAULT_G; ctx->k3_rpt = K3C_DEFAULT_RPT;
+    { const char *eg = getenv("QNMFIT_K3G"); int g2 = 0, r2 = 0;
+      if (eg && sscanf(eg, "%d,%d", &g2, &r2) == 2 && struct3_kernel(g2, r2)) { ctx->k3_g = g2; ctx->k3_rpt = r2; } }
     if ((e = cudaSetDevice(device)) != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaSetDevice"); delete ctx; return r; }
     // opt every kernel in to the full shared-memory carve-out once
     for (int N = 1; N <= QNMFIT_MAX_MODES_SMALL; ++N)
@@ -143,10 +147,18 @@ extern "C" int qnmfit_create(int device, qnmfit_ctx **out)
     e = cudaFuncSetAttribute((const void *)fit_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              ctx->smem_optin);
     if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaFuncSetAttribute(K2)"); delete ctx; return r; }
-    for (int G = 8; G <= 32; G *= 2) {
-        e = cudaFuncSetAttribute((const void *)struct_kernel(G), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 ctx->smem_optin);
-        if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaFuncSetAttribute(K3)"); delete ctx; return r; }
+    {
+        static const int forms[6][2] = {{1, 32}, {2, 16}, {2, 32}, {4, 8}, {4, 16}, {8, 8}};
+        for (int f = 0; f < 6; ++f) {
+            e = cudaFuncSetAttribute((const void *)struct3_kernel(forms[f][0], forms[f][1]),
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+            if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaFuncSetAttribute(K3c)"); delete ctx; return r; }
+            // ~45 KB per fit: ask for the full shared-memory carve-out so that 4-5 fits share an SM
+            // (the driver's default carve-out for a block of this size admits only two)
+            e = cudaFuncSetAttribute((const void *)struct3_kernel(forms[f][0], forms[f][1]),
+                                     cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaFuncSetAttribute(K3c carve-out)"); delete ctx; return r; }
+        }
     }
     *out = ctx;
     return 0;
@@ -234,7 +246,7 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
     const bool small_ok = b->n_series == 1 && b->n_modes <= QNMFIT_MAX_MODES_SMALL && !b->coef
         && !b->omega_rows && !b->coef_rows;
     const bool struct_ok = !b->coef_rows && b->n_modes + b->n_series <= 64
-        && StructSmem::bytes(b->n_modes, b->n_series, struct_group(b->n_modes + b->n_series)) <= (size_t)ctx->smem_optin;
+        && Struct3Smem::bytes(b->n_modes, b->n_series) <= (size_t)ctx->smem_optin;
     if (kernel == QNMFIT_KERNEL_AUTO)
         kernel = small_ok ? QNMFIT_KERNEL_SMALL : struct_ok ? QNMFIT_KERNEL_STRUCT : QNMFIT_KERNEL_GENERAL;
     if (kernel == QNMFIT_KERNEL_STRUCT && !struct_ok)
@@ -286,10 +298,9 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
         }
         if (best >= 1e300) return fail(ctx, QNMFIT_E_SHAPE, "K1: no lanes-per-fit choice fits shared memory");
     } else if (kernel == QNMFIT_KERNEL_STRUCT) {
-        const int G = struct_group(b->n_modes + b->n_series);
-        pl->lpf = G; pl->TR = K3_RPT * G;
-        pl->smem = StructSmem::bytes(b->n_modes, b->n_series, G);
-        pl->grid = b->n_fits; pl->block = K3_THREADS;
+        pl->lpf = ctx->k3_g; pl->TR = ctx->k3_g * ctx->k3_rpt;
+        pl->smem = Struct3Smem::bytes(b->n_modes, b->n_series);
+        pl->grid = b->n_fits; pl->block = ctx->k3_g * 32 * ((b->n_modes + b->n_series + 31) / 32);
     } else {
         const int L = b->n_series;
         int TR = 128;
@@ -353,8 +364,7 @@ static int launch(qnmfit_ctx *ctx, const qnmfit_batch *b, void *stream, bool eva
         small_kernel_t k = small_kernel(b->n_modes, pl.staged);
         k<<<pl.grid, pl.block, pl.smem, st>>>(p);
     } else if (pl.kernel == QNMFIT_KERNEL_STRUCT) {
-        struct_kernel_t k = struct_kernel(pl.lpf);
-        k<<<pl.grid, pl.block, pl.smem, st>>>(p);
+        struct3_kernel(ctx->k3_g, ctx->k3_rpt)<<<pl.grid, pl.block, pl.smem, st>>>(p);
     } else {
         fit_general_kernel<<<pl.grid, pl.block, pl.smem, st>>>(p, pl.TR, pl.TK);
     }
@@ -387,7 +397,7 @@ extern "C" int qnmfit_plan_batch(qnmfit_ctx *ctx, const qnmfit_batch *b, qnmfit_
     out->fast_mismatch = (pl.kernel != QNMFIT_KERNEL_GENERAL && b->uniform_weights && b->dt_nominal > 0.0 && !b->model) ? 1 : 0;
     cudaFuncAttributes fa;
     const void *fn = pl.kernel == QNMFIT_KERNEL_SMALL ? (const void *)small_kernel(b->n_modes, pl.staged)
-                   : pl.kernel == QNMFIT_KERNEL_STRUCT ? (const void *)struct_kernel(pl.lpf)
+                   : pl.kernel == QNMFIT_KERNEL_STRUCT ? (const void *)struct3_kernel(ctx->k3_g, ctx->k3_rpt)
                                                        : (const void *)fit_general_kernel;
     cudaError_t e = cudaFuncGetAttributes(&fa, fn);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaFuncGetAttributes");

@@ -16,7 +16,8 @@ def main():
     from qnmfits_b200 import workloads, _cabi
     from qnmfits_b200 import qnmfits as api
     workloads.use_synthetic_tables()
-    wl = workloads.config4()
+    n_t0 = int(os.environ.get("K3_FITS", "500"))
+    wl = workloads.config4(n_t0=n_t0)
     T_array = wl.T * np.ones(len(wl.t0_array))
     sweep = api._prepare_t0_sweep(np.asarray(wl.times), wl.data, wl.modes, wl.Mf, wl.chif,
                                   np.asarray(wl.t0_array, dtype=float), 'geq', T_array, wl.spherical_modes, 0.0)
