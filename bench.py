@@ -11,7 +11,7 @@ flat grid index over the N ranks (strong scaling: the grid is fixed), followed a
 by the NCCL all-gather of the mismatch slabs.
 
 * value      device-resident throughput: tables, times and data already in HBM; per
-             step one fit kernel (+ all-gather); CUDA events on the launching stream;
+             step one fit kernel (incl. the exchange); CUDA events on the launching stream;
              an L2 flush (256 MiB write) between steps, outside the events.
 * e2e        the same grid through the public API ``mismatch_M_chi_grid`` with HOST
              numpy inputs: host tabulation, H2D, kernel, gather, D2H inside the region.
@@ -227,12 +227,15 @@ def run_gpu_arm(args):
 
     # ---- device-resident arm: upload once, launch K times -------------------------
     sweep, shape = api._prepare_M_chi_grid(*grid_args, **grid_kw)
-    plan = eng.ctx.plan(sweep.batch)
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=eng.device)
     stream = torch.cuda.current_stream()
     for _ in range(max(args.warmup, 3)):
         sweep.launch()
     barrier()
+    plan = eng.ctx.plan(sweep.batch)
+    exchange = ("none (one rank)" if world == 1 else
+                "fused into the fit kernel: peer stores over NVLink + epoch flags (qnmfit_fit_batch_peers)"
+                if sweep.window is not None else "NCCL all_gather_into_tensor after the kernel")
     launches0 = eng.ctx.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
            torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -317,6 +320,7 @@ def run_gpu_arm(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "fits_per_step": n_fits, "rows": rows,
                        "modes": len(wl.modes), "sharding": f"flat grid index over {world} rank(s)",
+                       "exchange": exchange,
                        "l2": "256 MiB fill between timed steps (outside the CUDA events)",
                        "kernel": {"id": plan.kernel, "lanes_per_fit": plan.lanes_per_fit,
                                   "grid": plan.grid, "block": plan.block,

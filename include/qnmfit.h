@@ -35,13 +35,14 @@
 #ifndef QNMFIT_H
 #define QNMFIT_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define QNMFIT_ABI_VERSION 3
+#define QNMFIT_ABI_VERSION 4
 
 /* limits of the compiled kernels */
 #define QNMFIT_MAX_MODES_SMALL 8     /* register-resident TSQR kernel (K1)   */
@@ -54,6 +55,7 @@ extern "C" {
 #define QNMFIT_E_WINDOW    (-3)      /* shared window empty or outside the series */
 #define QNMFIT_E_ABI       (-4)      /* struct_size does not match this library   */
 #define QNMFIT_E_NOGPU     (-5)      /* no usable sm_100 device                   */
+#define QNMFIT_E_PEER      (-6)      /* bad peer-exchange descriptor              */
 
 /* per-fit status bits */
 #define QNMFIT_ST_OK            0
@@ -179,6 +181,55 @@ int qnmfit_fit_batch(qnmfit_ctx *ctx, const qnmfit_batch *b, void *stream);
 
 /* Model + mismatch (+ residual) only, with amplitudes read from b->C. */
 int qnmfit_eval_batch(qnmfit_ctx *ctx, const qnmfit_batch *b, void *stream);
+
+/* ---------------------------------------------------------------------------------
+ * Multi-GPU result exchange fused into the fit kernels (one process per GPU).
+ *
+ * The reference's sweeps are serial loops over independent fits
+ * (qnmfits/qnmfits.py:1271-1281, :1391-1410); here the flat fit index is split into one
+ * slab per GPU, and every GPU needs the whole mismatch array at the end.  Instead of a
+ * collective after the kernel, the thread that finishes a fit stores its mismatch
+ * straight into the result array of EVERY peer GPU (peer-mapped device memory, posted
+ * stores over NVLink / NVSwitch that overlap the remaining fits).  A one-warp barrier
+ * kernel follows on the same stream: lane r publishes the launch's epoch (and count of
+ * flagged fits) to peer r with system-scope release and waits for peer r's epoch.  When
+ * it has completed on a GPU, that GPU holds the complete array.
+ *
+ *   qnmfit_peer_alloc   device allocation (zero-filled) that other processes of this
+ *                       node can map, and its 64-byte handle (cudaIpcMemHandle_t);
+ *   qnmfit_peer_open    map the allocation behind a handle received from another rank;
+ *   qnmfit_peer_close / qnmfit_peer_free   undo the above;
+ *   qnmfit_fit_batch_peers   qnmfit_fit_batch + the exchange.  Element first_fit + i of
+ *                       mismatch[r] receives fit i for every r; b->mismatch must be
+ *                       mismatch[rank] + first_fit (the local copy).  All ranks must
+ *                       issue the launches of one epoch (SPMD); a rank with n_fits == 0
+ *                       still calls (only the barrier kernel runs).
+ */
+#define QNMFIT_MAX_PEERS 8
+
+typedef struct qnmfit_peers {
+    int32_t  struct_size;                   /* sizeof(qnmfit_peers), checked                  */
+    int32_t  n_peers;                       /* W: ranks incl. this one, 2..QNMFIT_MAX_PEERS   */
+    int32_t  rank;                          /* this rank, 0..W-1                              */
+    int32_t  reserved;
+    int64_t  epoch;                         /* > every earlier epoch used with these flags;
+                                               the same value on every rank                   */
+    int64_t  timeout_ns;                    /* give up waiting for a peer after this long
+                                               (<= 0: 30 s); the peer's slot of the local
+                                               flagged[] array is then set to NaN             */
+    double   *mismatch[QNMFIT_MAX_PEERS];   /* f64 [n_total] on every rank ([rank] = local)   */
+    double   *flagged[QNMFIT_MAX_PEERS];    /* f64 [W] on every rank: element `rank` of each
+                                               receives this launch's count of flagged fits   */
+    uint64_t *flags[QNMFIT_MAX_PEERS];      /* u64 [W] on every rank: element `rank` of each
+                                               is set to epoch once this launch's stores are
+                                               visible system-wide                            */
+} qnmfit_peers;
+
+int qnmfit_peer_alloc(qnmfit_ctx *ctx, size_t bytes, void **dptr, unsigned char handle[64]);
+int qnmfit_peer_open(qnmfit_ctx *ctx, const unsigned char handle[64], void **dptr);
+int qnmfit_peer_close(qnmfit_ctx *ctx, void *dptr);
+int qnmfit_peer_free(qnmfit_ctx *ctx, void *dptr);
+int qnmfit_fit_batch_peers(qnmfit_ctx *ctx, const qnmfit_batch *b, const qnmfit_peers *peers, void *stream);
 
 /* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
 int64_t qnmfit_launch_count(const qnmfit_ctx *ctx);

@@ -10,9 +10,10 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libqnmfit.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_MODES_SMALL = 8
 MAX_MODES = 64
+MAX_PEERS = 8
 
 KERNEL_AUTO, KERNEL_SMALL, KERNEL_GENERAL, KERNEL_STRUCT = 0, 1, 2, 3
 
@@ -54,6 +55,20 @@ class Batch(C.Structure):
         self.struct_size = C.sizeof(Batch)
 
 
+class Peers(C.Structure):
+    """Mirror of ``struct qnmfit_peers`` (multi-GPU exchange fused into the fit kernels)."""
+    _fields_ = [
+        ("struct_size", C.c_int32), ("n_peers", C.c_int32),
+        ("rank", C.c_int32), ("reserved", C.c_int32),
+        ("epoch", C.c_int64), ("timeout_ns", C.c_int64),
+        ("mismatch", _dp * MAX_PEERS), ("flagged", _dp * MAX_PEERS), ("flags", _dp * MAX_PEERS),
+    ]
+
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        self.struct_size = C.sizeof(Peers)
+
+
 class Plan(C.Structure):
     _fields_ = [
         ("kernel", C.c_int32), ("lanes_per_fit", C.c_int32),
@@ -68,6 +83,8 @@ EXPORTS = (
     "qnmfit_create", "qnmfit_destroy", "qnmfit_last_error", "qnmfit_fit_batch",
     "qnmfit_eval_batch", "qnmfit_launch_count", "qnmfit_plan_batch",
     "qnmfit_fp64_peak", "qnmfit_flops_per_fit", "qnmfit_abi_version",
+    "qnmfit_peer_alloc", "qnmfit_peer_open", "qnmfit_peer_close", "qnmfit_peer_free",
+    "qnmfit_fit_batch_peers",
 )
 
 _lib = None
@@ -100,6 +117,16 @@ def load_library(path=None):
     for name in ("qnmfit_fit_batch", "qnmfit_eval_batch"):
         fn = getattr(lib, name)
         fn.argtypes = [C.c_void_p, C.POINTER(Batch), C.c_void_p]
+        fn.restype = C.c_int
+    lib.qnmfit_fit_batch_peers.argtypes = [C.c_void_p, C.POINTER(Batch), C.POINTER(Peers), C.c_void_p]
+    lib.qnmfit_fit_batch_peers.restype = C.c_int
+    lib.qnmfit_peer_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
+    lib.qnmfit_peer_alloc.restype = C.c_int
+    lib.qnmfit_peer_open.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.qnmfit_peer_open.restype = C.c_int
+    for name in ("qnmfit_peer_close", "qnmfit_peer_free"):
+        fn = getattr(lib, name)
+        fn.argtypes = [C.c_void_p, C.c_void_p]
         fn.restype = C.c_int
     lib.qnmfit_launch_count.argtypes = [C.c_void_p]
     lib.qnmfit_launch_count.restype = C.c_int64
@@ -138,6 +165,28 @@ class Context:
 
     def eval_batch(self, batch, stream=0):
         self._check(self.lib.qnmfit_eval_batch(self.handle, C.byref(batch), C.c_void_p(stream)))
+
+    def fit_batch_peers(self, batch, peers, stream=0):
+        self._check(self.lib.qnmfit_fit_batch_peers(self.handle, C.byref(batch), C.byref(peers),
+                                                    C.c_void_p(stream)))
+
+    def peer_alloc(self, nbytes):
+        """(device pointer, 64-byte handle) of a zero-filled allocation other ranks can map."""
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        self._check(self.lib.qnmfit_peer_alloc(self.handle, int(nbytes), C.byref(ptr), handle))
+        return int(ptr.value), handle.raw
+
+    def peer_open(self, handle):
+        ptr = C.c_void_p()
+        self._check(self.lib.qnmfit_peer_open(self.handle, bytes(handle), C.byref(ptr)))
+        return int(ptr.value)
+
+    def peer_close(self, ptr):
+        self._check(self.lib.qnmfit_peer_close(self.handle, C.c_void_p(ptr)))
+
+    def peer_free(self, ptr):
+        self._check(self.lib.qnmfit_peer_free(self.handle, C.c_void_p(ptr)))
 
     def plan(self, batch):
         plan = Plan()

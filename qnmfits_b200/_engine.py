@@ -193,6 +193,10 @@ class Engine:
     def fit(self, batch):
         self.ctx.fit_batch(batch, self.stream())
 
+    def fit_peers(self, batch, peers):
+        """Fit + exchange fused in the kernel (``_dist.PeerWindow``)."""
+        self.ctx.fit_batch_peers(batch, peers, self.stream())
+
     def evaluate(self, batch):
         self.ctx.eval_batch(batch, self.stream())
 

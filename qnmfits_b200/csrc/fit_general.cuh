@@ -63,7 +63,7 @@ __device__ __forceinline__ double warp_sum(double v)
 
 // tile_rows / time_chunk are chosen by the host: TK = max(1, TR / L), rows used = TK * L.
 __global__ void __launch_bounds__(K2_THREADS, 1)
-fit_general_kernel(const FitParams p, const int TR, const int TK)
+fit_general_kernel(const __grid_constant__ FitParams p, const int TR, const int TK)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = p.n_modes, L = p.n_series;
@@ -296,10 +296,12 @@ fit_general_kernel(const FitParams p, const int TR, const int TK)
             a0 += sm.red[w * 4 + 0]; a1 += sm.red[w * 4 + 1];
             a2 += sm.red[w * 4 + 2]; a3 += sm.red[w * 4 + 3];
         }
-        p.mismatch[fit] = 1.0 - a0 / sqrt(a1 * a2);
+        const double mm = 1.0 - a0 / sqrt(a1 * a2);
+        p.mismatch[fit] = mm;
         if (p.residual) p.residual[fit] = a3;
         if (p.status) p.status[fit] = status;
         note_status(p, status);
+        peer_publish(p, fit, mm);
     }
 }
 #endif  // !QNMFIT_HOSTSIM

@@ -686,6 +686,7 @@ QF_HD void small_finalize(const FitParams &p, const SmallLane &L, const double (
     if (p.residual) p.residual[L.fit] = sums[3];
     if (p.status) p.status[L.fit] = status;
     note_status(p, status);
+    peer_publish(p, L.fit, mm);
 }
 
 // Fast path for (nearly) uniform grids — no second pass.  With m = A C = Q Q^H d:
@@ -728,10 +729,12 @@ QF_HD void small_fast_finalize(const FitParams &p, const SmallLane &L, const dou
     const double n1 = cn2 - 0.5 * (fma(mfx, mfx, mfy * mfy) + fma(mlx, mlx, mly * mly));
     const double n2 = tot[0] - 0.5 * (fma(d_first.x, d_first.x, d_first.y * d_first.y)
                                       + fma(d_last.x, d_last.x, d_last.y * d_last.y));
-    p.mismatch[L.fit] = 1.0 - num / sqrt(n1 * n2);
+    const double mm = 1.0 - num / sqrt(n1 * n2);
+    p.mismatch[L.fit] = mm;
     if (p.residual) p.residual[L.fit] = tot[1];
     if (p.status) p.status[L.fit] = status;
     note_status(p, status);
+    peer_publish(p, L.fit, mm);
 }
 
 #ifndef QNMFIT_HOSTSIM
@@ -739,7 +742,7 @@ QF_HD void small_fast_finalize(const FitParams &p, const SmallLane &L, const dou
 // The kernel.  STAGED: the union of all windows (times + data, 24 B/row) is copied
 // into shared memory once per CTA and reused by every fit the CTA handles.
 template <int N, int THREADS, bool STAGED>
-__global__ void __launch_bounds__(THREADS, 1) fit_small_kernel(const FitParams p)
+__global__ void __launch_bounds__(THREADS, 1) fit_small_kernel(const __grid_constant__ FitParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmallSmem<N, THREADS> sm;
@@ -800,9 +803,15 @@ __global__ void __launch_bounds__(THREADS, 1) fit_small_kernel(const FitParams p
 #pragma unroll
             for (int q = 0; q < 6; ++q) part[q] += __shfl_xor_sync(0xffffffffu, part[q], s);
         }
-        if (L.fit >= 0 && L.lf == 0 && L.re > L.rb)
-            small_fast_finalize(p, L, sm.ds[L.rb - sm.t_off + L.d_off], sm.ds[L.re - 1 - sm.t_off + L.d_off], part, acc.cn2,
-                                status);
+        if (L.fit >= 0 && L.lf == 0) {
+            if (L.re > L.rb) {
+                small_fast_finalize(p, L, sm.ds[L.rb - sm.t_off + L.d_off], sm.ds[L.re - 1 - sm.t_off + L.d_off], part,
+                                    acc.cn2, status);
+            } else {   // empty window: 0/0 like the general path, and the fit still counts as done
+                const double2 z = make_double2(0.0, 0.0);
+                small_fast_finalize(p, L, z, z, part, acc.cn2, status);
+            }
+        }
         return;
     }
     double sums[4];

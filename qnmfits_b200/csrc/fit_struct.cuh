@@ -270,7 +270,7 @@ __device__ __forceinline__ void k3c_load2(double2 (&X)[RPT], const Struct3Smem &
 
 template <int G, int RPT>
 #define K3C_MINB(G, RPT) (RPT >= 32 ? (G == 1 ? 4 : 2) : G <= 2 ? 4 : G == 4 ? 2 : 1)
-__global__ void __launch_bounds__(64 * G, K3C_MINB(G, RPT)) fit_struct3_kernel(const FitParams p)
+__global__ void __launch_bounds__(64 * G, K3C_MINB(G, RPT)) fit_struct3_kernel(const __grid_constant__ FitParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int TR = G * RPT;
@@ -454,10 +454,12 @@ __global__ void __launch_bounds__(64 * G, K3C_MINB(G, RPT)) fit_struct3_kernel(c
                 double a0 = 0.0, a1 = 0.0, a2 = 0.0;
                 for (int i = 0; i < L; ++i) { a0 += sm.ends[i * 3]; a1 += sm.ends[i * 3 + 1]; a2 += sm.ends[i * 3 + 2]; }
                 const double num = cn2 - 0.5 * a0, n1 = cn2 - 0.5 * a1, n2 = sdd - 0.5 * a2;
-                p.mismatch[fit] = 1.0 - num / sqrt(n1 * n2);
+                const double mm = 1.0 - num / sqrt(n1 * n2);
+                p.mismatch[fit] = mm;
                 if (p.residual) p.residual[fit] = res2;
                 if (p.status) p.status[fit] = status;
                 note_status(p, status);
+                peer_publish(p, fit, mm);
             }
             return;
         }
@@ -519,10 +521,12 @@ __global__ void __launch_bounds__(64 * G, K3C_MINB(G, RPT)) fit_struct3_kernel(c
             a0 += sm.red[w * 8 + 0]; a1 += sm.red[w * 8 + 1];
             a2 += sm.red[w * 8 + 2]; a3 += sm.red[w * 8 + 3];
         }
-        p.mismatch[fit] = 1.0 - a0 / sqrt(a1 * a2);
+        const double mm = 1.0 - a0 / sqrt(a1 * a2);
+        p.mismatch[fit] = mm;
         if (p.residual) p.residual[fit] = p.eval_only ? a3 : res2;
         if (p.status) p.status[fit] = status;
         note_status(p, status);
+        peer_publish(p, fit, mm);
     }
 }
 #endif  // !QNMFIT_HOSTSIM

@@ -24,6 +24,7 @@ struct qnmfit_ctx {
     int sm_count;
     int smem_optin;          // max dynamic shared memory per block
     long long launches;
+    double *peer_scratch;         // device: flagged-fit counter of qnmfit_fit_batch_peers when the caller gives none
     char err[512];
 };
 
@@ -47,7 +48,7 @@ static int cuda_fail(qnmfit_ctx *ctx, cudaError_t e, const char *what)
 // ---------------------------------------------------------------------------
 // kernel tables
 
-typedef void (*small_kernel_t)(const FitParams);
+typedef void (*small_kernel_t)(const FitParams);   // kernels take it as __grid_constant__
 
 template <int N>
 static small_kernel_t small_kernel_for(bool staged)
@@ -131,6 +132,7 @@ extern "C" int qnmfit_create(int device, qnmfit_ctx **out)
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
     ctx->launches = 0;
+    ctx->peer_scratch = nullptr;
     ctx->err[0] = 0;
     ctx->k3_g = K3C_DEFAULT_G; ctx->k3_rpt = K3C_DEFAULT_RPT;
     { const char *eg = getenv("QNMFIT_K3G"); int g2 = 0, r2 = 0;
@@ -166,6 +168,7 @@ extern "C" int qnmfit_create(int device, qnmfit_ctx **out)
 
 extern "C" int qnmfit_destroy(qnmfit_ctx *ctx)
 {
+    if (ctx && ctx->peer_scratch) { cudaSetDevice(ctx->device); cudaFree(ctx->peer_scratch); }
     delete ctx;
     return 0;
 }
@@ -348,19 +351,53 @@ static void fill_params(const qnmfit_batch *b, const Plan &pl, bool eval, FitPar
     p->stage_begin = pl.stage_begin; p->stage_rows = pl.stage_rows;
 }
 
-static int launch(qnmfit_ctx *ctx, const qnmfit_batch *b, void *stream, bool eval)
+static int validate_peers(qnmfit_ctx *ctx, const qnmfit_batch *b, const qnmfit_peers *pe)
+{
+    if (pe->struct_size != (int32_t)sizeof(qnmfit_peers))
+        return fail(ctx, QNMFIT_E_ABI, "qnmfit_peers.struct_size %d != %d", pe->struct_size, (int)sizeof(qnmfit_peers));
+    if (pe->n_peers < 2 || pe->n_peers > QNMFIT_MAX_PEERS || pe->rank < 0 || pe->rank >= pe->n_peers)
+        return fail(ctx, QNMFIT_E_PEER, "n_peers=%d (2..%d), rank=%d", pe->n_peers, QNMFIT_MAX_PEERS, pe->rank);
+    if (pe->epoch < 1) return fail(ctx, QNMFIT_E_PEER, "epoch %lld must be >= 1", (long long)pe->epoch);
+    for (int r = 0; r < pe->n_peers; ++r)
+        if (!pe->mismatch[r] || !pe->flagged[r] || !pe->flags[r])
+            return fail(ctx, QNMFIT_E_NULL, "peer %d: mismatch, flagged and flags are required", r);
+    if (b->n_fits > 0 && b->mismatch != pe->mismatch[pe->rank] + b->first_fit)
+        return fail(ctx, QNMFIT_E_PEER, "b->mismatch must be peers->mismatch[rank] + first_fit");
+    return 0;
+}
+
+static int launch(qnmfit_ctx *ctx, const qnmfit_batch *b, void *stream, bool eval, const qnmfit_peers *pe = nullptr)
 {
     int rc = validate(ctx, b, eval);
     if (rc) return rc;
-    if (b->n_fits == 0) return 0;
+    if (pe && (rc = validate_peers(ctx, b, pe))) return rc;
+    if (b->n_fits == 0 && !pe) return 0;
     Plan pl;
-    if ((rc = make_plan(ctx, b, &pl))) return rc;
+    memset(&pl, 0, sizeof(pl));
+    if (b->n_fits > 0 && (rc = make_plan(ctx, b, &pl))) return rc;
     FitParams p;
     fill_params(b, pl, eval, &p);
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
     cudaStream_t st = (cudaStream_t)stream;
-    if (pl.kernel == QNMFIT_KERNEL_SMALL) {
+    if (pe) {
+        if (!ctx->peer_scratch) {
+            if ((e = cudaMalloc(&ctx->peer_scratch, 16)) != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(peer scratch)");
+            if ((e = cudaMemset(ctx->peer_scratch, 0, 16)) != cudaSuccess) return cuda_fail(ctx, e, "cudaMemset(peer scratch)");
+        }
+        p.n_peers = pe->n_peers; p.peer_rank = pe->rank;
+        p.peer_epoch = (unsigned long long)pe->epoch; p.peer_timeout_ns = pe->timeout_ns;
+        for (int r = 0; r < pe->n_peers; ++r) {
+            p.peer_mismatch[r] = pe->mismatch[r]; p.peer_flagged[r] = pe->flagged[r];
+            p.peer_flags[r] = (unsigned long long *)pe->flags[r];
+        }
+        // the launch's flagged count travels with the epoch: count it in the ctx's scratch
+        // (reset by the barrier kernel) unless the caller supplied a counter
+        if (!p.flagged_count) p.flagged_count = ctx->peer_scratch;
+    }
+    if (b->n_fits == 0) {
+        // empty slab: only the barrier below
+    } else if (pl.kernel == QNMFIT_KERNEL_SMALL) {
         small_kernel_t k = small_kernel(b->n_modes, pl.staged);
         k<<<pl.grid, pl.block, pl.smem, st>>>(p);
     } else if (pl.kernel == QNMFIT_KERNEL_STRUCT) {
@@ -370,7 +407,12 @@ static int launch(qnmfit_ctx *ctx, const qnmfit_batch *b, void *stream, bool eva
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(ctx, e, "kernel launch");
-    ctx->launches += 1;
+    if (b->n_fits > 0) ctx->launches += 1;
+    if (pe) {
+        peer_barrier_kernel<<<1, 32, 0, st>>>(p);
+        if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(ctx, e, "peer barrier launch");
+        ctx->launches += 1;
+    }
     return 0;
 }
 
@@ -382,6 +424,67 @@ extern "C" int qnmfit_fit_batch(qnmfit_ctx *ctx, const qnmfit_batch *b, void *st
 extern "C" int qnmfit_eval_batch(qnmfit_ctx *ctx, const qnmfit_batch *b, void *stream)
 {
     return launch(ctx, b, stream, true);
+}
+
+extern "C" int qnmfit_fit_batch_peers(qnmfit_ctx *ctx, const qnmfit_batch *b, const qnmfit_peers *peers, void *stream)
+{
+    if (!ctx) return QNMFIT_E_NULL;
+    if (!peers) return fail(ctx, QNMFIT_E_NULL, "peers is NULL");
+    return launch(ctx, b, stream, false, peers);
+}
+
+// ---------------------------------------------------------------------------
+// peer-mappable device memory (cudaIpc*: one process per GPU on one node)
+
+extern "C" int qnmfit_peer_alloc(qnmfit_ctx *ctx, size_t bytes, void **dptr, unsigned char handle[64])
+{
+    if (!ctx) return QNMFIT_E_NULL;
+    if (!dptr || !handle || bytes == 0) return fail(ctx, QNMFIT_E_NULL, "qnmfit_peer_alloc: NULL argument or zero size");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
+    void *ptr = nullptr;
+    if ((e = cudaMalloc(&ptr, bytes)) != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(peer window)");
+    if ((e = cudaMemset(ptr, 0, bytes)) != cudaSuccess) { cudaFree(ptr); return cuda_fail(ctx, e, "cudaMemset(peer window)"); }
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) { cudaFree(ptr); return cuda_fail(ctx, e, "cudaDeviceSynchronize"); }
+    cudaIpcMemHandle_t h;
+    if ((e = cudaIpcGetMemHandle(&h, ptr)) != cudaSuccess) { cudaFree(ptr); return cuda_fail(ctx, e, "cudaIpcGetMemHandle"); }
+    memcpy(handle, &h, 64);
+    *dptr = ptr;
+    return 0;
+}
+
+extern "C" int qnmfit_peer_open(qnmfit_ctx *ctx, const unsigned char handle[64], void **dptr)
+{
+    if (!ctx) return QNMFIT_E_NULL;
+    if (!dptr || !handle) return fail(ctx, QNMFIT_E_NULL, "qnmfit_peer_open: NULL argument");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void *ptr = nullptr;
+    if ((e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess)) != cudaSuccess)
+        return cuda_fail(ctx, e, "cudaIpcOpenMemHandle");
+    *dptr = ptr;
+    return 0;
+}
+
+extern "C" int qnmfit_peer_close(qnmfit_ctx *ctx, void *dptr)
+{
+    if (!ctx) return QNMFIT_E_NULL;
+    if (!dptr) return 0;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e == cudaSuccess) e = cudaIpcCloseMemHandle(dptr);
+    return e == cudaSuccess ? 0 : cuda_fail(ctx, e, "cudaIpcCloseMemHandle");
+}
+
+extern "C" int qnmfit_peer_free(qnmfit_ctx *ctx, void *dptr)
+{
+    if (!ctx) return QNMFIT_E_NULL;
+    if (!dptr) return 0;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e == cudaSuccess) e = cudaFree(dptr);
+    return e == cudaSuccess ? 0 : cuda_fail(ctx, e, "cudaFree(peer window)");
 }
 
 extern "C" int qnmfit_plan_batch(qnmfit_ctx *ctx, const qnmfit_batch *b, qnmfit_plan *out)

@@ -148,6 +148,13 @@ struct FitParams {
     int fast_mismatch;   // K1: mismatch from QR by-products (uniform grid, no model output)
     int stage_begin;     // K1 staged variant: first staged row
     int stage_rows;      //                    number of staged rows
+    // multi-GPU exchange fused into the kernels (qnmfit_fit_batch_peers); n_peers <= 1: off
+    int n_peers, peer_rank;
+    unsigned long long peer_epoch;
+    long long peer_timeout_ns;
+    double *peer_mismatch[QNMFIT_MAX_PEERS];
+    double *peer_flagged[QNMFIT_MAX_PEERS];
+    unsigned long long *peer_flags[QNMFIT_MAX_PEERS];
 };
 
 QF_HD int fit_chi_index(const FitParams &p, int fit)
@@ -191,3 +198,63 @@ QF_HD void note_status(const FitParams &p, int status)
 #define QNMFIT_ST_RANK_DEFICIENT_ 1
 #define QNMFIT_ST_NONFINITE_ 2
 #define QNMFIT_ST_UNDERDETERMINED_ 4
+
+// ---- multi-GPU exchange (see include/qnmfit.h, qnmfit_fit_batch_peers) --------------
+//
+// peer_publish: called by the one thread that finished fit `fit`.  It stores the mismatch
+// into every peer's result array — plain posted stores over NVLink that travel while the
+// other fits are still being computed; nothing waits for them here (a system-scope fence
+// per fit or per CTA was measured to cost ~6 us per wave of CTAs: the CTA cannot retire
+// until the fence returns).  Their completion is guaranteed by the end of the kernel.
+//
+// peer_barrier_kernel (one warp, same stream, right after the fit kernel): lane r
+// publishes the launch's flagged count and then its epoch into slot `rank` of peer r
+// (release, system scope), then waits until peer r's epoch has arrived in the local flag
+// array (acquire).  A peer that does not arrive within the timeout leaves NaN in its slot
+// of the local flagged[] array and the host raises.
+#ifndef QNMFIT_HOSTSIM
+QF_DEV unsigned long long qf_globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+QF_DEV void peer_publish(const FitParams &p, int fit, double mm)
+{
+    if (p.n_peers <= 1) return;
+    const long long gi = p.first_fit + fit;
+    for (int r = 0; r < p.n_peers; ++r)
+        if (r != p.peer_rank) p.peer_mismatch[r][gi] = mm;
+}
+
+__global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant__ FitParams p)
+{
+    const int W = p.n_peers, me = p.peer_rank, r = threadIdx.x;
+    // the fit kernel has completed: the count of flagged fits is final; reset it for the next launch
+    double flagged = 0.0;
+    if (r == 0 && p.flagged_count)
+        flagged = __longlong_as_double((long long)atomicExch((unsigned long long *)p.flagged_count, 0ull));
+    flagged = __shfl_sync(0xffffffffu, flagged, 0);
+    if (r >= W) return;
+    *(volatile double *)(p.peer_flagged[r] + me) = flagged;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peer_flags[r] + me), "l"(p.peer_epoch) : "memory");
+    const unsigned long long start = qf_globaltimer();
+    const unsigned long long limit = p.peer_timeout_ns > 0 ? (unsigned long long)p.peer_timeout_ns : 30000000000ull;
+    const unsigned long long *f = p.peer_flags[me] + r;
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+        if (v >= p.peer_epoch) break;
+        if (qf_globaltimer() - start > limit) {
+            *(volatile double *)(p.peer_flagged[me] + r) = __longlong_as_double(0x7ff8000000000000ll);
+            break;
+        }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+}
+#else
+static inline void peer_publish(const FitParams &, int, double) {}
+#endif

@@ -392,12 +392,21 @@ class _Sweep:
         kw = dict(freq_scalars)
         kw.update({k: ptr for k, ptr in zip(names, ptrs[7:])})
 
-        # output slab: per mismatches + one counter of flagged fits
-        self.out_d = torch.empty(max(per, 1) + 1, dtype=torch.float64, device=eng.device)
+        # Results.  Single rank / NCCL path: a slab of `per` mismatches + one counter of
+        # flagged fits, all-gathered after the kernel.  Fused path (_dist.PeerWindow): the
+        # kernel stores every mismatch straight into the whole-sweep array of every rank.
+        self.window = _dist.peer_window(eng, n_fits) if self.ws > 1 else None
         self.gathered = None
         self.batch = None
+        self.slot = None
         dt = nominal_step(times[rb_all:re_all], wmax)
-        if n_local > 0:
+        if self.window is None:
+            self.out_d = torch.empty(max(per, 1) + 1, dtype=torch.float64, device=eng.device)
+            mismatch_d, flagged_d = self.out_d, self.out_d.data_ptr() + 8 * max(per, 1)
+        else:
+            self.out_d = None
+            mismatch_d, flagged_d = 0, None          # set per launch (epoch parity slot)
+        if n_local > 0 or self.window is not None:
             self.batch = eng.make_batch(
                 times_d=ptrs[0], data_d=ptrs[1], n_times=K_tot, series_stride=K_tot,
                 n_fits=n_local, n_modes=n_modes, n_series=L,
@@ -405,18 +414,24 @@ class _Sweep:
                 row_begin_d=ptrs[2], row_end_d=ptrs[3], t0_d=ptrs[4],
                 coef_d=ptrs[5], coef_index_d=ptrs[6], n_coef=n_coef,
                 dt_nominal=dt, uniform_weights=uniform_weights(times[rb_all:re_all], dt),
-                mismatch_d=self.out_d, flagged_d=self.out_d.data_ptr() + 8 * max(per, 1), **kw)
+                mismatch_d=mismatch_d, flagged_d=flagged_d, **kw)
         self.rows_max = re_all - rb_all
 
     def launch_kernel(self):
-        """Asynchronous: the fit kernel on this rank's slab."""
+        """Asynchronous: the fit kernel on this rank's slab (fused path: + the exchange)."""
+        if self.window is not None:
+            peers, local, self.slot = self.window.next_launch()
+            self.batch.mismatch = local + 8 * self.lo
+            self.eng.fit_peers(self.batch, peers)
+            return
         self.out_d[-1:].zero_()
         if self.batch is not None:
             self.eng.fit(self.batch)
 
     def gather(self):
-        """Asynchronous: all-gather of the slabs (NCCL); no-op on a single rank."""
-        if self.ws > 1:
+        """Asynchronous: all-gather of the slabs (NCCL); no-op on a single rank and on the
+        fused path, where the kernel has already delivered every slab to every rank."""
+        if self.ws > 1 and self.window is None:
             self.gathered = _dist.all_gather_slabs(self.out_d, self.out_d.numel() * self.ws)
 
     def launch(self):
@@ -426,6 +441,15 @@ class _Sweep:
     def fetch(self):
         """(mismatch of every fit as float64[n_fits], number of flagged fits), on the host."""
         per = max(self.per, 1)
+        if self.window is not None:
+            out = self.eng.download(self.window.result(self.slot, self.n_fits))
+            counts = out[:self.ws]
+            if not np.all(np.isfinite(counts)):
+                late = [r for r in range(self.ws) if not np.isfinite(counts[r])]
+                raise RuntimeError(
+                    f"qnmfits_b200: rank(s) {late} did not deliver their slab of the sweep within "
+                    "QNMFITS_B200_PEER_TIMEOUT_S; every rank must make the same sweep calls")
+            return out[_cabi.MAX_PEERS:], int(counts.sum())
         if self.ws > 1:
             full = self.eng.download(self.gathered).reshape(self.ws, per + 1)
             return full[:, :per].reshape(-1)[:self.n_fits].copy(), int(full[:, per].sum())

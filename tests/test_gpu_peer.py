@@ -1,0 +1,89 @@
+"""Two NCCL ranks on two GPUs: sweeps sharded by flat fit index with the exchange fused into
+the fit kernels (peer stores + epoch flags, include/qnmfit.h ``qnmfit_fit_batch_peers``)
+must give, on EVERY rank, the bit-identical result of the NCCL all-gather path (same slabs,
+same launch plan) and the result of the unsharded single-GPU sweep to 1e-12 (the slab size
+may select another lanes-per-fit split, i.e. another summation tree).  Needs two GPUs;
+skipped on a one-GPU box."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _sweeps(qf, wl3, wl2, wl4):
+    """The sweeps under test (K1 shared window, K1 per-fit windows, K3 multimode, one
+    single-fit sweep that leaves rank 1 without work), repeated to cycle epochs/slots."""
+    out = {}
+    for rep in range(3):
+        out[f"grid{rep}"] = qf.mismatch_M_chi_grid(wl3.times, wl3.data, wl3.modes, wl3.Mf_minmax,
+                                                   wl3.chif_minmax, wl3.t0, T=wl3.T, res=37 + rep)
+    out["t0"] = np.array(qf.mismatch_t0_array(wl2.times, wl2.data, wl2.modes, wl2.Mf, wl2.chif,
+                                              wl2.t0_array[:301]))
+    out["one"] = np.array(qf.mismatch_t0_array(wl2.times, wl2.data, wl2.modes, wl2.Mf, wl2.chif,
+                                               wl2.t0_array[:1]))
+    out["multimode"] = np.array(qf.mismatch_t0_array(wl4.times, wl4.data, wl4.modes, wl4.Mf, wl4.chif,
+                                                     wl4.t0_array))
+    out["grid_again"] = qf.mismatch_M_chi_grid(wl3.times, wl3.data, wl3.modes, wl3.Mf_minmax,
+                                               wl3.chif_minmax, wl3.t0, T=wl3.T, res=21)
+    return out
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import cases
+    import qnmfits_b200 as qf
+    from qnmfits_b200 import _dist, workloads
+    workloads.use_synthetic_tables()
+    wl3, wl2, wl4 = workloads.config3(res=8), workloads.config2(), cases.cfg4_small()
+
+    fused = _sweeps(qf, wl3, wl2, wl4)
+    assert _dist._windows, "the fused exchange was not used"
+    epochs = next(iter(_dist._windows.values())).epoch
+    os.environ["QNMFITS_B200_PEER"] = "0"
+    nccl = _sweeps(qf, wl3, wl2, wl4)
+    os.environ["QNMFITS_B200_NO_SHARD"] = "1"
+    single = _sweeps(qf, wl3, wl2, wl4)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), epochs=epochs,
+             **{f"fused_{k}": v for k, v in fused.items()},
+             **{f"nccl_{k}": v for k, v in nccl.items()},
+             **{f"single_{k}": v for k, v in single.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_fused_exchange_two_gpus_bit_identical(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for rank in range(2):
+        got = np.load(os.path.join(str(tmp_path), f"rank{rank}.npz"))
+        assert int(got["epochs"]) == 7          # one exchange per sweep call
+        names = [k[len("single_"):] for k in got.files if k.startswith("single_")]
+        assert len(names) == 7
+        for name in names:
+            one = got["single_" + name]
+            assert np.all(np.isfinite(one))
+            assert np.array_equal(got["fused_" + name], got["nccl_" + name]), (rank, name)
+            assert np.max(np.abs(got["fused_" + name] - one)) < 1e-12, (rank, name)
