@@ -231,6 +231,21 @@ int qnmfit_peer_close(qnmfit_ctx *ctx, void *dptr);
 int qnmfit_peer_free(qnmfit_ctx *ctx, void *dptr);
 int qnmfit_fit_batch_peers(qnmfit_ctx *ctx, const qnmfit_batch *b, const qnmfit_peers *peers, void *stream);
 
+/* Stream-ordered transfers for the host wrapper, so that a sweep through the Python API
+ * costs a handful of C calls (the reference pays none: its arrays never leave the host).
+ *   qnmfit_h2d       cudaMemcpyAsync host -> device on `stream`; `src` should be pinned.
+ *                    The ctx remembers the copy; qnmfit_h2d_wait blocks until the most
+ *                    recent one has left the host buffer (so a staging buffer can be
+ *                    refilled).
+ *   qnmfit_d2h       cudaMemcpyAsync device -> host; sync != 0: also wait for the stream.
+ *   qnmfit_zero      cudaMemsetAsync(dst, 0, bytes).
+ *   qnmfit_stream_sync   cudaStreamSynchronize. */
+int qnmfit_h2d(qnmfit_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, void *stream);
+int qnmfit_h2d_wait(qnmfit_ctx *ctx);
+int qnmfit_d2h(qnmfit_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes, void *stream, int sync);
+int qnmfit_zero(qnmfit_ctx *ctx, void *dst_dev, size_t bytes, void *stream);
+int qnmfit_stream_sync(qnmfit_ctx *ctx, void *stream);
+
 /* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
 int64_t qnmfit_launch_count(const qnmfit_ctx *ctx);
 

@@ -85,6 +85,7 @@ EXPORTS = (
     "qnmfit_fp64_peak", "qnmfit_flops_per_fit", "qnmfit_abi_version",
     "qnmfit_peer_alloc", "qnmfit_peer_open", "qnmfit_peer_close", "qnmfit_peer_free",
     "qnmfit_fit_batch_peers",
+    "qnmfit_h2d", "qnmfit_h2d_wait", "qnmfit_d2h", "qnmfit_zero", "qnmfit_stream_sync",
 )
 
 _lib = None
@@ -128,6 +129,16 @@ def load_library(path=None):
         fn = getattr(lib, name)
         fn.argtypes = [C.c_void_p, C.c_void_p]
         fn.restype = C.c_int
+    lib.qnmfit_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.qnmfit_h2d.restype = C.c_int
+    lib.qnmfit_h2d_wait.argtypes = [C.c_void_p]
+    lib.qnmfit_h2d_wait.restype = C.c_int
+    lib.qnmfit_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+    lib.qnmfit_d2h.restype = C.c_int
+    lib.qnmfit_zero.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.qnmfit_zero.restype = C.c_int
+    lib.qnmfit_stream_sync.argtypes = [C.c_void_p, C.c_void_p]
+    lib.qnmfit_stream_sync.restype = C.c_int
     lib.qnmfit_launch_count.argtypes = [C.c_void_p]
     lib.qnmfit_launch_count.restype = C.c_int64
     lib.qnmfit_plan_batch.argtypes = [C.c_void_p, C.POINTER(Batch), C.POINTER(Plan)]
@@ -187,6 +198,21 @@ class Context:
 
     def peer_free(self, ptr):
         self._check(self.lib.qnmfit_peer_free(self.handle, C.c_void_p(ptr)))
+
+    def h2d(self, dst, src, nbytes, stream=0):
+        self._check(self.lib.qnmfit_h2d(self.handle, dst, src, nbytes, stream))
+
+    def h2d_wait(self):
+        self._check(self.lib.qnmfit_h2d_wait(self.handle))
+
+    def d2h(self, dst, src, nbytes, stream=0, sync=True):
+        self._check(self.lib.qnmfit_d2h(self.handle, dst, src, nbytes, stream, 1 if sync else 0))
+
+    def zero(self, dst, nbytes, stream=0):
+        self._check(self.lib.qnmfit_zero(self.handle, dst, nbytes, stream))
+
+    def stream_sync(self, stream=0):
+        self._check(self.lib.qnmfit_stream_sync(self.handle, stream))
 
     def plan(self, batch):
         plan = Plan()

@@ -16,6 +16,10 @@ _engines = {}
 
 def get_engine(device=None):
     import torch
+    if device is None and _engines:
+        eng = _engines.get(torch.cuda.current_device())
+        if eng is not None:
+            return eng
     if not torch.cuda.is_available():
         raise RuntimeError(
             "qnmfits_b200 needs an NVIDIA B200 (sm_100a) GPU: torch.cuda.is_available() "
@@ -28,36 +32,48 @@ def get_engine(device=None):
     return _engines[device]
 
 
-def nominal_step(times, wmax):
-    """Nominal sample spacing if ``times`` is uniform enough for the recurrence path.
+def grid_plan(times, wmax, steps=None):
+    """(dt_nominal, uniform_weights) of a window's time samples, from one pass over its steps.
 
-    The kernels advance a row by ``z *= exp(-i w dt) * (1 - i w d_eps)`` where
-    ``d_eps`` is the deviation of the actual step from ``dt``; the dropped second
+    ``dt_nominal``: the nominal sample spacing if ``times`` is uniform enough for the
+    recurrence path.  The kernels advance a row by ``z *= exp(-i w dt) * (1 - i w d_eps)``
+    where ``d_eps`` is the deviation of the actual step from ``dt``; the dropped second
     order term is ``(|w| d_eps)^2 / 2`` per row, kept below 1e-19 here.  Grids like
-    ``np.arange(n) * 0.1`` (deviations ~1e-14) qualify; genuinely non-uniform grids
-    return 0.0, which selects direct exp/sincos evaluation of every element.
+    ``np.arange(n) * 0.1`` (deviations ~1e-14) qualify; genuinely non-uniform grids give
+    0.0, which selects direct exp/sincos evaluation of every element.
+
+    ``uniform_weights``: True when every step is within 1e-11 (relative) of ``dt``: the
+    trapezoid weights are then uniform to 1e-11 and K1/K3 may take the mismatch from
+    by-products of the factorisation instead of a weighted second pass (changes it by
+    < 1e-11).  ``steps`` = ``np.diff(times)`` if the caller has it already.
     """
     times = np.asarray(times, dtype=float)
     if times.size < 3:
-        return 0.0
-    steps = np.diff(times)
+        return 0.0, False
+    if steps is None:
+        steps = np.diff(times)
     dt = float((times[-1] - times[0]) / (times.size - 1))
     if not np.isfinite(dt) or dt <= 0.0:
-        return 0.0
+        return 0.0, False
     dev = float(np.max(np.abs(steps - dt)))
-    if dev * max(float(wmax), 1.0) <= 4e-10:
-        return dt
-    return 0.0
+    if not dev * max(float(wmax), 1.0) <= 4e-10:
+        return 0.0, False
+    return dt, bool(dev <= 1e-11 * dt)
 
 
-def uniform_weights(times, dt):
-    """True when every step is within 1e-11 (relative) of ``dt``: the trapezoid weights
-    are then uniform to 1e-11 and K1 may take the mismatch from by-products of the
-    factorisation instead of a weighted second pass (changes it by < 1e-11)."""
+def nominal_step(times, wmax, steps=None):
+    """``grid_plan(...)[0]``."""
+    return grid_plan(times, wmax, steps)[0]
+
+
+def uniform_weights(times, dt, steps=None):
+    """``grid_plan``'s second criterion for a given ``dt``."""
     times = np.asarray(times, dtype=float)
     if not dt > 0.0 or times.size < 3:
         return False
-    return bool(np.max(np.abs(np.diff(times) - dt)) <= 1e-11 * dt)
+    if steps is None:
+        steps = np.diff(times)
+    return bool(np.max(np.abs(steps - dt)) <= 1e-11 * dt)
 
 
 class Engine:
@@ -70,7 +86,8 @@ class Engine:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self._pinned_bufs = {}
-        self._upload_event = None
+        self._np_dtype = {torch.float64: np.float64, torch.complex128: np.complex128,
+                          torch.int32: np.int32, torch.int64: np.int64, torch.uint8: np.uint8}
 
     # ------------------------------------------------------------- transfers
 
@@ -94,61 +111,71 @@ class Engine:
         return self.torch.cuda.current_stream(self.device).cuda_stream
 
     # ---------------------------------------- low-overhead packed transfers
+    #
+    # A sweep through the public API moves every input in ONE host->device copy and
+    # every result in ONE device->host copy, issued through the thin C wrappers
+    # (qnmfit_h2d / qnmfit_d2h): a torch copy_ costs ~10 us of dispatch each.
 
     def _pinned(self, name, nbytes):
-        """A cached pinned host buffer of at least nbytes (uint8)."""
+        """A cached pinned host buffer of at least nbytes: (uint8 numpy view, address)."""
         buf = self._pinned_bufs.get(name)
-        if buf is None or buf.numel() < nbytes:
-            buf = self.torch.empty(max(nbytes, 1 << 16), dtype=self.torch.uint8, pin_memory=True)
-            self._pinned_bufs[name] = buf
-        return buf
+        if buf is None or buf[0].numel() < nbytes:
+            t = self.torch.empty(max(int(nbytes) * 5 // 4, 1 << 16), dtype=self.torch.uint8,
+                                 pin_memory=True)
+            buf = self._pinned_bufs[name] = (t, t.numpy(), t.data_ptr())
+        return buf[1], buf[2]
 
-    def upload_packed(self, arrays):
+    def upload_packed(self, arrays, out_bytes=0, stream=None):
         """Copy several host arrays to the device with ONE cudaMemcpyAsync.
 
         ``arrays`` is a list of C-contiguous numpy arrays (or None).  They are packed,
-        256-byte aligned, into a pinned staging buffer and copied into one freshly
-        allocated device buffer; returns (device_buffer, [device pointer or None, ...]).
-        The staging buffer is reused by the next call: the previous copy has completed
-        by then because every public API call ends with a stream synchronisation, and
-        an event guards the remaining cases.
+        256-byte aligned (the last one unpadded), into a pinned staging buffer and copied
+        into one freshly allocated device buffer, which also gets ``out_bytes`` of
+        (uninitialised) room for results behind the last array, 16-byte aligned.  Returns
+        (device_buffer, [device pointer or None, ...], pointer of the result region).
+        The staging buffer is reused by the next call, which first waits until the
+        previous copy has left it (``qnmfit_h2d_wait``).
         """
-        torch = self.torch
         offsets, total = [], 0
         for a in arrays:
             if a is None:
                 offsets.append(None)
                 continue
+            total = (total + 255) // 256 * 256
             offsets.append(total)
-            total += (a.nbytes + 255) // 256 * 256
-        total = max(total, 256)
-        if self._upload_event is not None:
-            self._upload_event.synchronize()
-        stage = self._pinned("upload", total)
-        stage_np = stage.numpy()
+            total += a.nbytes
+        self.ctx.h2d_wait()
+        stage_np, stage_ptr = self._pinned("upload", max(total, 8))
         for a, off in zip(arrays, offsets):
             if a is not None and a.nbytes:
                 stage_np[off:off + a.nbytes] = a.reshape(-1).view(np.uint8)
-        dev = torch.empty(total, dtype=torch.uint8, device=self.device)
-        dev.copy_(stage[:total], non_blocking=True)
-        if self._upload_event is None:
-            self._upload_event = torch.cuda.Event()
-        self._upload_event.record(torch.cuda.current_stream(self.device))
-        self.h2d_bytes += sum(a.nbytes for a in arrays if a is not None)
+        out_off = (total + 15) // 16 * 16
+        dev = self.torch.empty(max(out_off + int(out_bytes), 16), dtype=self.torch.uint8, device=self.device)
         base = dev.data_ptr()
-        return dev, [None if off is None else base + off for off in offsets]
+        if total:
+            self.ctx.h2d(base, stage_ptr, total, self.stream() if stream is None else stream)
+        self.h2d_bytes += total
+        return dev, [None if off is None else base + off for off in offsets], base + out_off
+
+    def download_raw(self, ptr, nbytes, dtype=np.float64, stream=None):
+        """``nbytes`` at device address ``ptr`` -> new numpy array of ``dtype``: one async
+        copy + one stream synchronisation.  Small results go through a cached pinned
+        buffer and are copied out; large ones land in a pinned block of their own (torch's
+        caching host allocator recycles it when the array dies), which saves the host copy."""
+        stream = self.stream() if stream is None else stream
+        self.d2h_bytes += nbytes
+        if nbytes >= 1 << 16:
+            block = self.torch.empty(nbytes, dtype=self.torch.uint8, pin_memory=True)
+            self.ctx.d2h(block.data_ptr(), ptr, nbytes, stream, sync=True)
+            return block.numpy().view(dtype)
+        stage_np, stage_ptr = self._pinned("download", max(nbytes, 8))
+        self.ctx.d2h(stage_ptr, ptr, nbytes, stream, sync=True)
+        return stage_np[:nbytes].view(dtype).copy()
 
     def download(self, tensor):
-        """Device tensor -> new numpy array through a cached pinned buffer (one async
-        copy + one stream synchronisation)."""
-        torch = self.torch
+        """Device tensor (contiguous) -> new numpy array, as ``download_raw``."""
         nbytes = tensor.numel() * tensor.element_size()
-        stage = self._pinned("download", nbytes)
-        view = stage[:nbytes].view(tensor.dtype)
-        view.copy_(tensor.reshape(-1), non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        self.d2h_bytes += nbytes
-        return view.numpy().copy()
+        return self.download_raw(tensor.data_ptr(), nbytes, self._np_dtype[tensor.dtype])
 
     # --------------------------------------------------------------- batches
 
@@ -201,4 +228,4 @@ class Engine:
         self.ctx.eval_batch(batch, self.stream())
 
     def synchronize(self):
-        self.torch.cuda.current_stream(self.device).synchronize()
+        self.ctx.stream_sync(self.stream())

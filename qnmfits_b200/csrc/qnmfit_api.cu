@@ -24,6 +24,8 @@ struct qnmfit_ctx {
     int sm_count;
     int smem_optin;          // max dynamic shared memory per block
     long long launches;
+    cudaEvent_t h2d_event;        // recorded after the most recent qnmfit_h2d
+    int h2d_pending;
     double *peer_scratch;         // device: flagged-fit counter of qnmfit_fit_batch_peers when the caller gives none
     char err[512];
 };
@@ -133,6 +135,8 @@ extern "C" int qnmfit_create(int device, qnmfit_ctx **out)
     ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
     ctx->launches = 0;
     ctx->peer_scratch = nullptr;
+    ctx->h2d_event = nullptr;
+    ctx->h2d_pending = 0;
     ctx->err[0] = 0;
     ctx->k3_g = K3C_DEFAULT_G; ctx->k3_rpt = K3C_DEFAULT_RPT;
     { const char *eg = getenv("QNMFIT_K3G"); int g2 = 0, r2 = 0;
@@ -169,6 +173,7 @@ extern "C" int qnmfit_create(int device, qnmfit_ctx **out)
 extern "C" int qnmfit_destroy(qnmfit_ctx *ctx)
 {
     if (ctx && ctx->peer_scratch) { cudaSetDevice(ctx->device); cudaFree(ctx->peer_scratch); }
+    if (ctx && ctx->h2d_event) cudaEventDestroy(ctx->h2d_event);
     delete ctx;
     return 0;
 }
@@ -431,6 +436,62 @@ extern "C" int qnmfit_fit_batch_peers(qnmfit_ctx *ctx, const qnmfit_batch *b, co
     if (!ctx) return QNMFIT_E_NULL;
     if (!peers) return fail(ctx, QNMFIT_E_NULL, "peers is NULL");
     return launch(ctx, b, stream, false, peers);
+}
+
+// ---------------------------------------------------------------------------
+// stream-ordered transfers for the host wrapper
+
+extern "C" int qnmfit_h2d(qnmfit_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, void *stream)
+{
+    if (!ctx) return QNMFIT_E_NULL;
+    if (bytes == 0) return 0;
+    if (!dst_dev || !src_host) return fail(ctx, QNMFIT_E_NULL, "qnmfit_h2d: NULL pointer");
+    cudaError_t e;
+    if (!ctx->h2d_event && (e = cudaEventCreateWithFlags(&ctx->h2d_event, cudaEventDisableTiming)) != cudaSuccess)
+        return cuda_fail(ctx, e, "cudaEventCreate");
+    if ((e = cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream)) != cudaSuccess)
+        return cuda_fail(ctx, e, "cudaMemcpyAsync(H2D)");
+    if ((e = cudaEventRecord(ctx->h2d_event, (cudaStream_t)stream)) != cudaSuccess) return cuda_fail(ctx, e, "cudaEventRecord");
+    ctx->h2d_pending = 1;
+    return 0;
+}
+
+extern "C" int qnmfit_h2d_wait(qnmfit_ctx *ctx)
+{
+    if (!ctx) return QNMFIT_E_NULL;
+    if (!ctx->h2d_pending) return 0;
+    ctx->h2d_pending = 0;
+    cudaError_t e = cudaEventSynchronize(ctx->h2d_event);
+    return e == cudaSuccess ? 0 : cuda_fail(ctx, e, "cudaEventSynchronize");
+}
+
+extern "C" int qnmfit_d2h(qnmfit_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes, void *stream, int sync)
+{
+    if (!ctx) return QNMFIT_E_NULL;
+    cudaError_t e = cudaSuccess;
+    if (bytes > 0) {
+        if (!dst_host || !src_dev) return fail(ctx, QNMFIT_E_NULL, "qnmfit_d2h: NULL pointer");
+        e = cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMemcpyAsync(D2H)");
+    }
+    if (sync && (e = cudaStreamSynchronize((cudaStream_t)stream)) != cudaSuccess) return cuda_fail(ctx, e, "cudaStreamSynchronize");
+    return 0;
+}
+
+extern "C" int qnmfit_zero(qnmfit_ctx *ctx, void *dst_dev, size_t bytes, void *stream)
+{
+    if (!ctx) return QNMFIT_E_NULL;
+    if (bytes == 0) return 0;
+    if (!dst_dev) return fail(ctx, QNMFIT_E_NULL, "qnmfit_zero: NULL pointer");
+    cudaError_t e = cudaMemsetAsync(dst_dev, 0, bytes, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : cuda_fail(ctx, e, "cudaMemsetAsync");
+}
+
+extern "C" int qnmfit_stream_sync(qnmfit_ctx *ctx, void *stream)
+{
+    if (!ctx) return QNMFIT_E_NULL;
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : cuda_fail(ctx, e, "cudaStreamSynchronize");
 }
 
 // ---------------------------------------------------------------------------

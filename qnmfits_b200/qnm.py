@@ -147,8 +147,25 @@ class qnm:
             omega = -np.conjugate(omega)
         return omega / Mf
 
+    def _scalar_key(self, kind, labels, *scalars):
+        """Memo key of a list call with scalar spin / mass, or None (array arguments,
+        unhashable labels): repeated calls on the same remnant skip the FITPACK
+        evaluations — the values are those the first call computed."""
+        try:
+            if any(np.ndim(v) != 0 for v in scalars):
+                return None
+            return (kind, tuple(map(tuple, labels))) + tuple(
+                v if isinstance(v, (int, float)) else float(v) for v in scalars)
+        except TypeError:
+            return None
+
     def omega_list(self, modes, chif, Mf=1, s=-2):
         """List of mode frequencies; 4p-tuples sum p constituents (qnm.py:237-280)."""
+        key = self._scalar_key('wl', modes, chif, Mf, s)
+        if key is not None:
+            hit = self._tabulated.get(key)
+            if hit is not None:
+                return list(hit)
         out = []
         for mode in modes:
             parts = [
@@ -156,6 +173,8 @@ class qnm:
                 for i in range(0, len(mode), 4)
             ]
             out.append(sum(parts))
+        if key is not None:
+            self._memo(key, lambda: tuple(out))
         return out
 
     def mu(self, ell, m, ellp, mp, nprime, sign, chif, s=-2):
@@ -173,10 +192,18 @@ class qnm:
 
     def mu_list(self, indices, chif, s=-2):
         """Mixing coefficients for (ell, m, ell', m', n', sign) tuples (qnm.py:363-393)."""
-        return [
+        key = self._scalar_key('ml', indices, chif, s)
+        if key is not None:
+            hit = self._tabulated.get(key)
+            if hit is not None:
+                return list(hit)
+        out = [
             self.mu(ell, m, ellp, mp, nprime, sign, chif, s)
             for ell, m, ellp, mp, nprime, sign in indices
         ]
+        if key is not None:
+            self._memo(key, lambda: tuple(out))
+        return out
 
     # ------------------------------------------------- factored device tables
 
@@ -191,7 +218,7 @@ class qnm:
             hit = self._tabulated[key] = compute()
         return hit
 
-    def constituent_table(self, modes, chif_values, s=-2):
+    def constituent_table(self, modes, chif_values, s=-2, with_max=False):
         """Mf-independent frequency table for a sweep over spins.
 
         Returns ``(table, mode_ptr)``: ``table`` is complex128 of shape
@@ -202,10 +229,19 @@ class qnm:
         forms ``omega_j = delta_factor_j * sum_p(table[c, p] * (1/Mf))`` with the
         rounding order of the reference (qnm.py:235 then the Python ``sum`` of
         qnm.py:272-280 then qnmfits.py:274), so the per-point frequencies match it
-        bit for bit.
+        bit for bit.  ``with_max``: also return max |table| (the frequency bound of the
+        device's row recurrence).  The assembled table is memoised per (modes, spins) as
+        well — read-only arrays are returned.
         """
         chif_values = np.atleast_1d(np.asarray(chif_values, dtype=float))
         chi_key = chif_values.tobytes()
+        try:
+            whole_key = ('table', tuple(map(tuple, modes)), s, chi_key)
+            hit = self._tabulated.get(whole_key)
+        except TypeError:
+            whole_key = hit = None
+        if hit is not None:
+            return hit if with_max else hit[:2]
         cols = []
         mode_ptr = [0]
         for mode in modes:
@@ -221,7 +257,13 @@ class qnm:
             mode_ptr.append(len(cols))
         table = np.ascontiguousarray(np.stack(cols, axis=1)) if cols else \
             np.zeros((len(chif_values), 0), dtype=complex)
-        return table, np.asarray(mode_ptr, dtype=np.int32)
+        mode_ptr = np.asarray(mode_ptr, dtype=np.int32)
+        table.setflags(write=False)
+        mode_ptr.setflags(write=False)
+        hit = (table, mode_ptr, float(np.max(np.abs(table))) if table.size else 0.0)
+        if whole_key is not None:
+            self._tabulated[whole_key] = hit
+        return hit if with_max else hit[:2]
 
     def mu_table(self, spherical_modes, modes, chif_values, s=-2):
         """Mixing coefficients mu[c, i, j] for spins c, spherical modes i, QNMs j.

@@ -25,7 +25,7 @@ Deliberate supersets of the reference (documented in DESIGN.md):
 import numpy as np
 
 from . import _cabi, _dist
-from ._engine import get_engine, nominal_step, uniform_weights
+from ._engine import get_engine, grid_plan, nominal_step, uniform_weights
 from .qnm import qnm as _qnm_class
 
 # Module-level provider *instance* that shadows the class, exactly like the
@@ -176,9 +176,10 @@ def _minimum_norm_from_factor(R, M):
 def _single_fit_on_device(times_m, data_rows, frequencies, t0, coef):
     """One fit on the device: ``data_rows`` is (L, K) — the masked series.
 
-    Returns dict with C, mismatch, residual, model (L, K), rank, s.
+    Returns dict with C, mismatch, residual, model (L, K), rank, s.  One packed upload,
+    one launch, one download: the result region behind the inputs holds
+    [C (N) | R (N x (N+1)) | model (L K) | mismatch, residual | status].
     """
-    import torch
     eng = get_engine()
     L, K = data_rows.shape
     N = len(frequencies)
@@ -187,38 +188,47 @@ def _single_fit_on_device(times_m, data_rows, frequencies, t0, coef):
     if K < 1:
         raise ValueError("the analysis window is empty")
     wmax = float(np.max(np.abs(frequencies))) if N else 0.0
-    times_d = eng.to_device(times_m, np.float64)
-    data_d = eng.to_device(data_rows, np.complex128)
-    omega_d = eng.to_device(np.asarray(frequencies, dtype=complex).reshape(1, N), np.complex128)
-    coef_d = None if coef is None else eng.to_device(
-        np.asarray(coef, dtype=complex).reshape(1, L, N), np.complex128)
-    C_d = eng.empty((1, N), torch.complex128)
-    mm_d = eng.empty((1,), torch.float64)
-    res_d = eng.empty((1,), torch.float64)
-    R_d = eng.empty((1, N, N + 1), torch.complex128)
-    st_d = eng.empty((1,), torch.int32)
-    model_d = eng.empty((1, L * K), torch.complex128)
+    stream = eng.stream()
+    host = [np.ascontiguousarray(times_m, dtype=np.float64),
+            np.ascontiguousarray(data_rows, dtype=np.complex128),
+            np.ascontiguousarray(frequencies, dtype=np.complex128).reshape(1, N),
+            None if coef is None else np.ascontiguousarray(coef, dtype=np.complex128).reshape(1, L, N),
+            None if coef is None else np.zeros(1, np.int32)]
+    n_c, n_r, n_m = 16 * N, 16 * N * (N + 1), 16 * L * K
+    out_bytes = n_c + n_r + n_m + 16 + 8
+    keep, ptrs, out = eng.upload_packed(host, out_bytes=out_bytes, stream=stream)
+    C_p, R_p, model_p = out, out + n_c, out + n_c + n_r
+    mm_p = model_p + n_m
     common = dict(
-        times_d=times_d, data_d=data_d, n_fits=1, n_modes=N, n_series=L,
+        times_d=ptrs[0], data_d=ptrs[1], n_times=K, series_stride=K, n_fits=1, n_modes=N, n_series=L,
         row_begin_all=0, row_end_all=K, t0_all=float(t0),
-        omega_d=omega_d, omega_shared=True, coef_d=coef_d, n_coef=0 if coef is None else 1,
-        coef_index_d=None if coef is None else eng.to_device(np.zeros(1, np.int32), np.int32),
+        omega_d=ptrs[2], omega_shared=True, coef_d=ptrs[3], n_coef=0 if coef is None else 1,
+        coef_index_d=ptrs[4],
         dt_nominal=nominal_step(times_m, wmax),
-        C_d=C_d, mismatch_d=mm_d, residual_d=res_d, status_d=st_d,
-        model_d=model_d, model_stride=L * K)
-    eng.fit(eng.make_batch(R_d=R_d, **common))
-    R = eng.to_host(R_d)[0]
+        C_d=C_p, mismatch_d=mm_p, residual_d=mm_p + 8, status_d=mm_p + 16,
+        model_d=model_p, model_stride=L * K)
+    eng.ctx.fit_batch(eng.make_batch(R_d=R_p, **common), stream)
+
+    def fetch():
+        raw = eng.download_raw(out, out_bytes, np.uint8, stream=stream)
+        return (raw[:n_c].view(np.complex128), raw[n_c:n_c + n_r].view(np.complex128).reshape(N, N + 1),
+                raw[n_c + n_r:n_c + n_r + n_m].view(np.complex128).reshape(L, K),
+                raw[n_c + n_r + n_m:n_c + n_r + n_m + 16].view(np.float64),
+                int(raw[n_c + n_r + n_m + 16:n_c + n_r + n_m + 20].view(np.int32)[0]))
+
+    C, R, model, scal, status = fetch()
     rank, s = _rank_and_singular_values(R, L * K)
     if rank < N:
         # numpy truncates here: complete the minimum-norm solution from the factor
         # and re-evaluate model / mismatch on the device with it.
-        C_min = _minimum_norm_from_factor(R, L * K)
-        C_d.copy_(torch.from_numpy(np.ascontiguousarray(C_min.reshape(1, N))))
-        eng.evaluate(eng.make_batch(**common))
+        C_min = np.ascontiguousarray(_minimum_norm_from_factor(R, L * K).reshape(N), dtype=np.complex128)
+        keep2, p2, _ = eng.upload_packed([C_min], stream=stream)
+        eng.ctx.eval_batch(eng.make_batch(**dict(common, C_d=p2[0])), stream)
+        _, _, model, scal, status = fetch()
+        C = C_min
     return {
-        'C': eng.to_host(C_d)[0], 'mismatch': np.float64(eng.to_host(mm_d)[0]),
-        'residual': eng.to_host(res_d)[0], 'model': eng.to_host(model_d)[0].reshape(L, K),
-        'rank': rank, 's': s, 'status': int(eng.to_host(st_d)[0]),
+        'C': C, 'mismatch': np.float64(scal[0]), 'residual': scal[1], 'model': model,
+        'rank': rank, 's': s, 'status': status,
     }
 
 
@@ -343,16 +353,19 @@ class _Sweep:
     ``windows`` is (begin[n], end[n]) int32 arrays or a single (begin, end) pair; ``t0s``
     is float64[n] or a scalar.  With torch.distributed initialised the flat fit index is
     split into one contiguous slab per rank (``_dist.shard_bounds``); ``launch`` runs
-    this rank's slab and all-gathers the mismatches.
+    this rank's slab and delivers every slab to every rank.
 
     Host overhead is kept small: every input goes to the device in ONE pinned-memory
-    copy (``Engine.upload_packed``); the kernels count flagged fits into one double
-    behind the mismatch slab, so the result comes back in ONE copy as well.
+    copy (``Engine.upload_packed``); the kernels count flagged fits into one double next
+    to the mismatch array, so the result comes back in ONE copy as well.  Three result
+    paths: one rank — [counter | mismatch] sits right behind the inputs in the same
+    device buffer (the counter's zero travels with the upload); several ranks — the
+    kernel stores into the peer windows of all ranks (``_dist.PeerWindow``), or, when
+    peer mapping is unavailable, an NCCL all-gather of [mismatch slab | counter].
     """
 
     def __init__(self, times, rows, *, n_fits, n_modes, windows, t0s, freq_arrays, freq_scalars,
-                 coef, coef_per_chi, wmax):
-        import torch
+                 coef, coef_per_chi, wmax, steps=None):
         eng = self.eng = get_engine()
         self.n_fits = n_fits
         self.rank, self.ws = _dist.world()
@@ -360,6 +373,7 @@ class _Sweep:
         self.lo, self.hi, self.per = lo, hi, per
         n_local = hi - lo
         L, K_tot = rows.shape
+        self.stream = eng.stream()
 
         shared_window = not isinstance(windows[0], np.ndarray)
         if shared_window:
@@ -383,29 +397,37 @@ class _Sweep:
             if not coef_per_chi:
                 coef_index = np.zeros(max(n_local, 1), np.int32)
 
+        self.window = _dist.peer_window(eng, n_fits) if self.ws > 1 else None
+        self.out_d = self.gathered = self.batch = self.slot = None
         names = list(freq_arrays)
         host = [np.ascontiguousarray(times, dtype=np.float64),
                 np.ascontiguousarray(rows, dtype=np.complex128), rb, re, t0_arr, coef_arr,
                 coef_index] + [np.ascontiguousarray(freq_arrays[k][0], dtype=freq_arrays[k][1])
                                for k in names]
-        self._inputs, ptrs = eng.upload_packed(host)
+        out_bytes = 0
+        if self.ws == 1:
+            host.append(_ZERO)                       # the counter of flagged fits, zeroed by the upload
+            out_bytes = 8 * n_fits
+        self._inputs, ptrs, out = eng.upload_packed(host, out_bytes=out_bytes, stream=self.stream)
         kw = dict(freq_scalars)
         kw.update({k: ptr for k, ptr in zip(names, ptrs[7:])})
 
-        # Results.  Single rank / NCCL path: a slab of `per` mismatches + one counter of
-        # flagged fits, all-gathered after the kernel.  Fused path (_dist.PeerWindow): the
-        # kernel stores every mismatch straight into the whole-sweep array of every rank.
-        self.window = _dist.peer_window(eng, n_fits) if self.ws > 1 else None
-        self.gathered = None
-        self.batch = None
-        self.slot = None
-        dt = nominal_step(times[rb_all:re_all], wmax)
-        if self.window is None:
+        if self.ws == 1:
+            mismatch_d, flagged_d = out, out - 8
+            self._result = out - 8                   # [counter | mismatch[n_fits]]
+            self._fresh = True                       # counter still zero from the upload
+        elif self.window is None:
+            import torch
             self.out_d = torch.empty(max(per, 1) + 1, dtype=torch.float64, device=eng.device)
             mismatch_d, flagged_d = self.out_d, self.out_d.data_ptr() + 8 * max(per, 1)
         else:
-            self.out_d = None
             mismatch_d, flagged_d = 0, None          # set per launch (epoch parity slot)
+        window_times = times[rb_all:re_all]
+        if steps is None:
+            steps = np.diff(window_times)
+        else:
+            steps = steps[rb_all:re_all - 1]
+        dt, uniform = grid_plan(window_times, wmax, steps)
         if n_local > 0 or self.window is not None:
             self.batch = eng.make_batch(
                 times_d=ptrs[0], data_d=ptrs[1], n_times=K_tot, series_stride=K_tot,
@@ -413,20 +435,26 @@ class _Sweep:
                 first_fit=lo, row_begin_all=rb_all, row_end_all=re_all, t0_all=t0_all,
                 row_begin_d=ptrs[2], row_end_d=ptrs[3], t0_d=ptrs[4],
                 coef_d=ptrs[5], coef_index_d=ptrs[6], n_coef=n_coef,
-                dt_nominal=dt, uniform_weights=uniform_weights(times[rb_all:re_all], dt),
+                dt_nominal=dt, uniform_weights=uniform,
                 mismatch_d=mismatch_d, flagged_d=flagged_d, **kw)
         self.rows_max = re_all - rb_all
 
     def launch_kernel(self):
         """Asynchronous: the fit kernel on this rank's slab (fused path: + the exchange)."""
+        eng = self.eng
         if self.window is not None:
             peers, local, self.slot = self.window.next_launch()
             self.batch.mismatch = local + 8 * self.lo
-            self.eng.fit_peers(self.batch, peers)
+            eng.ctx.fit_batch_peers(self.batch, peers, self.stream)
             return
-        self.out_d[-1:].zero_()
+        if self.ws == 1:
+            if not self._fresh:
+                eng.ctx.zero(self._result, 8, self.stream)
+            self._fresh = False
+        else:
+            self.out_d[-1:].zero_()
         if self.batch is not None:
-            self.eng.fit(self.batch)
+            eng.ctx.fit_batch(self.batch, self.stream)
 
     def gather(self):
         """Asynchronous: all-gather of the slabs (NCCL); no-op on a single rank and on the
@@ -441,6 +469,9 @@ class _Sweep:
     def fetch(self):
         """(mismatch of every fit as float64[n_fits], number of flagged fits), on the host."""
         per = max(self.per, 1)
+        if self.ws == 1:
+            out = self.eng.download_raw(self._result, 8 * (1 + self.n_fits), stream=self.stream)
+            return out[1:], int(out[0])
         if self.window is not None:
             out = self.eng.download(self.window.result(self.slot, self.n_fits))
             counts = out[:self.ws]
@@ -450,11 +481,11 @@ class _Sweep:
                     f"qnmfits_b200: rank(s) {late} did not deliver their slab of the sweep within "
                     "QNMFITS_B200_PEER_TIMEOUT_S; every rank must make the same sweep calls")
             return out[_cabi.MAX_PEERS:], int(counts.sum())
-        if self.ws > 1:
-            full = self.eng.download(self.gathered).reshape(self.ws, per + 1)
-            return full[:, :per].reshape(-1)[:self.n_fits].copy(), int(full[:, per].sum())
-        out = self.eng.download(self.out_d)
-        return out[:self.n_fits], int(out[per])
+        full = self.eng.download(self.gathered).reshape(self.ws, per + 1)
+        return full[:, :per].reshape(-1)[:self.n_fits].copy(), int(full[:, per].sum())
+
+
+_ZERO = np.zeros(2, np.float64)   # 16 bytes: the result region behind it stays contiguous
 
 
 def _sweep_on_device(*args, **kwargs):
@@ -573,18 +604,39 @@ def mismatch_t0_array(times, data, modes, Mf, chif, t0_array, t0_method='geq',
     return [np.float64(v) for v in mm]
 
 
+_linspace_memo = {}
+
+
+def _linspace(lo, hi, res):
+    """(np.linspace(lo, hi, res), its reciprocal, max |reciprocal|), memoised: the grid
+    axes of the reference (qnmfits.py:1387-1388) and the 1/Mf factors the device uses."""
+    key = (float(lo), float(hi), int(res))
+    hit = _linspace_memo.get(key)
+    if hit is None:
+        if len(_linspace_memo) > 256:
+            _linspace_memo.clear()
+        arr = np.linspace(lo, hi, res)
+        with np.errstate(divide='ignore'):
+            inv = 1.0 / arr
+        arr.setflags(write=False)
+        inv.setflags(write=False)
+        hit = _linspace_memo[key] = (arr, inv, float(np.max(np.abs(inv))) if res else 0.0)
+    return hit
+
+
 def _prepare_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0, t0_method='geq',
                         T=100, res=50, spherical_modes=None, delta=0.0):
     """Host tabulation + upload for the grid sweep; returns (sweep, shape)."""
     times = np.asarray(times)
     _check_modes(modes)
-    Mf_array = np.linspace(Mf_minmax[0], Mf_minmax[1], res)
-    chif_array = np.linspace(chif_minmax[0], chif_minmax[1], res)
+    Mf_array, inv_Mf, inv_max = _linspace(Mf_minmax[0], Mf_minmax[1], res)
+    chif_array = _linspace(chif_minmax[0], chif_minmax[1], res)[0]
     shape = (len(Mf_array), len(chif_array))
     n = shape[0] * shape[1]
     if n == 0:
         return None, shape
-    if np.any(np.diff(times) < 0):
+    steps = np.diff(times)
+    if steps.size and steps.min() < 0:
         raise ValueError("times must be ascending")
     window = _window_rows(times, t0, T, t0_method)
     if window[1] <= window[0]:
@@ -594,8 +646,7 @@ def _prepare_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0, t0_metho
     # Frequencies are tabulated for the `res` unique spins only and shipped factored:
     # the device forms omega = delta_factor * sum(table[chi] * (1/Mf)) per grid point
     # with the reference's rounding (qnm.py:235,272-280; qnmfits.py:274).
-    table, mode_ptr = qnm.constituent_table(modes, chif_array)
-    inv_Mf = 1.0 / Mf_array
+    table, mode_ptr, table_max = qnm.constituent_table(modes, chif_array, with_max=True)
     if keys is None:
         df = _delta_factor(delta, len(modes))
         df = np.broadcast_to(np.asarray(df, dtype=float), (len(modes),)).copy()
@@ -606,7 +657,7 @@ def _prepare_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0, t0_metho
                 raise ValueError("multimode fits take (ell, m, n, sign) labels only")
         df = None
         coef = qnm.mu_table(keys, modes, chif_array)
-    wmax = float(np.max(np.abs(table)) * np.max(np.abs(inv_Mf))
+    wmax = float(table_max * inv_max
                  * (1.0 if df is None else np.max(np.abs(df)))) * max(
                      len(m) // 4 for m in modes)
     freq_arrays = dict(
@@ -619,7 +670,7 @@ def _prepare_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0, t0_metho
         windows=window, t0s=float(t0), freq_arrays=freq_arrays,
         freq_scalars=dict(n_chi=len(chif_array), n_mf=len(Mf_array),
                           n_constituents=table.shape[1]),
-        coef=coef, coef_per_chi=True, wmax=wmax)
+        coef=coef, coef_per_chi=True, wmax=wmax, steps=steps)
     return sweep, shape
 
 
@@ -666,14 +717,13 @@ class _ResidentData:
         if self.window[1] <= self.window[0]:
             raise ValueError("the analysis window is empty")
         self.t0 = float(t0)
-        self._keep, ptrs = eng.upload_packed([np.ascontiguousarray(times), np.ascontiguousarray(rows)])
+        self._keep, ptrs, _ = eng.upload_packed([np.ascontiguousarray(times), np.ascontiguousarray(rows)])
         self.times_p, self.data_p = ptrs
         tw = times[self.window[0]:self.window[1]]
         # nominal_step() with the frequency bound applied per launch
         self._dt = nominal_step(tw, 0.0)
         self._dev = float(np.max(np.abs(np.diff(tw) - self._dt))) if self._dt > 0.0 else np.inf
         self.uniform = uniform_weights(tw, self._dt)
-        self.mm_d = torch.empty(1, dtype=torch.float64, device=eng.device)
         self.launches = 0
 
     def mismatches(self, omega, coef=None, series_index=None, n_series=1, row_end=None):
@@ -686,8 +736,6 @@ class _ResidentData:
         n, N = omega.shape
         if N > _cabi.MAX_MODES:
             raise ValueError(f"at most {_cabi.MAX_MODES} modes are supported, got {N}")
-        if self.mm_d.numel() < n:
-            self.mm_d = torch.empty(n, dtype=torch.float64, device=eng.device)
         finite = np.isfinite(omega).all()
         wmax = float(np.max(np.abs(omega))) if (n and finite) else np.inf
         dt = self._dt if self._dev * max(wmax, 1.0) <= 4e-10 else 0.0
@@ -699,19 +747,20 @@ class _ResidentData:
                   None if series_index is None else np.ascontiguousarray(series_index, dtype=np.int32),
                   None if coef is None else np.ascontiguousarray(coef, dtype=np.complex128),
                   None if coef is None else np.arange(n, dtype=np.int32), rb, re]
-        keep, ptrs = eng.upload_packed(arrays)
+        stream = eng.stream()
+        keep, ptrs, out = eng.upload_packed(arrays, out_bytes=8 * n, stream=stream)
         batch = eng.make_batch(
             times_d=self.times_p, data_d=self.data_p, n_times=self.K_tot, series_stride=self.K_tot,
             n_fits=n, n_modes=N, n_series=n_series, row_begin_all=self.window[0],
             row_end_all=self.window[1], t0_all=self.t0, omega_d=ptrs[0], series_index_d=ptrs[1],
             coef_d=ptrs[2], coef_index_d=ptrs[3], n_coef=0 if coef is None else n,
             row_begin_d=ptrs[4], row_end_d=ptrs[5], dt_nominal=dt,
-            uniform_weights=self.uniform and dt > 0.0, mismatch_d=self.mm_d)
-        eng.fit(batch)
+            uniform_weights=self.uniform and dt > 0.0, mismatch_d=out)
+        eng.ctx.fit_batch(batch, stream)
         self.launches += 1
-        out = eng.download(self.mm_d[:n])
+        result = eng.download_raw(out, 8 * n, stream=stream)
         del keep
-        return out
+        return result
 
 
 class _FreeFrequencyObjective(_ResidentData):
