@@ -95,25 +95,37 @@ class PeerWindow:
                 self.ptrs.append(ptr)
         self.view = torch.as_tensor(_DeviceMemory(self.local_ptr, self.n_words), device=eng.device)
         self.epoch = 0
+        self._peers = {}
         self.timeout_ns = int(float(os.environ.get("QNMFITS_B200_PEER_TIMEOUT_S", "30")) * 1e9)
+
+    def _slot_base(self, slot):
+        return self.WORDS_HEAD + slot * self.slot_words
 
     def next_launch(self):
         """Descriptor of the next exchange: (qnmfit_peers, local mismatch pointer, slot)."""
         from . import _cabi
         self.epoch += 1
         slot = self.epoch & 1
-        base = self.WORDS_HEAD + slot * self.slot_words
-        pe = _cabi.Peers(n_peers=self.ws, rank=self.rank, epoch=self.epoch, timeout_ns=self.timeout_ns)
-        for r, ptr in enumerate(self.ptrs):
-            pe.flags[r] = ptr
-            pe.flagged[r] = ptr + 8 * base
-            pe.mismatch[r] = ptr + 8 * (base + _cabi.MAX_PEERS)
-        return pe, self.local_ptr + 8 * (base + _cabi.MAX_PEERS), slot
+        pe = self._peers.get(slot)
+        if pe is None:                       # built once per slot; only the epoch changes
+            base = self._slot_base(slot)
+            pe = _cabi.Peers(n_peers=self.ws, rank=self.rank, timeout_ns=self.timeout_ns)
+            for r, ptr in enumerate(self.ptrs):
+                pe.flags[r] = ptr
+                pe.flagged[r] = ptr + 8 * base
+                pe.mismatch[r] = ptr + 8 * (base + _cabi.MAX_PEERS)
+            self._peers[slot] = pe
+        pe.epoch = self.epoch
+        return pe, self.local_ptr + 8 * (self._slot_base(slot) + _cabi.MAX_PEERS), slot
+
+    def result_ptr(self, slot):
+        """Device address of slot ``slot``: [per-rank flagged counts (8) | mismatch ...]."""
+        return self.local_ptr + 8 * self._slot_base(slot)
 
     def result(self, slot, n_items):
         """Device view of slot ``slot``: [per-rank flagged counts (8) | mismatch (n_items)]."""
         from . import _cabi
-        base = self.WORDS_HEAD + slot * self.slot_words
+        base = self._slot_base(slot)
         return self.view[base:base + _cabi.MAX_PEERS + n_items]
 
     def close(self):

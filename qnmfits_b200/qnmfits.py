@@ -473,7 +473,8 @@ class _Sweep:
             out = self.eng.download_raw(self._result, 8 * (1 + self.n_fits), stream=self.stream)
             return out[1:], int(out[0])
         if self.window is not None:
-            out = self.eng.download(self.window.result(self.slot, self.n_fits))
+            out = self.eng.download_raw(self.window.result_ptr(self.slot),
+                                        8 * (_cabi.MAX_PEERS + self.n_fits), stream=self.stream)
             counts = out[:self.ws]
             if not np.all(np.isfinite(counts)):
                 late = [r for r in range(self.ws) if not np.isfinite(counts[r])]
