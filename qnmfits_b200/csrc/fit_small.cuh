@@ -44,7 +44,12 @@ struct SmallLayout {
     QF_MEMBOTH static constexpr int pair(int j, int k) { return j * N - j * (j - 1) / 2 + (k - j - 1); }
 };
 
-// Views into the CTA's shared memory.
+// Rows appended to a staged window (copies of its last row) so that the pipelined leaf
+// loop may read up to two blocks ahead without clamping its indices.
+#define SMALL_STAGE_PAD 8
+
+// Views into the CTA's shared memory.  stage_rows counts the window's own rows; a staged
+// window (stage_rows > 0) is followed by SMALL_STAGE_PAD more.
 template <int N, int THREADS>
 struct SmallSmem {
     double2 *Ro;        // [NP][THREADS]   off-diagonal + rhs
@@ -59,11 +64,13 @@ struct SmallSmem {
 
     QF_MEMBOTH static size_t bytes(int fpc, int stage_rows)
     {
+        if (stage_rows > 0) stage_rows += SMALL_STAGE_PAD;
         return sizeof(double2) * (size_t)(SmallLayout<N>::NP * THREADS + 3 * N * fpc + stage_rows)
              + sizeof(double) * (size_t)(N * THREADS + stage_rows);
     }
     QF_MEM void carve(void *base, int fpc_, int stage_rows)
     {
+        if (stage_rows > 0) stage_rows += SMALL_STAGE_PAD;
         fpc = fpc_;
         double2 *p2 = (double2 *)base;
         Ro = p2; p2 += SmallLayout<N>::NP * THREADS;
@@ -282,11 +289,18 @@ QF_HD void small_absorb_v1(double2 (&B)[4][N + 1], double *Rd, double2 *Ro)
 // sees already interleaves independent chains: (A) the column norm and the raw dot
 // products b^H B_k of ALL trailing columns, rows outermost; (B) the reflector scalars,
 // whose rsqrt/rcp latency the dots cover; (C) the row of R and the rank-1 update.
-template <int N, int THREADS, int JSTART>
-QF_HD void small_absorb(double2 (&B)[4][N + 1], double *Rd, double2 *Ro)
+// `done(j)` runs after reflection j, when column j of B is dead: the pipelined leaf loop
+// refills it with the next block's rows there, so that this independent work overlaps the
+// latency-bound reflections of the last columns.
+struct SmallNoHook { QF_MEM void operator()(int) const {} };
+
+template <int N, int THREADS, int JSTART, class Hook>
+QF_HD void small_absorb_hook(double2 (&B)[4][N + 1], double *Rd, double2 *Ro, const Hook &done)
 {
 #ifdef QNMFIT_ABSORB_V1
     small_absorb_v1<N, THREADS, JSTART>(B, Rd, Ro);
+#pragma unroll
+    for (int j = JSTART; j < N; ++j) done(j);
 #else
     typedef SmallLayout<N> LY;
 #pragma unroll
@@ -353,9 +367,67 @@ QF_HD void small_absorb(double2 (&B)[4][N + 1], double *Rd, double2 *Ro)
                 B[i][k].y = by;
             }
         }
+        done(j);
     }
 #endif
 }
+
+template <int N, int THREADS, int JSTART>
+QF_HD void small_absorb(double2 (&B)[4][N + 1], double *Rd, double2 *Ro)
+{
+    small_absorb_hook<N, THREADS, JSTART>(B, Rd, Ro, SmallNoHook());
+}
+
+// Refill a column of B with the next block's four rows and advance the generator:
+// row k+1 = row k * (q + q(-i w) de_k), de_k the deviation of that step from the nominal one.
+template <int N>
+QF_HD void small_fill_column(double2 (&B)[4][N + 1], double2 (&z)[N], const double (&de)[4], const double2 *qq,
+                             const double2 *qw, int fpc, int c)
+{
+#ifndef QNMFIT_ABL_NOGEN
+    const double2 q = qq[c * fpc], w = qw[c * fpc];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        B[i][c] = z[c];
+        z[c] = c_mul(z[c], make_double2(fma(w.x, de[i], q.x), fma(w.y, de[i], q.y)));
+    }
+#else
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { B[i][c] = z[c]; z[c].x += de[i]; }
+#endif
+}
+
+// Pipelining of the leaf loop: the first H columns of the NEXT block are generated inside
+// the current block's reflection sweep — column c right after reflection c + S, when column
+// c of the current block has long been retired — so that this independent work fills the
+// latency-bound reflections of the last columns; the other columns are generated at the top
+// of the next iteration.  H = 0: everything at the top.  Measured on B200 (cfg3, N = 8,
+// tools/k1_variants.py): H = 0: 2.243 ms, H = 2: 2.244, H = 3: 2.245, H = 4: 2.248,
+// H = 8 / S = 0: 2.274 — ptxas already interleaves the generator with the sweep, and the
+// kernel time follows the FP64 instruction count (ablations: no generator -11.5 % time for
+// -10.2 % FP64 instructions; no rsqrt/rcp chains -2 % for -4.5 %), not the latency of the
+// last reflections.  Default: off.
+#ifndef QNMFIT_PIPE_H
+#define QNMFIT_PIPE_H(N) 0
+#endif
+#ifndef QNMFIT_PIPE_S
+#define QNMFIT_PIPE_S(N) ((N) - QNMFIT_PIPE_H(N))
+#endif
+
+template <int N>
+struct SmallRefill {
+    static constexpr int H = QNMFIT_PIPE_H(N), S = QNMFIT_PIPE_S(N);
+    static_assert(H >= 0 && H <= N && S >= 0 && H + S <= N, "column c is refilled after reflection c + S <= N - 1");
+    double2 (&B)[4][N + 1];
+    double2 (&z)[N];
+    const double (&de)[4];
+    const double2 *qq, *qw;
+    int fpc;
+    QF_MEM void operator()(int j) const
+    {
+        if (j >= S && j - S < H) small_fill_column<N>(B, z, de, qq, qw, fpc, j - S);
+    }
+};
 
 // Zero the lane's factor.
 template <int N, int THREADS>
@@ -425,7 +497,7 @@ QF_HD void small_leaf_generic(const FitParams &p, const SmallSmem<N, THREADS> &s
 // row k+1 = row k * (q + q(-i w) de_k), where de_k = (tau_{k+1} - tau_k) - dt is the
 // (tiny, exactly computed) deviation of that step from the nominal one.  The at most
 // three rows left over at the end of the lane are evaluated directly.
-template <int N, int THREADS>
+template <int N, int THREADS, bool PADDED>
 QF_HD void small_leaf_uniform(const FitParams &p, const SmallSmem<N, THREADS> &sm, const SmallLane &L, int tid,
                               SmallAcc &acc)
 {
@@ -441,46 +513,56 @@ QF_HD void small_leaf_uniform(const FitParams &p, const SmallSmem<N, THREADS> &s
     int row0 = L.lo;
     double2 z[N];
     double2 B[4][N + 1];
+    double de[4];
     double sdd1 = 0.0, res1 = 0.0;   // second accumulation chains
+    // Software pipeline (SmallRefill): while block b is folded into R, the first H columns
+    // of block b+1 are generated into the registers of columns the sweep has retired.  Rows
+    // read ahead of the lane's share are clamped to the window (PADDED: the staged window
+    // carries SMALL_STAGE_PAD duplicate rows instead); what they generate is never used,
+    // because every segment starts from a fresh anchor.
+    constexpr int H = SmallRefill<N>::H;
 #pragma unroll 1
     for (int blk = 0; blk < nfull;) {
         const int nb = nfull - blk < ablk ? nfull - blk : ablk;
         double tau = qf_sub_rn(ts[row0], t0);
 #pragma unroll
         for (int j = 0; j < N; ++j) z[j] = design_entry(om[j * fpc], tau);
-#pragma unroll 1
-        for (int b = 0; b < nb; ++b) {
-            // all loads of the block up front: one exposed shared-memory latency per block
-            const int r4 = row0 + 4 < last ? row0 + 4 : last;   // clamps only in the window's last block,
-            double tn[4];                                        // whose advanced z is never used
+        {   // deviations of the segment's first block; its first H columns
+            const int r4 = PADDED || row0 + 4 < last ? row0 + 4 : last;
+            double tn[4];
             tn[0] = ts[row0 + 1]; tn[1] = ts[row0 + 2]; tn[2] = ts[row0 + 3]; tn[3] = ts[r4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) B[i][N] = ds[row0 + i];
-            double de[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const double tau_n = qf_sub_rn(tn[i], t0);
                 de[i] = qf_sub_rn(qf_sub_rn(tau_n, tau), dt);
                 tau = tau_n;
             }
-#ifndef QNMFIT_ABL_NOGEN
 #pragma unroll
-            for (int j = 0; j < N; ++j) {
-                const double2 q = qq[j * fpc], w = qw[j * fpc];
+            for (int c = 0; c < H; ++c) small_fill_column<N>(B, z, de, qq, qw, fpc, c);
+        }
+#pragma unroll 1
+        for (int b = 0; b < nb; ++b) {
+            // all loads of the iteration up front: this block's data, the next block's times
+            double tn[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    B[i][j] = z[j];
-                    z[j] = c_mul(z[j], make_double2(fma(w.x, de[i], q.x), fma(w.y, de[i], q.y)));
-                }
+            for (int i = 0; i < 4; ++i) {
+                const int rt = PADDED || row0 + 5 + i < last ? row0 + 5 + i : last;
+                tn[i] = ts[rt];
+                B[i][N] = ds[row0 + i];
             }
-#else
+            // the remaining columns of this block, with this block's deviations ...
 #pragma unroll
-            for (int j = 0; j < N; ++j)
+            for (int c = H; c < N; ++c) small_fill_column<N>(B, z, de, qq, qw, fpc, c);
+            // ... then the next block's deviations
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { B[i][j] = z[j]; z[j].x += de[i]; }
-#endif
+            for (int i = 0; i < 4; ++i) {
+                const double tau_n = qf_sub_rn(tn[i], t0);
+                de[i] = qf_sub_rn(qf_sub_rn(tau_n, tau), dt);
+                tau = tau_n;
+            }
             small_acc_rhs2<N>(B, acc.sdd, sdd1);
-            small_absorb<N, THREADS, 0>(B, sm.Rd + tid, sm.Ro + tid);
+            const SmallRefill<N> refill = {B, z, de, qq, qw, fpc};
+            small_absorb_hook<N, THREADS, 0>(B, sm.Rd + tid, sm.Ro + tid, refill);
             small_acc_rhs2<N>(B, acc.res2, res1);
             row0 += 4;
         }
@@ -497,13 +579,13 @@ QF_HD void small_leaf_uniform(const FitParams &p, const SmallSmem<N, THREADS> &s
             B[i][N] = valid ? ds[valid ? row0 + i : row0] : zero;
             const int rn = row0 + i + 1 < last ? row0 + i + 1 : last;
             const double tau_n = qf_sub_rn(ts[rn], t0);
-            const double de = qf_sub_rn(qf_sub_rn(tau_n, tau), dt);
+            const double de1 = qf_sub_rn(qf_sub_rn(tau_n, tau), dt);
             tau = tau_n;
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 const double2 q = qq[j * fpc], w = qw[j * fpc];
                 B[i][j] = valid ? z[j] : zero;
-                z[j] = c_mul(z[j], make_double2(fma(w.x, de, q.x), fma(w.y, de, q.y)));
+                z[j] = c_mul(z[j], make_double2(fma(w.x, de1, q.x), fma(w.y, de1, q.y)));
             }
         }
         small_acc_rhs<N>(B, acc.sdd);
@@ -515,13 +597,13 @@ QF_HD void small_leaf_uniform(const FitParams &p, const SmallSmem<N, THREADS> &s
 }
 
 // Leaf stage: sequential TSQR over the lane's rows.
-template <int N, int THREADS>
+template <int N, int THREADS, bool PADDED = false>
 QF_HD void small_leaf(const FitParams &p, const SmallSmem<N, THREADS> &sm, const SmallLane &L, int tid,
                       SmallAcc &acc)
 {
     acc.sdd = acc.res2 = acc.cn2 = 0.0;
     if (L.fit < 0) return;
-    if (p.dt_nominal > 0.0) small_leaf_uniform<N, THREADS>(p, sm, L, tid, acc);
+    if (p.dt_nominal > 0.0) small_leaf_uniform<N, THREADS, PADDED>(p, sm, L, tid, acc);
     else small_leaf_generic<N, THREADS>(p, sm, L, tid, acc);
 }
 
@@ -753,9 +835,10 @@ __global__ void __launch_bounds__(THREADS, 1) fit_small_kernel(const __grid_cons
     if (STAGED) {
         double *ts_w = const_cast<double *>(sm.ts);
         double2 *ds_w = const_cast<double2 *>(sm.ds);
-        for (int r = tid; r < p.stage_rows; r += THREADS) {
-            ts_w[r] = p.times[p.stage_begin + r];
-            ds_w[r] = p.data[p.stage_begin + r];
+        for (int r = tid; r < p.stage_rows + SMALL_STAGE_PAD; r += THREADS) {
+            const int src = p.stage_begin + (r < p.stage_rows ? r : p.stage_rows - 1);
+            ts_w[r] = p.times[src];
+            ds_w[r] = p.data[src];
         }
         sm.t_off = p.stage_begin;
     } else {
@@ -786,7 +869,7 @@ __global__ void __launch_bounds__(THREADS, 1) fit_small_kernel(const __grid_cons
     SmallAcc acc;
     acc.sdd = acc.res2 = acc.cn2 = 0.0;
     if (!p.eval_only) {
-        small_leaf<N, THREADS>(p, sm, L, tid, acc);
+        small_leaf<N, THREADS, STAGED>(p, sm, L, tid, acc);
         for (int s = 1; s < lpf; s <<= 1) {
             __syncwarp();
             small_tree_level<N, THREADS>(p, sm, L, tid, s, acc);

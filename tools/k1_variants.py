@@ -15,9 +15,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "tools", "_variants")
 
-VARIANTS = {
-    "base": [],
-    "absv1": ["-DQNMFIT_ABSORB_V1"],
+VARIANTS = {       # leaf-loop pipelining: H columns of the next block refilled after reflection c + S
+    "h0": ["-DQNMFIT_PIPE_H(N)=0"],
+    "h2": ["-DQNMFIT_PIPE_H(N)=((N)>=2?2:0)"],
+    "h3": ["-DQNMFIT_PIPE_H(N)=((N)>=3?3:0)"],
+    "h4": [],
+    "h8s0": ["-DQNMFIT_PIPE_H(N)=(N)", "-DQNMFIT_PIPE_S(N)=0"],
 }
 
 
@@ -35,7 +38,7 @@ def build():
         assert p.wait() == 0, name
 
 
-def run(steps=10):
+def run(steps=20):
     import numpy as np
     import torch
     import qnmfits_b200 as qf
@@ -49,7 +52,7 @@ def run(steps=10):
                                            wl.t0, T=wl.T, res=256)
     stream = torch.cuda.current_stream()
     results = {}
-    names = sys.argv[2:] or list(VARIANTS)
+    names = sys.argv[2:] or sorted(f[len('libqnmfit_'):-3] for f in os.listdir(OUT) if f.startswith('libqnmfit_') and f.endswith('.so'))
     for name in names:
         path = os.path.join(OUT, f"libqnmfit_{name}.so")
         if not os.path.isfile(path):
@@ -57,7 +60,7 @@ def run(steps=10):
         lib = _cabi.load_library(path)
         h = C.c_void_p()
         assert lib.qnmfit_create(0, C.byref(h)) == 0
-        for anchor in (64,):
+        for anchor in (0,):
             for uw in (1,):
                 sweep.batch.anchor_rows = anchor
                 sweep.batch.uniform_weights = uw
