@@ -123,6 +123,7 @@ static void run(const qnmfit_batch *b, int lpf, bool eval)
 }
 
 extern "C" int hostsim_sizeof_batch(void) { return (int)sizeof(qnmfit_batch); }
+extern "C" int hostsim_sizeof_peers(void) { return (int)sizeof(qnmfit_peers); }
 
 // All pointers in *b are HOST pointers here.
 extern "C" int hostsim_fit_small(const qnmfit_batch *b, int lpf, int eval)

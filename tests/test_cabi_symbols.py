@@ -27,6 +27,7 @@ def test_abi_version_and_struct_size():
     assert lib.qnmfit_abi_version() == _cabi.ABI_VERSION
     hs = C.CDLL(os.path.join(ROOT, "tests", "hostsim", "libqnmfit_hostsim.so"))
     assert hs.hostsim_sizeof_batch() == C.sizeof(_cabi.Batch)
+    assert hs.hostsim_sizeof_peers() == C.sizeof(_cabi.Peers)
 
 
 def test_create_fails_loudly_without_device():

@@ -100,3 +100,49 @@ def test_dynamic_spectrum_tables_and_no_cpu_fallback(qf):
 
 def test_flops_formula():
     assert abs(_cabi.flops_per_fit(1000, 8) - 770378.67) < 1.0
+
+
+def test_grid_plan_equals_the_two_separate_checks():
+    from qnmfits_b200._engine import grid_plan, nominal_step, uniform_weights
+    rng = np.random.default_rng(5)
+    uniform = np.arange(-500, 1501) * 0.1
+    jitter = uniform + rng.normal(scale=3e-13, size=uniform.size)     # recurrence ok, weights not uniform
+    rough = np.sort(uniform + rng.uniform(-0.03, 0.03, size=uniform.size))
+    for times in (uniform, jitter, rough, uniform[:2], np.array([0.0, 0.0, 0.0])):
+        for wmax in (0.5, 40.0):
+            dt, uw = grid_plan(times, wmax)
+            assert dt == nominal_step(times, wmax)
+            assert uw == (uniform_weights(times, dt) if dt > 0 else False)
+            assert grid_plan(times, wmax, np.diff(times)) == (dt, uw)
+    assert grid_plan(uniform, 2.0) == (grid_plan(uniform, 2.0)[0], True)
+    assert grid_plan(jitter, 2.0)[0] > 0 and grid_plan(jitter, 2.0)[1] is False
+    assert grid_plan(rough, 2.0) == (0.0, False)
+
+
+def test_memoised_tables_equal_fresh_tabulation(qf):
+    """The memoised grid axes / frequency tables / label lists return what a fresh provider computes."""
+    from qnmfits_b200 import qnmfits as api
+    from qnmfits_b200.qnm import qnm as Provider
+    modes = [(2, 2, n, 1) for n in range(8)] + [(2, 2, 0, 1, 2, 2, 0, 1), (2, 2, 0, -1)]
+    chi = np.linspace(0.59, 0.79, 17)
+    first = qf.qnm.constituent_table(modes, chi, with_max=True)
+    again = qf.qnm.constituent_table(modes, chi, with_max=True)
+    fresh = Provider().constituent_table(modes, chi, with_max=True)
+    for a, b in ((first, again), (first, fresh)):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+    assert first[2] == np.max(np.abs(first[0]))
+    assert not first[0].flags.writeable
+    w1 = qf.qnm.omega_list(modes, 0.69, 0.95)
+    w2 = qf.qnm.omega_list(modes, 0.69, 0.95)
+    w3 = Provider().omega_list(modes, 0.69, 0.95)
+    assert w1 == w2 == w3 and isinstance(w2, list)
+    idx = [(2, 2) + m for m in modes[:8]] + [(3, 2, 2, 2, 0, -1), (2, 1, 2, 2, 0, 1)]
+    m1 = qf.qnm.mu_list(idx, 0.69)
+    assert m1 == qf.qnm.mu_list(idx, 0.69) == Provider().mu_list(idx, 0.69)
+    assert m1[-1] == 0 and isinstance(m1[-1], int)          # reference qnm.py:336-337
+    # array-valued spins are not memoised as scalars and still work
+    wa = qf.qnm.omega_list(modes[:2], np.array([0.5, 0.69]), 0.95)
+    assert wa[0].shape == (2,) and wa[0][1] == w1[0]
+    arr, inv, inv_max = api._linspace(0.85, 1.05, 256)
+    assert np.array_equal(arr, np.linspace(0.85, 1.05, 256)) and np.array_equal(inv, 1.0 / arr)
+    assert inv_max == np.max(np.abs(inv)) and api._linspace(0.85, 1.05, 256)[0] is arr
