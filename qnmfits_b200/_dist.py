@@ -23,6 +23,36 @@ def world():
     return 0, 1
 
 
+_local_devices = None
+
+
+def use_devices(devices=None):
+    """Single-process multi-GPU: make the sweep functions (``mismatch_t0_array``,
+    ``mismatch_M_chi_grid``, ...) split their fits over these CUDA devices, driven from
+    this one process.  ``devices``: a list of device indices, ``"all"`` for every visible
+    GPU, or ``None`` to go back to the current device only.  Ignored while a
+    torch.distributed job is active (one process per GPU then)."""
+    global _local_devices
+    if devices is None:
+        _local_devices = None
+        return None
+    import torch
+    if isinstance(devices, str):
+        if devices != "all":
+            raise ValueError('devices must be a list of device indices, "all" or None')
+        devices = list(range(torch.cuda.device_count()))
+    devices = [int(d) for d in devices]
+    if not devices or len(set(devices)) != len(devices) or \
+            any(d < 0 or d >= torch.cuda.device_count() for d in devices):
+        raise ValueError(f"bad device list {devices} ({torch.cuda.device_count()} visible)")
+    _local_devices = devices
+    return devices
+
+
+def local_devices():
+    return _local_devices
+
+
 def shard_bounds(n_items, rank, world_size):
     """Contiguous slab [lo, hi) of rank and the common padded slab length."""
     per = -(-int(n_items) // int(world_size)) if n_items > 0 else 0

@@ -191,10 +191,8 @@ class Engine:
                    model_d=None, model_stride=0, uniform_weights=False,
                    n_times=None, series_stride=None, flagged_d=None, series_index_d=None,
                    omega_rows_d=None, coef_rows_d=None):
-        def p(t):
-            if t is None or isinstance(t, int):
-                return t
-            return t.data_ptr()
+        def p(t):                              # device pointer: int, None, or a torch tensor
+            return t if t is None or type(t) is int else t.data_ptr()
         if n_times is None:
             n_times = int(times_d.numel())
         if series_stride is None:

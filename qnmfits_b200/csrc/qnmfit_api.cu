@@ -447,6 +447,8 @@ extern "C" int qnmfit_h2d(qnmfit_ctx *ctx, void *dst_dev, const void *src_host, 
     if (bytes == 0) return 0;
     if (!dst_dev || !src_host) return fail(ctx, QNMFIT_E_NULL, "qnmfit_h2d: NULL pointer");
     cudaError_t e;
+    // the event lives on the ctx's device; one process may drive several devices
+    if ((e = cudaSetDevice(ctx->device)) != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
     if (!ctx->h2d_event && (e = cudaEventCreateWithFlags(&ctx->h2d_event, cudaEventDisableTiming)) != cudaSuccess)
         return cuda_fail(ctx, e, "cudaEventCreate");
     if ((e = cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream)) != cudaSuccess)

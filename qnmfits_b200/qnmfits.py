@@ -365,11 +365,17 @@ class _Sweep:
     """
 
     def __init__(self, times, rows, *, n_fits, n_modes, windows, t0s, freq_arrays, freq_scalars,
-                 coef, coef_per_chi, wmax, steps=None):
-        eng = self.eng = get_engine()
+                 coef, coef_per_chi, wmax, steps=None, eng=None, slab=None):
         self.n_fits = n_fits
-        self.rank, self.ws = _dist.world()
-        lo, hi, per = _dist.shard_bounds(n_fits, self.rank, self.ws)
+        if slab is None:
+            eng = self.eng = get_engine()
+            self.rank, self.ws = _dist.world()
+            lo, hi, per = _dist.shard_bounds(n_fits, self.rank, self.ws)
+        else:                                        # one device of a single-process device group
+            self.eng = eng
+            self.rank, self.ws = 0, 1
+            lo, hi = slab
+            per = hi - lo
         self.lo, self.hi, self.per = lo, hi, per
         n_local = hi - lo
         L, K_tot = rows.shape
@@ -407,14 +413,14 @@ class _Sweep:
         out_bytes = 0
         if self.ws == 1:
             host.append(_ZERO)                       # the counter of flagged fits, zeroed by the upload
-            out_bytes = 8 * n_fits
+            out_bytes = 8 * n_local
         self._inputs, ptrs, out = eng.upload_packed(host, out_bytes=out_bytes, stream=self.stream)
         kw = dict(freq_scalars)
         kw.update({k: ptr for k, ptr in zip(names, ptrs[7:])})
 
         if self.ws == 1:
             mismatch_d, flagged_d = out, out - 8
-            self._result = out - 8                   # [counter | mismatch[n_fits]]
+            self._result = out - 8                   # [counter | mismatch[n_local]]
             self._fresh = True                       # counter still zero from the upload
         elif self.window is None:
             import torch
@@ -470,7 +476,7 @@ class _Sweep:
         """(mismatch of every fit as float64[n_fits], number of flagged fits), on the host."""
         per = max(self.per, 1)
         if self.ws == 1:
-            out = self.eng.download_raw(self._result, 8 * (1 + self.n_fits), stream=self.stream)
+            out = self.eng.download_raw(self._result, 8 * (1 + self.hi - self.lo), stream=self.stream)
             return out[1:], int(out[0])
         if self.window is not None:
             out = self.eng.download_raw(self.window.result_ptr(self.slot),
@@ -484,6 +490,52 @@ class _Sweep:
             return out[_cabi.MAX_PEERS:], int(counts.sum())
         full = self.eng.download(self.gathered).reshape(self.ws, per + 1)
         return full[:, :per].reshape(-1)[:self.n_fits].copy(), int(full[:, per].sum())
+
+
+class _DeviceGroupSweep:
+    """One process driving several GPUs (``qnmfits_b200.use_devices``): the flat fit index
+    is split into one slab per device, every device gets its own upload and launch on its
+    own stream, and the host concatenates the slabs — the call stays a plain function call
+    from a notebook (no torchrun).  Same interface as ``_Sweep``."""
+
+    def __init__(self, devices, args, kwargs):
+        import torch
+        self.n_fits = kwargs['n_fits']
+        self._restore = torch.cuda.current_device()
+        self.parts = []
+        n_dev = len(devices)
+        for i, dev in enumerate(devices):
+            lo, hi, _ = _dist.shard_bounds(self.n_fits, i, n_dev)
+            if hi > lo:
+                self.parts.append(_Sweep(*args, eng=get_engine(dev), slab=(lo, hi), **kwargs))
+        torch.cuda.set_device(self._restore)
+        self.rows_max = self.parts[0].rows_max
+        self.window = None
+
+    def launch_kernel(self):
+        import torch
+        for part in self.parts:                      # asynchronous: the devices run concurrently
+            part.launch_kernel()
+        torch.cuda.set_device(self._restore)         # the C launches select their own device
+
+    def gather(self):
+        pass
+
+    def launch(self):
+        self.launch_kernel()
+
+    def fetch(self):
+        results = [part.fetch() for part in self.parts]
+        return np.concatenate([r[0] for r in results]), sum(r[1] for r in results)
+
+
+def _make_sweep(*args, **kwargs):
+    """``_Sweep`` on this process's device, or a device group when ``use_devices`` named
+    several GPUs and no torch.distributed job is active."""
+    devices = _dist.local_devices()
+    if devices is not None and len(devices) > 1 and _dist.world()[1] == 1 and kwargs['n_fits'] > 0:
+        return _DeviceGroupSweep(devices, args, kwargs)
+    return _Sweep(*args, **kwargs)
 
 
 _ZERO = np.zeros(2, np.float64)   # 16 bytes: the result region behind it stays contiguous
@@ -543,7 +595,7 @@ def _prepare_t0_sweep(times, data, modes, Mf, chif, t0_array, t0_method, T_array
         mu_lists = _mu_lists(keys, modes, chif)
         coef = np.array([[complex(v) for v in row] for row in mu_lists],
                         dtype=complex).reshape(1, len(keys), len(modes))
-    return _Sweep(
+    return _make_sweep(
         np.asarray(times, dtype=float), rows, n_fits=n, n_modes=len(modes),
         windows=(begin, end), t0s=t0_array,
         freq_arrays=dict(omega_d=(frequencies.reshape(1, -1), np.complex128)),
@@ -650,7 +702,8 @@ def _prepare_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0, t0_metho
     table, mode_ptr, table_max = qnm.constituent_table(modes, chif_array, with_max=True)
     if keys is None:
         df = _delta_factor(delta, len(modes))
-        df = np.broadcast_to(np.asarray(df, dtype=float), (len(modes),)).copy()
+        df = np.full(len(modes), df, dtype=float) if np.ndim(df) == 0 else \
+            np.broadcast_to(np.asarray(df, dtype=float), (len(modes),)).copy()
         coef = None
     else:
         for mode in modes:
@@ -666,7 +719,7 @@ def _prepare_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0, t0_metho
         inv_Mf_d=(inv_Mf, np.float64))
     if df is not None:
         freq_arrays['delta_factor_d'] = (df, np.float64)
-    sweep = _Sweep(
+    sweep = _make_sweep(
         np.asarray(times, dtype=float), rows, n_fits=n, n_modes=len(modes),
         windows=window, t0s=float(t0), freq_arrays=freq_arrays,
         freq_scalars=dict(n_chi=len(chif_array), n_mf=len(Mf_array),
@@ -1042,6 +1095,6 @@ def _prepare_dynamic_t0_sweep(times, data, modes, Mf, chif, t0_array, t0_method,
     freq_arrays = dict(omega_rows_d=(omega_rows, np.complex128))
     if coef_rows is not None:
         freq_arrays['coef_rows_d'] = (coef_rows, np.complex128)
-    return _Sweep(np.asarray(times, dtype=float), rows, n_fits=n, n_modes=len(modes), windows=(begin, end),
+    return _make_sweep(np.asarray(times, dtype=float), rows, n_fits=n, n_modes=len(modes), windows=(begin, end),
                   t0s=t0_array, freq_arrays=freq_arrays, freq_scalars={}, coef=None, coef_per_chi=False,
                   wmax=float(np.max(np.abs(omega_rows))))

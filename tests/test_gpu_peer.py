@@ -87,3 +87,32 @@ def test_fused_exchange_two_gpus_bit_identical(tmp_path):
             assert np.all(np.isfinite(one))
             assert np.array_equal(got["fused_" + name], got["nccl_" + name]), (rank, name)
             assert np.max(np.abs(got["fused_" + name] - one)) < 1e-12, (rank, name)
+
+
+def test_single_process_device_group_matches_one_device():
+    """``use_devices``: one process drives two GPUs, the host concatenates the slabs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    import qnmfits_b200 as qf
+    from qnmfits_b200 import workloads
+    workloads.use_synthetic_tables()
+    wl3, wl2, wl4 = workloads.config3(res=8), workloads.config2(), cases.cfg4_small()
+    torch.cuda.set_device(0)
+    one = _sweeps(qf, wl3, wl2, wl4)
+    try:
+        assert qf.use_devices("all")[:2] == [0, 1]
+        qf.use_devices([1, 0])
+        two = _sweeps(qf, wl3, wl2, wl4)
+        assert torch.cuda.current_device() == 0
+    finally:
+        qf.use_devices(None)
+    again = _sweeps(qf, wl3, wl2, wl4)
+    for name, ref in one.items():
+        assert two[name].shape == ref.shape and np.all(np.isfinite(two[name]))
+        assert np.max(np.abs(two[name] - ref)) < 1e-12, name
+        assert np.array_equal(again[name], ref), name
+    with pytest.raises(ValueError):
+        qf.use_devices([0, 0])
