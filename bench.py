@@ -132,7 +132,7 @@ def run_reference_arm(args):
 class ClockSampler:
     """Samples SM clock and throttle reasons of one GPU via NVML while running."""
 
-    def __init__(self, index, period=0.05):
+    def __init__(self, index, period=0.004):
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
         self.max_mhz = None

@@ -116,6 +116,8 @@ class Engine:
     # every result in ONE device->host copy, issued through the thin C wrappers
     # (qnmfit_h2d / qnmfit_d2h): a torch copy_ costs ~10 us of dispatch each.
 
+    DIRECT_BYTES = 1 << 22   # arrays this large are uploaded straight from their own memory
+
     def _pinned(self, name, nbytes):
         """A cached pinned host buffer of at least nbytes: (uint8 numpy view, address)."""
         buf = self._pinned_bufs.get(name)
@@ -134,27 +136,37 @@ class Engine:
         (uninitialised) room for results behind the last array, 16-byte aligned.  Returns
         (device_buffer, [device pointer or None, ...], pointer of the result region).
         The staging buffer is reused by the next call, which first waits until the
-        previous copy has left it (``qnmfit_h2d_wait``).
+        previous copy has left it (``qnmfit_h2d_wait``).  Arrays of ``DIRECT_BYTES`` or
+        more are not staged: they are copied from their own (pageable) memory.
         """
-        offsets, total = [], 0
-        for a in arrays:
-            if a is None:
-                offsets.append(None)
-                continue
-            total = (total + 255) // 256 * 256
-            offsets.append(total)
-            total += a.nbytes
-        self.ctx.h2d_wait()
-        stage_np, stage_ptr = self._pinned("upload", max(total, 8))
-        for a, off in zip(arrays, offsets):
-            if a is not None and a.nbytes:
-                stage_np[off:off + a.nbytes] = a.reshape(-1).view(np.uint8)
+        # Arrays of several MB (a whole catalogue of waveforms) go straight from their own
+        # memory, behind the staged ones: staging them would cost a second host copy and a
+        # pinned buffer of that size.
+        offsets, total = [None] * len(arrays), 0
+        big = [i for i, a in enumerate(arrays) if a is not None and a.nbytes >= self.DIRECT_BYTES]
+        for group in ([i for i in range(len(arrays)) if i not in big], big):
+            for i in group:
+                if arrays[i] is None:
+                    continue
+                total = (total + 255) // 256 * 256
+                offsets[i] = total
+                total += arrays[i].nbytes
+            if group is not big:
+                small_end = total
+        stream = self.stream() if stream is None else stream
         out_off = (total + 15) // 16 * 16
         dev = self.torch.empty(max(out_off + int(out_bytes), 16), dtype=self.torch.uint8, device=self.device)
         base = dev.data_ptr()
-        if total:
-            self.ctx.h2d(base, stage_ptr, total, self.stream() if stream is None else stream)
-        self.h2d_bytes += total
+        if small_end:
+            self.ctx.h2d_wait()
+            stage_np, stage_ptr = self._pinned("upload", small_end)
+            for i, (a, off) in enumerate(zip(arrays, offsets)):
+                if a is not None and a.nbytes and i not in big:
+                    stage_np[off:off + a.nbytes] = a.reshape(-1).view(np.uint8)
+            self.ctx.h2d(base, stage_ptr, small_end, stream)
+        for i in big:                                # pageable source: returns once the data has left it
+            self.ctx.h2d(base + offsets[i], arrays[i].ctypes.data, arrays[i].nbytes, stream)
+        self.h2d_bytes += sum(a.nbytes for a in arrays if a is not None)
         return dev, [None if off is None else base + off for off in offsets], base + out_off
 
     def download_raw(self, ptr, nbytes, dtype=np.float64, stream=None):
