@@ -97,6 +97,8 @@ class Engine:
         self.h2d_bytes += a.nbytes
         if a.size == 0:
             return torch.empty(a.shape, dtype=torch.from_numpy(a).dtype, device=self.device)
+        if not a.flags.writeable:                   # memoised tables are read-only; torch wants writable
+            a = a.copy()
         return torch.from_numpy(a).to(self.device)
 
     def empty(self, shape, dtype):

@@ -47,18 +47,29 @@ def set_table_provider(modes_cache):
         inst._reset_sequences()
 
 
+_warned_fallback = False
+
+
 def _default_provider():
+    """The installed table source: what ``set_table_provider`` installed, else the ``qnm``
+    PyPI package (what the reference uses, qnm.py:134), else this package's own Leaver
+    solver (``qnmfits_b200.kerr``) with a one-time notice."""
+    global _warned_fallback
     if _table_provider is not None:
         return _table_provider
     try:
         import qnm as qnm_loader  # the PyPI package (Stein 2019)
-    except ImportError as exc:  # pragma: no cover - depends on environment
-        raise ImportError(
-            "The 'qnm' package (Kerr QNM tables) is not installed. Install it, or "
-            "call qnmfits_b200.set_table_provider(modes_cache) with a callable "
-            "returning objects with .a, .omega, .C (e.g. "
-            "qnmfits_b200.synthetic.modes_cache for benchmarks)."
-        ) from exc
+    except ImportError:
+        from . import kerr
+        if not _warned_fallback:
+            import warnings
+            warnings.warn(
+                "The 'qnm' package (Kerr QNM tables) is not installed: using the built-in Leaver "
+                "solver qnmfits_b200.kerr (same algorithm; frequencies agree to ~1e-9, overtones "
+                "n >= 8 of l = 2 unavailable).  Call qnmfits_b200.set_table_provider(...) to "
+                "install another source.", RuntimeWarning, stacklevel=3)
+            _warned_fallback = True
+        return kerr.modes_cache
     return qnm_loader.modes_cache
 
 

@@ -24,6 +24,12 @@ def use_synthetic_tables():
     set_table_provider(synthetic.modes_cache)
 
 
+def use_kerr_tables():
+    """Serve ``qnm.modes_cache`` from the built-in Leaver solver (``qnmfits_b200.kerr``)."""
+    from . import kerr
+    set_table_provider(kerr.modes_cache)
+
+
 def synthetic_modes_cache():
     return synthetic.modes_cache
 

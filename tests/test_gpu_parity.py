@@ -465,3 +465,41 @@ def test_dynamic_fits_vs_reference_golden(qf, eng, golden):
     # superset: coefficients that vanish identically (m' != m) — the reference cannot reshape them
     fit = qf.dynamic_multimode_ringdown_fit(wl4.times, wl4.data, cases.MM_MODES, Mf4, chi4, 5.0, T=80)
     assert np.isfinite(fit["mismatch"]) and fit["mismatch"] < 1e-3
+
+
+def test_real_kerr_tables_device_vs_oracle(qf, eng):
+    """The built-in Leaver provider (qnmfits_b200/kerr.py) through the whole device path:
+    single fit, Mf-chi grid and a multimode fit against the oracle fed by the same tables
+    (real Kerr numbers: other conditioning than the synthetic ladder)."""
+    from qnmfits_b200 import kerr
+    tables = orc.OracleTables(kerr.modes_cache)
+    wl = workloads.config1()
+    modes = [(2, 2, n, 1) for n in range(8)]
+    try:
+        workloads.use_kerr_tables()
+        w = np.array(qf.qnm.omega_list(modes, 0.69, 0.95))
+        assert np.array_equal(w, np.array(tables.omega_list(modes, 0.69, 0.95)))
+        rng = np.random.default_rng(4)
+        C = rng.normal(size=8) + 1j * rng.normal(size=8)
+        data = np.where(wl.times >= 0, (C[None, :] * np.exp(-1j * w[None, :] * wl.times[:, None])).sum(axis=1), 0)
+        data = data + 1e-6 * (rng.normal(size=data.size) + 1j * rng.normal(size=data.size))
+        fit = qf.ringdown_fit(wl.times, data, modes, 0.95, 0.69, 0.0)
+        ref = orc.ringdown_fit(tables, wl.times, data, modes, 0.95, 0.69, 0.0)
+        assert np.array_equal(fit["frequencies"], ref["frequencies"])
+        assert int(fit["rank"]) == int(ref["rank"]) == 8
+        err = np.max(np.abs(fit["C"] - ref["C"])) / np.max(np.abs(ref["C"]))
+        assert err < cases.amp_tol(ref["s"]), (err, ref["s"][0] / ref["s"][-1])
+        assert abs(fit["mismatch"] - ref["mismatch"]) < MM_TOL
+        grid = qf.mismatch_M_chi_grid(wl.times, data, modes, (0.9, 1.0), (0.6, 0.78), 0.0, res=6)
+        gref = orc.mismatch_M_chi_grid(tables, wl.times, data, modes, (0.9, 1.0), (0.6, 0.78), 0.0, res=6)
+        assert np.max(np.abs(grid - gref)) < MM_TOL
+        sph = [(2, 2), (3, 2), (4, 2)]
+        mm_modes = [(2, 2, 0, 1), (2, 2, 1, 1), (3, 2, 0, 1), (2, 2, 0, -1), (4, 2, 0, 1)]
+        dd = {lm: data * (0.3 ** i) * np.exp(0.4j * i) for i, lm in enumerate(sph)}
+        mfit = qf.multimode_ringdown_fit(wl.times, dd, mm_modes, 0.95, 0.69, 0.0, spherical_modes=sph)
+        mref = orc.multimode_ringdown_fit(tables, wl.times, dd, mm_modes, 0.95, 0.69, 0.0, spherical_modes=sph)
+        assert abs(mfit["mismatch"] - mref["mismatch"]) < MM_TOL
+        scale = np.max(np.abs(mref["C"]))
+        assert np.max(np.abs(mfit["C"] - mref["C"])) < 1e-7 * scale
+    finally:
+        workloads.use_synthetic_tables()

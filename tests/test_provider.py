@@ -74,12 +74,23 @@ def test_factored_frequency_formation_is_bit_exact(qf, golden):
             assert np.array_equal(got, want), (Mf, chi)
 
 
-def test_provider_required(qf):
+def test_default_provider_falls_back_to_the_builtin_leaver_solver(qf):
+    """Without the `qnm` PyPI package the provider serves Kerr tables from qnmfits_b200.kerr
+    (with a notice) instead of failing: omega_220(0.7) is the value the reference's notebook
+    prints."""
     from qnmfits_b200.qnm import set_table_provider, qnm as qnm_class
     from qnmfits_b200 import synthetic
+    try:
+        import qnm as _pypi  # noqa: F401
+        pytest.skip("the qnm package is installed: the fallback is not reached")
+    except ImportError:
+        pass
     set_table_provider(None)
     try:
-        with pytest.raises(ImportError):
-            qnm_class().omega(2, 2, 0, 1, 0.5)
+        import qnmfits_b200.qnm as mod
+        mod._warned_fallback = False
+        with pytest.warns(RuntimeWarning, match="built-in Leaver"):
+            w = qnm_class().omega(2, 2, 0, 1, 0.7)
+        assert abs(w - (0.53260024 - 0.08079287j)) < 1e-8
     finally:
         set_table_provider(synthetic.modes_cache)
