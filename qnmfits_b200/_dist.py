@@ -190,6 +190,9 @@ def peer_window(eng, n_items):
             or int(os.environ.get("LOCAL_WORLD_SIZE", ws)) != ws:
         return None
     win = _windows.get(eng.device_index)
+    if win is not None and (win.rank, win.ws) != (rank, ws):
+        del _windows[eng.device_index]       # another process group than the one it was built for
+        win = None
     if win is not None and win.capacity >= n_items:
         return win
     if win is not None:
