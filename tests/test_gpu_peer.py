@@ -116,3 +116,50 @@ def test_single_process_device_group_matches_one_device():
         assert np.array_equal(again[name], ref), name
     with pytest.raises(ValueError):
         qf.use_devices([0, 0])
+
+
+def _late_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_WORLD_SIZE=str(world),
+                      QNMFITS_B200_PEER_TIMEOUT_S="2")
+    import time
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import qnmfits_b200 as qf
+    from qnmfits_b200 import workloads
+    workloads.use_synthetic_tables()
+    wl = workloads.config3(res=8)
+    args = (wl.times, wl.data, wl.modes, wl.Mf_minmax, wl.chif_minmax, wl.t0)
+    first = qf.mismatch_M_chi_grid(*args, T=wl.T, res=12)
+    outcome = "ok"
+    if rank == 1:
+        time.sleep(6.0)                       # rank 0 gives up on this rank's slab after 2 s
+    t = time.time()
+    try:
+        second = qf.mismatch_M_chi_grid(*args, T=wl.T, res=12)
+        assert np.array_equal(second, first)
+    except RuntimeError as exc:
+        outcome = f"raised after {time.time() - t:.1f} s: {exc}"
+    dist.barrier()                            # the late rank catches up
+    third = qf.mismatch_M_chi_grid(*args, T=wl.T, res=12)     # both ranks again in step
+    assert np.array_equal(third, first)
+    with open(os.path.join(out_dir, f"late{rank}.txt"), "w") as f:
+        f.write(outcome)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_missing_peer_times_out_instead_of_hanging(tmp_path):
+    """A rank that is late by more than QNMFITS_B200_PEER_TIMEOUT_S makes the waiting rank
+    raise (its kernel leaves a NaN marker) — never a hang; the next sweep is in step again."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_late_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    late0 = open(os.path.join(str(tmp_path), "late0.txt")).read()
+    late1 = open(os.path.join(str(tmp_path), "late1.txt")).read()
+    assert late0.startswith("raised after") and "did not deliver" in late0, late0
+    assert late1 == "ok", late1
