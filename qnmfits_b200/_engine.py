@@ -47,16 +47,26 @@ def grid_plan(times, wmax, steps=None):
     by-products of the factorisation instead of a weighted second pass (changes it by
     < 1e-11).  ``steps`` = ``np.diff(times)`` if the caller has it already.
     """
+    return grid_decision(*step_stats(times, steps), wmax)
+
+
+def step_stats(times, steps=None):
+    """(dt, dev) of a window: mean step and largest deviation of a step from it, or
+    (0.0, inf) when the window is too short or not increasing."""
     times = np.asarray(times, dtype=float)
     if times.size < 3:
-        return 0.0, False
+        return 0.0, np.inf
     if steps is None:
         steps = np.diff(times)
     dt = float((times[-1] - times[0]) / (times.size - 1))
     if not np.isfinite(dt) or dt <= 0.0:
-        return 0.0, False
-    dev = float(np.max(np.abs(steps - dt)))
-    if not dev * max(float(wmax), 1.0) <= 4e-10:
+        return 0.0, np.inf
+    return dt, float(np.max(np.abs(steps - dt)))
+
+
+def grid_decision(dt, dev, wmax):
+    """``grid_plan``'s two criteria from the window's step statistics."""
+    if not dt > 0.0 or not dev * max(float(wmax), 1.0) <= 4e-10:
         return 0.0, False
     return dt, bool(dev <= 1e-11 * dt)
 

@@ -25,7 +25,7 @@ Deliberate supersets of the reference (documented in DESIGN.md):
 import numpy as np
 
 from . import _cabi, _dist
-from ._engine import get_engine, grid_plan, nominal_step, uniform_weights
+from ._engine import get_engine, grid_decision, grid_plan, nominal_step, step_stats, uniform_weights
 from .qnm import qnm as _qnm_class
 
 # Module-level provider *instance* that shadows the class, exactly like the
@@ -365,7 +365,7 @@ class _Sweep:
     """
 
     def __init__(self, times, rows, *, n_fits, n_modes, windows, t0s, freq_arrays, freq_scalars,
-                 coef, coef_per_chi, wmax, steps=None, eng=None, slab=None):
+                 coef, coef_per_chi, wmax, steps=None, stats=None, eng=None, slab=None):
         self.n_fits = n_fits
         if slab is None:
             eng = self.eng = get_engine()
@@ -428,12 +428,10 @@ class _Sweep:
             mismatch_d, flagged_d = self.out_d, self.out_d.data_ptr() + 8 * max(per, 1)
         else:
             mismatch_d, flagged_d = 0, None          # set per launch (epoch parity slot)
-        window_times = times[rb_all:re_all]
-        if steps is None:
-            steps = np.diff(window_times)
-        else:
-            steps = steps[rb_all:re_all - 1]
-        dt, uniform = grid_plan(window_times, wmax, steps)
+        if stats is None:                            # (mean step, largest deviation) of the window
+            window_times = times[rb_all:re_all]
+            stats = step_stats(window_times, None if steps is None else steps[rb_all:re_all - 1])
+        dt, uniform = grid_decision(stats[0], stats[1], wmax)
         if n_local > 0 or self.window is not None:
             self.batch = eng.make_batch(
                 times_d=ptrs[0], data_d=ptrs[1], n_times=K_tot, series_stride=K_tot,
@@ -677,6 +675,31 @@ def _linspace(lo, hi, res):
     return hit
 
 
+_time_axis_memo = {}
+
+
+def _time_axis(times, t0, T, t0_method):
+    """(ascending?, window rows, step statistics of the window) of a time array, memoised
+    on (t0, T, t0_method, len) and validated against a stored COPY of the array (one 16 KB
+    comparison instead of three passes over it): repeated sweeps over the same samples —
+    other data, other modes, other grids — skip the recomputation."""
+    key = (float(t0), float(T), t0_method, times.shape[0])
+    hit = _time_axis_memo.get(key)
+    if hit is not None and np.array_equal(hit[0], times):
+        return hit[1:]
+    steps = np.diff(times)
+    ascending = not (steps.size and steps.min() < 0)
+    window, stats = (0, 0), (0.0, np.inf)
+    if ascending:
+        window = _window_rows(times, t0, T, t0_method)
+        if window[1] > window[0]:
+            stats = step_stats(times[window[0]:window[1]], steps[window[0]:window[1] - 1])
+    if len(_time_axis_memo) > 64:
+        _time_axis_memo.clear()
+    _time_axis_memo[key] = (np.array(times, dtype=float, copy=True), ascending, window, stats)
+    return ascending, window, stats
+
+
 def _prepare_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0, t0_method='geq',
                         T=100, res=50, spherical_modes=None, delta=0.0):
     """Host tabulation + upload for the grid sweep; returns (sweep, shape)."""
@@ -688,10 +711,12 @@ def _prepare_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0, t0_metho
     n = shape[0] * shape[1]
     if n == 0:
         return None, shape
-    steps = np.diff(times)
-    if steps.size and steps.min() < 0:
+    if t0_method not in ('geq', 'closest'):
+        raise ValueError(
+            "Requested t0_method is not valid. Please choose between 'geq' and 'closest'")
+    ascending, window, stats = _time_axis(times, t0, T, t0_method)
+    if not ascending:
         raise ValueError("times must be ascending")
-    window = _window_rows(times, t0, T, t0_method)
     if window[1] <= window[0]:
         raise ValueError("the analysis window is empty")
     rows, keys = _series_rows(data, spherical_modes)
@@ -724,7 +749,7 @@ def _prepare_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0, t0_metho
         windows=window, t0s=float(t0), freq_arrays=freq_arrays,
         freq_scalars=dict(n_chi=len(chif_array), n_mf=len(Mf_array),
                           n_constituents=table.shape[1]),
-        coef=coef, coef_per_chi=True, wmax=wmax, steps=steps)
+        coef=coef, coef_per_chi=True, wmax=wmax, stats=stats)
     return sweep, shape
 
 
