@@ -14,7 +14,10 @@ restatement against those fixtures on every run and against the live reference w
 published known answers are the notebook values G1/G2, which
 need the real Kerr tables (``qnm`` PyPI package, unpinned in the reference's
 pyproject.toml:25) that are not installable offline.  G1's "mismatch 0, C = 1-1j"
-is table-independent and is tested; G2's numeric value is not.
+is table-independent and is tested; G2's numeric value, omega_220(0.7) =
+0.53260024-0.08079287i, is reproduced by the from-scratch Kerr provider
+``qnmfits_b200/kerr.py`` (``tests/test_kerr_provider.py``), which can feed this oracle
+like any other ``modes_cache``.
 
 The least-squares solve itself is third-party in the reference too:
 ``numpy.linalg.lstsq(a, b, rcond=None)`` -> LAPACK zgelsd (numpy unpinned in the
