@@ -39,6 +39,11 @@ def _sweeps(qf, wl3, wl2, wl4):
                                                      wl4.t0_array))
     out["grid_again"] = qf.mismatch_M_chi_grid(wl3.times, wl3.data, wl3.modes, wl3.Mf_minmax,
                                                wl3.chif_minmax, wl3.t0, T=wl3.T, res=21)
+    # more results than the first peer window holds (2^20): the window is re-created collectively
+    out["big"] = qf.mismatch_M_chi_grid(wl3.times, wl3.data, wl3.modes[:2], wl3.Mf_minmax,
+                                        wl3.chif_minmax, wl3.t0, T=30, res=1030)
+    out["after_big"] = qf.mismatch_M_chi_grid(wl3.times, wl3.data, wl3.modes, wl3.Mf_minmax,
+                                              wl3.chif_minmax, wl3.t0, T=wl3.T, res=9)
     return out
 
 
@@ -58,12 +63,13 @@ def _worker(rank, world, port, out_dir):
 
     fused = _sweeps(qf, wl3, wl2, wl4)
     assert _dist._windows, "the fused exchange was not used"
-    epochs = next(iter(_dist._windows.values())).epoch
+    win = next(iter(_dist._windows.values()))
+    epochs, capacity = win.epoch, win.capacity
     os.environ["QNMFITS_B200_PEER"] = "0"
     nccl = _sweeps(qf, wl3, wl2, wl4)
     os.environ["QNMFITS_B200_NO_SHARD"] = "1"
     single = _sweeps(qf, wl3, wl2, wl4)
-    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), epochs=epochs,
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), epochs=epochs, capacity=capacity,
              **{f"fused_{k}": v for k, v in fused.items()},
              **{f"nccl_{k}": v for k, v in nccl.items()},
              **{f"single_{k}": v for k, v in single.items()})
@@ -79,9 +85,10 @@ def test_fused_exchange_two_gpus_bit_identical(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     for rank in range(2):
         got = np.load(os.path.join(str(tmp_path), f"rank{rank}.npz"))
-        assert int(got["epochs"]) == 7          # one exchange per sweep call
+        assert int(got["capacity"]) == 1 << 21  # grown once, for the 1030 x 1030 grid
+        assert int(got["epochs"]) == 2          # ... and the new window counts its own exchanges
         names = [k[len("single_"):] for k in got.files if k.startswith("single_")]
-        assert len(names) == 7
+        assert len(names) == 9
         for name in names:
             one = got["single_" + name]
             assert np.all(np.isfinite(one))
