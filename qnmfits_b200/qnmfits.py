@@ -391,6 +391,7 @@ class _Sweep:
             re = np.ascontiguousarray(windows[1][lo:hi], dtype=np.int32)
         if re_all <= rb_all:
             raise ValueError("the analysis window is empty")
+        self._row_begin, self._row_end = rb, re     # host copies (repair of rank-deficient fits)
         if np.ndim(t0s) == 0:
             t0_arr, t0_all = None, float(t0s)
         else:
@@ -471,11 +472,18 @@ class _Sweep:
         self.gather()
 
     def fetch(self):
-        """(mismatch of every fit as float64[n_fits], number of flagged fits), on the host."""
+        """(mismatch of every fit as float64[n_fits], number of fits still flagged), on the host.
+
+        Fits the device flagged as numerically rank deficient are repaired first
+        (``_repair_rank_deficient``), so what is left in the count are fits numpy could not
+        have solved either (underdetermined, non-finite)."""
         per = max(self.per, 1)
         if self.ws == 1:
             out = self.eng.download_raw(self._result, 8 * (1 + self.hi - self.lo), stream=self.stream)
-            return out[1:], int(out[0])
+            mm, flagged = out[1:], int(out[0])
+            if flagged:
+                flagged = self._repair_rank_deficient(mm)
+            return mm, flagged
         if self.window is not None:
             out = self.eng.download_raw(self.window.result_ptr(self.slot),
                                         8 * (_cabi.MAX_PEERS + self.n_fits), stream=self.stream)
@@ -485,9 +493,74 @@ class _Sweep:
                 raise RuntimeError(
                     f"qnmfits_b200: rank(s) {late} did not deliver their slab of the sweep within "
                     "QNMFITS_B200_PEER_TIMEOUT_S; every rank must make the same sweep calls")
-            return out[_cabi.MAX_PEERS:], int(counts.sum())
-        full = self.eng.download(self.gathered).reshape(self.ws, per + 1)
-        return full[:, :per].reshape(-1)[:self.n_fits].copy(), int(full[:, per].sum())
+            mm, flagged = out[_cabi.MAX_PEERS:], int(counts.sum())
+        else:
+            full = self.eng.download(self.gathered).reshape(self.ws, per + 1)
+            mm, flagged = full[:, :per].reshape(-1)[:self.n_fits].copy(), int(full[:, per].sum())
+        if flagged:
+            # every rank saw the same total, so every rank takes this (rare) branch: repair
+            # the own slab, then exchange the repaired slabs and the remaining counts
+            import torch
+            import torch.distributed as dist
+            left = self._repair_rank_deficient(mm[self.lo:self.hi]) if self.hi > self.lo else 0
+            slab = torch.zeros(per + 1, dtype=torch.float64, device=self.eng.device)
+            slab[:self.hi - self.lo] = torch.from_numpy(np.ascontiguousarray(mm[self.lo:self.hi])).to(self.eng.device)
+            slab[per] = float(left)
+            full = self.eng.download(_dist.all_gather_slabs(slab, slab.numel() * self.ws)).reshape(self.ws, per + 1)
+            mm, flagged = full[:, :per].reshape(-1)[:self.n_fits].copy(), int(full[:, per].sum())
+        return mm, flagged
+
+    def _repair_rank_deficient(self, mm):
+        """numpy.linalg.lstsq truncates singular values below ``eps * max(M, N) * s_max``
+        (numpy/linalg/_linalg.py:2553) and returns the minimum-norm amplitudes; the kernels
+        return the basic QR solution and flag such fits (late start times with many overtones,
+        duplicated labels).  Rare path: refit this slab with the triangular factor exported,
+        complete the minimum-norm solution of every flagged fit on the host
+        (``_minimum_norm_from_factor``, as ``ringdown_fit`` does for a single fit), re-evaluate
+        model and mismatch of those fits on the device and patch ``mm`` (the slab's
+        mismatches) in place.  Returns the number of flagged fits that are NOT of this kind."""
+        import torch
+        eng, b0 = self.eng, self.batch
+        n_local, N, L = self.hi - self.lo, b0.n_modes, b0.n_series
+        left = 0
+        chunk = max(1, min(n_local, (1 << 28) // (16 * N * (N + 1))))
+        for a in range(0, n_local, chunk):
+            nb = min(n_local, a + chunk) - a
+            R_d = torch.empty((nb, N, N + 1), dtype=torch.complex128, device=eng.device)
+            C_d = torch.empty((nb, N), dtype=torch.complex128, device=eng.device)
+            st_d = torch.zeros(nb, dtype=torch.int32, device=eng.device)
+            mm_d = torch.empty(nb, dtype=torch.float64, device=eng.device)
+            b = type(b0).from_buffer_copy(b0)
+            b.n_fits, b.first_fit = nb, b0.first_fit + a
+            for name, width in (("row_begin", 4), ("row_end", 4), ("t0", 8), ("coef_index", 4), ("chi_index", 4),
+                                ("mf_index", 4), ("series_index", 4)):
+                ptr = getattr(b0, name)
+                if ptr:
+                    setattr(b, name, ptr + width * a)
+            if b0.omega and not b0.omega_shared:
+                b.omega = b0.omega + 16 * N * a
+            b.mismatch, b.flagged_count = mm_d.data_ptr(), None
+            b.R, b.C, b.status = R_d.data_ptr(), C_d.data_ptr(), st_d.data_ptr()
+            b.residual, b.model = None, None
+            eng.ctx.fit_batch(b, self.stream)
+            st = eng.download(st_d)
+            idx = np.nonzero(st)[0]
+            if idx.size == 0:
+                continue
+            bad = idx[(st[idx] & ~_cabi.ST_RANK_DEFICIENT) != 0]
+            left += int(bad.size)
+            idx = idx[(st[idx] & ~_cabi.ST_RANK_DEFICIENT) == 0]
+            if idx.size == 0:
+                continue
+            sel = torch.from_numpy(idx).to(eng.device)
+            R = eng.download(R_d.index_select(0, sel).contiguous()).reshape(idx.size, N, N + 1)
+            rb = self._row_begin[a + idx] if self._row_begin is not None else np.full(idx.size, b0.row_begin_all)
+            re = self._row_end[a + idx] if self._row_end is not None else np.full(idx.size, b0.row_end_all)
+            C_min = np.stack([_minimum_norm_from_factor(R[k], L * int(re[k] - rb[k])) for k in range(idx.size)])
+            C_d.index_copy_(0, sel, torch.from_numpy(np.ascontiguousarray(C_min, dtype=np.complex128)).to(eng.device))
+            eng.ctx.eval_batch(b, self.stream)
+            mm[a + idx] = eng.download(mm_d)[idx]
+        return left
 
 
 class _DeviceGroupSweep:
@@ -549,10 +622,9 @@ def _warn_status(flagged, what):
     if flagged:
         import warnings
         warnings.warn(
-            f"{what}: {flagged} fit(s) were flagged by the device (numerically rank "
-            "deficient by numpy's eps*max(M,N) criterion, underdetermined or non-finite); "
-            "numpy.linalg.lstsq would truncate singular values there, the device returns "
-            "the basic QR solution (mismatch may differ).",
+            f"{what}: {flagged} fit(s) were flagged by the device as underdetermined (rows <= "
+            "columns) or non-finite; their mismatch is not meaningful (numerically rank-deficient "
+            "fits are completed to numpy.linalg.lstsq's minimum-norm solution and are not counted).",
             RuntimeWarning, stacklevel=3)
 
 

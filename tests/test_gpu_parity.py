@@ -503,3 +503,63 @@ def test_real_kerr_tables_device_vs_oracle(qf, eng):
         assert np.max(np.abs(mfit["C"] - mref["C"])) < 1e-7 * scale
     finally:
         workloads.use_synthetic_tables()
+
+
+def test_sweeps_on_a_nonuniform_grid_and_ragged_windows(qf, eng, oracle_tables):
+    """Sweeps through the direct-evaluation generator (no nominal step) and with windows cut
+    short by the end of the series: K1 (8 modes), K3 single series (12 modes) and a multimode
+    Mf-chi grid, against the oracle; an empty window raises before any launch."""
+    wl = workloads.config2(n_t0=24)
+    rng = np.random.default_rng(8)
+    times = np.sort(wl.times + rng.uniform(-0.03, 0.03, size=wl.times.size))
+    t0s = np.linspace(20.0, 140.0, 24)                     # the last windows hit the end of the data
+    for modes in (wl.modes, [(2, 2, n, 1) for n in range(12)]):
+        # 12 overtones at these late start times are numerically rank deficient: numpy
+        # truncates singular values, the sweep completes the same minimum-norm solution
+        # from the device factor (no warning is left over)
+        with warnings.catch_warnings():
+            warnings.simplefilter("error")
+            got = qf.mismatch_t0_array(times, wl.data, modes, wl.Mf, wl.chif, t0s, T_array=60)
+        want = orc.mismatch_t0_array(oracle_tables, times, wl.data, modes, wl.Mf, wl.chif, t0s, T_array=60)
+        np.testing.assert_allclose(got, want, rtol=0, atol=MM_TOL)
+    w4 = cases.cfg4_small()
+    grid = qf.mismatch_M_chi_grid(w4.times, w4.data, w4.modes, (0.9, 1.0), (0.6, 0.78), 5.0, T=70, res=5,
+                                  spherical_modes=w4.spherical_modes)
+    want = orc.mismatch_M_chi_grid(oracle_tables, w4.times, w4.data, w4.modes, (0.9, 1.0), (0.6, 0.78), 5.0,
+                                   T=70, res=5, spherical_modes=w4.spherical_modes)
+    np.testing.assert_allclose(grid, want, rtol=0, atol=MM_TOL)
+    with pytest.raises(ValueError, match="window is empty"):
+        qf.mismatch_t0_array(times, wl.data, wl.modes, wl.Mf, wl.chif, np.array([10.0, 500.0]))
+    with pytest.raises(ValueError, match="window is empty"):
+        qf.mismatch_M_chi_grid(times, wl.data, wl.modes, (0.9, 1.0), (0.6, 0.7), 500.0, res=3)
+
+
+def test_rank_deficient_fits_in_sweeps_follow_numpy(qf, eng, oracle_tables):
+    """Sweeps whose fits numpy solves by truncating singular values (duplicated labels; many
+    overtones at late start times) return numpy's mismatches: uniform grid (fast-mismatch
+    path), Mf-chi grid, multimode."""
+    wl = workloads.config2(n_t0=16)
+    dup = [(2, 2, n, 1) for n in (0, 1, 9, 10)]          # (2,2,9) and (2,2,10) resolve to one sequence
+    t0s = np.linspace(0.0, 30.0, 16)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        got = qf.mismatch_t0_array(wl.times, wl.data, dup, wl.Mf, wl.chif, t0s)
+        grid = qf.mismatch_M_chi_grid(wl.times, wl.data, dup, (0.9, 1.0), (0.6, 0.78), 5.0, res=4)
+        late = qf.mismatch_t0_array(wl.times, wl.data, [(2, 2, n, 1) for n in range(12)], wl.Mf, wl.chif,
+                                    np.linspace(25.0, 60.0, 16), T_array=50)
+    want = orc.mismatch_t0_array(oracle_tables, wl.times, wl.data, dup, wl.Mf, wl.chif, t0s)
+    np.testing.assert_allclose(got, want, rtol=0, atol=MM_TOL)
+    gwant = orc.mismatch_M_chi_grid(oracle_tables, wl.times, wl.data, dup, (0.9, 1.0), (0.6, 0.78), 5.0, res=4)
+    np.testing.assert_allclose(grid, gwant, rtol=0, atol=MM_TOL)
+    lwant = orc.mismatch_t0_array(oracle_tables, wl.times, wl.data, [(2, 2, n, 1) for n in range(12)], wl.Mf,
+                                  wl.chif, np.linspace(25.0, 60.0, 16), T_array=50)
+    np.testing.assert_allclose(late, lwant, rtol=0, atol=MM_TOL)
+    w4 = cases.cfg4_small()
+    mm_dup = w4.modes + [w4.modes[0]]                     # a duplicated QNM in a multimode fit
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        mgot = qf.mismatch_t0_array(w4.times, w4.data, mm_dup, w4.Mf, w4.chif, w4.t0_array,
+                                    spherical_modes=w4.spherical_modes)
+    mwant = orc.mismatch_t0_array(oracle_tables, w4.times, w4.data, mm_dup, w4.Mf, w4.chif, w4.t0_array,
+                                  spherical_modes=w4.spherical_modes)
+    np.testing.assert_allclose(mgot, mwant, rtol=0, atol=MM_TOL)
