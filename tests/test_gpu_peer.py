@@ -39,6 +39,10 @@ def _sweeps(qf, wl3, wl2, wl4):
                                                      wl4.t0_array))
     out["grid_again"] = qf.mismatch_M_chi_grid(wl3.times, wl3.data, wl3.modes, wl3.Mf_minmax,
                                                wl3.chif_minmax, wl3.t0, T=wl3.T, res=21)
+    # numerically rank-deficient fits (duplicated label): every rank repairs its slab to numpy's
+    # minimum-norm solution and the repaired slabs are exchanged once more
+    out["deficient"] = np.array(qf.mismatch_t0_array(wl2.times, wl2.data, [(2, 2, n, 1) for n in (0, 1, 9, 10)],
+                                                     wl2.Mf, wl2.chif, wl2.t0_array[:45]))
     # more results than the first peer window holds (2^20): the window is re-created collectively
     out["big"] = qf.mismatch_M_chi_grid(wl3.times, wl3.data, wl3.modes[:2], wl3.Mf_minmax,
                                         wl3.chif_minmax, wl3.t0, T=30, res=1030)
@@ -88,7 +92,7 @@ def test_fused_exchange_two_gpus_bit_identical(tmp_path):
         assert int(got["capacity"]) == 1 << 21  # grown once, for the 1030 x 1030 grid
         assert int(got["epochs"]) == 2          # ... and the new window counts its own exchanges
         names = [k[len("single_"):] for k in got.files if k.startswith("single_")]
-        assert len(names) == 9
+        assert len(names) == 10
         for name in names:
             one = got["single_" + name]
             assert np.all(np.isfinite(one))
