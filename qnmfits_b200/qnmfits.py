@@ -347,6 +347,59 @@ def _series_rows(data, spherical_modes):
     return np.asarray(data, dtype=complex).reshape(1, -1), None
 
 
+def _repair_rank_deficient(eng, b0, n_local, stream, row_begin, row_end, mm):
+    """numpy.linalg.lstsq truncates singular values below ``eps * max(M, N) * s_max``
+    (numpy/linalg/_linalg.py:2553) and returns the minimum-norm amplitudes; the kernels
+    return the basic QR solution and flag such fits (late start times with many overtones,
+    duplicated labels).  Rare path: refit this slab with the triangular factor exported,
+    complete the minimum-norm solution of every flagged fit on the host
+    (``_minimum_norm_from_factor``, as ``ringdown_fit`` does for a single fit), re-evaluate
+    model and mismatch of those fits on the device and patch ``mm`` (the batch's
+    mismatches) in place.  Returns the number of flagged fits that are NOT of this kind."""
+    import torch
+    N, L = b0.n_modes, b0.n_series
+    left = 0
+    chunk = max(1, min(n_local, (1 << 28) // (16 * N * (N + 1))))
+    for a in range(0, n_local, chunk):
+        nb = min(n_local, a + chunk) - a
+        R_d = torch.empty((nb, N, N + 1), dtype=torch.complex128, device=eng.device)
+        C_d = torch.empty((nb, N), dtype=torch.complex128, device=eng.device)
+        st_d = torch.zeros(nb, dtype=torch.int32, device=eng.device)
+        mm_d = torch.empty(nb, dtype=torch.float64, device=eng.device)
+        b = type(b0).from_buffer_copy(b0)
+        b.n_fits, b.first_fit = nb, b0.first_fit + a
+        for name, width in (("row_begin", 4), ("row_end", 4), ("t0", 8), ("coef_index", 4), ("chi_index", 4),
+                            ("mf_index", 4), ("series_index", 4)):
+            ptr = getattr(b0, name)
+            if ptr:
+                setattr(b, name, ptr + width * a)
+        if b0.omega and not b0.omega_shared:
+            b.omega = b0.omega + 16 * N * a
+        b.mismatch, b.flagged_count = mm_d.data_ptr(), None
+        b.R, b.C, b.status = R_d.data_ptr(), C_d.data_ptr(), st_d.data_ptr()
+        b.residual, b.model = None, None
+        eng.ctx.fit_batch(b, stream)
+        st = eng.download(st_d)
+        idx = np.nonzero(st)[0]
+        if idx.size == 0:
+            continue
+        bad = idx[(st[idx] & ~_cabi.ST_RANK_DEFICIENT) != 0]
+        left += int(bad.size)
+        idx = idx[(st[idx] & ~_cabi.ST_RANK_DEFICIENT) == 0]
+        if idx.size == 0:
+            continue
+        sel = torch.from_numpy(idx).to(eng.device)
+        R = eng.download(R_d.index_select(0, sel).contiguous()).reshape(idx.size, N, N + 1)
+        rb = row_begin[a + idx] if row_begin is not None else np.full(idx.size, b0.row_begin_all)
+        re = row_end[a + idx] if row_end is not None else np.full(idx.size, b0.row_end_all)
+        C_min = np.stack([_minimum_norm_from_factor(R[k], L * int(re[k] - rb[k])) for k in range(idx.size)])
+        C_d.index_copy_(0, sel, torch.from_numpy(np.ascontiguousarray(C_min, dtype=np.complex128)).to(eng.device))
+        eng.ctx.eval_batch(b, stream)
+        mm[a + idx] = eng.download(mm_d)[idx]
+    return left
+
+
+
 class _Sweep:
     """A sweep whose inputs are resident on the device: upload once, launch many times.
 
@@ -511,56 +564,9 @@ class _Sweep:
         return mm, flagged
 
     def _repair_rank_deficient(self, mm):
-        """numpy.linalg.lstsq truncates singular values below ``eps * max(M, N) * s_max``
-        (numpy/linalg/_linalg.py:2553) and returns the minimum-norm amplitudes; the kernels
-        return the basic QR solution and flag such fits (late start times with many overtones,
-        duplicated labels).  Rare path: refit this slab with the triangular factor exported,
-        complete the minimum-norm solution of every flagged fit on the host
-        (``_minimum_norm_from_factor``, as ``ringdown_fit`` does for a single fit), re-evaluate
-        model and mismatch of those fits on the device and patch ``mm`` (the slab's
-        mismatches) in place.  Returns the number of flagged fits that are NOT of this kind."""
-        import torch
-        eng, b0 = self.eng, self.batch
-        n_local, N, L = self.hi - self.lo, b0.n_modes, b0.n_series
-        left = 0
-        chunk = max(1, min(n_local, (1 << 28) // (16 * N * (N + 1))))
-        for a in range(0, n_local, chunk):
-            nb = min(n_local, a + chunk) - a
-            R_d = torch.empty((nb, N, N + 1), dtype=torch.complex128, device=eng.device)
-            C_d = torch.empty((nb, N), dtype=torch.complex128, device=eng.device)
-            st_d = torch.zeros(nb, dtype=torch.int32, device=eng.device)
-            mm_d = torch.empty(nb, dtype=torch.float64, device=eng.device)
-            b = type(b0).from_buffer_copy(b0)
-            b.n_fits, b.first_fit = nb, b0.first_fit + a
-            for name, width in (("row_begin", 4), ("row_end", 4), ("t0", 8), ("coef_index", 4), ("chi_index", 4),
-                                ("mf_index", 4), ("series_index", 4)):
-                ptr = getattr(b0, name)
-                if ptr:
-                    setattr(b, name, ptr + width * a)
-            if b0.omega and not b0.omega_shared:
-                b.omega = b0.omega + 16 * N * a
-            b.mismatch, b.flagged_count = mm_d.data_ptr(), None
-            b.R, b.C, b.status = R_d.data_ptr(), C_d.data_ptr(), st_d.data_ptr()
-            b.residual, b.model = None, None
-            eng.ctx.fit_batch(b, self.stream)
-            st = eng.download(st_d)
-            idx = np.nonzero(st)[0]
-            if idx.size == 0:
-                continue
-            bad = idx[(st[idx] & ~_cabi.ST_RANK_DEFICIENT) != 0]
-            left += int(bad.size)
-            idx = idx[(st[idx] & ~_cabi.ST_RANK_DEFICIENT) == 0]
-            if idx.size == 0:
-                continue
-            sel = torch.from_numpy(idx).to(eng.device)
-            R = eng.download(R_d.index_select(0, sel).contiguous()).reshape(idx.size, N, N + 1)
-            rb = self._row_begin[a + idx] if self._row_begin is not None else np.full(idx.size, b0.row_begin_all)
-            re = self._row_end[a + idx] if self._row_end is not None else np.full(idx.size, b0.row_end_all)
-            C_min = np.stack([_minimum_norm_from_factor(R[k], L * int(re[k] - rb[k])) for k in range(idx.size)])
-            C_d.index_copy_(0, sel, torch.from_numpy(np.ascontiguousarray(C_min, dtype=np.complex128)).to(eng.device))
-            eng.ctx.eval_batch(b, self.stream)
-            mm[a + idx] = eng.download(mm_d)[idx]
-        return left
+        """Patch the slab's mismatches ``mm`` in place (see ``_repair_rank_deficient``)."""
+        return _repair_rank_deficient(self.eng, self.batch, self.hi - self.lo, self.stream,
+                                      self._row_begin, self._row_end, mm)
 
 
 class _DeviceGroupSweep:
@@ -897,7 +903,8 @@ class _ResidentData:
         arrays = [omega,
                   None if series_index is None else np.ascontiguousarray(series_index, dtype=np.int32),
                   None if coef is None else np.ascontiguousarray(coef, dtype=np.complex128),
-                  None if coef is None else np.arange(n, dtype=np.int32), rb, re]
+                  None if coef is None else np.arange(n, dtype=np.int32), rb, re,
+                  _ZERO]                             # counter of flagged fits, zeroed by the upload
         stream = eng.stream()
         keep, ptrs, out = eng.upload_packed(arrays, out_bytes=8 * n, stream=stream)
         batch = eng.make_batch(
@@ -906,13 +913,16 @@ class _ResidentData:
             row_end_all=self.window[1], t0_all=self.t0, omega_d=ptrs[0], series_index_d=ptrs[1],
             coef_d=ptrs[2], coef_index_d=ptrs[3], n_coef=0 if coef is None else n,
             row_begin_d=ptrs[4], row_end_d=ptrs[5], dt_nominal=dt,
-            uniform_weights=self.uniform and dt > 0.0, mismatch_d=out)
+            uniform_weights=self.uniform and dt > 0.0, mismatch_d=out, flagged_d=out - 8)
         eng.ctx.fit_batch(batch, stream)
         self.launches += 1
-        result = eng.download_raw(out, 8 * n, stream=stream)
+        result = eng.download_raw(out - 8, 8 * (n + 1), stream=stream)
+        flagged, result = int(result[0]), result[1:]
+        if flagged:
+            # a trial frequency (numerically) equal to another column: numpy truncates, so do we
+            _repair_rank_deficient(eng, batch, n, stream, rb, re, result)
         del keep
         return result
-
 
 class _FreeFrequencyObjective(_ResidentData):
     """The reference's ``mismatch_f_tau`` (qnmfits.py:2003-2029) for S waveforms that

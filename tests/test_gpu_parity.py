@@ -563,3 +563,19 @@ def test_rank_deficient_fits_in_sweeps_follow_numpy(qf, eng, oracle_tables):
     mwant = orc.mismatch_t0_array(oracle_tables, w4.times, w4.data, mm_dup, w4.Mf, w4.chif, w4.t0_array,
                                   spherical_modes=w4.spherical_modes)
     np.testing.assert_allclose(mgot, mwant, rtol=0, atol=MM_TOL)
+
+
+def test_omega_grid_node_on_a_fixed_mode_follows_numpy(qf, eng, oracle_tables):
+    """A frequency-grid node that coincides with one of the fixed modes makes two columns equal:
+    numpy truncates the zero singular value; so does the device path (repair of flagged fits)."""
+    wl = workloads.config1()
+    m2 = wl.modes[:2]
+    w0 = complex(qf.qnm.omega_list(m2, 0.69, 0.95)[0])
+    d = 0.125                                             # the centre node is w0 to an ulp
+    re_mm, im_mm = (w0.real - d, w0.real + d), (w0.imag - d, w0.imag + d)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        got = qf.mismatch_omega_grid(wl.times, wl.data, m2, 0.95, 0.69, re_mm, im_mm, 5.0, T=80, res=5)
+    want = orc.mismatch_omega_grid(oracle_tables, wl.times, wl.data, m2, 0.95, 0.69, re_mm, im_mm, 5.0, T=80, res=5)
+    assert abs(np.linspace(*re_mm, 5)[2] - w0.real) < 1e-15 and abs(np.linspace(*im_mm, 5)[2] - w0.imag) < 1e-15
+    np.testing.assert_allclose(got, want, rtol=0, atol=MM_TOL)
