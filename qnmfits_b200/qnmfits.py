@@ -173,27 +173,32 @@ def _minimum_norm_from_factor(R, M):
     return Vh.conj().T[:, keep] @ (c[keep] / s[keep])
 
 
-def _single_fit_on_device(times_m, data_rows, frequencies, t0, coef):
+def _single_fit_on_device(times_m, data_rows, frequencies, t0, coef, omega_rows=None, coef_rows=None):
     """One fit on the device: ``data_rows`` is (L, K) — the masked series.
 
     Returns dict with C, mismatch, residual, model (L, K), rank, s.  One packed upload,
     one launch, one download: the result region behind the inputs holds
     [C (N) | R (N x (N+1)) | model (L K) | mismatch, residual | status].
+    ``omega_rows`` (N, K) / ``coef_rows`` (L, N, K): per-sample frequencies / mixing
+    coefficients of a dynamic fit instead of ``frequencies`` / ``coef``.
     """
     eng = get_engine()
     L, K = data_rows.shape
-    N = len(frequencies)
+    N = len(frequencies) if omega_rows is None else omega_rows.shape[0]
     if N > _cabi.MAX_MODES:
         raise ValueError(f"at most {_cabi.MAX_MODES} modes are supported, got {N}")
     if K < 1:
         raise ValueError("the analysis window is empty")
-    wmax = float(np.max(np.abs(frequencies))) if N else 0.0
+    dynamic = omega_rows is not None
+    wmax = float(np.max(np.abs(frequencies))) if (N and not dynamic) else 0.0
     stream = eng.stream()
     host = [np.ascontiguousarray(times_m, dtype=np.float64),
             np.ascontiguousarray(data_rows, dtype=np.complex128),
-            np.ascontiguousarray(frequencies, dtype=np.complex128).reshape(1, N),
+            None if dynamic else np.ascontiguousarray(frequencies, dtype=np.complex128).reshape(1, N),
             None if coef is None else np.ascontiguousarray(coef, dtype=np.complex128).reshape(1, L, N),
-            None if coef is None else np.zeros(1, np.int32)]
+            None if coef is None else np.zeros(1, np.int32),
+            None if not dynamic else np.ascontiguousarray(omega_rows, dtype=np.complex128),
+            None if coef_rows is None else np.ascontiguousarray(coef_rows, dtype=np.complex128)]
     n_c, n_r, n_m = 16 * N, 16 * N * (N + 1), 16 * L * K
     out_bytes = n_c + n_r + n_m + 16 + 8
     keep, ptrs, out = eng.upload_packed(host, out_bytes=out_bytes, stream=stream)
@@ -202,9 +207,9 @@ def _single_fit_on_device(times_m, data_rows, frequencies, t0, coef):
     common = dict(
         times_d=ptrs[0], data_d=ptrs[1], n_times=K, series_stride=K, n_fits=1, n_modes=N, n_series=L,
         row_begin_all=0, row_end_all=K, t0_all=float(t0),
-        omega_d=ptrs[2], omega_shared=True, coef_d=ptrs[3], n_coef=0 if coef is None else 1,
-        coef_index_d=ptrs[4],
-        dt_nominal=nominal_step(times_m, wmax),
+        omega_d=ptrs[2], omega_shared=not dynamic, coef_d=ptrs[3], n_coef=0 if coef is None else 1,
+        coef_index_d=ptrs[4], omega_rows_d=ptrs[5], coef_rows_d=ptrs[6],
+        dt_nominal=0.0 if dynamic else nominal_step(times_m, wmax),
         C_d=C_p, mismatch_d=mm_p, residual_d=mm_p + 8, status_d=mm_p + 16,
         model_d=model_p, model_stride=L * K)
     eng.ctx.fit_batch(eng.make_batch(R_d=R_p, **common), stream)
@@ -1105,33 +1110,17 @@ def _row_tables(times, modes, Mf, chif, keys):
 
 
 def _dynamic_fit_on_device(times_m, data_rows, omega_rows, coef_rows, t0):
-    """One fit with per-row tables: K3 (single series) or K2 (per-row mixing)."""
-    import torch
-    eng = get_engine()
+    """One fit with per-row tables: K3 (single series) or K2 (per-row mixing); same device
+    round trip and the same minimum-norm completion of rank-deficient fits as
+    ``_single_fit_on_device``."""
     L, K = data_rows.shape
     N = omega_rows.shape[0]
-    if N > _cabi.MAX_MODES:
-        raise ValueError(f"at most {_cabi.MAX_MODES} modes are supported, got {N}")
-    if K < 1:
-        raise ValueError("the analysis window is empty")
-    C_d = eng.empty((1, N), torch.complex128)
-    mm_d = eng.empty((1,), torch.float64)
-    res_d = eng.empty((1,), torch.float64)
-    st_d = eng.empty((1,), torch.int32)
-    model_d = eng.empty((1, L * K), torch.complex128)
-    eng.fit(eng.make_batch(
-        times_d=eng.to_device(times_m, np.float64), data_d=eng.to_device(data_rows, np.complex128),
-        n_fits=1, n_modes=N, n_series=L, row_begin_all=0, row_end_all=K, t0_all=float(t0),
-        omega_rows_d=eng.to_device(omega_rows, np.complex128),
-        coef_rows_d=None if coef_rows is None else eng.to_device(coef_rows, np.complex128),
-        C_d=C_d, mismatch_d=mm_d, residual_d=res_d, status_d=st_d, model_d=model_d, model_stride=L * K))
-    status = int(eng.to_host(st_d)[0])
-    _warn_status(1 if status else 0, "dynamic fit")
-    residual = eng.to_host(res_d)
-    return {'C': eng.to_host(C_d)[0], 'mismatch': np.float64(eng.to_host(mm_d)[0]),
-            'residual': residual if (status & _cabi.ST_RANK_DEFICIENT) == 0 and L * K > N
+    out = _single_fit_on_device(times_m, data_rows, None, t0, None, omega_rows=omega_rows, coef_rows=coef_rows)
+    _warn_status(1 if out['status'] & ~_cabi.ST_RANK_DEFICIENT else 0, "dynamic fit")
+    return {'C': out['C'], 'mismatch': out['mismatch'],
+            'residual': np.array([out['residual']]) if (out['rank'] == N and L * K > N)
             else np.array([], dtype=np.float64),
-            'model': eng.to_host(model_d)[0].reshape(L, K)}
+            'model': out['model']}
 
 
 def dynamic_ringdown_fit(times, data, modes, Mf, chif, t0, t0_method='geq', T=100):
