@@ -57,7 +57,7 @@ for case in range(n_cases):
     method = 'geq' if rng.random() < 0.7 else 'closest'
     T = float(rng.uniform(20, 110))
     delta = 0.0 if rng.random() < 0.6 else list(rng.uniform(-0.02, 0.02, size=len(modes)))
-    kind = rng.integers(0, 4)
+    kind = rng.integers(0, 7)
     try:
         if kind == 0:
             t0 = float(rng.uniform(-5, 40))
@@ -77,6 +77,33 @@ for case in range(n_cases):
             got = qf.mismatch_M_chi_grid(times, data, modes, (0.9, 1.0), (0.55, 0.8), t0, method, T, 4, None, delta)
             want = orc.mismatch_M_chi_grid(tables, times, data, modes, (0.9, 1.0), (0.55, 0.8), t0, method, T, 4, None, delta)
             dmm = float(np.max(np.abs(got - want)))
+            extra = {}
+        elif kind == 4:                                   # dynamic single fit (time-dependent spectrum)
+            lin = [m for m in modes if len(m) == 4][:8] or [(2, 2, 0, 1)]
+            t0 = float(rng.uniform(0, 30))
+            x = np.exp(-np.clip(times, 0, None) / 15.0)
+            Mf_t, chi_t = Mf - 0.03 * x, chif - 0.05 * x
+            got = qf.dynamic_ringdown_fit(times, data, lin, Mf_t, chi_t, t0, method, T)
+            want = orc.dynamic_ringdown_fit(tables, times, data, lin, Mf_t, chi_t, t0, method, T)
+            dmm = abs(got['mismatch'] - want['mismatch'])
+            extra = {}
+        elif kind == 5:                                   # frequency grid around a fixed-mode set
+            lin = [m for m in modes if len(m) == 4][:5]
+            t0 = float(rng.uniform(0, 30))
+            got = qf.mismatch_omega_grid(times, data, lin, Mf, chif, (0.2, 0.9), (-0.7, -0.05), t0, method, T, 5)
+            want = orc.mismatch_omega_grid(tables, times, data, lin, Mf, chif, (0.2, 0.9), (-0.7, -0.05), t0, method, T, 5)
+            dmm = float(np.max(np.abs(got - want)))
+            extra = {}
+        elif kind == 6:                                   # dynamic multimode fit
+            sph = [(2, 2), (3, 2), (4, 2)]
+            lin = [m for m in modes if len(m) == 4][:6] or [(2, 2, 0, 1)]
+            dd = {lm: data * (0.4 ** i) * np.exp(0.3j * i) for i, lm in enumerate(sph)}
+            t0 = float(rng.uniform(0, 30))
+            x = np.exp(-np.clip(times, 0, None) / 15.0)
+            Mf_t, chi_t = Mf - 0.03 * x, chif - 0.05 * x
+            got = qf.dynamic_multimode_ringdown_fit(times, dd, lin, Mf_t, chi_t, t0, method, T, sph)
+            want = orc.dynamic_multimode_ringdown_fit(tables, times, dd, lin, Mf_t, chi_t, t0, method, T, sph)
+            dmm = abs(got['mismatch'] - want['mismatch'])
             extra = {}
         else:
             sph = [(2, 2), (3, 2), (4, 2)]
