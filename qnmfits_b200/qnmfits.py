@@ -715,7 +715,7 @@ def mismatch_t0_array(times, data, modes, Mf, chif, t0_array, t0_method='geq',
         sweep.launch()
         mm, status = sweep.fetch()
         _warn_status(status, "mismatch_t0_array")
-        return [np.float64(v) for v in mm]
+        return list(mm)          # np.float64 scalars, like the reference
 
     if np.any(np.diff(times) < 0):
         # Unsorted time arrays make the 'geq' mask non-contiguous: fit one by one.
@@ -735,7 +735,7 @@ def mismatch_t0_array(times, data, modes, Mf, chif, t0_array, t0_method='geq',
     sweep.launch()
     mm, status = sweep.fetch()
     _warn_status(status, "mismatch_t0_array")
-    return [np.float64(v) for v in mm]
+    return list(mm)              # np.float64 scalars, like the reference
 
 
 _linspace_memo = {}
