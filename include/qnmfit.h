@@ -45,7 +45,8 @@ extern "C" {
 #define QNMFIT_ABI_VERSION 4
 
 /* limits of the compiled kernels */
-#define QNMFIT_MAX_MODES_SMALL 8     /* register-resident TSQR kernel (K1)   */
+#define QNMFIT_MAX_MODES_SMALL 12    /* register-resident TSQR kernel (K1): 4-row blocks
+                                        up to 8 columns, 3 rows for 9-10, 2 rows for 11-12 */
 #define QNMFIT_DEFAULT_ANCHOR_ROWS 256 /* measured on B200: accuracy is flat from 16 to 512 rows */
 #define QNMFIT_MAX_MODES 64          /* CTA-cooperative general kernel (K2)  */
 
@@ -59,16 +60,18 @@ extern "C" {
 
 /* per-fit status bits */
 #define QNMFIT_ST_OK            0
-#define QNMFIT_ST_RANK_DEFICIENT 1   /* |R_jj| <= eps*max(M,N)*max|R_jj| for some j:
-                                        numpy.linalg.lstsq(rcond=None) may truncate
-                                        (numpy/linalg/_linalg.py:2553) — amplitudes are
-                                        a basic, not the minimum-norm, solution     */
+#define QNMFIT_ST_RANK_DEFICIENT 1   /* |R_jj| <= 1024*eps*max(M,N)*max|R_jj| for some j:
+                                        numpy.linalg.lstsq(rcond=None) MAY truncate a
+                                        singular value (numpy/linalg/_linalg.py:2553; the
+                                        diagonal of R can sit ~700x above s_min/s_max, hence
+                                        the margin) — amplitudes are the basic QR solution;
+                                        the caller decides with the SVD of the exported R   */
 #define QNMFIT_ST_NONFINITE     2    /* non-finite value met in inputs or outputs  */
 #define QNMFIT_ST_UNDERDETERMINED 4  /* rows <= columns                            */
 
 /* kernel selection (qnmfit_batch.kernel) */
 #define QNMFIT_KERNEL_AUTO    0
-#define QNMFIT_KERNEL_SMALL   1      /* K1: n_series == 1 and n_modes <= 8         */
+#define QNMFIT_KERNEL_SMALL   1      /* K1: n_series == 1 and n_modes <= 12        */
 #define QNMFIT_KERNEL_GENERAL 2      /* K2: any n_series, n_modes <= 64            */
 #define QNMFIT_KERNEL_STRUCT  3      /* K3: n_modes + n_series <= 64, structured QR */
 

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libqnmfit.so")
 
 ABI_VERSION = 4
-MAX_MODES_SMALL = 8
+MAX_MODES_SMALL = 12
 MAX_MODES = 64
 MAX_PEERS = 8
 

@@ -37,7 +37,9 @@
 
 template <int N>
 struct SmallLayout {
-    static constexpr int MB = 4;                      // rows per register block
+    // rows per register block: the block [MB x (N+1)] complex lives in registers next to the
+    // generator state (N complex) and the dot-product accumulators (2 (N+1) doubles)
+    static constexpr int MB = N <= 8 ? 4 : N <= 10 ? 3 : 2;
     static constexpr int NC = N + 1;                  // columns incl. right-hand side
     static constexpr int NP = N * (N + 1) / 2;        // strictly-upper entries incl. rhs column
     // index of R[j][k], j < k <= N (k == N is the rhs column)
@@ -91,12 +93,13 @@ struct SmallLane {
     int lf;         // lane index within the fit
     int rb, re;     // window rows of the fit
     int lo, hi;     // rows of this lane
-    int nblk;       // 4-row blocks of this lane (same for all lanes of a fit)
+    int nblk;       // MB-row blocks of this lane (same for all lanes of a fit)
     double t0;
     long long d_off;   // element offset of the fit's own data series (series_index; 0 when shared)
 };
 
-QF_HD SmallLane small_lane_setup(const FitParams &p, int cta, int tid, int threads, bool per_fit_data = true)
+QF_HD SmallLane small_lane_setup(const FitParams &p, int cta, int tid, int threads, bool per_fit_data = true,
+                                 int mb = 4)
 {
     SmallLane L;
     const int lpf = p.lanes_per_fit;
@@ -119,8 +122,8 @@ QF_HD SmallLane small_lane_setup(const FitParams &p, int cta, int tid, int threa
         if (L.re < L.rb) L.re = L.rb;
         int M = L.re - L.rb;
         int rpl = (M + lpf - 1) / lpf;
-        rpl = (rpl + 3) / 4 * 4;
-        L.nblk = rpl / 4;
+        rpl = (rpl + mb - 1) / mb * mb;
+        L.nblk = rpl / mb;
         L.lo = L.rb + L.lf * rpl;
         if (L.lo > L.re) L.lo = L.re;
         L.hi = L.lo + rpl;
@@ -142,10 +145,11 @@ struct SmallGen {
 // belong to the lane (no per-row selects); otherwise rows beyond L.hi are zero rows.
 template <int N, int THREADS, bool FULL>
 QF_HD void small_emit(const FitParams &p, const SmallSmem<N, THREADS> &sm, const SmallLane &L,
-                      SmallGen<N> &g, int row0, bool direct, double2 (&B)[4][N + 1])
+                      SmallGen<N> &g, int row0, bool direct, double2 (&B)[SmallLayout<N>::MB][N + 1])
 {
+    constexpr int MB = SmallLayout<N>::MB;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < MB; ++i) {
         const int r = row0 + i;
         const bool valid = FULL || r < L.hi;
         const double2 zero = make_double2(0.0, 0.0);
@@ -158,7 +162,7 @@ QF_HD void small_emit(const FitParams &p, const SmallSmem<N, THREADS> &sm, const
         if (rn < L.rb) rn = L.rb;
         const double tau_n = qf_sub_rn(sm.ts[rn - sm.t_off], L.t0);
         if (direct) {
-            if (rn < L.hi && i < 3) {
+            if (rn < L.hi && i < MB - 1) {
 #pragma unroll
                 for (int j = 0; j < N; ++j) g.z[j] = design_entry(sm.om[j * sm.fpc + L.slot], tau_n);
             }
@@ -184,9 +188,10 @@ QF_HD void small_emit(const FitParams &p, const SmallSmem<N, THREADS> &sm, const
 
 template <int N, int THREADS>
 QF_HD void small_generate(const FitParams &p, const SmallSmem<N, THREADS> &sm, const SmallLane &L,
-                          SmallGen<N> &g, int blk, int ablk, double2 (&B)[4][N + 1])
+                          SmallGen<N> &g, int blk, int ablk, double2 (&B)[SmallLayout<N>::MB][N + 1])
 {
-    const int row0 = L.lo + blk * 4;
+    constexpr int MB = SmallLayout<N>::MB;
+    const int row0 = L.lo + blk * MB;
     const bool direct = !(p.dt_nominal > 0.0);
     if ((direct || blk % ablk == 0) && row0 < L.hi) {
         g.tau_a = qf_sub_rn(sm.ts[row0 - sm.t_off], L.t0);
@@ -195,16 +200,17 @@ QF_HD void small_generate(const FitParams &p, const SmallSmem<N, THREADS> &sm, c
         g.eps = 0.0;
         g.n = 0;
     }
-    if (row0 + 4 <= L.hi) small_emit<N, THREADS, true>(p, sm, L, g, row0, direct, B);
+    if (row0 + MB <= L.hi) small_emit<N, THREADS, true>(p, sm, L, g, row0, direct, B);
     else small_emit<N, THREADS, false>(p, sm, L, g, row0, direct, B);
 }
 
 // Fold the 4 x (N+1) block B into the lane's factor: N Householder reflections of
 // [R; B], columns JSTART..N-1 (columns below JSTART of B must be zero).
 template <int N, int THREADS, int JSTART>
-QF_HD void small_absorb_v1(double2 (&B)[4][N + 1], double *Rd, double2 *Ro)
+QF_HD void small_absorb_v1(double2 (&B)[SmallLayout<N>::MB][N + 1], double *Rd, double2 *Ro)
 {
     typedef SmallLayout<N> LY;
+    static_assert(LY::MB == 4, "the v1 form is written for four-row blocks");
 #pragma unroll
     for (int j = JSTART; j < N; ++j) {
         const double r = Rd[j * THREADS];
@@ -295,7 +301,7 @@ QF_HD void small_absorb_v1(double2 (&B)[4][N + 1], double *Rd, double2 *Ro)
 struct SmallNoHook { QF_MEM void operator()(int) const {} };
 
 template <int N, int THREADS, int JSTART, class Hook>
-QF_HD void small_absorb_hook(double2 (&B)[4][N + 1], double *Rd, double2 *Ro, const Hook &done)
+QF_HD void small_absorb_hook(double2 (&B)[SmallLayout<N>::MB][N + 1], double *Rd, double2 *Ro, const Hook &done)
 {
 #ifdef QNMFIT_ABSORB_V1
     small_absorb_v1<N, THREADS, JSTART>(B, Rd, Ro);
@@ -308,28 +314,50 @@ QF_HD void small_absorb_hook(double2 (&B)[4][N + 1], double *Rd, double2 *Ro, co
         const double r = Rd[j * THREADS];
         double sr[N + 1], si[N + 1];
         // (A)
-        double sig0 = fma(B[0][j].x, B[0][j].x, 1e-300), sig1 = B[1][j].x * B[1][j].x;
+        double t;
+        if constexpr (LY::MB == 4) {
+            double sig0 = fma(B[0][j].x, B[0][j].x, 1e-300), sig1 = B[1][j].x * B[1][j].x;
 #pragma unroll
-        for (int k = j + 1; k <= N; ++k) { sr[k] = B[0][j].x * B[0][k].x; si[k] = B[0][j].x * B[0][k].y; }
-        sig0 = fma(B[0][j].y, B[0][j].y, sig0);
-        sig1 = fma(B[1][j].y, B[1][j].y, sig1);
+            for (int k = j + 1; k <= N; ++k) { sr[k] = B[0][j].x * B[0][k].x; si[k] = B[0][j].x * B[0][k].y; }
+            sig0 = fma(B[0][j].y, B[0][j].y, sig0);
+            sig1 = fma(B[1][j].y, B[1][j].y, sig1);
 #pragma unroll
-        for (int k = j + 1; k <= N; ++k) { sr[k] = fma(B[0][j].y, B[0][k].y, sr[k]); si[k] = fma(-B[0][j].y, B[0][k].x, si[k]); }
-        sig0 = fma(B[2][j].x, B[2][j].x, sig0);
-        sig1 = fma(B[3][j].x, B[3][j].x, sig1);
+            for (int k = j + 1; k <= N; ++k) { sr[k] = fma(B[0][j].y, B[0][k].y, sr[k]); si[k] = fma(-B[0][j].y, B[0][k].x, si[k]); }
+            sig0 = fma(B[2][j].x, B[2][j].x, sig0);
+            sig1 = fma(B[3][j].x, B[3][j].x, sig1);
 #pragma unroll
-        for (int k = j + 1; k <= N; ++k) { sr[k] = fma(B[1][j].x, B[1][k].x, sr[k]); si[k] = fma(B[1][j].x, B[1][k].y, si[k]); }
-        sig0 = fma(B[2][j].y, B[2][j].y, sig0);
-        sig1 = fma(B[3][j].y, B[3][j].y, sig1);
+            for (int k = j + 1; k <= N; ++k) { sr[k] = fma(B[1][j].x, B[1][k].x, sr[k]); si[k] = fma(B[1][j].x, B[1][k].y, si[k]); }
+            sig0 = fma(B[2][j].y, B[2][j].y, sig0);
+            sig1 = fma(B[3][j].y, B[3][j].y, sig1);
 #pragma unroll
-        for (int k = j + 1; k <= N; ++k) { sr[k] = fma(B[1][j].y, B[1][k].y, sr[k]); si[k] = fma(-B[1][j].y, B[1][k].x, si[k]); }
-        const double t = fma(r, r, sig0 + sig1);
+            for (int k = j + 1; k <= N; ++k) { sr[k] = fma(B[1][j].y, B[1][k].y, sr[k]); si[k] = fma(-B[1][j].y, B[1][k].x, si[k]); }
+            t = fma(r, r, sig0 + sig1);
 #pragma unroll
-        for (int i = 2; i < 4; ++i) {
+            for (int i = 2; i < 4; ++i) {
 #pragma unroll
-            for (int k = j + 1; k <= N; ++k) { sr[k] = fma(B[i][j].x, B[i][k].x, sr[k]); si[k] = fma(B[i][j].x, B[i][k].y, si[k]); }
+                for (int k = j + 1; k <= N; ++k) { sr[k] = fma(B[i][j].x, B[i][k].x, sr[k]); si[k] = fma(B[i][j].x, B[i][k].y, si[k]); }
 #pragma unroll
-            for (int k = j + 1; k <= N; ++k) { sr[k] = fma(B[i][j].y, B[i][k].y, sr[k]); si[k] = fma(-B[i][j].y, B[i][k].x, si[k]); }
+                for (int k = j + 1; k <= N; ++k) { sr[k] = fma(B[i][j].y, B[i][k].y, sr[k]); si[k] = fma(-B[i][j].y, B[i][k].x, si[k]); }
+            }
+        } else {      // shorter blocks (N > 8): the same sums, rows innermost
+            double sig0 = 1e-300, sig1 = 0.0;
+#pragma unroll
+            for (int k = j + 1; k <= N; ++k) { sr[k] = B[0][j].x * B[0][k].x; si[k] = B[0][j].x * B[0][k].y; }
+#pragma unroll
+            for (int k = j + 1; k <= N; ++k) { sr[k] = fma(B[0][j].y, B[0][k].y, sr[k]); si[k] = fma(-B[0][j].y, B[0][k].x, si[k]); }
+#pragma unroll
+            for (int i = 0; i < LY::MB; ++i) {
+                if (i & 1) { sig1 = fma(B[i][j].x, B[i][j].x, sig1); sig1 = fma(B[i][j].y, B[i][j].y, sig1); }
+                else { sig0 = fma(B[i][j].x, B[i][j].x, sig0); sig0 = fma(B[i][j].y, B[i][j].y, sig0); }
+            }
+            t = fma(r, r, sig0 + sig1);
+#pragma unroll
+            for (int i = 1; i < LY::MB; ++i) {
+#pragma unroll
+                for (int k = j + 1; k <= N; ++k) { sr[k] = fma(B[i][j].x, B[i][k].x, sr[k]); si[k] = fma(B[i][j].x, B[i][k].y, si[k]); }
+#pragma unroll
+                for (int k = j + 1; k <= N; ++k) { sr[k] = fma(B[i][j].y, B[i][k].y, sr[k]); si[k] = fma(-B[i][j].y, B[i][k].x, si[k]); }
+            }
         }
         // (B)
 #ifdef QNMFIT_ABL_NOSCALAR
@@ -357,7 +385,7 @@ QF_HD void small_absorb_hook(double2 (&B)[4][N + 1], double *Rd, double2 *Ro, co
             Rjk.y = fma(-v0, pi, Rjk.y);
             Ro[LY::pair(j, k) * THREADS] = Rjk;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < LY::MB; ++i) {
                 double bx = B[i][k].x, by = B[i][k].y;
                 bx = fma(-pr, B[i][j].x, bx);
                 by = fma(-pr, B[i][j].y, by);
@@ -373,7 +401,7 @@ QF_HD void small_absorb_hook(double2 (&B)[4][N + 1], double *Rd, double2 *Ro, co
 }
 
 template <int N, int THREADS, int JSTART>
-QF_HD void small_absorb(double2 (&B)[4][N + 1], double *Rd, double2 *Ro)
+QF_HD void small_absorb(double2 (&B)[SmallLayout<N>::MB][N + 1], double *Rd, double2 *Ro)
 {
     small_absorb_hook<N, THREADS, JSTART>(B, Rd, Ro, SmallNoHook());
 }
@@ -381,19 +409,19 @@ QF_HD void small_absorb(double2 (&B)[4][N + 1], double *Rd, double2 *Ro)
 // Refill a column of B with the next block's four rows and advance the generator:
 // row k+1 = row k * (q + q(-i w) de_k), de_k the deviation of that step from the nominal one.
 template <int N>
-QF_HD void small_fill_column(double2 (&B)[4][N + 1], double2 (&z)[N], const double (&de)[4], const double2 *qq,
+QF_HD void small_fill_column(double2 (&B)[SmallLayout<N>::MB][N + 1], double2 (&z)[N], const double (&de)[SmallLayout<N>::MB], const double2 *qq,
                              const double2 *qw, int fpc, int c)
 {
 #ifndef QNMFIT_ABL_NOGEN
     const double2 q = qq[c * fpc], w = qw[c * fpc];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < SmallLayout<N>::MB; ++i) {
         B[i][c] = z[c];
         z[c] = c_mul(z[c], make_double2(fma(w.x, de[i], q.x), fma(w.y, de[i], q.y)));
     }
 #else
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { B[i][c] = z[c]; z[c].x += de[i]; }
+    for (int i = 0; i < SmallLayout<N>::MB; ++i) { B[i][c] = z[c]; z[c].x += de[i]; }
 #endif
 }
 
@@ -418,9 +446,9 @@ template <int N>
 struct SmallRefill {
     static constexpr int H = QNMFIT_PIPE_H(N), S = QNMFIT_PIPE_S(N);
     static_assert(H >= 0 && H <= N && S >= 0 && H + S <= N, "column c is refilled after reflection c + S <= N - 1");
-    double2 (&B)[4][N + 1];
+    double2 (&B)[SmallLayout<N>::MB][N + 1];
     double2 (&z)[N];
-    const double (&de)[4];
+    const double (&de)[SmallLayout<N>::MB];
     const double2 *qq, *qw;
     int fpc;
     QF_MEM void operator()(int j) const
@@ -449,10 +477,10 @@ struct SmallAcc {
 };
 
 template <int N>
-QF_HD void small_acc_rhs(const double2 (&B)[4][N + 1], double &acc)
+QF_HD void small_acc_rhs(const double2 (&B)[SmallLayout<N>::MB][N + 1], double &acc)
 {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < SmallLayout<N>::MB; ++i) {
         acc = fma(B[i][N].x, B[i][N].x, acc);
         acc = fma(B[i][N].y, B[i][N].y, acc);
     }
@@ -460,12 +488,20 @@ QF_HD void small_acc_rhs(const double2 (&B)[4][N + 1], double &acc)
 
 // Same, as two independent chains (rows 0-1 and rows 2-3).
 template <int N>
-QF_HD void small_acc_rhs2(const double2 (&B)[4][N + 1], double &a0, double &a1)
+QF_HD void small_acc_rhs2(const double2 (&B)[SmallLayout<N>::MB][N + 1], double &a0, double &a1)
 {
-    a0 = fma(B[0][N].x, B[0][N].x, a0); a1 = fma(B[2][N].x, B[2][N].x, a1);
-    a0 = fma(B[0][N].y, B[0][N].y, a0); a1 = fma(B[2][N].y, B[2][N].y, a1);
-    a0 = fma(B[1][N].x, B[1][N].x, a0); a1 = fma(B[3][N].x, B[3][N].x, a1);
-    a0 = fma(B[1][N].y, B[1][N].y, a0); a1 = fma(B[3][N].y, B[3][N].y, a1);
+    if constexpr (SmallLayout<N>::MB == 4) {
+        a0 = fma(B[0][N].x, B[0][N].x, a0); a1 = fma(B[2][N].x, B[2][N].x, a1);
+        a0 = fma(B[0][N].y, B[0][N].y, a0); a1 = fma(B[2][N].y, B[2][N].y, a1);
+        a0 = fma(B[1][N].x, B[1][N].x, a0); a1 = fma(B[3][N].x, B[3][N].x, a1);
+        a0 = fma(B[1][N].y, B[1][N].y, a0); a1 = fma(B[3][N].y, B[3][N].y, a1);
+    } else {
+#pragma unroll
+        for (int i = 0; i < SmallLayout<N>::MB; ++i) {
+            if (i & 1) { a1 = fma(B[i][N].x, B[i][N].x, a1); a1 = fma(B[i][N].y, B[i][N].y, a1); }
+            else { a0 = fma(B[i][N].x, B[i][N].x, a0); a0 = fma(B[i][N].y, B[i][N].y, a0); }
+        }
+    }
 }
 
 // Leaf stage, general form: any grid (direct evaluation of every element when
@@ -474,16 +510,17 @@ template <int N, int THREADS>
 QF_HD void small_leaf_generic(const FitParams &p, const SmallSmem<N, THREADS> &sm, const SmallLane &L, int tid,
                               SmallAcc &acc)
 {
-    int ablk = (p.anchor_rows > 0 ? p.anchor_rows : QNMFIT_DEFAULT_ANCHOR_ROWS) / 4;
+    constexpr int MB = SmallLayout<N>::MB;
+    int ablk = (p.anchor_rows > 0 ? p.anchor_rows : QNMFIT_DEFAULT_ANCHOR_ROWS) / MB;
     if (ablk < 1) ablk = 1;
     SmallGen<N> g;
 #pragma unroll
     for (int j = 0; j < N; ++j) g.z[j] = make_double2(0.0, 0.0);
     g.tau_a = 0.0; g.eps = 0.0; g.n = 0;
-    double2 B[4][N + 1];
+    double2 B[SmallLayout<N>::MB][N + 1];
 #pragma unroll 1
     for (int blk = 0; blk < L.nblk; ++blk) {
-        if (L.lo + blk * 4 >= L.hi) break;
+        if (L.lo + blk * MB >= L.hi) break;
         small_generate<N, THREADS>(p, sm, L, g, blk, ablk, B);
         small_acc_rhs<N>(B, acc.sdd);
         small_absorb<N, THREADS, 0>(B, sm.Rd + tid, sm.Ro + tid);
@@ -506,14 +543,15 @@ QF_HD void small_leaf_uniform(const FitParams &p, const SmallSmem<N, THREADS> &s
     const double2 *om = sm.om + L.slot, *qq = sm.qq + L.slot, *qw = sm.qw + L.slot;
     const int fpc = sm.fpc;
     const double dt = p.dt_nominal, t0 = L.t0;
-    int ablk = (p.anchor_rows > 0 ? p.anchor_rows : QNMFIT_DEFAULT_ANCHOR_ROWS) / 4;
+    constexpr int MB = SmallLayout<N>::MB;
+    int ablk = (p.anchor_rows > 0 ? p.anchor_rows : QNMFIT_DEFAULT_ANCHOR_ROWS) / MB;
     if (ablk < 1) ablk = 1;
-    const int nfull = (L.hi - L.lo) >> 2;
+    const int nfull = MB == 4 ? (L.hi - L.lo) >> 2 : (L.hi - L.lo) / MB;
     const int last = L.re - 1;
     int row0 = L.lo;
     double2 z[N];
-    double2 B[4][N + 1];
-    double de[4];
+    double2 B[SmallLayout<N>::MB][N + 1];
+    double de[MB];
     double sdd1 = 0.0, res1 = 0.0;   // second accumulation chains
     // Software pipeline (SmallRefill): while block b is folded into R, the first H columns
     // of block b+1 are generated into the registers of columns the sweep has retired.  Rows
@@ -528,11 +566,13 @@ QF_HD void small_leaf_uniform(const FitParams &p, const SmallSmem<N, THREADS> &s
 #pragma unroll
         for (int j = 0; j < N; ++j) z[j] = design_entry(om[j * fpc], tau);
         {   // deviations of the segment's first block; its first H columns
-            const int r4 = PADDED || row0 + 4 < last ? row0 + 4 : last;
-            double tn[4];
-            tn[0] = ts[row0 + 1]; tn[1] = ts[row0 + 2]; tn[2] = ts[row0 + 3]; tn[3] = ts[r4];
+            const int rM = PADDED || row0 + MB < last ? row0 + MB : last;
+            double tn[MB];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < MB - 1; ++i) tn[i] = ts[row0 + 1 + i];
+            tn[MB - 1] = ts[rM];
+#pragma unroll
+            for (int i = 0; i < MB; ++i) {
                 const double tau_n = qf_sub_rn(tn[i], t0);
                 de[i] = qf_sub_rn(qf_sub_rn(tau_n, tau), dt);
                 tau = tau_n;
@@ -543,10 +583,10 @@ QF_HD void small_leaf_uniform(const FitParams &p, const SmallSmem<N, THREADS> &s
 #pragma unroll 1
         for (int b = 0; b < nb; ++b) {
             // all loads of the iteration up front: this block's data, the next block's times
-            double tn[4];
+            double tn[MB];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int rt = PADDED || row0 + 5 + i < last ? row0 + 5 + i : last;
+            for (int i = 0; i < MB; ++i) {
+                const int rt = PADDED || row0 + MB + 1 + i < last ? row0 + MB + 1 + i : last;
                 tn[i] = ts[rt];
                 B[i][N] = ds[row0 + i];
             }
@@ -555,7 +595,7 @@ QF_HD void small_leaf_uniform(const FitParams &p, const SmallSmem<N, THREADS> &s
             for (int c = H; c < N; ++c) small_fill_column<N>(B, z, de, qq, qw, fpc, c);
             // ... then the next block's deviations
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < MB; ++i) {
                 const double tau_n = qf_sub_rn(tn[i], t0);
                 de[i] = qf_sub_rn(qf_sub_rn(tau_n, tau), dt);
                 tau = tau_n;
@@ -564,17 +604,17 @@ QF_HD void small_leaf_uniform(const FitParams &p, const SmallSmem<N, THREADS> &s
             const SmallRefill<N> refill = {B, z, de, qq, qw, fpc};
             small_absorb_hook<N, THREADS, 0>(B, sm.Rd + tid, sm.Ro + tid, refill);
             small_acc_rhs2<N>(B, acc.res2, res1);
-            row0 += 4;
+            row0 += MB;
         }
         blk += nb;
     }
-    if (row0 < L.hi) {   // ragged tail (at most 3 rows): anchor, recurrence, zero rows beyond the lane's share
+    if (row0 < L.hi) {   // ragged tail (fewer than MB rows): anchor, recurrence, zero rows beyond the lane's share
         double tau = qf_sub_rn(ts[row0], t0);
 #pragma unroll
         for (int j = 0; j < N; ++j) z[j] = design_entry(om[j * fpc], tau);
         const double2 zero = make_double2(0.0, 0.0);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < MB; ++i) {
             const bool valid = row0 + i < L.hi;
             B[i][N] = valid ? ds[valid ? row0 + i : row0] : zero;
             const int rn = row0 + i + 1 < last ? row0 + i + 1 : last;
@@ -607,15 +647,15 @@ QF_HD void small_leaf(const FitParams &p, const SmallSmem<N, THREADS> &sm, const
     else small_leaf_generic<N, THREADS>(p, sm, L, tid, acc);
 }
 
-// Absorb rows B0..B0+3 of the partner's triangle (rows >= N are zero rows).  Row r of a
+// Absorb rows B0..B0+MB-1 of the partner's triangle (rows >= N are zero rows).  Row r of a
 // triangle is zero left of column r, so the reflections can start at column B0.
 template <int N, int THREADS, int B0>
 QF_HD void small_tree_block(const SmallSmem<N, THREADS> &sm, int tid, int pt, SmallAcc &acc)
 {
     if constexpr (B0 < N) {
-        double2 B[4][N + 1];
+        double2 B[SmallLayout<N>::MB][N + 1];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < SmallLayout<N>::MB; ++i) {
             const int row = B0 + i;
 #pragma unroll
             for (int k = 0; k <= N; ++k) {
@@ -629,7 +669,7 @@ QF_HD void small_tree_block(const SmallSmem<N, THREADS> &sm, int tid, int pt, Sm
         }
         small_absorb<N, THREADS, B0>(B, sm.Rd + tid, sm.Ro + tid);
         small_acc_rhs<N>(B, acc.res2);
-        small_tree_block<N, THREADS, B0 + 4>(sm, tid, pt, acc);
+        small_tree_block<N, THREADS, B0 + SmallLayout<N>::MB>(sm, tid, pt, acc);
     }
 }
 
@@ -658,7 +698,7 @@ QF_HD void small_backsub(const FitParams &p, const SmallSmem<N, THREADS> &sm, co
         dmax = a > dmax ? a : dmax;
         dmin = a < dmin ? a : dmin;
     }
-    const double cut = 2.220446049250313e-16 * (double)(M > N ? M : N) * dmax;
+    const double cut = QNMFIT_RANK_FLAG_MARGIN * 2.220446049250313e-16 * (double)(M > N ? M : N) * dmax;
     if (!(dmin > cut)) status |= QNMFIT_ST_RANK_DEFICIENT_;
     if (M <= N) status |= QNMFIT_ST_UNDERDETERMINED_;
     if (p.R) {
@@ -720,20 +760,21 @@ QF_HD void small_eval(const FitParams &p, const SmallSmem<N, THREADS> &sm, const
 #pragma unroll
         for (int j = 0; j < N; ++j) C[j] = sm.Ro[LY::pair(j, N) * THREADS + t0lane];
     }
-    int ablk = (p.anchor_rows > 0 ? p.anchor_rows : QNMFIT_DEFAULT_ANCHOR_ROWS) / 4;
+    constexpr int MB = SmallLayout<N>::MB;
+    int ablk = (p.anchor_rows > 0 ? p.anchor_rows : QNMFIT_DEFAULT_ANCHOR_ROWS) / MB;
     if (ablk < 1) ablk = 1;
     SmallGen<N> g;
 #pragma unroll
     for (int j = 0; j < N; ++j) g.z[j] = make_double2(0.0, 0.0);
     g.tau_a = 0.0; g.eps = 0.0; g.n = 0;
-    double2 B[4][N + 1];
+    double2 B[SmallLayout<N>::MB][N + 1];
 #pragma unroll 1
     for (int blk = 0; blk < L.nblk; ++blk) {
-        const int row0 = L.lo + blk * 4;
+        const int row0 = L.lo + blk * MB;
         if (row0 >= L.hi) break;
         small_generate<N, THREADS>(p, sm, L, g, blk, ablk, B);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < MB; ++i) {
             const int r = row0 + i;
             if (r < L.hi) {
                 double mx = 0.0, my = 0.0;
@@ -861,7 +902,7 @@ __global__ void __launch_bounds__(THREADS, 1) fit_small_kernel(const __grid_cons
             }
         }
     }
-    const SmallLane L = small_lane_setup(p, blockIdx.x, tid, THREADS, !STAGED);
+    const SmallLane L = small_lane_setup(p, blockIdx.x, tid, THREADS, !STAGED, SmallLayout<N>::MB);
     small_clear<N, THREADS>(sm, tid);
     __syncthreads();
 

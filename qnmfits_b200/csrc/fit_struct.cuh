@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(64 * G, K3C_MINB(G, RPT)) fit_struct3_kernel(c
                 dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, s));
             }
             const double dim = (double)(Mrows > N ? Mrows : N);
-            if (!(dmin > 2.220446049250313e-16 * dim * dmax)) status |= QNMFIT_ST_RANK_DEFICIENT_;
+            if (!(dmin > QNMFIT_RANK_FLAG_MARGIN * 2.220446049250313e-16 * dim * dmax)) status |= QNMFIT_ST_RANK_DEFICIENT_;
             if (Mrows <= N) status |= QNMFIT_ST_UNDERDETERMINED_;
             if (p.R) {
                 double2 *Rout = p.R + (long long)fit * N * (N + 1);

@@ -52,11 +52,16 @@ static int cuda_fail(qnmfit_ctx *ctx, cudaError_t e, const char *what)
 
 typedef void (*small_kernel_t)(const FitParams);   // kernels take it as __grid_constant__
 
+// Threads per CTA of K1: one 256-thread CTA per SM while the per-lane factor (N (N+1)/2
+// complex + N real in shared memory) allows it, fewer lanes for the wider factors.
+static constexpr int k1_threads_ct(int N) { return N <= 9 ? K1_THREADS : N == 10 ? 192 : 160; }
+static int k1_threads(int N) { return k1_threads_ct(N); }
+
 template <int N>
 static small_kernel_t small_kernel_for(bool staged)
 {
-    return staged ? (small_kernel_t)fit_small_kernel<N, K1_THREADS, true>
-                  : (small_kernel_t)fit_small_kernel<N, K1_THREADS, false>;
+    return staged ? (small_kernel_t)fit_small_kernel<N, k1_threads_ct(N), true>
+                  : (small_kernel_t)fit_small_kernel<N, k1_threads_ct(N), false>;
 }
 
 static small_kernel_t small_kernel(int N, bool staged)
@@ -70,6 +75,10 @@ static small_kernel_t small_kernel(int N, bool staged)
     case 5: return small_kernel_for<5>(staged);
     case 6: return small_kernel_for<6>(staged);
     case 7: return small_kernel_for<7>(staged);
+    case 9: return small_kernel_for<9>(staged);
+    case 10: return small_kernel_for<10>(staged);
+    case 11: return small_kernel_for<11>(staged);
+    case 12: return small_kernel_for<12>(staged);
 #endif
     case 8: return small_kernel_for<8>(staged);
     }
@@ -92,20 +101,32 @@ static struct_kernel_t struct3_kernel(int G, int RPT)
     return nullptr;
 }
 
+template <int N>
+static size_t small_smem_bytes_for(int fpc, int stage_rows)
+{
+    return SmallSmem<N, k1_threads_ct(N)>::bytes(fpc, stage_rows);
+}
+
 static size_t small_smem_bytes(int N, int fpc, int stage_rows)
 {
     switch (N) {
-    case 1: return SmallSmem<1, K1_THREADS>::bytes(fpc, stage_rows);
-    case 2: return SmallSmem<2, K1_THREADS>::bytes(fpc, stage_rows);
-    case 3: return SmallSmem<3, K1_THREADS>::bytes(fpc, stage_rows);
-    case 4: return SmallSmem<4, K1_THREADS>::bytes(fpc, stage_rows);
-    case 5: return SmallSmem<5, K1_THREADS>::bytes(fpc, stage_rows);
-    case 6: return SmallSmem<6, K1_THREADS>::bytes(fpc, stage_rows);
-    case 7: return SmallSmem<7, K1_THREADS>::bytes(fpc, stage_rows);
-    case 8: return SmallSmem<8, K1_THREADS>::bytes(fpc, stage_rows);
+    case 1: return small_smem_bytes_for<1>(fpc, stage_rows);
+    case 2: return small_smem_bytes_for<2>(fpc, stage_rows);
+    case 3: return small_smem_bytes_for<3>(fpc, stage_rows);
+    case 4: return small_smem_bytes_for<4>(fpc, stage_rows);
+    case 5: return small_smem_bytes_for<5>(fpc, stage_rows);
+    case 6: return small_smem_bytes_for<6>(fpc, stage_rows);
+    case 7: return small_smem_bytes_for<7>(fpc, stage_rows);
+    case 8: return small_smem_bytes_for<8>(fpc, stage_rows);
+    case 9: return small_smem_bytes_for<9>(fpc, stage_rows);
+    case 10: return small_smem_bytes_for<10>(fpc, stage_rows);
+    case 11: return small_smem_bytes_for<11>(fpc, stage_rows);
+    case 12: return small_smem_bytes_for<12>(fpc, stage_rows);
     }
     return 0;
 }
+
+static int small_block_rows(int N) { return N <= 8 ? 4 : N <= 10 ? 3 : 2; }   // SmallLayout<N>::MB
 
 // ---------------------------------------------------------------------------
 // context
@@ -275,7 +296,7 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
         const int stage_rows = Mmax;
         double best = 1e300;
         for (int lpf = 1; lpf <= 32; lpf *= 2) {
-            const int fpc = K1_THREADS / lpf;
+            const int fpc = k1_threads(N) / lpf;
             // CTAs that may be co-resident on an SM by thread count; staging the window
             // must not reduce that (8 warps per SM are needed to keep the FP64 pipe fed)
 #ifdef K1_FORCE_CPS   /* developer experiments (tools/k1_variants.py) */
@@ -294,13 +315,14 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
 #endif
             const int ctas = (b->n_fits + fpc - 1) / fpc;
             const int waves = (ctas + ctx->sm_count * want_cps - 1) / (ctx->sm_count * want_cps);
-            const int rpl = ((Mmax + lpf - 1) / lpf + 3) / 4;
+            const int mb = small_block_rows(N);
+            const int rpl = ((Mmax + lpf - 1) / lpf + mb - 1) / mb;
             const double blocks = rpl * (1.0 + 0.2) /* second pass ~ 20% of a first-pass block */
-                                + ilog2(lpf) * ((N + 3) / 4);
+                                + ilog2(lpf) * ((N + mb - 1) / mb);
             const double cost = (double)(waves > 0 ? waves : 1) * blocks * (staged ? 1.0 : 1.03);
             if (cost < best) {
                 best = cost;
-                pl->lpf = lpf; pl->grid = ctas; pl->block = K1_THREADS; pl->smem = smem; pl->staged = staged;
+                pl->lpf = lpf; pl->grid = ctas; pl->block = k1_threads(N); pl->smem = smem; pl->staged = staged;
                 pl->stage_begin = b->row_begin_all; pl->stage_rows = staged ? stage_rows : 0;
             }
         }

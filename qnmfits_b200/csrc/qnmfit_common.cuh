@@ -195,6 +195,12 @@ QF_HD void note_status(const FitParams &p, int status)
     }
 }
 
+// numpy.linalg.lstsq truncates singular values below eps * max(M, N) * s_max.  The kernels
+// only see the diagonal of R, and min |R_jj| / max |R_jj| can sit several hundred times above
+// s_min / s_max (measured up to 684x on overtone ladders), so the flag is raised with that
+// margin: it means "numpy MAY truncate here"; the host decides with the singular values of
+// the exported factor (qnmfits.py, _minimum_norm_from_factor).
+#define QNMFIT_RANK_FLAG_MARGIN 1024.0
 #define QNMFIT_ST_RANK_DEFICIENT_ 1
 #define QNMFIT_ST_NONFINITE_ 2
 #define QNMFIT_ST_UNDERDETERMINED_ 4

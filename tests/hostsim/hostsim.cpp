@@ -69,7 +69,7 @@ static void run(const qnmfit_batch *b, int lpf, bool eval)
         std::vector<SmallAcc> acc(HS_THREADS);
         for (auto &a : acc) a.sdd = a.res2 = a.cn2 = 0.0;
         for (int tid = 0; tid < HS_THREADS; ++tid) {
-            lanes[tid] = small_lane_setup(p, cta, tid, HS_THREADS);
+            lanes[tid] = small_lane_setup(p, cta, tid, HS_THREADS, true, SmallLayout<N>::MB);
             small_clear<N, HS_THREADS>(sm, tid);
         }
         if (!eval) {
@@ -140,6 +140,10 @@ extern "C" int hostsim_fit_small(const qnmfit_batch *b, int lpf, int eval)
     case 6: run<6>(b, lpf, eval); break;
     case 7: run<7>(b, lpf, eval); break;
     case 8: run<8>(b, lpf, eval); break;
+    case 9: run<9>(b, lpf, eval); break;
+    case 10: run<10>(b, lpf, eval); break;
+    case 11: run<11>(b, lpf, eval); break;
+    case 12: run<12>(b, lpf, eval); break;
     }
     return 0;
 }

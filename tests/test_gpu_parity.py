@@ -250,7 +250,8 @@ def _synthetic_stack(N, L, K_tot, seed, uniform=True):
 
 
 @pytest.mark.parametrize("N,L,use_coef", [(3, 2, True), (12, 1, False), (12, 1, True), (20, 5, True),
-                                           (40, 21, True), (63, 1, False), (9, 7, True)])
+                                           (40, 21, True), (63, 1, False), (9, 7, True), (9, 1, False),
+                                           (10, 1, False), (11, 1, False), (16, 1, False)])
 def test_struct_kernel_vs_oracle_and_general_kernel(qf, eng, N, L, use_coef):
     """K3 (structured two-phase QR) for every lanes-per-column variant, uniform (fast
     mismatch and second pass) and non-uniform grids, against numpy lstsq on the explicit
@@ -276,6 +277,10 @@ def test_struct_kernel_vs_oracle_and_general_kernel(qf, eng, N, L, use_coef):
         variants = [("k3_second_pass", _cabi.KERNEL_STRUCT, False), ("k2", _cabi.KERNEL_GENERAL, False)]
         if uniform:
             variants.insert(0, ("k3_fast", _cabi.KERNEL_STRUCT, True))
+        if N <= _cabi.MAX_MODES_SMALL and L == 1 and not use_coef:   # K1 with 2- or 3-row blocks
+            variants.append(("k1_second_pass", _cabi.KERNEL_SMALL, False))
+            if uniform:
+                variants.append(("k1_fast", _cabi.KERNEL_SMALL, True))
         for name, kernel, fast in variants:
             C_d = eng.empty((1, N), torch.complex128)
             mm_d = eng.empty((1,), torch.float64)
@@ -290,7 +295,8 @@ def test_struct_kernel_vs_oracle_and_general_kernel(qf, eng, N, L, use_coef):
             np.testing.assert_allclose(eng.to_host(res_d)[0], res_ref[0], rtol=1e-6, err_msg=name)
             assert int(eng.to_host(st_d)[0]) == 0, name
         plan = eng.ctx.plan(eng.make_batch(kernel=_cabi.KERNEL_AUTO, mismatch_d=mm_d, **d))
-        assert plan.kernel == (_cabi.KERNEL_STRUCT if (N > 8 or L > 1 or use_coef) else _cabi.KERNEL_SMALL)
+        assert plan.kernel == (_cabi.KERNEL_STRUCT if (N > _cabi.MAX_MODES_SMALL or L > 1 or use_coef)
+                               else _cabi.KERNEL_SMALL)
 
 
 def test_struct_kernel_many_fits_windows_and_eval(qf, eng):

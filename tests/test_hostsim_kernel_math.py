@@ -213,3 +213,42 @@ def test_oracle_free_frequency_fit_vs_reference_golden(golden, oracle_tables):
         w = orc.free_frequency_fit(oracle_tables, wl.times, wl.data[b], 0.0, modes=wl.modes, Mf=wl.Mf,
                                    chif=wl.chif)
         assert abs(w - g["fixed1_omega"][b]) < 1e-12
+
+
+@pytest.mark.parametrize("N", [9, 10, 11, 12])
+def test_wider_factors_use_shorter_blocks(qf, oracle_tables, N):
+    """K1 beyond eight columns: 3-row blocks for N = 9, 10 and 2-row blocks for N = 11, 12
+    (SmallLayout<N>::MB).  Full-rank label sets against the oracle for several lane splits,
+    both mismatch paths, ragged windows and a start-time sweep."""
+    from oracle import qnmfits_oracle as orc
+    wl = workloads.config1()
+    modes = [(2, 2, n, 1) for n in range(8)] + [(3, 2, n, 1) for n in range(N - 8)]
+    w = np.array(qf.qnm.omega_list(modes, 0.69, 0.95))
+    ref = orc.ringdown_fit(oracle_tables, wl.times, wl.data, modes, 0.95, 0.69, 0.0)
+    assert int(ref["rank"]) == N
+    win = api._window_rows(wl.times, 0.0, 100, "geq")
+    for lpf in (1, 4, 32):
+        for uw in (0, 1):
+            out = hs.run(wl.times, wl.data, n_fits=1, n_modes=N, window=win, t0=0.0, lpf=lpf,
+                         omega=w.reshape(1, -1), omega_shared=True, uniform_weights=uw)
+            err = np.max(np.abs(out["C"][0] - ref["C"])) / np.max(np.abs(ref["C"]))
+            assert err < cases.amp_tol(ref["s"]), (lpf, uw, err)
+            assert abs(out["mismatch"][0] - ref["mismatch"]) < 1e-10
+            assert out["status"][0] == 0
+    for M in (N + 1, 23, 64, 101):                       # windows that are no multiple of the block height
+        rb, re = 500, 500 + M
+        a, C, r, rank, s, model = orc.lstsq_fit(wl.times[rb:re], wl.data[rb:re], w, 0.0)
+        want = orc.mismatch(wl.times[rb:re], model, wl.data[rb:re])
+        for lpf in (1, 2, 8):
+            out = hs.run(wl.times, wl.data, n_fits=1, n_modes=N, window=(rb, re), t0=0.0, lpf=lpf,
+                         omega=w.reshape(1, -1), omega_shared=True)
+            if rank == N and s[-1] > 1e-9 * s[0]:
+                assert abs(out["mismatch"][0] - want) < 1e-10 and out["status"][0] == 0, (M, lpf)
+            elif rank < N:                               # numpy truncates: the device must flag the fit
+                assert out["status"][0] != 0, (M, lpf)
+    t0s = np.linspace(-3.0, 12.0, 7)
+    begin, end = api._window_rows_many(wl.times, t0s, 100 * np.ones(7), "geq")
+    out = hs.run(wl.times, wl.data, n_fits=7, n_modes=N, window=(begin, end), t0=t0s, lpf=8,
+                 omega=w.reshape(1, -1), omega_shared=True, uniform_weights=1)
+    want = orc.mismatch_t0_array(oracle_tables, wl.times, wl.data, modes, 0.95, 0.69, t0s)
+    np.testing.assert_allclose(out["mismatch"], want, rtol=0, atol=1e-10)
