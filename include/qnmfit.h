@@ -46,7 +46,7 @@ extern "C" {
 
 /* limits of the compiled kernels */
 #define QNMFIT_MAX_MODES_SMALL 12    /* register-resident TSQR kernel (K1): 4-row blocks
-                                        up to 8 columns, 3 rows for 9-10, 2 rows for 11-12 */
+                                        up to 8 columns, 3-row blocks for 9-12          */
 #define QNMFIT_DEFAULT_ANCHOR_ROWS 256 /* measured on B200: accuracy is flat from 16 to 512 rows */
 #define QNMFIT_MAX_MODES 64          /* CTA-cooperative general kernel (K2)  */
 

@@ -35,11 +35,16 @@
 #define QNMFIT_SPLIT_COLS 0   /* measured on B200: splitting costs registers and is slower */
 #endif
 
+#ifndef QNMFIT_MB3_MAX_N
+#define QNMFIT_MB3_MAX_N 12   /* measured on B200: 3-row blocks beat 2-row blocks at N = 11, 12 (+8 %, +6 %) despite spills */
+#endif
+
 template <int N>
 struct SmallLayout {
     // rows per register block: the block [MB x (N+1)] complex lives in registers next to the
-    // generator state (N complex) and the dot-product accumulators (2 (N+1) doubles)
-    static constexpr int MB = N <= 8 ? 4 : N <= 10 ? 3 : 2;
+    // generator state (N complex) and the dot-product accumulators (2 (N+1) doubles): four
+    // rows up to eight columns, three beyond (two is the fallback form, QNMFIT_MB3_MAX_N)
+    static constexpr int MB = N <= 8 ? 4 : N <= QNMFIT_MB3_MAX_N ? 3 : 2;
     static constexpr int NC = N + 1;                  // columns incl. right-hand side
     static constexpr int NP = N * (N + 1) / 2;        // strictly-upper entries incl. rhs column
     // index of R[j][k], j < k <= N (k == N is the rhs column)

@@ -126,7 +126,7 @@ static size_t small_smem_bytes(int N, int fpc, int stage_rows)
     return 0;
 }
 
-static int small_block_rows(int N) { return N <= 8 ? 4 : N <= 10 ? 3 : 2; }   // SmallLayout<N>::MB
+static int small_block_rows(int N) { return N <= 8 ? 4 : N <= QNMFIT_MB3_MAX_N ? 3 : 2; }   // SmallLayout<N>::MB
 
 // ---------------------------------------------------------------------------
 // context

@@ -1,20 +1,31 @@
-import sys, os, json
-sys.path.insert(0, os.getcwd())
-import torch
-from qnmfits_b200 import workloads, _cabi
-from qnmfits_b200 import qnmfits as api
+#!/usr/bin/env python
+"""Developer tool (GPU box): kernel time of a single-series 128 x 128 Mf-chi grid (16384 fits,
+M = 1000) for N = 8 .. 24 columns: where K1 hands over to K3."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from qnmfits_b200 import workloads, _cabi  # noqa: E402
+from qnmfits_b200 import qnmfits as api  # noqa: E402
+
 workloads.use_synthetic_tables()
 wl = workloads.config3(res=128)
-for N in (8, 9, 10, 12, 16, 24):
-    modes = [(2, 2, n, 1) for n in range(min(N, 12))] + [(3, 2, n, 1) for n in range(max(0, N - 12))]
+for N in [int(a) for a in sys.argv[1:]] or (8, 9, 10, 11, 12, 16, 24):
+    modes = [(2, 2, n, 1) for n in range(min(N, 9))] + [(3, 2, n, 1) for n in range(max(0, N - 9))]
     sweep, shape = api._prepare_M_chi_grid(wl.times, wl.data, modes, wl.Mf_minmax, wl.chif_minmax, wl.t0, T=wl.T, res=128)
-    for _ in range(2): sweep.launch()
+    for _ in range(2):
+        sweep.launch()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(3): sweep.launch_kernel()
-    e1.record(); torch.cuda.synchronize()
+    for _ in range(3):
+        sweep.launch_kernel()
+    e1.record()
+    torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
     plan = sweep.eng.ctx.plan(sweep.batch)
     fl = _cabi.flops_per_fit(sweep.rows_max, N, 1, True) * 16384
-    print(N, 'kernel', plan.kernel, 'ms %.3f' % ms, 'fits/s %.3g' % (16384 / ms * 1e3), 'TF %.2f' % (fl / ms * 1e-9), 'block', plan.block, 'regs', plan.regs_per_thread, flush=True)
+    print(N, 'kernel', plan.kernel, 'ms %.3f' % ms, 'fits/s %.3g' % (16384 / ms * 1e3), 'TF %.2f' % (fl / ms * 1e-9),
+          'block', plan.block, 'lpf', plan.lanes_per_fit, 'regs', plan.regs_per_thread, flush=True)
