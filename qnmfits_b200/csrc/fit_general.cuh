@@ -54,13 +54,6 @@ struct GeneralSmem {
     }
 };
 
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-    return v;
-}
-
 // tile_rows / time_chunk are chosen by the host: TK = max(1, TR / L), rows used = TK * L.
 __global__ void __launch_bounds__(K2_THREADS, 1)
 fit_general_kernel(const __grid_constant__ FitParams p, const int TR, const int TK)

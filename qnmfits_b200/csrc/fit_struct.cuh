@@ -36,7 +36,6 @@
 // sweeps (G, RPT) through QNMFIT_K3G.
 #pragma once
 #include "qnmfit_common.cuh"
-#include "fit_general.cuh"
 
 #ifndef QNMFIT_HOSTSIM
 

@@ -8,15 +8,10 @@
 #include <stdio.h>
 #include <string.h>
 
-#include "qnmfit.h"
-#include "fit_small.cuh"
-#include "fit_general.cuh"
-#include "fit_struct.cuh"
 #include <stdlib.h>
 
-#ifndef K1_THREADS
-#define K1_THREADS 256
-#endif
+#include "qnmfit.h"
+#include "kernels.h"
 
 struct qnmfit_ctx {
     int k3_g, k3_rpt;        // K3: lanes per column, rows per thread (developer knob QNMFIT_K3G="G,RPT")
@@ -46,87 +41,6 @@ static int cuda_fail(qnmfit_ctx *ctx, cudaError_t e, const char *what)
 {
     return fail(ctx, (int)e, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
 }
-
-// ---------------------------------------------------------------------------
-// kernel tables
-
-typedef void (*small_kernel_t)(const FitParams);   // kernels take it as __grid_constant__
-
-// Threads per CTA of K1: one 256-thread CTA per SM while the per-lane factor (N (N+1)/2
-// complex + N real in shared memory) allows it, fewer lanes for the wider factors.
-static constexpr int k1_threads_ct(int N) { return N <= 9 ? K1_THREADS : N == 10 ? 192 : 160; }
-static int k1_threads(int N) { return k1_threads_ct(N); }
-
-template <int N>
-static small_kernel_t small_kernel_for(bool staged)
-{
-    return staged ? (small_kernel_t)fit_small_kernel<N, k1_threads_ct(N), true>
-                  : (small_kernel_t)fit_small_kernel<N, k1_threads_ct(N), false>;
-}
-
-static small_kernel_t small_kernel(int N, bool staged)
-{
-    switch (N) {
-#ifndef QNMFIT_ONLY_N8
-    case 1: return small_kernel_for<1>(staged);
-    case 2: return small_kernel_for<2>(staged);
-    case 3: return small_kernel_for<3>(staged);
-    case 4: return small_kernel_for<4>(staged);
-    case 5: return small_kernel_for<5>(staged);
-    case 6: return small_kernel_for<6>(staged);
-    case 7: return small_kernel_for<7>(staged);
-    case 9: return small_kernel_for<9>(staged);
-    case 10: return small_kernel_for<10>(staged);
-    case 11: return small_kernel_for<11>(staged);
-    case 12: return small_kernel_for<12>(staged);
-#endif
-    case 8: return small_kernel_for<8>(staged);
-    }
-    return nullptr;
-}
-
-typedef void (*struct_kernel_t)(const FitParams);
-
-#define K3C_DEFAULT_G 4
-#define K3C_DEFAULT_RPT 16
-
-static struct_kernel_t struct3_kernel(int G, int RPT)
-{
-    if (G == 1 && RPT == 32) return fit_struct3_kernel<1, 32>;
-    if (G == 2 && RPT == 16) return fit_struct3_kernel<2, 16>;
-    if (G == 2 && RPT == 32) return fit_struct3_kernel<2, 32>;
-    if (G == 4 && RPT == 8) return fit_struct3_kernel<4, 8>;
-    if (G == 4 && RPT == 16) return fit_struct3_kernel<4, 16>;
-    if (G == 8 && RPT == 8) return fit_struct3_kernel<8, 8>;
-    return nullptr;
-}
-
-template <int N>
-static size_t small_smem_bytes_for(int fpc, int stage_rows)
-{
-    return SmallSmem<N, k1_threads_ct(N)>::bytes(fpc, stage_rows);
-}
-
-static size_t small_smem_bytes(int N, int fpc, int stage_rows)
-{
-    switch (N) {
-    case 1: return small_smem_bytes_for<1>(fpc, stage_rows);
-    case 2: return small_smem_bytes_for<2>(fpc, stage_rows);
-    case 3: return small_smem_bytes_for<3>(fpc, stage_rows);
-    case 4: return small_smem_bytes_for<4>(fpc, stage_rows);
-    case 5: return small_smem_bytes_for<5>(fpc, stage_rows);
-    case 6: return small_smem_bytes_for<6>(fpc, stage_rows);
-    case 7: return small_smem_bytes_for<7>(fpc, stage_rows);
-    case 8: return small_smem_bytes_for<8>(fpc, stage_rows);
-    case 9: return small_smem_bytes_for<9>(fpc, stage_rows);
-    case 10: return small_smem_bytes_for<10>(fpc, stage_rows);
-    case 11: return small_smem_bytes_for<11>(fpc, stage_rows);
-    case 12: return small_smem_bytes_for<12>(fpc, stage_rows);
-    }
-    return 0;
-}
-
-static int small_block_rows(int N) { return N <= 8 ? 4 : N <= QNMFIT_MB3_MAX_N ? 3 : 2; }   // SmallLayout<N>::MB
 
 // ---------------------------------------------------------------------------
 // context
@@ -161,31 +75,25 @@ extern "C" int qnmfit_create(int device, qnmfit_ctx **out)
     ctx->err[0] = 0;
     ctx->k3_g = K3C_DEFAULT_G; ctx->k3_rpt = K3C_DEFAULT_RPT;
     { const char *eg = getenv("QNMFIT_K3G"); int g2 = 0, r2 = 0;
-      if (eg && sscanf(eg, "%d,%d", &g2, &r2) == 2 && struct3_kernel(g2, r2)) { ctx->k3_g = g2; ctx->k3_rpt = r2; } }
+      if (eg && sscanf(eg, "%d,%d", &g2, &r2) == 2 && k3_kernel_ptr(g2, r2)) { ctx->k3_g = g2; ctx->k3_rpt = r2; } }
     if ((e = cudaSetDevice(device)) != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaSetDevice"); delete ctx; return r; }
     // opt every kernel in to the full shared-memory carve-out once
     for (int N = 1; N <= QNMFIT_MAX_MODES_SMALL; ++N)
         for (int st = 0; st < 2; ++st) {
-            if (!small_kernel(N, st != 0)) continue;
-            e = cudaFuncSetAttribute((const void *)small_kernel(N, st != 0),
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+            if (!k1_kernel_ptr(N, st != 0)) continue;
+            e = cudaFuncSetAttribute(k1_kernel_ptr(N, st != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
             if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaFuncSetAttribute(K1)"); delete ctx; return r; }
         }
-    e = cudaFuncSetAttribute((const void *)fit_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             ctx->smem_optin);
+    e = cudaFuncSetAttribute(k2_kernel_ptr(), cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
     if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaFuncSetAttribute(K2)"); delete ctx; return r; }
-    {
-        static const int forms[6][2] = {{1, 32}, {2, 16}, {2, 32}, {4, 8}, {4, 16}, {8, 8}};
-        for (int f = 0; f < 6; ++f) {
-            e = cudaFuncSetAttribute((const void *)struct3_kernel(forms[f][0], forms[f][1]),
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
-            if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaFuncSetAttribute(K3c)"); delete ctx; return r; }
-            // ~45 KB per fit: ask for the full shared-memory carve-out so that 4-5 fits share an SM
-            // (the driver's default carve-out for a block of this size admits only two)
-            e = cudaFuncSetAttribute((const void *)struct3_kernel(forms[f][0], forms[f][1]),
-                                     cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaFuncSetAttribute(K3c carve-out)"); delete ctx; return r; }
-        }
+    for (int f = 0; f < K3_FORMS; ++f) {
+        const void *k3 = k3_kernel_ptr(k3_forms[f][0], k3_forms[f][1]);
+        e = cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+        if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaFuncSetAttribute(K3c)"); delete ctx; return r; }
+        // ~45 KB per fit: ask for the full shared-memory carve-out so that 4-5 fits share an SM
+        // (the driver's default carve-out for a block of this size admits only two)
+        e = cudaFuncSetAttribute(k3, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaFuncSetAttribute(K3c carve-out)"); delete ctx; return r; }
     }
     *out = ctx;
     return 0;
@@ -275,7 +183,7 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
     const bool small_ok = b->n_series == 1 && b->n_modes <= QNMFIT_MAX_MODES_SMALL && !b->coef
         && !b->omega_rows && !b->coef_rows;
     const bool struct_ok = !b->coef_rows && b->n_modes + b->n_series <= 64
-        && Struct3Smem::bytes(b->n_modes, b->n_series) <= (size_t)ctx->smem_optin;
+        && k3_smem_bytes(b->n_modes, b->n_series) <= (size_t)ctx->smem_optin;
     if (kernel == QNMFIT_KERNEL_AUTO)
         kernel = small_ok ? QNMFIT_KERNEL_SMALL : struct_ok ? QNMFIT_KERNEL_STRUCT : QNMFIT_KERNEL_GENERAL;
     if (kernel == QNMFIT_KERNEL_STRUCT && !struct_ok)
@@ -305,17 +213,17 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
             const int want_cps = 256 / K1_THREADS > 0 ? 256 / K1_THREADS : 1;
 #endif
             const size_t per_cta = ((size_t)ctx->smem_optin + 1024) / want_cps - 1024;
-            size_t smem = small_smem_bytes(N, fpc, stage_rows);
+            size_t smem = k1_smem_bytes(N, fpc, stage_rows);
             bool staged = b->series_index == nullptr;   // per-fit series are read through L1/L2
-            if (!staged) smem = small_smem_bytes(N, fpc, 0);
-            if (staged && smem > per_cta) { staged = false; smem = small_smem_bytes(N, fpc, 0); }
+            if (!staged) smem = k1_smem_bytes(N, fpc, 0);
+            if (staged && smem > per_cta) { staged = false; smem = k1_smem_bytes(N, fpc, 0); }
             if (smem > per_cta) continue;
 #ifdef K1_FORCE_CPS
             if (smem < per_cta * 6 / 10) smem = per_cta * 6 / 10;   // pad so that no more CTAs become resident
 #endif
             const int ctas = (b->n_fits + fpc - 1) / fpc;
             const int waves = (ctas + ctx->sm_count * want_cps - 1) / (ctx->sm_count * want_cps);
-            const int mb = small_block_rows(N);
+            const int mb = k1_block_rows(N);
             const int rpl = ((Mmax + lpf - 1) / lpf + mb - 1) / mb;
             const double blocks = rpl * (1.0 + 0.2) /* second pass ~ 20% of a first-pass block */
                                 + ilog2(lpf) * ((N + mb - 1) / mb);
@@ -329,7 +237,7 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
         if (best >= 1e300) return fail(ctx, QNMFIT_E_SHAPE, "K1: no lanes-per-fit choice fits shared memory");
     } else if (kernel == QNMFIT_KERNEL_STRUCT) {
         pl->lpf = ctx->k3_g; pl->TR = ctx->k3_g * ctx->k3_rpt;
-        pl->smem = Struct3Smem::bytes(b->n_modes, b->n_series);
+        pl->smem = k3_smem_bytes(b->n_modes, b->n_series);
         pl->grid = b->n_fits; pl->block = ctx->k3_g * 32 * ((b->n_modes + b->n_series + 31) / 32);
     } else {
         const int L = b->n_series;
@@ -337,7 +245,7 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
         while (TR >= 32) {
             if (TR >= L) {
                 const int TK = TR / L > 0 ? TR / L : 1;
-                size_t smem = GeneralSmem::bytes(N, L, TR, TK);
+                size_t smem = k2_smem_bytes(N, L, TR, TK);
                 if (smem <= (size_t)ctx->smem_optin) {
                     pl->TR = TR; pl->TK = TK; pl->smem = smem;
                     break;
@@ -425,19 +333,16 @@ static int launch(qnmfit_ctx *ctx, const qnmfit_batch *b, void *stream, bool eva
     if (b->n_fits == 0) {
         // empty slab: only the barrier below
     } else if (pl.kernel == QNMFIT_KERNEL_SMALL) {
-        small_kernel_t k = small_kernel(b->n_modes, pl.staged);
-        k<<<pl.grid, pl.block, pl.smem, st>>>(p);
+        e = k1_launch(b->n_modes, pl.staged, pl.grid, pl.block, pl.smem, st, p);
     } else if (pl.kernel == QNMFIT_KERNEL_STRUCT) {
-        struct3_kernel(ctx->k3_g, ctx->k3_rpt)<<<pl.grid, pl.block, pl.smem, st>>>(p);
+        e = k3_launch(ctx->k3_g, ctx->k3_rpt, pl.grid, pl.block, pl.smem, st, p);
     } else {
-        fit_general_kernel<<<pl.grid, pl.block, pl.smem, st>>>(p, pl.TR, pl.TK);
+        e = k2_launch(pl.grid, pl.smem, st, p, pl.TR, pl.TK);
     }
-    e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(ctx, e, "kernel launch");
     if (b->n_fits > 0) ctx->launches += 1;
     if (pe) {
-        peer_barrier_kernel<<<1, 32, 0, st>>>(p);
-        if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(ctx, e, "peer barrier launch");
+        if ((e = peer_barrier_launch(st, p)) != cudaSuccess) return cuda_fail(ctx, e, "peer barrier launch");
         ctx->launches += 1;
     }
     return 0;
@@ -584,9 +489,8 @@ extern "C" int qnmfit_plan_batch(qnmfit_ctx *ctx, const qnmfit_batch *b, qnmfit_
     out->smem_bytes = (int32_t)pl.smem; out->staged = pl.staged ? 1 : 0;
     out->fast_mismatch = (pl.kernel != QNMFIT_KERNEL_GENERAL && b->uniform_weights && b->dt_nominal > 0.0 && !b->model) ? 1 : 0;
     cudaFuncAttributes fa;
-    const void *fn = pl.kernel == QNMFIT_KERNEL_SMALL ? (const void *)small_kernel(b->n_modes, pl.staged)
-                   : pl.kernel == QNMFIT_KERNEL_STRUCT ? (const void *)struct3_kernel(ctx->k3_g, ctx->k3_rpt)
-                                                       : (const void *)fit_general_kernel;
+    const void *fn = pl.kernel == QNMFIT_KERNEL_SMALL ? k1_kernel_ptr(b->n_modes, pl.staged)
+                   : pl.kernel == QNMFIT_KERNEL_STRUCT ? k3_kernel_ptr(ctx->k3_g, ctx->k3_rpt) : k2_kernel_ptr();
     cudaError_t e = cudaFuncGetAttributes(&fa, fn);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaFuncGetAttributes");
     out->regs_per_thread = fa.numRegs;
@@ -594,93 +498,7 @@ extern "C" int qnmfit_plan_batch(qnmfit_ctx *ctx, const qnmfit_batch *b, qnmfit_
 }
 
 // ---------------------------------------------------------------------------
-// FP64 peak micro-benchmarks (the roofline denominator; MEASURED_PEAKS.json has no
-// FP64 entry).  Eight independent dependent-FMA chains per thread / four MMA
-// accumulators per warp; results are stored so nothing is optimised away.
-
-__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double b, double c)
-{
-    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
-           a6 = a0 + 6, a7 = a0 + 7;
-    for (int i = 0; i < iters; ++i) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
-            a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
-        }
-    }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
-}
-
-// DFMA whose three source operands are all distinct registers and never repeat in the
-// same operand slot of consecutive instructions (no operand-reuse-cache hits): the rate
-// the register file can feed, which is what bounds register-blocked FP64 code like the
-// Householder updates of K1/K2.
-__global__ void __launch_bounds__(256) dfma_3op_kernel(double *out, int iters, double b, double c)
-{
-    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
-           a6 = a0 + 6, a7 = a0 + 7;
-    double b0 = b, b1 = b + 1e-9, b2 = b + 2e-9, b3 = b + 3e-9, b4 = b + 4e-9, b5 = b + 5e-9, b6 = b + 6e-9,
-           b7 = b + 7e-9;
-    double c0 = c, c1 = c * 2, c2 = c * 3, c3 = c * 4, c4 = c * 5, c5 = c * 6, c6 = c * 7, c7 = c * 8;
-    for (int i = 0; i < iters; ++i) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a0) : "d"(b0), "d"(c0));
-            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a1) : "d"(b1), "d"(c1));
-            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a2) : "d"(b2), "d"(c2));
-            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a3) : "d"(b3), "d"(c3));
-            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a4) : "d"(b4), "d"(c4));
-            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a5) : "d"(b5), "d"(c5));
-            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a6) : "d"(b6), "d"(c6));
-            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a7) : "d"(b7), "d"(c7));
-        }
-    }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
-}
-
-// Same, but the multiplier is shared by consecutive instructions (one operand served by
-// the reuse cache, two register reads per DFMA) — the pattern of a rank-1 update.
-__global__ void __launch_bounds__(256) dfma_2op_kernel(double *out, int iters, double b, double c)
-{
-    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
-           a6 = a0 + 6, a7 = a0 + 7;
-    double c0 = c, c1 = c * 2, c2 = c * 3, c3 = c * 4, c4 = c * 5, c5 = c * 6, c6 = c * 7, c7 = c * 8;
-    for (int i = 0; i < iters; ++i) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a0) : "d"(b), "d"(c0));
-            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a1) : "d"(b), "d"(c1));
-            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a2) : "d"(b), "d"(c2));
-            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a3) : "d"(b), "d"(c3));
-            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a4) : "d"(b), "d"(c4));
-            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a5) : "d"(b), "d"(c5));
-            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a6) : "d"(b), "d"(c6));
-            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a7) : "d"(b), "d"(c7));
-        }
-    }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
-}
-
-__global__ void __launch_bounds__(256) dmma_peak_kernel(double *out, int iters, double b, double c)
-{
-    double a = threadIdx.x * 1e-3 + 0.5, bb = b;
-    double c00 = c, c01 = c, c10 = c + 1, c11 = c + 1, c20 = c + 2, c21 = c + 2, c30 = c + 3, c31 = c + 3;
-    for (int i = 0; i < iters; ++i) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                         : "+d"(c00), "+d"(c01) : "d"(a), "d"(bb));
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                         : "+d"(c10), "+d"(c11) : "d"(a), "d"(bb));
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                         : "+d"(c20), "+d"(c21) : "d"(a), "d"(bb));
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                         : "+d"(c30), "+d"(c31) : "d"(a), "d"(bb));
-        }
-    }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = ((c00 + c01) + (c10 + c11)) + ((c20 + c21) + (c30 + c31));
-}
+// FP64 peak micro-benchmarks (kernels in misc_kernels.cu)
 
 extern "C" int qnmfit_fp64_peak(qnmfit_ctx *ctx, int kind, int iters, double *tflops)
 {
@@ -701,10 +519,7 @@ extern "C" int qnmfit_fp64_peak(qnmfit_ctx *ctx, int kind, int iters, double *tf
     float best_ms = 1e30f;
     for (int rep = 0; rep < 6; ++rep) {   // first reps warm up; best of the rest
         cudaEventRecord(ev0, 0);
-        if (kind == 0) dfma_peak_kernel<<<grid, block>>>(out, iters, 0.999999, 1e-9);
-        else if (kind == 2) dfma_3op_kernel<<<grid, block>>>(out, iters, 0.999999, 1e-9);
-        else if (kind == 3) dfma_2op_kernel<<<grid, block>>>(out, iters, 0.999999, 1e-9);
-        else dmma_peak_kernel<<<grid, block>>>(out, iters, 0.999999, 1e-9);
+        if ((e = fp64_peak_launch(kind, grid, block, out, iters)) != cudaSuccess) break;
         cudaEventRecord(ev1, 0);
         e = cudaEventSynchronize(ev1);
         if (e != cudaSuccess) break;
@@ -719,6 +534,7 @@ extern "C" int qnmfit_fp64_peak(qnmfit_ctx *ctx, int kind, int iters, double *tf
     if (e != cudaSuccess) return cuda_fail(ctx, e, "fp64 peak kernel");
     double flops;
     if (kind == 0 || kind == 2 || kind == 3) flops = 2.0 * 64.0 * (double)iters * (double)grid * block;   // 8 chains x 8 unroll
+    else if (kind == 4) flops = (2.0 * 64.0 * block + 2.0 * 256.0 * 16.0 * (block / 32)) * (double)iters * (double)grid;
     else flops = 2.0 * 256.0 * 32.0 * (double)iters * (double)grid * (block / 32);        // 32 MMAs x 256 FMA
     *tflops = flops / (best_ms * 1e-3) * 1e-12;
     return 0;

@@ -226,6 +226,14 @@ QF_DEV unsigned long long qf_globaltimer()
     return t;
 }
 
+// fixed-order butterfly sum over the 32 lanes of a warp
+QF_DEV double warp_sum(double v)
+{
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    return v;
+}
+
 QF_DEV void peer_publish(const FitParams &p, int fit, double mm)
 {
     if (p.n_peers <= 1) return;
@@ -234,6 +242,7 @@ QF_DEV void peer_publish(const FitParams &p, int fit, double mm)
         if (r != p.peer_rank) p.peer_mismatch[r][gi] = mm;
 }
 
+#ifdef QNMFIT_DEFINE_PEER_BARRIER   /* defined once, in misc_kernels.cu */
 __global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant__ FitParams p)
 {
     const int W = p.n_peers, me = p.peer_rank, r = threadIdx.x;
@@ -261,6 +270,7 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant_
     }
     __threadfence_system();
 }
+#endif  // QNMFIT_DEFINE_PEER_BARRIER
 #else
 static inline void peer_publish(const FitParams &, int, double) {}
 #endif

@@ -5,5 +5,11 @@ set -e
 cd "$(dirname "$0")/.."
 name=$1; shift
 mkdir -p tools/_variants
-nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared \
-  -Iinclude -Iqnmfits_b200/csrc -DQNMFIT_ONLY_N8 "$@" -o tools/_variants/libqnmfit_$name.so qnmfits_b200/csrc/qnmfit_api.cu
+python - "$name" "$@" <<'PY'
+import sys, os
+sys.path.insert(0, os.getcwd())
+import __graft_entry__ as ge
+name, flags = sys.argv[1], sys.argv[2:]
+ge.build_library(force=True, extra_flags=flags, lib=os.path.join("tools", "_variants", f"libqnmfit_{name}.so"),
+                 build_dir=os.path.join("build", "variant_" + name))
+PY
