@@ -212,6 +212,8 @@ def multimode_ringdown_fit(tables, times, data_dict, modes, Mf, chif, t0,
         mu_lists = [tables.mu_list([lm + mode for mode in modes], chif)
                     for lm in spherical_modes]
     else:
+        if callable(coef_override):                  # spin-dependent columns (grids)
+            coef_override = coef_override(chif)
         mu_lists = [list(row) for row in coef_override]
     a, C, res, rank, s, model = lstsq_fit(t_m, stacked, frequencies, t0, mu_lists)
     K = len(t_m)
@@ -228,7 +230,7 @@ def multimode_ringdown_fit(tables, times, data_dict, modes, Mf, chif, t0,
 
 
 def mismatch_t0_array(tables, times, data, modes, Mf, chif, t0_array, t0_method='geq',
-                      T_array=100, spherical_modes=None, delta=0.0):
+                      T_array=100, spherical_modes=None, delta=0.0, coef_override=None):
     """qnmfits/qnmfits.py:1259-1301 (fixed-spectrum branch only)."""
     if type(T_array) != np.ndarray:
         T_array = T_array * np.ones(len(t0_array))
@@ -236,7 +238,7 @@ def mismatch_t0_array(tables, times, data, modes, Mf, chif, t0_array, t0_method=
     for t0, T in zip(t0_array, T_array):
         if type(data) == dict:
             fit = multimode_ringdown_fit(tables, times, data, modes, Mf, chif, t0,
-                                         t0_method, T, spherical_modes)
+                                         t0_method, T, spherical_modes, coef_override)
         else:
             fit = ringdown_fit(tables, times, data, modes, Mf, chif, t0, t0_method,
                                T, delta)
@@ -252,7 +254,7 @@ def grid_axes(Mf_minmax, chif_minmax, res):
 
 def mismatch_M_chi_grid(tables, times, data, modes, Mf_minmax, chif_minmax, t0,
                         t0_method='geq', T=100, res=50, spherical_modes=None,
-                        delta=0.0, flat_indices=None):
+                        delta=0.0, flat_indices=None, coef_override=None):
     """qnmfits/qnmfits.py:1382-1415.
 
     ``flat_indices`` restricts the loop to a subset of the res*res flat indices (the
@@ -268,7 +270,7 @@ def mismatch_M_chi_grid(tables, times, data, modes, Mf_minmax, chif_minmax, t0,
         chif = chif_array[i % len(chif_array)]
         if type(data) is dict:
             fit = multimode_ringdown_fit(tables, times, data, modes, Mf, chif, t0,
-                                         t0_method, T, spherical_modes)
+                                         t0_method, T, spherical_modes, coef_override)
         else:
             fit = ringdown_fit(tables, times, data, modes, Mf, chif, t0, t0_method,
                                T, delta)

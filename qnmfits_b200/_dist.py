@@ -4,9 +4,12 @@ Index sharding of sweeps over the ranks of a ``torch.distributed`` job.
 The reference treats every grid point / start time as an independent loop iteration
 (reference qnmfits/qnmfits.py:1271-1281, :1391-1410), so the flat fit index is split
 into one contiguous slab per rank with no data-path exchange; the only collective is
-the all-gather of the per-fit mismatches (NCCL over NVLink on GPUs; gloo in the CPU
-tests of this logic).  A fit's arithmetic never depends on which rank or CTA runs
-it, so the gathered result is bit-identical to the single-GPU one.
+the exchange of the per-fit mismatches (fused into the fit kernels over peer-mapped memory,
+or an NCCL all-gather; gloo in the CPU tests of this logic).  A fit's arithmetic — including
+the number of lanes that share it and the order in which their partial factors are combined
+— is a function of the fit's own shape (rows, columns) only, never of the slab, rank or CTA
+that runs it (qnmfit_api.cu, make_plan), so the gathered result is bit-identical to the
+single-GPU one (tests/test_gpu_peer.py, test_gpu_parity.py::test_slab_launches...).
 """
 import os
 
@@ -126,7 +129,7 @@ class PeerWindow:
         self.view = torch.as_tensor(_DeviceMemory(self.local_ptr, self.n_words), device=eng.device)
         self.epoch = 0
         self._peers = {}
-        self.timeout_ns = int(float(os.environ.get("QNMFITS_B200_PEER_TIMEOUT_S", "30")) * 1e9)
+        self.timeout_ns = int(float(os.environ.get("QNMFITS_B200_PEER_TIMEOUT_S", "600")) * 1e9)
 
     def _slot_base(self, slot):
         return self.WORDS_HEAD + slot * self.slot_words

@@ -86,6 +86,33 @@ def uniform_weights(times, dt, steps=None):
     return bool(np.max(np.abs(steps - dt)) <= 1e-11 * dt)
 
 
+def pack_layout(sizes, direct_bytes, zero_head=0):
+    """Byte offsets of a packed upload (``Engine.upload_packed``): pure arithmetic, unit-tested
+    on the CPU.  ``sizes``: byte counts (None = absent array).  Arrays of ``direct_bytes`` or
+    more go first (each copied from its own memory); the others form ONE staged group behind
+    them, 256-byte aligned each, closed by ``zero_head`` zero bytes; the result region starts
+    right after the staged group.  Returns (offsets, stage_begin, stage_end, out_offset) with
+    ``out_offset == stage_end`` and, when ``zero_head`` > 0, the zero bytes at
+    ``[out_offset - zero_head, out_offset)``."""
+    if zero_head % 16:
+        raise ValueError("zero_head must be a multiple of 16")
+    offsets, total = [None] * len(sizes), 0
+    big = [i for i, n in enumerate(sizes) if n is not None and n >= direct_bytes]
+    for i in big:
+        total = (total + 255) // 256 * 256
+        offsets[i] = total
+        total += sizes[i]
+    stage_begin = total = (total + 255) // 256 * 256
+    for i, n in enumerate(sizes):
+        if n is None or i in big:
+            continue
+        total = (total + 255) // 256 * 256
+        offsets[i] = total
+        total += n
+    total = (total + 15) // 16 * 16 + zero_head
+    return offsets, stage_begin, total, total
+
+
 class Engine:
     def __init__(self, device):
         import torch
@@ -139,46 +166,40 @@ class Engine:
             buf = self._pinned_bufs[name] = (t, t.numpy(), t.data_ptr())
         return buf[1], buf[2]
 
-    def upload_packed(self, arrays, out_bytes=0, stream=None):
+    def upload_packed(self, arrays, out_bytes=0, stream=None, zero_head=0):
         """Copy several host arrays to the device with ONE cudaMemcpyAsync.
 
         ``arrays`` is a list of C-contiguous numpy arrays (or None).  They are packed,
-        256-byte aligned (the last one unpadded), into a pinned staging buffer and copied
-        into one freshly allocated device buffer, which also gets ``out_bytes`` of
-        (uninitialised) room for results behind the last array, 16-byte aligned.  Returns
-        (device_buffer, [device pointer or None, ...], pointer of the result region).
+        256-byte aligned, into a pinned staging buffer and copied into one freshly
+        allocated device buffer, which also gets ``out_bytes`` of (uninitialised) room for
+        results behind everything else, 16-byte aligned.  ``zero_head`` (a multiple of 16)
+        bytes of zeros travel with the staged copy and sit IMMEDIATELY in front of the
+        result region, whatever the sizes of the arrays (``pack_layout``): a sweep keeps its
+        counter of flagged fits there, so that [counter | results] comes back in one copy.
+        Returns (device_buffer, [device pointer or None, ...], pointer of the result region).
         The staging buffer is reused by the next call, which first waits until the
         previous copy has left it (``qnmfit_h2d_wait``).  Arrays of ``DIRECT_BYTES`` or
-        more are not staged: they are copied from their own (pageable) memory.
+        more are not staged: they are copied from their own (pageable) memory into the
+        front of the device buffer.
         """
-        # Arrays of several MB (a whole catalogue of waveforms) go straight from their own
-        # memory, behind the staged ones: staging them would cost a second host copy and a
-        # pinned buffer of that size.
-        offsets, total = [None] * len(arrays), 0
-        big = [i for i, a in enumerate(arrays) if a is not None and a.nbytes >= self.DIRECT_BYTES]
-        for group in ([i for i in range(len(arrays)) if i not in big], big):
-            for i in group:
-                if arrays[i] is None:
-                    continue
-                total = (total + 255) // 256 * 256
-                offsets[i] = total
-                total += arrays[i].nbytes
-            if group is not big:
-                small_end = total
+        sizes = [None if a is None else a.nbytes for a in arrays]
+        offsets, stage_begin, stage_end, out_off = pack_layout(sizes, self.DIRECT_BYTES, zero_head)
         stream = self.stream() if stream is None else stream
-        out_off = (total + 15) // 16 * 16
         dev = self.torch.empty(max(out_off + int(out_bytes), 16), dtype=self.torch.uint8, device=self.device)
         base = dev.data_ptr()
-        if small_end:
+        if stage_end > stage_begin:
             self.ctx.h2d_wait()
-            stage_np, stage_ptr = self._pinned("upload", small_end)
-            for i, (a, off) in enumerate(zip(arrays, offsets)):
-                if a is not None and a.nbytes and i not in big:
-                    stage_np[off:off + a.nbytes] = a.reshape(-1).view(np.uint8)
-            self.ctx.h2d(base, stage_ptr, small_end, stream)
-        for i in big:                                # pageable source: returns once the data has left it
-            self.ctx.h2d(base + offsets[i], arrays[i].ctypes.data, arrays[i].nbytes, stream)
-        self.h2d_bytes += sum(a.nbytes for a in arrays if a is not None)
+            stage_np, stage_ptr = self._pinned("upload", stage_end - stage_begin)
+            for a, off, size in zip(arrays, offsets, sizes):
+                if a is not None and size and size < self.DIRECT_BYTES:
+                    stage_np[off - stage_begin:off - stage_begin + size] = a.reshape(-1).view(np.uint8)
+            if zero_head:
+                stage_np[stage_end - stage_begin - zero_head:stage_end - stage_begin] = 0
+            self.ctx.h2d(base + stage_begin, stage_ptr, stage_end - stage_begin, stream)
+        for a, off, size in zip(arrays, offsets, sizes):   # pageable source: returns once the data has left it
+            if a is not None and size is not None and size >= self.DIRECT_BYTES:
+                self.ctx.h2d(base + off, a.ctypes.data, size, stream)
+        self.h2d_bytes += sum(sz for sz in sizes if sz is not None)
         return dev, [None if off is None else base + off for off in offsets], base + out_off
 
     def download_raw(self, ptr, nbytes, dtype=np.float64, stream=None):

@@ -19,8 +19,14 @@ Deliberate supersets of the reference (documented in DESIGN.md):
   prints and then dies with ``UnboundLocalError``, qnmfits.py:246-248,270-271);
 * Python ints are accepted for ``Mf`` / ``chif`` in ``mismatch_t0_array`` (the
   reference routes them to the dynamic branch and raises, qnmfits.py:1268);
-* time-dependent ``Mf`` / ``chif`` arrays (the dynamic-spectrum fits,
-  qnmfits.py:318-475,676-911) are not part of this hot path: NotImplementedError.
+* ``multimode_ringdown_fit`` and the sweeps over dict data accept nonlinear (quadratic,
+  ...) QNM labels when the caller supplies their per-series coefficients through
+  ``coef_columns`` (the reference raises, qnm.py:390; its only definition of such
+  coefficients is the alpha columns of spatial_mapping_functions.py:202-240).
+
+Time-dependent ``Mf`` / ``chif`` arrays select the dynamic-spectrum fits
+(``dynamic_ringdown_fit``, ``dynamic_multimode_ringdown_fit`` and the dynamic branch of
+``mismatch_t0_array``; reference qnmfits.py:318-475, 676-911, 1286-1299).
 """
 import numpy as np
 
@@ -229,7 +235,8 @@ def _single_fit_on_device(times_m, data_rows, frequencies, t0, coef, omega_rows=
         C_min = np.ascontiguousarray(_minimum_norm_from_factor(R, L * K).reshape(N), dtype=np.complex128)
         keep2, p2, _ = eng.upload_packed([C_min], stream=stream)
         eng.ctx.eval_batch(eng.make_batch(**dict(common, C_d=p2[0])), stream)
-        _, _, model, scal, status = fetch()
+        _, _, model, scal, status_eval = fetch()
+        status |= status_eval                        # keep the fit's own bits (underdetermined, non-finite)
         C = C_min
     return {
         'C': C, 'mismatch': np.float64(scal[0]), 'residual': scal[1], 'model': model,
@@ -286,24 +293,94 @@ def ringdown_fit(times, data, modes, Mf, chif, t0, t0_method='geq', T=100,
     }
 
 
-def _mu_lists(spherical_modes, modes, chif):
-    """The reference's list-of-lists of mixing coefficients (qnmfits.py:618-622)."""
-    for mode in modes:
+_NONLINEAR_MSG = (
+    "multimode fits take (ell, m, n, sign) labels only unless coef_columns supplies the "
+    "per-series coefficients of the other labels: the reference has no definition of mixing "
+    "coefficients for nonlinear QNMs (qnm.py:390: too many values to unpack (expected 6))")
+
+
+def _coef_column(value, keys, chif):
+    """One caller-supplied coefficient column as complex (L,) for a scalar spin, or
+    (n_chi, L) for an array of spins.  ``value``: array-like (L,) — one coefficient per
+    spherical mode, in the order of ``spherical_modes`` —, array-like (n_chi, L), a dict
+    {(ell, m): coefficient} (absent keys are 0), or a callable of the spin returning any of
+    these."""
+    if callable(value):
+        value = value(chif)
+    if isinstance(value, dict):
+        value = [value.get(tuple(lm), 0) for lm in keys]
+        value = np.stack([np.broadcast_to(np.asarray(v, dtype=complex), np.shape(chif)) for v in value], axis=-1)
+    arr = np.asarray(value, dtype=complex)
+    L = len(keys)
+    if np.ndim(chif) == 0:
+        if arr.shape != (L,):
+            raise ValueError(f"a coefficient column must have one entry per spherical mode ({L}), got {arr.shape}")
+        return arr
+    n = len(chif)
+    if arr.shape == (L,):
+        return np.broadcast_to(arr, (n, L))
+    if arr.shape != (n, L):
+        raise ValueError(f"a coefficient column on a spin grid must have shape ({L},) or ({n}, {L}), got {arr.shape}")
+    return arr
+
+
+def _columns(coef_columns):
+    return {} if not coef_columns else {tuple(k): v for k, v in coef_columns.items()}
+
+
+def _mu_lists(spherical_modes, modes, chif, coef_columns=None):
+    """The reference's list-of-lists of mixing coefficients (qnmfits.py:618-622).
+
+    Superset: a label listed in ``coef_columns`` takes its column of per-series
+    coefficients from the caller instead of ``qnm.mu`` — this is how quadratic QNMs enter a
+    multimode fit, with the semantics of the reference's only definition of such
+    coefficients, ``coef_lists = mu + alpha`` in spatial_mapping_functions.py:202-240: the
+    coefficient multiplies the mode's column exp(-i w t) in the rows of that spherical mode."""
+    cols = _columns(coef_columns)
+    linear = [mode for mode in modes if tuple(mode) not in cols]
+    for mode in linear:
         if len(mode) != 4:
             # the reference unpacks exactly six indices (qnm.py:390) and raises
-            raise ValueError(
-                "multimode fits take (ell, m, n, sign) labels only: the reference has no "
-                "definition of mixing coefficients for nonlinear QNMs (too many values "
-                "to unpack (expected 6))")
-    return [qnm.mu_list([tuple(lm) + tuple(mode) for mode in modes], chif)
-            for lm in spherical_modes]
+            raise ValueError(_NONLINEAR_MSG)
+    given = {label: _coef_column(value, spherical_modes, chif) for label, value in cols.items()
+             if any(tuple(mode) == label for mode in modes)}
+    out = []
+    for i, lm in enumerate(spherical_modes):
+        mu = iter(qnm.mu_list([tuple(lm) + tuple(mode) for mode in linear], chif))
+        out.append([given[tuple(mode)][..., i] if tuple(mode) in given else next(mu) for mode in modes])
+    return out
+
+
+def _coef_table(keys, modes, chif_values, coef_columns=None):
+    """``qnm.mu_table`` with caller-supplied columns: complex (n_chi, L, N)."""
+    cols = _columns(coef_columns)
+    linear = [j for j, mode in enumerate(modes) if tuple(mode) not in cols]
+    for j in linear:
+        if len(modes[j]) != 4:
+            raise ValueError(_NONLINEAR_MSG)
+    if len(linear) == len(modes):
+        return qnm.mu_table(keys, modes, chif_values)
+    chif_values = np.atleast_1d(np.asarray(chif_values, dtype=float))
+    out = np.zeros((len(chif_values), len(keys), len(modes)), dtype=complex)
+    if linear:
+        out[:, :, linear] = qnm.mu_table(keys, [modes[j] for j in linear], chif_values)
+    for j, mode in enumerate(modes):
+        if tuple(mode) in cols:
+            out[:, :, j] = _coef_column(cols[tuple(mode)], keys, chif_values)
+    return out
 
 
 def multimode_ringdown_fit(times, data_dict, modes, Mf, chif, t0,
-                           t0_method='geq', T=100, spherical_modes=None):
+                           t0_method='geq', T=100, spherical_modes=None, coef_columns=None):
     """Fit several spherical-harmonic series at once with spheroidal mixing
     (reference qnmfits.py:478-673).  Returns the reference's 11-key dict incl.
     'weighted_C' (mu_i * C per spherical mode) and per-mode 'model' / 'data' dicts.
+
+    ``coef_columns`` (not in the reference, after its arguments): {label: coefficients per
+    spherical mode} for labels whose column is not a Kerr mixing coefficient — quadratic
+    QNMs (8-tuples; their frequency is the sum of the constituents', qnm.py:272-280) with
+    the alpha coefficients of spatial_mapping_functions.py:202-240, or any other column the
+    caller wants to fix.  See ``_coef_column`` for the accepted forms.
     """
     times = np.asarray(times)
     if spherical_modes is None:
@@ -311,8 +388,9 @@ def multimode_ringdown_fit(times, data_dict, modes, Mf, chif, t0,
     sel = _window(times, t0, T, t0_method)
     times_masked = times[sel]
     data_dict_mask = {lm: np.asarray(data_dict[lm])[sel] for lm in spherical_modes}
+    _check_modes(modes)
     frequencies = np.array(qnm.omega_list(modes, chif, Mf))
-    mu_lists = _mu_lists(spherical_modes, modes, chif)
+    mu_lists = _mu_lists(spherical_modes, modes, chif, coef_columns)
     coef = np.array([[complex(v) for v in row] for row in mu_lists], dtype=complex)
     coef = coef.reshape(len(spherical_modes), len(modes))
     rows = np.stack([np.asarray(data_dict_mask[lm], dtype=complex) for lm in spherical_modes]) \
@@ -469,11 +547,12 @@ class _Sweep:
                 np.ascontiguousarray(rows, dtype=np.complex128), rb, re, t0_arr, coef_arr,
                 coef_index] + [np.ascontiguousarray(freq_arrays[k][0], dtype=freq_arrays[k][1])
                                for k in names]
-        out_bytes = 0
+        out_bytes = zero_head = 0
         if self.ws == 1:
-            host.append(_ZERO)                       # the counter of flagged fits, zeroed by the upload
-            out_bytes = 8 * n_local
-        self._inputs, ptrs, out = eng.upload_packed(host, out_bytes=out_bytes, stream=self.stream)
+            zero_head = 16                           # the counter of flagged fits, zeroed by the upload,
+            out_bytes = 8 * n_local                  # always directly in front of the result region
+        self._inputs, ptrs, out = eng.upload_packed(host, out_bytes=out_bytes, stream=self.stream,
+                                                    zero_head=zero_head)
         kw = dict(freq_scalars)
         kw.update({k: ptr for k, ptr in zip(names, ptrs[7:])})
 
@@ -620,9 +699,6 @@ def _make_sweep(*args, **kwargs):
     return _Sweep(*args, **kwargs)
 
 
-_ZERO = np.zeros(2, np.float64)   # 16 bytes: the result region behind it stays contiguous
-
-
 def _sweep_on_device(*args, **kwargs):
     sweep = _Sweep(*args, **kwargs)
     sweep.launch()
@@ -659,7 +735,7 @@ def _window_rows_many(times, t0_array, T_array, t0_method):
 
 
 def _prepare_t0_sweep(times, data, modes, Mf, chif, t0_array, t0_method, T_array,
-                      spherical_modes, delta):
+                      spherical_modes, delta, coef_columns=None):
     """Host tabulation + upload for the start-time sweep; returns the device-resident sweep."""
     n = len(t0_array)
     rows, keys = _series_rows(data, spherical_modes)
@@ -673,7 +749,7 @@ def _prepare_t0_sweep(times, data, modes, Mf, chif, t0_array, t0_method, T_array
         coef = None
     else:
         frequencies = np.array(qnm.omega_list(modes, chif, Mf))
-        mu_lists = _mu_lists(keys, modes, chif)
+        mu_lists = _mu_lists(keys, modes, chif, coef_columns)
         coef = np.array([[complex(v) for v in row] for row in mu_lists],
                         dtype=complex).reshape(1, len(keys), len(modes))
     return _make_sweep(
@@ -685,12 +761,13 @@ def _prepare_t0_sweep(times, data, modes, Mf, chif, t0_array, t0_method, T_array
 
 
 def mismatch_t0_array(times, data, modes, Mf, chif, t0_array, t0_method='geq',
-                      T_array=100, spherical_modes=None, delta=0.0):
+                      T_array=100, spherical_modes=None, delta=0.0, coef_columns=None):
     """Mismatch for an array of start times (reference qnmfits.py:1183-1301).
 
     Returns a Python list of np.float64 like the reference (its docstring says
     ndarray; the code returns a list, qnmfits.py:1259,1301).  ``delta`` is ignored for
-    dict data, as in the reference (qnmfits.py:1251).
+    dict data, as in the reference (qnmfits.py:1251).  ``coef_columns``: see
+    ``multimode_ringdown_fit`` (dict data with a fixed remnant only).
     """
     times = np.asarray(times)
     t0_array = np.asarray(t0_array, dtype=float)
@@ -724,14 +801,14 @@ def mismatch_t0_array(times, data, modes, Mf, chif, t0_array, t0_method='geq',
         for t0, T in zip(t0_array, T_array):
             if type(data) is dict:
                 out.append(fit(times, data, modes, Mf, chif, t0, t0_method, T,
-                               spherical_modes)['mismatch'])
+                               spherical_modes, coef_columns)['mismatch'])
             else:
                 out.append(fit(times, data, modes, Mf, chif, t0, t0_method, T,
                                delta)['mismatch'])
         return out
 
     sweep = _prepare_t0_sweep(times, data, modes, Mf, chif, t0_array, t0_method, T_array,
-                              spherical_modes, delta)
+                              spherical_modes, delta, coef_columns)
     sweep.launch()
     mm, status = sweep.fetch()
     _warn_status(status, "mismatch_t0_array")
@@ -784,7 +861,7 @@ def _time_axis(times, t0, T, t0_method):
 
 
 def _prepare_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0, t0_method='geq',
-                        T=100, res=50, spherical_modes=None, delta=0.0):
+                        T=100, res=50, spherical_modes=None, delta=0.0, coef_columns=None):
     """Host tabulation + upload for the grid sweep; returns (sweep, shape)."""
     times = np.asarray(times)
     _check_modes(modes)
@@ -814,11 +891,8 @@ def _prepare_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0, t0_metho
             np.broadcast_to(np.asarray(df, dtype=float), (len(modes),)).copy()
         coef = None
     else:
-        for mode in modes:
-            if len(mode) != 4:
-                raise ValueError("multimode fits take (ell, m, n, sign) labels only")
         df = None
-        coef = qnm.mu_table(keys, modes, chif_array)
+        coef = _coef_table(keys, modes, chif_array, coef_columns)
     wmax = float(table_max * inv_max
                  * (1.0 if df is None else np.max(np.abs(df)))) * max(
                      len(m) // 4 for m in modes)
@@ -838,16 +912,18 @@ def _prepare_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0, t0_metho
 
 def mismatch_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0,
                         t0_method='geq', T=100, res=50, spherical_modes=None,
-                        delta=0.0):
+                        delta=0.0, coef_columns=None):
     """Mismatch on a res x res grid of remnant mass and spin (reference
     qnmfits.py:1304-1415).  Returns float64 (res, res) indexed [iMf, ichif].
 
     The flat index i = iMf * res + ichif of the reference's loop (qnmfits.py:1393-1394,
     1404-1405) is the sharding axis: each rank of an initialised torch.distributed job
-    fits one contiguous slab and the mismatches are all-gathered.
+    fits one contiguous slab and the mismatches are all-gathered.  ``coef_columns``: see
+    ``multimode_ringdown_fit``; on the grid a column may depend on the spin (a callable of
+    ``chif``, or an array (res, L) along ``np.linspace(*chif_minmax, res)``).
     """
     sweep, shape = _prepare_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0,
-                                       t0_method, T, res, spherical_modes, delta)
+                                       t0_method, T, res, spherical_modes, delta, coef_columns)
     if sweep is None:
         return np.reshape(np.array([]), shape)
     sweep.launch()
@@ -908,10 +984,10 @@ class _ResidentData:
         arrays = [omega,
                   None if series_index is None else np.ascontiguousarray(series_index, dtype=np.int32),
                   None if coef is None else np.ascontiguousarray(coef, dtype=np.complex128),
-                  None if coef is None else np.arange(n, dtype=np.int32), rb, re,
-                  _ZERO]                             # counter of flagged fits, zeroed by the upload
+                  None if coef is None else np.arange(n, dtype=np.int32), rb, re]
         stream = eng.stream()
-        keep, ptrs, out = eng.upload_packed(arrays, out_bytes=8 * n, stream=stream)
+        # 16 zero bytes in front of the result region: the counter of flagged fits
+        keep, ptrs, out = eng.upload_packed(arrays, out_bytes=8 * n, stream=stream, zero_head=16)
         batch = eng.make_batch(
             times_d=self.times_p, data_d=self.data_p, n_times=self.K_tot, series_stride=self.K_tot,
             n_fits=n, n_modes=N, n_series=n_series, row_begin_all=self.window[0],
@@ -1040,10 +1116,11 @@ class _RemnantObjective(_ResidentData):
     """``mismatch_M_chi`` of calculate_epsilon (reference qnmfits.py:1523-1540, 1554-1571):
     mismatch of the fit at (Mf, chif), chif clipped to [0, 0.99]."""
 
-    def __init__(self, times, data, modes, t0, t0_method, T, spherical_modes, delta):
+    def __init__(self, times, data, modes, t0, t0_method, T, spherical_modes, delta, coef_columns=None):
         rows, self.keys = _series_rows(data, spherical_modes)
         super().__init__(times, rows, t0, t0_method, T)
         self.modes = modes
+        self.coef_columns = coef_columns
         self.df = None if self.keys is not None else _delta_factor(delta, len(modes))
 
     def __call__(self, X, idx=None):
@@ -1056,12 +1133,13 @@ class _RemnantObjective(_ResidentData):
             if self.keys is None:
                 omega[k] = self.df * omega[k]
             else:
-                coef[k] = [[complex(v) for v in row] for row in _mu_lists(self.keys, self.modes, chif)]
+                coef[k] = [[complex(v) for v in row] for row in _mu_lists(self.keys, self.modes, chif, self.coef_columns)]
         return self.mismatches(omega, coef=coef, n_series=1 if self.keys is None else len(self.keys))
 
 
 def calculate_epsilon(times, data, modes, Mf, chif, t0, t0_method='geq', T=100,
-                      spherical_modes=None, min_method='Nelder-Mead', delta=0.0, x0=None):
+                      spherical_modes=None, min_method='Nelder-Mead', delta=0.0, x0=None,
+                      coef_columns=None):
     """Remnant mass and spin minimising the mismatch and their distance epsilon from
     (Mf, chif) (reference qnmfits.py:1418-1594: same start point, bounds [(0, 2), (0, 0.99)],
     xatol = 1e-6).  Returns (epsilon, Mf_bestfit, chif_bestfit).
@@ -1073,7 +1151,7 @@ def calculate_epsilon(times, data, modes, Mf, chif, t0, t0_method='geq', T=100,
     if x0 is None:
         x0 = [Mf, chif]
     bounds = [(0, 2.0), (0, 0.99)]
-    objective = _RemnantObjective(times, data, modes, t0, t0_method, T, spherical_modes, delta)
+    objective = _RemnantObjective(times, data, modes, t0, t0_method, T, spherical_modes, delta, coef_columns)
     if min_method == 'Nelder-Mead':
         from ._neldermead import minimize_lockstep
         res = minimize_lockstep(objective, np.asarray(x0, dtype=float).reshape(1, 2), bounds, xatol=1e-6)

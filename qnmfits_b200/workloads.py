@@ -112,28 +112,85 @@ def multimode_labels():
     return spherical, modes
 
 
-def config4(n_t0=500, spherical=None, modes=None, sigma=1e-6):
+QUADRATIC_LABELS = [
+    (2, 2, 0, 1, 2, 2, 0, 1),       # m = 4: sourced in (4, 4)
+    (2, 2, 0, 1, 2, 2, 1, 1),
+    (2, -2, 0, 1, 2, -2, 0, 1),     # m = -4
+    (2, 2, 0, 1, 2, -2, 0, 1),      # m = 0: the memory-like product
+]
+
+
+def multimode_labels_quadratic():
+    """BASELINE.json config 4 as stated: 21 spherical modes (ell <= 4) and ~40 QNMs — regular,
+    mirror AND quadratic.  36 linear labels (``multimode_labels`` without the (3,0,n) and
+    (4,0,n) overtones) + the four ``QUADRATIC_LABELS``."""
+    spherical, modes = multimode_labels()
+    modes = [mode for mode in modes if not (mode[1] == 0 and mode[0] > 2)]
+    return spherical, modes + list(QUADRATIC_LABELS)
+
+
+def quadratic_alpha(label, spherical, chif):
+    """Synthetic per-series coefficients of a quadratic QNM (the role of ``Qmu_B`` in the
+    reference, spatial_mapping_functions.py:202-210, whose dependencies — spherical.Wigner3j,
+    spin-weight-0 Kerr sequences — are absent here): non-zero only in the spherical modes with
+    m = m1 + m2, smooth in the spin, decaying with ell away from ell1 + ell2.  Deterministic
+    input generator, not physics.  Returns complex (L,) for a scalar spin, (n, L) for an array."""
+    l1, m1, n1, _, l2, m2, n2, _ = label
+    chif = np.asarray(chif, dtype=float)
+    out = np.zeros(chif.shape + (len(spherical),), dtype=complex)
+    for i, (ell, m) in enumerate(spherical):
+        if m != m1 + m2 or ell < abs(m):
+            continue
+        out[..., i] = (0.21 + 0.05j * (1 + n1 + n2)) * (1.0 - 0.2 * chif + 0.1j * chif ** 2) \
+            / (1.0 + 0.6 * abs(l1 + l2 - ell))
+    return out
+
+
+def quadratic_columns(spherical, labels=None):
+    """``coef_columns`` argument of the public API for the synthetic quadratic coefficients."""
+    labels = QUADRATIC_LABELS if labels is None else labels
+    return {label: (lambda chif, label=label: quadratic_alpha(label, spherical, chif)) for label in labels}
+
+
+def coef_override(spherical, modes, chif, tables=None):
+    """The oracle's ``coef_override`` (L, N) that corresponds to ``quadratic_columns``: mu for
+    linear labels, the synthetic alpha for quadratic ones."""
+    provider = qnm if tables is None else tables
+    out = np.zeros((len(spherical), len(modes)), dtype=complex)
+    for j, mode in enumerate(modes):
+        if len(mode) == 4:
+            out[:, j] = [complex(v) for v in provider.mu_list([lm + mode for lm in spherical], chif)]
+        else:
+            out[:, j] = quadratic_alpha(mode, spherical, chif)
+    return out
+
+
+def config4(n_t0=500, spherical=None, modes=None, sigma=1e-6, quadratic=False):
     """multimode sweep: 21 series x 40 QNMs with spheroidal mixing and mirror modes.
 
-    Nonlinear (quadratic) labels are not included: the reference's
-    multimode_ringdown_fit cannot express them (qnm.py:390 raises), so there is no
-    reference result to be faithful to.
+    ``quadratic=False``: linear labels only — the shape the reference's
+    multimode_ringdown_fit can express (qnm.py:390 raises for nonlinear labels), pinned to the
+    golden fixtures.  ``quadratic=True``: config 4 as BASELINE.json states it, with quadratic
+    QNMs entering through caller-supplied coefficient columns (``extra['coef_columns']`` for the
+    public API, ``coef_override`` for the oracle).
     """
     if spherical is None or modes is None:
-        spherical, modes = multimode_labels()
+        spherical, modes = multimode_labels_quadratic() if quadratic else multimode_labels()
     times = default_times()
     omega = np.array(qnm.omega_list(modes, CHIF_TRUE, MF_TRUE))
     rng = np.random.default_rng(0)
     C = rng.normal(size=len(modes)) + 1j * rng.normal(size=len(modes))
     noise_rng = np.random.default_rng(1)
+    coef = coef_override(spherical, modes, CHIF_TRUE)
     data = {}
-    for lm in spherical:
-        mu = np.array([complex(v) for v in
-                       qnm.mu_list([lm + mode for mode in modes], CHIF_TRUE)])
-        data[lm] = ringdown(times, 0.0, mu * C, omega) + _noise(noise_rng, len(times), sigma)
+    for i, lm in enumerate(spherical):
+        data[lm] = ringdown(times, 0.0, coef[i] * C, omega) + _noise(noise_rng, len(times), sigma)
+    extra = {"C_true": C}
+    if any(len(mode) != 4 for mode in modes):
+        extra["coef_columns"] = quadratic_columns(spherical, [m for m in modes if len(m) != 4])
     return Workload("cfg4_multimode_t0_sweep", times, data, modes,
                     t0_array=np.linspace(0.0, 50.0, n_t0), spherical_modes=spherical,
-                    extra={"C_true": C})
+                    extra=extra)
 
 
 def config5(n_waveforms=4096, n_fixed=2, sigma=1e-6):

@@ -585,3 +585,110 @@ def test_omega_grid_node_on_a_fixed_mode_follows_numpy(qf, eng, oracle_tables):
     want = orc.mismatch_omega_grid(oracle_tables, wl.times, wl.data, m2, 0.95, 0.69, re_mm, im_mm, 5.0, T=80, res=5)
     assert abs(np.linspace(*re_mm, 5)[2] - w0.real) < 1e-15 and abs(np.linspace(*im_mm, 5)[2] - w0.imag) < 1e-15
     np.testing.assert_allclose(got, want, rtol=0, atol=MM_TOL)
+
+
+# --------------------------------------------------------------------------
+# BASELINE.json config 4 as stated (quadratic QNMs in the multimode fit) and the full-size
+# configurations
+
+def test_quadratic_qnms_in_multimode_fit_vs_oracle(qf, eng, oracle_tables):
+    """multimode_ringdown_fit with quadratic labels whose per-series coefficients come from
+    the caller (``coef_columns``; semantics of the reference's mapping fit, coef = mu for
+    linear labels and alpha for quadratic ones, spatial_mapping_functions.py:202-240)
+    against the oracle's ``coef_override`` path: every key of the result dict."""
+    wl = workloads.config4(n_t0=3, quadratic=True)
+    cols = wl.extra["coef_columns"]
+    assert sum(len(m) == 8 for m in wl.modes) == 4
+    over = workloads.coef_override(wl.spherical_modes, wl.modes, wl.chif, oracle_tables)
+    for t0, T, method in ((0.0, 100, 'geq'), (7.33, 60, 'closest')):
+        fit = qf.multimode_ringdown_fit(wl.times, wl.data, wl.modes, wl.Mf, wl.chif, t0, method, T,
+                                        wl.spherical_modes, coef_columns=cols)
+        ref = orc.multimode_ringdown_fit(oracle_tables, wl.times, wl.data, wl.modes, wl.Mf, wl.chif, t0,
+                                         method, T, wl.spherical_modes, coef_override=over)
+        assert list(fit.keys()) == list(ref.keys())
+        assert np.array_equal(fit["frequencies"], ref["frequencies"])
+        assert np.array_equal(fit["model_times"], ref["model_times"])
+        s = np.linalg.svd(_stacked_design(ref, over, t0), compute_uv=False)
+        scale = np.max(np.abs(ref["C"]))
+        assert np.max(np.abs(fit["C"] - ref["C"])) / scale < cases.amp_tol(s)
+        assert abs(fit["mismatch"] - ref["mismatch"]) < MM_TOL
+        assert fit["residual"].shape == ref["residual"].shape
+        for lm in wl.spherical_modes:
+            np.testing.assert_allclose(fit["model"][lm], ref["model"][lm], rtol=0, atol=1e-8 * scale)
+            np.testing.assert_allclose(fit["weighted_C"][lm], ref["weighted_C"][lm], rtol=0,
+                                       atol=cases.amp_tol(s) * scale)
+    # the injected amplitudes come back (noise 1e-6)
+    fit = qf.multimode_ringdown_fit(wl.times, wl.data, wl.modes, wl.Mf, wl.chif, 0.0, 'geq', 100,
+                                    wl.spherical_modes, coef_columns=cols)
+    assert np.max(np.abs(fit["C"] - wl.extra["C_true"])) < 1e-3
+
+
+def _stacked_design(ref, coef, t0):
+    tau = ref["model_times"] - t0
+    E = np.exp(-1j * np.outer(tau, ref["frequencies"]))
+    return np.concatenate([E * coef[i][None, :] for i in range(coef.shape[0])])
+
+
+def test_config4_full_size_with_quadratic_qnms_sampled_vs_oracle(qf, eng, oracle_tables):
+    """Config 4 at BASELINE size — 500 start times x (21 series x 40 QNMs incl. mirror and
+    quadratic modes) — through mismatch_t0_array; 32 sampled start times against the oracle."""
+    wl = workloads.config4(n_t0=500, quadratic=True)
+    got = np.array(qf.mismatch_t0_array(wl.times, wl.data, wl.modes, wl.Mf, wl.chif, wl.t0_array,
+                                        T_array=wl.T, spherical_modes=wl.spherical_modes,
+                                        coef_columns=wl.extra["coef_columns"]))
+    assert got.shape == (500,) and np.all(np.isfinite(got))
+    over = workloads.coef_override(wl.spherical_modes, wl.modes, wl.chif, oracle_tables)
+    idx = np.unique(np.concatenate([[0, 499], np.random.default_rng(4).choice(500, 30, replace=False)]))
+    want = orc.mismatch_t0_array(oracle_tables, wl.times, wl.data, wl.modes, wl.Mf, wl.chif,
+                                 wl.t0_array[idx], T_array=wl.T, spherical_modes=wl.spherical_modes,
+                                 coef_override=over)
+    np.testing.assert_allclose(got[idx], want, rtol=0, atol=MM_TOL)
+    # the linear-label shape of the golden fixtures at full size as well
+    wl = workloads.config4(n_t0=500)
+    got = np.array(qf.mismatch_t0_array(wl.times, wl.data, wl.modes, wl.Mf, wl.chif, wl.t0_array,
+                                        T_array=wl.T, spherical_modes=wl.spherical_modes))
+    want = orc.mismatch_t0_array(oracle_tables, wl.times, wl.data, wl.modes, wl.Mf, wl.chif,
+                                 wl.t0_array[idx], T_array=wl.T, spherical_modes=wl.spherical_modes)
+    np.testing.assert_allclose(got[idx], want, rtol=0, atol=MM_TOL)
+
+
+def test_multimode_grid_with_spin_dependent_columns_vs_oracle(qf, eng, oracle_tables):
+    """mismatch_M_chi_grid over dict data with quadratic columns that depend on the spin:
+    every grid point against the oracle (callable coef_override)."""
+    wl = workloads.config4(n_t0=1, quadratic=True)
+    sph = [(2, 2), (3, 2), (4, 4), (2, 0), (4, -4)]
+    modes = [(2, 2, 0, 1), (2, 2, 1, 1), (3, 2, 0, 1), (4, 4, 0, 1), (2, 0, 0, 1), (2, -2, 0, -1),
+             (4, -4, 0, 1)] + list(workloads.QUADRATIC_LABELS)
+    cols = workloads.quadratic_columns(sph)
+    data = {lm: wl.data[lm] for lm in sph}
+    grid = qf.mismatch_M_chi_grid(wl.times, data, modes, (0.9, 1.0), (0.6, 0.75), 2.0, T=80, res=5,
+                                  spherical_modes=sph, coef_columns=cols)
+    want = orc.mismatch_M_chi_grid(
+        oracle_tables, wl.times, data, modes, (0.9, 1.0), (0.6, 0.75), 2.0, T=80, res=5, spherical_modes=sph,
+        coef_override=lambda chif: workloads.coef_override(sph, modes, chif, oracle_tables))
+    np.testing.assert_allclose(grid, want, rtol=0, atol=MM_TOL)
+
+
+def test_config3_full_grid_512_points_vs_oracle(qf, eng, oracle_tables):
+    """The headline grid (256 x 256, 8 overtones) against the oracle on 512 sampled points."""
+    wl = workloads.config3(res=256)
+    grid = qf.mismatch_M_chi_grid(wl.times, wl.data, wl.modes, wl.Mf_minmax, wl.chif_minmax, wl.t0,
+                                  T=wl.T, res=256)
+    idx = np.sort(np.random.default_rng(12).choice(256 * 256, 512, replace=False))
+    want = orc.mismatch_M_chi_grid(oracle_tables, wl.times, wl.data, wl.modes, wl.Mf_minmax, wl.chif_minmax,
+                                   wl.t0, T=wl.T, res=256, flat_indices=idx)
+    np.testing.assert_allclose(grid.reshape(-1)[idx], want, rtol=0, atol=MM_TOL)
+
+
+def test_config5_full_size_sampled_vs_scipy(qf, eng, oracle_tables):
+    """Config 5 at BASELINE size: 4096 waveforms searched in lock step; 128 sampled waveforms
+    against scipy's Nelder-Mead on the numpy objective (the reference's own code path,
+    qnmfits.py:1995-2038).  Agreement is at the optimiser's resolution (see
+    test_free_frequency_fit_vs_reference_golden_and_oracle): 1e-6 in the frequency."""
+    wl = workloads.config5(n_waveforms=4096, n_fixed=2)
+    got = qf.free_frequency_fit_batch(wl.times, wl.data, 0.0, modes=wl.modes, Mf=wl.Mf, chif=wl.chif)
+    assert got.shape == (4096,)
+    idx = np.sort(np.random.default_rng(5).choice(4096, 128, replace=False))
+    want = np.array([orc.free_frequency_fit(oracle_tables, wl.times, wl.data[b], 0.0, modes=wl.modes, Mf=wl.Mf,
+                                            chif=wl.chif) for b in idx])
+    np.testing.assert_allclose(got[idx], want, rtol=0, atol=1e-6)

@@ -146,3 +146,66 @@ def test_memoised_tables_equal_fresh_tabulation(qf):
     arr, inv, inv_max = api._linspace(0.85, 1.05, 256)
     assert np.array_equal(arr, np.linspace(0.85, 1.05, 256)) and np.array_equal(inv, 1.0 / arr)
     assert inv_max == np.max(np.abs(inv)) and api._linspace(0.85, 1.05, 256)[0] is arr
+
+
+def test_pack_layout_keeps_the_counter_in_front_of_the_results():
+    """The zero head (a sweep's counter of flagged fits) sits immediately before the result
+    region whatever the array sizes — also when an array is large enough to be uploaded
+    from its own memory (>= DIRECT_BYTES), which moves it out of the staged group."""
+    direct = _engine.Engine.DIRECT_BYTES
+    for sizes in ([16008, 32016, None, None, 128, 64],
+                  [2400000, 16 * 300000, None, 4004, 4004, 8008, 128],     # 300 000-sample series: data >= 4 MB
+                  [direct, direct + 8, 24, None],
+                  [None, None],
+                  [40]):
+        for zero_head in (0, 16):
+            offsets, stage_begin, stage_end, out = _engine.pack_layout(sizes, direct, zero_head)
+            assert out == stage_end and out % 16 == 0
+            spans = sorted((off, off + n) for off, n in zip(offsets, sizes) if n is not None)
+            for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+                assert a1 <= b0                      # no overlap
+            for off, n in zip(offsets, sizes):
+                if n is None:
+                    assert off is None
+                    continue
+                assert off % 256 == 0
+                assert off + n <= out - zero_head    # nothing reaches into the zero head or beyond
+                staged = n < direct
+                assert (off >= stage_begin) == staged
+            # every large array precedes the staged group
+            assert all(off + n <= stage_begin for off, n in zip(offsets, sizes) if n is not None and n >= direct)
+    with pytest.raises(ValueError):
+        _engine.pack_layout([8], direct, zero_head=8)
+
+
+def test_coef_columns_assemble_like_the_reference_mapping_fit(qf):
+    """Caller-supplied coefficient columns (quadratic QNMs in a multimode fit): linear labels
+    keep qnm.mu, listed labels take the caller's column — ``coef_lists = mu + alpha`` of the
+    reference's spatial_mapping_functions.py:202-210 — for scalar spins and on a spin grid."""
+    from qnmfits_b200 import workloads
+    spherical, modes = workloads.multimode_labels_quadratic()
+    cols = workloads.quadratic_columns(spherical)
+    assert len(modes) == 40 and sum(len(m) == 8 for m in modes) == 4
+    want = workloads.coef_override(spherical, modes, 0.69)
+    lists = api._mu_lists(spherical, modes, 0.69, cols)
+    got = np.array([[complex(v) for v in row] for row in lists])
+    assert np.array_equal(got, want)
+    # array, dict and callable forms of a column are equivalent
+    label = workloads.QUADRATIC_LABELS[0]
+    alpha = workloads.quadratic_alpha(label, spherical, 0.69)
+    as_dict = {lm: alpha[i] for i, lm in enumerate(spherical) if alpha[i] != 0}
+    for form in (alpha, list(alpha), as_dict, lambda chif: workloads.quadratic_alpha(label, spherical, chif)):
+        lists = api._mu_lists(spherical, [modes[0], label], 0.69, {label: form})
+        assert np.array_equal(np.array([row[1] for row in lists]), alpha)
+    chis = np.linspace(0.6, 0.75, 5)
+    table = api._coef_table(spherical, modes, chis, cols)
+    assert table.shape == (5, 21, 40)
+    for c, chif in enumerate(chis):
+        np.testing.assert_allclose(table[c], workloads.coef_override(spherical, modes, float(chif)), rtol=0, atol=1e-15)
+    # without columns the nonlinear label is rejected like in the reference (qnm.py:390)
+    with pytest.raises(ValueError):
+        api._mu_lists(spherical, modes, 0.69)
+    with pytest.raises(ValueError):
+        api._coef_table(spherical, modes, chis)
+    with pytest.raises(ValueError):
+        api._mu_lists(spherical, modes, 0.69, {label: np.ones(3)})
