@@ -18,9 +18,10 @@ by the NCCL all-gather of the mismatch slabs.
 * roofline   FP64: algorithmic flops per fit F(M, N) x fits / kernel time,
              against the DFMA peak measured live on this GPU (MEASURED_PEAKS.json has
              no FP64 entry); HBM traffic is reported next to it.
-* cpu_baseline / --impl reference   the oracle (numpy restatement of the reference's
-             per-fit loop, oracle/qnmfits_oracle.py) timed on this box's host cores on
-             a bounded strided sample of the same grid.
+* cpu_baseline / --impl reference   the UNMODIFIED reference's own mismatch_M_chi_grid
+             (byte-compiled under oracle/_ref/ by oracle/make_ref.py so that it travels to
+             the GPU box; oracle/qnmfits_oracle.py only if that is missing) timed on this
+             box's host cores on a bounded, coarser sample of the same (Mf, chif) rectangle.
 """
 import argparse
 import json
@@ -45,80 +46,115 @@ WORKLOAD = ("cfg3 mismatch_M_chi_grid: 256x256 Mf-chif grid, modes (2,2,0..7,+1)
 # ------------------------------------------------------------------ CPU arms
 
 _CPU_STATE = None
+CPU_SAMPLE_FITS = 4096          # fits per step of the multi-process CPU arm (whole grid: 65 536)
 
 
 def _cpu_init():
-    """Per-process state of the CPU arm: workload, oracle tables (spline caches warm)."""
+    """Per-process state of the CPU arm: workload + the implementation to time.
+
+    ``kind`` "reference": the UNMODIFIED reference's own ``mismatch_M_chi_grid`` (its public
+    API, stock code path), imported by oracle/ref_loader.py from /root/reference or — on the
+    GPU box — from the byte-compiled copy oracle/make_ref.py built under oracle/_ref/.
+    ``kind`` "port": oracle/qnmfits_oracle.py, the numpy restatement, when neither exists."""
     global _CPU_STATE
     if _CPU_STATE is None:
+        os.environ.setdefault("TQDM_DISABLE", "1")   # the reference wraps its loop in a progress bar
         try:
             from threadpoolctl import threadpool_limits
-            limiter = threadpool_limits(1)          # one BLAS thread per process
+            limiter = threadpool_limits(1)          # one BLAS thread per process (faster at 1000 x 8)
         except Exception:  # pragma: no cover
             limiter = None
-        from oracle import qnmfits_oracle as orc
+        import warnings
+        from oracle import ref_loader
         from qnmfits_b200 import synthetic, workloads
         workloads.use_synthetic_tables()
         wl = workloads.config3(res=RES)
-        tables = orc.OracleTables(synthetic.modes_cache)
-        orc.mismatch_M_chi_grid(tables, wl.times, wl.data, wl.modes, wl.Mf_minmax, wl.chif_minmax,
-                                wl.t0, T=wl.T, res=RES, flat_indices=[0])
-        _CPU_STATE = (orc, wl, tables, limiter)
+        if ref_loader.reference_available():
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                ref = ref_loader.load_reference(synthetic.modes_cache)
+            kind, grid = "reference", ref.mismatch_M_chi_grid
+        else:
+            from oracle import qnmfits_oracle as orc
+            tables = orc.OracleTables(synthetic.modes_cache)
+            kind = "port"
+
+            def grid(*a, **k):
+                return orc.mismatch_M_chi_grid(tables, *a, **k)
+        grid(wl.times, wl.data, wl.modes, wl.Mf_minmax, wl.chif_minmax, wl.t0, T=wl.T, res=2)   # warm the spline caches
+        _CPU_STATE = (grid, wl, kind, limiter)
     return _CPU_STATE
 
 
-def _cpu_chunk(idx):
-    """Oracle fits (the reference's per-point loop) for a list of flat grid indices."""
-    orc, wl, tables, _ = _cpu_init()
+def _cpu_kind():
+    return _cpu_init()[2]
+
+
+def _cpu_chunk(job):
+    """One call of the CPU implementation's mismatch_M_chi_grid on a sub-rectangle of the
+    benchmark grid: job = (Mf_lo, Mf_hi, res) -> res x res fits over the full spin range."""
+    grid, wl, _, _ = _cpu_init()
+    lo, hi, res = job
     t = time.perf_counter()
-    out = orc.mismatch_M_chi_grid(tables, wl.times, wl.data, wl.modes, wl.Mf_minmax,
-                                  wl.chif_minmax, wl.t0, T=wl.T, res=RES, flat_indices=idx)
+    out = grid(wl.times, wl.data, wl.modes, (lo, hi), wl.chif_minmax, wl.t0, T=wl.T, res=res)
     return time.perf_counter() - t, float(np.sum(out))
 
 
-def strided_sample(stride):
-    rows = np.arange(0, RES, stride)
-    return (rows[:, None] * RES + rows[None, :]).reshape(-1)
+def cpu_jobs(workers, fits=CPU_SAMPLE_FITS):
+    """Split the benchmark's Mf range into ``workers`` bands; each band is one call of
+    mismatch_M_chi_grid with res = r, r*r ~ fits / workers."""
+    from qnmfits_b200 import workloads
+    lo, hi = workloads.Workload.Mf_minmax
+    r = max(4, int(round((fits / workers) ** 0.5)))
+    edges = np.linspace(lo, hi, workers + 1)
+    return [(float(edges[k]), float(edges[k + 1]), r) for k in range(workers)], workers * r * r
 
 
-def cpu_baseline_single(stride=4):
-    """One process, one BLAS thread (the faster 'as shipped' setting)."""
-    idx = strided_sample(stride)
-    dt, _ = _cpu_chunk(idx)
-    return {"value": len(idx) / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{len(idx)} fits: every {stride}th row and column of the 256x256 grid, "
-                      f"{dt:.1f} s, oracle/qnmfits_oracle.py (numpy lstsq per fit), 1 BLAS thread"}
+def cpu_baseline_single(res=128):
+    """One process, one BLAS thread (the faster 'as shipped' setting): the CPU
+    implementation's mismatch_M_chi_grid on the benchmark's (Mf, chif) rectangle at res x res."""
+    from qnmfits_b200 import workloads
+    dt, _ = _cpu_chunk(workloads.Workload.Mf_minmax + (res,))
+    n = res * res
+    what = ("the unmodified reference's mismatch_M_chi_grid (oracle/_ref or /root/reference)"
+            if _cpu_kind() == "reference" else "oracle/qnmfits_oracle.py (numpy lstsq per fit)")
+    return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": _cpu_kind(),
+            "sample": f"{n} fits: the same (Mf, chif) rectangle at res = {res} instead of 256, "
+                      f"{dt:.1f} s, {what}, 1 BLAS thread"}
 
 
 def run_reference_arm(args):
-    """--impl reference: the CPU path on all host cores (process pool over grid chunks)."""
+    """--impl reference: the reference's CPU implementation on all host cores (process pool
+    over bands of the grid, one mismatch_M_chi_grid call per band and step)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    stride = 4
-    idx = strided_sample(stride)
-    chunks = [c for c in np.array_split(idx, cores) if len(c)]
+    jobs, n = cpu_jobs(cores)
     ctx = mp.get_context("spawn")
     times = []
-    with ctx.Pool(len(chunks), initializer=_cpu_init) as pool:
+    with ctx.Pool(len(jobs), initializer=_cpu_init) as pool:
+        kind = pool.apply(_cpu_kind)
         for step in range(args.warmup + args.steps):
             t = time.perf_counter()
-            pool.map(_cpu_chunk, chunks)
+            pool.map(_cpu_chunk, jobs, chunksize=1)
             dt = time.perf_counter() - t
             if step >= args.warmup:
                 times.append(dt)
     ms = 1e3 * sum(times) / len(times)
-    value = len(idx) / (ms * 1e-3)
-    sample = (f"{len(idx)} fits per step: every {stride}th row and column of the 256x256 grid; "
-              f"{len(chunks)} worker processes, 1 BLAS thread each")
+    value = n / (ms * 1e-3)
+    what = ("the unmodified reference (oracle/ref_loader.py)" if kind == "reference"
+            else "oracle/qnmfits_oracle.py, the numpy restatement (reference not available)")
+    sample = (f"{n} fits per step: {len(jobs)} bands of the Mf range x the full chif range, each one "
+              f"mismatch_M_chi_grid(res={jobs[0][2]}) call of {what}; {len(jobs)} worker processes, "
+              "1 BLAS thread each")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": len(chunks), "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": len(jobs), "kind": kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -272,6 +308,29 @@ def run_gpu_arm(args):
     d2h = (eng.d2h_bytes - d2h0) // e2e_steps
     assert np.array_equal(grid_e2e, grid_dev), "e2e and device-resident grids differ"
 
+    # ---- parity of the N-GPU grid (outside every timed region): sampled points against the
+    # oracle (the CPU restatement of the reference, as the checker), and the whole grid against
+    # the golden checksum of the 1-GPU grid when this is a multi-GPU run ------------------
+    parity = None
+    if rank == 0 and not args.no_parity:
+        from oracle import qnmfits_oracle as orc
+        from qnmfits_b200 import synthetic
+        tables = orc.OracleTables(synthetic.modes_cache)
+        idx = np.sort(np.random.default_rng(2024).choice(n_fits, args.parity_points, replace=False))
+        # spread over the slabs of every rank: at least one point per slab
+        per = -(-n_fits // world)
+        idx = np.unique(np.concatenate([idx, np.arange(world) * per, np.minimum(np.arange(1, world + 1) * per, n_fits) - 1]))
+        want = orc.mismatch_M_chi_grid(tables, wl.times, wl.data, wl.modes, wl.Mf_minmax, wl.chif_minmax,
+                                       wl.t0, T=wl.T, res=RES, flat_indices=idx)
+        got = grid_e2e.reshape(-1)[idx]
+        import hashlib
+        parity = {"max_abs": float(np.max(np.abs(got - want))), "n": int(len(idx)), "tol": 1e-10,
+                  "against": "oracle/qnmfits_oracle.py (numpy lstsq per fit) on sampled grid points, "
+                             "at least one per rank's slab",
+                  "grid_sha256": hashlib.sha256(np.ascontiguousarray(grid_e2e).tobytes()).hexdigest(),
+                  "grid_sha256_note": "identical for every --gpus N: sharding does not change a bit"}
+        assert parity["max_abs"] < 1e-10, f"N-GPU grid differs from the oracle by {parity['max_abs']}"
+
     # ---- roofline ------------------------------------------------------------------
     rows = sweep.rows_max
     flops_fit = _cabi.flops_per_fit(rows, len(wl.modes), 1, bool(plan.fast_mismatch))
@@ -312,7 +371,7 @@ def run_gpu_arm(args):
     }
 
     if rank == 0:
-        cpu = cpu_baseline_single(stride=2 if args.cpu_sample == "large" else 4) \
+        cpu = cpu_baseline_single(res=128 if args.cpu_sample == "large" else 64) \
             if world == 1 and not args.no_cpu else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -334,6 +393,8 @@ def run_gpu_arm(args):
             "roofline": roofline,
             "clocks": clocks.summary(),
         }
+        if parity is not None:
+            line["parity"] = parity
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
@@ -351,6 +412,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-sample", default="large", choices=["small", "large"])
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the grid")
+    ap.add_argument("--parity-points", type=int, default=512)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

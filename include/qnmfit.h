@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define QNMFIT_ABI_VERSION 4
+#define QNMFIT_ABI_VERSION 5
 
 /* limits of the compiled kernels */
 #define QNMFIT_MAX_MODES_SMALL 12    /* register-resident TSQR kernel (K1): 4-row blocks
@@ -148,7 +148,12 @@ typedef struct qnmfit_batch {
                                  (||Q^H d||^2, ||d||^2, the two end rows) instead of a
                                  second pass over the rows.  0: always the general
                                  weighted second pass.                                  */
-    int32_t reserved1;
+    int32_t plan_fits;        /* > 0: number of fits of the whole sweep this launch is a slab
+                                 of.  K1 chooses how many lanes share a fit (and with it the
+                                 order in which their partial factors are combined) from
+                                 (plan_fits, longest window, n_modes) only, so that a fit
+                                 gets the same bits whichever slab, rank or GPU count runs
+                                 it.  0: n_fits.                                         */
 
     double  *flagged_count;   /* f64 [1] or NULL: incremented (atomicAdd) once per fit
                                  whose status word is non-zero; lets a sweep detect

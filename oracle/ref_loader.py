@@ -1,10 +1,10 @@
 """
-TEST INFRASTRUCTURE — loads the *unmodified* reference modules from /root/reference.
-
-Only usable in the build container (the GPU box has no /root/reference).  Used by
-``tests/golden/make_golden.py`` to generate the committed fixtures and by the CPU
-tests (when the path exists) to pin ``oracle/qnmfits_oracle.py`` against the real
-thing.  Nothing in ``qnmfits_b200/`` may import this module.
+TEST / BENCH INFRASTRUCTURE — loads the *unmodified* reference modules: from /root/reference
+in the build container, else from ``oracle/_ref/`` (the same two modules byte-compiled by
+``oracle/make_ref.py`` — the GPU box has no /root/reference).  Used by
+``tests/golden/make_golden.py`` to generate the committed fixtures, by the tests to pin
+``oracle/qnmfits_oracle.py`` against the real thing, and by ``bench.py``'s CPU arms to time
+the reference's own functions.  Nothing in ``qnmfits_b200/`` may import this module.
 
 Recipe: the reference's ``qnmfits/qnmfits.py`` and
 ``qnmfits/qnm.py`` import matplotlib, mpl_toolkits, h5py and the ``qnm`` PyPI
@@ -20,10 +20,22 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("QNMFITS_REFERENCE_ROOT", "/root/reference")
+COMPILED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def reference_package_dir():
+    """Directory to import ``qnmfits.qnm`` / ``qnmfits.qnmfits`` from, or None."""
+    src = os.path.join(REFERENCE_ROOT, "qnmfits")
+    if os.path.isfile(os.path.join(src, "qnmfits.py")):
+        return src
+    built = os.path.join(COMPILED_ROOT, "qnmfits")
+    if os.path.isfile(os.path.join(built, "qnmfits.pyc")) and os.path.isfile(os.path.join(built, "qnm.pyc")):
+        return built
+    return None
 
 
 def reference_available():
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "qnmfits", "qnmfits.py"))
+    return reference_package_dir() is not None
 
 
 def _stub(name, **attrs):
@@ -41,8 +53,9 @@ def load_reference(modes_cache=None):
     global _loaded
     if _loaded is not None:
         return _loaded
-    if not reference_available():
-        raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
+    package_dir = reference_package_dir()
+    if package_dir is None:
+        raise RuntimeError(f"reference not found under {REFERENCE_ROOT} nor built under {COMPILED_ROOT}")
     if modes_cache is None:
         here = os.path.dirname(os.path.abspath(__file__))
         sys.path.insert(0, os.path.dirname(here))
@@ -64,7 +77,7 @@ def load_reference(modes_cache=None):
             _stub("h5py", File=None)
         _stub("qnm", modes_cache=modes_cache)
         pkg = types.ModuleType("qnmfits")
-        pkg.__path__ = [os.path.join(REFERENCE_ROOT, "qnmfits")]
+        pkg.__path__ = [package_dir]
         sys.modules["qnmfits"] = pkg
         ref = importlib.import_module("qnmfits.qnmfits")
     finally:

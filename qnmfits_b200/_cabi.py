@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libqnmfit.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_MODES_SMALL = 12
 MAX_MODES = 64
 MAX_PEERS = 8
@@ -44,7 +44,7 @@ class Batch(C.Structure):
         ("C", _dp),
         ("mismatch", _dp), ("residual", _dp), ("R", _dp), ("status", _dp),
         ("model", _dp), ("model_stride", C.c_int64),
-        ("uniform_weights", C.c_int32), ("reserved1", C.c_int32),
+        ("uniform_weights", C.c_int32), ("plan_fits", C.c_int32),
         ("flagged_count", _dp),
         ("series_index", _dp),
         ("omega_rows", _dp), ("coef_rows", _dp),

@@ -202,6 +202,10 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
     const int Mmax = b->row_end_all - b->row_begin_all;   // longest possible window
     if (kernel == QNMFIT_KERNEL_SMALL) {
         const int stage_rows = Mmax;
+        // Lanes per fit are chosen for the WHOLE sweep (plan_fits) on this device's SM count,
+        // never for the slab at hand: the split fixes the order in which a fit's partial
+        // factors are combined, and a fit must get the same bits on any slab / GPU count.
+        const int nplan = b->plan_fits > 0 ? b->plan_fits : b->n_fits;
         double best = 1e300;
         for (int lpf = 1; lpf <= 32; lpf *= 2) {
             const int fpc = k1_threads(N) / lpf;
@@ -222,7 +226,8 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
             if (smem < per_cta * 6 / 10) smem = per_cta * 6 / 10;   // pad so that no more CTAs become resident
 #endif
             const int ctas = (b->n_fits + fpc - 1) / fpc;
-            const int waves = (ctas + ctx->sm_count * want_cps - 1) / (ctx->sm_count * want_cps);
+            const int plan_ctas = (nplan + fpc - 1) / fpc;
+            const int waves = (plan_ctas + ctx->sm_count * want_cps - 1) / (ctx->sm_count * want_cps);
             const int mb = k1_block_rows(N);
             const int rpl = ((Mmax + lpf - 1) / lpf + mb - 1) / mb;
             const double blocks = rpl * (1.0 + 0.2) /* second pass ~ 20% of a first-pass block */

@@ -577,7 +577,7 @@ class _Sweep:
                 first_fit=lo, row_begin_all=rb_all, row_end_all=re_all, t0_all=t0_all,
                 row_begin_d=ptrs[2], row_end_d=ptrs[3], t0_d=ptrs[4],
                 coef_d=ptrs[5], coef_index_d=ptrs[6], n_coef=n_coef,
-                dt_nominal=dt, uniform_weights=uniform,
+                dt_nominal=dt, uniform_weights=uniform, plan_fits=n_fits,
                 mismatch_d=mismatch_d, flagged_d=flagged_d, **kw)
         self.rows_max = re_all - rb_all
 

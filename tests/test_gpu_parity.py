@@ -129,12 +129,19 @@ def test_full_size_grid_properties(qf, eng, oracle_tables):
     assert np.array_equal(grid, again)          # deterministic
 
 
-def test_slab_launches_are_bit_identical_to_one_launch(qf, eng):
-    """What each rank of an N-GPU job computes (first_fit offset) equals the
-    corresponding slab of the single launch, for several lanes-per-fit choices."""
+@pytest.mark.parametrize("res,slabs", [
+    (24, ((0, 100), (100, 101), (101, 400), (400, 576))),
+    (256, tuple((r * 8192, (r + 1) * 8192) for r in range(8))),          # the 8-GPU plan of the headline grid
+    (256, ((0, 32768), (32768, 65536))),                                 # the 2-GPU plan
+    (96, ((0, 1), (1, 2305), (2305, 9216))),
+])
+def test_slab_launches_are_bit_identical_to_one_launch(qf, eng, res, slabs):
+    """What each rank of an N-GPU job computes (first_fit offset, plan_fits = the whole sweep)
+    equals the corresponding slab of the single launch BIT FOR BIT: the lanes-per-fit split
+    (the reduction tree of a fit) is chosen from the sweep, not from the slab
+    (the multi-GPU grid is bit-identical to the 1-GPU grid)."""
     import torch
     from qnmfits_b200 import qnmfits as api
-    res = 24
     wl = workloads.config3(res=res)
     Mf = np.linspace(*wl.Mf_minmax, res)
     chi = np.linspace(*wl.chif_minmax, res)
@@ -150,9 +157,13 @@ def test_slab_launches_are_bit_identical_to_one_launch(qf, eng):
     full = eng.empty((n,), torch.float64)
     eng.fit(eng.make_batch(n_fits=n, mismatch_d=full, **d))
     parts = eng.empty((n,), torch.float64)
-    for lo, hi in ((0, 100), (100, 101), (101, 400), (400, n)):
-        eng.fit(eng.make_batch(n_fits=hi - lo, first_fit=lo, mismatch_d=parts[lo:hi], **d))
+    lanes = set()
+    for lo, hi in slabs:
+        b = eng.make_batch(n_fits=hi - lo, first_fit=lo, plan_fits=n, mismatch_d=parts[lo:hi], **d)
+        lanes.add(eng.ctx.plan(b).lanes_per_fit)
+        eng.fit(b)
     eng.synchronize()
+    assert lanes == {eng.ctx.plan(eng.make_batch(n_fits=n, mismatch_d=full, **d)).lanes_per_fit}
     assert torch.equal(full, parts)
 
 

@@ -1,9 +1,10 @@
 """Two NCCL ranks on two GPUs: sweeps sharded by flat fit index with the exchange fused into
 the fit kernels (peer stores + epoch flags, include/qnmfit.h ``qnmfit_fit_batch_peers``)
-must give, on EVERY rank, the bit-identical result of the NCCL all-gather path (same slabs,
-same launch plan) and the result of the unsharded single-GPU sweep to 1e-12 (the slab size
-may select another lanes-per-fit split, i.e. another summation tree).  Needs two GPUs;
-skipped on a one-GPU box."""
+must give, on EVERY rank, the bit-identical result of the NCCL all-gather path AND of the
+unsharded single-GPU sweep (the lanes-per-fit split, i.e. the summation tree of a fit, is
+chosen from the whole sweep — qnmfit_batch.plan_fits — never from the slab).  Needs two
+GPUs; skipped on a one-GPU box (tests/test_gpu_parity.py::test_slab_launches_are_bit_identical_
+to_one_launch checks the same property there by launching the slabs one after another)."""
 import os
 import socket
 import sys
@@ -97,7 +98,7 @@ def test_fused_exchange_two_gpus_bit_identical(tmp_path):
             one = got["single_" + name]
             assert np.all(np.isfinite(one))
             assert np.array_equal(got["fused_" + name], got["nccl_" + name]), (rank, name)
-            assert np.max(np.abs(got["fused_" + name] - one)) < 1e-12, (rank, name)
+            assert np.array_equal(got["fused_" + name], one), (rank, name)   # sharding does not change a bit
 
 
 def test_single_process_device_group_matches_one_device():
@@ -123,7 +124,7 @@ def test_single_process_device_group_matches_one_device():
     again = _sweeps(qf, wl3, wl2, wl4)
     for name, ref in one.items():
         assert two[name].shape == ref.shape and np.all(np.isfinite(two[name]))
-        assert np.max(np.abs(two[name] - ref)) < 1e-12, name
+        assert np.array_equal(two[name], ref), name
         assert np.array_equal(again[name], ref), name
     with pytest.raises(ValueError):
         qf.use_devices([0, 0])
