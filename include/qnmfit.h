@@ -60,12 +60,12 @@ extern "C" {
 
 /* per-fit status bits */
 #define QNMFIT_ST_OK            0
-#define QNMFIT_ST_RANK_DEFICIENT 1   /* |R_jj| <= 1024*eps*max(M,N)*max|R_jj| for some j:
-                                        numpy.linalg.lstsq(rcond=None) MAY truncate a
-                                        singular value (numpy/linalg/_linalg.py:2553; the
-                                        diagonal of R can sit ~700x above s_min/s_max, hence
-                                        the margin) — amplitudes are the basic QR solution;
-                                        the caller decides with the SVD of the exported R   */
+#define QNMFIT_ST_RANK_DEFICIENT 1   /* numpy.linalg.lstsq(rcond=None) MAY truncate a singular
+                                        value (numpy/linalg/_linalg.py:2553): the device's
+                                        estimate of s_min (inverse iteration on the triangle)
+                                        is within 8x of eps*max(M,N)*||R||_F — amplitudes are
+                                        the basic QR solution; the caller decides with the SVD
+                                        of the exported R (qnmfit_common.cuh)                 */
 #define QNMFIT_ST_NONFINITE     2    /* non-finite value met in inputs or outputs  */
 #define QNMFIT_ST_UNDERDETERMINED 4  /* rows <= columns                            */
 
@@ -74,6 +74,9 @@ extern "C" {
 #define QNMFIT_KERNEL_SMALL   1      /* K1: n_series == 1 and n_modes <= 12        */
 #define QNMFIT_KERNEL_GENERAL 2      /* K2: any n_series, n_modes <= 64            */
 #define QNMFIT_KERNEL_STRUCT  3      /* K3: n_modes + n_series <= 64, structured QR */
+#define QNMFIT_KERNEL_PANEL   4      /* K4: structured QR, blocked (compact WY) with the
+                                        trailing update on the FP64 tensor cores (DMMA);
+                                        any n_modes <= 64 whose tile fits shared memory */
 
 typedef struct qnmfit_ctx qnmfit_ctx;
 
@@ -173,6 +176,21 @@ typedef struct qnmfit_batch {
                                     omega / omega_tilde                                 */
     const double  *coef_rows;    /* c128[L][N][n_times] or NULL: mu_ij at sample k;
                                     replaces coef                                       */
+
+    /* ---- flagged fits and their repair ---- */
+    int32_t *flag_list;          /* i32 [2 * flag_capacity] or NULL: every fit whose status word
+                                    is non-zero appends (fit, status) at the cursor given by
+                                    the old value of *flagged_count (entries beyond the
+                                    capacity are dropped; the count stays exact)          */
+    int32_t flag_capacity;
+    int32_t reserved2;
+    const int32_t *fit_index;    /* i32 [B] or NULL: a launch over a SUBSET of a sweep's fits.
+                                    Fit b of the launch reads every per-fit input (windows,
+                                    t0, omega, chi / Mf / coef / series indices, the implicit
+                                    grid index first_fit + .) under index fit_index[b] and
+                                    stores its outputs at b.  With plan_fits of the sweep the
+                                    arithmetic of a fit is that of the sweep's own launch —
+                                    how the host repairs exactly the flagged fits          */
 } qnmfit_batch;
 
 /* Create / destroy a context bound to one CUDA device (one process per GPU). */
@@ -253,6 +271,28 @@ int qnmfit_h2d_wait(qnmfit_ctx *ctx);
 int qnmfit_d2h(qnmfit_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes, void *stream, int sync);
 int qnmfit_zero(qnmfit_ctx *ctx, void *dst_dev, size_t bytes, void *stream);
 int qnmfit_stream_sync(qnmfit_ctx *ctx, void *stream);
+
+/* One sweep with HOST inputs and a HOST result in a single call — what the loops of
+ * mismatch_M_chi_grid / mismatch_t0_array (reference qnmfits/qnmfits.py:1271-1281,
+ * :1391-1410) cost through this library: copy `n_uploads` host arrays into their device
+ * locations (staged through pinned memory owned by the ctx; QNMFIT_RUN_COALESCE: the
+ * destinations ascend inside ONE device allocation and everything between them is padding,
+ * so they travel in one cudaMemcpyAsync), zero *b->flagged_count (QNMFIT_RUN_ZERO_COUNTER),
+ * launch the fits (with the peer exchange when `peers` is not NULL), copy `result_bytes`
+ * from `result_dev` back to `result_host` (QNMFIT_RUN_RESULT_PINNED: `result_host` is
+ * page-locked, copy straight into it) and wait for the stream. */
+typedef struct qnmfit_copy {
+    void       *dst_dev;
+    const void *src_host;
+    size_t      bytes;
+} qnmfit_copy;
+#define QNMFIT_RUN_COALESCE      1
+#define QNMFIT_RUN_ZERO_COUNTER  2
+#define QNMFIT_RUN_RESULT_PINNED 4
+int qnmfit_run_host(qnmfit_ctx *ctx, const qnmfit_batch *b, const qnmfit_peers *peers,
+                    const qnmfit_copy *uploads, int n_uploads,
+                    const void *result_dev, void *result_host, size_t result_bytes,
+                    int flags, void *stream);
 
 /* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
 int64_t qnmfit_launch_count(const qnmfit_ctx *ctx);

@@ -11,6 +11,7 @@ module-level provider *instance* ``qnm`` which shadows the class of the same nam
 """
 from .qnm import qnm, set_table_provider  # noqa: F401  (class; shadowed below)
 from .qnmfits import *  # noqa: F401,F403  (functions + the `qnm` instance)
+from .qnmfits import clear_sweep_cache  # noqa: F401
 from ._dist import use_devices  # noqa: F401  (single-process multi-GPU sweeps)
 
 __version__ = "0.1.0"

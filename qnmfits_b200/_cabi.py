@@ -15,7 +15,7 @@ MAX_MODES_SMALL = 12
 MAX_MODES = 64
 MAX_PEERS = 8
 
-KERNEL_AUTO, KERNEL_SMALL, KERNEL_GENERAL, KERNEL_STRUCT = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_SMALL, KERNEL_GENERAL, KERNEL_STRUCT, KERNEL_PANEL = 0, 1, 2, 3, 4
 
 ST_RANK_DEFICIENT, ST_NONFINITE, ST_UNDERDETERMINED = 1, 2, 4
 
@@ -48,6 +48,8 @@ class Batch(C.Structure):
         ("flagged_count", _dp),
         ("series_index", _dp),
         ("omega_rows", _dp), ("coef_rows", _dp),
+        ("flag_list", _dp), ("flag_capacity", C.c_int32), ("reserved2", C.c_int32),
+        ("fit_index", _dp),
     ]
 
     def __init__(self, **kw):
@@ -69,6 +71,14 @@ class Peers(C.Structure):
         self.struct_size = C.sizeof(Peers)
 
 
+class Copy(C.Structure):
+    """Mirror of ``struct qnmfit_copy`` (one host -> device upload of ``qnmfit_run_host``)."""
+    _fields_ = [("dst_dev", _dp), ("src_host", _dp), ("bytes", C.c_size_t)]
+
+
+RUN_COALESCE, RUN_ZERO_COUNTER, RUN_RESULT_PINNED = 1, 2, 4
+
+
 class Plan(C.Structure):
     _fields_ = [
         ("kernel", C.c_int32), ("lanes_per_fit", C.c_int32),
@@ -86,6 +96,7 @@ EXPORTS = (
     "qnmfit_peer_alloc", "qnmfit_peer_open", "qnmfit_peer_close", "qnmfit_peer_free",
     "qnmfit_fit_batch_peers",
     "qnmfit_h2d", "qnmfit_h2d_wait", "qnmfit_d2h", "qnmfit_zero", "qnmfit_stream_sync",
+    "qnmfit_run_host",
 )
 
 _lib = None
@@ -139,6 +150,9 @@ def load_library(path=None):
     lib.qnmfit_zero.restype = C.c_int
     lib.qnmfit_stream_sync.argtypes = [C.c_void_p, C.c_void_p]
     lib.qnmfit_stream_sync.restype = C.c_int
+    lib.qnmfit_run_host.argtypes = [C.c_void_p, C.POINTER(Batch), C.POINTER(Peers), C.POINTER(Copy), C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+    lib.qnmfit_run_host.restype = C.c_int
     lib.qnmfit_launch_count.argtypes = [C.c_void_p]
     lib.qnmfit_launch_count.restype = C.c_int64
     lib.qnmfit_plan_batch.argtypes = [C.c_void_p, C.POINTER(Batch), C.POINTER(Plan)]
@@ -213,6 +227,13 @@ class Context:
 
     def stream_sync(self, stream=0):
         self._check(self.lib.qnmfit_stream_sync(self.handle, stream))
+
+    def run_host(self, batch, peers, uploads, n_uploads, result_dev, result_host, result_bytes, flags, stream=0):
+        """``qnmfit_run_host``: uploads, launch, download, synchronise in one C call.
+        ``uploads`` is a ctypes array of ``Copy`` (or None), ``peers`` a ``Peers`` or None."""
+        self._check(self.lib.qnmfit_run_host(
+            self.handle, C.byref(batch), None if peers is None else C.byref(peers), uploads, n_uploads,
+            result_dev, result_host, result_bytes, flags, stream))
 
     def plan(self, batch):
         plan = Plan()

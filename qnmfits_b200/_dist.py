@@ -128,6 +128,7 @@ class PeerWindow:
                 self.ptrs.append(ptr)
         self.view = torch.as_tensor(_DeviceMemory(self.local_ptr, self.n_words), device=eng.device)
         self.epoch = 0
+        self.closed = False
         self._peers = {}
         self.timeout_ns = int(float(os.environ.get("QNMFITS_B200_PEER_TIMEOUT_S", "600")) * 1e9)
 
@@ -163,6 +164,7 @@ class PeerWindow:
 
     def close(self):
         import torch.distributed as dist
+        self.closed = True               # prepared sweeps that hold this window must not reuse it
         self.eng.synchronize()
         dist.barrier()                       # nobody writes into a window that is going away
         for ptr in self._opened:

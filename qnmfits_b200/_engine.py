@@ -235,7 +235,8 @@ class Engine:
                    C_d=None, mismatch_d=None, residual_d=None, R_d=None, status_d=None,
                    model_d=None, model_stride=0, uniform_weights=False,
                    n_times=None, series_stride=None, flagged_d=None, series_index_d=None,
-                   omega_rows_d=None, coef_rows_d=None, plan_fits=0):
+                   omega_rows_d=None, coef_rows_d=None, plan_fits=0,
+                   flag_list_d=None, flag_capacity=0, fit_index_d=None):
         def p(t):                              # device pointer: int, None, or a torch tensor
             return t if t is None or type(t) is int else t.data_ptr()
         if n_times is None:
@@ -258,7 +259,8 @@ class Engine:
             status=p(status_d), model=p(model_d), model_stride=int(model_stride),
             uniform_weights=1 if uniform_weights else 0, flagged_count=p(flagged_d),
             series_index=p(series_index_d), omega_rows=p(omega_rows_d), coef_rows=p(coef_rows_d),
-            plan_fits=int(plan_fits))
+            plan_fits=int(plan_fits), flag_list=p(flag_list_d), flag_capacity=int(flag_capacity),
+            fit_index=p(fit_index_d))
         return b
 
     def fit(self, batch):

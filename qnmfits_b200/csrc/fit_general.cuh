@@ -65,9 +65,10 @@ fit_general_kernel(const __grid_constant__ FitParams p, const int TR, const int 
     GeneralSmem sm;
     sm.carve(smem_raw, N, L, TR, TK);
 
-    int rb = p.row_begin ? p.row_begin[fit] : p.row_begin_all;
-    int re = p.row_end ? p.row_end[fit] : p.row_end_all;
-    const double t0 = p.t0 ? p.t0[fit] : p.t0_all;
+    const int fi = input_fit(p, fit);             // index of the fit's inputs (see input_fit)
+    int rb = p.row_begin ? p.row_begin[fi] : p.row_begin_all;
+    int re = p.row_end ? p.row_end[fi] : p.row_end_all;
+    const double t0 = p.t0 ? p.t0[fi] : p.t0_all;
     if (rb < 0) rb = 0;
     if (re > p.n_times) re = p.n_times;
     if (re < rb) re = rb;
@@ -75,11 +76,11 @@ fit_general_kernel(const __grid_constant__ FitParams p, const int TR, const int 
     const long long Mrows = (long long)K * L;
     const double2 *coef = nullptr;
     if (p.coef) {
-        const int ci = p.coef_index ? p.coef_index[fit] : fit_chi_index(p, fit);
+        const int ci = p.coef_index ? p.coef_index[fi] : fit_chi_index(p, fi);
         coef = p.coef + (long long)ci * L * N;
     }
 
-    for (int j = tid; j < N; j += K2_THREADS) sm.om[j] = fit_omega(p, fit, j);
+    for (int j = tid; j < N; j += K2_THREADS) sm.om[j] = fit_omega(p, fi, j);
     for (int e = tid; e < N * (N + 1); e += K2_THREADS) sm.R[e] = make_double2(0.0, 0.0);
     for (int e = tid; e < 2 * N; e += K2_THREADS) sm.diag[e] = 0.0;
     __syncthreads();
@@ -187,7 +188,11 @@ fit_general_kernel(const __grid_constant__ FitParams p, const int TR, const int 
                 dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, s));
             }
             const double dim = (double)(Mrows > N ? Mrows : N);
-            if (!(dmin > QNMFIT_RANK_FLAG_MARGIN * 2.220446049250313e-16 * dim * dmax)) status |= QNMFIT_ST_RANK_DEFICIENT_;
+            if (!(dmin > QNMFIT_RANK_PREFILTER * QNMFIT_EPS * dim * dmax)) {   // rare: confirm (qnmfit_common.cuh)
+                if (rank_suspect_warp([&](int j, int k) { return sm.R[j * (N + 1) + k]; }, [&](int j) { return dg[j]; },
+                                      N, dim, sm.Cv, lane))
+                    status |= QNMFIT_ST_RANK_DEFICIENT_;
+            }
             if (Mrows <= N) status |= QNMFIT_ST_UNDERDETERMINED_;
             if (p.R) {
                 double2 *Rout = p.R + (long long)fit * N * (N + 1);
@@ -293,7 +298,7 @@ fit_general_kernel(const __grid_constant__ FitParams p, const int TR, const int 
         p.mismatch[fit] = mm;
         if (p.residual) p.residual[fit] = a3;
         if (p.status) p.status[fit] = status;
-        note_status(p, status);
+        note_status(p, fit, status);
         peer_publish(p, fit, mm);
     }
 }

@@ -118,10 +118,11 @@ QF_HD SmallLane small_lane_setup(const FitParams &p, int cta, int tid, int threa
     L.t0 = 0.0;
     L.d_off = 0;
     if (L.fit >= 0) {
-        if (per_fit_data && p.series_index) L.d_off = (long long)p.series_index[fit] * p.series_stride;
-        L.rb = p.row_begin ? p.row_begin[fit] : p.row_begin_all;
-        L.re = p.row_end ? p.row_end[fit] : p.row_end_all;
-        L.t0 = p.t0 ? p.t0[fit] : p.t0_all;
+        const int fi = input_fit(p, fit);
+        if (per_fit_data && p.series_index) L.d_off = (long long)p.series_index[fi] * p.series_stride;
+        L.rb = p.row_begin ? p.row_begin[fi] : p.row_begin_all;
+        L.re = p.row_end ? p.row_end[fi] : p.row_end_all;
+        L.t0 = p.t0 ? p.t0[fi] : p.t0_all;
         if (L.rb < 0) L.rb = 0;
         if (L.re > p.n_times) L.re = p.n_times;
         if (L.re < L.rb) L.re = L.rb;
@@ -703,8 +704,15 @@ QF_HD void small_backsub(const FitParams &p, const SmallSmem<N, THREADS> &sm, co
         dmax = a > dmax ? a : dmax;
         dmin = a < dmin ? a : dmin;
     }
-    const double cut = QNMFIT_RANK_FLAG_MARGIN * 2.220446049250313e-16 * (double)(M > N ? M : N) * dmax;
-    if (!(dmin > cut)) status |= QNMFIT_ST_RANK_DEFICIENT_;
+    const double dim = (double)(M > N ? M : N);
+    if (!(dmin > QNMFIT_RANK_PREFILTER * QNMFIT_EPS * dim * dmax)) {
+        // rare: confirm with an estimate of the smallest singular value (qnmfit_common.cuh)
+        const double *Rd = sm.Rd + tid;
+        const double2 *Ro = sm.Ro + tid;
+        if (rank_suspect_serial<N>([&](int j, int k) { return Ro[LY::pair(j, k) * THREADS]; },
+                                   [&](int j) { return Rd[j * THREADS]; }, dim))
+            status |= QNMFIT_ST_RANK_DEFICIENT_;
+    }
     if (M <= N) status |= QNMFIT_ST_UNDERDETERMINED_;
     if (p.R) {
         double2 *Rout = p.R + (long long)L.fit * N * (N + 1);
@@ -813,7 +821,7 @@ QF_HD void small_finalize(const FitParams &p, const SmallLane &L, const double (
     p.mismatch[L.fit] = mm;
     if (p.residual) p.residual[L.fit] = sums[3];
     if (p.status) p.status[L.fit] = status;
-    note_status(p, status);
+    note_status(p, L.fit, status);
     peer_publish(p, L.fit, mm);
 }
 
@@ -861,7 +869,7 @@ QF_HD void small_fast_finalize(const FitParams &p, const SmallLane &L, const dou
     p.mismatch[L.fit] = mm;
     if (p.residual) p.residual[L.fit] = tot[1];
     if (p.status) p.status[L.fit] = status;
-    note_status(p, status);
+    note_status(p, L.fit, status);
     peer_publish(p, L.fit, mm);
 }
 
@@ -898,7 +906,7 @@ __global__ void __launch_bounds__(THREADS, 1) fit_small_kernel(const __grid_cons
         const int slot = idx / N, j = idx - slot * N;
         const int fit = cta_first + slot;
         if (fit < p.n_fits) {
-            const double2 w = fit_omega(p, fit, j);
+            const double2 w = fit_omega(p, input_fit(p, fit), j);
             sm.om[j * fpc + slot] = w;
             if (p.dt_nominal > 0.0) {
                 const double2 q = design_entry(w, p.dt_nominal);

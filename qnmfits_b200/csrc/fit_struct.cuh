@@ -267,87 +267,23 @@ __device__ __forceinline__ void k3c_load2(double2 (&X)[RPT], const Struct3Smem &
     }
 }
 
-template <int G, int RPT>
-#define K3C_MINB(G, RPT) (RPT >= 32 ? (G == 1 ? 4 : 2) : G <= 2 ? 4 : G == 4 ? 2 : 1)
-__global__ void __launch_bounds__(64 * G, K3C_MINB(G, RPT)) fit_struct3_kernel(const __grid_constant__ FitParams p)
+// Everything after the factorisation, shared by K3 and K4 (fit_panel.cuh): rank flag,
+// export of the factor, back-substitution, then either the mismatch from the by-products of
+// the factorisation (uniform grids) or the second streaming pass (model, trapezoid sums).
+// SM provides R1, R2 (PackedR), diag1, diag2, Cv, om, scratch, red, ends as Struct3Smem does.
+// sdd = this thread's share of sum |d|^2, res2 = its share of the annihilated rhs entries.
+template <class SM>
+__device__ __forceinline__ void struct_finish(const FitParams &p, const SM &sm, const int fit, const int N, const int L,
+                                              const int rb, const int re, const double t0, const double2 *coef,
+                                              const bool two_phase, double sdd, double res2)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int TR = G * RPT;
-    static_assert(TR <= K3C_MAXROWS, "tile taller than the v buffer");
-    const int N = p.n_modes, L = p.n_series, NC = N + L;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nwarps = nthr >> 5;
-    const int c = tid / G, g = tid % G;
-    const int fit = blockIdx.x;
-    Struct3Smem sm;
-    sm.carve(smem_raw, N, L);
-
-    int rb = p.row_begin ? p.row_begin[fit] : p.row_begin_all;
-    int re = p.row_end ? p.row_end[fit] : p.row_end_all;
-    const double t0 = p.t0 ? p.t0[fit] : p.t0_all;
-    if (rb < 0) rb = 0;
-    if (re > p.n_times) re = p.n_times;
-    if (re < rb) re = rb;
     const int K = re - rb;
     const long long Mrows = (long long)K * L;
-    const double2 *coef = nullptr;
-    if (p.coef) {
-        const int ci = p.coef_index ? p.coef_index[fit] : fit_chi_index(p, fit);
-        coef = p.coef + (long long)ci * L * N;
-    }
-    const bool two_phase = (coef != nullptr) || L > 1;
-
-    for (int j = tid; j < N; j += nthr) {
-        const double2 w = fit_omega(p, fit, j);
-        sm.om[j] = w;
-        if (p.dt_nominal > 0.0) {
-            const double2 q = design_entry(w, p.dt_nominal);
-            sm.qq[j] = q;
-            sm.qw[j] = c_mul(q, make_double2(w.y, -w.x));
-        }
-        sm.diag1[j] = 0.0;
-        sm.diag2[j] = 0.0;
-    }
-    {
-        const int n1 = (int)PackedR::entries(N, NC - 1), n2 = (int)PackedR::entries(N, N);
-        for (int e = tid; e < n1; e += nthr) sm.R1.a[e] = make_double2(0.0, 0.0);
-        for (int e = tid; e < n2; e += nthr) sm.R2.a[e] = make_double2(0.0, 0.0);
-    }
-    __syncthreads();
-
     int status = 0;
-    double sdd = 0.0, res2 = 0.0;
-    int buf = 0;
-    double2 X[RPT];
-
     if (!p.eval_only) {
-        // ---------------- phase 1: [E | d_1..d_L] ----------------
-        const int ntiles = (K + TR - 1) / TR;
-#pragma unroll 1
-        for (int tile = 0; tile < ntiles; ++tile) {
-            k3c_load1<RPT>(X, p, sm, c, N, NC, rb + tile * TR + g * RPT, re, t0, sdd);
-            double part = k3c_norm2<RPT>(X);
-            k3c_reflect<G, RPT>(X, part, c, g, NC, N, 0, sm.R1, sm.diag1, sm.vbuf, sm.scal, buf);
-            if (c >= N && c < NC) res2 += part;
-        }
-        __syncthreads();
-
-        // ---------------- phase 2: stacked [R_E D_i | Y_i] ----------------
         const PackedR &Rf = two_phase ? sm.R2 : sm.R1;
         double *dgf = two_phase ? sm.diag2 : sm.diag1;
-        if (two_phase) {
-            const int rows2 = N * L;
-            const int ntiles2 = (rows2 + TR - 1) / TR;
-#pragma unroll 1
-            for (int tile = 0; tile < ntiles2; ++tile) {
-                const int jstart = (tile * TR) / L;             // first non-zero column of the tile
-                k3c_load2<RPT>(X, sm, coef, c, N, L, tile * TR + g * RPT, rows2);
-                double part = k3c_norm2<RPT>(X);
-                k3c_reflect<G, RPT>(X, part, c, g, N + 1, N, jstart, sm.R2, sm.diag2, sm.vbuf, sm.scal, buf);
-                if (c == N) res2 += part;
-            }
-            __syncthreads();
-        }
-
         // ---------------- back-substitution (warp 0) ----------------
         if (warp == 0) {
             double dmax = 0.0, dmin = 1e300;
@@ -362,7 +298,11 @@ __global__ void __launch_bounds__(64 * G, K3C_MINB(G, RPT)) fit_struct3_kernel(c
                 dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, s));
             }
             const double dim = (double)(Mrows > N ? Mrows : N);
-            if (!(dmin > QNMFIT_RANK_FLAG_MARGIN * 2.220446049250313e-16 * dim * dmax)) status |= QNMFIT_ST_RANK_DEFICIENT_;
+            if (!(dmin > QNMFIT_RANK_PREFILTER * QNMFIT_EPS * dim * dmax)) {   // rare: confirm (qnmfit_common.cuh)
+                if (rank_suspect_warp([&](int j, int k) { return Rf.at(j, k); }, [&](int j) { return dgf[j]; }, N, dim,
+                                      sm.Cv, lane))
+                    status |= QNMFIT_ST_RANK_DEFICIENT_;
+            }
             if (Mrows <= N) status |= QNMFIT_ST_UNDERDETERMINED_;
             if (p.R) {
                 double2 *Rout = p.R + (long long)fit * N * (N + 1);
@@ -457,7 +397,7 @@ __global__ void __launch_bounds__(64 * G, K3C_MINB(G, RPT)) fit_struct3_kernel(c
                 p.mismatch[fit] = mm;
                 if (p.residual) p.residual[fit] = res2;
                 if (p.status) p.status[fit] = status;
-                note_status(p, status);
+                note_status(p, fit, status);
                 peer_publish(p, fit, mm);
             }
             return;
@@ -524,8 +464,89 @@ __global__ void __launch_bounds__(64 * G, K3C_MINB(G, RPT)) fit_struct3_kernel(c
         p.mismatch[fit] = mm;
         if (p.residual) p.residual[fit] = p.eval_only ? a3 : res2;
         if (p.status) p.status[fit] = status;
-        note_status(p, status);
+        note_status(p, fit, status);
         peer_publish(p, fit, mm);
     }
+}
+
+template <int G, int RPT>
+#define K3C_MINB(G, RPT) (RPT >= 32 ? (G == 1 ? 4 : 2) : G <= 2 ? 4 : G == 4 ? 2 : 1)
+__global__ void __launch_bounds__(64 * G, K3C_MINB(G, RPT)) fit_struct3_kernel(const __grid_constant__ FitParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int TR = G * RPT;
+    static_assert(TR <= K3C_MAXROWS, "tile taller than the v buffer");
+    const int N = p.n_modes, L = p.n_series, NC = N + L;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nwarps = nthr >> 5;
+    const int c = tid / G, g = tid % G;
+    const int fit = blockIdx.x;
+    Struct3Smem sm;
+    sm.carve(smem_raw, N, L);
+
+    const int fi = input_fit(p, fit);             // index of the fit's inputs (see input_fit)
+    int rb = p.row_begin ? p.row_begin[fi] : p.row_begin_all;
+    int re = p.row_end ? p.row_end[fi] : p.row_end_all;
+    const double t0 = p.t0 ? p.t0[fi] : p.t0_all;
+    if (rb < 0) rb = 0;
+    if (re > p.n_times) re = p.n_times;
+    if (re < rb) re = rb;
+    const int K = re - rb;
+    const double2 *coef = nullptr;
+    if (p.coef) {
+        const int ci = p.coef_index ? p.coef_index[fi] : fit_chi_index(p, fi);
+        coef = p.coef + (long long)ci * L * N;
+    }
+    const bool two_phase = (coef != nullptr) || L > 1;
+
+    for (int j = tid; j < N; j += nthr) {
+        const double2 w = fit_omega(p, fi, j);
+        sm.om[j] = w;
+        if (p.dt_nominal > 0.0) {
+            const double2 q = design_entry(w, p.dt_nominal);
+            sm.qq[j] = q;
+            sm.qw[j] = c_mul(q, make_double2(w.y, -w.x));
+        }
+        sm.diag1[j] = 0.0;
+        sm.diag2[j] = 0.0;
+    }
+    {
+        const int n1 = (int)PackedR::entries(N, NC - 1), n2 = (int)PackedR::entries(N, N);
+        for (int e = tid; e < n1; e += nthr) sm.R1.a[e] = make_double2(0.0, 0.0);
+        for (int e = tid; e < n2; e += nthr) sm.R2.a[e] = make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+
+    double sdd = 0.0, res2 = 0.0;
+    int buf = 0;
+    double2 X[RPT];
+
+    if (!p.eval_only) {
+        // ---------------- phase 1: [E | d_1..d_L] ----------------
+        const int ntiles = (K + TR - 1) / TR;
+#pragma unroll 1
+        for (int tile = 0; tile < ntiles; ++tile) {
+            k3c_load1<RPT>(X, p, sm, c, N, NC, rb + tile * TR + g * RPT, re, t0, sdd);
+            double part = k3c_norm2<RPT>(X);
+            k3c_reflect<G, RPT>(X, part, c, g, NC, N, 0, sm.R1, sm.diag1, sm.vbuf, sm.scal, buf);
+            if (c >= N && c < NC) res2 += part;
+        }
+        __syncthreads();
+
+        // ---------------- phase 2: stacked [R_E D_i | Y_i] ----------------
+        if (two_phase) {
+            const int rows2 = N * L;
+            const int ntiles2 = (rows2 + TR - 1) / TR;
+#pragma unroll 1
+            for (int tile = 0; tile < ntiles2; ++tile) {
+                const int jstart = (tile * TR) / L;             // first non-zero column of the tile
+                k3c_load2<RPT>(X, sm, coef, c, N, L, tile * TR + g * RPT, rows2);
+                double part = k3c_norm2<RPT>(X);
+                k3c_reflect<G, RPT>(X, part, c, g, N + 1, N, jstart, sm.R2, sm.diag2, sm.vbuf, sm.scal, buf);
+                if (c == N) res2 += part;
+            }
+            __syncthreads();
+        }
+    }
+    struct_finish(p, sm, fit, N, L, rb, re, t0, coef, two_phase, sdd, res2);
 }
 #endif  // !QNMFIT_HOSTSIM

@@ -40,6 +40,12 @@ size_t k3_smem_bytes(int N, int L);
 const void *k3_kernel_ptr(int G, int RPT);                  // NULL: form not compiled
 cudaError_t k3_launch(int G, int RPT, int grid, int block, size_t smem, cudaStream_t st, const FitParams &p);
 
+// ---- K4 (fit_panel.cuh): blocked Householder, trailing update on the FP64 tensor cores ------
+size_t k4_smem_bytes(int N, int L);
+int k4_threads();
+const void *k4_kernel_ptr();
+cudaError_t k4_launch(int grid, size_t smem, cudaStream_t st, const FitParams &p);
+
 // ---- multi-GPU epoch barrier (qnmfit_common.cuh) and the FP64 peak micro-benchmarks ------
 cudaError_t peer_barrier_launch(cudaStream_t st, const FitParams &p);
 cudaError_t fp64_peak_launch(int kind, int grid, int block, double *out, int iters);

@@ -22,6 +22,8 @@ struct qnmfit_ctx {
     cudaEvent_t h2d_event;        // recorded after the most recent qnmfit_h2d
     int h2d_pending;
     double *peer_scratch;         // device: flagged-fit counter of qnmfit_fit_batch_peers when the caller gives none
+    unsigned char *stage_up, *stage_down;   // pinned staging of qnmfit_run_host
+    size_t stage_up_bytes, stage_down_bytes;
     char err[512];
 };
 
@@ -70,6 +72,8 @@ extern "C" int qnmfit_create(int device, qnmfit_ctx **out)
     ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
     ctx->launches = 0;
     ctx->peer_scratch = nullptr;
+    ctx->stage_up = ctx->stage_down = nullptr;
+    ctx->stage_up_bytes = ctx->stage_down_bytes = 0;
     ctx->h2d_event = nullptr;
     ctx->h2d_pending = 0;
     ctx->err[0] = 0;
@@ -86,6 +90,10 @@ extern "C" int qnmfit_create(int device, qnmfit_ctx **out)
         }
     e = cudaFuncSetAttribute(k2_kernel_ptr(), cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
     if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaFuncSetAttribute(K2)"); delete ctx; return r; }
+    e = cudaFuncSetAttribute(k4_kernel_ptr(), cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k4_kernel_ptr(), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaFuncSetAttribute(K4)"); delete ctx; return r; }
     for (int f = 0; f < K3_FORMS; ++f) {
         const void *k3 = k3_kernel_ptr(k3_forms[f][0], k3_forms[f][1]);
         e = cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
@@ -103,6 +111,8 @@ extern "C" int qnmfit_destroy(qnmfit_ctx *ctx)
 {
     if (ctx && ctx->peer_scratch) { cudaSetDevice(ctx->device); cudaFree(ctx->peer_scratch); }
     if (ctx && ctx->h2d_event) cudaEventDestroy(ctx->h2d_event);
+    if (ctx && ctx->stage_up) cudaFreeHost(ctx->stage_up);
+    if (ctx && ctx->stage_down) cudaFreeHost(ctx->stage_down);
     delete ctx;
     return 0;
 }
@@ -171,6 +181,8 @@ static int validate(qnmfit_ctx *ctx, const qnmfit_batch *b, bool eval)
     if (b->anchor_rows < 0 || (b->anchor_rows % 4) != 0)
         return fail(ctx, QNMFIT_E_SHAPE, "anchor_rows %d must be a non-negative multiple of 4", b->anchor_rows);
     if (!(b->dt_nominal >= 0.0)) return fail(ctx, QNMFIT_E_SHAPE, "dt_nominal must be >= 0");
+    if (b->flag_list && b->flag_capacity < 1)
+        return fail(ctx, QNMFIT_E_SHAPE, "flag_list needs flag_capacity >= 1 (and flagged_count, its cursor)");
     return 0;
 }
 
@@ -184,8 +196,17 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
         && !b->omega_rows && !b->coef_rows;
     const bool struct_ok = !b->coef_rows && b->n_modes + b->n_series <= 64
         && k3_smem_bytes(b->n_modes, b->n_series) <= (size_t)ctx->smem_optin;
-    if (kernel == QNMFIT_KERNEL_AUTO)
-        kernel = small_ok ? QNMFIT_KERNEL_SMALL : struct_ok ? QNMFIT_KERNEL_STRUCT : QNMFIT_KERNEL_GENERAL;
+    const bool panel_ok = !b->coef_rows && b->n_series <= 64
+        && k4_smem_bytes(b->n_modes, b->n_series) <= (size_t)ctx->smem_optin;
+    if (kernel == QNMFIT_KERNEL_AUTO) {
+        const char *force = getenv("QNMFIT_AUTO_STRUCT");     // developer knob: K3 instead of K4
+        kernel = small_ok ? QNMFIT_KERNEL_SMALL
+               : panel_ok && !(force && force[0] == '1' && struct_ok) ? QNMFIT_KERNEL_PANEL
+               : struct_ok ? QNMFIT_KERNEL_STRUCT : QNMFIT_KERNEL_GENERAL;
+    }
+    if (kernel == QNMFIT_KERNEL_PANEL && !panel_ok)
+        return fail(ctx, QNMFIT_E_SHAPE, "K4 needs no per-row coef table and a tile that fits shared memory (n_modes=%d, n_series=%d)",
+                    b->n_modes, b->n_series);
     if (kernel == QNMFIT_KERNEL_STRUCT && !struct_ok)
         return fail(ctx, QNMFIT_E_SHAPE, "K3 needs n_modes + n_series <= 64 (got %d + %d) and no per-row coef table",
                     b->n_modes, b->n_series);
@@ -195,7 +216,8 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
     if (b->series_index && kernel != QNMFIT_KERNEL_SMALL)
         return fail(ctx, QNMFIT_E_SHAPE, "series_index is supported by K1 only (n_modes <= %d, no coef table)",
                     QNMFIT_MAX_MODES_SMALL);
-    if (kernel != QNMFIT_KERNEL_SMALL && kernel != QNMFIT_KERNEL_GENERAL && kernel != QNMFIT_KERNEL_STRUCT)
+    if (kernel != QNMFIT_KERNEL_SMALL && kernel != QNMFIT_KERNEL_GENERAL && kernel != QNMFIT_KERNEL_STRUCT
+        && kernel != QNMFIT_KERNEL_PANEL)
         return fail(ctx, QNMFIT_E_SHAPE, "unknown kernel id %d", b->kernel);
     pl->kernel = kernel;
     const int N = b->n_modes;
@@ -240,6 +262,9 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
             }
         }
         if (best >= 1e300) return fail(ctx, QNMFIT_E_SHAPE, "K1: no lanes-per-fit choice fits shared memory");
+    } else if (kernel == QNMFIT_KERNEL_PANEL) {
+        pl->lpf = 1; pl->smem = k4_smem_bytes(b->n_modes, b->n_series);
+        pl->grid = b->n_fits; pl->block = k4_threads();
     } else if (kernel == QNMFIT_KERNEL_STRUCT) {
         pl->lpf = ctx->k3_g; pl->TR = ctx->k3_g * ctx->k3_rpt;
         pl->smem = k3_smem_bytes(b->n_modes, b->n_series);
@@ -286,6 +311,8 @@ static void fill_params(const qnmfit_batch *b, const Plan &pl, bool eval, FitPar
     p->R = (double2 *)b->R; p->status = b->status;
     p->model = (double2 *)b->model; p->model_stride = b->model_stride; p->omega_shared = b->omega_shared;
     p->flagged_count = b->flagged_count;
+    p->flag_list = b->flag_list; p->flag_capacity = b->flag_list ? b->flag_capacity : 0;
+    p->fit_index = b->fit_index;
     p->lanes_per_fit = pl.lpf; p->eval_only = eval ? 1 : 0;
     p->fast_mismatch = (pl.kernel != QNMFIT_KERNEL_GENERAL && !eval && b->uniform_weights && b->dt_nominal > 0.0 && !b->model) ? 1 : 0;
     p->stage_begin = pl.stage_begin; p->stage_rows = pl.stage_rows;
@@ -301,6 +328,7 @@ static int validate_peers(qnmfit_ctx *ctx, const qnmfit_batch *b, const qnmfit_p
     for (int r = 0; r < pe->n_peers; ++r)
         if (!pe->mismatch[r] || !pe->flagged[r] || !pe->flags[r])
             return fail(ctx, QNMFIT_E_NULL, "peer %d: mismatch, flagged and flags are required", r);
+    if (b->fit_index) return fail(ctx, QNMFIT_E_PEER, "fit_index launches (repairs) do not take part in the exchange");
     if (b->n_fits > 0 && b->mismatch != pe->mismatch[pe->rank] + b->first_fit)
         return fail(ctx, QNMFIT_E_PEER, "b->mismatch must be peers->mismatch[rank] + first_fit");
     return 0;
@@ -339,6 +367,8 @@ static int launch(qnmfit_ctx *ctx, const qnmfit_batch *b, void *stream, bool eva
         // empty slab: only the barrier below
     } else if (pl.kernel == QNMFIT_KERNEL_SMALL) {
         e = k1_launch(b->n_modes, pl.staged, pl.grid, pl.block, pl.smem, st, p);
+    } else if (pl.kernel == QNMFIT_KERNEL_PANEL) {
+        e = k4_launch(pl.grid, pl.smem, st, p);
     } else if (pl.kernel == QNMFIT_KERNEL_STRUCT) {
         e = k3_launch(ctx->k3_g, ctx->k3_rpt, pl.grid, pl.block, pl.smem, st, p);
     } else {
@@ -368,6 +398,92 @@ extern "C" int qnmfit_fit_batch_peers(qnmfit_ctx *ctx, const qnmfit_batch *b, co
     if (!ctx) return QNMFIT_E_NULL;
     if (!peers) return fail(ctx, QNMFIT_E_NULL, "peers is NULL");
     return launch(ctx, b, stream, false, peers);
+}
+
+// ---------------------------------------------------------------------------
+// one sweep with host inputs and a host result in a single call
+
+static int grow_pinned(qnmfit_ctx *ctx, unsigned char **buf, size_t *have, size_t need)
+{
+    if (*have >= need) return 0;
+    if (*buf) cudaFreeHost(*buf);
+    *buf = nullptr; *have = 0;
+    size_t bytes = need + need / 4 + 4096;
+    cudaError_t e = cudaMallocHost((void **)buf, bytes);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMallocHost(staging)");
+    *have = bytes;
+    return 0;
+}
+
+extern "C" int qnmfit_run_host(qnmfit_ctx *ctx, const qnmfit_batch *b, const qnmfit_peers *peers,
+                               const qnmfit_copy *uploads, int n_uploads, const void *result_dev,
+                               void *result_host, size_t result_bytes, int flags, void *stream)
+{
+    if (!ctx) return QNMFIT_E_NULL;
+    if (!b) return fail(ctx, QNMFIT_E_NULL, "batch is NULL");
+    if (n_uploads < 0 || (n_uploads > 0 && !uploads)) return fail(ctx, QNMFIT_E_NULL, "uploads is NULL");
+    if (result_bytes > 0 && (!result_dev || !result_host)) return fail(ctx, QNMFIT_E_NULL, "result pointers are NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
+    int rc;
+    // ---- uploads: staged through the ctx's pinned buffer (free again: every call ends with a
+    // stream synchronisation).  Layout of the staging = layout of the device destinations.
+    if (n_uploads > 0) {
+        const bool coalesce = (flags & QNMFIT_RUN_COALESCE) != 0;
+        size_t total = 0;
+        if (coalesce) {
+            for (int i = 0; i < n_uploads; ++i) {
+                if (!uploads[i].dst_dev || (uploads[i].bytes && !uploads[i].src_host))
+                    return fail(ctx, QNMFIT_E_NULL, "upload %d: NULL pointer", i);
+                if (i > 0 && (const char *)uploads[i].dst_dev < (const char *)uploads[i - 1].dst_dev + uploads[i - 1].bytes)
+                    return fail(ctx, QNMFIT_E_SHAPE, "QNMFIT_RUN_COALESCE: destinations must ascend without overlap");
+            }
+            total = (size_t)((const char *)uploads[n_uploads - 1].dst_dev - (const char *)uploads[0].dst_dev)
+                  + uploads[n_uploads - 1].bytes;
+        } else {
+            for (int i = 0; i < n_uploads; ++i) {
+                if (uploads[i].bytes && (!uploads[i].dst_dev || !uploads[i].src_host))
+                    return fail(ctx, QNMFIT_E_NULL, "upload %d: NULL pointer", i);
+                total += (uploads[i].bytes + 255) / 256 * 256;
+            }
+        }
+        if ((rc = grow_pinned(ctx, &ctx->stage_up, &ctx->stage_up_bytes, total))) return rc;
+        if (coalesce) {
+            const char *base = (const char *)uploads[0].dst_dev;
+            for (int i = 0; i < n_uploads; ++i)
+                memcpy(ctx->stage_up + ((const char *)uploads[i].dst_dev - base), uploads[i].src_host, uploads[i].bytes);
+            if ((e = cudaMemcpyAsync(uploads[0].dst_dev, ctx->stage_up, total, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+                return cuda_fail(ctx, e, "cudaMemcpyAsync(H2D)");
+        } else {
+            size_t off = 0;
+            for (int i = 0; i < n_uploads; ++i) {
+                if (!uploads[i].bytes) continue;
+                memcpy(ctx->stage_up + off, uploads[i].src_host, uploads[i].bytes);
+                if ((e = cudaMemcpyAsync(uploads[i].dst_dev, ctx->stage_up + off, uploads[i].bytes,
+                                         cudaMemcpyHostToDevice, st)) != cudaSuccess)
+                    return cuda_fail(ctx, e, "cudaMemcpyAsync(H2D)");
+                off += (uploads[i].bytes + 255) / 256 * 256;
+            }
+        }
+    }
+    if ((flags & QNMFIT_RUN_ZERO_COUNTER) && b->flagged_count) {
+        if ((e = cudaMemsetAsync(b->flagged_count, 0, sizeof(double), st)) != cudaSuccess)
+            return cuda_fail(ctx, e, "cudaMemsetAsync(counter)");
+    }
+    if ((rc = launch(ctx, b, stream, false, peers))) return rc;
+    if (result_bytes > 0) {
+        void *dst = result_host;
+        if (!(flags & QNMFIT_RUN_RESULT_PINNED)) {
+            if ((rc = grow_pinned(ctx, &ctx->stage_down, &ctx->stage_down_bytes, result_bytes))) return rc;
+            dst = ctx->stage_down;
+        }
+        if ((e = cudaMemcpyAsync(dst, result_dev, result_bytes, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+            return cuda_fail(ctx, e, "cudaMemcpyAsync(D2H)");
+    }
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(ctx, e, "cudaStreamSynchronize");
+    if (result_bytes > 0 && !(flags & QNMFIT_RUN_RESULT_PINNED)) memcpy(result_host, ctx->stage_down, result_bytes);
+    return 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -495,7 +611,8 @@ extern "C" int qnmfit_plan_batch(qnmfit_ctx *ctx, const qnmfit_batch *b, qnmfit_
     out->fast_mismatch = (pl.kernel != QNMFIT_KERNEL_GENERAL && b->uniform_weights && b->dt_nominal > 0.0 && !b->model) ? 1 : 0;
     cudaFuncAttributes fa;
     const void *fn = pl.kernel == QNMFIT_KERNEL_SMALL ? k1_kernel_ptr(b->n_modes, pl.staged)
-                   : pl.kernel == QNMFIT_KERNEL_STRUCT ? k3_kernel_ptr(ctx->k3_g, ctx->k3_rpt) : k2_kernel_ptr();
+                   : pl.kernel == QNMFIT_KERNEL_STRUCT ? k3_kernel_ptr(ctx->k3_g, ctx->k3_rpt)
+                   : pl.kernel == QNMFIT_KERNEL_PANEL ? k4_kernel_ptr() : k2_kernel_ptr();
     cudaError_t e = cudaFuncGetAttributes(&fa, fn);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaFuncGetAttributes");
     out->regs_per_thread = fa.numRegs;

@@ -141,6 +141,9 @@ struct FitParams {
     double2 *model;
     long long model_stride;
     double *flagged_count;
+    int *flag_list;            // [2 * flag_capacity]: (fit, status) of the flagged fits, or NULL
+    int flag_capacity;
+    const int *fit_index;      // [n_fits] or NULL: launch fit b reads the inputs of sweep fit fit_index[b]
     int omega_shared;
     // launch-time choices
     int lanes_per_fit;   // K1: power of two, 1..32
@@ -156,6 +159,14 @@ struct FitParams {
     double *peer_flagged[QNMFIT_MAX_PEERS];
     unsigned long long *peer_flags[QNMFIT_MAX_PEERS];
 };
+
+// Index under which launch fit `fit` finds its per-fit INPUTS (windows, t0, frequencies,
+// table indices, data series): itself, or — in a launch over a subset of a sweep's fits (the
+// repair of flagged fits) — the sweep's index of that fit.  Outputs are always stored at `fit`.
+QF_HD int input_fit(const FitParams &p, int fit)
+{
+    return p.fit_index ? p.fit_index[fit] : fit;
+}
 
 QF_HD int fit_chi_index(const FitParams &p, int fit)
 {
@@ -183,24 +194,107 @@ QF_HD double2 row_omega(const FitParams &p, const double2 *om, int j, int k)
     return p.omega_rows ? p.omega_rows[(long long)j * p.n_times + k] : om[j];
 }
 
-// count a fit whose status word is non-zero
-QF_HD void note_status(const FitParams &p, int status)
+// count a fit whose status word is non-zero and append (fit, status) to the launch's list of
+// flagged fits (the counter's old value is the cursor), so that the host can repair exactly
+// those fits without reading a status word per fit
+QF_HD void note_status(const FitParams &p, int fit, int status)
 {
     if (status != 0 && p.flagged_count) {
 #ifdef QNMFIT_HOSTSIM
+        const double old = *p.flagged_count;
         *p.flagged_count += 1.0;
 #else
-        atomicAdd(p.flagged_count, 1.0);
+        const double old = atomicAdd(p.flagged_count, 1.0);
 #endif
+        if (p.flag_list && old < (double)p.flag_capacity) {
+            const int cur = (int)old;
+            p.flag_list[2 * cur] = fit;
+            p.flag_list[2 * cur + 1] = status;
+        }
     }
 }
 
-// numpy.linalg.lstsq truncates singular values below eps * max(M, N) * s_max.  The kernels
-// only see the diagonal of R, and min |R_jj| / max |R_jj| can sit several hundred times above
-// s_min / s_max (measured up to 684x on overtone ladders), so the flag is raised with that
-// margin: it means "numpy MAY truncate here"; the host decides with the singular values of
-// the exported factor (qnmfits.py, _minimum_norm_from_factor).
-#define QNMFIT_RANK_FLAG_MARGIN 1024.0
+// numpy.linalg.lstsq truncates singular values below eps * max(M, N) * s_max
+// (numpy/linalg/_linalg.py:2553).  The kernels decide "numpy MAY truncate here" in two steps:
+//   1. prefilter on the diagonal of R: min |R_jj| <= PREFILTER * eps * max(M, N) * max |R_jj|.
+//      min/max of the diagonal of an unpivoted QR sits above s_min / s_max (measured up to 684x
+//      on overtone ladders), hence the generous factor;
+//   2. for the fits that pass it, an estimate of s_min by three steps of inverse iteration on
+//      R^H R (two triangular solves each, start vector of ones; the estimate converges to
+//      s_min from above) against MARGIN * eps * max(M, N) * ||R||_F  (||R||_F >= s_max).
+// A flagged fit keeps the basic QR solution on the device; the host decides with the singular
+// values of the exported factor and completes numpy's minimum-norm answer (qnmfits.py,
+// _minimum_norm_from_factor).  Fits that are not flagged are full rank by numpy's criterion
+// with a margin of >= MARGIN in s_min.
+#define QNMFIT_RANK_PREFILTER 1.0e4
+#define QNMFIT_RANK_MARGIN 8.0
+#define QNMFIT_EPS 2.220446049250313e-16
+
+// Serial estimator (K1: lane 0 of the fit).  R(j, k), j < k < N: strictly upper entries;
+// D(j): the real diagonal.  frob2 = ||R||_F^2.  Returns true when the fit must be flagged.
+template <int N, class RF, class DF>
+QF_HD bool rank_suspect_serial(const RF &R, const DF &D, double dim)
+{
+    double frob2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const double d = D(j);
+        if (d == 0.0) return true;
+        frob2 = fma(d, d, frob2);
+#pragma unroll
+        for (int k = j + 1; k < N; ++k) {
+            const double2 r = R(j, k);
+            frob2 = fma(r.x, r.x, frob2);
+            frob2 = fma(r.y, r.y, frob2);
+        }
+    }
+    double2 x[N];
+    const double x0 = 1.0 / sqrt((double)N);
+#pragma unroll
+    for (int j = 0; j < N; ++j) x[j] = make_double2(x0, 0.0);
+    double nz = 1.0;
+#pragma unroll 1
+    for (int it = 0; it < 3; ++it) {
+        // R^H y = x (forward): y_j = (x_j - sum_{i<j} conj(R_ij) y_i) / R_jj
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double ax = x[j].x, ay = x[j].y;
+#pragma unroll
+            for (int i = 0; i < j; ++i) {
+                const double2 r = R(i, j);
+                ax = fma(-r.x, x[i].x, ax); ax = fma(-r.y, x[i].y, ax);
+                ay = fma(-r.x, x[i].y, ay); ay = fma(r.y, x[i].x, ay);
+            }
+            const double inv = 1.0 / D(j);
+            x[j] = make_double2(ax * inv, ay * inv);
+        }
+        // R z = y (backward)
+        double n2 = 0.0;
+#pragma unroll
+        for (int j = N - 1; j >= 0; --j) {
+            double ax = x[j].x, ay = x[j].y;
+#pragma unroll
+            for (int k = j + 1; k < N; ++k) {
+                const double2 r = R(j, k);
+                ax = fma(-r.x, x[k].x, ax); ax = fma(r.y, x[k].y, ax);
+                ay = fma(-r.x, x[k].y, ay); ay = fma(-r.y, x[k].x, ay);
+            }
+            const double inv = 1.0 / D(j);
+            x[j] = make_double2(ax * inv, ay * inv);
+            n2 = fma(x[j].x, x[j].x, n2);
+            n2 = fma(x[j].y, x[j].y, n2);
+        }
+        nz = sqrt(n2);
+        if (!(nz < 1e300)) return true;              // overflow / NaN: as singular as it gets
+        const double s = 1.0 / nz;
+#pragma unroll
+        for (int j = 0; j < N; ++j) x[j] = make_double2(x[j].x * s, x[j].y * s);
+    }
+    // ||(R^H R)^-1 x|| = nz with ||x|| = 1  =>  s_min^2 <= 1 / nz
+    const double cut = QNMFIT_RANK_MARGIN * QNMFIT_EPS * dim;
+    return !(1.0 / nz > cut * cut * frob2);
+}
+
 #define QNMFIT_ST_RANK_DEFICIENT_ 1
 #define QNMFIT_ST_NONFINITE_ 2
 #define QNMFIT_ST_UNDERDETERMINED_ 4
@@ -232,6 +326,71 @@ QF_DEV double warp_sum(double v)
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
     return v;
+}
+
+// The same estimate computed by one warp (K2 / K3: N up to 64, R in shared memory); x is a
+// scratch vector of N complex in shared memory.  All 32 lanes call it; the result is uniform.
+template <class RF, class DF>
+QF_DEV bool rank_suspect_warp(const RF &R, const DF &D, int N, double dim, double2 *x, int lane)
+{
+    double frob2 = 0.0;
+    bool zero_diag = false;
+    for (int j = 0; j < N; ++j) {
+        const double d = D(j);
+        zero_diag |= (d == 0.0);
+        if (lane == 0) frob2 = fma(d, d, frob2);
+        for (int k = j + 1 + lane; k < N; k += 32) {
+            const double2 r = R(j, k);
+            frob2 = fma(r.x, r.x, frob2);
+            frob2 = fma(r.y, r.y, frob2);
+        }
+    }
+    if (zero_diag) return true;
+    frob2 = warp_sum(frob2);
+    const double x0 = 1.0 / sqrt((double)N);
+    for (int j = lane; j < N; j += 32) x[j] = make_double2(x0, 0.0);
+    __syncwarp();
+    double nz = 1.0;
+    for (int it = 0; it < 3; ++it) {
+        for (int j = 0; j < N; ++j) {                // R^H y = x
+            double ax = 0.0, ay = 0.0;
+            for (int i = lane; i < j; i += 32) {
+                const double2 r = R(i, j), xi = x[i];
+                ax = fma(r.x, xi.x, ax); ax = fma(r.y, xi.y, ax);
+                ay = fma(r.x, xi.y, ay); ay = fma(-r.y, xi.x, ay);
+            }
+            ax = warp_sum(ax); ay = warp_sum(ay);
+            if (lane == 0) {
+                const double inv = 1.0 / D(j);
+                x[j] = make_double2((x[j].x - ax) * inv, (x[j].y - ay) * inv);
+            }
+            __syncwarp();
+        }
+        double n2 = 0.0;
+        for (int j = N - 1; j >= 0; --j) {           // R z = y
+            double ax = 0.0, ay = 0.0;
+            for (int k = j + 1 + lane; k < N; k += 32) {
+                const double2 r = R(j, k), xk = x[k];
+                ax = fma(r.x, xk.x, ax); ax = fma(-r.y, xk.y, ax);
+                ay = fma(r.x, xk.y, ay); ay = fma(r.y, xk.x, ay);
+            }
+            ax = warp_sum(ax); ay = warp_sum(ay);
+            const double inv = 1.0 / D(j);
+            const double2 z = make_double2((x[j].x - ax) * inv, (x[j].y - ay) * inv);
+            __syncwarp();
+            if (lane == 0) x[j] = z;
+            __syncwarp();
+            n2 = fma(z.x, z.x, n2);
+            n2 = fma(z.y, z.y, n2);
+        }
+        nz = sqrt(n2);
+        if (!(nz < 1e300)) return true;
+        const double sc = 1.0 / nz;
+        for (int j = lane; j < N; j += 32) x[j] = make_double2(x[j].x * sc, x[j].y * sc);
+        __syncwarp();
+    }
+    const double cut = QNMFIT_RANK_MARGIN * QNMFIT_EPS * dim;
+    return !(1.0 / nz > cut * cut * frob2);
 }
 
 QF_DEV void peer_publish(const FitParams &p, int fit, double mm)

@@ -83,6 +83,7 @@ class qnm:
     """Frequencies and spherical-spheroidal mixing coefficients of Kerr QNMs."""
 
     _instances = []
+    _epoch = 0
 
     #: multiplets that the Leaver solver of the ``qnm`` package cannot follow
     #: (reference qnm.py:67), as (ell, m, n, s)
@@ -101,6 +102,7 @@ class qnm:
     # ------------------------------------------------------------------ tables
 
     def _reset_sequences(self):
+        qnm._epoch += 1                  # prepared sweeps keyed on the tables are stale now
         self._interpolated_qnm_funcs = {}
         self._tabulated = {}
         self._load_cook_multiplets()

@@ -430,57 +430,69 @@ def _series_rows(data, spherical_modes):
     return np.asarray(data, dtype=complex).reshape(1, -1), None
 
 
-def _repair_rank_deficient(eng, b0, n_local, stream, row_begin, row_end, mm):
+#: entries of the device-side list of flagged fits (fit, status); a sweep with more flagged
+#: fits than this falls back to re-fitting its whole slab
+FLAG_CAPACITY = 256
+
+
+def _repair_fits(eng, b0, stream, idx, row_begin, row_end, mm):
+    """Complete the fits ``idx`` (slab-local indices, all flagged rank deficient) to numpy's
+    minimum-norm solution: ONE launch over exactly those fits (``fit_index``; same launch plan
+    as the sweep, so the factor is the sweep's own), the SVD of each exported N x (N+1) factor
+    on the host (``_minimum_norm_from_factor``, as ``ringdown_fit`` does for a single fit), one
+    ``qnmfit_eval_batch`` for model and mismatch, and ``mm[idx]`` patched in place."""
+    N, L = b0.n_modes, b0.n_series
+    nb = int(idx.size)
+    n_r, n_c = 16 * N * (N + 1) * nb, 16 * N * nb
+    keep, ptrs, out = eng.upload_packed([np.ascontiguousarray(idx, dtype=np.int32)],
+                                        out_bytes=n_r + n_c + 8 * nb, stream=stream)
+    b = type(b0).from_buffer_copy(b0)
+    b.n_fits, b.fit_index = nb, ptrs[0]
+    b.R, b.C, b.mismatch = out, out + n_r, out + n_r + n_c
+    b.status = b.residual = b.model = b.flagged_count = b.flag_list = None
+    eng.ctx.fit_batch(b, stream)
+    R = eng.download_raw(out, n_r, np.complex128, stream=stream).reshape(nb, N, N + 1)
+    rb = row_begin[idx] if row_begin is not None else np.full(nb, b0.row_begin_all)
+    re = row_end[idx] if row_end is not None else np.full(nb, b0.row_end_all)
+    C_min = np.ascontiguousarray(
+        np.stack([_minimum_norm_from_factor(R[k], L * int(re[k] - rb[k])) for k in range(nb)]), dtype=np.complex128)
+    eng.ctx.h2d_wait()
+    eng.ctx.h2d(out + n_r, C_min.ctypes.data, C_min.nbytes, stream)     # pageable source: returns when copied
+    eng.ctx.eval_batch(b, stream)
+    mm[idx] = eng.download_raw(out + n_r + n_c, 8 * nb, stream=stream)
+    del keep
+
+
+def _repair_rank_deficient(eng, b0, n_local, stream, row_begin, row_end, mm, flags=None):
     """numpy.linalg.lstsq truncates singular values below ``eps * max(M, N) * s_max``
     (numpy/linalg/_linalg.py:2553) and returns the minimum-norm amplitudes; the kernels
     return the basic QR solution and flag such fits (late start times with many overtones,
-    duplicated labels).  Rare path: refit this slab with the triangular factor exported,
-    complete the minimum-norm solution of every flagged fit on the host
-    (``_minimum_norm_from_factor``, as ``ringdown_fit`` does for a single fit), re-evaluate
-    model and mismatch of those fits on the device and patch ``mm`` (the batch's
-    mismatches) in place.  Returns the number of flagged fits that are NOT of this kind."""
-    import torch
-    N, L = b0.n_modes, b0.n_series
-    left = 0
-    chunk = max(1, min(n_local, (1 << 28) // (16 * N * (N + 1))))
-    for a in range(0, n_local, chunk):
-        nb = min(n_local, a + chunk) - a
-        R_d = torch.empty((nb, N, N + 1), dtype=torch.complex128, device=eng.device)
-        C_d = torch.empty((nb, N), dtype=torch.complex128, device=eng.device)
-        st_d = torch.zeros(nb, dtype=torch.int32, device=eng.device)
-        mm_d = torch.empty(nb, dtype=torch.float64, device=eng.device)
+    duplicated labels).  ``flags``: the (fit, status) pairs the kernels listed (int32 (n, 2))
+    — exactly those fits are repaired (``_repair_fits``); None (the list overflowed): the slab
+    is re-fitted with a status word per fit to find them.  Patches ``mm`` (the slab's
+    mismatches) in place; returns the number of flagged fits that are NOT of this kind."""
+    if flags is None:
+        import torch
+        st_d = torch.zeros(n_local, dtype=torch.int32, device=eng.device)
+        mm_d = torch.empty(n_local, dtype=torch.float64, device=eng.device)
         b = type(b0).from_buffer_copy(b0)
-        b.n_fits, b.first_fit = nb, b0.first_fit + a
-        for name, width in (("row_begin", 4), ("row_end", 4), ("t0", 8), ("coef_index", 4), ("chi_index", 4),
-                            ("mf_index", 4), ("series_index", 4)):
-            ptr = getattr(b0, name)
-            if ptr:
-                setattr(b, name, ptr + width * a)
-        if b0.omega and not b0.omega_shared:
-            b.omega = b0.omega + 16 * N * a
-        b.mismatch, b.flagged_count = mm_d.data_ptr(), None
-        b.R, b.C, b.status = R_d.data_ptr(), C_d.data_ptr(), st_d.data_ptr()
-        b.residual, b.model = None, None
+        b.mismatch, b.status = mm_d.data_ptr(), st_d.data_ptr()
+        b.flagged_count = b.flag_list = b.residual = b.model = b.R = b.C = None
         eng.ctx.fit_batch(b, stream)
         st = eng.download(st_d)
         idx = np.nonzero(st)[0]
-        if idx.size == 0:
-            continue
-        bad = idx[(st[idx] & ~_cabi.ST_RANK_DEFICIENT) != 0]
-        left += int(bad.size)
-        idx = idx[(st[idx] & ~_cabi.ST_RANK_DEFICIENT) == 0]
-        if idx.size == 0:
-            continue
-        sel = torch.from_numpy(idx).to(eng.device)
-        R = eng.download(R_d.index_select(0, sel).contiguous()).reshape(idx.size, N, N + 1)
-        rb = row_begin[a + idx] if row_begin is not None else np.full(idx.size, b0.row_begin_all)
-        re = row_end[a + idx] if row_end is not None else np.full(idx.size, b0.row_end_all)
-        C_min = np.stack([_minimum_norm_from_factor(R[k], L * int(re[k] - rb[k])) for k in range(idx.size)])
-        C_d.index_copy_(0, sel, torch.from_numpy(np.ascontiguousarray(C_min, dtype=np.complex128)).to(eng.device))
-        eng.ctx.eval_batch(b, stream)
-        mm[a + idx] = eng.download(mm_d)[idx]
-    return left
-
+        flags = np.stack([idx, st[idx]], axis=1) if idx.size else np.zeros((0, 2), np.int64)
+    if len(flags) == 0:
+        return 0
+    order = np.argsort(flags[:, 0], kind='stable')       # the list is filled in completion order
+    idx, st = flags[order, 0].astype(np.int64), flags[order, 1]
+    deficient = (st & ~_cabi.ST_RANK_DEFICIENT) == 0
+    if np.any(deficient):
+        todo = idx[deficient]
+        step = max(1, (1 << 27) // (16 * b0.n_modes * (b0.n_modes + 1)))
+        for a in range(0, len(todo), step):
+            _repair_fits(eng, b0, stream, todo[a:a + step], row_begin, row_end, mm)
+    return int(np.count_nonzero(~deficient))
 
 
 class _Sweep:
@@ -493,11 +505,17 @@ class _Sweep:
 
     Host overhead is kept small: every input goes to the device in ONE pinned-memory
     copy (``Engine.upload_packed``); the kernels count flagged fits into one double next
-    to the mismatch array, so the result comes back in ONE copy as well.  Three result
-    paths: one rank — [counter | mismatch] sits right behind the inputs in the same
-    device buffer (the counter's zero travels with the upload); several ranks — the
-    kernel stores into the peer windows of all ranks (``_dist.PeerWindow``), or, when
-    peer mapping is unavailable, an NCCL all-gather of [mismatch slab | counter].
+    to the mismatch array and list them behind it, so the result comes back in ONE copy as
+    well.  Three result paths: one rank — [counter | mismatch | flag list] sits right behind
+    the inputs in the same device buffer (the counter's zero travels with the upload);
+    several ranks — the kernel stores into the peer windows of all ranks
+    (``_dist.PeerWindow``), or, when peer mapping is unavailable, an NCCL all-gather of
+    [mismatch slab | counter].
+
+    ``rerun(times, rows)`` repeats the sweep with fresh time / data arrays of the same shape
+    through ONE C call (``qnmfit_run_host``: staged upload, launch, download, synchronise) —
+    the steady state of a user looping over waveforms, and what ``mismatch_M_chi_grid`` /
+    ``mismatch_t0_array`` do when called again with the same problem (``_cached_sweep``).
     """
 
     def __init__(self, times, rows, *, n_fits, n_modes, windows, t0s, freq_arrays, freq_scalars,
@@ -515,6 +533,7 @@ class _Sweep:
         self.lo, self.hi, self.per = lo, hi, per
         n_local = hi - lo
         L, K_tot = rows.shape
+        self.rows_shape = (L, K_tot)
         self.stream = eng.stream()
 
         shared_window = not isinstance(windows[0], np.ndarray)
@@ -547,25 +566,32 @@ class _Sweep:
                 np.ascontiguousarray(rows, dtype=np.complex128), rb, re, t0_arr, coef_arr,
                 coef_index] + [np.ascontiguousarray(freq_arrays[k][0], dtype=freq_arrays[k][1])
                                for k in names]
-        out_bytes = zero_head = 0
+        self._dyn_bytes = (host[0].nbytes, host[1].nbytes)
+        cap = self._flag_cap = FLAG_CAPACITY
+        out_bytes, zero_head = 8 * cap, 0
         if self.ws == 1:
             zero_head = 16                           # the counter of flagged fits, zeroed by the upload,
-            out_bytes = 8 * n_local                  # always directly in front of the result region
+            out_bytes += 8 * n_local                 # always directly in front of the result region
         self._inputs, ptrs, out = eng.upload_packed(host, out_bytes=out_bytes, stream=self.stream,
                                                     zero_head=zero_head)
+        self._dyn_ptrs = (ptrs[0], ptrs[1])
         kw = dict(freq_scalars)
         kw.update({k: ptr for k, ptr in zip(names, ptrs[7:])})
 
         if self.ws == 1:
             mismatch_d, flagged_d = out, out - 8
-            self._result = out - 8                   # [counter | mismatch[n_local]]
+            self._flag_list = out + 8 * n_local
+            self._result = out - 8                   # [counter | mismatch[n_local] | flag list]
+            self._result_bytes = 8 * (1 + n_local + cap)
             self._fresh = True                       # counter still zero from the upload
         elif self.window is None:
             import torch
             self.out_d = torch.empty(max(per, 1) + 1, dtype=torch.float64, device=eng.device)
             mismatch_d, flagged_d = self.out_d, self.out_d.data_ptr() + 8 * max(per, 1)
+            self._flag_list = out
         else:
             mismatch_d, flagged_d = 0, None          # set per launch (epoch parity slot)
+            self._flag_list = out
         if stats is None:                            # (mean step, largest deviation) of the window
             window_times = times[rb_all:re_all]
             stats = step_stats(window_times, None if steps is None else steps[rb_all:re_all - 1])
@@ -578,8 +604,10 @@ class _Sweep:
                 row_begin_d=ptrs[2], row_end_d=ptrs[3], t0_d=ptrs[4],
                 coef_d=ptrs[5], coef_index_d=ptrs[6], n_coef=n_coef,
                 dt_nominal=dt, uniform_weights=uniform, plan_fits=n_fits,
-                mismatch_d=mismatch_d, flagged_d=flagged_d, **kw)
+                mismatch_d=mismatch_d, flagged_d=flagged_d,
+                flag_list_d=self._flag_list, flag_capacity=cap, **kw)
         self.rows_max = re_all - rb_all
+        self._uploads = None
 
     def launch_kernel(self):
         """Asynchronous: the fit kernel on this rank's slab (fused path: + the exchange)."""
@@ -608,6 +636,55 @@ class _Sweep:
         self.launch_kernel()
         self.gather()
 
+    # ------------------------------------------------------------ results
+
+    def _flags_from(self, tail, count):
+        """(fit, status) pairs from the downloaded list, or None when it overflowed."""
+        if count > self._flag_cap:
+            return None
+        return tail[:count].view(np.int32).reshape(-1, 2)
+
+    def _local_flags(self, count):
+        """Download this rank's flag list (several ranks: it is not part of the exchanged result)."""
+        if count > self._flag_cap:
+            return None
+        raw = self.eng.download_raw(self._flag_list, 8 * count, np.int32, stream=self.stream)
+        return raw.reshape(-1, 2)
+
+    def _finish_single(self, out):
+        """[counter | mismatch | flag list] of a one-rank sweep -> (mismatch, fits still flagged)."""
+        n_local = self.hi - self.lo
+        mm, flagged = out[1:1 + n_local], int(out[0])
+        if flagged:
+            flagged = self._repair_rank_deficient(mm, self._flags_from(out[1 + n_local:], flagged))
+        return mm, flagged
+
+    def _finish_window(self, out):
+        counts = out[:self.ws]
+        if not np.all(np.isfinite(counts)):
+            late = [r for r in range(self.ws) if not np.isfinite(counts[r])]
+            raise RuntimeError(
+                f"qnmfits_b200: rank(s) {late} did not deliver their slab of the sweep within "
+                "QNMFITS_B200_PEER_TIMEOUT_S; every rank must make the same sweep calls")
+        return self._finish_ranks(out[_cabi.MAX_PEERS:_cabi.MAX_PEERS + self.n_fits], int(counts.sum()),
+                                  int(counts[self.rank]))
+
+    def _finish_ranks(self, mm, flagged, own):
+        if flagged:
+            # every rank saw the same total, so every rank takes this (rare) branch: repair
+            # the own slab, then exchange the repaired slabs and the remaining counts
+            import torch
+            per = max(self.per, 1)
+            left = 0
+            if own and self.hi > self.lo:
+                left = self._repair_rank_deficient(mm[self.lo:self.hi], self._local_flags(own))
+            slab = torch.zeros(per + 1, dtype=torch.float64, device=self.eng.device)
+            slab[:self.hi - self.lo] = torch.from_numpy(np.ascontiguousarray(mm[self.lo:self.hi])).to(self.eng.device)
+            slab[per] = float(left)
+            full = self.eng.download(_dist.all_gather_slabs(slab, slab.numel() * self.ws)).reshape(self.ws, per + 1)
+            mm, flagged = full[:, :per].reshape(-1)[:self.n_fits].copy(), int(full[:, per].sum())
+        return mm, flagged
+
     def fetch(self):
         """(mismatch of every fit as float64[n_fits], number of fits still flagged), on the host.
 
@@ -616,41 +693,72 @@ class _Sweep:
         have solved either (underdetermined, non-finite)."""
         per = max(self.per, 1)
         if self.ws == 1:
-            out = self.eng.download_raw(self._result, 8 * (1 + self.hi - self.lo), stream=self.stream)
-            mm, flagged = out[1:], int(out[0])
-            if flagged:
-                flagged = self._repair_rank_deficient(mm)
-            return mm, flagged
+            return self._finish_single(self.eng.download_raw(self._result, self._result_bytes, stream=self.stream))
         if self.window is not None:
-            out = self.eng.download_raw(self.window.result_ptr(self.slot),
-                                        8 * (_cabi.MAX_PEERS + self.n_fits), stream=self.stream)
-            counts = out[:self.ws]
-            if not np.all(np.isfinite(counts)):
-                late = [r for r in range(self.ws) if not np.isfinite(counts[r])]
-                raise RuntimeError(
-                    f"qnmfits_b200: rank(s) {late} did not deliver their slab of the sweep within "
-                    "QNMFITS_B200_PEER_TIMEOUT_S; every rank must make the same sweep calls")
-            mm, flagged = out[_cabi.MAX_PEERS:], int(counts.sum())
-        else:
-            full = self.eng.download(self.gathered).reshape(self.ws, per + 1)
-            mm, flagged = full[:, :per].reshape(-1)[:self.n_fits].copy(), int(full[:, per].sum())
-        if flagged:
-            # every rank saw the same total, so every rank takes this (rare) branch: repair
-            # the own slab, then exchange the repaired slabs and the remaining counts
-            import torch
-            import torch.distributed as dist
-            left = self._repair_rank_deficient(mm[self.lo:self.hi]) if self.hi > self.lo else 0
-            slab = torch.zeros(per + 1, dtype=torch.float64, device=self.eng.device)
-            slab[:self.hi - self.lo] = torch.from_numpy(np.ascontiguousarray(mm[self.lo:self.hi])).to(self.eng.device)
-            slab[per] = float(left)
-            full = self.eng.download(_dist.all_gather_slabs(slab, slab.numel() * self.ws)).reshape(self.ws, per + 1)
-            mm, flagged = full[:, :per].reshape(-1)[:self.n_fits].copy(), int(full[:, per].sum())
-        return mm, flagged
+            return self._finish_window(self.eng.download_raw(
+                self.window.result_ptr(self.slot), 8 * (_cabi.MAX_PEERS + self.n_fits), stream=self.stream))
+        full = self.eng.download(self.gathered).reshape(self.ws, per + 1)
+        counts = full[:, per]
+        return self._finish_ranks(full[:, :per].reshape(-1)[:self.n_fits].copy(), int(counts.sum()),
+                                  int(counts[self.rank]))
 
-    def _repair_rank_deficient(self, mm):
+    def _repair_rank_deficient(self, mm, flags=None):
         """Patch the slab's mismatches ``mm`` in place (see ``_repair_rank_deficient``)."""
         return _repair_rank_deficient(self.eng, self.batch, self.hi - self.lo, self.stream,
-                                      self._row_begin, self._row_end, mm)
+                                      self._row_begin, self._row_end, mm, flags)
+
+    # ------------------------------------------------------------ one C call per sweep
+
+    def rerun(self, times, rows):
+        """The sweep once more with other ``times`` (float64 (K_tot,)) and data ``rows`` (a list
+        of L complex128 (K_tot,) arrays or one (L, K_tot) array) of the shapes it was prepared
+        for: upload, launch (+ exchange), download and synchronisation in ONE C call
+        (``qnmfit_run_host``).  The NCCL fallback path re-uploads and goes through
+        ``launch`` / ``fetch``.  Returns what ``fetch`` returns."""
+        eng, ctx = self.eng, self.eng.ctx
+        if isinstance(rows, np.ndarray):
+            rows = [rows] if rows.ndim == 1 else ([rows.reshape(-1)] if rows.flags.c_contiguous else list(rows))
+        L, K_tot = self.rows_shape
+        n_series = len(rows)
+        up = self._uploads
+        if up is None or len(up) != 1 + n_series:
+            up = self._uploads = (_cabi.Copy * (1 + n_series))()
+            up[0].dst_dev, up[0].bytes = self._dyn_ptrs[0], self._dyn_bytes[0]
+            each = self._dyn_bytes[1] // n_series
+            for i in range(n_series):
+                up[1 + i].dst_dev, up[1 + i].bytes = self._dyn_ptrs[1] + i * each, each
+            gap_ok = self._dyn_ptrs[0] < self._dyn_ptrs[1] and \
+                self._dyn_ptrs[1] == (self._dyn_ptrs[0] + self._dyn_bytes[0] + 255) // 256 * 256
+            self._run_flags = _cabi.RUN_COALESCE if gap_ok else 0
+        if times.nbytes != up[0].bytes or any(r.nbytes != up[1].bytes for r in rows):
+            raise ValueError("rerun: array shapes differ from the prepared sweep")
+        up[0].src_host = times.ctypes.data
+        for i, r in enumerate(rows):
+            up[1 + i].src_host = r.ctypes.data
+        eng.h2d_bytes += times.nbytes + sum(r.nbytes for r in rows)
+        if self.ws > 1 and self.window is None:      # NCCL fallback: separate upload, launch, gather
+            for c in up:
+                ctx.h2d(c.dst_dev, c.src_host, c.bytes, self.stream)
+            self.launch()
+            return self.fetch()
+        if self.window is not None:
+            peers, local, self.slot = self.window.next_launch()
+            self.batch.mismatch = local + 8 * self.lo
+            res_ptr, nbytes, flags = self.window.result_ptr(self.slot), 8 * (_cabi.MAX_PEERS + self.n_fits), self._run_flags
+        else:
+            peers, res_ptr, nbytes = None, self._result, self._result_bytes
+            flags = self._run_flags | _cabi.RUN_ZERO_COUNTER
+            self._fresh = False
+        eng.d2h_bytes += nbytes
+        if nbytes >= 1 << 16:                        # lands in a pinned block of its own: no host copy
+            block = eng.torch.empty(nbytes, dtype=eng.torch.uint8, pin_memory=True)
+            out = block.numpy().view(np.float64)
+            ctx.run_host(self.batch, peers, up, len(up), res_ptr, block.data_ptr(), nbytes,
+                         flags | _cabi.RUN_RESULT_PINNED, self.stream)
+        else:
+            out = np.empty(nbytes // 8, dtype=np.float64)
+            ctx.run_host(self.batch, peers, up, len(up), res_ptr, out.ctypes.data, nbytes, flags, self.stream)
+        return self._finish_window(out) if self.window is not None else self._finish_single(out)
 
 
 class _DeviceGroupSweep:
@@ -688,6 +796,88 @@ class _DeviceGroupSweep:
     def fetch(self):
         results = [part.fetch() for part in self.parts]
         return np.concatenate([r[0] for r in results]), sum(r[1] for r in results)
+
+
+# --------------------------------------------------------------------------
+# prepared sweeps, kept for repeated calls
+#
+# A second call of mismatch_M_chi_grid / mismatch_t0_array with the same problem (labels, grid
+# or start times, window, table provider — everything except the VALUES of the data) finds its
+# tables, window rows and launch descriptor on the device already: the call then costs one
+# comparison of ``times`` with the stored copy and one C call that uploads ``times`` and the
+# data from the host, launches and returns the result (``_Sweep.rerun``).  The reference
+# repeats all of its per-point work on every call; what is cached here is only what it would
+# recompute identically.
+
+_sweep_cache = {}
+_SWEEP_CACHE_MAX = 8
+_SWEEP_CACHE_MAX_BYTES = 1 << 24
+
+
+def _delta_key(delta):
+    if isinstance(delta, (int, float, np.integer, np.floating)) and not isinstance(delta, bool):
+        return float(delta)
+    if isinstance(delta, (list, np.ndarray)):
+        try:
+            return ('a', np.asarray(delta, dtype=float).tobytes())
+        except (TypeError, ValueError):
+            return None
+    return None
+
+
+def _problem_key(kind, times, data, modes, spherical_modes, delta, coef_columns, scalars):
+    """Hashable signature of a sweep, or None when it must not be cached (caller-supplied
+    coefficient callables, a single-process device group, unhashable arguments)."""
+    if coef_columns or _dist.local_devices() is not None or times.ndim != 1:
+        return None
+    try:
+        if type(data) is dict:
+            keys = tuple(data.keys()) if spherical_modes is None else tuple(tuple(lm) for lm in spherical_modes)
+            n_data = len(data[keys[0]]) if keys else -1
+        else:
+            keys, n_data = None, len(data)
+        dk = _delta_key(delta)
+        if dk is None or n_data != len(times) or n_data * 16 * (1 if keys is None else len(keys)) > _SWEEP_CACHE_MAX_BYTES:
+            return None
+        key = (kind, _qnm_class._epoch, tuple(tuple(mode) for mode in modes), keys, dk, len(times),
+               _dist.world(), scalars)
+        hash(key)
+        return key
+    except (TypeError, KeyError, IndexError):
+        return None
+
+
+def _cached_sweep(key, times):
+    """The prepared sweep of this problem if the time samples are the ones it was built for."""
+    hit = None if key is None else _sweep_cache.get(key)
+    if hit is None:
+        return None
+    sweep = hit[0]
+    if (sweep.window is not None and sweep.window.closed) or sweep.eng is not get_engine() \
+            or not np.array_equal(hit[1], times):
+        del _sweep_cache[key]
+        return None
+    return hit
+
+
+def _cache_sweep(key, sweep, times, *aux):
+    if key is None or not isinstance(sweep, _Sweep):
+        return
+    while len(_sweep_cache) >= _SWEEP_CACHE_MAX:
+        del _sweep_cache[next(iter(_sweep_cache))]
+    _sweep_cache[key] = (sweep, np.array(times, dtype=float, copy=True)) + aux
+
+
+def clear_sweep_cache():
+    """Drop the prepared sweeps kept for repeated calls (frees their device buffers)."""
+    _sweep_cache.clear()
+
+
+def _data_rows(data, keys):
+    """The series to fit as a list of C-contiguous complex128 arrays (no copy when they already are)."""
+    if keys is None:
+        return [np.ascontiguousarray(data, dtype=np.complex128).reshape(-1)]
+    return [np.ascontiguousarray(data[lm], dtype=np.complex128).reshape(-1) for lm in keys]
 
 
 def _make_sweep(*args, **kwargs):
@@ -807,10 +997,19 @@ def mismatch_t0_array(times, data, modes, Mf, chif, t0_array, t0_method='geq',
                                delta)['mismatch'])
         return out
 
-    sweep = _prepare_t0_sweep(times, data, modes, Mf, chif, t0_array, t0_method, T_array,
-                              spherical_modes, delta, coef_columns)
-    sweep.launch()
-    mm, status = sweep.fetch()
+    key = _problem_key('t0', times, data, modes, spherical_modes, delta, coef_columns,
+                       (float(Mf), float(chif), t0_method, t0_array.tobytes(),
+                        np.asarray(T_array, dtype=float).tobytes()))
+    hit = _cached_sweep(key, times)
+    if hit is not None:
+        mm, status = hit[0].rerun(np.ascontiguousarray(times, dtype=np.float64), _data_rows(data, hit[2]))
+    else:
+        sweep = _prepare_t0_sweep(times, data, modes, Mf, chif, t0_array, t0_method, T_array,
+                                  spherical_modes, delta, coef_columns)
+        sweep.launch()
+        mm, status = sweep.fetch()
+        _cache_sweep(key, sweep, times, None if type(data) is not dict else
+                     (list(data.keys()) if spherical_modes is None else list(spherical_modes)))
     _warn_status(status, "mismatch_t0_array")
     return list(mm)              # np.float64 scalars, like the reference
 
@@ -876,7 +1075,17 @@ def _prepare_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0, t0_metho
             "Requested t0_method is not valid. Please choose between 'geq' and 'closest'")
     ascending, window, stats = _time_axis(times, t0, T, t0_method)
     if not ascending:
-        raise ValueError("times must be ascending")
+        # The reference's boolean mask (qnmfits.py:233) / argmin slice (:240-244) work on
+        # unsorted samples too: fit the selected samples in their own order (every row of the
+        # design matrix is evaluated directly; the trapezoid weights follow np.trapezoid).
+        sel = _window(times, t0, T, t0_method)
+        if type(data) is dict:
+            keys0 = list(data.keys()) if spherical_modes is None else list(spherical_modes)
+            data, spherical_modes = {lm: np.asarray(data[lm])[sel] for lm in keys0}, keys0
+        else:
+            data = np.asarray(data)[sel]
+        times = times[sel]
+        window, stats = (0, len(times)), (0.0, np.inf)
     if window[1] <= window[0]:
         raise ValueError("the analysis window is empty")
     rows, keys = _series_rows(data, spherical_modes)
@@ -922,12 +1131,27 @@ def mismatch_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0,
     ``multimode_ringdown_fit``; on the grid a column may depend on the spin (a callable of
     ``chif``, or an array (res, L) along ``np.linspace(*chif_minmax, res)``).
     """
-    sweep, shape = _prepare_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0,
-                                       t0_method, T, res, spherical_modes, delta, coef_columns)
-    if sweep is None:
-        return np.reshape(np.array([]), shape)
-    sweep.launch()
-    mm, status = sweep.fetch()
+    times = np.asarray(times)
+    try:
+        scalars = (float(Mf_minmax[0]), float(Mf_minmax[1]), float(chif_minmax[0]), float(chif_minmax[1]),
+                   float(t0), t0_method, float(T), int(res))
+    except (TypeError, ValueError):
+        scalars = None
+    key = None if scalars is None else _problem_key('grid', times, data, modes, spherical_modes, delta,
+                                                    coef_columns, scalars)
+    hit = _cached_sweep(key, times)
+    if hit is not None:
+        sweep, _, shape, keys = hit
+        mm, status = sweep.rerun(np.ascontiguousarray(times, dtype=np.float64), _data_rows(data, keys))
+    else:
+        sweep, shape = _prepare_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0,
+                                           t0_method, T, res, spherical_modes, delta, coef_columns)
+        if sweep is None:
+            return np.reshape(np.array([]), shape)
+        sweep.launch()
+        mm, status = sweep.fetch()
+        _cache_sweep(key, sweep, times, shape, None if type(data) is not dict else
+                     (list(data.keys()) if spherical_modes is None else list(spherical_modes)))
     _warn_status(status, "mismatch_M_chi_grid")
     return np.reshape(mm, shape)
 
@@ -986,24 +1210,29 @@ class _ResidentData:
                   None if coef is None else np.ascontiguousarray(coef, dtype=np.complex128),
                   None if coef is None else np.arange(n, dtype=np.int32), rb, re]
         stream = eng.stream()
-        # 16 zero bytes in front of the result region: the counter of flagged fits
-        keep, ptrs, out = eng.upload_packed(arrays, out_bytes=8 * n, stream=stream, zero_head=16)
+        # 16 zero bytes in front of the result region: the counter of flagged fits; the list of
+        # flagged fits behind the mismatches -> [counter | mismatch | flag list] in one download
+        cap = FLAG_CAPACITY
+        keep, ptrs, out = eng.upload_packed(arrays, out_bytes=8 * (n + cap), stream=stream, zero_head=16)
         batch = eng.make_batch(
             times_d=self.times_p, data_d=self.data_p, n_times=self.K_tot, series_stride=self.K_tot,
             n_fits=n, n_modes=N, n_series=n_series, row_begin_all=self.window[0],
             row_end_all=self.window[1], t0_all=self.t0, omega_d=ptrs[0], series_index_d=ptrs[1],
             coef_d=ptrs[2], coef_index_d=ptrs[3], n_coef=0 if coef is None else n,
             row_begin_d=ptrs[4], row_end_d=ptrs[5], dt_nominal=dt,
-            uniform_weights=self.uniform and dt > 0.0, mismatch_d=out, flagged_d=out - 8)
+            uniform_weights=self.uniform and dt > 0.0, mismatch_d=out, flagged_d=out - 8,
+            flag_list_d=out + 8 * n, flag_capacity=cap, plan_fits=n)
         eng.ctx.fit_batch(batch, stream)
         self.launches += 1
-        result = eng.download_raw(out - 8, 8 * (n + 1), stream=stream)
-        flagged, result = int(result[0]), result[1:]
+        raw = eng.download_raw(out - 8, 8 * (1 + n + cap), stream=stream)
+        flagged, result = int(raw[0]), raw[1:1 + n]
         if flagged:
             # a trial frequency (numerically) equal to another column: numpy truncates, so do we
-            _repair_rank_deficient(eng, batch, n, stream, rb, re, result)
+            flags = raw[1 + n:1 + n + flagged].view(np.int32).reshape(-1, 2) if flagged <= cap else None
+            _repair_rank_deficient(eng, batch, n, stream, rb, re, result, flags)
         del keep
         return result
+
 
 class _FreeFrequencyObjective(_ResidentData):
     """The reference's ``mismatch_f_tau`` (qnmfits.py:2003-2029) for S waveforms that

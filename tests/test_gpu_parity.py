@@ -262,11 +262,12 @@ def _synthetic_stack(N, L, K_tot, seed, uniform=True):
 
 @pytest.mark.parametrize("N,L,use_coef", [(3, 2, True), (12, 1, False), (12, 1, True), (20, 5, True),
                                            (40, 21, True), (63, 1, False), (9, 7, True), (9, 1, False),
-                                           (10, 1, False), (11, 1, False), (16, 1, False)])
+                                           (10, 1, False), (11, 1, False), (16, 1, False), (1, 1, True),
+                                           (8, 2, True), (17, 3, True), (44, 21, True), (64, 30, True)])
 def test_struct_kernel_vs_oracle_and_general_kernel(qf, eng, N, L, use_coef):
-    """K3 (structured two-phase QR) for every lanes-per-column variant, uniform (fast
+    """K4 (blocked structured QR on DMMA) and K3 (structured two-phase QR), uniform (fast
     mismatch and second pass) and non-uniform grids, against numpy lstsq on the explicit
-    stacked matrix and against K2."""
+    stacked matrix and against K2; shapes beyond K3's 64 columns run K4 only."""
     import torch
     K_tot = 700
     for uniform in (True, False):
@@ -285,9 +286,13 @@ def test_struct_kernel_vs_oracle_and_general_kernel(qf, eng, N, L, use_coef):
             d.update(coef_d=eng.to_device(coef.reshape(1, L, N), np.complex128), n_coef=1,
                      coef_index_d=eng.to_device(np.zeros(1, np.int32), np.int32))
         tol = cases.amp_tol(s)
-        variants = [("k3_second_pass", _cabi.KERNEL_STRUCT, False), ("k2", _cabi.KERNEL_GENERAL, False)]
+        variants = [("k4_second_pass", _cabi.KERNEL_PANEL, False), ("k2", _cabi.KERNEL_GENERAL, False)]
+        if N + L <= 64:
+            variants.append(("k3_second_pass", _cabi.KERNEL_STRUCT, False))
         if uniform:
-            variants.insert(0, ("k3_fast", _cabi.KERNEL_STRUCT, True))
+            variants.insert(0, ("k4_fast", _cabi.KERNEL_PANEL, True))
+            if N + L <= 64:
+                variants.insert(0, ("k3_fast", _cabi.KERNEL_STRUCT, True))
         if N <= _cabi.MAX_MODES_SMALL and L == 1 and not use_coef:   # K1 with 2- or 3-row blocks
             variants.append(("k1_second_pass", _cabi.KERNEL_SMALL, False))
             if uniform:
@@ -306,12 +311,13 @@ def test_struct_kernel_vs_oracle_and_general_kernel(qf, eng, N, L, use_coef):
             np.testing.assert_allclose(eng.to_host(res_d)[0], res_ref[0], rtol=1e-6, err_msg=name)
             assert int(eng.to_host(st_d)[0]) == 0, name
         plan = eng.ctx.plan(eng.make_batch(kernel=_cabi.KERNEL_AUTO, mismatch_d=mm_d, **d))
-        assert plan.kernel == (_cabi.KERNEL_STRUCT if (N > _cabi.MAX_MODES_SMALL or L > 1 or use_coef)
+        assert plan.kernel == (_cabi.KERNEL_PANEL if (N > _cabi.MAX_MODES_SMALL or L > 1 or use_coef)
                                else _cabi.KERNEL_SMALL)
 
 
-def test_struct_kernel_many_fits_windows_and_eval(qf, eng):
-    """K3 on a sweep: per-fit windows and start times, model output, eval-only path."""
+@pytest.mark.parametrize("kernel", [_cabi.KERNEL_STRUCT, _cabi.KERNEL_PANEL])
+def test_struct_kernel_many_fits_windows_and_eval(qf, eng, kernel):
+    """K3 / K4 on a sweep: per-fit windows and start times, model output, eval-only path."""
     import torch
     N, L, K_tot, B = 10, 3, 500, 37
     times, data, freq, coef = _synthetic_stack(N, L, K_tot, seed=7)
@@ -326,7 +332,7 @@ def test_struct_kernel_many_fits_windows_and_eval(qf, eng):
              coef_index_d=eng.to_device(np.zeros(B, np.int32), np.int32),
              n_fits=B, n_modes=N, n_series=L, row_begin_all=int(rb.min()), row_end_all=int(re.max()),
              row_begin_d=eng.to_device(rb, np.int32), row_end_d=eng.to_device(re, np.int32),
-             t0_d=eng.to_device(t0, np.float64), dt_nominal=0.1, kernel=_cabi.KERNEL_STRUCT)
+             t0_d=eng.to_device(t0, np.float64), dt_nominal=0.1, kernel=kernel)
     C_d = eng.empty((B, N), torch.complex128)
     mm_d = eng.empty((B,), torch.float64)
     model_d = eng.empty((B, L * Kmax), torch.complex128)
@@ -703,3 +709,82 @@ def test_config5_full_size_sampled_vs_scipy(qf, eng, oracle_tables):
     want = np.array([orc.free_frequency_fit(oracle_tables, wl.times, wl.data[b], 0.0, modes=wl.modes, Mf=wl.Mf,
                                             chif=wl.chif) for b in idx])
     np.testing.assert_allclose(got[idx], want, rtol=0, atol=1e-6)
+
+
+# --------------------------------------------------------------------------
+# repeated calls (prepared sweeps), repair of exactly the flagged fits, unsorted samples
+
+def test_repeated_calls_reuse_the_prepared_sweep_and_stay_exact(qf, eng, oracle_tables):
+    """The second call with the same problem goes through ONE C call (qnmfit_run_host) on the
+    prepared sweep; results are bit-identical to a cold call, other data values are honoured,
+    other time samples invalidate the entry."""
+    from qnmfits_b200 import qnmfits as api
+    wl = workloads.config3(res=20)
+    args = (wl.modes, wl.Mf_minmax, wl.chif_minmax, wl.t0)
+    qf.clear_sweep_cache()
+    cold = qf.mismatch_M_chi_grid(wl.times, wl.data, *args, T=wl.T, res=20)
+    assert len(api._sweep_cache) == 1
+    launches = eng.ctx.launch_count()
+    warm = qf.mismatch_M_chi_grid(wl.times, wl.data, *args, T=wl.T, res=20)
+    assert eng.ctx.launch_count() == launches + 1 and len(api._sweep_cache) == 1
+    assert np.array_equal(cold, warm)
+    other = wl.data * (1.0 + 0.01j) + 1e-4 * np.exp(-0.3j * wl.times)
+    got = qf.mismatch_M_chi_grid(wl.times, other, *args, T=wl.T, res=20)
+    qf.clear_sweep_cache()
+    fresh = qf.mismatch_M_chi_grid(wl.times, other, *args, T=wl.T, res=20)
+    assert np.array_equal(got, fresh) and not np.array_equal(got, cold)
+    want = orc.mismatch_M_chi_grid(oracle_tables, wl.times, other, *args, T=wl.T, res=20)
+    np.testing.assert_allclose(got, want, rtol=0, atol=MM_TOL)
+    shifted = wl.times + 0.003                      # other samples: other window arithmetic
+    got = qf.mismatch_M_chi_grid(shifted, wl.data, *args, T=wl.T, res=20)
+    want = orc.mismatch_M_chi_grid(oracle_tables, shifted, wl.data, *args, T=wl.T, res=20)
+    np.testing.assert_allclose(got, want, rtol=0, atol=MM_TOL)
+    # start-time sweeps and dict data the same way
+    wl4 = cases.cfg4_small()
+    a4 = (wl4.modes, wl4.Mf, wl4.chif, wl4.t0_array)
+    qf.clear_sweep_cache()
+    cold = qf.mismatch_t0_array(wl4.times, wl4.data, *a4)
+    warm = qf.mismatch_t0_array(wl4.times, wl4.data, *a4)
+    assert np.array_equal(cold, warm) and len(api._sweep_cache) == 1
+    scaled = {lm: 0.5 * v for lm, v in wl4.data.items()}
+    got = qf.mismatch_t0_array(wl4.times, scaled, *a4)
+    np.testing.assert_allclose(got, cold, rtol=0, atol=1e-12)      # the mismatch is scale invariant
+    qf.clear_sweep_cache()
+
+
+def test_only_the_flagged_fits_are_repaired(qf, eng, oracle_tables):
+    """One rank-deficient fit in a large sweep — a frequency grid whose centre point coincides
+    with the fixed mode, so that exactly there two columns are equal and numpy truncates: the
+    kernels list the fit, and the host re-fits exactly that fit (one subset launch + one eval
+    launch), not the 10 201 of the sweep."""
+    wl = workloads.config1()
+    w0 = complex(qf.qnm.omega_list([(2, 2, 0, 1)], wl.chif, wl.Mf)[0])
+    re_mm = (w0.real - 0.25, w0.real + 0.25)
+    im_mm = (w0.imag - 0.05, w0.imag + 0.05)
+    res = 101
+    assert np.linspace(*re_mm, res)[50] == w0.real and np.linspace(*im_mm, res)[50] == w0.imag
+    launches = eng.ctx.launch_count()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = qf.mismatch_omega_grid(wl.times, wl.data, [(2, 2, 0, 1)], wl.Mf, wl.chif, re_mm, im_mm, 0.0, T=100, res=res)
+    used = eng.ctx.launch_count() - launches
+    assert got.shape == (res, res) and np.all(np.isfinite(got))
+    # the reference's loop on the centre point and a few others (qnmfits.py:1785-1803)
+    for i_re, i_im in ((50, 50), (49, 50), (50, 51), (0, 0), (100, 37)):
+        freq = np.array([w0, np.linspace(*re_mm, res)[i_re] + 1j * np.linspace(*im_mm, res)[i_im]])
+        sl = slice(*np.searchsorted(wl.times, [0.0, 100.0]))
+        a, C, r, rank, s, model = orc.lstsq_fit(wl.times[sl], wl.data[sl], freq, 0.0)
+        assert rank == (1 if (i_re, i_im) == (50, 50) else 2)
+        assert abs(got[i_im, i_re] - orc.mismatch(wl.times[sl], model, wl.data[sl])) < MM_TOL, (i_re, i_im)
+    assert used == 3, used                           # sweep + refit of the one flagged fit + its evaluation
+
+
+def test_grid_on_unsorted_samples_follows_the_reference_mask(qf, eng, oracle_tables):
+    """mismatch_M_chi_grid with shuffled time samples: the reference's boolean mask works on any
+    order (qnmfits.py:233); so does the device path (direct evaluation of every row)."""
+    wl = workloads.config3(res=5)
+    perm = np.random.default_rng(3).permutation(len(wl.times))
+    t, d = wl.times[perm], wl.data[perm]
+    got = qf.mismatch_M_chi_grid(t, d, wl.modes[:4], wl.Mf_minmax, wl.chif_minmax, 2.0, T=40, res=5)
+    want = orc.mismatch_M_chi_grid(oracle_tables, t, d, wl.modes[:4], wl.Mf_minmax, wl.chif_minmax, 2.0, T=40, res=5)
+    np.testing.assert_allclose(got, want, rtol=0, atol=MM_TOL)
