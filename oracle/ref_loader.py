@@ -29,9 +29,29 @@ def reference_package_dir():
     if os.path.isfile(os.path.join(src, "qnmfits.py")):
         return src
     built = os.path.join(COMPILED_ROOT, "qnmfits")
-    if os.path.isfile(os.path.join(built, "qnmfits.pyc")) and os.path.isfile(os.path.join(built, "qnm.pyc")):
+    if os.path.isfile(os.path.join(built, "qnmfits.code")) and os.path.isfile(os.path.join(built, "qnm.code")):
         return built
     return None
+
+
+def _import_reference(package_dir):
+    """``qnmfits.qnmfits`` from the sources, or from the marshalled code objects of oracle/_ref
+    (executed as the modules ``qnmfits.qnm`` and ``qnmfits.qnmfits`` of the bare package)."""
+    if os.path.isfile(os.path.join(package_dir, "qnmfits.py")):
+        return importlib.import_module("qnmfits.qnmfits")
+    import marshal
+    mods = {}
+    for name in ("qnm", "qnmfits"):
+        full = "qnmfits." + name
+        mod = types.ModuleType(full)
+        mod.__package__ = "qnmfits"
+        mod.__file__ = os.path.join(package_dir, name + ".code")
+        sys.modules[full] = mod
+        setattr(sys.modules["qnmfits"], name, mod)
+        with open(mod.__file__, "rb") as fh:
+            exec(marshal.load(fh), mod.__dict__)
+        mods[name] = mod
+    return mods["qnmfits"]
 
 
 def reference_available():
@@ -79,7 +99,7 @@ def load_reference(modes_cache=None):
         pkg = types.ModuleType("qnmfits")
         pkg.__path__ = [package_dir]
         sys.modules["qnmfits"] = pkg
-        ref = importlib.import_module("qnmfits.qnmfits")
+        ref = _import_reference(package_dir)
     finally:
         # Leave no stubs behind: the reference module keeps its own references.
         for k, v in saved.items():

@@ -14,9 +14,8 @@
 //
 //   panel     warp 0 factors the 8 panel columns (two rows per lane in registers, column
 //             norms and dot products by warp shuffles), and builds the 8 x 8 triangular T
-//             of  H_7 ... H_0 = I - V T^H V^H  from by-products of the factorisation: the Gram
-//             matrix of the reflector tails follows from the dot products already formed,
-//                 g_ij = d_ij - |b_i|^2 p_ij - sum_{i<l<j} g_il p_lj;
+//             of  H_7 ... H_0 = I - V T^H V^H  from the Gram matrix of the reflector tails,
+//             whose entries ride along in the same shuffle reductions;
 //   update    every warp takes 8-column chunks of the trailing matrix [E_trailing | d_1..d_L]:
 //                 X = diag(v0) R_panel,chunk + V_b^H B_chunk      (8 x 64 x 8)   DMMA m8n8k4
 //                 W = T^H X                                        (8 x 8 x 8)    DMMA
@@ -45,7 +44,6 @@ struct PanelSmem {
     PackedR R2;       // N rows, N+1 columns: second factor | Q^H d  (lives in unused tile columns when it fits)
     double2 *tile;    // [NC][K4_S] column-major
     double2 *Tm;      // [8][8]  T of the current panel (upper triangular, zero below)
-    double2 *pbuf;    // [8][8]  p_jk of the current panel
     double2 *gbuf;    // [8][8]  Gram of the reflector tails
     double2 *xw;      // [K4_WARPS][8][K4_XS]  fragment-layout exchange, one per warp
     double2 *om, *qq, *qw, *Cv;   // [N]
@@ -54,6 +52,11 @@ struct PanelSmem {
     double *v0;       // [8]
     double *red;      // [16][8]
     double *ends;     // [64][3]
+    // The same arrays as element offsets from the start of the CTA's shared memory (double2
+    // units; o_diag*, o_v0 in doubles).  The hot code addresses shared memory as
+    // k4_shared()[offset]: through the pointers above nvcc cannot prove the address space once
+    // struct_finish is part of the kernel, and every tile access becomes a generic LD.E / ST.E.
+    int o_R1, o_R2, o_tile, o_Tm, o_gbuf, o_xw, o_om, o_qq, o_qw, o_diag1, o_diag2, o_v0;
 
     // does R2 fit behind the N+1 columns phase 2 uses?
     __host__ __device__ static bool r2_in_tile(int N, int L)
@@ -68,7 +71,7 @@ struct PanelSmem {
         size_t tile = (size_t)(N + L) * K4_S;
         const size_t scr = (size_t)L * N + (size_t)K3C_TK * N;
         if (tile < scr) tile = scr;
-        return sizeof(double2) * (r1 + r2 + tile + 3 * 64 + (size_t)K4_WARPS * 8 * K4_XS + 4 * (size_t)N)
+        return sizeof(double2) * (r1 + r2 + tile + 2 * 64 + (size_t)K4_WARPS * 8 * K4_XS + 4 * (size_t)N)
              + sizeof(double) * (2 * (size_t)N + 8 + 128 + 64 * 3);
     }
     __device__ void carve(void *base, int N, int L)
@@ -84,7 +87,7 @@ struct PanelSmem {
         R2.W = N;
         if (r2_in_tile(N, L)) R2.a = tile + (size_t)(N + 1) * K4_S;
         else { R2.a = p; p += PackedR::entries(N, N); }
-        Tm = p; p += 64; pbuf = p; p += 64; gbuf = p; p += 64;
+        Tm = p; p += 64; gbuf = p; p += 64;
         xw = p; p += K4_WARPS * 8 * K4_XS;
         om = p; p += N; qq = p; p += N; qw = p; p += N; Cv = p; p += N;
         double *d = (double *)p;
@@ -93,8 +96,27 @@ struct PanelSmem {
         v0 = d; d += 8;
         red = d; d += 128;
         ends = d;
+        const double2 *b2 = (const double2 *)base;
+        const double *b1 = (const double *)base;
+        o_R1 = (int)(R1.a - b2); o_R2 = (int)(R2.a - b2); o_tile = (int)(tile - b2);
+        o_Tm = (int)(Tm - b2); o_gbuf = (int)(gbuf - b2); o_xw = (int)(xw - b2);
+        o_om = (int)(om - b2); o_qq = (int)(qq - b2); o_qw = (int)(qw - b2);
+        o_diag1 = (int)(diag1 - b1); o_diag2 = (int)(diag2 - b1); o_v0 = (int)(v0 - b1);
     }
 };
+
+// the CTA's dynamic shared memory, typed: indexing THIS pointer keeps the accesses LDS / STS
+__device__ __forceinline__ double2 *k4_shared()
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    return (double2 *)smem_raw;
+}
+
+// entry (j, k), j < k, of a packed factor with W columns right of column 0 (PackedR::at)
+__device__ __forceinline__ int k4_ridx(const int o_R, const int W, const int j, const int k)
+{
+    return o_R + j * W - (j * (j - 1)) / 2 + (k - j - 1);
+}
 
 // D (8 x 8) += A (8 x 4, row) * B (4 x 8, col), FP64 tensor core.  Fragments (PTX ISA, m8n8k4
 // .f64): a = A[lane >> 2][lane & 3], b = B[lane & 3][lane >> 2], d0/d1 = D[lane >> 2][2 (lane & 3) + 0/1].
@@ -113,70 +135,91 @@ __device__ __forceinline__ double2 k4_cmul(const double2 a, const double2 b)
 // Panel factorisation by warp 0: reflections first..w-1 of the panel starting at column j0
 // (columns before `first` are structurally zero in this tile: phase 2).  Lane l holds rows
 // l and l + 32 of the 8 panel columns.  On return the tile's panel columns hold the
-// reflector tails b_j (the V_b of the update), R / diag the new entries of the panel's rows
-// within the panel, sm.v0 the leading reflector entries and sm.Tm the triangular factor.
-__device__ __forceinline__ void k4_panel(const PanelSmem &sm, const PackedR &R, double *diag, const int j0, const int w,
-                                         const int first, const int lane)
+// reflector tails b_j (the V_b of the update), the factor (o_R, RW, o_diag) the new entries of
+// the panel's rows within the panel, v0[] the leading reflector entries and Tm the triangular
+// factor T.  Latency is what matters here (the other warps wait): per reflection ONE round of
+// warp reductions carries the tail norm, the dot products with the later panel columns and
+// the Gram entries with the earlier tails (their final values: T needs them to full accuracy —
+// forming them from by-products of the reflections loses ||B_k|| / ||b_k|| digits on
+// ill-conditioned overtone columns); all shuffles of a butterfly level are issued together.
+__device__ __forceinline__ void k4_panel(const PanelSmem &sm, const int o_R, const int RW, const int o_diag,
+                                         const int j0, const int w, const int first, const int lane)
 {
+    double2 *const S2 = k4_shared();
+    double *const S1 = (double *)S2;
     double2 X[2][K4_NB];
 #pragma unroll
     for (int kk = 0; kk < K4_NB; ++kk) {
-        const double2 *col = sm.tile + (size_t)(j0 + kk) * K4_S;
+        const int col = sm.o_tile + (j0 + (kk < w ? kk : 0)) * K4_S;
         const bool live = kk < w;
-        X[0][kk] = live ? col[lane] : make_double2(0.0, 0.0);
-        X[1][kk] = live ? col[lane + 32] : make_double2(0.0, 0.0);
+        const double2 x0 = S2[col + lane], x1 = S2[col + lane + 32];
+        X[0][kk] = live ? x0 : make_double2(0.0, 0.0);
+        X[1][kk] = live ? x1 : make_double2(0.0, 0.0);
     }
-    // lane jj keeps reflection jj's by-products: its tail norm and raw dot products
-    double sig_mine = 0.0, beta_mine = 0.0;
-    double2 d_mine[K4_NB];
+    const int i = lane & 7;                       // lanes 0..7 build row i of T
+    double2 Ti[K4_NB];
 #pragma unroll
-    for (int kk = 0; kk < K4_NB; ++kk) d_mine[kk] = make_double2(0.0, 0.0);
-    sm.pbuf[lane] = make_double2(0.0, 0.0);
-    sm.pbuf[lane + 32] = make_double2(0.0, 0.0);
-    __syncwarp();
+    for (int kk = 0; kk < K4_NB; ++kk) Ti[kk] = make_double2(0.0, 0.0);
 
 #pragma unroll
     for (int jj = 0; jj < K4_NB; ++jj) {
-        double v0 = 0.0, beta = 0.0;
+        double v0 = 0.0;
         if (jj >= first && jj < w) {             // warp-uniform
             const int j = j0 + jj;
-            // (A) tail norm and the raw dot products b^H B_k of the panel's later columns
-            double sig = fma(X[0][jj].x, X[0][jj].x, X[1][jj].x * X[1][jj].x);
-            sig = fma(X[0][jj].y, X[0][jj].y, sig);
-            sig = fma(X[1][jj].y, X[1][jj].y, sig);
-            double dr[K4_NB], di[K4_NB];
+            // (A) this lane's share of: val[0] = |b|^2;  val[1 + 2c], val[2 + 2c] = the dot product with
+            // the c-th other column: g_kk,jj = b_kk^H b_jj for earlier tails, d_jj,kk = b_jj^H B_kk for later columns
+            double val[2 * K4_NB - 1];
+            val[0] = fma(X[0][jj].x, X[0][jj].x, X[1][jj].x * X[1][jj].x);
+            val[0] = fma(X[0][jj].y, X[0][jj].y, val[0]);
+            val[0] = fma(X[1][jj].y, X[1][jj].y, val[0]);
 #pragma unroll
-            for (int kk = jj + 1; kk < K4_NB; ++kk) {
-                dr[kk] = fma(X[0][jj].x, X[0][kk].x, X[1][jj].x * X[1][kk].x);
-                di[kk] = fma(X[0][jj].x, X[0][kk].y, X[1][jj].x * X[1][kk].y);
-                dr[kk] = fma(X[0][jj].y, X[0][kk].y, dr[kk]);
-                di[kk] = fma(-X[0][jj].y, X[0][kk].x, di[kk]);
-                dr[kk] = fma(X[1][jj].y, X[1][kk].y, dr[kk]);
-                di[kk] = fma(-X[1][jj].y, X[1][kk].x, di[kk]);
+            for (int kk = 0; kk < K4_NB; ++kk) {
+                if (kk == jj) continue;
+                const int c = kk < jj ? kk : kk - 1;
+                const int a = kk < jj ? kk : jj, bcol = kk < jj ? jj : kk;      // conj(X[.][a]) * X[.][bcol]
+                double dr = fma(X[0][a].x, X[0][bcol].x, X[1][a].x * X[1][bcol].x);
+                double di = fma(X[0][a].x, X[0][bcol].y, X[1][a].x * X[1][bcol].y);
+                dr = fma(X[0][a].y, X[0][bcol].y, dr);
+                di = fma(-X[0][a].y, X[0][bcol].x, di);
+                dr = fma(X[1][a].y, X[1][bcol].y, dr);
+                di = fma(-X[1][a].y, X[1][bcol].x, di);
+                val[1 + 2 * c] = dr;
+                val[2 + 2 * c] = di;
             }
-            sig = warp_sum(sig);
 #pragma unroll
-            for (int kk = jj + 1; kk < K4_NB; ++kk) { dr[kk] = warp_sum(dr[kk]); di[kk] = warp_sum(di[kk]); }
+            for (int s = 16; s > 0; s >>= 1) {
+                double tmp[2 * K4_NB - 1];
+#pragma unroll
+                for (int v = 0; v < 2 * K4_NB - 1; ++v) tmp[v] = __shfl_xor_sync(0xffffffffu, val[v], s);
+#pragma unroll
+                for (int v = 0; v < 2 * K4_NB - 1; ++v) val[v] += tmp[v];
+            }
+            // row i of T, column jj:  T_i,jj = -beta_jj sum_{l<jj} T_il g_l,jj  (in the shadow of the scalars)
+            double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int l = 0; l < jj; ++l) {
+                const double gx = val[1 + 2 * l], gy = val[2 + 2 * l];
+                acc.x = fma(Ti[l].x, gx, acc.x); acc.x = fma(-Ti[l].y, gy, acc.x);
+                acc.y = fma(Ti[l].x, gy, acc.y); acc.y = fma(Ti[l].y, gx, acc.y);
+            }
             // (B) reflector scalars (every lane the same)
-            const double r = diag[j];
-            const double t = fma(r, r, sig) + 1e-300;        // fit_small.cuh: an all-zero column needs no branch
+            const double r = S1[o_diag + j];
+            const double t = fma(r, r, val[0]) + 1e-300;     // fit_small.cuh: an all-zero column needs no branch
             const double y = qf_rsqrt(t);
             const double nrm = t * y;
             const double ar = fabs(r);
             v0 = copysign(ar + nrm, r);
-            beta = qf_rcp(nrm * (ar + nrm));
+            const double beta = qf_rcp(nrm * (ar + nrm));
+            Ti[jj] = jj == i ? make_double2(beta, 0.0) : jj > i ? make_double2(-beta * acc.x, -beta * acc.y) : Ti[jj];
             // (C) the panel's row of R and the rank-1 update of the panel's later columns
+            double2 rnew[K4_NB];
 #pragma unroll
             for (int kk = jj + 1; kk < K4_NB; ++kk) {
                 if (kk < w) {
-                    double2 &Rjk = R.at(j, j0 + kk);
-                    const double2 old = Rjk;
-                    const double2 pv = make_double2(fma(v0, old.x, dr[kk]) * beta, fma(v0, old.y, di[kk]) * beta);
-                    __syncwarp();
-                    if (lane == 0) {
-                        Rjk = make_double2(fma(-v0, pv.x, old.x), fma(-v0, pv.y, old.y));
-                        sm.pbuf[jj * 8 + kk] = pv;
-                    }
+                    const double2 old = S2[k4_ridx(o_R, RW, j, j0 + kk)];
+                    const double2 pv = make_double2(fma(v0, old.x, val[1 + 2 * (kk - 1)]) * beta,
+                                                    fma(v0, old.y, val[2 + 2 * (kk - 1)]) * beta);
+                    rnew[kk] = make_double2(fma(-v0, pv.x, old.x), fma(-v0, pv.y, old.y));
 #pragma unroll
                     for (int a = 0; a < 2; ++a) {
                         double bx = X[a][kk].x, by = X[a][kk].y;
@@ -186,100 +229,71 @@ __device__ __forceinline__ void k4_panel(const PanelSmem &sm, const PackedR &R, 
                         by = fma(-pv.y, X[a][jj].x, by);
                         X[a][kk] = make_double2(bx, by);
                     }
-                    if (lane == jj) d_mine[kk] = make_double2(dr[kk], di[kk]);
                 }
             }
-            if (lane == jj) { sig_mine = sig; beta_mine = beta; }
-            __syncwarp();                                    // every lane has read diag[j]
-            if (lane == 0) diag[j] = -copysign(nrm, r);
+            __syncwarp();                                    // every lane has read row j of the factor
+            if (lane == 0) {
+                S1[o_diag + j] = -copysign(nrm, r);
+#pragma unroll
+                for (int kk = jj + 1; kk < K4_NB; ++kk)
+                    if (kk < w) S2[k4_ridx(o_R, RW, j, j0 + kk)] = rnew[kk];
+            }
         }
-        if (lane == 0) sm.v0[jj] = v0;
+        if (lane == 0) S1[sm.o_v0 + jj] = v0;
     }
-    // the reflector tails become the V_b of the update
+    // the reflector tails become the V_b of the update; T (zero below the diagonal and in the
+    // rows / columns of absent reflections)
 #pragma unroll
     for (int kk = 0; kk < K4_NB; ++kk) {
         if (kk < w) {
-            double2 *col = sm.tile + (size_t)(j0 + kk) * K4_S;
-            col[lane] = X[0][kk];
-            col[lane + 32] = X[1][kk];
+            const int col = sm.o_tile + (j0 + kk) * K4_S;
+            S2[col + lane] = X[0][kk];
+            S2[col + lane + 32] = X[1][kk];
         }
     }
-    __syncwarp();
-    // Gram of the tails, row i by lane i:  g_ij = d_ij - |b_i|^2 p_ij - sum_{i<l<j} g_il p_lj
-    // (zero for j <= i), then  T_ij = -beta_j sum_{l<j} T_il g_lj,  T_ii = beta_i.
-    {
-        const int i = lane & 7;
-        double2 gi[K4_NB];
+    if (lane < 8) {
 #pragma unroll
-        for (int j = 0; j < K4_NB; ++j) {
-            double2 acc = make_double2(0.0, 0.0);
-            if (j > i) {
-                const double2 pij = sm.pbuf[i * 8 + j];
-                acc = make_double2(fma(-sig_mine, pij.x, d_mine[j].x), fma(-sig_mine, pij.y, d_mine[j].y));
-            }
-#pragma unroll
-            for (int l = 1; l < j; ++l) {           // g_il = 0 for l <= i, so the sum may start at 1
-                const double2 plj = sm.pbuf[l * 8 + j];
-                acc.x = fma(-gi[l].x, plj.x, acc.x); acc.x = fma(gi[l].y, plj.y, acc.x);
-                acc.y = fma(-gi[l].x, plj.y, acc.y); acc.y = fma(-gi[l].y, plj.x, acc.y);
-            }
-            gi[j] = j > i ? acc : make_double2(0.0, 0.0);
-            if (lane < 8) sm.gbuf[i * 8 + j] = gi[j];
-        }
-        __syncwarp();
-        // betas of all reflections, from the lanes that own them
-        double bj[K4_NB];
-#pragma unroll
-        for (int j = 0; j < K4_NB; ++j) bj[j] = __shfl_sync(0xffffffffu, beta_mine, j);
-        double2 Ti[K4_NB];
-#pragma unroll
-        for (int j = 0; j < K4_NB; ++j) {
-            double2 acc = make_double2(0.0, 0.0);
-#pragma unroll
-            for (int l = 0; l < j; ++l) {
-                const double2 glj = sm.gbuf[l * 8 + j];
-                acc.x = fma(Ti[l].x, glj.x, acc.x); acc.x = fma(-Ti[l].y, glj.y, acc.x);
-                acc.y = fma(Ti[l].x, glj.y, acc.y); acc.y = fma(Ti[l].y, glj.x, acc.y);
-            }
-            Ti[j] = j < i ? make_double2(0.0, 0.0)
-                  : j == i ? make_double2(beta_mine, 0.0) : make_double2(-bj[j] * acc.x, -bj[j] * acc.y);
-            if (lane < 8) sm.Tm[i * 8 + j] = Ti[j];
-        }
+        for (int j = 0; j < K4_NB; ++j) S2[sm.o_Tm + i * 8 + j] = Ti[j];
     }
 }
 
 // ---------------------------------------------------------------------------------------
 // Trailing update of one 8-column chunk [c0, c0 + 8) by one warp (columns >= ncols are
 // padding: read as zero, never stored).  Vr / Vi: the warp's A fragments of V_b^H for the 16
-// k-steps of the tile's 64 rows (thread (g, t): conj V_b[4 s + t][g]).  Shared-memory access
+// k-steps of the tile's 64 rows (thread (g, t): V_b[4 s + t][g]).  Shared-memory access
 // patterns with the odd column stride K4_S: the C fragments of the second product are
 // conflict-free, its A fragments and the B fragments of the first product are two-way.
-__device__ __forceinline__ void k4_update_chunk(const PanelSmem &sm, const PackedR &R, const int j0, const int w,
-                                                const int first, const int c0, const int ncols,
-                                                const double (&Vr)[16], const double (&Vi)[16], double2 *xw,
+__device__ __forceinline__ void k4_update_chunk(const PanelSmem &sm, const int o_R, const int RW, const int j0,
+                                                const int w, const int first, const int c0, const int ncols,
+                                                const double (&Vr)[16], const double (&Vi)[16], const int o_xw,
                                                 const int lane)
 {
+    double2 *const S2 = k4_shared();
+    double *const S1 = (double *)S2;
     const int g = lane >> 2, t = lane & 3;
     const int col0 = c0 + 2 * t, col1 = col0 + 1;
     const bool ok0 = col0 < ncols, ok1 = col1 < ncols;
     const bool row_ok = g < w && g >= first;                  // reflector g exists
-    const double v0g = sm.v0[g];                               // zero for absent reflectors
+    const double v0g = S1[sm.o_v0 + g];                        // zero for absent reflectors
+    const int r0i = k4_ridx(o_R, RW, j0 + (row_ok ? g : 0), ok0 ? col0 : c0);
+    const int r1i = k4_ridx(o_R, RW, j0 + (row_ok ? g : 0), ok1 ? col1 : c0);
     // ---- X = diag(v0) R_panel,chunk + V_b^H B_chunk
     double xr0 = 0.0, xr1 = 0.0, xi0 = 0.0, xi1 = 0.0;         // even k-steps (and the R term)
     double yr0 = 0.0, yr1 = 0.0, yi0 = 0.0, yi1 = 0.0;         // odd k-steps
-    if (row_ok) {
-        if (ok0) { const double2 r = R.at(j0 + g, col0); xr0 = v0g * r.x; xi0 = v0g * r.y; }
-        if (ok1) { const double2 r = R.at(j0 + g, col1); xr1 = v0g * r.x; xi1 = v0g * r.y; }
+    {
+        const double2 ra = S2[r0i], rb = S2[r1i];
+        if (row_ok && ok0) { xr0 = v0g * ra.x; xi0 = v0g * ra.y; }
+        if (row_ok && ok1) { xr1 = v0g * rb.x; xi1 = v0g * rb.y; }
     }
     {
         const int cb = c0 + g;
         const bool okb = cb < ncols;
-        const double2 *bcol = sm.tile + (size_t)(okb ? cb : c0) * K4_S + t;
+        const int bcol = sm.o_tile + (okb ? cb : c0) * K4_S + t;
 #pragma unroll
         for (int s = 0; s < 16; s += 2) {
-            double2 b0 = bcol[4 * s], b1 = bcol[4 * s + 4];
+            double2 b0 = S2[bcol + 4 * s], b1 = S2[bcol + 4 * s + 4];
             if (!okb) { b0 = make_double2(0.0, 0.0); b1 = b0; }
-            // X += conj(V)^T B:  Xr += Vr Br + Vi Bi,  Xi += Vr Bi - Vi Br   (Vi holds +Im V)
+            // X += conj(V)^T B:  Xr += Vr Br + Vi Bi,  Xi += Vr Bi - Vi Br
             k4_dmma(xr0, xr1, Vr[s], b0.x);         k4_dmma(yr0, yr1, Vr[s + 1], b1.x);
             k4_dmma(xi0, xi1, Vr[s], b0.y);         k4_dmma(yi0, yi1, Vr[s + 1], b1.y);
             k4_dmma(xr0, xr1, Vi[s], b0.y);         k4_dmma(yr0, yr1, Vi[s + 1], b1.y);
@@ -289,14 +303,14 @@ __device__ __forceinline__ void k4_update_chunk(const PanelSmem &sm, const Packe
     xr0 += yr0; xr1 += yr1; xi0 += yi0; xi1 += yi1;
     // ---- W = T^H X: X goes from the accumulator layout to the B layout through the warp's buffer
     __syncwarp();
-    xw[g * K4_XS + 2 * t] = make_double2(xr0, xi0);
-    xw[g * K4_XS + 2 * t + 1] = make_double2(xr1, xi1);
+    S2[o_xw + g * K4_XS + 2 * t] = make_double2(xr0, xi0);
+    S2[o_xw + g * K4_XS + 2 * t + 1] = make_double2(xr1, xi1);
     __syncwarp();
     double wr0 = 0.0, wr1 = 0.0, wi0 = 0.0, wi1 = 0.0;
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-        const double2 xb = xw[(4 * s + t) * K4_XS + g];        // X[4 s + t][g]
-        const double2 tt = sm.Tm[(4 * s + t) * 8 + g];          // T^H[g][4 s + t] = conj(T[4 s + t][g])
+        const double2 xb = S2[o_xw + (4 * s + t) * K4_XS + g];     // X[4 s + t][g]
+        const double2 tt = S2[sm.o_Tm + (4 * s + t) * 8 + g];      // T^H[g][4 s + t] = conj(T[4 s + t][g])
         // W += conj(T)^T X:  Wr += Tr Xr + Ti Xi,  Wi += Tr Xi - Ti Xr
         k4_dmma(wr0, wr1, tt.x, xb.x);
         k4_dmma(wi0, wi1, tt.x, xb.y);
@@ -305,26 +319,26 @@ __device__ __forceinline__ void k4_update_chunk(const PanelSmem &sm, const Packe
     }
     // ---- the panel's rows of R
     if (row_ok) {
-        if (ok0) { double2 &r = R.at(j0 + g, col0); r = make_double2(fma(-v0g, wr0, r.x), fma(-v0g, wi0, r.y)); }
-        if (ok1) { double2 &r = R.at(j0 + g, col1); r = make_double2(fma(-v0g, wr1, r.x), fma(-v0g, wi1, r.y)); }
+        if (ok0) { const double2 r = S2[r0i]; S2[r0i] = make_double2(fma(-v0g, wr0, r.x), fma(-v0g, wi0, r.y)); }
+        if (ok1) { const double2 r = S2[r1i]; S2[r1i] = make_double2(fma(-v0g, wr1, r.x), fma(-v0g, wi1, r.y)); }
     }
     // ---- B_chunk -= V_b W: -W in the B layout
     __syncwarp();
-    xw[g * K4_XS + 2 * t] = make_double2(-wr0, -wi0);
-    xw[g * K4_XS + 2 * t + 1] = make_double2(-wr1, -wi1);
+    S2[o_xw + g * K4_XS + 2 * t] = make_double2(-wr0, -wi0);
+    S2[o_xw + g * K4_XS + 2 * t + 1] = make_double2(-wr1, -wi1);
     __syncwarp();
-    const double2 n0 = xw[t * K4_XS + g], n1 = xw[(4 + t) * K4_XS + g];      // -W[t][g], -W[4 + t][g]
+    const double2 n0 = S2[o_xw + t * K4_XS + g], n1 = S2[o_xw + (4 + t) * K4_XS + g];     // -W[t][g], -W[4 + t][g]
     const bool va0 = t < w && t >= first, va1 = 4 + t < w && 4 + t >= first;    // panel columns that are reflectors
-    const double2 *vcol0 = sm.tile + (size_t)(j0 + (va0 ? t : 0)) * K4_S + g;
-    const double2 *vcol1 = sm.tile + (size_t)(j0 + (va1 ? 4 + t : 0)) * K4_S + g;
-    double2 *ccol0 = sm.tile + (size_t)(ok0 ? col0 : c0) * K4_S + g;
-    double2 *ccol1 = sm.tile + (size_t)(ok1 ? col1 : c0) * K4_S + g;
+    const int vcol0 = sm.o_tile + (j0 + (va0 ? t : 0)) * K4_S + g;
+    const int vcol1 = sm.o_tile + (j0 + (va1 ? 4 + t : 0)) * K4_S + g;
+    const int ccol0 = sm.o_tile + (ok0 ? col0 : c0) * K4_S + g;
+    const int ccol1 = sm.o_tile + (ok1 ? col1 : c0) * K4_S + g;
 #pragma unroll
     for (int r = 0; r < K4_M / 8; ++r) {
-        double2 a0 = vcol0[8 * r], a1 = vcol1[8 * r];
+        double2 a0 = S2[vcol0 + 8 * r], a1 = S2[vcol1 + 8 * r];
         if (!va0) a0 = make_double2(0.0, 0.0);
         if (!va1) a1 = make_double2(0.0, 0.0);
-        double2 c_0 = ccol0[8 * r], c_1 = ccol1[8 * r];
+        const double2 c_0 = S2[ccol0 + 8 * r], c_1 = S2[ccol1 + 8 * r];
         double cr0 = c_0.x, cr1 = c_1.x, ci0 = c_0.y, ci1 = c_1.y;
         // C += V (-W):  Cr += Vr Nr - Vi Ni,  Ci += Vr Ni + Vi Nr
         k4_dmma(cr0, cr1, a0.x, n0.x);
@@ -335,20 +349,24 @@ __device__ __forceinline__ void k4_update_chunk(const PanelSmem &sm, const Packe
         k4_dmma(ci0, ci1, a1.x, n1.y);
         k4_dmma(cr0, cr1, a1.y, -n1.y);
         k4_dmma(ci0, ci1, a1.y, n1.x);
-        if (ok0) ccol0[8 * r] = make_double2(cr0, ci0);
-        if (ok1) ccol1[8 * r] = make_double2(cr1, ci1);
+        if (ok0) S2[ccol0 + 8 * r] = make_double2(cr0, ci0);
+        if (ok1) S2[ccol1 + 8 * r] = make_double2(cr1, ci1);
     }
 }
 
-// All reflections jstart..N-1 of [R; tile] (tile: K4_M rows x ncols columns in sm.tile).
-__device__ __forceinline__ void k4_factor_tile(const PanelSmem &sm, const PackedR &R, double *diag, const int ncols,
-                                               const int N, const int jstart, const int lane, const int warp)
+// All reflections jstart..N-1 of [R; tile] (tile: K4_M rows x ncols columns; factor at o_R with
+// RW columns right of column 0, diagonal at o_diag).  `warp` must be warp-uniform for the
+// compiler (see the kernel), or every shuffle of the panel is wrapped in a convergence check.
+__device__ __forceinline__ void k4_factor_tile(const PanelSmem &sm, const int o_R, const int RW, const int o_diag,
+                                               const int ncols, const int N, const int jstart, const int lane,
+                                               const int warp)
 {
+    double2 *const S2 = k4_shared();
 #pragma unroll 1
     for (int j0 = (jstart / K4_NB) * K4_NB; j0 < N; j0 += K4_NB) {
         const int w = N - j0 < K4_NB ? N - j0 : K4_NB;
         const int first = jstart > j0 ? jstart - j0 : 0;
-        if (warp == 0) k4_panel(sm, R, diag, j0, w, first, lane);
+        if (warp == 0) k4_panel(sm, o_R, RW, o_diag, j0, w, first, lane);
         __syncthreads();
         const int cbeg = j0 + w;
         const int nchunks = (ncols - cbeg + 7) / 8;
@@ -357,16 +375,16 @@ __device__ __forceinline__ void k4_factor_tile(const PanelSmem &sm, const Packed
             {
                 const int g = lane >> 2, t = lane & 3;
                 const bool live = g < w && g >= first;
-                const double2 *vcol = sm.tile + (size_t)(j0 + (live ? g : 0)) * K4_S + t;
+                const int vcol = sm.o_tile + (j0 + (live ? g : 0)) * K4_S + t;
 #pragma unroll
                 for (int s = 0; s < 16; ++s) {
-                    const double2 v = vcol[4 * s];
+                    const double2 v = S2[vcol + 4 * s];
                     Vr[s] = live ? v.x : 0.0;
                     Vi[s] = live ? v.y : 0.0;
                 }
             }
             for (int ch = warp; ch < nchunks; ch += K4_WARPS)
-                k4_update_chunk(sm, R, j0, w, first, cbeg + 8 * ch, ncols, Vr, Vi, sm.xw + warp * 8 * K4_XS, lane);
+                k4_update_chunk(sm, o_R, RW, j0, w, first, cbeg + 8 * ch, ncols, Vr, Vi, sm.o_xw + warp * 8 * K4_XS, lane);
         }
         __syncthreads();
     }
@@ -377,10 +395,13 @@ __global__ void __launch_bounds__(K4_THREADS, 2) fit_panel_kernel(const __grid_c
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = p.n_modes, L = p.n_series, NC = N + L;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform by construction
     const int fit = blockIdx.x;
     PanelSmem sm;
     sm.carve(smem_raw, N, L);
+    double2 *const S2 = k4_shared();
+    double *const S1 = (double *)S2;
 
     const int fi = input_fit(p, fit);
     int rb = p.row_begin ? p.row_begin[fi] : p.row_begin_all;
@@ -400,21 +421,21 @@ __global__ void __launch_bounds__(K4_THREADS, 2) fit_panel_kernel(const __grid_c
 
     for (int j = tid; j < N; j += K4_THREADS) {
         const double2 w = fit_omega(p, fi, j);
-        sm.om[j] = w;
+        S2[sm.o_om + j] = w;
         if (p.dt_nominal > 0.0) {
             const double2 q = design_entry(w, p.dt_nominal);
-            sm.qq[j] = q;
-            sm.qw[j] = c_mul(q, make_double2(w.y, -w.x));
+            S2[sm.o_qq + j] = q;
+            S2[sm.o_qw + j] = c_mul(q, make_double2(w.y, -w.x));
         }
-        sm.diag1[j] = 0.0;
-        sm.diag2[j] = 0.0;
+        S1[sm.o_diag1 + j] = 0.0;
+        S1[sm.o_diag2 + j] = 0.0;
     }
     {
         const int n1 = (int)PackedR::entries(N, NC - 1);
-        for (int e = tid; e < n1; e += K4_THREADS) sm.R1.a[e] = make_double2(0.0, 0.0);
+        for (int e = tid; e < n1; e += K4_THREADS) S2[sm.o_R1 + e] = make_double2(0.0, 0.0);
         if (!PanelSmem::r2_in_tile(N, L)) {
             const int n2 = (int)PackedR::entries(N, N);
-            for (int e = tid; e < n2; e += K4_THREADS) sm.R2.a[e] = make_double2(0.0, 0.0);
+            for (int e = tid; e < n2; e += K4_THREADS) S2[sm.o_R2 + e] = make_double2(0.0, 0.0);
         }
     }
     __syncthreads();
@@ -430,17 +451,17 @@ __global__ void __launch_bounds__(K4_THREADS, 2) fit_panel_kernel(const __grid_c
             // (fit_small.cuh, small_leaf_uniform), or direct evaluation of every element
             for (int e = tid; e < N * 4; e += K4_THREADS) {
                 const int c = e >> 2, seg = e & 3;
-                double2 *col = sm.tile + (size_t)c * K4_S + seg * 16;
+                const int col = sm.o_tile + c * K4_S + seg * 16;
                 const int first = row0 + seg * 16;
                 if (recur) {
                     if (first < re) {
                         const double dt = p.dt_nominal;
                         double tau = qf_sub_rn(p.times[first], t0);
-                        double2 z = design_entry(sm.om[c], tau);
-                        const double2 q = sm.qq[c], wq = sm.qw[c];
+                        double2 z = design_entry(S2[sm.o_om + c], tau);
+                        const double2 q = S2[sm.o_qq + c], wq = S2[sm.o_qw + c];
 #pragma unroll 4
                         for (int r = 0; r < 16; ++r) {
-                            col[r] = first + r < re ? z : make_double2(0.0, 0.0);
+                            S2[col + r] = first + r < re ? z : make_double2(0.0, 0.0);
                             const int kn = first + r + 1 < re ? first + r + 1 : re - 1;
                             const double tau_n = qf_sub_rn(p.times[kn], t0);
                             const double de = qf_sub_rn(qf_sub_rn(tau_n, tau), dt);
@@ -448,13 +469,16 @@ __global__ void __launch_bounds__(K4_THREADS, 2) fit_panel_kernel(const __grid_c
                             z = c_mul(z, make_double2(fma(wq.x, de, q.x), fma(wq.y, de, q.y)));
                         }
                     } else {
-                        for (int r = 0; r < 16; ++r) col[r] = make_double2(0.0, 0.0);
+                        for (int r = 0; r < 16; ++r) S2[col + r] = make_double2(0.0, 0.0);
                     }
                 } else {
                     for (int r = 0; r < 16; ++r) {
                         double2 v = make_double2(0.0, 0.0);
-                        if (first + r < re) v = design_entry(row_omega(p, sm.om, c, first + r), qf_sub_rn(p.times[first + r], t0));
-                        col[r] = v;
+                        if (first + r < re) {
+                            const double2 om = p.omega_rows ? p.omega_rows[(long long)c * p.n_times + first + r] : S2[sm.o_om + c];
+                            v = design_entry(om, qf_sub_rn(p.times[first + r], t0));
+                        }
+                        S2[col + r] = v;
                     }
                 }
             }
@@ -463,15 +487,15 @@ __global__ void __launch_bounds__(K4_THREADS, 2) fit_panel_kernel(const __grid_c
                 const int i = e / K4_M, r = e - i * K4_M;
                 double2 v = make_double2(0.0, 0.0);
                 if (row0 + r < re) v = p.data[(long long)i * p.series_stride + row0 + r];
-                sm.tile[(size_t)(N + i) * K4_S + r] = v;
+                S2[sm.o_tile + (N + i) * K4_S + r] = v;
                 sdd = fma(v.x, v.x, sdd);
                 sdd = fma(v.y, v.y, sdd);
             }
             __syncthreads();
-            k4_factor_tile(sm, sm.R1, sm.diag1, NC, N, 0, lane, warp);
+            k4_factor_tile(sm, sm.o_R1, NC - 1, sm.o_diag1, NC, N, 0, lane, warp);
             for (int e = tid; e < L * K4_M; e += K4_THREADS) {     // what is left of the right-hand sides
                 const int i = e / K4_M, r = e - i * K4_M;
-                const double2 v = sm.tile[(size_t)(N + i) * K4_S + r];
+                const double2 v = S2[sm.o_tile + (N + i) * K4_S + r];
                 res2 = fma(v.x, v.x, res2);
                 res2 = fma(v.y, v.y, res2);
             }
@@ -482,7 +506,7 @@ __global__ void __launch_bounds__(K4_THREADS, 2) fit_panel_kernel(const __grid_c
         if (two_phase) {
             if (PanelSmem::r2_in_tile(N, L)) {      // R2 lives behind the N + 1 columns of the phase-2 tile
                 const int n2 = (int)PackedR::entries(N, N);
-                for (int e = tid; e < n2; e += K4_THREADS) sm.R2.a[e] = make_double2(0.0, 0.0);
+                for (int e = tid; e < n2; e += K4_THREADS) S2[sm.o_R2 + e] = make_double2(0.0, 0.0);
             }
             const int rows2 = N * L;
             const int ntiles2 = (rows2 + K4_M - 1) / K4_M;
@@ -495,18 +519,19 @@ __global__ void __launch_bounds__(K4_THREADS, 2) fit_panel_kernel(const __grid_c
                     double2 v = make_double2(0.0, 0.0);
                     if (q < rows2) {
                         const int rr = q / L, i = q - rr * L;
-                        if (c == N) v = sm.R1.at(rr, N + i);
+                        if (c == N) v = S2[k4_ridx(sm.o_R1, NC - 1, rr, N + i)];
                         else if (c >= rr) {
                             const double2 cf = coef ? coef[i * N + c] : make_double2(1.0, 0.0);
-                            v = c == rr ? make_double2(cf.x * sm.diag1[rr], cf.y * sm.diag1[rr]) : k4_cmul(cf, sm.R1.at(rr, c));
+                            const double d = S1[sm.o_diag1 + rr];
+                            v = c == rr ? make_double2(cf.x * d, cf.y * d) : k4_cmul(cf, S2[k4_ridx(sm.o_R1, NC - 1, rr, c)]);
                         }
                     }
-                    sm.tile[(size_t)c * K4_S + r] = v;
+                    S2[sm.o_tile + c * K4_S + r] = v;
                 }
                 __syncthreads();
-                k4_factor_tile(sm, sm.R2, sm.diag2, N + 1, N, jstart, lane, warp);
+                k4_factor_tile(sm, sm.o_R2, N, sm.o_diag2, N + 1, N, jstart, lane, warp);
                 for (int r = tid; r < K4_M; r += K4_THREADS) {
-                    const double2 v = sm.tile[(size_t)N * K4_S + r];
+                    const double2 v = S2[sm.o_tile + N * K4_S + r];
                     res2 = fma(v.x, v.x, res2);
                     res2 = fma(v.y, v.y, res2);
                 }

@@ -199,10 +199,14 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
     const bool panel_ok = !b->coef_rows && b->n_series <= 64
         && k4_smem_bytes(b->n_modes, b->n_series) <= (size_t)ctx->smem_optin;
     if (kernel == QNMFIT_KERNEL_AUTO) {
-        const char *force = getenv("QNMFIT_AUTO_STRUCT");     // developer knob: K3 instead of K4
+        // K3 where it applies (N + L <= 64) unless QNMFIT_AUTO_PANEL=1, K4 beyond: K4's trailing
+        // update runs on the tensor cores, but its panel factorisation is not yet fast enough to
+        // beat K3 on the shapes both take
+        const char *force = getenv("QNMFIT_AUTO_PANEL");
+        const bool prefer_panel = force && force[0] == '1';
         kernel = small_ok ? QNMFIT_KERNEL_SMALL
-               : panel_ok && !(force && force[0] == '1' && struct_ok) ? QNMFIT_KERNEL_PANEL
-               : struct_ok ? QNMFIT_KERNEL_STRUCT : QNMFIT_KERNEL_GENERAL;
+               : struct_ok && !(prefer_panel && panel_ok) ? QNMFIT_KERNEL_STRUCT
+               : panel_ok ? QNMFIT_KERNEL_PANEL : QNMFIT_KERNEL_GENERAL;
     }
     if (kernel == QNMFIT_KERNEL_PANEL && !panel_ok)
         return fail(ctx, QNMFIT_E_SHAPE, "K4 needs no per-row coef table and a tile that fits shared memory (n_modes=%d, n_series=%d)",
