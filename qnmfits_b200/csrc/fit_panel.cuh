@@ -43,13 +43,13 @@ struct PanelSmem {
     PackedR R1;       // N rows, N+L columns: R_E | Y
     PackedR R2;       // N rows, N+1 columns: second factor | Q^H d  (lives in unused tile columns when it fits)
     double2 *tile;    // [NC][K4_S] column-major
-    double2 *Tm;      // [8][8]  T of the current panel (upper triangular, zero below)
+    double2 *Tm;      // [2][8][8]  T of the panel being applied / being factored (upper triangular, zero below)
     double2 *gbuf;    // [8][8]  Gram of the reflector tails
     double2 *xw;      // [K4_WARPS][8][K4_XS]  fragment-layout exchange, one per warp
     double2 *om, *qq, *qw, *Cv;   // [N]
     double2 *scratch; // struct_finish: cc [L][N] then E [K3C_TK][N]   (overlays the tile)
     double *diag1, *diag2;        // [N]
-    double *v0;       // [8]
+    double *v0;       // [2][8]: leading reflector entries of the same two panels
     double *red;      // [16][8]
     double *ends;     // [64][3]
     // The same arrays as element offsets from the start of the CTA's shared memory (double2
@@ -71,8 +71,8 @@ struct PanelSmem {
         size_t tile = (size_t)(N + L) * K4_S;
         const size_t scr = (size_t)L * N + (size_t)K3C_TK * N;
         if (tile < scr) tile = scr;
-        return sizeof(double2) * (r1 + r2 + tile + 2 * 64 + (size_t)K4_WARPS * 8 * K4_XS + 4 * (size_t)N)
-             + sizeof(double) * (2 * (size_t)N + 8 + 128 + 64 * 3);
+        return sizeof(double2) * (r1 + r2 + tile + 3 * 64 + (size_t)K4_WARPS * 8 * K4_XS + 4 * (size_t)N)
+             + sizeof(double) * (2 * (size_t)N + 16 + 128 + 64 * 3);
     }
     __device__ void carve(void *base, int N, int L)
     {
@@ -87,13 +87,13 @@ struct PanelSmem {
         R2.W = N;
         if (r2_in_tile(N, L)) R2.a = tile + (size_t)(N + 1) * K4_S;
         else { R2.a = p; p += PackedR::entries(N, N); }
-        Tm = p; p += 64; gbuf = p; p += 64;
+        Tm = p; p += 128; gbuf = p; p += 64;
         xw = p; p += K4_WARPS * 8 * K4_XS;
         om = p; p += N; qq = p; p += N; qw = p; p += N; Cv = p; p += N;
         double *d = (double *)p;
         diag1 = d; d += N;
         diag2 = d; d += N;
-        v0 = d; d += 8;
+        v0 = d; d += 16;
         red = d; d += 128;
         ends = d;
         const double2 *b2 = (const double2 *)base;
@@ -131,129 +131,136 @@ __device__ __forceinline__ double2 k4_cmul(const double2 a, const double2 b)
     return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));
 }
 
+// sum over the 4 lanes that share a panel column (every lane of the warp must call it)
+__device__ __forceinline__ double k4_sum4(double v)
+{
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
 // ---------------------------------------------------------------------------------------
-// Panel factorisation by warp 0: reflections first..w-1 of the panel starting at column j0
-// (columns before `first` are structurally zero in this tile: phase 2).  Lane l holds rows
-// l and l + 32 of the 8 panel columns.  On return the tile's panel columns hold the
-// reflector tails b_j (the V_b of the update), the factor (o_R, RW, o_diag) the new entries of
-// the panel's rows within the panel, v0[] the leading reflector entries and Tm the triangular
-// factor T.  Latency is what matters here (the other warps wait): per reflection ONE round of
-// warp reductions carries the tail norm, the dot products with the later panel columns and
-// the Gram entries with the earlier tails (their final values: T needs them to full accuracy —
-// forming them from by-products of the reflections loses ||B_k|| / ||b_k|| digits on
-// ill-conditioned overtone columns); all shuffles of a butterfly level are issued together.
+// Panel factorisation by ONE warp: reflections first..w-1 of the panel starting at column j0
+// (columns before `first` are structurally zero in this tile: phase 2).  Lane (c = lane / 4,
+// q = lane % 4) owns rows q + 4 a, a = 0..15, of panel column c in registers: a column's dot
+// product needs two shuffle levels over its four lanes, and the whole warp runs the same
+// instruction stream (eight columns side by side).  Reflection jj:
+//   * every column keeps |its rows|^2 current (accumulated by the update pass); column jj's
+//     lanes publish their rows — the final reflector tail b_jj — to the tile, and every lane
+//     forms the reflector scalars from the broadcast norm;
+//   * every column forms b_jj^H x over its rows: later columns update their entry of row jj of
+//     the factor and their rows; earlier columns (final tails) deliver the Gram entry g_c,jj =
+//     b_c^H b_jj that T needs (formed from the final tails: building it from by-products of
+//     the reflections loses ||B_k|| / ||b_k|| digits on ill-conditioned overtone columns);
+//   * lanes 0..7 extend row `lane` of T by column jj:  T_ii = beta_i,
+//     T_i,jj = -beta_jj sum_{l<jj} T_il g_l,jj.
+// On return the tile's panel columns hold the tails (the V_b of the update), the factor
+// (o_R, RW, o_diag) the panel's rows within the panel, v0[buf] / Tm[buf] the leading reflector
+// entries and T.  Two earlier forms are in profiles/README.md: rows over lanes with all eight
+// columns per lane (15-value five-level butterflies: issue-bound on one scheduler, 16.5 k
+// cycles per panel) and the whole CTA with one barrier per reflection (10 k cycles, and no
+// warp left to apply the previous panel meanwhile).
 __device__ __forceinline__ void k4_panel(const PanelSmem &sm, const int o_R, const int RW, const int o_diag,
-                                         const int j0, const int w, const int first, const int lane)
+                                         const int j0, const int w, const int first, const int lane, const int buf)
 {
     double2 *const S2 = k4_shared();
     double *const S1 = (double *)S2;
-    double2 X[2][K4_NB];
+    const int c = lane >> 2, q = lane & 3;
+    const bool in_panel = c < w;
+    const int colbase = sm.o_tile + (j0 + (in_panel ? c : 0)) * K4_S + q;
+    double2 x[16];
+    double part0 = 0.0, part1 = 0.0;
 #pragma unroll
-    for (int kk = 0; kk < K4_NB; ++kk) {
-        const int col = sm.o_tile + (j0 + (kk < w ? kk : 0)) * K4_S;
-        const bool live = kk < w;
-        const double2 x0 = S2[col + lane], x1 = S2[col + lane + 32];
-        X[0][kk] = live ? x0 : make_double2(0.0, 0.0);
-        X[1][kk] = live ? x1 : make_double2(0.0, 0.0);
+    for (int a = 0; a < 16; ++a) {
+        const double2 v = S2[colbase + 4 * a];
+        x[a] = in_panel ? v : make_double2(0.0, 0.0);
     }
-    const int i = lane & 7;                       // lanes 0..7 build row i of T
-    double2 Ti[K4_NB];
+#pragma unroll
+    for (int a = 0; a < 16; a += 2) {
+        part0 = fma(x[a].x, x[a].x, part0);         part1 = fma(x[a + 1].x, x[a + 1].x, part1);
+        part0 = fma(x[a].y, x[a].y, part0);         part1 = fma(x[a + 1].y, x[a + 1].y, part1);
+    }
+    double part = part0 + part1;
+    S2[sm.o_gbuf + lane] = make_double2(0.0, 0.0);
+    S2[sm.o_gbuf + lane + 32] = make_double2(0.0, 0.0);
+    double2 Ti[K4_NB];                            // lanes 0..7: row `lane` of T
 #pragma unroll
     for (int kk = 0; kk < K4_NB; ++kk) Ti[kk] = make_double2(0.0, 0.0);
+    __syncwarp();
 
 #pragma unroll
     for (int jj = 0; jj < K4_NB; ++jj) {
-        double v0 = 0.0;
+        double v0 = 0.0, beta = 0.0;
         if (jj >= first && jj < w) {             // warp-uniform
             const int j = j0 + jj;
-            // (A) this lane's share of: val[0] = |b|^2;  val[1 + 2c], val[2 + 2c] = the dot product with
-            // the c-th other column: g_kk,jj = b_kk^H b_jj for earlier tails, d_jj,kk = b_jj^H B_kk for later columns
-            double val[2 * K4_NB - 1];
-            val[0] = fma(X[0][jj].x, X[0][jj].x, X[1][jj].x * X[1][jj].x);
-            val[0] = fma(X[0][jj].y, X[0][jj].y, val[0]);
-            val[0] = fma(X[1][jj].y, X[1][jj].y, val[0]);
+            const double tot = __shfl_sync(0xffffffffu, k4_sum4(part), 4 * jj);     // |b_jj|^2
+            if (c == jj) {
 #pragma unroll
-            for (int kk = 0; kk < K4_NB; ++kk) {
-                if (kk == jj) continue;
-                const int c = kk < jj ? kk : kk - 1;
-                const int a = kk < jj ? kk : jj, bcol = kk < jj ? jj : kk;      // conj(X[.][a]) * X[.][bcol]
-                double dr = fma(X[0][a].x, X[0][bcol].x, X[1][a].x * X[1][bcol].x);
-                double di = fma(X[0][a].x, X[0][bcol].y, X[1][a].x * X[1][bcol].y);
-                dr = fma(X[0][a].y, X[0][bcol].y, dr);
-                di = fma(-X[0][a].y, X[0][bcol].x, di);
-                dr = fma(X[1][a].y, X[1][bcol].y, dr);
-                di = fma(-X[1][a].y, X[1][bcol].x, di);
-                val[1 + 2 * c] = dr;
-                val[2 + 2 * c] = di;
+                for (int a = 0; a < 16; ++a) S2[colbase + 4 * a] = x[a];             // the final tail b_jj
             }
-#pragma unroll
-            for (int s = 16; s > 0; s >>= 1) {
-                double tmp[2 * K4_NB - 1];
-#pragma unroll
-                for (int v = 0; v < 2 * K4_NB - 1; ++v) tmp[v] = __shfl_xor_sync(0xffffffffu, val[v], s);
-#pragma unroll
-                for (int v = 0; v < 2 * K4_NB - 1; ++v) val[v] += tmp[v];
-            }
-            // row i of T, column jj:  T_i,jj = -beta_jj sum_{l<jj} T_il g_l,jj  (in the shadow of the scalars)
-            double2 acc = make_double2(0.0, 0.0);
-#pragma unroll
-            for (int l = 0; l < jj; ++l) {
-                const double gx = val[1 + 2 * l], gy = val[2 + 2 * l];
-                acc.x = fma(Ti[l].x, gx, acc.x); acc.x = fma(-Ti[l].y, gy, acc.x);
-                acc.y = fma(Ti[l].x, gy, acc.y); acc.y = fma(Ti[l].y, gx, acc.y);
-            }
-            // (B) reflector scalars (every lane the same)
             const double r = S1[o_diag + j];
-            const double t = fma(r, r, val[0]) + 1e-300;     // fit_small.cuh: an all-zero column needs no branch
+            const double t = fma(r, r, tot) + 1e-300;        // fit_small.cuh: an all-zero column needs no branch
             const double y = qf_rsqrt(t);
             const double nrm = t * y;
             const double ar = fabs(r);
             v0 = copysign(ar + nrm, r);
-            const double beta = qf_rcp(nrm * (ar + nrm));
-            Ti[jj] = jj == i ? make_double2(beta, 0.0) : jj > i ? make_double2(-beta * acc.x, -beta * acc.y) : Ti[jj];
-            // (C) the panel's row of R and the rank-1 update of the panel's later columns
-            double2 rnew[K4_NB];
+            beta = qf_rcp(nrm * (ar + nrm));
+            const bool later = c > jj && in_panel;
+            const int ri = k4_ridx(o_R, RW, j, j0 + (later ? c : jj + 1));
+            const double2 old = S2[ri];
+            __syncwarp();                                    // tail visible; diag[j] and row j read by all
+            if (lane == 0) S1[o_diag + j] = -copysign(nrm, r);
+            // b_jj^H x over this lane's rows, four independent chains
+            const int bbase = sm.o_tile + j * K4_S + q;
+            // (sixteen independent accumulators: a lone warp must cover the DFMA latency by itself)
+            double2 b[16];
+            double s_xx[4] = {0.0, 0.0, 0.0, 0.0}, s_yy[4] = {0.0, 0.0, 0.0, 0.0};
+            double s_xy[4] = {0.0, 0.0, 0.0, 0.0}, s_yx[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-            for (int kk = jj + 1; kk < K4_NB; ++kk) {
-                if (kk < w) {
-                    const double2 old = S2[k4_ridx(o_R, RW, j, j0 + kk)];
-                    const double2 pv = make_double2(fma(v0, old.x, val[1 + 2 * (kk - 1)]) * beta,
-                                                    fma(v0, old.y, val[2 + 2 * (kk - 1)]) * beta);
-                    rnew[kk] = make_double2(fma(-v0, pv.x, old.x), fma(-v0, pv.y, old.y));
+            for (int a = 0; a < 16; ++a) {
+                b[a] = S2[bbase + 4 * a];
+                s_xx[a & 3] = fma(b[a].x, x[a].x, s_xx[a & 3]);
+                s_yy[a & 3] = fma(b[a].y, x[a].y, s_yy[a & 3]);
+                s_xy[a & 3] = fma(b[a].x, x[a].y, s_xy[a & 3]);
+                s_yx[a & 3] = fma(b[a].y, x[a].x, s_yx[a & 3]);
+            }
+            const double dr = k4_sum4(((s_xx[0] + s_yy[0]) + (s_xx[1] + s_yy[1])) + ((s_xx[2] + s_yy[2]) + (s_xx[3] + s_yy[3])));
+            const double di = k4_sum4(((s_xy[0] - s_yx[0]) + (s_xy[1] - s_yx[1])) + ((s_xy[2] - s_yx[2]) + (s_xy[3] - s_yx[3])));
+            if (later) {
+                const double pr = fma(v0, old.x, dr) * beta, pi = fma(v0, old.y, di) * beta;
+                if (q == 0) S2[ri] = make_double2(fma(-v0, pr, old.x), fma(-v0, pi, old.y));
+                double pn[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-                    for (int a = 0; a < 2; ++a) {
-                        double bx = X[a][kk].x, by = X[a][kk].y;
-                        bx = fma(-pv.x, X[a][jj].x, bx);
-                        by = fma(-pv.x, X[a][jj].y, by);
-                        bx = fma(pv.y, X[a][jj].y, bx);
-                        by = fma(-pv.y, X[a][jj].x, by);
-                        X[a][kk] = make_double2(bx, by);
-                    }
+                for (int a = 0; a < 16; ++a) {
+                    double bx = x[a].x, by = x[a].y;
+                    bx = fma(-pr, b[a].x, bx);
+                    by = fma(-pr, b[a].y, by);
+                    bx = fma(pi, b[a].y, bx);
+                    by = fma(-pi, b[a].x, by);
+                    x[a] = make_double2(bx, by);
+                    pn[a & 3] = fma(bx, bx, pn[a & 3]);
+                    pn[4 + (a & 3)] = fma(by, by, pn[4 + (a & 3)]);
                 }
+                part = ((pn[0] + pn[4]) + (pn[1] + pn[5])) + ((pn[2] + pn[6]) + (pn[3] + pn[7]));
+            } else if (c < jj && q == 0) {
+                S2[sm.o_gbuf + c * 8 + jj] = make_double2(dr, -di);      // g_c,jj = b_c^H b_jj
             }
-            __syncwarp();                                    // every lane has read row j of the factor
-            if (lane == 0) {
-                S1[o_diag + j] = -copysign(nrm, r);
+            __syncwarp();                                    // Gram column jj complete
+            // column jj of T, row `lane` (lanes 0..7)
+            double2 acc = make_double2(0.0, 0.0);
 #pragma unroll
-                for (int kk = jj + 1; kk < K4_NB; ++kk)
-                    if (kk < w) S2[k4_ridx(o_R, RW, j, j0 + kk)] = rnew[kk];
+            for (int l = 0; l < jj; ++l) {
+                const double2 g = S2[sm.o_gbuf + l * 8 + jj];
+                acc.x = fma(Ti[l].x, g.x, acc.x); acc.x = fma(-Ti[l].y, g.y, acc.x);
+                acc.y = fma(Ti[l].x, g.y, acc.y); acc.y = fma(Ti[l].y, g.x, acc.y);
             }
+            Ti[jj] = jj == lane ? make_double2(beta, 0.0) : jj > lane ? make_double2(-beta * acc.x, -beta * acc.y) : Ti[jj];
         }
-        if (lane == 0) S1[sm.o_v0 + jj] = v0;
+        if (lane == 0) S1[sm.o_v0 + buf * 8 + jj] = v0;
     }
-    // the reflector tails become the V_b of the update; T (zero below the diagonal and in the
-    // rows / columns of absent reflections)
+    if (lane < K4_NB) {
 #pragma unroll
-    for (int kk = 0; kk < K4_NB; ++kk) {
-        if (kk < w) {
-            const int col = sm.o_tile + (j0 + kk) * K4_S;
-            S2[col + lane] = X[0][kk];
-            S2[col + lane + 32] = X[1][kk];
-        }
-    }
-    if (lane < 8) {
-#pragma unroll
-        for (int j = 0; j < K4_NB; ++j) S2[sm.o_Tm + i * 8 + j] = Ti[j];
+        for (int jc = 0; jc < K4_NB; ++jc) S2[sm.o_Tm + buf * 64 + lane * 8 + jc] = Ti[jc];
     }
 }
 
@@ -266,7 +273,7 @@ __device__ __forceinline__ void k4_panel(const PanelSmem &sm, const int o_R, con
 __device__ __forceinline__ void k4_update_chunk(const PanelSmem &sm, const int o_R, const int RW, const int j0,
                                                 const int w, const int first, const int c0, const int ncols,
                                                 const double (&Vr)[16], const double (&Vi)[16], const int o_xw,
-                                                const int lane)
+                                                const int lane, const int buf)
 {
     double2 *const S2 = k4_shared();
     double *const S1 = (double *)S2;
@@ -274,7 +281,7 @@ __device__ __forceinline__ void k4_update_chunk(const PanelSmem &sm, const int o
     const int col0 = c0 + 2 * t, col1 = col0 + 1;
     const bool ok0 = col0 < ncols, ok1 = col1 < ncols;
     const bool row_ok = g < w && g >= first;                  // reflector g exists
-    const double v0g = S1[sm.o_v0 + g];                        // zero for absent reflectors
+    const double v0g = S1[sm.o_v0 + buf * 8 + g];              // zero for absent reflectors
     const int r0i = k4_ridx(o_R, RW, j0 + (row_ok ? g : 0), ok0 ? col0 : c0);
     const int r1i = k4_ridx(o_R, RW, j0 + (row_ok ? g : 0), ok1 ? col1 : c0);
     // ---- X = diag(v0) R_panel,chunk + V_b^H B_chunk
@@ -310,7 +317,7 @@ __device__ __forceinline__ void k4_update_chunk(const PanelSmem &sm, const int o
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
         const double2 xb = S2[o_xw + (4 * s + t) * K4_XS + g];     // X[4 s + t][g]
-        const double2 tt = S2[sm.o_Tm + (4 * s + t) * 8 + g];      // T^H[g][4 s + t] = conj(T[4 s + t][g])
+        const double2 tt = S2[sm.o_Tm + buf * 64 + (4 * s + t) * 8 + g];   // T^H[g][4 s + t] = conj(T[4 s + t][g])
         // W += conj(T)^T X:  Wr += Tr Xr + Ti Xi,  Wi += Tr Xi - Ti Xr
         k4_dmma(wr0, wr1, tt.x, xb.x);
         k4_dmma(wi0, wi1, tt.x, xb.y);
@@ -354,37 +361,73 @@ __device__ __forceinline__ void k4_update_chunk(const PanelSmem &sm, const int o
     }
 }
 
+// The A fragments of V_b^H for the 16 k-steps of the tile's 64 rows (thread (g, t): V_b[4 s + t][g]).
+__device__ __forceinline__ void k4_load_v(const PanelSmem &sm, const int j0, const int w, const int first,
+                                          const int lane, double (&Vr)[16], double (&Vi)[16])
+{
+    double2 *const S2 = k4_shared();
+    const int g = lane >> 2, t = lane & 3;
+    const bool live = g < w && g >= first;
+    const int vcol = sm.o_tile + (j0 + (live ? g : 0)) * K4_S + t;
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        const double2 v = S2[vcol + 4 * s];
+        Vr[s] = live ? v.x : 0.0;
+        Vi[s] = live ? v.y : 0.0;
+    }
+}
+
 // All reflections jstart..N-1 of [R; tile] (tile: K4_M rows x ncols columns; factor at o_R with
-// RW columns right of column 0, diagonal at o_diag).  `warp` must be warp-uniform for the
-// compiler (see the kernel), or every shuffle of the panel is wrapped in a convergence check.
+// RW columns right of column 0, diagonal at o_diag), software-pipelined over the panels: while
+// the other warps apply panel p to the trailing chunks, the panel warp applies it to the chunk
+// that holds panel p + 1 and factors that panel right away (T / v0 double-buffered), so the
+// latency-bound panel chain and the tensor-core update of one fit overlap; one CTA barrier per
+// panel.  The panel warp rotates with the panel index (and the CTA), so that the two
+// co-resident fits do not queue their panels on the same scheduler.  `warp` must be
+// warp-uniform for the compiler (see the kernel).
 __device__ __forceinline__ void k4_factor_tile(const PanelSmem &sm, const int o_R, const int RW, const int o_diag,
                                                const int ncols, const int N, const int jstart, const int lane,
                                                const int warp)
 {
-    double2 *const S2 = k4_shared();
+    const int pfirst = jstart / K4_NB, plast = (N + K4_NB - 1) / K4_NB - 1;
+    // the two CTAs of an SM sit in warp slots 0-3 and 4-7 (scheduler = slot % 4): offset their
+    // panel warps by two so that both panels never queue on one scheduler
+    unsigned slot0;
+    asm("mov.u32 %0, %%warpid;" : "=r"(slot0));
+    const int rot = 2 * (int)((__shfl_sync(0xffffffffu, slot0, 0) >> 2) & 1);
+    if (warp == ((pfirst + rot) & (K4_WARPS - 1)))
+        k4_panel(sm, o_R, RW, o_diag, pfirst * K4_NB, N - pfirst * K4_NB < K4_NB ? N - pfirst * K4_NB : K4_NB,
+                 jstart - pfirst * K4_NB, lane, pfirst & 1);
+    __syncthreads();
 #pragma unroll 1
-    for (int j0 = (jstart / K4_NB) * K4_NB; j0 < N; j0 += K4_NB) {
+    for (int pi = pfirst; pi <= plast; ++pi) {
+        const int j0 = pi * K4_NB;
         const int w = N - j0 < K4_NB ? N - j0 : K4_NB;
         const int first = jstart > j0 ? jstart - j0 : 0;
-        if (warp == 0) k4_panel(sm, o_R, RW, o_diag, j0, w, first, lane);
-        __syncthreads();
         const int cbeg = j0 + w;
         const int nchunks = (ncols - cbeg + 7) / 8;
-        if (warp < nchunks) {
-            double Vr[16], Vi[16];
-            {
-                const int g = lane >> 2, t = lane & 3;
-                const bool live = g < w && g >= first;
-                const int vcol = sm.o_tile + (j0 + (live ? g : 0)) * K4_S + t;
-#pragma unroll
-                for (int s = 0; s < 16; ++s) {
-                    const double2 v = S2[vcol + 4 * s];
-                    Vr[s] = live ? v.x : 0.0;
-                    Vi[s] = live ? v.y : 0.0;
-                }
+        const int buf = pi & 1;
+        const int xw = sm.o_xw + warp * 8 * K4_XS;
+        double Vr[16], Vi[16];
+        if (pi < plast) {
+            // chunk 0 = the columns of panel pi + 1: its warp applies panel pi to them, then factors them
+            const int pw = (pi + 1 + rot) & (K4_WARPS - 1);
+            const int slot = (warp - pw - 1) & (K4_WARPS - 1);      // 0..2 for the other warps, 3 for the panel warp
+            if (warp == pw) {
+                k4_load_v(sm, j0, w, first, lane, Vr, Vi);
+                k4_update_chunk(sm, o_R, RW, j0, w, first, cbeg, ncols, Vr, Vi, xw, lane, buf);
+                __syncwarp();
+                const int j1 = j0 + K4_NB;
+                k4_panel(sm, o_R, RW, o_diag, j1, N - j1 < K4_NB ? N - j1 : K4_NB, 0, lane, buf ^ 1);
+            } else if (1 + slot < nchunks) {
+                k4_load_v(sm, j0, w, first, lane, Vr, Vi);
+                for (int ch = 1 + slot; ch < nchunks; ch += K4_WARPS - 1)
+                    k4_update_chunk(sm, o_R, RW, j0, w, first, cbeg + 8 * ch, ncols, Vr, Vi, xw, lane, buf);
             }
+        } else if (warp < nchunks) {                                 // last panel: every warp takes chunks
+            k4_load_v(sm, j0, w, first, lane, Vr, Vi);
             for (int ch = warp; ch < nchunks; ch += K4_WARPS)
-                k4_update_chunk(sm, o_R, RW, j0, w, first, cbeg + 8 * ch, ncols, Vr, Vi, sm.o_xw + warp * 8 * K4_XS, lane);
+                k4_update_chunk(sm, o_R, RW, j0, w, first, cbeg + 8 * ch, ncols, Vr, Vi, xw, lane, buf);
         }
         __syncthreads();
     }

@@ -57,7 +57,7 @@ for case in range(n_cases):
     method = 'geq' if rng.random() < 0.7 else 'closest'
     T = float(rng.uniform(20, 110))
     delta = 0.0 if rng.random() < 0.6 else list(rng.uniform(-0.02, 0.02, size=len(modes)))
-    kind = rng.integers(0, 7)
+    kind = rng.integers(0, 8)
     try:
         if kind == 0:
             t0 = float(rng.uniform(-5, 40))
@@ -104,6 +104,17 @@ for case in range(n_cases):
             got = qf.dynamic_multimode_ringdown_fit(times, dd, lin, Mf_t, chi_t, t0, method, T, sph)
             want = orc.dynamic_multimode_ringdown_fit(tables, times, dd, lin, Mf_t, chi_t, t0, method, T, sph)
             dmm = abs(got['mismatch'] - want['mismatch'])
+            extra = {}
+        elif kind == 7:                                   # multimode sweep with quadratic labels (coef_columns)
+            sph = [(2, 2), (3, 2), (4, 4), (4, 2)]
+            mm_modes = ([m for m in modes if len(m) == 4][:7] or [(2, 2, 0, 1)]) + list(workloads.QUADRATIC_LABELS[:2])
+            dd = {lm: data * (0.4 ** i) * np.exp(0.3j * i) for i, lm in enumerate(sph)}
+            t0s = np.sort(rng.uniform(0, 40, size=9))
+            got = np.array(qf.mismatch_t0_array(times, dd, mm_modes, Mf, chif, t0s, method, T, sph,
+                                                coef_columns=workloads.quadratic_columns(sph)))
+            want = np.array(orc.mismatch_t0_array(tables, times, dd, mm_modes, Mf, chif, t0s, method, T, sph,
+                                                  coef_override=workloads.coef_override(sph, mm_modes, chif, tables)))
+            dmm = float(np.max(np.abs(got - want)))
             extra = {}
         else:
             sph = [(2, 2), (3, 2), (4, 2)]

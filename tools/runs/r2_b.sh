@@ -7,5 +7,5 @@ timeout 900 python -m pytest tests -m gpu -x -q -k "multimode or struct or confi
 tail -25 gpurun_out/r2_tests_b.log
 timeout 300 python tools/k3_time.py 10 > gpurun_out/r2_k4_time.log 2>&1; tail -5 gpurun_out/r2_k4_time.log
 K3_FITS=296 timeout 600 ncu --set full --import-source on --clock-control none -k regex:fit_panel -c 1 \
-   -o gpurun_out/prof_k4_r02_v2 -f python tools/k3_time.py 1 > gpurun_out/r2_ncu_k4.log 2>&1
+   -o gpurun_out/prof_k4_r02_v4 -f python tools/k3_time.py 1 > gpurun_out/r2_ncu_k4.log 2>&1
 tail -3 gpurun_out/r2_ncu_k4.log

@@ -4,7 +4,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 for tool in memcheck racecheck synccheck; do
-  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_target.py \
+  timeout 420 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_target.py \
     > gpurun_out/sanitizer_$tool.log 2>&1
   echo "$tool exit $?" >> gpurun_out/sanitizer_$tool.log
   tail -4 gpurun_out/sanitizer_$tool.log
