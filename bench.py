@@ -348,13 +348,18 @@ def run_gpu_arm(args):
     hbm_peak = json.load(open(peaks_file)).get("hbm_gbs") if os.path.isfile(peaks_file) else 6650.0
     # algorithmic HBM bytes per launch: window (times + data) + tables + 8 B/fit mismatch
     alg_bytes = rows * 24 + RES * len(wl.modes) * 16 + RES * 8 + fits_per_launch * (8 + 4)
-    traffic = None
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel per launch: NOT measured in
+    # this run (a number taken under a profiler is not a bench value) — read from the committed
+    # summary of the round's `ncu --set full` capture of the same command, and labelled so
+    traffic = traffic_source = None
     prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
     if os.path.isfile(prof):
-        traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        summary = json.load(open(prof))
+        traffic = summary.get("dram_bytes_per_launch")
+        traffic_source = "profiles/ncu_summary.json: " + str(summary.get("source", "ncu --set full capture"))
     roofline = {
         "bound": "fp64", "achieved": achieved, "peak": peak_dfma, "unit": "TFLOP/s",
-        "frac": achieved / peak_dfma, "traffic": traffic,
+        "frac": achieved / peak_dfma, "traffic": traffic, "traffic_source": traffic_source,
         "peak_source": "measured live: best of three dependent-free DFMA loops on all SMs "
                        "(qnmfit_fp64_peak); MEASURED_PEAKS.json has no FP64 entry; nominal "
                        "148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2 TFLOP/s",
