@@ -314,7 +314,10 @@ int qnmfit_plan_batch(qnmfit_ctx *ctx, const qnmfit_batch *b, qnmfit_plan *plan)
 /* FP64 peak micro-benchmarks on the ctx's device.  kind 0 = DFMA, operands mostly from
  * the reuse cache (vector pipe peak); 1 = DMMA m8n8k4 (tensor pipe); 2 = DFMA with three
  * distinct register operands per instruction (register-file read bound); 3 = DFMA with
- * two register reads + one reused operand.  Writes TFLOP/s (2 flops per FMA). */
+ * two register reads + one reused operand; 4 = DFMA and DMMA interleaved in one warp.
+ * Writes TFLOP/s (2 flops per FMA).  Kinds 20 + n / 30 + n (n = 1, 2, 4, 8) are latency
+ * probes instead: ONE warp issuing DMMA / DFMA on n independent accumulators; they write
+ * the measured CYCLES per instruction. */
 int qnmfit_fp64_peak(qnmfit_ctx *ctx, int kind, int iters, double *tflops);
 
 /* Algorithmic FP64 flops credited to one fit (DESIGN.md "flop accounting"), with

@@ -131,6 +131,36 @@ __device__ __forceinline__ double2 k4_cmul(const double2 a, const double2 b)
     return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));
 }
 
+#ifdef K4_TRACE
+// developer build (tools/build_variant.sh k4trace -DK4_TRACE): per-warp clock stamps of CTA 0's
+// pipeline, read back with qnmfit_debug_trace (tools/k4_trace.py)
+__device__ long long k4_trace_buf[8192];
+__device__ int k4_trace_n;
+#define K4_STAMP(tag)                                                                                     \
+    do {                                                                                                  \
+        if (blockIdx.x == 0 && lane == 0) {                                                               \
+            const int slot_ = atomicAdd(&k4_trace_n, 1);                                                  \
+            if (slot_ < 2048) { k4_trace_buf[4 * slot_] = clock64(); k4_trace_buf[4 * slot_ + 1] = warp;  \
+                                k4_trace_buf[4 * slot_ + 2] = (tag); k4_trace_buf[4 * slot_ + 3] = pi; }   \
+        }                                                                                                 \
+    } while (0)
+#ifndef K4_TRACE_PANEL
+#define K4_PSTAMP(tag, jj) do { } while (0)
+#else
+#define K4_PSTAMP(tag, jj)                                                                                \
+    do {                                                                                                  \
+        if (blockIdx.x == 0 && lane == 0) {                                                               \
+            const int slot_ = atomicAdd(&k4_trace_n, 1);                                                  \
+            if (slot_ < 2048) { k4_trace_buf[4 * slot_] = clock64(); k4_trace_buf[4 * slot_ + 1] = 100;   \
+                                k4_trace_buf[4 * slot_ + 2] = (tag); k4_trace_buf[4 * slot_ + 3] = (jj); } \
+        }                                                                                                 \
+    } while (0)
+#endif
+#else
+#define K4_STAMP(tag) do { } while (0)
+#define K4_PSTAMP(tag, jj) do { } while (0)
+#endif
+
 // sum over the 4 lanes that share a panel column (every lane of the warp must call it)
 __device__ __forceinline__ double k4_sum4(double v)
 {
@@ -181,38 +211,34 @@ __device__ __forceinline__ void k4_panel(const PanelSmem &sm, const int o_R, con
         part0 = fma(x[a].y, x[a].y, part0);         part1 = fma(x[a + 1].y, x[a + 1].y, part1);
     }
     double part = part0 + part1;
+    double betas[K4_NB];                          // beta of the panel's reflections (0: absent)
+#pragma unroll
+    for (int kk = 0; kk < K4_NB; ++kk) betas[kk] = 0.0;
     S2[sm.o_gbuf + lane] = make_double2(0.0, 0.0);
     S2[sm.o_gbuf + lane + 32] = make_double2(0.0, 0.0);
-    double2 Ti[K4_NB];                            // lanes 0..7: row `lane` of T
-#pragma unroll
-    for (int kk = 0; kk < K4_NB; ++kk) Ti[kk] = make_double2(0.0, 0.0);
     __syncwarp();
 
 #pragma unroll
     for (int jj = 0; jj < K4_NB; ++jj) {
-        double v0 = 0.0, beta = 0.0;
+        double v0 = 0.0;
         if (jj >= first && jj < w) {             // warp-uniform
             const int j = j0 + jj;
+            // One barrier per reflection (the tail must be in the tile before it is read); everything
+            // behind it is ONE basic block, so that the scalar chain (rsqrt, rcp: ~130 cycles of
+            // dependent operations), the dot products and the update interleave — a lone in-order
+            // warp stalls on every chain the compiler cannot overlap.
             const double tot = __shfl_sync(0xffffffffu, k4_sum4(part), 4 * jj);     // |b_jj|^2
             if (c == jj) {
 #pragma unroll
                 for (int a = 0; a < 16; ++a) S2[colbase + 4 * a] = x[a];             // the final tail b_jj
             }
-            const double r = S1[o_diag + j];
-            const double t = fma(r, r, tot) + 1e-300;        // fit_small.cuh: an all-zero column needs no branch
-            const double y = qf_rsqrt(t);
-            const double nrm = t * y;
-            const double ar = fabs(r);
-            v0 = copysign(ar + nrm, r);
-            beta = qf_rcp(nrm * (ar + nrm));
             const bool later = c > jj && in_panel;
             const int ri = k4_ridx(o_R, RW, j, j0 + (later ? c : jj + 1));
+            const double r = S1[o_diag + j];
             const double2 old = S2[ri];
-            __syncwarp();                                    // tail visible; diag[j] and row j read by all
-            if (lane == 0) S1[o_diag + j] = -copysign(nrm, r);
-            // b_jj^H x over this lane's rows, four independent chains
+            __syncwarp();
+            // b_jj^H x over this lane's rows (sixteen independent accumulators)
             const int bbase = sm.o_tile + j * K4_S + q;
-            // (sixteen independent accumulators: a lone warp must cover the DFMA latency by itself)
             double2 b[16];
             double s_xx[4] = {0.0, 0.0, 0.0, 0.0}, s_yy[4] = {0.0, 0.0, 0.0, 0.0};
             double s_xy[4] = {0.0, 0.0, 0.0, 0.0}, s_yx[4] = {0.0, 0.0, 0.0, 0.0};
@@ -224,10 +250,20 @@ __device__ __forceinline__ void k4_panel(const PanelSmem &sm, const int o_R, con
                 s_xy[a & 3] = fma(b[a].x, x[a].y, s_xy[a & 3]);
                 s_yx[a & 3] = fma(b[a].y, x[a].x, s_yx[a & 3]);
             }
+            // reflector scalars (every lane the same)
+            const double t = fma(r, r, tot) + 1e-300;        // fit_small.cuh: an all-zero column needs no branch
+            const double y = qf_rsqrt(t);
+            const double nrm = t * y;
+            const double ar = fabs(r);
+            v0 = copysign(ar + nrm, r);
+            const double beta = qf_rcp(nrm * (ar + nrm));
             const double dr = k4_sum4(((s_xx[0] + s_yy[0]) + (s_xx[1] + s_yy[1])) + ((s_xx[2] + s_yy[2]) + (s_xx[3] + s_yy[3])));
             const double di = k4_sum4(((s_xy[0] - s_yx[0]) + (s_xy[1] - s_yx[1])) + ((s_xy[2] - s_yx[2]) + (s_xy[3] - s_yx[3])));
+            betas[jj] = beta;
+            if (c < jj && q == 0) S2[sm.o_gbuf + c * 8 + jj] = make_double2(dr, -di);     // g_c,jj = b_c^H b_jj
+            // the panel's row of R and the rank-1 update of the later columns
+            const double pr = fma(v0, old.x, dr) * beta, pi = fma(v0, old.y, di) * beta;
             if (later) {
-                const double pr = fma(v0, old.x, dr) * beta, pi = fma(v0, old.y, di) * beta;
                 if (q == 0) S2[ri] = make_double2(fma(-v0, pr, old.x), fma(-v0, pi, old.y));
                 double pn[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
@@ -242,25 +278,36 @@ __device__ __forceinline__ void k4_panel(const PanelSmem &sm, const int o_R, con
                     pn[4 + (a & 3)] = fma(by, by, pn[4 + (a & 3)]);
                 }
                 part = ((pn[0] + pn[4]) + (pn[1] + pn[5])) + ((pn[2] + pn[6]) + (pn[3] + pn[7]));
-            } else if (c < jj && q == 0) {
-                S2[sm.o_gbuf + c * 8 + jj] = make_double2(dr, -di);      // g_c,jj = b_c^H b_jj
             }
-            __syncwarp();                                    // Gram column jj complete
-            // column jj of T, row `lane` (lanes 0..7)
-            double2 acc = make_double2(0.0, 0.0);
-#pragma unroll
-            for (int l = 0; l < jj; ++l) {
-                const double2 g = S2[sm.o_gbuf + l * 8 + jj];
-                acc.x = fma(Ti[l].x, g.x, acc.x); acc.x = fma(-Ti[l].y, g.y, acc.x);
-                acc.y = fma(Ti[l].x, g.y, acc.y); acc.y = fma(Ti[l].y, g.x, acc.y);
-            }
-            Ti[jj] = jj == lane ? make_double2(beta, 0.0) : jj > lane ? make_double2(-beta * acc.x, -beta * acc.y) : Ti[jj];
+            if (lane == 0) S1[o_diag + j] = -copysign(nrm, r);
         }
         if (lane == 0) S1[sm.o_v0 + buf * 8 + jj] = v0;
     }
-    if (lane < K4_NB) {
+    // the tails are in the tile (the V_b of the update).  T from the Gram of the tails (strict
+    // upper part in gbuf), column j by back-substitution on e_j — every column independent of the
+    // others, lane j (< 8) builds column j in registers, all lanes run the same predicated code:
+    //   T_jj = beta_j,   T_ij = -beta_i sum_{l = i+1..j} g_il T_lj   (i = j-1 .. 0)
+    // (columns of absent reflections come out zero: beta = 0).
+    __syncwarp();
+    {
+        const int jc = lane & 7;
+        double2 Tc[K4_NB];
 #pragma unroll
-        for (int jc = 0; jc < K4_NB; ++jc) S2[sm.o_Tm + buf * 64 + lane * 8 + jc] = Ti[jc];
+        for (int i = K4_NB - 1; i >= 0; --i) {
+            double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int l = i + 1; l < K4_NB; ++l) {
+                const double2 g = S2[sm.o_gbuf + i * 8 + l];
+                acc.x = fma(g.x, Tc[l].x, acc.x); acc.x = fma(-g.y, Tc[l].y, acc.x);
+                acc.y = fma(g.x, Tc[l].y, acc.y); acc.y = fma(g.y, Tc[l].x, acc.y);
+            }
+            const double bi = betas[i];
+            Tc[i] = i > jc ? make_double2(0.0, 0.0) : i == jc ? make_double2(bi, 0.0) : make_double2(-bi * acc.x, -bi * acc.y);
+        }
+        if (lane < K4_NB) {
+#pragma unroll
+            for (int i = 0; i < K4_NB; ++i) S2[sm.o_Tm + buf * 64 + i * 8 + jc] = Tc[i];
+        }
     }
 }
 
@@ -273,7 +320,8 @@ __device__ __forceinline__ void k4_panel(const PanelSmem &sm, const int o_R, con
 __device__ __forceinline__ void k4_update_chunk(const PanelSmem &sm, const int o_R, const int RW, const int j0,
                                                 const int w, const int first, const int c0, const int ncols,
                                                 const double (&Vr)[16], const double (&Vi)[16], const int o_xw,
-                                                const int lane, const int buf)
+                                                const int lane, const int buf, const int r_begin = 0,
+                                                const int r_end = K4_M / 8, const bool write_R = true)
 {
     double2 *const S2 = k4_shared();
     double *const S1 = (double *)S2;
@@ -324,8 +372,8 @@ __device__ __forceinline__ void k4_update_chunk(const PanelSmem &sm, const int o
         k4_dmma(wr0, wr1, tt.y, xb.y);
         k4_dmma(wi0, wi1, tt.y, -xb.x);
     }
-    // ---- the panel's rows of R
-    if (row_ok) {
+    // ---- the panel's rows of R (one warp only when several share the chunk by row tiles)
+    if (row_ok && write_R) {
         if (ok0) { const double2 r = S2[r0i]; S2[r0i] = make_double2(fma(-v0g, wr0, r.x), fma(-v0g, wi0, r.y)); }
         if (ok1) { const double2 r = S2[r1i]; S2[r1i] = make_double2(fma(-v0g, wr1, r.x), fma(-v0g, wi1, r.y)); }
     }
@@ -342,6 +390,7 @@ __device__ __forceinline__ void k4_update_chunk(const PanelSmem &sm, const int o
     const int ccol1 = sm.o_tile + (ok1 ? col1 : c0) * K4_S + g;
 #pragma unroll
     for (int r = 0; r < K4_M / 8; ++r) {
+        if (r < r_begin || r >= r_end) continue;
         double2 a0 = S2[vcol0 + 8 * r], a1 = S2[vcol1 + 8 * r];
         if (!va0) a0 = make_double2(0.0, 0.0);
         if (!va1) a1 = make_double2(0.0, 0.0);
@@ -381,7 +430,7 @@ __device__ __forceinline__ void k4_load_v(const PanelSmem &sm, const int j0, con
 // RW columns right of column 0, diagonal at o_diag), software-pipelined over the panels: while
 // the other warps apply panel p to the trailing chunks, the panel warp applies it to the chunk
 // that holds panel p + 1 and factors that panel right away (T / v0 double-buffered), so the
-// latency-bound panel chain and the tensor-core update of one fit overlap; one CTA barrier per
+// latency-bound panel chain and the tensor-core update of one fit overlap; two CTA barriers per
 // panel.  The panel warp rotates with the panel index (and the CTA), so that the two
 // co-resident fits do not queue their panels on the same scheduler.  `warp` must be
 // warp-uniform for the compiler (see the kernel).
@@ -410,26 +459,37 @@ __device__ __forceinline__ void k4_factor_tile(const PanelSmem &sm, const int o_
         const int xw = sm.o_xw + warp * 8 * K4_XS;
         double Vr[16], Vi[16];
         if (pi < plast) {
-            // chunk 0 = the columns of panel pi + 1: its warp applies panel pi to them, then factors them
+            // chunk 0 = the columns of panel pi + 1, which its warp factors next: it is on the fit's
+            // critical chain, so ALL warps apply panel pi to it — each forms X and W for the chunk
+            // (the same 72 DMMA, in parallel on the four schedulers) and updates two of its eight
+            // row tiles; the panel warp also stores the chunk's rows of R
             const int pw = (pi + 1 + rot) & (K4_WARPS - 1);
             const int slot = (warp - pw - 1) & (K4_WARPS - 1);      // 0..2 for the other warps, 3 for the panel warp
+            K4_STAMP(0);
+            k4_load_v(sm, j0, w, first, lane, Vr, Vi);
+            K4_STAMP(1);
+            k4_update_chunk(sm, o_R, RW, j0, w, first, cbeg, ncols, Vr, Vi, xw, lane, buf, 2 * warp, 2 * warp + 2, warp == pw);
+            K4_STAMP(2);
+            __syncthreads();
+            K4_STAMP(3);
             if (warp == pw) {
-                k4_load_v(sm, j0, w, first, lane, Vr, Vi);
-                k4_update_chunk(sm, o_R, RW, j0, w, first, cbeg, ncols, Vr, Vi, xw, lane, buf);
-                __syncwarp();
                 const int j1 = j0 + K4_NB;
                 k4_panel(sm, o_R, RW, o_diag, j1, N - j1 < K4_NB ? N - j1 : K4_NB, 0, lane, buf ^ 1);
-            } else if (1 + slot < nchunks) {
-                k4_load_v(sm, j0, w, first, lane, Vr, Vi);
+                K4_STAMP(4);
+            } else {
                 for (int ch = 1 + slot; ch < nchunks; ch += K4_WARPS - 1)
                     k4_update_chunk(sm, o_R, RW, j0, w, first, cbeg + 8 * ch, ncols, Vr, Vi, xw, lane, buf);
+                K4_STAMP(5);
             }
         } else if (warp < nchunks) {                                 // last panel: every warp takes chunks
+            K4_STAMP(6);
             k4_load_v(sm, j0, w, first, lane, Vr, Vi);
             for (int ch = warp; ch < nchunks; ch += K4_WARPS)
                 k4_update_chunk(sm, o_R, RW, j0, w, first, cbeg + 8 * ch, ncols, Vr, Vi, xw, lane, buf);
+            K4_STAMP(7);
         }
         __syncthreads();
+        K4_STAMP(8);
     }
 }
 

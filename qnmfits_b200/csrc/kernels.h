@@ -49,3 +49,4 @@ cudaError_t k4_launch(int grid, size_t smem, cudaStream_t st, const FitParams &p
 // ---- multi-GPU epoch barrier (qnmfit_common.cuh) and the FP64 peak micro-benchmarks ------
 cudaError_t peer_barrier_launch(cudaStream_t st, const FitParams &p);
 cudaError_t fp64_peak_launch(int kind, int grid, int block, double *out, int iters);
+cudaError_t fp64_latency_launch(int kind, double *out, int iters);   // kinds 20+n / 30+n: cycles per DMMA / DFMA, n chains, one warp

@@ -118,6 +118,71 @@ __global__ void __launch_bounds__(256) dfma_dmma_mix_kernel(double *out, int ite
         ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)) + ((c00 + c01) + (c10 + c11));
 }
 
+// kinds 20 + n (n = 1, 2, 4, 8): latency probe — ONE warp issuing DMMAs on n independent accumulators;
+// out[0] = cycles per DMMA.  kinds 30 + n: the same for DFMA.
+template <int CHAINS, bool MMA>
+__global__ void __launch_bounds__(32) fp64_latency_kernel(double *out, int iters, double b, double c)
+{
+    double a = threadIdx.x * 1e-3 + 0.5, bb = b;
+    double acc[CHAINS][2];
+#pragma unroll
+    for (int k = 0; k < CHAINS; ++k) { acc[k][0] = c + k; acc[k][1] = c - k; }
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int k = 0; k < CHAINS; ++k) {
+                if (MMA)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(acc[k][0]), "+d"(acc[k][1]) : "d"(a), "d"(bb));
+                else
+                    asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(acc[k][0]) : "d"(a), "d"(bb));
+            }
+        }
+    }
+    const long long t1 = clock64();
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < CHAINS; ++k) sum += acc[k][0] + acc[k][1];
+    if (threadIdx.x == 0) { out[0] = (double)(t1 - t0) / ((double)iters * 8.0 * CHAINS); out[1] = sum; }
+}
+
+// kind 40: dependent chain  x <- rcp(rsqrt(x) + c)  (the reflector scalars of the fit kernels);
+// kind 41: dependent chain  x <- x + shfl_xor(x, 1)  (one level of a warp reduction);
+// kind 42: dependent chain through shared memory  x <- lds(sts(x))  with __syncwarp.
+__global__ void __launch_bounds__(32) misc_latency_kernel(double *out, int iters, int kind, double c)
+{
+    __shared__ double buf[32];
+    double x = 1.0 + threadIdx.x * 1e-3;
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (kind == 40) x = qf_rcp(qf_rsqrt(x) + c);
+            else if (kind == 41) x = x + __shfl_xor_sync(0xffffffffu, x, 1);
+            else { buf[threadIdx.x] = x; __syncwarp(); x = buf[threadIdx.x ^ 1] * c; __syncwarp(); }
+        }
+    }
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) { out[0] = (double)(t1 - t0) / ((double)iters * 8.0); out[1] = x; }
+}
+
+cudaError_t fp64_latency_launch(int kind, double *out, int iters)
+{
+    if (kind >= 40) {
+        misc_latency_kernel<<<1, 32>>>(out, iters, kind, 1.0 + 1e-9);
+        return cudaGetLastError();
+    }
+    const bool mma = kind < 30;
+    const int n = mma ? kind - 20 : kind - 30;
+#define QF_LAT(N) if (n == N) { if (mma) fp64_latency_kernel<N, true><<<1, 32>>>(out, iters, 0.999999, 1e-9); \
+                                else fp64_latency_kernel<N, false><<<1, 32>>>(out, iters, 0.999999, 1e-9); }
+    QF_LAT(1) QF_LAT(2) QF_LAT(4) QF_LAT(8)
+#undef QF_LAT
+    return cudaGetLastError();
+}
+
 cudaError_t fp64_peak_launch(int kind, int grid, int block, double *out, int iters)
 {
     if (kind == 0) dfma_peak_kernel<<<grid, block>>>(out, iters, 0.999999, 1e-9);

@@ -268,6 +268,8 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
         if (best >= 1e300) return fail(ctx, QNMFIT_E_SHAPE, "K1: no lanes-per-fit choice fits shared memory");
     } else if (kernel == QNMFIT_KERNEL_PANEL) {
         pl->lpf = 1; pl->smem = k4_smem_bytes(b->n_modes, b->n_series);
+        { const char *pad = getenv("QNMFIT_K4_ONE_PER_SM");     // developer knob: one fit per SM (contention studies)
+          if (pad && pad[0] == '1' && pl->smem < (size_t)120 * 1024) pl->smem = (size_t)120 * 1024; }
         pl->grid = b->n_fits; pl->block = k4_threads();
     } else if (kernel == QNMFIT_KERNEL_STRUCT) {
         pl->lpf = ctx->k3_g; pl->TR = ctx->k3_g * ctx->k3_rpt;
@@ -632,6 +634,19 @@ extern "C" int qnmfit_fp64_peak(qnmfit_ctx *ctx, int kind, int iters, double *tf
     if (iters < 1) iters = 1;
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
+    if (kind >= 20) {   // latency probes: one warp, n independent chains; *tflops receives CYCLES per instruction
+        double *out = nullptr;
+        if ((e = cudaMalloc(&out, 2 * sizeof(double))) != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc");
+        double host[2] = {0.0, 0.0};
+        for (int rep = 0; rep < 2 && e == cudaSuccess; ++rep) {
+            e = fp64_latency_launch(kind, out, iters);
+            if (e == cudaSuccess) e = cudaMemcpy(host, out, sizeof(host), cudaMemcpyDeviceToHost);
+        }
+        cudaFree(out);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "fp64 latency probe");
+        *tflops = host[0];
+        return 0;
+    }
     // kinds >= 10: the same kernels at the occupancy of K1 (one 256-thread CTA per SM,
     // two warps per scheduler) to see what that occupancy can extract from the pipe
     const bool low_occ = kind >= 10;
