@@ -7,39 +7,56 @@
     const void *k1_kernel_ptr_part##P(int N, bool staged);                                           \
     cudaError_t k1_launch_part##P(int N, bool staged, int grid, int block, size_t smem, cudaStream_t st, \
                                   const FitParams &p);
-K1_DECL(0) K1_DECL(1) K1_DECL(2) K1_DECL(3)
+K1_DECL(0) K1_DECL(1) K1_DECL(2) K1_DECL(3) K1_DECL(4) K1_DECL(5)
 
 int k1_block_rows(int N) { return N <= 8 ? 4 : N <= QNMFIT_MB3_MAX_N ? 3 : 2; }   // SmallLayout<N>::MB
 static_assert(SmallLayout<8>::MB == 4 && SmallLayout<9>::MB == 3 && SmallLayout<12>::MB == (12 <= QNMFIT_MB3_MAX_N ? 3 : 2),
               "k1_block_rows must mirror SmallLayout<N>::MB");
 
-size_t k1_smem_bytes(int N, int fpc, int stage_rows)
+// part holding the (N, threads) instance; -1: none
+static int part_for(int N, int threads)
 {
-    switch (k1_part_of(N)) {
+    if (N < 1 || N > QNMFIT_MAX_MODES_SMALL) return -1;
+    if (threads == k1_threads(N)) return k1_part_of(N);
+    if (threads == k1_alt_threads(N)) return k1_alt_part_of(N);
+    return -1;
+}
+
+size_t k1_smem_bytes(int N, int threads, int fpc, int stage_rows)
+{
+    switch (part_for(N, threads)) {
     case 0: return k1_smem_bytes_part0(N, fpc, stage_rows);
     case 1: return k1_smem_bytes_part1(N, fpc, stage_rows);
     case 2: return k1_smem_bytes_part2(N, fpc, stage_rows);
-    default: return k1_smem_bytes_part3(N, fpc, stage_rows);
+    case 3: return k1_smem_bytes_part3(N, fpc, stage_rows);
+    case 4: return k1_smem_bytes_part4(N, fpc, stage_rows);
+    case 5: return k1_smem_bytes_part5(N, fpc, stage_rows);
     }
+    return (size_t)-1;
 }
 
-const void *k1_kernel_ptr(int N, bool staged)
+const void *k1_kernel_ptr(int N, int threads, bool staged)
 {
-    if (N < 1 || N > QNMFIT_MAX_MODES_SMALL) return nullptr;
-    switch (k1_part_of(N)) {
+    switch (part_for(N, threads)) {
     case 0: return k1_kernel_ptr_part0(N, staged);
     case 1: return k1_kernel_ptr_part1(N, staged);
     case 2: return k1_kernel_ptr_part2(N, staged);
-    default: return k1_kernel_ptr_part3(N, staged);
+    case 3: return k1_kernel_ptr_part3(N, staged);
+    case 4: return k1_kernel_ptr_part4(N, staged);
+    case 5: return k1_kernel_ptr_part5(N, staged);
     }
+    return nullptr;
 }
 
 cudaError_t k1_launch(int N, bool staged, int grid, int block, size_t smem, cudaStream_t st, const FitParams &p)
 {
-    switch (k1_part_of(N)) {
+    switch (part_for(N, block)) {
     case 0: return k1_launch_part0(N, staged, grid, block, smem, st, p);
     case 1: return k1_launch_part1(N, staged, grid, block, smem, st, p);
     case 2: return k1_launch_part2(N, staged, grid, block, smem, st, p);
-    default: return k1_launch_part3(N, staged, grid, block, smem, st, p);
+    case 3: return k1_launch_part3(N, staged, grid, block, smem, st, p);
+    case 4: return k1_launch_part4(N, staged, grid, block, smem, st, p);
+    case 5: return k1_launch_part5(N, staged, grid, block, smem, st, p);
     }
+    return cudaErrorInvalidDeviceFunction;
 }

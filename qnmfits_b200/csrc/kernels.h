@@ -14,15 +14,27 @@
 #endif
 
 // ---- K1 (fit_small.cuh): instances N = 1..12, with / without the staged window ----------
-#define K1_PARTS 4
+#define K1_PARTS 6
 // threads per CTA: one 256-thread CTA per SM while the per-lane factor (N (N+1)/2 complex +
 // N real in shared memory) allows it, fewer lanes for the wider factors
 static constexpr int k1_threads_ct(int N) { return N <= 9 ? K1_THREADS : N == 10 ? 192 : 160; }
 static inline int k1_threads(int N) { return k1_threads_ct(N); }
+// Second block size for N <= 8 (parts 4, 5): seven warps.  A slab whose lanes fill 6.9 warps
+// per SM (8192 fits x 4 lanes on 148 SMs: one rank's share of the 256 x 256 grid on 8 GPUs)
+// runs as 147 CTAs of 224 threads on 147 SMs instead of 128 CTAs of 256 on 128.  The block size
+// never enters a fit's arithmetic (a fit is lanes_per_fit lanes of ONE warp), so the choice is
+// made per slab (qnmfit_api.cu, make_plan) and the bits stay those of any other split.
+#ifndef K1_ALT_THREADS
+#define K1_ALT_THREADS 224
+#endif
+static constexpr int k1_alt_threads_ct(int N) { return N <= 8 ? K1_ALT_THREADS : 0; }
+static inline int k1_alt_threads(int N) { return k1_alt_threads_ct(N); }              // 0: none
 static constexpr int k1_part_of(int N) { return N <= 6 ? 0 : N <= 8 ? 1 : N <= 10 ? 2 : 3; }
+static constexpr int k1_alt_part_of(int N) { return N <= 6 ? 4 : 5; }
 int k1_block_rows(int N);                                   // SmallLayout<N>::MB
-size_t k1_smem_bytes(int N, int fpc, int stage_rows);
-const void *k1_kernel_ptr(int N, bool staged);              // for cudaFuncSetAttribute / GetAttributes
+// `threads` = k1_threads(N) or k1_alt_threads(N)
+size_t k1_smem_bytes(int N, int threads, int fpc, int stage_rows);
+const void *k1_kernel_ptr(int N, int threads, bool staged); // for cudaFuncSetAttribute / GetAttributes
 cudaError_t k1_launch(int N, bool staged, int grid, int block, size_t smem, cudaStream_t st, const FitParams &p);
 
 // ---- K2 (fit_general.cuh) -------------------------------------------------------------

@@ -83,9 +83,11 @@ extern "C" int qnmfit_create(int device, qnmfit_ctx **out)
     if ((e = cudaSetDevice(device)) != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaSetDevice"); delete ctx; return r; }
     // opt every kernel in to the full shared-memory carve-out once
     for (int N = 1; N <= QNMFIT_MAX_MODES_SMALL; ++N)
-        for (int st = 0; st < 2; ++st) {
-            if (!k1_kernel_ptr(N, st != 0)) continue;
-            e = cudaFuncSetAttribute(k1_kernel_ptr(N, st != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+        for (int st = 0; st < 4; ++st) {
+            const int threads = st < 2 ? k1_threads(N) : k1_alt_threads(N);
+            const void *fn = threads ? k1_kernel_ptr(N, threads, (st & 1) != 0) : nullptr;
+            if (!fn) continue;
+            e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
             if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaFuncSetAttribute(K1)"); delete ctx; return r; }
         }
     e = cudaFuncSetAttribute(k2_kernel_ptr(), cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
@@ -233,7 +235,9 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
         // factors are combined, and a fit must get the same bits on any slab / GPU count.
         const int nplan = b->plan_fits > 0 ? b->plan_fits : b->n_fits;
         double best = 1e300;
+        const char *force_lpf = getenv("QNMFIT_K1_LPF");       // developer knob (tools/slab_time.py)
         for (int lpf = 1; lpf <= 32; lpf *= 2) {
+            if (force_lpf && atoi(force_lpf) > 0 && lpf != atoi(force_lpf)) continue;
             const int fpc = k1_threads(N) / lpf;
             // CTAs that may be co-resident on an SM by thread count; staging the window
             // must not reduce that (8 warps per SM are needed to keep the FP64 pipe fed)
@@ -243,10 +247,10 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
             const int want_cps = 256 / K1_THREADS > 0 ? 256 / K1_THREADS : 1;
 #endif
             const size_t per_cta = ((size_t)ctx->smem_optin + 1024) / want_cps - 1024;
-            size_t smem = k1_smem_bytes(N, fpc, stage_rows);
+            size_t smem = k1_smem_bytes(N, k1_threads(N), fpc, stage_rows);
             bool staged = b->series_index == nullptr;   // per-fit series are read through L1/L2
-            if (!staged) smem = k1_smem_bytes(N, fpc, 0);
-            if (staged && smem > per_cta) { staged = false; smem = k1_smem_bytes(N, fpc, 0); }
+            if (!staged) smem = k1_smem_bytes(N, k1_threads(N), fpc, 0);
+            if (staged && smem > per_cta) { staged = false; smem = k1_smem_bytes(N, k1_threads(N), fpc, 0); }
             if (smem > per_cta) continue;
 #ifdef K1_FORCE_CPS
             if (smem < per_cta * 6 / 10) smem = per_cta * 6 / 10;   // pad so that no more CTAs become resident
@@ -266,6 +270,22 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
             }
         }
         if (best >= 1e300) return fail(ctx, QNMFIT_E_SHAPE, "K1: no lanes-per-fit choice fits shared memory");
+        // Block size for THIS slab (it does not enter a fit's arithmetic, kernels.h): seven warps
+        // per CTA when that saves a wave or fills more SMs.  A seven-warp CTA takes 0.936 of
+        // the time of an eight-warp one (measured, profiles/slab_time_r02.json).
+#ifndef K1_FORCE_CPS
+        const int alt = k1_alt_threads(N);
+        if (alt > 0 && alt % pl->lpf == 0) {
+            const int fpc_alt = alt / pl->lpf;
+            const size_t smem_alt = k1_smem_bytes(N, alt, fpc_alt, pl->staged ? stage_rows : 0);
+            const int ctas_alt = (b->n_fits + fpc_alt - 1) / fpc_alt;
+            const int waves = (pl->grid + ctx->sm_count - 1) / ctx->sm_count;
+            const int waves_alt = (ctas_alt + ctx->sm_count - 1) / ctx->sm_count;
+            if (smem_alt <= (size_t)ctx->smem_optin && waves_alt * 0.936 < waves * 0.999) {
+                pl->grid = ctas_alt; pl->block = alt; pl->smem = smem_alt;
+            }
+        }
+#endif
     } else if (kernel == QNMFIT_KERNEL_PANEL) {
         pl->lpf = 1; pl->smem = k4_smem_bytes(b->n_modes, b->n_series);
         { const char *pad = getenv("QNMFIT_K4_ONE_PER_SM");     // developer knob: one fit per SM (contention studies)
@@ -616,7 +636,7 @@ extern "C" int qnmfit_plan_batch(qnmfit_ctx *ctx, const qnmfit_batch *b, qnmfit_
     out->smem_bytes = (int32_t)pl.smem; out->staged = pl.staged ? 1 : 0;
     out->fast_mismatch = (pl.kernel != QNMFIT_KERNEL_GENERAL && b->uniform_weights && b->dt_nominal > 0.0 && !b->model) ? 1 : 0;
     cudaFuncAttributes fa;
-    const void *fn = pl.kernel == QNMFIT_KERNEL_SMALL ? k1_kernel_ptr(b->n_modes, pl.staged)
+    const void *fn = pl.kernel == QNMFIT_KERNEL_SMALL ? k1_kernel_ptr(b->n_modes, pl.block, pl.staged)
                    : pl.kernel == QNMFIT_KERNEL_STRUCT ? k3_kernel_ptr(ctx->k3_g, ctx->k3_rpt)
                    : pl.kernel == QNMFIT_KERNEL_PANEL ? k4_kernel_ptr() : k2_kernel_ptr();
     cudaError_t e = cudaFuncGetAttributes(&fa, fn);

@@ -157,13 +157,18 @@ def test_slab_launches_are_bit_identical_to_one_launch(qf, eng, res, slabs):
     full = eng.empty((n,), torch.float64)
     eng.fit(eng.make_batch(n_fits=n, mismatch_d=full, **d))
     parts = eng.empty((n,), torch.float64)
-    lanes = set()
+    lanes, blocks = set(), set()
     for lo, hi in slabs:
         b = eng.make_batch(n_fits=hi - lo, first_fit=lo, plan_fits=n, mismatch_d=parts[lo:hi], **d)
         lanes.add(eng.ctx.plan(b).lanes_per_fit)
+        blocks.add(eng.ctx.plan(b).block)
         eng.fit(b)
     eng.synchronize()
-    assert lanes == {eng.ctx.plan(eng.make_batch(n_fits=n, mismatch_d=full, **d)).lanes_per_fit}
+    whole = eng.ctx.plan(eng.make_batch(n_fits=n, mismatch_d=full, **d))
+    assert lanes == {whole.lanes_per_fit}
+    if res == 256 and torch.cuda.get_device_properties(0).multi_processor_count == 148:
+        # the block size IS chosen per slab (seven warps fill 147 SMs with an eighth of the grid)
+        assert whole.block == 256 and blocks == {224}
     assert torch.equal(full, parts)
 
 
