@@ -12,10 +12,11 @@ LIB_PATH = os.path.join(_HERE, "libqnmfit.so")
 
 ABI_VERSION = 5
 MAX_MODES_SMALL = 12
+MIN_MODES_PAIR, MAX_MODES_PAIR = 9, 16
 MAX_MODES = 64
 MAX_PEERS = 8
 
-KERNEL_AUTO, KERNEL_SMALL, KERNEL_GENERAL, KERNEL_STRUCT, KERNEL_PANEL = 0, 1, 2, 3, 4
+KERNEL_AUTO, KERNEL_SMALL, KERNEL_GENERAL, KERNEL_STRUCT, KERNEL_PANEL, KERNEL_PAIR = 0, 1, 2, 3, 4, 5
 
 ST_RANK_DEFICIENT, ST_NONFINITE, ST_UNDERDETERMINED = 1, 2, 4
 

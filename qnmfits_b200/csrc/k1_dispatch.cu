@@ -60,3 +60,30 @@ cudaError_t k1_launch(int N, bool staged, int grid, int block, size_t smem, cuda
     }
     return cudaErrorInvalidDeviceFunction;
 }
+
+// ---- K1p (k1p_inst.cu, two parts) -------------------------------------------------------------
+#define K1P_DECL(P)                                                                                  \
+    size_t k1p_smem_bytes_part##P(int N, int fpc, int stage_rows);                                   \
+    const void *k1p_kernel_ptr_part##P(int N, bool staged);                                          \
+    cudaError_t k1p_launch_part##P(int N, bool staged, int grid, int block, size_t smem, cudaStream_t st, \
+                                   const FitParams &p);
+K1P_DECL(0) K1P_DECL(1)
+
+size_t k1p_smem_bytes(int N, int fpc, int stage_rows)
+{
+    if (N < K1P_MIN_N || N > K1P_MAX_N) return (size_t)-1;
+    return N <= 12 ? k1p_smem_bytes_part0(N, fpc, stage_rows) : k1p_smem_bytes_part1(N, fpc, stage_rows);
+}
+
+const void *k1p_kernel_ptr(int N, bool staged)
+{
+    if (N < K1P_MIN_N || N > K1P_MAX_N) return nullptr;
+    return N <= 12 ? k1p_kernel_ptr_part0(N, staged) : k1p_kernel_ptr_part1(N, staged);
+}
+
+cudaError_t k1p_launch(int N, bool staged, int grid, int block, size_t smem, cudaStream_t st, const FitParams &p)
+{
+    if (N < K1P_MIN_N || N > K1P_MAX_N) return cudaErrorInvalidDeviceFunction;
+    return N <= 12 ? k1p_launch_part0(N, staged, grid, block, smem, st, p)
+                   : k1p_launch_part1(N, staged, grid, block, smem, st, p);
+}

@@ -37,6 +37,44 @@ size_t k1_smem_bytes(int N, int threads, int fpc, int stage_rows);
 const void *k1_kernel_ptr(int N, int threads, bool staged); // for cudaFuncSetAttribute / GetAttributes
 cudaError_t k1_launch(int N, bool staged, int grid, int block, size_t smem, cudaStream_t st, const FitParams &p);
 
+// ---- K1p (fit_pair.cuh): N = 9..16, the columns of a row slice split over CS lanes ------------
+#define K1P_MIN_N 9
+#define K1P_MAX_N 16
+// Lanes per row slice and rows per register block, measured on the 128 x 128 grid
+// (profiles/k1p_variants_r02.txt): two lanes while their halves of the factor leave >= 224
+// lanes per CTA (N <= 12), four beyond; taller blocks where the registers allow.
+#ifndef K1P_CS
+#define K1P_CS(N) ((N) <= 12 ? 2 : 4)
+#endif
+#ifndef K1P_MB
+#define K1P_MB(N) ((N) <= 11 ? 6 : (N) == 12 ? 4 : (N) == 13 ? 8 : 6)
+#endif
+// AUTO prefers K1p from this column count on (K1's three-row blocks are still faster at N = 9)
+#define K1P_AUTO_MIN_N 10
+static constexpr int k1p_cs_ct(int N) { return K1P_CS(N); }
+static constexpr int k1p_mb_ct(int N) { return K1P_MB(N); }
+// entries of the factor per lane (PairLayout<N, CS>::E, checked in k1p_inst.cu)
+static constexpr int k1p_entries_ct(int N, int CS)
+{
+    int e = N;
+    for (int s = 1; CS * s < N + 1; ++s) e += N + 1 - CS * s;
+    return e;
+}
+// threads per CTA: the most (multiple of 32, <= 256) whose factors leave room for a staged
+// window of ~1000 rows and the frequency tables of eight-lane fits
+static constexpr int k1p_threads_ct(int N)
+{
+    for (int t = 256; t > 128; t -= 32)
+        if (16 * k1p_entries_ct(N, K1P_CS(N)) * t + 48 * N * (t / 8) + 24 * 1024 + 1024 <= 227 * 1024) return t;
+    return 128;
+}
+static inline int k1p_cs(int N) { return k1p_cs_ct(N); }
+static inline int k1p_mb(int N) { return k1p_mb_ct(N); }
+static inline int k1p_threads(int N) { return k1p_threads_ct(N); }
+size_t k1p_smem_bytes(int N, int fpc, int stage_rows);
+const void *k1p_kernel_ptr(int N, bool staged);
+cudaError_t k1p_launch(int N, bool staged, int grid, int block, size_t smem, cudaStream_t st, const FitParams &p);
+
 // ---- K2 (fit_general.cuh) -------------------------------------------------------------
 #define K2_THREADS 256
 size_t k2_smem_bytes(int N, int L, int TR, int TK);

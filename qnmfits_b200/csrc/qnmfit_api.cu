@@ -90,6 +90,13 @@ extern "C" int qnmfit_create(int device, qnmfit_ctx **out)
             e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
             if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaFuncSetAttribute(K1)"); delete ctx; return r; }
         }
+    for (int N = K1P_MIN_N; N <= K1P_MAX_N; ++N)
+        for (int st = 0; st < 2; ++st) {
+            const void *fn = k1p_kernel_ptr(N, st != 0);
+            if (!fn) continue;
+            e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+            if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaFuncSetAttribute(K1p)"); delete ctx; return r; }
+        }
     e = cudaFuncSetAttribute(k2_kernel_ptr(), cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
     if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaFuncSetAttribute(K2)"); delete ctx; return r; }
     e = cudaFuncSetAttribute(k4_kernel_ptr(), cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
@@ -196,6 +203,8 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
     int kernel = b->kernel;
     const bool small_ok = b->n_series == 1 && b->n_modes <= QNMFIT_MAX_MODES_SMALL && !b->coef
         && !b->omega_rows && !b->coef_rows;
+    const bool pair_ok = b->n_series == 1 && b->n_modes >= K1P_MIN_N && b->n_modes <= K1P_MAX_N && !b->coef
+        && !b->omega_rows && !b->coef_rows;
     const bool struct_ok = !b->coef_rows && b->n_modes + b->n_series <= 64
         && k3_smem_bytes(b->n_modes, b->n_series) <= (size_t)ctx->smem_optin;
     const bool panel_ok = !b->coef_rows && b->n_series <= 64
@@ -206,7 +215,10 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
         // beat K3 on the shapes both take
         const char *force = getenv("QNMFIT_AUTO_PANEL");
         const bool prefer_panel = force && force[0] == '1';
-        kernel = small_ok ? QNMFIT_KERNEL_SMALL
+        const char *no_pair = getenv("QNMFIT_AUTO_PAIR");     // "0": the choice before K1p existed
+        const bool prefer_pair = pair_ok && b->n_modes >= K1P_AUTO_MIN_N && !(no_pair && no_pair[0] == '0');
+        kernel = prefer_pair ? QNMFIT_KERNEL_PAIR
+               : small_ok ? QNMFIT_KERNEL_SMALL
                : struct_ok && !(prefer_panel && panel_ok) ? QNMFIT_KERNEL_STRUCT
                : panel_ok ? QNMFIT_KERNEL_PANEL : QNMFIT_KERNEL_GENERAL;
     }
@@ -216,14 +228,17 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
     if (kernel == QNMFIT_KERNEL_STRUCT && !struct_ok)
         return fail(ctx, QNMFIT_E_SHAPE, "K3 needs n_modes + n_series <= 64 (got %d + %d) and no per-row coef table",
                     b->n_modes, b->n_series);
+    if (kernel == QNMFIT_KERNEL_PAIR && !pair_ok)
+        return fail(ctx, QNMFIT_E_SHAPE, "K1p needs n_series == 1, %d <= n_modes <= %d and no coef table",
+                    K1P_MIN_N, K1P_MAX_N);
     if (kernel == QNMFIT_KERNEL_SMALL && !small_ok)
         return fail(ctx, QNMFIT_E_SHAPE, "K1 needs n_series == 1, n_modes <= %d and no coef table",
                     QNMFIT_MAX_MODES_SMALL);
-    if (b->series_index && kernel != QNMFIT_KERNEL_SMALL)
-        return fail(ctx, QNMFIT_E_SHAPE, "series_index is supported by K1 only (n_modes <= %d, no coef table)",
-                    QNMFIT_MAX_MODES_SMALL);
+    if (b->series_index && kernel != QNMFIT_KERNEL_SMALL && kernel != QNMFIT_KERNEL_PAIR)
+        return fail(ctx, QNMFIT_E_SHAPE, "series_index is supported by K1 / K1p only (n_modes <= %d, no coef table)",
+                    K1P_MAX_N);
     if (kernel != QNMFIT_KERNEL_SMALL && kernel != QNMFIT_KERNEL_GENERAL && kernel != QNMFIT_KERNEL_STRUCT
-        && kernel != QNMFIT_KERNEL_PANEL)
+        && kernel != QNMFIT_KERNEL_PANEL && kernel != QNMFIT_KERNEL_PAIR)
         return fail(ctx, QNMFIT_E_SHAPE, "unknown kernel id %d", b->kernel);
     pl->kernel = kernel;
     const int N = b->n_modes;
@@ -286,6 +301,32 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
             }
         }
 #endif
+    } else if (kernel == QNMFIT_KERNEL_PAIR) {
+        // as K1: lanes per fit for the WHOLE sweep (plan_fits); a fit takes lpf / CS row slices
+        const int CS = k1p_cs(N), mb = k1p_mb(N), threads = k1p_threads(N);
+        const int nplan = b->plan_fits > 0 ? b->plan_fits : b->n_fits;
+        const char *force_lpf = getenv("QNMFIT_K1_LPF");
+        double best = 1e300;
+        for (int lpf = CS; lpf <= 32; lpf *= 2) {
+            if (force_lpf && atoi(force_lpf) > 0 && lpf != atoi(force_lpf)) continue;
+            const int fpc = threads / lpf;
+            bool staged = b->series_index == nullptr;
+            size_t smem = k1p_smem_bytes(N, fpc, staged ? Mmax : 0);
+            if (staged && smem > (size_t)ctx->smem_optin) { staged = false; smem = k1p_smem_bytes(N, fpc, 0); }
+            if (smem > (size_t)ctx->smem_optin) continue;
+            const int plan_ctas = (nplan + fpc - 1) / fpc;
+            const int waves = (plan_ctas + ctx->sm_count - 1) / ctx->sm_count;
+            const int groups = lpf / CS;
+            const int rpl = ((Mmax + groups - 1) / groups + mb - 1) / mb;
+            const double blocks = rpl + ilog2(groups) * ((N + mb - 1) / mb);
+            const double cost = (double)(waves > 0 ? waves : 1) * blocks * (staged ? 1.0 : 1.03);
+            if (cost < best) {
+                best = cost;
+                pl->lpf = lpf; pl->grid = (b->n_fits + fpc - 1) / fpc; pl->block = threads; pl->smem = smem;
+                pl->staged = staged; pl->stage_begin = b->row_begin_all; pl->stage_rows = staged ? Mmax : 0;
+            }
+        }
+        if (best >= 1e300) return fail(ctx, QNMFIT_E_SHAPE, "K1p: no lanes-per-fit choice fits shared memory");
     } else if (kernel == QNMFIT_KERNEL_PANEL) {
         pl->lpf = 1; pl->smem = k4_smem_bytes(b->n_modes, b->n_series);
         { const char *pad = getenv("QNMFIT_K4_ONE_PER_SM");     // developer knob: one fit per SM (contention studies)
@@ -393,6 +434,8 @@ static int launch(qnmfit_ctx *ctx, const qnmfit_batch *b, void *stream, bool eva
         // empty slab: only the barrier below
     } else if (pl.kernel == QNMFIT_KERNEL_SMALL) {
         e = k1_launch(b->n_modes, pl.staged, pl.grid, pl.block, pl.smem, st, p);
+    } else if (pl.kernel == QNMFIT_KERNEL_PAIR) {
+        e = k1p_launch(b->n_modes, pl.staged, pl.grid, pl.block, pl.smem, st, p);
     } else if (pl.kernel == QNMFIT_KERNEL_PANEL) {
         e = k4_launch(pl.grid, pl.smem, st, p);
     } else if (pl.kernel == QNMFIT_KERNEL_STRUCT) {
@@ -637,6 +680,7 @@ extern "C" int qnmfit_plan_batch(qnmfit_ctx *ctx, const qnmfit_batch *b, qnmfit_
     out->fast_mismatch = (pl.kernel != QNMFIT_KERNEL_GENERAL && b->uniform_weights && b->dt_nominal > 0.0 && !b->model) ? 1 : 0;
     cudaFuncAttributes fa;
     const void *fn = pl.kernel == QNMFIT_KERNEL_SMALL ? k1_kernel_ptr(b->n_modes, pl.block, pl.staged)
+                   : pl.kernel == QNMFIT_KERNEL_PAIR ? k1p_kernel_ptr(b->n_modes, pl.staged)
                    : pl.kernel == QNMFIT_KERNEL_STRUCT ? k3_kernel_ptr(ctx->k3_g, ctx->k3_rpt)
                    : pl.kernel == QNMFIT_KERNEL_PANEL ? k4_kernel_ptr() : k2_kernel_ptr();
     cudaError_t e = cudaFuncGetAttributes(&fa, fn);

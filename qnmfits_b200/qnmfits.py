@@ -1244,9 +1244,9 @@ class _FreeFrequencyObjective(_ResidentData):
         super().__init__(times, data, t0, t0_method, T)
         self.fixed = np.asarray(fixed_frequencies, dtype=complex).reshape(-1)
         self.N = len(self.fixed) + 1
-        if self.N > _cabi.MAX_MODES_SMALL and self.S > 1:
+        if self.N > _cabi.MAX_MODES_PAIR and self.S > 1:
             raise NotImplementedError(
-                f"batched free-frequency fits support at most {_cabi.MAX_MODES_SMALL - 1} fixed modes")
+                f"batched free-frequency fits support at most {_cabi.MAX_MODES_PAIR - 1} fixed modes")
 
     def __call__(self, X, idx):
         omega = np.empty((len(idx), self.N), dtype=np.complex128)

@@ -267,7 +267,8 @@ def _synthetic_stack(N, L, K_tot, seed, uniform=True):
 
 @pytest.mark.parametrize("N,L,use_coef", [(3, 2, True), (12, 1, False), (12, 1, True), (20, 5, True),
                                            (40, 21, True), (63, 1, False), (9, 7, True), (9, 1, False),
-                                           (10, 1, False), (11, 1, False), (16, 1, False), (1, 1, True),
+                                           (10, 1, False), (11, 1, False), (16, 1, False), (13, 1, False), (14, 1, False),
+                                           (15, 1, False), (1, 1, True),
                                            (8, 2, True), (17, 3, True), (44, 21, True), (64, 30, True)])
 def test_struct_kernel_vs_oracle_and_general_kernel(qf, eng, N, L, use_coef):
     """K4 (blocked structured QR on DMMA) and K3 (structured two-phase QR), uniform (fast
@@ -302,6 +303,11 @@ def test_struct_kernel_vs_oracle_and_general_kernel(qf, eng, N, L, use_coef):
             variants.append(("k1_second_pass", _cabi.KERNEL_SMALL, False))
             if uniform:
                 variants.append(("k1_fast", _cabi.KERNEL_SMALL, True))
+        pair = _cabi.MIN_MODES_PAIR <= N <= _cabi.MAX_MODES_PAIR and L == 1 and not use_coef
+        if pair:                                                      # K1p: columns split over 2 / 4 lanes
+            variants.append(("k1p_second_pass", _cabi.KERNEL_PAIR, False))
+            if uniform:
+                variants.append(("k1p_fast", _cabi.KERNEL_PAIR, True))
         for name, kernel, fast in variants:
             C_d = eng.empty((1, N), torch.complex128)
             mm_d = eng.empty((1,), torch.float64)
@@ -316,8 +322,9 @@ def test_struct_kernel_vs_oracle_and_general_kernel(qf, eng, N, L, use_coef):
             np.testing.assert_allclose(eng.to_host(res_d)[0], res_ref[0], rtol=1e-6, err_msg=name)
             assert int(eng.to_host(st_d)[0]) == 0, name
         plan = eng.ctx.plan(eng.make_batch(kernel=_cabi.KERNEL_AUTO, mismatch_d=mm_d, **d))
-        want = _cabi.KERNEL_SMALL
-        if N > _cabi.MAX_MODES_SMALL or L > 1 or use_coef:
+        auto_pair = pair and N >= 10                                  # K1 keeps N = 9
+        want = _cabi.KERNEL_PAIR if auto_pair else _cabi.KERNEL_SMALL
+        if not auto_pair and (N > _cabi.MAX_MODES_SMALL or L > 1 or use_coef):
             want = _cabi.KERNEL_STRUCT if N + L <= 64 else _cabi.KERNEL_PANEL    # K4 takes over where K3 ends
         assert plan.kernel == want
 
@@ -361,6 +368,57 @@ def test_struct_kernel_many_fits_windows_and_eval(qf, eng, kernel):
         np.testing.assert_allclose(got, m_ref, rtol=0, atol=1e-8 * np.max(np.abs(C_ref)))
     np.testing.assert_allclose(eng.to_host(mm_fast), mm, rtol=0, atol=1e-11)
     np.testing.assert_allclose(eng.to_host(mm_eval), mm, rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("N", [9, 12, 14, 16])
+def test_pair_kernel_many_fits_windows_series_and_eval(qf, eng, N):
+    """K1p (columns of a row slice split over 2 / 4 lanes) on a sweep of 41 fits sharing warps:
+    per-fit windows of different lengths (so lanes run blocks they have no rows for), per-fit
+    start times, per-fit data series (``series_index``), model output, the fast mismatch and
+    the eval-only path — each fit against numpy lstsq on its explicit matrix."""
+    import torch
+    K_tot, B, n_series = 520, 41, 3
+    times, data, freq, _ = _synthetic_stack(N, n_series, K_tot, seed=50 + N)
+    rng = np.random.default_rng(N)
+    rb = rng.integers(0, 60, B).astype(np.int32)
+    re = (rb + rng.integers(40, 440, B)).astype(np.int32)
+    re[3] = rb[3] + N + 1                               # barely overdetermined
+    t0 = times[rb] - 0.03
+    which = rng.integers(0, n_series, B).astype(np.int32)
+    Kmax = int(re.max() - rb.min())
+    d = dict(times_d=eng.to_device(times, np.float64), data_d=eng.to_device(data, np.complex128),
+             omega_d=eng.to_device(freq.reshape(1, -1), np.complex128), omega_shared=True,
+             series_index_d=eng.to_device(which, np.int32), series_stride=K_tot,
+             n_fits=B, n_modes=N, n_series=1, row_begin_all=int(rb.min()), row_end_all=int(re.max()),
+             row_begin_d=eng.to_device(rb, np.int32), row_end_d=eng.to_device(re, np.int32),
+             t0_d=eng.to_device(t0, np.float64), dt_nominal=0.1, kernel=_cabi.KERNEL_PAIR)
+    C_d = eng.empty((B, N), torch.complex128)
+    mm_d = eng.empty((B,), torch.float64)
+    st_d = eng.empty((B,), torch.int32)
+    model_d = eng.empty((B, Kmax), torch.complex128)
+    eng.fit(eng.make_batch(C_d=C_d, mismatch_d=mm_d, model_d=model_d, model_stride=Kmax, status_d=st_d, **d))
+    mm_fast = eng.empty((B,), torch.float64)
+    eng.fit(eng.make_batch(mismatch_d=mm_fast, uniform_weights=True, **d))
+    mm_eval = eng.empty((B,), torch.float64)
+    eng.evaluate(eng.make_batch(C_d=C_d, mismatch_d=mm_eval, **d))
+    C, mm, model, st = eng.to_host(C_d), eng.to_host(mm_d), eng.to_host(model_d), eng.to_host(st_d)
+    checked = 0
+    for b in range(B):
+        sl = slice(rb[b], re[b])
+        K = re[b] - rb[b]
+        a, C_ref, res, rank, s, m_ref = orc.lstsq_fit(times[sl], data[which[b], sl], freq, t0[b], None)
+        if rank < N or st[b] != 0:
+            assert st[b] != 0 or s[-1] > 1e-13 * s[0]      # flagged fits go to the host repair path
+            continue
+        checked += 1
+        assert np.max(np.abs(C[b] - C_ref)) / np.max(np.abs(C_ref)) < cases.amp_tol(s), (b, K)
+        mm_ref = orc.mismatch(times[sl], m_ref, data[which[b], sl])
+        assert abs(mm[b] - mm_ref) < MM_TOL, (b, K)
+        np.testing.assert_allclose(model[b, :K], m_ref, rtol=0, atol=1e-8 * np.max(np.abs(C_ref)))
+    assert checked >= B // 2
+    ok = st == 0
+    np.testing.assert_allclose(eng.to_host(mm_fast)[ok], mm[ok], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(eng.to_host(mm_eval)[ok], mm[ok], rtol=0, atol=1e-12)
 
 
 def test_free_frequency_fit_vs_reference_golden_and_oracle(qf, eng, golden, oracle_tables):

@@ -26,7 +26,7 @@ warnings.simplefilter("ignore")
 
 
 def random_modes():
-    n = int(rng.integers(1, 13))
+    n = int(rng.integers(1, 17))
     pool = [(2, 2, k, 1) for k in range(12)] + [(2, 2, k, -1) for k in range(3)] + \
         [(3, 2, k, 1) for k in range(3)] + [(2, 2, 0, 1, 2, 2, 0, 1), (2, 2, 0, 1, 2, 2, 1, 1), (2, 2, 9, 1), (2, 2, 10, 1)]
     idx = rng.choice(len(pool), size=min(n, len(pool)), replace=False)
