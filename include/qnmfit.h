@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define QNMFIT_ABI_VERSION 5
+#define QNMFIT_ABI_VERSION 6
 
 /* limits of the compiled kernels */
 #define QNMFIT_MAX_MODES_SMALL 12    /* register-resident TSQR kernel (K1): 4-row blocks
@@ -284,7 +284,13 @@ int qnmfit_stream_sync(qnmfit_ctx *ctx, void *stream);
  * so they travel in one cudaMemcpyAsync), zero *b->flagged_count (QNMFIT_RUN_ZERO_COUNTER),
  * launch the fits (with the peer exchange when `peers` is not NULL), copy `result_bytes`
  * from `result_dev` back to `result_host` (QNMFIT_RUN_RESULT_PINNED: `result_host` is
- * page-locked, copy straight into it) and wait for the stream. */
+ * page-locked, copy straight into it) and wait for the stream.
+ * One host thread driving several devices issues the call once per device with
+ * QNMFIT_RUN_NO_SYNC (return as soon as everything is enqueued; needs a page-locked
+ * `result_host`; the caller waits with qnmfit_stream_sync before it reads the result or uses
+ * the ctx again) and QNMFIT_RUN_UPLOADS_PINNED (the `src_host` arrays are page-locked already
+ * — one staging copy shared by all devices — and, with QNMFIT_RUN_COALESCE, laid out like
+ * their destinations). */
 typedef struct qnmfit_copy {
     void       *dst_dev;
     const void *src_host;
@@ -293,6 +299,8 @@ typedef struct qnmfit_copy {
 #define QNMFIT_RUN_COALESCE      1
 #define QNMFIT_RUN_ZERO_COUNTER  2
 #define QNMFIT_RUN_RESULT_PINNED 4
+#define QNMFIT_RUN_NO_SYNC       8
+#define QNMFIT_RUN_UPLOADS_PINNED 16
 int qnmfit_run_host(qnmfit_ctx *ctx, const qnmfit_batch *b, const qnmfit_peers *peers,
                     const qnmfit_copy *uploads, int n_uploads,
                     const void *result_dev, void *result_host, size_t result_bytes,

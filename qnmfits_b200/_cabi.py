@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libqnmfit.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_MODES_SMALL = 12
 MIN_MODES_PAIR, MAX_MODES_PAIR = 9, 16
 MAX_MODES = 64
@@ -77,7 +77,7 @@ class Copy(C.Structure):
     _fields_ = [("dst_dev", _dp), ("src_host", _dp), ("bytes", C.c_size_t)]
 
 
-RUN_COALESCE, RUN_ZERO_COUNTER, RUN_RESULT_PINNED = 1, 2, 4
+RUN_COALESCE, RUN_ZERO_COUNTER, RUN_RESULT_PINNED, RUN_NO_SYNC, RUN_UPLOADS_PINNED = 1, 2, 4, 8, 16
 
 
 class Plan(C.Structure):

@@ -498,8 +498,11 @@ extern "C" int qnmfit_run_host(qnmfit_ctx *ctx, const qnmfit_batch *b, const qnm
     int rc;
     // ---- uploads: staged through the ctx's pinned buffer (free again: every call ends with a
     // stream synchronisation).  Layout of the staging = layout of the device destinations.
+    if ((flags & QNMFIT_RUN_NO_SYNC) && result_bytes > 0 && !(flags & QNMFIT_RUN_RESULT_PINNED))
+        return fail(ctx, QNMFIT_E_SHAPE, "QNMFIT_RUN_NO_SYNC needs QNMFIT_RUN_RESULT_PINNED");
     if (n_uploads > 0) {
         const bool coalesce = (flags & QNMFIT_RUN_COALESCE) != 0;
+        const bool pinned = (flags & QNMFIT_RUN_UPLOADS_PINNED) != 0;
         size_t total = 0;
         if (coalesce) {
             for (int i = 0; i < n_uploads; ++i) {
@@ -507,6 +510,9 @@ extern "C" int qnmfit_run_host(qnmfit_ctx *ctx, const qnmfit_batch *b, const qnm
                     return fail(ctx, QNMFIT_E_NULL, "upload %d: NULL pointer", i);
                 if (i > 0 && (const char *)uploads[i].dst_dev < (const char *)uploads[i - 1].dst_dev + uploads[i - 1].bytes)
                     return fail(ctx, QNMFIT_E_SHAPE, "QNMFIT_RUN_COALESCE: destinations must ascend without overlap");
+                if (pinned && (const char *)uploads[i].src_host - (const char *)uploads[0].src_host
+                              != (const char *)uploads[i].dst_dev - (const char *)uploads[0].dst_dev)
+                    return fail(ctx, QNMFIT_E_SHAPE, "QNMFIT_RUN_UPLOADS_PINNED | COALESCE: sources must be laid out like the destinations");
             }
             total = (size_t)((const char *)uploads[n_uploads - 1].dst_dev - (const char *)uploads[0].dst_dev)
                   + uploads[n_uploads - 1].bytes;
@@ -517,19 +523,27 @@ extern "C" int qnmfit_run_host(qnmfit_ctx *ctx, const qnmfit_batch *b, const qnm
                 total += (uploads[i].bytes + 255) / 256 * 256;
             }
         }
-        if ((rc = grow_pinned(ctx, &ctx->stage_up, &ctx->stage_up_bytes, total))) return rc;
+        if (!pinned && (rc = grow_pinned(ctx, &ctx->stage_up, &ctx->stage_up_bytes, total))) return rc;
         if (coalesce) {
-            const char *base = (const char *)uploads[0].dst_dev;
-            for (int i = 0; i < n_uploads; ++i)
-                memcpy(ctx->stage_up + ((const char *)uploads[i].dst_dev - base), uploads[i].src_host, uploads[i].bytes);
-            if ((e = cudaMemcpyAsync(uploads[0].dst_dev, ctx->stage_up, total, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+            const void *src = uploads[0].src_host;
+            if (!pinned) {
+                const char *base = (const char *)uploads[0].dst_dev;
+                for (int i = 0; i < n_uploads; ++i)
+                    memcpy(ctx->stage_up + ((const char *)uploads[i].dst_dev - base), uploads[i].src_host, uploads[i].bytes);
+                src = ctx->stage_up;
+            }
+            if ((e = cudaMemcpyAsync(uploads[0].dst_dev, src, total, cudaMemcpyHostToDevice, st)) != cudaSuccess)
                 return cuda_fail(ctx, e, "cudaMemcpyAsync(H2D)");
         } else {
             size_t off = 0;
             for (int i = 0; i < n_uploads; ++i) {
                 if (!uploads[i].bytes) continue;
-                memcpy(ctx->stage_up + off, uploads[i].src_host, uploads[i].bytes);
-                if ((e = cudaMemcpyAsync(uploads[i].dst_dev, ctx->stage_up + off, uploads[i].bytes,
+                const void *src = uploads[i].src_host;
+                if (!pinned) {
+                    memcpy(ctx->stage_up + off, uploads[i].src_host, uploads[i].bytes);
+                    src = ctx->stage_up + off;
+                }
+                if ((e = cudaMemcpyAsync(uploads[i].dst_dev, src, uploads[i].bytes,
                                          cudaMemcpyHostToDevice, st)) != cudaSuccess)
                     return cuda_fail(ctx, e, "cudaMemcpyAsync(H2D)");
                 off += (uploads[i].bytes + 255) / 256 * 256;
@@ -550,6 +564,7 @@ extern "C" int qnmfit_run_host(qnmfit_ctx *ctx, const qnmfit_batch *b, const qnm
         if ((e = cudaMemcpyAsync(dst, result_dev, result_bytes, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
             return cuda_fail(ctx, e, "cudaMemcpyAsync(D2H)");
     }
+    if (flags & QNMFIT_RUN_NO_SYNC) return 0;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(ctx, e, "cudaStreamSynchronize");
     if (result_bytes > 0 && !(flags & QNMFIT_RUN_RESULT_PINNED)) memcpy(result_host, ctx->stage_down, result_bytes);
     return 0;

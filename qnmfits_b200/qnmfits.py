@@ -765,11 +765,19 @@ class _DeviceGroupSweep:
     """One process driving several GPUs (``qnmfits_b200.use_devices``): the flat fit index
     is split into one slab per device, every device gets its own upload and launch on its
     own stream, and the host concatenates the slabs — the call stays a plain function call
-    from a notebook (no torchrun).  Same interface as ``_Sweep``."""
+    from a notebook (no torchrun).  Same interface as ``_Sweep``.
+
+    ``rerun`` (a repeated call with the same problem) stages ``times`` and the data ONCE in a
+    page-locked buffer laid out like the devices' input blocks, then issues one
+    ``qnmfit_run_host`` per device without waiting (``RUN_NO_SYNC | RUN_UPLOADS_PINNED``: one
+    H2D, the counter's memset and the launch, all asynchronous), then one D2H per device into
+    its page-locked result block, and only then waits for the streams: the devices compute
+    concurrently and the host work per device is the four enqueues (13 us measured)."""
 
     def __init__(self, devices, args, kwargs):
         import torch
         self.n_fits = kwargs['n_fits']
+        self.devices = tuple(devices)
         self._restore = torch.cuda.current_device()
         self.parts = []
         n_dev = len(devices)
@@ -780,6 +788,8 @@ class _DeviceGroupSweep:
         torch.cuda.set_device(self._restore)
         self.rows_max = self.parts[0].rows_max
         self.window = None
+        self.eng = self.parts[0].eng
+        self._stage = None
 
     def launch_kernel(self):
         import torch
@@ -796,6 +806,66 @@ class _DeviceGroupSweep:
     def fetch(self):
         results = [part.fetch() for part in self.parts]
         return np.concatenate([r[0] for r in results]), sum(r[1] for r in results)
+
+    def _prepare_rerun(self, n_series):
+        """Page-locked staging shared by the devices and, per device, the upload descriptors
+        and a page-locked result block."""
+        import torch
+        p0 = self.parts[0]
+        span = p0._dyn_ptrs[1] - p0._dyn_ptrs[0]
+        same = all(p._dyn_ptrs[1] - p._dyn_ptrs[0] == span and p._dyn_bytes == p0._dyn_bytes for p in self.parts)
+        data_off = (p0._dyn_bytes[0] + 255) // 256 * 256
+        coalesce = same and span == data_off         # [times | padding | data] inside one input block
+        stage = torch.empty(data_off + p0._dyn_bytes[1], dtype=torch.uint8, pin_memory=True)
+        base = stage.data_ptr()
+        each = p0._dyn_bytes[1] // n_series
+        host = stage.numpy()
+        self._stage = (stage, host[:p0._dyn_bytes[0]].view(np.float64),
+                       [host[data_off + i * each:data_off + (i + 1) * each].view(np.complex128) for i in range(n_series)])
+        for part in self.parts:
+            up = (_cabi.Copy * (1 + n_series))()
+            up[0].dst_dev, up[0].src_host, up[0].bytes = part._dyn_ptrs[0], base, part._dyn_bytes[0]
+            for i in range(n_series):
+                up[1 + i].dst_dev = part._dyn_ptrs[1] + i * each
+                up[1 + i].src_host = base + data_off + i * each
+                up[1 + i].bytes = each
+            block = torch.empty(part._result_bytes, dtype=torch.uint8, pin_memory=True)
+            part._group_run = (up, block, block.numpy().view(np.float64),
+                               _cabi.RUN_NO_SYNC | _cabi.RUN_UPLOADS_PINNED | _cabi.RUN_RESULT_PINNED
+                               | _cabi.RUN_ZERO_COUNTER | (_cabi.RUN_COALESCE if coalesce else 0))
+
+    def rerun(self, times, rows):
+        if isinstance(rows, np.ndarray):
+            rows = [rows] if rows.ndim == 1 else list(rows.reshape(self.parts[0].rows_shape))
+        if self._stage is None or len(self._stage[2]) != len(rows):
+            self._prepare_rerun(len(rows))
+        _, t_view, r_views = self._stage
+        if times.shape != t_view.shape or any(r.shape != v.shape for r, v in zip(rows, r_views)):
+            raise ValueError("rerun: array shapes differ from the prepared sweep")
+        np.copyto(t_view, times)
+        for r, v in zip(rows, r_views):
+            np.copyto(v, r)
+        for part in self.parts:                      # upload and launch on every device first ...
+            up, block, _, flags = part._group_run
+            part._fresh = False
+            part.eng.h2d_bytes += part._dyn_bytes[0] + part._dyn_bytes[1]
+            part.eng.d2h_bytes += part._result_bytes
+            part.eng.ctx.run_host(part.batch, None, up, len(up), 0, 0, 0, flags, part.stream)
+        for part in self.parts:                      # ... the downloads queue up behind the kernels ...
+            part.eng.ctx.d2h(part._group_run[1].data_ptr(), part._result, part._result_bytes, part.stream, sync=False)
+        mm_all = np.empty(self.n_fits, dtype=np.float64)
+        flagged = 0
+        for part in self.parts:                      # ... then wait, device by device
+            part.eng.ctx.stream_sync(part.stream)
+            out = part._group_run[2]                 # [counter | mismatch slab | flag list], page-locked
+            n_local = part.hi - part.lo
+            mm = mm_all[part.lo:part.hi]
+            np.copyto(mm, out[1:1 + n_local])
+            count = int(out[0])
+            if count:
+                count = part._repair_rank_deficient(mm, part._flags_from(out[1 + n_local:].copy(), count))
+            flagged += count
+        return mm_all, flagged
 
 
 # --------------------------------------------------------------------------
@@ -827,8 +897,8 @@ def _delta_key(delta):
 
 def _problem_key(kind, times, data, modes, spherical_modes, delta, coef_columns, scalars):
     """Hashable signature of a sweep, or None when it must not be cached (caller-supplied
-    coefficient callables, a single-process device group, unhashable arguments)."""
-    if coef_columns or _dist.local_devices() is not None or times.ndim != 1:
+    coefficient callables, unhashable arguments)."""
+    if coef_columns or times.ndim != 1:
         return None
     try:
         if type(data) is dict:
@@ -840,7 +910,7 @@ def _problem_key(kind, times, data, modes, spherical_modes, delta, coef_columns,
         if dk is None or n_data != len(times) or n_data * 16 * (1 if keys is None else len(keys)) > _SWEEP_CACHE_MAX_BYTES:
             return None
         key = (kind, _qnm_class._epoch, tuple(tuple(mode) for mode in modes), keys, dk, len(times),
-               _dist.world(), scalars)
+               _dist.world(), None if _dist.local_devices() is None else tuple(_dist.local_devices()), scalars)
         hash(key)
         return key
     except (TypeError, KeyError, IndexError):
@@ -853,15 +923,16 @@ def _cached_sweep(key, times):
     if hit is None:
         return None
     sweep = hit[0]
-    if (sweep.window is not None and sweep.window.closed) or sweep.eng is not get_engine() \
-            or not np.array_equal(hit[1], times):
+    stale = sweep.eng is not get_engine() if isinstance(sweep, _Sweep) else \
+        any(part.eng is not get_engine(dev) for part, dev in zip(sweep.parts, sweep.devices))
+    if (sweep.window is not None and sweep.window.closed) or stale or not np.array_equal(hit[1], times):
         del _sweep_cache[key]
         return None
     return hit
 
 
 def _cache_sweep(key, sweep, times, *aux):
-    if key is None or not isinstance(sweep, _Sweep):
+    if key is None or not isinstance(sweep, (_Sweep, _DeviceGroupSweep)):
         return
     while len(_sweep_cache) >= _SWEEP_CACHE_MAX:
         del _sweep_cache[next(iter(_sweep_cache))]

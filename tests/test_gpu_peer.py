@@ -114,17 +114,31 @@ def test_single_process_device_group_matches_one_device():
     wl3, wl2, wl4 = workloads.config3(res=8), workloads.config2(), cases.cfg4_small()
     torch.cuda.set_device(0)
     one = _sweeps(qf, wl3, wl2, wl4)
+    grid8_args = (wl3.modes, wl3.Mf_minmax, wl3.chif_minmax, wl3.t0)
+    grid8 = qf.mismatch_M_chi_grid(wl3.times, wl3.data, *grid8_args, T=wl3.T, res=8)
     try:
         assert qf.use_devices("all")[:2] == [0, 1]
         qf.use_devices([1, 0])
         two = _sweeps(qf, wl3, wl2, wl4)
         assert torch.cuda.current_device() == 0
+        # repeated calls find the prepared sweeps of the group and go through its one-call-per-
+        # device path (staging shared by the devices, no wait between the devices' enqueues)
+        launches = [qf.qnmfits.get_engine(dev).ctx.launch_count() for dev in (0, 1)]
+        two_again = _sweeps(qf, wl3, wl2, wl4)
+        other = wl3.data * (1.0 + 0.1j) + 1e-3 * np.exp(0.3j * wl3.times)
+        grid8_two = qf.mismatch_M_chi_grid(wl3.times, wl3.data, *grid8_args, T=wl3.T, res=8)
+        grid_other = qf.mismatch_M_chi_grid(wl3.times, other, *grid8_args, T=wl3.T, res=8)     # prepared: rerun
+        assert all(qf.qnmfits.get_engine(dev).ctx.launch_count() > n for dev, n in zip((0, 1), launches))
     finally:
         qf.use_devices(None)
     again = _sweeps(qf, wl3, wl2, wl4)
+    grid_other_one = qf.mismatch_M_chi_grid(wl3.times, other, *grid8_args, T=wl3.T, res=8)
+    assert np.array_equal(grid8_two, grid8) and np.array_equal(grid_other, grid_other_one)
+    assert not np.array_equal(grid_other_one, grid8)
     for name, ref in one.items():
         assert two[name].shape == ref.shape and np.all(np.isfinite(two[name]))
         assert np.array_equal(two[name], ref), name
+        assert np.array_equal(two_again[name], ref), name
         assert np.array_equal(again[name], ref), name
     with pytest.raises(ValueError):
         qf.use_devices([0, 0])

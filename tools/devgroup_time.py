@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Developer tool (multi-GPU box): mismatch_M_chi_grid (cfg3, 256 x 256) from ONE process
-driving 1..N GPUs (qnmfits_b200.use_devices), wall clock per call."""
+driving 1..N GPUs (qnmfits_b200.use_devices), wall clock per call (repeated calls: the
+prepared sweep of the group is found and only times + data travel)."""
 import json
 import os
 import sys
