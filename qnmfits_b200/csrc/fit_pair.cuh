@@ -34,6 +34,14 @@ template <int N, int CS>
 struct PairLayout {
     static_assert(CS == 2 || CS == 4, "2 or 4 lanes per row slice");
     static constexpr int S = (N + 1 + CS - 1) / CS;            // slots (columns) per lane
+    // frequency tables: one row of N entries per fit behind CS - 1 leading entries (and one
+    // trailing), so that slot s of lane h — column N - CS s - h, which may be the data column N
+    // or lie left of column 0 — reads entry tab(N - h) - CS s of its fit's row without a clamp.
+    // What it finds there for those two cases (a neighbouring fit's entry, or padding) is
+    // never used: the data slot is overwritten with the data, and a slot left of column 0 is
+    // neither a reflector nor a trailing column of any reflection.
+    static constexpr int NT = N;
+    QF_MEMBOTH static constexpr int tab(int k) { return CS - 1 + k; }
     // rows of the factor stored for slot s (lane 0's column is the longest of the slot; the
     // right-hand side, slot 0 of lane 0, has N rows)
     QF_MEMBOTH static constexpr int rows(int s) { return s == 0 ? N : N + 1 - CS * s; }
@@ -48,9 +56,9 @@ struct PairLayout {
 template <int N, int CS, int THREADS>
 struct PairSmem {
     double2 *R;         // [E][THREADS]    the lanes' columns of their factors
-    double2 *om;        // [N][fpc]        frequencies of the CTA's fits
-    double2 *qq;        // [N][fpc]        exp(-i w dt)
-    double2 *qw;        // [N][fpc]        exp(-i w dt) * (-i w)
+    double2 *om;        // [fpc][NT]       frequencies of the CTA's fits (PairLayout::tab)
+    double2 *qq;        // [fpc][NT]       exp(-i w dt)
+    double2 *qw;        // [fpc][NT]       exp(-i w dt) * (-i w)
     const double2 *ds;  // [stage_rows]    staged data window (or global data)
     const double *ts;   // [stage_rows]    staged times (or global times)
     int fpc, t_off;
@@ -58,7 +66,7 @@ struct PairSmem {
     QF_MEMBOTH static size_t bytes(int fpc, int stage_rows)
     {
         if (stage_rows > 0) stage_rows += SMALL_STAGE_PAD;
-        return sizeof(double2) * (size_t)(PairLayout<N, CS>::E * THREADS + 3 * N * fpc + stage_rows)
+        return sizeof(double2) * (size_t)(PairLayout<N, CS>::E * THREADS + 3 * (PairLayout<N, CS>::NT * fpc + CS) + stage_rows)
              + sizeof(double) * (size_t)stage_rows;
     }
     QF_MEM void carve(void *basep, int fpc_, int stage_rows)
@@ -67,9 +75,9 @@ struct PairSmem {
         fpc = fpc_;
         double2 *p2 = (double2 *)basep;
         R = p2; p2 += PairLayout<N, CS>::E * THREADS;
-        om = p2; p2 += N * fpc;
-        qq = p2; p2 += N * fpc;
-        qw = p2; p2 += N * fpc;
+        om = p2; p2 += PairLayout<N, CS>::NT * fpc + CS;
+        qq = p2; p2 += PairLayout<N, CS>::NT * fpc + CS;
+        qw = p2; p2 += PairLayout<N, CS>::NT * fpc + CS;
         ds = p2; p2 += stage_rows;
         ts = (const double *)p2;
     }
@@ -214,16 +222,13 @@ QF_HD void pair_leaf(const FitParams &p, const PairSmem<N, CS, THREADS> &sm, con
     const bool direct = !(dt > 0.0);
     int ablk = (p.anchor_rows > 0 ? p.anchor_rows : QNMFIT_DEFAULT_ANCHOR_ROWS) / MB;
     if (ablk < 1) ablk = 1;
-    // this lane's columns: slot s holds column N - CS s - h (slot 0 of lane 0: the data)
-    int kc[S];
-    bool model_col[S];
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-        const int k = N - CS * s - h;
-        model_col[s] = k >= 0 && k < N;
-        kc[s] = (k < 0 ? 0 : k > N - 1 ? N - 1 : k) * fpc + L.slot;
-    }
-    const int nblk_w = __reduce_max_sync(0xffffffffu, L.nblk);
+    // this lane's columns: slot s holds column N - CS s - h (slot 0 of lane 0: the data); see
+    // PairLayout::NT for what the table holds for the data slot and left of column 0
+    const double2 *om = sm.om + L.slot * LY::NT + LY::tab(N - h);
+    const double2 *qq = sm.qq + L.slot * LY::NT + LY::tab(N - h);
+    const double2 *qw = sm.qw + L.slot * LY::NT + LY::tab(N - h);
+    const unsigned full = 0xffffffffu;
+    const int nblk_w = __reduce_max_sync(full, L.nblk);
     const int last = L.re > L.rb ? L.re - 1 : L.rb;
     double2 z[S];
     double2 B[MB][S];
@@ -240,33 +245,53 @@ QF_HD void pair_leaf(const FitParams &p, const PairSmem<N, CS, THREADS> &sm, con
         if (direct || blk % ablk == 0) {
             tau = qf_sub_rn(ts[ra], t0);
 #pragma unroll
-            for (int s = 0; s < S; ++s) z[s] = model_col[s] ? design_entry(sm.om[kc[s]], tau) : zero;
+            for (int s = 0; s < S; ++s) z[s] = design_entry(om[-CS * s], tau);
         }
+        if (!direct && __all_sync(full, row0 + MB <= L.hi)) {
+            // every lane of the warp has a full block: no per-row selects
 #pragma unroll
-        for (int i = 0; i < MB; ++i) {
-            const int r = ra + i;
-            const bool valid = live && r < L.hi;
-            const int rc = r < last ? r : last;
-            const int rn = r + 1 < last ? r + 1 : last;
-            const double2 dval = ds[rc];
-#pragma unroll
-            for (int s = 0; s < S; ++s) B[i][s] = valid ? z[s] : zero;
-            if (h == 0) B[i][0] = valid ? dval : zero;
-            const double tau_n = qf_sub_rn(ts[rn], t0);
-            if (direct) {
-                if (i < MB - 1) {
-#pragma unroll
-                    for (int s = 0; s < S; ++s) z[s] = model_col[s] ? design_entry(sm.om[kc[s]], tau_n) : zero;
-                }
-            } else {
+            for (int i = 0; i < MB; ++i) {
+                const int r = row0 + i;
+                const int rn = r + 1 < last ? r + 1 : last;
+                const double2 dval = ds[r];
+                const double tau_n = qf_sub_rn(ts[rn], t0);
                 const double de = qf_sub_rn(qf_sub_rn(tau_n, tau), dt);
+                tau = tau_n;
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
-                    const double2 q = sm.qq[kc[s]], w = sm.qw[kc[s]];
+                    B[i][s] = z[s];
+                    const double2 q = qq[-CS * s], w = qw[-CS * s];
                     z[s] = c_mul(z[s], make_double2(fma(w.x, de, q.x), fma(w.y, de, q.y)));
                 }
+                if (h == 0) B[i][0] = dval;
             }
-            tau = tau_n;
+        } else {
+#pragma unroll
+            for (int i = 0; i < MB; ++i) {
+                const int r = ra + i;
+                const bool valid = live && r < L.hi;
+                const int rc = r < last ? r : last;
+                const int rn = r + 1 < last ? r + 1 : last;
+                const double2 dval = ds[rc];
+#pragma unroll
+                for (int s = 0; s < S; ++s) B[i][s] = valid ? z[s] : zero;
+                if (h == 0) B[i][0] = valid ? dval : zero;
+                const double tau_n = qf_sub_rn(ts[rn], t0);
+                if (direct) {
+                    if (i < MB - 1) {
+#pragma unroll
+                        for (int s = 0; s < S; ++s) z[s] = design_entry(om[-CS * s], tau_n);
+                    }
+                } else {
+                    const double de = qf_sub_rn(qf_sub_rn(tau_n, tau), dt);
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        const double2 q = qq[-CS * s], w = qw[-CS * s];
+                        z[s] = c_mul(z[s], make_double2(fma(w.x, de, q.x), fma(w.y, de, q.y)));
+                    }
+                }
+                tau = tau_n;
+            }
         }
         pair_acc_rhs<MB, S>(B, acc.sdd, sdd1);
         pair_absorb<N, CS, MB, THREADS, 0>(B, sm.R + tid, h, live);
@@ -383,7 +408,7 @@ QF_HD void pair_fast_partials(const FitParams &p, const PairSmem<N, CS, THREADS>
     const double tau_f = qf_sub_rn(sm.ts[L.rb - sm.t_off], L.t0);
     const double tau_l = qf_sub_rn(sm.ts[L.re - 1 - sm.t_off], L.t0);
     for (int j = L.lf; j < N; j += p.lanes_per_fit) {
-        const double2 w = sm.om[j * sm.fpc + L.slot];
+        const double2 w = sm.om[L.slot * LY::NT + LY::tab(j)];
         const double2 C = sm.R[(LY::base(0) + j) * THREADS + t0lane];
         const double2 af = design_entry(w, tau_f), al = design_entry(w, tau_l);
         part[2] = fma(af.x, C.x, part[2]); part[2] = fma(-af.y, C.y, part[2]);
@@ -425,12 +450,12 @@ QF_HD void pair_eval(const FitParams &p, const PairSmem<N, CS, THREADS> &sm, con
         const double tau_r = qf_sub_rn(ts[r], L.t0);
         if (direct || (r - a) % arows == 0) {
 #pragma unroll
-            for (int j = 0; j < N; ++j) z[j] = design_entry(sm.om[j * sm.fpc + L.slot], tau_r);
+            for (int j = 0; j < N; ++j) z[j] = design_entry(sm.om[L.slot * LY::NT + LY::tab(j)], tau_r);
         } else {
             const double de = qf_sub_rn(qf_sub_rn(tau_r, tau), p.dt_nominal);
 #pragma unroll
             for (int j = 0; j < N; ++j) {
-                const double2 q = sm.qq[j * sm.fpc + L.slot], w = sm.qw[j * sm.fpc + L.slot];
+                const double2 q = sm.qq[L.slot * LY::NT + LY::tab(j)], w = sm.qw[L.slot * LY::NT + LY::tab(j)];
                 z[j] = c_mul(z[j], make_double2(fma(w.x, de, q.x), fma(w.y, de, q.y)));
             }
         }
@@ -482,18 +507,19 @@ __global__ void __launch_bounds__(THREADS, 1) fit_pair_kernel(const __grid_const
         sm.t_off = 0;
     }
     const int cta_first = blockIdx.x * fpc;
-    for (int idx = tid; idx < fpc * N; idx += THREADS) {
-        const int slot = idx / N, j = idx - slot * N;
+    for (int idx = tid; idx < fpc * N + CS; idx += THREADS) {
+        const int e = idx - (CS - 1);                 // entry of the [fpc][N] table, or padding
+        const int slot = e >= 0 ? e / N : 0, j = e - slot * N;
         const int fit = cta_first + slot;
         double2 w = make_double2(0.0, 0.0), q = w, qw = w;
-        if (fit < p.n_fits) {
+        if (e >= 0 && slot < fpc && fit < p.n_fits) {
             w = fit_omega(p, input_fit(p, fit), j);
             if (p.dt_nominal > 0.0) {
                 q = design_entry(w, p.dt_nominal);
                 qw = c_mul(q, make_double2(w.y, -w.x));
             }
         }
-        sm.om[j * fpc + slot] = w; sm.qq[j * fpc + slot] = q; sm.qw[j * fpc + slot] = qw;
+        sm.om[idx] = w; sm.qq[idx] = q; sm.qw[idx] = qw;
     }
     const int safe_row = STAGED ? p.stage_begin : 0;
     const SmallLane L = pair_lane_setup<CS>(p, blockIdx.x, tid, THREADS, !STAGED, MB, safe_row);

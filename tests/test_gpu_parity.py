@@ -451,11 +451,12 @@ def test_free_frequency_fit_vs_reference_golden_and_oracle(qf, eng, golden, orac
         qf.free_frequency_fit(wl.times, wl.data[0], 0.0, t0_method='nearest')
 
 
-def test_free_frequency_objective_matches_oracle_mismatch(qf, eng, oracle_tables):
+@pytest.mark.parametrize("n_fixed", [2, 9, 11])
+def test_free_frequency_objective_matches_oracle_mismatch(qf, eng, oracle_tables, n_fixed):
     """One batched objective call (per-fit data rows, per-fit trial frequency) against the
-    numpy objective of the reference (qnmfits.py:2003-2029)."""
+    numpy objective of the reference (qnmfits.py:2003-2029); 9 and 11 fixed modes run on K1p."""
     from qnmfits_b200 import qnmfits as api
-    wl = workloads.config5(n_waveforms=33, n_fixed=2)
+    wl = workloads.config5(n_waveforms=33, n_fixed=n_fixed)
     fixed = np.array(qf.qnm.omega_list(wl.modes, wl.chif, wl.Mf))
     obj = api._FreeFrequencyObjective(wl.times, wl.data, 0.0, fixed, 'geq', 100)
     rng = np.random.default_rng(8)
