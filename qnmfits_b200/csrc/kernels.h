@@ -41,16 +41,17 @@ cudaError_t k1_launch(int N, bool staged, int grid, int block, size_t smem, cuda
 #define K1P_MIN_N 9
 #define K1P_MAX_N 16
 // Lanes per row slice and rows per register block, measured on the 128 x 128 grid
-// (profiles/k1p_variants_r02.txt): two lanes while their halves of the factor leave >= 224
-// lanes per CTA (N <= 12), four beyond; taller blocks where the registers allow.
+// (profiles/k1p_variants_r02.txt: A = 2 lanes / 4 rows, C = 4 / 8, D = 2 / 6 (4 beyond N = 12),
+// E = 4 / 6, F = 2 / 8 up to N = 10 and 2 / 5 beyond, G = 4 / 10): two lanes while their halves of
+// the factor leave >= 224 lanes per CTA (N <= 12), four beyond; taller blocks where the registers allow.
 #ifndef K1P_CS
 #define K1P_CS(N) ((N) <= 12 ? 2 : 4)
 #endif
 #ifndef K1P_MB
-#define K1P_MB(N) ((N) <= 11 ? 6 : (N) == 12 ? 4 : (N) == 13 ? 8 : 6)
+#define K1P_MB(N) ((N) <= 10 ? 6 : (N) == 11 ? 5 : (N) == 12 ? 4 : (N) <= 14 ? 8 : 6)
 #endif
-// AUTO prefers K1p from this column count on (K1's three-row blocks are still faster at N = 9)
-#define K1P_AUTO_MIN_N 10
+// AUTO prefers K1p from this column count on
+#define K1P_AUTO_MIN_N 9
 static constexpr int k1p_cs_ct(int N) { return K1P_CS(N); }
 static constexpr int k1p_mb_ct(int N) { return K1P_MB(N); }
 // entries of the factor per lane (PairLayout<N, CS>::E, checked in k1p_inst.cu)

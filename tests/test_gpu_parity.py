@@ -322,7 +322,7 @@ def test_struct_kernel_vs_oracle_and_general_kernel(qf, eng, N, L, use_coef):
             np.testing.assert_allclose(eng.to_host(res_d)[0], res_ref[0], rtol=1e-6, err_msg=name)
             assert int(eng.to_host(st_d)[0]) == 0, name
         plan = eng.ctx.plan(eng.make_batch(kernel=_cabi.KERNEL_AUTO, mismatch_d=mm_d, **d))
-        auto_pair = pair and N >= 10                                  # K1 keeps N = 9
+        auto_pair = pair
         want = _cabi.KERNEL_PAIR if auto_pair else _cabi.KERNEL_SMALL
         if not auto_pair and (N > _cabi.MAX_MODES_SMALL or L > 1 or use_coef):
             want = _cabi.KERNEL_STRUCT if N + L <= 64 else _cabi.KERNEL_PANEL    # K4 takes over where K3 ends
