@@ -77,10 +77,10 @@ extern "C" {
 #define QNMFIT_KERNEL_PANEL   4      /* K4: structured QR, blocked (compact WY) with the
                                         trailing update on the FP64 tensor cores (DMMA);
                                         any n_modes <= 64 whose tile fits shared memory */
-#define QNMFIT_KERNEL_PAIR    5      /* K1p: n_series == 1, 9 <= n_modes <= 16: K1 with the
-                                        columns of a row slice split over 2 or 4 lanes  */
+#define QNMFIT_KERNEL_PAIR    5      /* K1p: n_series == 1, 9 <= n_modes <= 24: K1 with the
+                                        columns of a row slice split over 2, 4 or 8 lanes */
 #define QNMFIT_MIN_MODES_PAIR 9
-#define QNMFIT_MAX_MODES_PAIR 16
+#define QNMFIT_MAX_MODES_PAIR 24
 
 typedef struct qnmfit_ctx qnmfit_ctx;
 

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libqnmfit.so")
 
 ABI_VERSION = 6
 MAX_MODES_SMALL = 12
-MIN_MODES_PAIR, MAX_MODES_PAIR = 9, 16
+MIN_MODES_PAIR, MAX_MODES_PAIR = 9, 24
 MAX_MODES = 64
 MAX_PEERS = 8
 

@@ -188,7 +188,7 @@ fit_general_kernel(const __grid_constant__ FitParams p, const int TR, const int 
                 dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, s));
             }
             const double dim = (double)(Mrows > N ? Mrows : N);
-            if (!(dmin > QNMFIT_RANK_PREFILTER * QNMFIT_EPS * dim * dmax)) {   // rare: confirm (qnmfit_common.cuh)
+            if (!(dmin > rank_prefilter(N) * QNMFIT_EPS * dim * dmax)) {   // rare: confirm (qnmfit_common.cuh)
                 if (rank_suspect_warp([&](int j, int k) { return sm.R[j * (N + 1) + k]; }, [&](int j) { return dg[j]; },
                                       N, dim, sm.Cv, lane))
                     status |= QNMFIT_ST_RANK_DEFICIENT_;

@@ -1,4 +1,4 @@
-// fit_pair.cuh — K1p: single-series fits with 9 .. 16 columns, columns split over lanes.
+// fit_pair.cuh — K1p: single-series fits with 9 .. 24 columns, columns split over lanes.
 //
 // Same algorithm and the same reference lines as K1 (fit_small.cuh: sequential TSQR of the
 // lane's rows in register blocks, R-combine tree, back-substitution, mismatch from the
@@ -6,7 +6,7 @@
 // holds what.  K1 gives every lane ALL N + 1 columns of its rows, and beyond eight columns
 // that no longer fits: the register block shrinks to three and two rows, the per-lane factor
 // (N (N+1) / 2 complex in shared memory) cuts the CTA to 160 lanes, and the N = 12 instance
-// spills.  Here a row slice is owned by a GROUP of CS adjacent lanes (CS = 2 or 4) and lane h
+// spills.  Here a row slice is owned by a GROUP of CS adjacent lanes (CS = 2, 4 or 8) and lane h
 // of the group holds only the columns k with (N - k) mod CS == h (k = N: the right-hand side),
 // in "slots" s = (N - k) / CS counted from the right-hand side backwards:
 //
@@ -30,9 +30,17 @@
 #include "qnmfit_common.cuh"
 #include "fit_small.cuh"     // SmallLane, SmallAcc, small_fast_finalize, small_finalize, SMALL_STAGE_PAD
 
+// Once-per-fit stages are real calls: their register needs must not perturb the allocation
+// of the block loop (with them inlined, the N = 13, 14 instances spilled ~100 B inside it).
+#ifndef QNMFIT_HOSTSIM
+#define PAIR_COLD static __device__ __noinline__
+#else
+#define PAIR_COLD static inline
+#endif
+
 template <int N, int CS>
 struct PairLayout {
-    static_assert(CS == 2 || CS == 4, "2 or 4 lanes per row slice");
+    static_assert(CS == 2 || CS == 4 || CS == 8, "2, 4 or 8 lanes per row slice");
     static constexpr int S = (N + 1 + CS - 1) / CS;            // slots (columns) per lane
     // frequency tables: one row of N entries per fit behind CS - 1 leading entries (and one
     // trailing), so that slot s of lane h — column N - CS s - h, which may be the data column N
@@ -330,11 +338,120 @@ QF_HD void pair_tree_block(const PairSmem<N, CS, THREADS> &sm, int tid, int pt, 
     }
 }
 
+// "numpy MAY truncate a singular value here" (qnmfit_common.cuh), decided by the lanes of the fit
+// together: the estimate of s_min by inverse iteration on R^H R, as rank_suspect_warp, with the
+// iteration vector spread over the fit's lanes_per_fit lanes (lane lf holds entries lf,
+// lf + lpf, ...) and both triangular solves column by column — the owner of an entry finishes
+// it, a width-lpf shuffle broadcasts it, every lane updates its own entries.  Called by ALL
+// lanes of the warp (uniform control flow); the result is uniform within a fit.  The serial
+// form (lane 0 alone, rank_suspect_serial) cost 24 % of the N = 16 kernel once the prefilter
+// sent every fit of that size here.
+template <int N, int CS, int THREADS>
+PAIR_COLD bool pair_rank_suspect(const FitParams &p, const PairSmem<N, CS, THREADS> &sm, const SmallLane &L, int tid)
+{
+    typedef PairLayout<N, CS> LY;
+    constexpr int ME = (N + CS - 1) / CS;              // entries per lane at the smallest lanes_per_fit (= CS)
+    const unsigned full = 0xffffffffu;
+    const int lpf = p.lanes_per_fit;
+    const double2 *R0 = sm.R + (tid - L.lf);           // lane 0 of the fit: its group holds the final factor
+    auto Rat = [&](int j, int k) {                     // R[j][k], j <= k < N
+        const int dd = N - k;
+        return R0[(LY::base(dd / CS) + j) * THREADS + dd % CS];
+    };
+    const int M = L.re - L.rb;
+    const double dim = (double)(M > N ? M : N);
+    double dmax = 0.0, dmin = 1e300, frob2 = 0.0;
+    bool zero_diag = false;
+    double inv[ME];
+    double2 v[ME];
+    int col_off[ME], row_off[ME];                      // entry k = lf + m lpf of this lane: R[j][k] = R0[col_off + j THREADS],
+    const double x0 = 1.0 / sqrt((double)N);           //                                    R[k][c] = R0[off(c) + row_off]
+#pragma unroll
+    for (int m = 0; m < ME; ++m) {
+        inv[m] = 0.0; v[m] = make_double2(0.0, 0.0);
+        const int k = L.lf + m * lpf, dd = N - (k < N ? k : N - 1);
+        col_off[m] = LY::base(dd / CS) * THREADS + dd % CS;
+        row_off[m] = (k < N ? k : 0) * THREADS;
+    }
+#pragma unroll 1
+    for (int j = 0; j < N; ++j) {
+        const double dj = Rat(j, j).x;
+        const double a = fabs(dj);
+        dmax = a > dmax ? a : dmax;
+        dmin = a < dmin ? a : dmin;
+        zero_diag |= (dj == 0.0);
+#pragma unroll
+        for (int m = 0; m < ME; ++m)
+            if (j == L.lf + m * lpf) { inv[m] = 1.0 / dj; v[m] = make_double2(x0, 0.0); }
+    }
+    const bool need = L.fit >= 0 && !(dmin > rank_prefilter(N) * QNMFIT_EPS * dim * dmax);
+    if (!__any_sync(full, need)) return false;
+    // ||R||_F^2: each lane its own columns
+#pragma unroll 1
+    for (int k = L.lf; k < N; k += lpf)
+        for (int j = 0; j <= k; ++j) {
+            const double2 r = Rat(j, k);
+            frob2 = fma(r.x, r.x, frob2);
+            frob2 = fma(r.y, r.y, frob2);
+        }
+    for (int s = 1; s < lpf; s <<= 1) frob2 += __shfl_xor_sync(full, frob2, s);
+    double nz = 1.0;
+    bool bad = zero_diag;
+#pragma unroll 1
+    for (int it = 0; it < 3; ++it) {
+#pragma unroll 1
+        for (int j = 0; j < N; ++j) {                  // R^H y = x, column by column
+            double sx = 0.0, sy = 0.0;
+#pragma unroll
+            for (int m = 0; m < ME; ++m)
+                if (j == L.lf + m * lpf) { v[m].x *= inv[m]; v[m].y *= inv[m]; sx = v[m].x; sy = v[m].y; }
+            const double yx = __shfl_sync(full, sx, j % lpf, lpf), yy = __shfl_sync(full, sy, j % lpf, lpf);
+#pragma unroll
+            for (int m = 0; m < ME; ++m) {
+                const int k = L.lf + m * lpf;
+                if (k > j && k < N) {                  // x_k -= conj(R_jk) y_j
+                    const double2 r = R0[col_off[m] + j * THREADS];
+                    v[m].x = fma(-r.x, yx, v[m].x); v[m].x = fma(-r.y, yy, v[m].x);
+                    v[m].y = fma(-r.x, yy, v[m].y); v[m].y = fma(r.y, yx, v[m].y);
+                }
+            }
+        }
+        double n2 = 0.0;
+#pragma unroll 1
+        for (int k = N - 1; k >= 0; --k) {             // R z = y, column by column
+            double sx = 0.0, sy = 0.0;
+#pragma unroll
+            for (int m = 0; m < ME; ++m)
+                if (k == L.lf + m * lpf) { v[m].x *= inv[m]; v[m].y *= inv[m]; sx = v[m].x; sy = v[m].y; }
+            const double zx = __shfl_sync(full, sx, k % lpf, lpf), zy = __shfl_sync(full, sy, k % lpf, lpf);
+            n2 = fma(zx, zx, n2);
+            n2 = fma(zy, zy, n2);
+            const int koff = LY::base((N - k) / CS) * THREADS + (N - k) % CS;      // column k (uniform)
+#pragma unroll
+            for (int m = 0; m < ME; ++m) {
+                const int j = L.lf + m * lpf;
+                if (j < k) {                           // y_j -= R_jk z_k
+                    const double2 r = R0[koff + row_off[m]];
+                    v[m].x = fma(-r.x, zx, v[m].x); v[m].x = fma(r.y, zy, v[m].x);
+                    v[m].y = fma(-r.x, zy, v[m].y); v[m].y = fma(-r.y, zx, v[m].y);
+                }
+            }
+        }
+        nz = sqrt(n2);
+        if (!(nz < 1e300)) bad = true;                 // overflow / NaN: as singular as it gets
+        const double sc = bad ? 0.0 : 1.0 / nz;
+#pragma unroll
+        for (int m = 0; m < ME; ++m) { v[m].x *= sc; v[m].y *= sc; }
+    }
+    const double cut = QNMFIT_RANK_MARGIN * QNMFIT_EPS * dim;
+    return need && (bad || !(1.0 / nz > cut * cut * frob2));
+}
+
 // Back-substitution by lane 0 of the fit (it reads all CS lanes' columns of the factor);
 // leaves C in the right-hand-side entries of lane 0.
 template <int N, int CS, int THREADS>
-QF_HD void pair_backsub(const FitParams &p, const PairSmem<N, CS, THREADS> &sm, const SmallLane &L, int tid,
-                        int &status, SmallAcc &acc)
+PAIR_COLD void pair_backsub(const FitParams &p, const PairSmem<N, CS, THREADS> &sm, const SmallLane &L, int tid,
+                        const bool suspect, int &status, SmallAcc &acc)
 {
     typedef PairLayout<N, CS> LY;
     if (L.fit < 0 || L.lf != 0) return;
@@ -342,17 +459,7 @@ QF_HD void pair_backsub(const FitParams &p, const PairSmem<N, CS, THREADS> &sm, 
     const double2 *R0 = sm.R + tid;
     auto Roff = [&](int j, int k) { return R0[LY::entry(j, k) * THREADS + LY::lane_of(k)]; };
     auto Rdiag = [&](int j) { return R0[LY::entry(j, j) * THREADS + LY::lane_of(j)].x; };
-    double dmax = 0.0, dmin = 1e300;
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-        const double a = fabs(Rdiag(j));
-        dmax = a > dmax ? a : dmax;
-        dmin = a < dmin ? a : dmin;
-    }
-    const double dim = (double)(M > N ? M : N);
-    if (!(dmin > QNMFIT_RANK_PREFILTER * QNMFIT_EPS * dim * dmax)) {
-        if (rank_suspect_serial<N>(Roff, Rdiag, dim)) status |= QNMFIT_ST_RANK_DEFICIENT_;
-    }
+    if (suspect) status |= QNMFIT_ST_RANK_DEFICIENT_;
     if (M <= N) status |= QNMFIT_ST_UNDERDETERMINED_;
     if (p.R) {
         double2 *Rout = p.R + (long long)L.fit * N * (N + 1);
@@ -421,7 +528,7 @@ QF_HD void pair_fast_partials(const FitParams &p, const PairSmem<N, CS, THREADS>
 // Second pass (general path): model rows and the trapezoid-weighted inner products, one row
 // at a time; the CS lanes of a group take contiguous parts of the group's rows.
 template <int N, int CS, int THREADS>
-QF_HD void pair_eval(const FitParams &p, const PairSmem<N, CS, THREADS> &sm, const SmallLane &L, const int h,
+PAIR_COLD void pair_eval(const FitParams &p, const PairSmem<N, CS, THREADS> &sm, const SmallLane &L, const int h,
                      int tid, double (&sums)[4])
 {
     typedef PairLayout<N, CS> LY;
@@ -545,7 +652,8 @@ __global__ void __launch_bounds__(THREADS, 1) fit_pair_kernel(const __grid_const
             if (live && h == 0) acc.res2 += r2;
         }
         __syncwarp();
-        pair_backsub<N, CS, THREADS>(p, sm, L, tid, status, acc);
+        const bool suspect = pair_rank_suspect<N, CS, THREADS>(p, sm, L, tid);
+        pair_backsub<N, CS, THREADS>(p, sm, L, tid, suspect, status, acc);
         __syncwarp();
     }
     if (p.fast_mismatch) {

@@ -705,7 +705,7 @@ QF_HD void small_backsub(const FitParams &p, const SmallSmem<N, THREADS> &sm, co
         dmin = a < dmin ? a : dmin;
     }
     const double dim = (double)(M > N ? M : N);
-    if (!(dmin > QNMFIT_RANK_PREFILTER * QNMFIT_EPS * dim * dmax)) {
+    if (!(dmin > rank_prefilter(N) * QNMFIT_EPS * dim * dmax)) {
         // rare: confirm with an estimate of the smallest singular value (qnmfit_common.cuh)
         const double *Rd = sm.Rd + tid;
         const double2 *Ro = sm.Ro + tid;

@@ -298,7 +298,7 @@ __device__ __forceinline__ void struct_finish(const FitParams &p, const SM &sm, 
                 dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, s));
             }
             const double dim = (double)(Mrows > N ? Mrows : N);
-            if (!(dmin > QNMFIT_RANK_PREFILTER * QNMFIT_EPS * dim * dmax)) {   // rare: confirm (qnmfit_common.cuh)
+            if (!(dmin > rank_prefilter(N) * QNMFIT_EPS * dim * dmax)) {   // rare: confirm (qnmfit_common.cuh)
                 if (rank_suspect_warp([&](int j, int k) { return Rf.at(j, k); }, [&](int j) { return dgf[j]; }, N, dim,
                                       sm.Cv, lane))
                     status |= QNMFIT_ST_RANK_DEFICIENT_;

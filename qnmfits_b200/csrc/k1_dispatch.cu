@@ -61,29 +61,37 @@ cudaError_t k1_launch(int N, bool staged, int grid, int block, size_t smem, cuda
     return cudaErrorInvalidDeviceFunction;
 }
 
-// ---- K1p (k1p_inst.cu, two parts) -------------------------------------------------------------
+// ---- K1p (k1p_inst.cu, K1P_PARTS parts) -------------------------------------------------------
 #define K1P_DECL(P)                                                                                  \
     size_t k1p_smem_bytes_part##P(int N, int fpc, int stage_rows);                                   \
     const void *k1p_kernel_ptr_part##P(int N, bool staged);                                          \
     cudaError_t k1p_launch_part##P(int N, bool staged, int grid, int block, size_t smem, cudaStream_t st, \
                                    const FitParams &p);
-K1P_DECL(0) K1P_DECL(1)
+K1P_DECL(0) K1P_DECL(1) K1P_DECL(2) K1P_DECL(3) K1P_DECL(4) K1P_DECL(5) K1P_DECL(6) K1P_DECL(7) K1P_DECL(8) K1P_DECL(9)
+static_assert(K1P_PARTS == 10 && k1p_part_of(K1P_MAX_N) == 9, "one K1P_DECL / table entry per part");
+
+typedef size_t (*k1p_smem_fn)(int, int, int);
+typedef const void *(*k1p_ptr_fn)(int, bool);
+typedef cudaError_t (*k1p_launch_fn)(int, bool, int, int, size_t, cudaStream_t, const FitParams &);
+#define K1P_TABLE(fn) { fn##_part0, fn##_part1, fn##_part2, fn##_part3, fn##_part4, fn##_part5, fn##_part6, fn##_part7, fn##_part8, fn##_part9 }
+static const k1p_smem_fn k1p_smem_table[K1P_PARTS] = K1P_TABLE(k1p_smem_bytes);
+static const k1p_ptr_fn k1p_ptr_table[K1P_PARTS] = K1P_TABLE(k1p_kernel_ptr);
+static const k1p_launch_fn k1p_launch_table[K1P_PARTS] = K1P_TABLE(k1p_launch);
 
 size_t k1p_smem_bytes(int N, int fpc, int stage_rows)
 {
     if (N < K1P_MIN_N || N > K1P_MAX_N) return (size_t)-1;
-    return N <= 12 ? k1p_smem_bytes_part0(N, fpc, stage_rows) : k1p_smem_bytes_part1(N, fpc, stage_rows);
+    return k1p_smem_table[k1p_part_of(N)](N, fpc, stage_rows);
 }
 
 const void *k1p_kernel_ptr(int N, bool staged)
 {
     if (N < K1P_MIN_N || N > K1P_MAX_N) return nullptr;
-    return N <= 12 ? k1p_kernel_ptr_part0(N, staged) : k1p_kernel_ptr_part1(N, staged);
+    return k1p_ptr_table[k1p_part_of(N)](N, staged);
 }
 
 cudaError_t k1p_launch(int N, bool staged, int grid, int block, size_t smem, cudaStream_t st, const FitParams &p)
 {
     if (N < K1P_MIN_N || N > K1P_MAX_N) return cudaErrorInvalidDeviceFunction;
-    return N <= 12 ? k1p_launch_part0(N, staged, grid, block, smem, st, p)
-                   : k1p_launch_part1(N, staged, grid, block, smem, st, p);
+    return k1p_launch_table[k1p_part_of(N)](N, staged, grid, block, smem, st, p);
 }

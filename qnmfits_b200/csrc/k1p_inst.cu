@@ -1,10 +1,11 @@
-// k1p_inst.cu — instances of K1p (fit_pair.cuh), N = 9 .. 16.  Compiled twice with
-// -DK1P_PART=0 (N = 9-12) and 1 (N = 13-16) so that the unrolled kernels build in parallel.
+// k1p_inst.cu — instances of K1p (fit_pair.cuh), N = 9 .. 24.  Compiled ten times with
+// -DK1P_PART=0..9 (N = 9-12, 13-16, then one column count per part: 17 .. 24) so that the
+// unrolled kernels build in parallel (kernels.h: k1p_part_of).
 #include "kernels.h"
 #include "fit_pair.cuh"
 
 #ifndef K1P_PART
-#error "compile with -DK1P_PART=0..1"
+#error "compile with -DK1P_PART=0..9"
 #endif
 
 typedef void (*pair_kernel_t)(const FitParams);
@@ -24,11 +25,13 @@ static pair_kernel_t pair_kernel(int N, bool staged)
     case 10: return pair_kernel_for<10>(staged);
     case 11: return pair_kernel_for<11>(staged);
     case 12: return pair_kernel_for<12>(staged);
-#else
+#elif K1P_PART == 1
     case 13: return pair_kernel_for<13>(staged);
     case 14: return pair_kernel_for<14>(staged);
     case 15: return pair_kernel_for<15>(staged);
     case 16: return pair_kernel_for<16>(staged);
+#else
+    case K1P_PART + 15: return pair_kernel_for<K1P_PART + 15>(staged);
 #endif
     }
     return nullptr;
@@ -52,11 +55,13 @@ size_t K1P_CAT(k1p_smem_bytes_part, K1P_PART)(int N, int fpc, int stage_rows)
     case 10: return pair_smem_bytes_for<10>(fpc, stage_rows);
     case 11: return pair_smem_bytes_for<11>(fpc, stage_rows);
     case 12: return pair_smem_bytes_for<12>(fpc, stage_rows);
-#else
+#elif K1P_PART == 1
     case 13: return pair_smem_bytes_for<13>(fpc, stage_rows);
     case 14: return pair_smem_bytes_for<14>(fpc, stage_rows);
     case 15: return pair_smem_bytes_for<15>(fpc, stage_rows);
     case 16: return pair_smem_bytes_for<16>(fpc, stage_rows);
+#else
+    case K1P_PART + 15: return pair_smem_bytes_for<K1P_PART + 15>(fpc, stage_rows);
 #endif
     }
     return (size_t)-1;

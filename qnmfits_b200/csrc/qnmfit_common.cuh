@@ -216,9 +216,13 @@ QF_HD void note_status(const FitParams &p, int fit, int status)
 
 // numpy.linalg.lstsq truncates singular values below eps * max(M, N) * s_max
 // (numpy/linalg/_linalg.py:2553).  The kernels decide "numpy MAY truncate here" in two steps:
-//   1. prefilter on the diagonal of R: min |R_jj| <= PREFILTER * eps * max(M, N) * max |R_jj|.
-//      min/max of the diagonal of an unpivoted QR sits above s_min / s_max (measured up to 684x
-//      on overtone ladders), hence the generous factor;
+//   1. prefilter on the diagonal of R: min |R_jj| <= prefilter(N) * eps * max(M, N) * max |R_jj|.
+//      min/max of the diagonal of an unpivoted QR sits above s_min / s_max — by up to 684x on
+//      overtone ladders of up to 12 columns, but the gap grows with the column count (1.7e5 at
+//      19 columns, tests/test_gpu_parity.py::test_pair_kernel_many_fits_windows_series_and_eval;
+//      2.8e4 on random label sets of 12 .. 15 columns, 1.5e5 at 20 .. 23; the bound is 2^(N-1))
+//      — hence 1e5 up to eight columns and a factor 4 per column beyond, which from about
+//      fourteen columns on sends every fit to step 2;
 //   2. for the fits that pass it, an estimate of s_min by three steps of inverse iteration on
 //      R^H R (two triangular solves each, start vector of ones; the estimate converges to
 //      s_min from above) against MARGIN * eps * max(M, N) * ||R||_F  (||R||_F >= s_max).
@@ -226,7 +230,11 @@ QF_HD void note_status(const FitParams &p, int fit, int status)
 // values of the exported factor and completes numpy's minimum-norm answer (qnmfits.py,
 // _minimum_norm_from_factor).  Fits that are not flagged are full rank by numpy's criterion
 // with a margin of >= MARGIN in s_min.
-#define QNMFIT_RANK_PREFILTER 1.0e4
+#define QNMFIT_RANK_PREFILTER 1.0e5
+QF_HD double rank_prefilter(int n_modes)
+{
+    return n_modes <= 8 ? QNMFIT_RANK_PREFILTER : ldexp(QNMFIT_RANK_PREFILTER, 2 * (n_modes - 8));
+}
 #define QNMFIT_RANK_MARGIN 8.0
 #define QNMFIT_EPS 2.220446049250313e-16
 
@@ -328,11 +336,18 @@ QF_DEV double warp_sum(double v)
     return v;
 }
 
-// The same estimate computed by one warp (K2 / K3: N up to 64, R in shared memory); x is a
-// scratch vector of N complex in shared memory.  All 32 lanes call it; the result is uniform.
+// The same estimate computed by one warp (K2 / K3 / K4: N up to 64, R in shared memory).  All
+// 32 lanes call it; the result is uniform.  Lane l holds entries l and l + 32 of the iteration
+// vector in registers and both triangular solves run column by column: the owner of entry j
+// finishes it (one multiplication by the reciprocal diagonal), broadcasts it with a shuffle,
+// and every lane updates its own entries with one complex FMA — no reduction per step (the
+// first form summed a row per step over the warp: two five-level butterflies and a division
+// for each of the 6 N steps, 75 us at N = 40).  `x` (scratch in shared memory) is not used.
 template <class RF, class DF>
 QF_DEV bool rank_suspect_warp(const RF &R, const DF &D, int N, double dim, double2 *x, int lane)
 {
+    (void)x;
+    const unsigned full = 0xffffffffu;
     double frob2 = 0.0;
     bool zero_diag = false;
     for (int j = 0; j < N; ++j) {
@@ -347,47 +362,52 @@ QF_DEV bool rank_suspect_warp(const RF &R, const DF &D, int N, double dim, doubl
     }
     if (zero_diag) return true;
     frob2 = warp_sum(frob2);
+    const int k0 = lane, k1 = lane + 32;
+    const bool has0 = k0 < N, has1 = k1 < N;
+    const double inv0 = has0 ? 1.0 / D(k0) : 0.0, inv1 = has1 ? 1.0 / D(k1) : 0.0;
     const double x0 = 1.0 / sqrt((double)N);
-    for (int j = lane; j < N; j += 32) x[j] = make_double2(x0, 0.0);
-    __syncwarp();
+    double2 v0 = make_double2(has0 ? x0 : 0.0, 0.0), v1 = make_double2(has1 ? x0 : 0.0, 0.0);
     double nz = 1.0;
     for (int it = 0; it < 3; ++it) {
-        for (int j = 0; j < N; ++j) {                // R^H y = x
-            double ax = 0.0, ay = 0.0;
-            for (int i = lane; i < j; i += 32) {
-                const double2 r = R(i, j), xi = x[i];
-                ax = fma(r.x, xi.x, ax); ax = fma(r.y, xi.y, ax);
-                ay = fma(r.x, xi.y, ay); ay = fma(-r.y, xi.x, ay);
+        for (int j = 0; j < N; ++j) {                // R^H y = x, column by column
+            if (j == k0) { v0.x *= inv0; v0.y *= inv0; }
+            if (j == k1) { v1.x *= inv1; v1.y *= inv1; }
+            const double sx = j < 32 ? v0.x : v1.x, sy = j < 32 ? v0.y : v1.y;
+            const double yx = __shfl_sync(full, sx, j & 31), yy = __shfl_sync(full, sy, j & 31);
+            if (has0 && k0 > j) {                    // x_k -= conj(R_jk) y_j
+                const double2 r = R(j, k0);
+                v0.x = fma(-r.x, yx, v0.x); v0.x = fma(-r.y, yy, v0.x);
+                v0.y = fma(-r.x, yy, v0.y); v0.y = fma(r.y, yx, v0.y);
             }
-            ax = warp_sum(ax); ay = warp_sum(ay);
-            if (lane == 0) {
-                const double inv = 1.0 / D(j);
-                x[j] = make_double2((x[j].x - ax) * inv, (x[j].y - ay) * inv);
+            if (has1 && k1 > j) {
+                const double2 r = R(j, k1);
+                v1.x = fma(-r.x, yx, v1.x); v1.x = fma(-r.y, yy, v1.x);
+                v1.y = fma(-r.x, yy, v1.y); v1.y = fma(r.y, yx, v1.y);
             }
-            __syncwarp();
         }
         double n2 = 0.0;
-        for (int j = N - 1; j >= 0; --j) {           // R z = y
-            double ax = 0.0, ay = 0.0;
-            for (int k = j + 1 + lane; k < N; k += 32) {
-                const double2 r = R(j, k), xk = x[k];
-                ax = fma(r.x, xk.x, ax); ax = fma(-r.y, xk.y, ax);
-                ay = fma(r.x, xk.y, ay); ay = fma(r.y, xk.x, ay);
+        for (int k = N - 1; k >= 0; --k) {           // R z = y, column by column
+            if (k == k0) { v0.x *= inv0; v0.y *= inv0; }
+            if (k == k1) { v1.x *= inv1; v1.y *= inv1; }
+            const double sx = k < 32 ? v0.x : v1.x, sy = k < 32 ? v0.y : v1.y;
+            const double zx = __shfl_sync(full, sx, k & 31), zy = __shfl_sync(full, sy, k & 31);
+            n2 = fma(zx, zx, n2);
+            n2 = fma(zy, zy, n2);
+            if (k0 < k) {                            // y_j -= R_jk z_k
+                const double2 r = R(k0, k);
+                v0.x = fma(-r.x, zx, v0.x); v0.x = fma(r.y, zy, v0.x);
+                v0.y = fma(-r.x, zy, v0.y); v0.y = fma(-r.y, zx, v0.y);
             }
-            ax = warp_sum(ax); ay = warp_sum(ay);
-            const double inv = 1.0 / D(j);
-            const double2 z = make_double2((x[j].x - ax) * inv, (x[j].y - ay) * inv);
-            __syncwarp();
-            if (lane == 0) x[j] = z;
-            __syncwarp();
-            n2 = fma(z.x, z.x, n2);
-            n2 = fma(z.y, z.y, n2);
+            if (k1 < k) {
+                const double2 r = R(k1, k);
+                v1.x = fma(-r.x, zx, v1.x); v1.x = fma(r.y, zy, v1.x);
+                v1.y = fma(-r.x, zy, v1.y); v1.y = fma(-r.y, zx, v1.y);
+            }
         }
         nz = sqrt(n2);
         if (!(nz < 1e300)) return true;
         const double sc = 1.0 / nz;
-        for (int j = lane; j < N; j += 32) x[j] = make_double2(x[j].x * sc, x[j].y * sc);
-        __syncwarp();
+        v0.x *= sc; v0.y *= sc; v1.x *= sc; v1.y *= sc;
     }
     const double cut = QNMFIT_RANK_MARGIN * QNMFIT_EPS * dim;
     return !(1.0 / nz > cut * cut * frob2);

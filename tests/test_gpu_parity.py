@@ -268,7 +268,7 @@ def _synthetic_stack(N, L, K_tot, seed, uniform=True):
 @pytest.mark.parametrize("N,L,use_coef", [(3, 2, True), (12, 1, False), (12, 1, True), (20, 5, True),
                                            (40, 21, True), (63, 1, False), (9, 7, True), (9, 1, False),
                                            (10, 1, False), (11, 1, False), (16, 1, False), (13, 1, False), (14, 1, False),
-                                           (15, 1, False), (1, 1, True),
+                                           (15, 1, False), (17, 1, False), (20, 1, False), (24, 1, False), (1, 1, True),
                                            (8, 2, True), (17, 3, True), (44, 21, True), (64, 30, True)])
 def test_struct_kernel_vs_oracle_and_general_kernel(qf, eng, N, L, use_coef):
     """K4 (blocked structured QR on DMMA) and K3 (structured two-phase QR), uniform (fast
@@ -370,7 +370,7 @@ def test_struct_kernel_many_fits_windows_and_eval(qf, eng, kernel):
     np.testing.assert_allclose(eng.to_host(mm_eval), mm, rtol=0, atol=1e-12)
 
 
-@pytest.mark.parametrize("N", [9, 12, 14, 16])
+@pytest.mark.parametrize("N", [9, 12, 14, 16, 19, 24])
 def test_pair_kernel_many_fits_windows_series_and_eval(qf, eng, N):
     """K1p (columns of a row slice split over 2 / 4 lanes) on a sweep of 41 fits sharing warps:
     per-fit windows of different lengths (so lanes run blocks they have no rows for), per-fit
