@@ -289,7 +289,8 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
         // per CTA when that saves a wave or fills more SMs.  A seven-warp CTA takes 0.936 of
         // the time of an eight-warp one (measured, profiles/slab_time_r02.json).
 #ifndef K1_FORCE_CPS
-        const int alt = k1_alt_threads(N);
+        const char *no_alt = getenv("QNMFIT_K1_ALT_BLOCK");     // "0": developer A/B (tools/runs/r2_ab8.sh)
+        const int alt = no_alt && no_alt[0] == '0' ? 0 : k1_alt_threads(N);
         if (alt > 0 && alt % pl->lpf == 0) {
             const int fpc_alt = alt / pl->lpf;
             const size_t smem_alt = k1_smem_bytes(N, alt, fpc_alt, pl->staged ? stage_rows : 0);

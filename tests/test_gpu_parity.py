@@ -396,12 +396,21 @@ def test_pair_kernel_many_fits_windows_series_and_eval(qf, eng, N):
     mm_d = eng.empty((B,), torch.float64)
     st_d = eng.empty((B,), torch.int32)
     model_d = eng.empty((B, Kmax), torch.complex128)
-    eng.fit(eng.make_batch(C_d=C_d, mismatch_d=mm_d, model_d=model_d, model_stride=Kmax, status_d=st_d, **d))
+    R_d = eng.empty((B, N, N + 1), torch.complex128)
+    eng.fit(eng.make_batch(C_d=C_d, mismatch_d=mm_d, model_d=model_d, model_stride=Kmax, status_d=st_d, R_d=R_d, **d))
     mm_fast = eng.empty((B,), torch.float64)
     eng.fit(eng.make_batch(mismatch_d=mm_fast, uniform_weights=True, **d))
     mm_eval = eng.empty((B,), torch.float64)
     eng.evaluate(eng.make_batch(C_d=C_d, mismatch_d=mm_eval, **d))
     C, mm, model, st = eng.to_host(C_d), eng.to_host(mm_d), eng.to_host(model_d), eng.to_host(st_d)
+    R = eng.to_host(R_d)
+    for b in (0, 3, B - 1):                             # the exported factor [R | Q^H d]: what the host repair reads
+        sl = slice(rb[b], re[b])
+        A = np.exp(-1j * np.outer(times[sl] - t0[b], freq))
+        Ad = np.column_stack([A, data[which[b], sl]])
+        assert np.allclose(np.tril(R[b, :, :N], -1), 0) and np.allclose(np.diagonal(R[b, :, :N]).imag, 0)
+        gram, want = R[b].conj().T @ R[b], Ad.conj().T @ Ad
+        assert np.max(np.abs(gram[:N] - want[:N])) < 1e-9 * np.max(np.abs(want))
     checked = 0
     for b in range(B):
         sl = slice(rb[b], re[b])
