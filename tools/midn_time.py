@@ -7,6 +7,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
 import torch  # noqa: E402
 from qnmfits_b200 import workloads, _cabi  # noqa: E402
 from qnmfits_b200 import qnmfits as api  # noqa: E402
@@ -16,30 +17,25 @@ wl = workloads.config3(res=128)
 for N in [int(a) for a in sys.argv[1:]] or (8, 9, 10, 11, 12, 16, 24):
     modes = [(2, 2, n, 1) for n in range(min(N, 9))] + [(3, 2, n, 1) for n in range(max(0, N - 9))]
     sweep, shape = api._prepare_M_chi_grid(wl.times, wl.data, modes, wl.Mf_minmax, wl.chif_minmax, wl.t0, T=wl.T, res=128)
-    kernels = [_cabi.KERNEL_AUTO]
-    if os.environ.get("MIDN_ONLY_AUTO") == "1":
-        pass
-    elif N <= _cabi.MAX_MODES_SMALL:
-        kernels.append(_cabi.KERNEL_SMALL)
-    if len(kernels) > 1 or N > _cabi.MAX_MODES_SMALL:
+    kernels = [_cabi.KERNEL_AUTO]                       # MIDN_ONLY_AUTO=1: only what AUTO picks
+    if os.environ.get("MIDN_ONLY_AUTO") != "1":
+        if N <= _cabi.MAX_MODES_SMALL:
+            kernels.append(_cabi.KERNEL_SMALL)
         if _cabi.MIN_MODES_PAIR <= N <= _cabi.MAX_MODES_PAIR:
             kernels.append(_cabi.KERNEL_PAIR)
         if N >= 9:
             kernels.append(_cabi.KERNEL_STRUCT)
-    if os.environ.get("MIDN_ONLY_AUTO") == "1":
-        kernels = [_cabi.KERNEL_AUTO]
-    ref = None
+    ref, auto_kernel = None, None
     for kernel in kernels:
         sweep.batch.kernel = kernel
         plan = sweep.eng.ctx.plan(sweep.batch)
-        if kernel != _cabi.KERNEL_AUTO and plan.kernel == auto_kernel:
-            continue
         if kernel == _cabi.KERNEL_AUTO:
             auto_kernel = plan.kernel
+        elif plan.kernel == auto_kernel:
+            continue                                    # already timed as AUTO
         for _ in range(2):
             sweep.launch()
         torch.cuda.synchronize()
-        import numpy as np
         mm = sweep.fetch()[0]
         if ref is None:
             ref = mm
