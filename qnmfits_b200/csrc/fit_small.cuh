@@ -60,9 +60,14 @@ struct SmallLayout {
 template <int N, int THREADS>
 struct SmallSmem {
     double2 *Ro;        // [NP][THREADS]   off-diagonal + rhs
-    double2 *om;        // [N][fpc]        frequencies of the CTA's fits
-    double2 *qq;        // [N][fpc]        exp(-i w dt)
-    double2 *qw;        // [N][fpc]        exp(-i w dt) * (-i w)
+    // frequency tables: one row of TS entries per fit (TS odd: rows of different fits start in
+    // different banks), so that a lane reads column j at an immediate offset from its fit's row.
+    // The first layout, [N][fpc], cost one IMAD per access (column index x runtime fpc): 32 of
+    // the block loop's 66 IMADs at N = 8, each of which holds the issue port for a cycle.
+    static constexpr int TS = N | 1;
+    double2 *om;        // [fpc][TS]       frequencies of the CTA's fits
+    double2 *qq;        // [fpc][TS]       exp(-i w dt)
+    double2 *qw;        // [fpc][TS]       exp(-i w dt) * (-i w)
     const double2 *ds;  // [stage_rows]    staged data window (or global data)
     double *Rd;         // [N][THREADS]    real diagonal
     const double *ts;   // [stage_rows]    staged times (or global times)
@@ -72,7 +77,7 @@ struct SmallSmem {
     QF_MEMBOTH static size_t bytes(int fpc, int stage_rows)
     {
         if (stage_rows > 0) stage_rows += SMALL_STAGE_PAD;
-        return sizeof(double2) * (size_t)(SmallLayout<N>::NP * THREADS + 3 * N * fpc + stage_rows)
+        return sizeof(double2) * (size_t)(SmallLayout<N>::NP * THREADS + 3 * TS * fpc + stage_rows)
              + sizeof(double) * (size_t)(N * THREADS + stage_rows);
     }
     QF_MEM void carve(void *base, int fpc_, int stage_rows)
@@ -81,9 +86,9 @@ struct SmallSmem {
         fpc = fpc_;
         double2 *p2 = (double2 *)base;
         Ro = p2; p2 += SmallLayout<N>::NP * THREADS;
-        om = p2; p2 += N * fpc;
-        qq = p2; p2 += N * fpc;
-        qw = p2; p2 += N * fpc;
+        om = p2; p2 += TS * fpc;
+        qq = p2; p2 += TS * fpc;
+        qw = p2; p2 += TS * fpc;
         ds = p2; p2 += stage_rows;
         double *p1 = (double *)p2;
         Rd = p1; p1 += N * THREADS;
@@ -170,7 +175,7 @@ QF_HD void small_emit(const FitParams &p, const SmallSmem<N, THREADS> &sm, const
         if (direct) {
             if (rn < L.hi && i < MB - 1) {
 #pragma unroll
-                for (int j = 0; j < N; ++j) g.z[j] = design_entry(sm.om[j * sm.fpc + L.slot], tau_n);
+                for (int j = 0; j < N; ++j) g.z[j] = design_entry(sm.om[L.slot * sm.TS + j], tau_n);
             }
         } else {
             g.n += 1;
@@ -180,8 +185,8 @@ QF_HD void small_emit(const FitParams &p, const SmallSmem<N, THREADS> &sm, const
 #ifndef QNMFIT_ABL_NOGEN
 #pragma unroll
             for (int j = 0; j < N; ++j) {
-                const double2 q = sm.qq[j * sm.fpc + L.slot];
-                const double2 w = sm.qw[j * sm.fpc + L.slot];
+                const double2 q = sm.qq[L.slot * sm.TS + j];
+                const double2 w = sm.qw[L.slot * sm.TS + j];
                 const double2 qe = make_double2(fma(w.x, de, q.x), fma(w.y, de, q.y));
                 g.z[j] = c_mul(g.z[j], qe);
             }
@@ -202,7 +207,7 @@ QF_HD void small_generate(const FitParams &p, const SmallSmem<N, THREADS> &sm, c
     if ((direct || blk % ablk == 0) && row0 < L.hi) {
         g.tau_a = qf_sub_rn(sm.ts[row0 - sm.t_off], L.t0);
 #pragma unroll
-        for (int j = 0; j < N; ++j) g.z[j] = design_entry(sm.om[j * sm.fpc + L.slot], g.tau_a);
+        for (int j = 0; j < N; ++j) g.z[j] = design_entry(sm.om[L.slot * sm.TS + j], g.tau_a);
         g.eps = 0.0;
         g.n = 0;
     }
@@ -416,10 +421,10 @@ QF_HD void small_absorb(double2 (&B)[SmallLayout<N>::MB][N + 1], double *Rd, dou
 // row k+1 = row k * (q + q(-i w) de_k), de_k the deviation of that step from the nominal one.
 template <int N>
 QF_HD void small_fill_column(double2 (&B)[SmallLayout<N>::MB][N + 1], double2 (&z)[N], const double (&de)[SmallLayout<N>::MB], const double2 *qq,
-                             const double2 *qw, int fpc, int c)
+                             const double2 *qw, int c)
 {
 #ifndef QNMFIT_ABL_NOGEN
-    const double2 q = qq[c * fpc], w = qw[c * fpc];
+    const double2 q = qq[c], w = qw[c];
 #pragma unroll
     for (int i = 0; i < SmallLayout<N>::MB; ++i) {
         B[i][c] = z[c];
@@ -456,10 +461,9 @@ struct SmallRefill {
     double2 (&z)[N];
     const double (&de)[SmallLayout<N>::MB];
     const double2 *qq, *qw;
-    int fpc;
     QF_MEM void operator()(int j) const
     {
-        if (j >= S && j - S < H) small_fill_column<N>(B, z, de, qq, qw, fpc, j - S);
+        if (j >= S && j - S < H) small_fill_column<N>(B, z, de, qq, qw, j - S);
     }
 };
 
@@ -546,8 +550,7 @@ QF_HD void small_leaf_uniform(const FitParams &p, const SmallSmem<N, THREADS> &s
 {
     const double *ts = sm.ts - sm.t_off;
     const double2 *ds = sm.ds - sm.t_off + L.d_off;
-    const double2 *om = sm.om + L.slot, *qq = sm.qq + L.slot, *qw = sm.qw + L.slot;
-    const int fpc = sm.fpc;
+    const double2 *om = sm.om + L.slot * sm.TS, *qq = sm.qq + L.slot * sm.TS, *qw = sm.qw + L.slot * sm.TS;
     const double dt = p.dt_nominal, t0 = L.t0;
     constexpr int MB = SmallLayout<N>::MB;
     int ablk = (p.anchor_rows > 0 ? p.anchor_rows : QNMFIT_DEFAULT_ANCHOR_ROWS) / MB;
@@ -570,7 +573,7 @@ QF_HD void small_leaf_uniform(const FitParams &p, const SmallSmem<N, THREADS> &s
         const int nb = nfull - blk < ablk ? nfull - blk : ablk;
         double tau = qf_sub_rn(ts[row0], t0);
 #pragma unroll
-        for (int j = 0; j < N; ++j) z[j] = design_entry(om[j * fpc], tau);
+        for (int j = 0; j < N; ++j) z[j] = design_entry(om[j], tau);
         {   // deviations of the segment's first block; its first H columns
             const int rM = PADDED || row0 + MB < last ? row0 + MB : last;
             double tn[MB];
@@ -584,7 +587,7 @@ QF_HD void small_leaf_uniform(const FitParams &p, const SmallSmem<N, THREADS> &s
                 tau = tau_n;
             }
 #pragma unroll
-            for (int c = 0; c < H; ++c) small_fill_column<N>(B, z, de, qq, qw, fpc, c);
+            for (int c = 0; c < H; ++c) small_fill_column<N>(B, z, de, qq, qw, c);
         }
 #pragma unroll 1
         for (int b = 0; b < nb; ++b) {
@@ -598,7 +601,7 @@ QF_HD void small_leaf_uniform(const FitParams &p, const SmallSmem<N, THREADS> &s
             }
             // the remaining columns of this block, with this block's deviations ...
 #pragma unroll
-            for (int c = H; c < N; ++c) small_fill_column<N>(B, z, de, qq, qw, fpc, c);
+            for (int c = H; c < N; ++c) small_fill_column<N>(B, z, de, qq, qw, c);
             // ... then the next block's deviations
 #pragma unroll
             for (int i = 0; i < MB; ++i) {
@@ -607,7 +610,7 @@ QF_HD void small_leaf_uniform(const FitParams &p, const SmallSmem<N, THREADS> &s
                 tau = tau_n;
             }
             small_acc_rhs2<N>(B, acc.sdd, sdd1);
-            const SmallRefill<N> refill = {B, z, de, qq, qw, fpc};
+            const SmallRefill<N> refill = {B, z, de, qq, qw};
             small_absorb_hook<N, THREADS, 0>(B, sm.Rd + tid, sm.Ro + tid, refill);
             small_acc_rhs2<N>(B, acc.res2, res1);
             row0 += MB;
@@ -617,7 +620,7 @@ QF_HD void small_leaf_uniform(const FitParams &p, const SmallSmem<N, THREADS> &s
     if (row0 < L.hi) {   // ragged tail (fewer than MB rows): anchor, recurrence, zero rows beyond the lane's share
         double tau = qf_sub_rn(ts[row0], t0);
 #pragma unroll
-        for (int j = 0; j < N; ++j) z[j] = design_entry(om[j * fpc], tau);
+        for (int j = 0; j < N; ++j) z[j] = design_entry(om[j], tau);
         const double2 zero = make_double2(0.0, 0.0);
 #pragma unroll
         for (int i = 0; i < MB; ++i) {
@@ -629,7 +632,7 @@ QF_HD void small_leaf_uniform(const FitParams &p, const SmallSmem<N, THREADS> &s
             tau = tau_n;
 #pragma unroll
             for (int j = 0; j < N; ++j) {
-                const double2 q = qq[j * fpc], w = qw[j * fpc];
+                const double2 q = qq[j], w = qw[j];
                 B[i][j] = valid ? z[j] : zero;
                 z[j] = c_mul(z[j], make_double2(fma(w.x, de1, q.x), fma(w.y, de1, q.y)));
             }
@@ -846,7 +849,7 @@ QF_HD void small_fast_partials(const FitParams &p, const SmallSmem<N, THREADS> &
     const double tau_f = qf_sub_rn(sm.ts[L.rb - sm.t_off], L.t0);
     const double tau_l = qf_sub_rn(sm.ts[L.re - 1 - sm.t_off], L.t0);
     for (int j = L.lf; j < N; j += p.lanes_per_fit) {
-        const double2 w = sm.om[j * sm.fpc + L.slot];
+        const double2 w = sm.om[L.slot * sm.TS + j];
         const double2 C = sm.Ro[(j * N - j * (j - 1) / 2 + (N - j - 1)) * THREADS + t0lane];
         const double2 af = design_entry(w, tau_f), al = design_entry(w, tau_l);
         part[2] = fma(af.x, C.x, part[2]); part[2] = fma(-af.y, C.y, part[2]);
@@ -907,11 +910,11 @@ __global__ void __launch_bounds__(THREADS, 1) fit_small_kernel(const __grid_cons
         const int fit = cta_first + slot;
         if (fit < p.n_fits) {
             const double2 w = fit_omega(p, input_fit(p, fit), j);
-            sm.om[j * fpc + slot] = w;
+            sm.om[slot * sm.TS + j] = w;
             if (p.dt_nominal > 0.0) {
                 const double2 q = design_entry(w, p.dt_nominal);
-                sm.qq[j * fpc + slot] = q;
-                sm.qw[j * fpc + slot] = c_mul(q, make_double2(w.y, -w.x));
+                sm.qq[slot * sm.TS + j] = q;
+                sm.qw[slot * sm.TS + j] = c_mul(q, make_double2(w.y, -w.x));
             }
         }
     }

@@ -56,11 +56,11 @@ static void run(const qnmfit_batch *b, int lpf, bool eval)
             const int fit = cta * fpc + slot;
             if (fit < p.n_fits) {
                 const double2 w = fit_omega(p, fit, j);
-                sm.om[j * fpc + slot] = w;
+                sm.om[slot * sm.TS + j] = w;
                 if (p.dt_nominal > 0.0) {
                     const double2 q = design_entry(w, p.dt_nominal);
-                    sm.qq[j * fpc + slot] = q;
-                    sm.qw[j * fpc + slot] = c_mul(q, make_double2(w.y, -w.x));
+                    sm.qq[slot * sm.TS + j] = q;
+                    sm.qw[slot * sm.TS + j] = c_mul(q, make_double2(w.y, -w.x));
                 }
             }
         }
