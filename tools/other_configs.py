@@ -21,13 +21,17 @@ out = {}
 
 
 def timeit(fn, n=5):
+    """Median wall clock of n calls after two warm-up calls (the first prepares the sweep)."""
+    fn()
     fn()
     torch.cuda.synchronize()
-    t = time.perf_counter()
+    times = []
     for _ in range(n):
+        t = time.perf_counter()
         r = fn()
-    torch.cuda.synchronize()
-    return (time.perf_counter() - t) / n, r
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t)
+    return float(np.median(times)), r
 
 
 wl = workloads.config1()
@@ -50,7 +54,7 @@ out["cfg2"] = dict(gpu_ms=dt * 1e3, fits=1000, gpu_fits_per_s=1000 / dt, cpu_s_s
 
 wl = workloads.config4()
 dt, mm = timeit(lambda: qf.mismatch_t0_array(wl.times, wl.data, wl.modes, wl.Mf, wl.chif, wl.t0_array,
-                                             T_array=wl.T, spherical_modes=wl.spherical_modes), 3)
+                                             T_array=wl.T, spherical_modes=wl.spherical_modes), 9)
 t = time.perf_counter()
 idx = [0, 250, 499]
 want = orc.mismatch_t0_array(tables, wl.times, wl.data, wl.modes, wl.Mf, wl.chif, wl.t0_array[idx],
