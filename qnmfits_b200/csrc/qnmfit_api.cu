@@ -210,11 +210,14 @@ static int make_plan(qnmfit_ctx *ctx, const qnmfit_batch *b, Plan *pl)
     const bool panel_ok = !b->coef_rows && b->n_series <= 64
         && k4_smem_bytes(b->n_modes, b->n_series) <= (size_t)ctx->smem_optin;
     if (kernel == QNMFIT_KERNEL_AUTO) {
-        // K3 where it applies (N + L <= 64) unless QNMFIT_AUTO_PANEL=1, K4 beyond: K4's trailing
-        // update runs on the tensor cores, but its panel factorisation is not yet fast enough to
-        // beat K3 on the shapes both take
+        // K3 where it applies (N + L <= 64) except for the large stacked shapes, K4 there and
+        // beyond 64 columns (QNMFIT_AUTO_PANEL=1 / 0 forces K4 / K3 wherever both apply): K4's
+        // trailing update runs on the tensor cores, but its panel factorisation only pays off
+        // when the trailing matrix is wide
         const char *force = getenv("QNMFIT_AUTO_PANEL");
-        const bool prefer_panel = force && force[0] == '1';
+        // measured (profiles/k3_time_r02.json, k34_sweep_r02.json): K4 wins from about 36 columns
+        // with several stacked series on (cfg4: 2.50 against 2.66 ms), K3 below
+        const bool prefer_panel = force ? force[0] == '1' : (b->n_modes >= 36 && b->n_series >= 8);
         const char *no_pair = getenv("QNMFIT_AUTO_PAIR");     // "0": the choice before K1p existed
         const bool prefer_pair = pair_ok && b->n_modes >= K1P_AUTO_MIN_N && !(no_pair && no_pair[0] == '0');
         kernel = prefer_pair ? QNMFIT_KERNEL_PAIR
