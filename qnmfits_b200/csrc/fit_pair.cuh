@@ -29,6 +29,9 @@
 #pragma once
 #include "qnmfit_common.cuh"
 #include "fit_small.cuh"     // SmallLane, SmallAcc, small_fast_finalize, small_finalize, SMALL_STAGE_PAD
+#ifdef QNMFIT_HOSTSIM
+#include "hostsim_warp.h"    // tests/hostsim: the warp collectives, emulated with one fiber per lane
+#endif
 
 // Once-per-fit stages are real calls: their register needs must not perturb the allocation
 // of the block loop (with them inlined, the N = 13, 14 instances spilled ~100 B inside it).
@@ -142,14 +145,18 @@ QF_HD void pair_absorb(double2 (&B)[MB][PairLayout<N, CS>::S], double2 *Rt, cons
     for (int j = JSTART; j < N; ++j) {
         const int d = N - j, own = d % CS, sj = d / CS;       // column j: lane `own`, slot sj
         const int ST = (d + CS - 1) / CS;                     // slots that can hold a trailing column (k > j)
-        // ---- column j of the block and R_jj, from their owner
+        // ---- R_jj and column j of the block, from their owner.  R_jj is read in place, from the
+        // owner's shared memory, BEFORE the shuffles: the owner overwrites it further down, and
+        // only the shuffles order that store behind the other lanes' loads (the lock-step host
+        // emulation, which runs a lane from one collective to the next, caught the load sitting
+        // behind them).
+        const double r = Rt[(LY::base(sj) + j) * THREADS + (own - h)].x;
         double2 v[MB];
 #pragma unroll
         for (int i = 0; i < MB; ++i) {
             v[i].x = __shfl_sync(full, B[i][sj].x, own, CS);
             v[i].y = __shfl_sync(full, B[i][sj].y, own, CS);
         }
-        const double r = Rt[(LY::base(sj) + j) * THREADS + (own - h)].x;       // the owner's entry, read in place
         // ---- (A) column norm and the raw dot products v^H B_s of the trailing slots
         double sr[LY::S], si[LY::S];
         double sig0 = 1e-300, sig1 = 0.0;     // seed: an exactly zero column needs no branch (fit_small.cuh)
@@ -317,6 +324,12 @@ QF_HD void pair_tree_block(const PairSmem<N, CS, THREADS> &sm, int tid, int pt, 
 {
     typedef PairLayout<N, CS> LY;
     if constexpr (B0 < N) {
+        // The previous block ended with reflection N - 1, whose owner stored R_jj behind that
+        // reflection's shuffles; when this block starts at the same column (B0 = N - 1) the other
+        // lanes read that entry with no collective in between.  A converged warp executes the
+        // store first, but only a barrier makes that order a guarantee (found by the lock-step
+        // host emulation, which runs each lane from one collective to the next).
+        __syncwarp();
         double2 B[MB][LY::S];
 #pragma unroll
         for (int i = 0; i < MB; ++i) {
@@ -588,53 +601,32 @@ PAIR_COLD void pair_eval(const FitParams &p, const PairSmem<N, CS, THREADS> &sm,
     }
 }
 
-#ifndef QNMFIT_HOSTSIM
-template <int N, int CS, int MB, int THREADS, bool STAGED>
-__global__ void __launch_bounds__(THREADS, 1) fit_pair_kernel(const __grid_constant__ FitParams p)
+// Entry idx of the CTA's padded frequency tables (PairLayout::NT): the CTA fills idx = 0 .. fpc N + CS - 1.
+template <int N, int CS, int THREADS>
+QF_HD void pair_fill_tables(const FitParams &p, const PairSmem<N, CS, THREADS> &sm, int cta_first, int fpc, int idx)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    typedef PairLayout<N, CS> LY;
-    PairSmem<N, CS, THREADS> sm;
-    const int lpf = p.lanes_per_fit;
-    const int fpc = THREADS / lpf;
-    const int tid = threadIdx.x;
-    sm.carve(smem_raw, fpc, STAGED ? p.stage_rows : 0);
-    if (STAGED) {
-        double *ts_w = const_cast<double *>(sm.ts);
-        double2 *ds_w = const_cast<double2 *>(sm.ds);
-        for (int r = tid; r < p.stage_rows + SMALL_STAGE_PAD; r += THREADS) {
-            const int src = p.stage_begin + (r < p.stage_rows ? r : p.stage_rows - 1);
-            ts_w[r] = p.times[src];
-            ds_w[r] = p.data[src];
+    const int e = idx - (CS - 1);                 // entry of the [fpc][N] table, or padding
+    const int slot = e >= 0 ? e / N : 0, j = e - slot * N;
+    const int fit = cta_first + slot;
+    double2 w = make_double2(0.0, 0.0), q = w, qw = w;
+    if (e >= 0 && slot < fpc && fit < p.n_fits) {
+        w = fit_omega(p, input_fit(p, fit), j);
+        if (p.dt_nominal > 0.0) {
+            q = design_entry(w, p.dt_nominal);
+            qw = c_mul(q, make_double2(w.y, -w.x));
         }
-        sm.t_off = p.stage_begin;
-    } else {
-        sm.ts = p.times;
-        sm.ds = p.data;
-        sm.t_off = 0;
     }
-    const int cta_first = blockIdx.x * fpc;
-    for (int idx = tid; idx < fpc * N + CS; idx += THREADS) {
-        const int e = idx - (CS - 1);                 // entry of the [fpc][N] table, or padding
-        const int slot = e >= 0 ? e / N : 0, j = e - slot * N;
-        const int fit = cta_first + slot;
-        double2 w = make_double2(0.0, 0.0), q = w, qw = w;
-        if (e >= 0 && slot < fpc && fit < p.n_fits) {
-            w = fit_omega(p, input_fit(p, fit), j);
-            if (p.dt_nominal > 0.0) {
-                q = design_entry(w, p.dt_nominal);
-                qw = c_mul(q, make_double2(w.y, -w.x));
-            }
-        }
-        sm.om[idx] = w; sm.qq[idx] = q; sm.qw[idx] = qw;
-    }
-    const int safe_row = STAGED ? p.stage_begin : 0;
-    const SmallLane L = pair_lane_setup<CS>(p, blockIdx.x, tid, THREADS, !STAGED, MB, safe_row);
-    const int h = L.lf % CS;
-#pragma unroll 1
-    for (int e = 0; e < LY::E; ++e) sm.R[e * THREADS + tid] = make_double2(0.0, 0.0);
-    __syncthreads();
+    sm.om[idx] = w; sm.qq[idx] = q; sm.qw[idx] = qw;
+}
 
+// Everything a lane does once the CTA's shared memory is set up (tables filled, factors zeroed,
+// window staged).  Called by all lanes of a warp together: the kernel below, and the lock-step
+// host emulation of tests/hostsim.
+template <int N, int CS, int MB, int THREADS>
+QF_HD void pair_lane_body(const FitParams &p, const PairSmem<N, CS, THREADS> &sm, const SmallLane &L, int tid)
+{
+    const int lpf = p.lanes_per_fit;
+    const int h = L.lf % CS;
     int status = 0;
     SmallAcc acc;
     acc.sdd = acc.res2 = acc.cn2 = 0.0;
@@ -645,11 +637,9 @@ __global__ void __launch_bounds__(THREADS, 1) fit_pair_kernel(const __grid_const
         for (int s = 1; s < lpf / CS; s <<= 1) {            // R-combine over the fit's row groups
             __syncwarp();
             const bool live = L.fit >= 0 && (grp % (2 * s)) == 0;
-            double r2 = 0.0;
             SmallAcc tacc; tacc.res2 = 0.0;
             pair_tree_block<N, CS, MB, THREADS, 0>(sm, tid, live ? tid + s * CS : tid, h, live, tacc);
-            r2 = tacc.res2;
-            if (live && h == 0) acc.res2 += r2;
+            if (live && h == 0) acc.res2 += tacc.res2;
         }
         __syncwarp();
         const bool suspect = pair_rank_suspect<N, CS, THREADS>(p, sm, L, tid);
@@ -681,5 +671,39 @@ __global__ void __launch_bounds__(THREADS, 1) fit_pair_kernel(const __grid_const
         for (int q = 0; q < 4; ++q) sums[q] += __shfl_xor_sync(0xffffffffu, sums[q], s);
     }
     small_finalize(p, L, sums, status);
+}
+
+#ifndef QNMFIT_HOSTSIM
+template <int N, int CS, int MB, int THREADS, bool STAGED>
+__global__ void __launch_bounds__(THREADS, 1) fit_pair_kernel(const __grid_constant__ FitParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef PairLayout<N, CS> LY;
+    PairSmem<N, CS, THREADS> sm;
+    const int lpf = p.lanes_per_fit;
+    const int fpc = THREADS / lpf;
+    const int tid = threadIdx.x;
+    sm.carve(smem_raw, fpc, STAGED ? p.stage_rows : 0);
+    if (STAGED) {
+        double *ts_w = const_cast<double *>(sm.ts);
+        double2 *ds_w = const_cast<double2 *>(sm.ds);
+        for (int r = tid; r < p.stage_rows + SMALL_STAGE_PAD; r += THREADS) {
+            const int src = p.stage_begin + (r < p.stage_rows ? r : p.stage_rows - 1);
+            ts_w[r] = p.times[src];
+            ds_w[r] = p.data[src];
+        }
+        sm.t_off = p.stage_begin;
+    } else {
+        sm.ts = p.times;
+        sm.ds = p.data;
+        sm.t_off = 0;
+    }
+    for (int idx = tid; idx < fpc * N + CS; idx += THREADS)
+        pair_fill_tables<N, CS, THREADS>(p, sm, blockIdx.x * fpc, fpc, idx);
+    const SmallLane L = pair_lane_setup<CS>(p, blockIdx.x, tid, THREADS, !STAGED, MB, STAGED ? p.stage_begin : 0);
+#pragma unroll 1
+    for (int e = 0; e < LY::E; ++e) sm.R[e * THREADS + tid] = make_double2(0.0, 0.0);
+    __syncthreads();
+    pair_lane_body<N, CS, MB, THREADS>(p, sm, L, tid);
 }
 #endif  // !QNMFIT_HOSTSIM

@@ -1,6 +1,8 @@
 // hostsim.cpp — TEST HARNESS ONLY.  Compiles the K1 device code (fit_small.cuh) as
 // plain host C++ (-DQNMFIT_HOSTSIM) and runs the lanes of each CTA one after another,
-// phase by phase, exactly as the CUDA kernel orders them.  It lets the CPU-only test
+// phase by phase, exactly as the CUDA kernel orders them; and the K1p device code
+// (fit_pair.cuh), whose lanes exchange data with shuffles inside the block loop, with the 32
+// lanes of a warp in lock step (hostsim_warp.h: one fiber per lane).  It lets the CPU-only test
 // tier check the kernel's arithmetic (streamed TSQR, anchored recurrence, R-combine,
 // back-substitution, mismatch sums) against the oracle.  It is never loaded by the
 // qnmfits_b200 package.
@@ -13,6 +15,8 @@
 
 #include "qnmfit.h"
 #include "fit_small.cuh"
+#include "k1p_config.h"
+#include "fit_pair.cuh"
 
 #define HS_THREADS 256
 
@@ -120,6 +124,54 @@ static void run(const qnmfit_batch *b, int lpf, bool eval)
             small_finalize(p, lanes[tid], s4, status[tid]);
         }
     }
+}
+
+// K1p: the CTA's shared memory is set up serially, then each warp runs in lock step.
+#define HSP_THREADS 64
+template <int N>
+static void run_pair(const qnmfit_batch *b, int lpf, bool eval)
+{
+    constexpr int CS = k1p_cs_ct(N), MB = k1p_mb_ct(N);
+    typedef PairLayout<N, CS> LY;
+    static_assert(LY::E == k1p_entries_ct(N, CS), "k1p_config.h mirrors PairLayout::E");
+    FitParams p;
+    fill_params(b, lpf, eval, &p);
+    const int fpc = HSP_THREADS / lpf;
+    const int ctas = (b->n_fits + fpc - 1) / fpc;
+    std::vector<unsigned char> smem(PairSmem<N, CS, HSP_THREADS>::bytes(fpc, 0) + 64);
+    for (int cta = 0; cta < ctas; ++cta) {
+        PairSmem<N, CS, HSP_THREADS> sm;
+        sm.carve(smem.data(), fpc, 0);
+        sm.ts = p.times; sm.ds = p.data; sm.t_off = 0;
+        for (int idx = 0; idx < fpc * N + CS; ++idx) pair_fill_tables<N, CS, HSP_THREADS>(p, sm, cta * fpc, fpc, idx);
+        for (int e = 0; e < LY::E * HSP_THREADS; ++e) sm.R[e] = make_double2(0.0, 0.0);
+        for (int warp = 0; warp < HSP_THREADS / 32; ++warp)
+            hswarp::run_warp([&](int lane) {
+                const int tid = warp * 32 + lane;
+                const SmallLane L = pair_lane_setup<CS>(p, cta, tid, HSP_THREADS, true, MB, 0);
+                pair_lane_body<N, CS, MB, HSP_THREADS>(p, sm, L, tid);
+            });
+    }
+}
+
+// All pointers in *b are HOST pointers here.  Column counts: a sample of every configuration
+// (2 / 4 / 8 lanes per row slice, 4 / 5 / 6 / 8 rows per block).
+extern "C" int hostsim_fit_pair(const qnmfit_batch *b, int lpf, int eval)
+{
+    if (!b || b->struct_size != (int)sizeof(qnmfit_batch)) return QNMFIT_E_ABI;
+    if (b->n_series != 1) return QNMFIT_E_SHAPE;
+    if (lpf < 1 || lpf > 32 || (lpf & (lpf - 1)) || lpf < k1p_cs_ct(b->n_modes)) return QNMFIT_E_SHAPE;
+    switch (b->n_modes) {
+    case 9: run_pair<9>(b, lpf, eval); break;
+    case 11: run_pair<11>(b, lpf, eval); break;
+    case 12: run_pair<12>(b, lpf, eval); break;
+    case 14: run_pair<14>(b, lpf, eval); break;
+    case 16: run_pair<16>(b, lpf, eval); break;
+    case 19: run_pair<19>(b, lpf, eval); break;
+    case 24: run_pair<24>(b, lpf, eval); break;
+    default: return QNMFIT_E_SHAPE;
+    }
+    return 0;
 }
 
 extern "C" int hostsim_sizeof_batch(void) { return (int)sizeof(qnmfit_batch); }

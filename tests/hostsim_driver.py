@@ -17,6 +17,7 @@ def lib():
     if _hs is None:
         _hs = C.CDLL(os.path.join(ROOT, "tests", "hostsim", "libqnmfit_hostsim.so"))
         _hs.hostsim_fit_small.argtypes = [C.POINTER(_cabi.Batch), C.c_int, C.c_int]
+        _hs.hostsim_fit_pair.argtypes = [C.POINTER(_cabi.Batch), C.c_int, C.c_int]
     return _hs
 
 
@@ -27,7 +28,8 @@ def _p(a):
 def run(times, data, *, n_fits, n_modes, window, t0, lpf=4, eval_only=False, dt=None,
         anchor_rows=0, omega=None, omega_shared=False, table=None, mode_ptr=None, inv_Mf=None,
         delta_factor=None, n_chi=0, n_mf=0, first_fit=0, C_in=None, want_model=False,
-        uniform_weights=0, series_index=None):
+        uniform_weights=0, series_index=None, pair=False):
+    """``pair=True``: the K1p code (csrc/fit_pair.cuh), warps in lock step; otherwise K1."""
     times = np.ascontiguousarray(times, dtype=float)
     data = np.ascontiguousarray(data, dtype=complex)
     keep = [times, data]
@@ -82,6 +84,7 @@ def run(times, data, *, n_fits, n_modes, window, t0, lpf=4, eval_only=False, dt=
                     dt_nominal=float(dt), anchor_rows=anchor_rows, C=_p(Cbuf), mismatch=_p(mm),
                     residual=_p(res), R=_p(R), status=_p(st), model=_p(model),
                     model_stride=Mmax if want_model else 0, uniform_weights=int(uniform_weights), **kw)
-    rc = lib().hostsim_fit_small(C.byref(b), int(lpf), 1 if eval_only else 0)
+    entry = lib().hostsim_fit_pair if pair else lib().hostsim_fit_small
+    rc = entry(C.byref(b), int(lpf), 1 if eval_only else 0)
     assert rc == 0, rc
     return dict(C=Cbuf, mismatch=mm, residual=res, R=R, status=st, model=model, dt=dt)

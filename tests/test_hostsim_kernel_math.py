@@ -252,3 +252,77 @@ def test_wider_factors_use_shorter_blocks(qf, oracle_tables, N):
                  omega=w.reshape(1, -1), omega_shared=True, uniform_weights=1)
     want = orc.mismatch_t0_array(oracle_tables, wl.times, wl.data, modes, 0.95, 0.69, t0s)
     np.testing.assert_allclose(out["mismatch"], want, rtol=0, atol=1e-10)
+
+
+# ---------------------------------------------------------------------------------------
+# K1p (csrc/fit_pair.cuh): the lanes of a row slice exchange block columns with shuffles inside
+# the block loop, so the harness runs each warp in lock step (tests/hostsim/hostsim_warp.h), which
+# also checks that every lane of a warp executes the same sequence of collectives.
+
+def _damped_stack(N, S, K_tot, seed):
+    rng = np.random.default_rng(seed)
+    times = np.arange(K_tot) * 0.1
+    freq = np.linspace(-0.1 * N, 0.1 * N, N) + 0.013 * rng.standard_normal(N) - 1j * (0.02 + 0.06 * rng.random(N))
+    C = rng.standard_normal((S, N)) + 1j * rng.standard_normal((S, N))
+    data = np.exp(-1j * np.outer(times - times[3], freq)) @ C.T
+    data = data.T + 1e-5 * (rng.standard_normal((S, K_tot)) + 1j * rng.standard_normal((S, K_tot)))
+    return times, data, freq
+
+
+@pytest.mark.parametrize("N,lpf", [(9, 2), (9, 8), (11, 4), (12, 4), (14, 8), (16, 4), (19, 16), (24, 8), (24, 32)])
+def test_pair_kernel_emulated_in_lock_step_vs_numpy(N, lpf):
+    """Seven fits sharing warps: windows of different lengths (lanes run blocks they have no rows
+    for), per-fit start times and data series; second pass with model output, fast mismatch and
+    the eval-only path, each fit against numpy lstsq on its explicit matrix."""
+    times, data, freq = _damped_stack(N, 2, 360, seed=70 + N)
+    rng = np.random.default_rng(N + lpf)
+    B = 7
+    rb = rng.integers(0, 40, B).astype(np.int32)
+    re = (rb + rng.integers(3 * N, 300, B)).astype(np.int32)
+    re[2] = rb[2] + N + 1                                # barely overdetermined
+    t0 = times[rb] - 0.03
+    which = rng.integers(0, 2, B).astype(np.int32)
+    kw = dict(n_fits=B, n_modes=N, window=(rb, re), t0=t0, lpf=lpf, omega=freq.reshape(1, -1), omega_shared=True,
+              series_index=which, pair=True, dt=0.1)
+    out = hs.run(times, data, want_model=True, **kw)
+    fast = hs.run(times, data, uniform_weights=1, **kw)
+    ev = hs.run(times, data, eval_only=True, C_in=out["C"], **kw)
+    checked = 0
+    for b in range(B):
+        sl = slice(rb[b], re[b])
+        K = re[b] - rb[b]
+        a, C_ref, res, rank, s, m_ref = orc.lstsq_fit(times[sl], data[which[b], sl], freq, t0[b], None)
+        if rank < N:
+            assert out["status"][b] & 1, (b, K)          # numpy truncates: the device must say so
+            continue
+        if out["status"][b] != 0:
+            continue                                     # flagged with margin: the host would decide
+        checked += 1
+        assert np.max(np.abs(out["C"][b] - C_ref)) / np.max(np.abs(C_ref)) < cases.amp_tol(s), (b, K)
+        mm_ref = orc.mismatch(times[sl], m_ref, data[which[b], sl])
+        assert abs(out["mismatch"][b] - mm_ref) < 1e-10, (b, K)
+        assert abs(fast["mismatch"][b] - out["mismatch"][b]) < 1e-11
+        assert abs(ev["mismatch"][b] - out["mismatch"][b]) < 1e-12
+        np.testing.assert_allclose(out["model"][b][:K], m_ref, rtol=0, atol=1e-8 * np.max(np.abs(C_ref)))
+        Ad = np.column_stack([a, data[which[b], sl]])
+        gram, want = out["R"][b].conj().T @ out["R"][b], Ad.conj().T @ Ad
+        assert np.max(np.abs(gram[:N] - want[:N])) < 1e-9 * np.max(np.abs(want))
+    assert checked >= 3
+
+
+def test_pair_kernel_emulated_grid_matches_small_kernel():
+    """The factored-frequency path (M-chi grid) through K1p at nine columns against K1 on the same
+    fits: same rows, same reflections in another distribution over lanes -> agreement to rounding."""
+    wl = workloads.config3(res=4)
+    import qnmfits_b200 as qf
+    modes = [(2, 2, n, 1) for n in range(8)] + [(3, 2, 0, 1)]
+    Mf = np.linspace(*wl.Mf_minmax, 4)
+    chi = np.linspace(*wl.chif_minmax, 4)
+    table, ptr = qf.qnm.constituent_table(modes, chi)
+    win = api._window_rows(wl.times, 0.0, 100, "geq")
+    kw = dict(n_fits=16, n_modes=9, window=win, t0=0.0, table=table, mode_ptr=ptr, inv_Mf=1.0 / Mf, n_chi=4, n_mf=4,
+              dt=0.1, uniform_weights=1)
+    pair = hs.run(wl.times, wl.data, lpf=8, pair=True, **kw)
+    small = hs.run(wl.times, wl.data, lpf=8, **kw)
+    assert np.all(pair["status"] == 0) and np.all(small["status"] == 0)
+    np.testing.assert_allclose(pair["mismatch"], small["mismatch"], rtol=0, atol=1e-12)
