@@ -129,7 +129,7 @@ static void run(const qnmfit_batch *b, int lpf, bool eval)
 // K1p: the CTA's shared memory is set up serially, then each warp runs in lock step.
 #define HSP_THREADS 64
 template <int N>
-static void run_pair(const qnmfit_batch *b, int lpf, bool eval)
+static void run_pair(const qnmfit_batch *b, int lpf, bool eval, bool descending)
 {
     constexpr int CS = k1p_cs_ct(N), MB = k1p_mb_ct(N);
     typedef PairLayout<N, CS> LY;
@@ -150,25 +150,28 @@ static void run_pair(const qnmfit_batch *b, int lpf, bool eval)
                 const int tid = warp * 32 + lane;
                 const SmallLane L = pair_lane_setup<CS>(p, cta, tid, HSP_THREADS, true, MB, 0);
                 pair_lane_body<N, CS, MB, HSP_THREADS>(p, sm, L, tid);
-            });
+            }, descending);
     }
 }
 
 // All pointers in *b are HOST pointers here.  Column counts: a sample of every configuration
 // (2 / 4 / 8 lanes per row slice, 4 / 5 / 6 / 8 rows per block).
+// eval: bit 0 = eval-only launch, bit 1 = resume the lanes of a warp in descending order
 extern "C" int hostsim_fit_pair(const qnmfit_batch *b, int lpf, int eval)
 {
+    const bool descending = (eval & 2) != 0;
+    eval &= 1;
     if (!b || b->struct_size != (int)sizeof(qnmfit_batch)) return QNMFIT_E_ABI;
     if (b->n_series != 1) return QNMFIT_E_SHAPE;
     if (lpf < 1 || lpf > 32 || (lpf & (lpf - 1)) || lpf < k1p_cs_ct(b->n_modes)) return QNMFIT_E_SHAPE;
     switch (b->n_modes) {
-    case 9: run_pair<9>(b, lpf, eval); break;
-    case 11: run_pair<11>(b, lpf, eval); break;
-    case 12: run_pair<12>(b, lpf, eval); break;
-    case 14: run_pair<14>(b, lpf, eval); break;
-    case 16: run_pair<16>(b, lpf, eval); break;
-    case 19: run_pair<19>(b, lpf, eval); break;
-    case 24: run_pair<24>(b, lpf, eval); break;
+    case 9: run_pair<9>(b, lpf, eval, descending); break;
+    case 11: run_pair<11>(b, lpf, eval, descending); break;
+    case 12: run_pair<12>(b, lpf, eval, descending); break;
+    case 14: run_pair<14>(b, lpf, eval, descending); break;
+    case 16: run_pair<16>(b, lpf, eval, descending); break;
+    case 19: run_pair<19>(b, lpf, eval, descending); break;
+    case 24: run_pair<24>(b, lpf, eval, descending); break;
     default: return QNMFIT_E_SHAPE;
     }
     return 0;

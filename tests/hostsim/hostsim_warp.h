@@ -6,6 +6,12 @@
 // a slower lane still has to read.  Every collective carries a tag (kind and width); the emulator
 // aborts when the lanes of a warp do not execute the same sequence of collectives — which checks
 // the kernels' claim that their control flow around shuffles is warp-uniform.
+//
+// Between two collectives a lane runs ALONE, the lanes one after another in ascending or (second
+// argument of run_warp) descending order.  That is stricter than the hardware about the order of
+// shared-memory accesses of different lanes: a load that relies on another lane's earlier store
+// (or must precede another lane's later store) with no collective in between goes wrong in one
+// of the two orders.
 #pragma once
 #include <stdio.h>
 #include <stdlib.h>
@@ -22,6 +28,7 @@ struct Warp {
     ucontext_t sched, ctx[LANES];
     bool done[LANES];
     int lane;                       // the lane that is running
+    bool descending;                // lanes are resumed 31 .. 0 instead of 0 .. 31
     unsigned long long count[LANES];  // collectives executed by each lane
     double xd[2][LANES];
     long long xi[2][LANES];
@@ -47,10 +54,10 @@ inline int arrive(int tag, double d, long long i)
     w->count[l] += 1;
     w->xd[ph][l] = d; w->xi[ph][l] = i; w->tag[ph][l] = tag;
     swapcontext(&w->ctx[l], &w->sched);
-    // resumed: every lane has published.  Lanes below l have already run on to their next
-    // collective (or to the end); lanes above l still wait in this one.
+    // resumed: every lane has published.  Lanes resumed before l have already run on to their
+    // next collective (or to the end); the others still wait in this one.
     for (int o = 0; o < LANES; ++o) {
-        const bool ahead = o < l;
+        const bool ahead = w->descending ? o > l : o < l;
         const bool ok = ahead ? (w->done[o] ? w->count[o] == w->count[l] : w->count[o] == w->count[l] + 1)
                               : (!w->done[o] && w->count[o] == w->count[l]);
         if (!ok || w->tag[ph][o] != tag)
@@ -68,10 +75,11 @@ inline void trampoline()
 }
 
 // run body(lane) for the 32 lanes of one warp in lock step
-inline void run_warp(const std::function<void(int)> &body)
+inline void run_warp(const std::function<void(int)> &body, bool descending = false)
 {
     Warp w;
     w.body = &body;
+    w.descending = descending;
     w.stacks.resize((size_t)LANES * STACK_BYTES);
     Warp *outer = current();
     current() = &w;
@@ -85,7 +93,8 @@ inline void run_warp(const std::function<void(int)> &body)
     }
     for (bool any = true; any;) {
         any = false;
-        for (int l = 0; l < LANES; ++l) {
+        for (int i = 0; i < LANES; ++i) {
+            const int l = descending ? LANES - 1 - i : i;
             if (w.done[l]) continue;
             w.lane = l;
             swapcontext(&w.sched, &w.ctx[l]);

@@ -28,8 +28,9 @@ def _p(a):
 def run(times, data, *, n_fits, n_modes, window, t0, lpf=4, eval_only=False, dt=None,
         anchor_rows=0, omega=None, omega_shared=False, table=None, mode_ptr=None, inv_Mf=None,
         delta_factor=None, n_chi=0, n_mf=0, first_fit=0, C_in=None, want_model=False,
-        uniform_weights=0, series_index=None, pair=False):
-    """``pair=True``: the K1p code (csrc/fit_pair.cuh), warps in lock step; otherwise K1."""
+        uniform_weights=0, series_index=None, pair=False, descending=False):
+    """``pair=True``: the K1p code (csrc/fit_pair.cuh), warps in lock step (``descending``: the lanes
+    of a warp are resumed 31 .. 0 instead of 0 .. 31 between collectives); otherwise K1."""
     times = np.ascontiguousarray(times, dtype=float)
     data = np.ascontiguousarray(data, dtype=complex)
     keep = [times, data]
@@ -85,6 +86,6 @@ def run(times, data, *, n_fits, n_modes, window, t0, lpf=4, eval_only=False, dt=
                     residual=_p(res), R=_p(R), status=_p(st), model=_p(model),
                     model_stride=Mmax if want_model else 0, uniform_weights=int(uniform_weights), **kw)
     entry = lib().hostsim_fit_pair if pair else lib().hostsim_fit_small
-    rc = entry(C.byref(b), int(lpf), 1 if eval_only else 0)
+    rc = entry(C.byref(b), int(lpf), (1 if eval_only else 0) | (2 if pair and descending else 0))
     assert rc == 0, rc
     return dict(C=Cbuf, mismatch=mm, residual=res, R=R, status=st, model=model, dt=dt)

@@ -269,11 +269,14 @@ def _damped_stack(N, S, K_tot, seed):
     return times, data, freq
 
 
+@pytest.mark.parametrize("descending", [False, True])
 @pytest.mark.parametrize("N,lpf", [(9, 2), (9, 8), (11, 4), (12, 4), (14, 8), (16, 4), (19, 16), (24, 8), (24, 32)])
-def test_pair_kernel_emulated_in_lock_step_vs_numpy(N, lpf):
+def test_pair_kernel_emulated_in_lock_step_vs_numpy(N, lpf, descending):
     """Seven fits sharing warps: windows of different lengths (lanes run blocks they have no rows
     for), per-fit start times and data series; second pass with model output, fast mismatch and
-    the eval-only path, each fit against numpy lstsq on its explicit matrix."""
+    the eval-only path, each fit against numpy lstsq on its explicit matrix.  Between collectives
+    the lanes run one after another, in ascending and in descending order: a cross-lane
+    shared-memory dependence that no collective orders fails in one of the two."""
     times, data, freq = _damped_stack(N, 2, 360, seed=70 + N)
     rng = np.random.default_rng(N + lpf)
     B = 7
@@ -283,7 +286,7 @@ def test_pair_kernel_emulated_in_lock_step_vs_numpy(N, lpf):
     t0 = times[rb] - 0.03
     which = rng.integers(0, 2, B).astype(np.int32)
     kw = dict(n_fits=B, n_modes=N, window=(rb, re), t0=t0, lpf=lpf, omega=freq.reshape(1, -1), omega_shared=True,
-              series_index=which, pair=True, dt=0.1)
+              series_index=which, pair=True, dt=0.1, descending=descending)
     out = hs.run(times, data, want_model=True, **kw)
     fast = hs.run(times, data, uniform_weights=1, **kw)
     ev = hs.run(times, data, eval_only=True, C_in=out["C"], **kw)
