@@ -1,43 +1,53 @@
-// hostsim_warp.h — TEST HARNESS ONLY.  Lock-step emulation of one warp on the host: the 32 lanes
-// run as 32 fibers (ucontext); a warp collective (__shfl_sync, __shfl_xor_sync, __all_sync,
+// hostsim_warp.h — TEST HARNESS ONLY.  Lock-step emulation of one CTA on the host: every thread
+// runs as a fiber (ucontext).  A warp collective (__shfl_sync, __shfl_xor_sync, __all_sync,
 // __any_sync, __reduce_max_sync, __syncwarp) publishes the lane's value, yields to the scheduler
-// and reads its partners' values once every lane has arrived.  The exchange buffers alternate
-// between consecutive collectives, so a lane that is one collective ahead does not overwrite what
-// a slower lane still has to read.  Every collective carries a tag (kind and width); the emulator
-// aborts when the lanes of a warp do not execute the same sequence of collectives — which checks
-// the kernels' claim that their control flow around shuffles is warp-uniform.
+// and reads its partners' values once all 32 lanes of its warp have arrived; __syncthreads does the
+// same for the whole CTA.  The exchange buffers alternate between consecutive collectives of a
+// warp, so a lane that is one collective ahead does not overwrite what a slower lane still has to
+// read.  Every collective carries a tag (kind and width); the emulator aborts when the lanes of a
+// warp do not execute the same sequence of collectives — which checks the kernels' claim that
+// their control flow around shuffles is warp-uniform — and when the CTA dead-locks (a barrier not
+// reached by every thread).
 //
-// Between two collectives a lane runs ALONE, the lanes one after another in ascending or (second
-// argument of run_warp) descending order.  That is stricter than the hardware about the order of
-// shared-memory accesses of different lanes: a load that relies on another lane's earlier store
-// (or must precede another lane's later store) with no collective in between goes wrong in one
-// of the two orders.
+// Between two collectives a thread runs ALONE, the threads one after another in ascending or
+// descending order.  That is stricter than the hardware about the order of shared-memory
+// accesses of different threads: a load that relies on another thread's earlier store (or must
+// precede another thread's later store) with no barrier in between goes wrong in one of the two
+// orders.  compute-sanitizer's racecheck is not available on the GPU pool of this project; this is
+// the substitute for the kernels compiled into the harness.
 #pragma once
 #include <stdio.h>
 #include <stdlib.h>
 #include <ucontext.h>
 
 #include <functional>
+#include <memory>
 #include <vector>
 
 namespace hswarp {
 
-enum { LANES = 32, STACK_BYTES = 1 << 20 };
+enum { LANES = 32, STACK_BYTES = 512 << 10 };
 
-struct Warp {
-    ucontext_t sched, ctx[LANES];
-    bool done[LANES];
-    int lane;                       // the lane that is running
-    bool descending;                // lanes are resumed 31 .. 0 instead of 0 .. 31
-    unsigned long long count[LANES];  // collectives executed by each lane
-    double xd[2][LANES];
-    long long xi[2][LANES];
-    int tag[2][LANES];
+struct Idx { int x; };
+
+struct Cta {
+    ucontext_t sched;
+    std::vector<ucontext_t> ctx;
+    std::unique_ptr<char[]> stacks;               // not zero-filled: pages are touched on demand
+    std::vector<char> done, wait;                 // wait: 0 runnable, 1 in a warp collective, 2 in __syncthreads
+    std::vector<unsigned long long> count;        // warp collectives executed by each thread
+    std::vector<double> xd;                       // [warp][2][LANES]
+    std::vector<long long> xi;
+    std::vector<int> tag;
+    std::vector<int> warp_arrived;
+    int cta_arrived;
+    int nthreads, cur, block;
+    bool descending;
+    unsigned char *smem;
     const std::function<void(int)> *body;
-    std::vector<char> stacks;
 };
 
-inline Warp *&current() { static thread_local Warp *w = nullptr; return w; }
+inline Cta *&current() { static thread_local Cta *c = nullptr; return c; }
 
 inline void fail(const char *what)
 {
@@ -45,103 +55,154 @@ inline void fail(const char *what)
     abort();
 }
 
-// publish, wait for the whole warp, return the buffer index to read from
+inline Cta *need()
+{
+    Cta *c = current();
+    if (!c) fail("collective outside hswarp::run_cta");
+    return c;
+}
+
+inline Idx thread_idx() { Idx i; i.x = need()->cur; return i; }
+inline Idx block_idx() { Idx i; i.x = need()->block; return i; }
+inline Idx block_dim() { Idx i; i.x = need()->nthreads; return i; }
+inline unsigned char *dyn_smem() { return need()->smem; }
+inline int lane_id() { return need()->cur % LANES; }
+
+// publish in the warp's buffer, wait for the warp, return the index of the buffer to read
 inline int arrive(int tag, double d, long long i)
 {
-    Warp *w = current();
-    if (!w) fail("warp collective outside hswarp::run_warp");
-    const int l = w->lane, ph = (int)(w->count[l] & 1);
-    w->count[l] += 1;
-    w->xd[ph][l] = d; w->xi[ph][l] = i; w->tag[ph][l] = tag;
-    swapcontext(&w->ctx[l], &w->sched);
-    // resumed: every lane has published.  Lanes resumed before l have already run on to their
-    // next collective (or to the end); the others still wait in this one.
-    for (int o = 0; o < LANES; ++o) {
-        const bool ahead = w->descending ? o > l : o < l;
-        const bool ok = ahead ? (w->done[o] ? w->count[o] == w->count[l] : w->count[o] == w->count[l] + 1)
-                              : (!w->done[o] && w->count[o] == w->count[l]);
-        if (!ok || w->tag[ph][o] != tag)
-            fail("the lanes of a warp did not execute the same sequence of collectives");
+    Cta *c = need();
+    const int t = c->cur, w = t / LANES, l = t % LANES, ph = (int)(c->count[t] & 1);
+    c->count[t] += 1;
+    const int slot = (w * 2 + ph) * LANES;
+    c->xd[slot + l] = d; c->xi[slot + l] = i; c->tag[slot + l] = tag;
+    c->wait[t] = 1;
+    if (++c->warp_arrived[w] == LANES) {
+        c->warp_arrived[w] = 0;
+        for (int o = 0; o < LANES; ++o) c->wait[w * LANES + o] = 0;
     }
-    return ph;
+    swapcontext(&c->ctx[t], &c->sched);
+    for (int o = 0; o < LANES; ++o)
+        if (c->tag[slot + o] != tag) fail("the lanes of a warp did not execute the same sequence of collectives");
+    return slot;
+}
+
+inline void cta_barrier()
+{
+    Cta *c = need();
+    const int t = c->cur;
+    c->wait[t] = 2;
+    if (++c->cta_arrived == c->nthreads) {
+        c->cta_arrived = 0;
+        for (int o = 0; o < c->nthreads; ++o) {
+            if (c->wait[o] != 2) fail("__syncthreads reached while a thread waits in a warp collective");
+            c->wait[o] = 0;
+        }
+    }
+    swapcontext(&c->ctx[t], &c->sched);
 }
 
 inline void trampoline()
 {
-    Warp *w = current();
-    const int l = w->lane;
-    (*w->body)(l);
-    w->done[l] = true;
+    Cta *c = current();
+    const int t = c->cur;
+    (*c->body)(t);
+    c->done[t] = 1;
 }
 
-// run body(lane) for the 32 lanes of one warp in lock step
-inline void run_warp(const std::function<void(int)> &body, bool descending = false)
+// run body(tid) for the nthreads (a multiple of 32) threads of one CTA in lock step
+inline void run_cta(int nthreads, const std::function<void(int)> &body, bool descending = false, int block = 0,
+                    unsigned char *smem = nullptr)
 {
-    Warp w;
-    w.body = &body;
-    w.descending = descending;
-    w.stacks.resize((size_t)LANES * STACK_BYTES);
-    Warp *outer = current();
-    current() = &w;
-    for (int l = 0; l < LANES; ++l) {
-        w.done[l] = false; w.count[l] = 0;
-        getcontext(&w.ctx[l]);
-        w.ctx[l].uc_stack.ss_sp = w.stacks.data() + (size_t)l * STACK_BYTES;
-        w.ctx[l].uc_stack.ss_size = STACK_BYTES;
-        w.ctx[l].uc_link = &w.sched;
-        makecontext(&w.ctx[l], (void (*)())trampoline, 0);
+    if (nthreads % LANES) fail("run_cta: the thread count must be a multiple of 32");
+    Cta c;
+    c.nthreads = nthreads; c.body = &body; c.descending = descending; c.block = block; c.smem = smem;
+    c.ctx.resize(nthreads);
+    c.stacks.reset(new char[(size_t)nthreads * STACK_BYTES]);
+    c.done.assign(nthreads, 0); c.wait.assign(nthreads, 0); c.count.assign(nthreads, 0);
+    const int nwarps = nthreads / LANES;
+    c.xd.assign((size_t)nwarps * 2 * LANES, 0.0); c.xi.assign((size_t)nwarps * 2 * LANES, 0);
+    c.tag.assign((size_t)nwarps * 2 * LANES, 0);
+    c.warp_arrived.assign(nwarps, 0);
+    c.cta_arrived = 0;
+    Cta *outer = current();
+    current() = &c;
+    for (int t = 0; t < nthreads; ++t) {
+        getcontext(&c.ctx[t]);
+        c.ctx[t].uc_stack.ss_sp = c.stacks.get() + (size_t)t * STACK_BYTES;
+        c.ctx[t].uc_stack.ss_size = STACK_BYTES;
+        c.ctx[t].uc_link = &c.sched;
+        makecontext(&c.ctx[t], (void (*)())trampoline, 0);
     }
-    for (bool any = true; any;) {
-        any = false;
-        for (int i = 0; i < LANES; ++i) {
-            const int l = descending ? LANES - 1 - i : i;
-            if (w.done[l]) continue;
-            w.lane = l;
-            swapcontext(&w.sched, &w.ctx[l]);
-            any = true;
+    for (;;) {
+        bool ran = false, all_done = true;
+        for (int i = 0; i < nthreads; ++i) {
+            const int t = descending ? nthreads - 1 - i : i;
+            if (c.done[t]) continue;
+            all_done = false;
+            if (c.wait[t]) continue;
+            c.cur = t;
+            swapcontext(&c.sched, &c.ctx[t]);
+            ran = true;
         }
-        bool first = w.done[0];
-        for (int l = 1; l < LANES; ++l)
-            if (w.done[l] != first) fail("some lanes of a warp finished while others wait in a collective");
+        if (all_done) break;
+        if (!ran) fail("dead-lock: a barrier or warp collective was not reached by all of its threads");
     }
     current() = outer;
 }
 
+inline void run_warp(const std::function<void(int)> &body, bool descending = false)
+{
+    run_cta(LANES, body, descending);
+}
+
 }  // namespace hswarp
 
-// ---- the CUDA warp intrinsics the K1p device code uses, for the host build ---------------------
+// ---- the CUDA built-ins the emulated device code uses, for the host build -----------------------
+#define threadIdx (hswarp::thread_idx())
+#define blockIdx (hswarp::block_idx())
+#define blockDim (hswarp::block_dim())
+static inline void __syncthreads() { hswarp::cta_barrier(); }
+
 static inline double __shfl_sync(unsigned, double v, int src, int width = 32)
 {
-    const int l = hswarp::current() ? hswarp::current()->lane : 0;
-    const int ph = hswarp::arrive(0x100 + width, v, 0);
-    return hswarp::current()->xd[ph][(l & ~(width - 1)) | (src & (width - 1))];
+    const int l = hswarp::lane_id();
+    const int slot = hswarp::arrive(0x100 + width, v, 0);
+    return hswarp::current()->xd[slot + ((l & ~(width - 1)) | (src & (width - 1)))];
 }
 static inline double __shfl_xor_sync(unsigned, double v, int lane_mask, int width = 32)
 {
-    const int l = hswarp::current() ? hswarp::current()->lane : 0;
-    const int ph = hswarp::arrive(0x200 + width, v, 0);
+    const int l = hswarp::lane_id();
+    const int slot = hswarp::arrive(0x200 + width, v, 0);
     const int o = l ^ lane_mask;
-    return (o & ~(width - 1)) == (l & ~(width - 1)) ? hswarp::current()->xd[ph][o] : v;
+    return (o & ~(width - 1)) == (l & ~(width - 1)) ? hswarp::current()->xd[slot + o] : v;
+}
+static inline int __shfl_xor_sync(unsigned, int v, int lane_mask, int width = 32)
+{
+    const int l = hswarp::lane_id();
+    const int slot = hswarp::arrive(0x280 + width, 0.0, v);
+    const int o = l ^ lane_mask;
+    return (o & ~(width - 1)) == (l & ~(width - 1)) ? (int)hswarp::current()->xi[slot + o] : v;
 }
 static inline int __all_sync(unsigned, int pred)
 {
-    const int ph = hswarp::arrive(0x300, 0.0, pred != 0);
+    const int slot = hswarp::arrive(0x300, 0.0, pred != 0);
     int r = 1;
-    for (int o = 0; o < hswarp::LANES; ++o) r &= (int)hswarp::current()->xi[ph][o];
+    for (int o = 0; o < hswarp::LANES; ++o) r &= (int)hswarp::current()->xi[slot + o];
     return r;
 }
 static inline int __any_sync(unsigned, int pred)
 {
-    const int ph = hswarp::arrive(0x400, 0.0, pred != 0);
+    const int slot = hswarp::arrive(0x400, 0.0, pred != 0);
     int r = 0;
-    for (int o = 0; o < hswarp::LANES; ++o) r |= (int)hswarp::current()->xi[ph][o];
+    for (int o = 0; o < hswarp::LANES; ++o) r |= (int)hswarp::current()->xi[slot + o];
     return r;
 }
 static inline int __reduce_max_sync(unsigned, int v)
 {
-    const int ph = hswarp::arrive(0x500, 0.0, v);
-    long long r = hswarp::current()->xi[ph][0];
-    for (int o = 1; o < hswarp::LANES; ++o) r = hswarp::current()->xi[ph][o] > r ? hswarp::current()->xi[ph][o] : r;
+    const int slot = hswarp::arrive(0x500, 0.0, v);
+    long long r = hswarp::current()->xi[slot];
+    for (int o = 1; o < hswarp::LANES; ++o) r = hswarp::current()->xi[slot + o] > r ? hswarp::current()->xi[slot + o] : r;
     return (int)r;
 }
 static inline void __syncwarp(unsigned = 0xffffffffu) { hswarp::arrive(0x600, 0.0, 0); }
