@@ -37,8 +37,6 @@
 #pragma once
 #include "qnmfit_common.cuh"
 
-#ifndef QNMFIT_HOSTSIM
-
 #define K3C_MAXROWS 64             // tallest tile (rows) any variant uses: sizes the v buffer
 #define K3C_TK 16                 // time chunk of the second pass
 
@@ -163,12 +161,16 @@ __device__ __forceinline__ void k3c_reflect(double2 (&X)[RPT], double &part, con
                 sr2 = fma(b2.y, X[r + 2].y, sr2); si2 = fma(-b2.y, X[r + 2].x, si2);
                 sr3 = fma(b3.y, X[r + 3].y, sr3); si3 = fma(-b3.y, X[r + 3].x, si3);
             }
+            // R_jc is read by all G lanes of the column and rewritten by lane 0 of the group: the
+            // load sits BEFORE the group sums, whose shuffles order it ahead of that store (a
+            // converged warp executes the loads first anyway; the lock-step host emulation, which
+            // runs a thread alone from one collective to the next, does not)
+            const double2 old = act ? R.at(j, c) : make_double2(0.0, 0.0);
             const double sr = k3c_group_sum<G>((sr0 + sr1) + (sr2 + sr3));
             const double si = k3c_group_sum<G>((si0 + si1) + (si2 + si3));
             if (act) {
                 const double v0 = scal[buf * 2], beta = scal[buf * 2 + 1];
                 double2 &Rjc = R.at(j, c);
-                const double2 old = Rjc;
                 const double pr = fma(v0, old.x, sr) * beta;
                 const double pi = fma(v0, old.y, si) * beta;
                 if (g == 0) Rjc = make_double2(fma(-v0, pr, old.x), fma(-v0, pi, old.y));
@@ -473,7 +475,7 @@ template <int G, int RPT>
 #define K3C_MINB(G, RPT) (RPT >= 32 ? (G == 1 ? 4 : 2) : G <= 2 ? 4 : G == 4 ? 2 : 1)
 __global__ void __launch_bounds__(64 * G, K3C_MINB(G, RPT)) fit_struct3_kernel(const __grid_constant__ FitParams p)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    QF_DYN_SMEM(smem_raw);
     constexpr int TR = G * RPT;
     static_assert(TR <= K3C_MAXROWS, "tile taller than the v buffer");
     const int N = p.n_modes, L = p.n_series, NC = N + L;
@@ -549,4 +551,3 @@ __global__ void __launch_bounds__(64 * G, K3C_MINB(G, RPT)) fit_struct3_kernel(c
     }
     struct_finish(p, sm, fit, N, L, rb, re, t0, coef, two_phase, sdd, res2);
 }
-#endif  // !QNMFIT_HOSTSIM

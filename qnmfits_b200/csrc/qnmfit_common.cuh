@@ -11,6 +11,17 @@
 #include "qnmfit.h"
 
 #ifdef QNMFIT_HOSTSIM
+#include "hostsim_warp.h"    // tests/hostsim: warp collectives and __syncthreads, one fiber per thread
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __noinline__
+#define __launch_bounds__(...)
+#define __grid_constant__
+#define QF_DYN_SMEM(name) unsigned char *name = hswarp::dyn_smem()
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
 struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 #define QF_HD static inline
@@ -26,6 +37,7 @@ static inline double qf_rcp(double x) { return 1.0 / x; }
 static inline void qf_sincos(double y, double *s, double *c) { *s = sin(y); *c = cos(y); }
 #else
 #include <cuda_runtime.h>
+#define QF_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #define QF_HD __device__ __forceinline__
 #define QF_BOTH __host__ __device__ __forceinline__
 #define QF_MEM __device__ __forceinline__
@@ -327,6 +339,7 @@ QF_DEV unsigned long long qf_globaltimer()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+#endif
 
 // fixed-order butterfly sum over the 32 lanes of a warp
 QF_DEV double warp_sum(double v)
@@ -413,6 +426,7 @@ QF_DEV bool rank_suspect_warp(const RF &R, const DF &D, int N, double dim, doubl
     return !(1.0 / nz > cut * cut * frob2);
 }
 
+#ifndef QNMFIT_HOSTSIM
 QF_DEV void peer_publish(const FitParams &p, int fit, double mm)
 {
     if (p.n_peers <= 1) return;

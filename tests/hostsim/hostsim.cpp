@@ -2,7 +2,9 @@
 // plain host C++ (-DQNMFIT_HOSTSIM) and runs the lanes of each CTA one after another,
 // phase by phase, exactly as the CUDA kernel orders them; and the K1p device code
 // (fit_pair.cuh), whose lanes exchange data with shuffles inside the block loop, with the 32
-// lanes of a warp in lock step (hostsim_warp.h: one fiber per lane).  It lets the CPU-only test
+// lanes of a warp in lock step (hostsim_warp.h: one fiber per lane); and K3 (fit_struct.cuh, the
+// kernel function itself) with all threads of a CTA as fibers, warp collectives and
+// __syncthreads emulated.  It lets the CPU-only test
 // tier check the kernel's arithmetic (streamed TSQR, anchored recurrence, R-combine,
 // back-substitution, mismatch sums) against the oracle.  It is never loaded by the
 // qnmfits_b200 package.
@@ -17,6 +19,7 @@
 #include "fit_small.cuh"
 #include "k1p_config.h"
 #include "fit_pair.cuh"
+#include "fit_struct.cuh"
 
 #define HS_THREADS 256
 
@@ -174,6 +177,28 @@ extern "C" int hostsim_fit_pair(const qnmfit_batch *b, int lpf, int eval)
     case 24: run_pair<24>(b, lpf, eval, descending); break;
     default: return QNMFIT_E_SHAPE;
     }
+    return 0;
+}
+
+// K3: the unmodified kernel function, one emulated CTA per fit (form G = 4 lanes per column,
+// RPT = 16 rows per thread: the library's default).
+extern "C" int hostsim_fit_struct(const qnmfit_batch *b, int eval)
+{
+    if (!b || b->struct_size != (int)sizeof(qnmfit_batch)) return QNMFIT_E_ABI;
+    const bool descending = (eval & 2) != 0;
+    eval &= 1;
+    constexpr int G = 4, RPT = 16;
+    const int N = b->n_modes, L = b->n_series;
+    if (N < 1 || L < 1 || N + L > 64 || b->coef_rows || b->series_index) return QNMFIT_E_SHAPE;
+    FitParams p;
+    fill_params(b, G, eval != 0, &p);
+    p.coef = (const double2 *)b->coef; p.coef_index = b->coef_index; p.n_coef = b->n_coef;
+    p.omega_rows = (const double2 *)b->omega_rows;
+    p.fast_mismatch = (!eval && b->uniform_weights && b->dt_nominal > 0.0 && !b->model) ? 1 : 0;
+    const int threads = G * 32 * ((N + L + 31) / 32);
+    std::vector<unsigned char> smem(Struct3Smem::bytes(N, L) + 64);
+    for (int fit = 0; fit < b->n_fits; ++fit)
+        hswarp::run_cta(threads, [&](int) { fit_struct3_kernel<G, RPT>(p); }, descending, fit, smem.data());
     return 0;
 }
 

@@ -18,6 +18,7 @@ def lib():
         _hs = C.CDLL(os.path.join(ROOT, "tests", "hostsim", "libqnmfit_hostsim.so"))
         _hs.hostsim_fit_small.argtypes = [C.POINTER(_cabi.Batch), C.c_int, C.c_int]
         _hs.hostsim_fit_pair.argtypes = [C.POINTER(_cabi.Batch), C.c_int, C.c_int]
+        _hs.hostsim_fit_struct.argtypes = [C.POINTER(_cabi.Batch), C.c_int]
     return _hs
 
 
@@ -89,3 +90,47 @@ def run(times, data, *, n_fits, n_modes, window, t0, lpf=4, eval_only=False, dt=
     rc = entry(C.byref(b), int(lpf), (1 if eval_only else 0) | (2 if pair and descending else 0))
     assert rc == 0, rc
     return dict(C=Cbuf, mismatch=mm, residual=res, R=R, status=st, model=model, dt=dt)
+
+
+def run_struct(times, data, *, n_fits, n_modes, window, t0, omega, coef=None, eval_only=False, dt=None,
+               uniform_weights=0, C_in=None, want_model=False, descending=False):
+    """K3 (csrc/fit_struct.cuh): the kernel function itself on an emulated CTA per fit.  ``data`` is
+    (L, K_tot); ``omega`` (N,) shared by all fits; ``coef`` (L, N) or None (single series, no table)."""
+    times = np.ascontiguousarray(times, dtype=float)
+    data = np.ascontiguousarray(np.atleast_2d(data), dtype=complex)
+    L, K_tot = data.shape
+    om = np.ascontiguousarray(omega, dtype=complex).reshape(1, -1)
+    keep = [times, data, om]
+    kw = dict(omega=_p(om), omega_shared=1)
+    if isinstance(window[0], np.ndarray):
+        rb = np.ascontiguousarray(window[0], np.int32)
+        re = np.ascontiguousarray(window[1], np.int32)
+        keep += [rb, re]
+        kw.update(row_begin=_p(rb), row_end=_p(re), row_begin_all=int(rb.min()), row_end_all=int(re.max()))
+    else:
+        kw.update(row_begin_all=int(window[0]), row_end_all=int(window[1]))
+    if np.ndim(t0) == 0:
+        kw.update(t0_all=float(t0))
+    else:
+        t0a = np.ascontiguousarray(t0, dtype=float)
+        keep.append(t0a)
+        kw.update(t0=_p(t0a))
+    if coef is not None:
+        cf = np.ascontiguousarray(coef, dtype=complex).reshape(1, L, n_modes)
+        ci = np.zeros(n_fits, np.int32)
+        keep += [cf, ci]
+        kw.update(coef=_p(cf), coef_index=_p(ci), n_coef=1)
+    if dt is None:
+        dt = nominal_step(times[kw["row_begin_all"]:kw["row_end_all"]], float(np.max(np.abs(om))))
+    Mmax = kw["row_end_all"] - kw["row_begin_all"]
+    Cbuf = np.zeros((n_fits, n_modes), complex) if C_in is None else np.ascontiguousarray(C_in, dtype=complex)
+    mm, res = np.zeros(n_fits), np.zeros(n_fits)
+    st = np.zeros(n_fits, np.int32)
+    model = np.zeros((n_fits, L * Mmax), complex) if want_model else None
+    b = _cabi.Batch(n_fits=n_fits, n_modes=n_modes, n_series=L, n_times=K_tot, series_stride=K_tot,
+                    times=_p(times), data=_p(data), dt_nominal=float(dt), C=_p(Cbuf), mismatch=_p(mm),
+                    residual=_p(res), status=_p(st), model=_p(model), model_stride=L * Mmax if want_model else 0,
+                    uniform_weights=int(uniform_weights), **kw)
+    rc = lib().hostsim_fit_struct(C.byref(b), (1 if eval_only else 0) | (2 if descending else 0))
+    assert rc == 0, rc
+    return dict(C=Cbuf, mismatch=mm, residual=res, status=st, model=model, dt=dt)

@@ -329,3 +329,72 @@ def test_pair_kernel_emulated_grid_matches_small_kernel():
     small = hs.run(wl.times, wl.data, lpf=8, **kw)
     assert np.all(pair["status"] == 0) and np.all(small["status"] == 0)
     np.testing.assert_allclose(pair["mismatch"], small["mismatch"], rtol=0, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------
+# K3 (csrc/fit_struct.cuh): the kernel function itself, one emulated CTA per fit — all threads as
+# fibers, warp shuffles and __syncthreads emulated, the threads resumed in ascending and in
+# descending order between barriers (the stand-in for racecheck, which the GPU pool does not offer).
+
+def _stack(N, L, K_tot, seed, uniform=True):
+    rng = np.random.default_rng(seed)
+    times = np.arange(K_tot) * 0.1 if uniform else np.cumsum(0.05 + 0.1 * rng.random(K_tot))
+    freq = np.linspace(-0.1 * N, 0.1 * N, N) + 0.013 * rng.standard_normal(N) - 1j * (0.02 + 0.06 * rng.random(N))
+    coef = rng.standard_normal((L, N)) + 1j * rng.standard_normal((L, N))
+    C = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    E = np.exp(-1j * np.outer(times - times[3], freq))
+    data = np.stack([E @ (coef[i] * C) for i in range(L)])
+    data += 1e-5 * (rng.standard_normal(data.shape) + 1j * rng.standard_normal(data.shape))
+    return times, data, freq, coef
+
+
+@pytest.mark.parametrize("descending", [False, True])
+@pytest.mark.parametrize("N,L,use_coef", [(3, 2, True), (10, 3, True), (12, 1, False), (9, 7, True), (20, 5, True),
+                                          (40, 21, True)])
+def test_struct_kernel_emulated_cta_vs_numpy(N, L, use_coef, descending):
+    """Structured two-phase QR (K3) on uniform grids (fast mismatch and second pass, model output,
+    eval-only) and on a non-uniform grid (direct evaluation), against numpy lstsq on the explicit
+    stacked matrix."""
+    for uniform in (True, False):
+        K_tot = 330 if N < 40 else 200
+        times, data, freq, coef = _stack(N, L, K_tot, seed=N * 100 + L, uniform=uniform)
+        rb, re, t0 = 3, K_tot - 14, float(times[3])      # a row count that is no multiple of the tile height
+        K = re - rb
+        a, C_ref, res_ref, rank, s, model = orc.lstsq_fit(times[rb:re], data[:, rb:re].reshape(-1), freq, t0,
+                                                          coef if (use_coef or L > 1) else None)
+        assert rank == N
+        mm_ref = orc.multimode_mismatch(times[rb:re], {i: model[i * K:(i + 1) * K] for i in range(L)},
+                                        {i: data[i, rb:re] for i in range(L)})
+        kw = dict(n_fits=1, n_modes=N, window=(rb, re), t0=t0, omega=freq, coef=coef if (use_coef or L > 1) else None,
+                  dt=0.1 if uniform else 0.0, descending=descending)
+        out = hs.run_struct(times, data, want_model=True, **kw)
+        assert out["status"][0] == 0
+        assert np.max(np.abs(out["C"][0] - C_ref)) / np.max(np.abs(C_ref)) < cases.amp_tol(s), (uniform,)
+        assert abs(out["mismatch"][0] - mm_ref) < 1e-10
+        np.testing.assert_allclose(out["residual"][0], res_ref[0], rtol=1e-6)
+        got = np.concatenate([out["model"][0][i * K:(i + 1) * K] for i in range(L)])
+        np.testing.assert_allclose(got, model, rtol=0, atol=1e-8 * np.max(np.abs(C_ref)))
+        ev = hs.run_struct(times, data, eval_only=True, C_in=out["C"], **kw)
+        assert abs(ev["mismatch"][0] - out["mismatch"][0]) < 1e-12
+        if uniform:
+            fast = hs.run_struct(times, data, uniform_weights=1, **kw)
+            assert abs(fast["mismatch"][0] - mm_ref) < 1e-10
+
+
+def test_struct_kernel_emulated_sweep_with_ragged_windows():
+    """Several fits, each with its own window and start time (a t0 sweep of a multimode fit)."""
+    N, L, B = 10, 3, 6
+    times, data, freq, coef = _stack(N, L, 300, seed=7)
+    rng = np.random.default_rng(3)
+    rb = rng.integers(0, 40, B).astype(np.int32)
+    re = (rb + rng.integers(90, 250, B)).astype(np.int32)
+    t0 = times[rb] - 0.03
+    out = hs.run_struct(times, data, n_fits=B, n_modes=N, window=(rb, re), t0=t0, omega=freq, coef=coef, dt=0.1)
+    for b in range(B):
+        sl = slice(rb[b], re[b])
+        K = re[b] - rb[b]
+        a, C_ref, res, rank, s, m_ref = orc.lstsq_fit(times[sl], data[:, sl].reshape(-1), freq, t0[b], coef)
+        assert np.max(np.abs(out["C"][b] - C_ref)) / np.max(np.abs(C_ref)) < cases.amp_tol(s)
+        mm_ref = orc.multimode_mismatch(times[sl], {i: m_ref[i * K:(i + 1) * K] for i in range(L)},
+                                        {i: data[i, sl] for i in range(L)})
+        assert abs(out["mismatch"][b] - mm_ref) < 1e-10
