@@ -19,8 +19,6 @@
 #pragma once
 #include "qnmfit_common.cuh"
 
-#ifndef QNMFIT_HOSTSIM
-
 #define K2_THREADS 256
 #define K2_WARPS (K2_THREADS / 32)
 
@@ -58,7 +56,7 @@ struct GeneralSmem {
 __global__ void __launch_bounds__(K2_THREADS, 1)
 fit_general_kernel(const __grid_constant__ FitParams p, const int TR, const int TK)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    QF_DYN_SMEM(smem_raw);
     const int N = p.n_modes, L = p.n_series;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fit = blockIdx.x;
@@ -302,4 +300,3 @@ fit_general_kernel(const __grid_constant__ FitParams p, const int TR, const int 
         peer_publish(p, fit, mm);
     }
 }
-#endif  // !QNMFIT_HOSTSIM

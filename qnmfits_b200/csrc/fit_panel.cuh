@@ -30,8 +30,6 @@
 #include "qnmfit_common.cuh"
 #include "fit_struct.cuh"
 
-#ifndef QNMFIT_HOSTSIM
-
 #define K4_THREADS 128
 #define K4_WARPS (K4_THREADS / 32)
 #define K4_M 64                   // tile rows
@@ -108,7 +106,7 @@ struct PanelSmem {
 // the CTA's dynamic shared memory, typed: indexing THIS pointer keeps the accesses LDS / STS
 __device__ __forceinline__ double2 *k4_shared()
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    QF_DYN_SMEM(smem_raw);
     return (double2 *)smem_raw;
 }
 
@@ -122,8 +120,12 @@ __device__ __forceinline__ int k4_ridx(const int o_R, const int W, const int j, 
 // .f64): a = A[lane >> 2][lane & 3], b = B[lane & 3][lane >> 2], d0/d1 = D[lane >> 2][2 (lane & 3) + 0/1].
 __device__ __forceinline__ void k4_dmma(double &d0, double &d1, const double a, const double b)
 {
+#ifndef QNMFIT_HOSTSIM
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+#else
+    hs_dmma_m8n8k4(d0, d1, a, b);      // tests/hostsim/hostsim_warp.h: the same fragments, on the host
+#endif
 }
 
 __device__ __forceinline__ double2 k4_cmul(const double2 a, const double2 b)
@@ -442,7 +444,11 @@ __device__ __forceinline__ void k4_factor_tile(const PanelSmem &sm, const int o_
     // the two CTAs of an SM sit in warp slots 0-3 and 4-7 (scheduler = slot % 4): offset their
     // panel warps by two so that both panels never queue on one scheduler
     unsigned slot0;
+#ifndef QNMFIT_HOSTSIM
     asm("mov.u32 %0, %%warpid;" : "=r"(slot0));
+#else
+    slot0 = (unsigned)(threadIdx.x >> 5);
+#endif
     const int rot = 2 * (int)((__shfl_sync(0xffffffffu, slot0, 0) >> 2) & 1);
     if (warp == ((pfirst + rot) & (K4_WARPS - 1)))
         k4_panel(sm, o_R, RW, o_diag, pfirst * K4_NB, N - pfirst * K4_NB < K4_NB ? N - pfirst * K4_NB : K4_NB,
@@ -496,7 +502,7 @@ __device__ __forceinline__ void k4_factor_tile(const PanelSmem &sm, const int o_
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(K4_THREADS, 2) fit_panel_kernel(const __grid_constant__ FitParams p)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    QF_DYN_SMEM(smem_raw);
     const int N = p.n_modes, L = p.n_series, NC = N + L;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform by construction
@@ -644,4 +650,3 @@ __global__ void __launch_bounds__(K4_THREADS, 2) fit_panel_kernel(const __grid_c
     }
     struct_finish(p, sm, fit, N, L, rb, re, t0, coef, two_phase, sdd, res2);
 }
-#endif  // !QNMFIT_HOSTSIM

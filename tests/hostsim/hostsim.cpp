@@ -20,6 +20,8 @@
 #include "k1p_config.h"
 #include "fit_pair.cuh"
 #include "fit_struct.cuh"
+#include "fit_panel.cuh"
+#include "fit_general.cuh"
 
 #define HS_THREADS 256
 
@@ -199,6 +201,50 @@ extern "C" int hostsim_fit_struct(const qnmfit_batch *b, int eval)
     std::vector<unsigned char> smem(Struct3Smem::bytes(N, L) + 64);
     for (int fit = 0; fit < b->n_fits; ++fit)
         hswarp::run_cta(threads, [&](int) { fit_struct3_kernel<G, RPT>(p); }, descending, fit, smem.data());
+    return 0;
+}
+
+// K2: the unmodified kernel function (streamed dense Householder; the only kernel that takes
+// per-row mixing tables), tile geometry chosen as the library does.
+extern "C" int hostsim_fit_general(const qnmfit_batch *b, int eval)
+{
+    if (!b || b->struct_size != (int)sizeof(qnmfit_batch)) return QNMFIT_E_ABI;
+    const bool descending = (eval & 2) != 0;
+    eval &= 1;
+    const int N = b->n_modes, L = b->n_series;
+    if (N < 1 || L < 1 || N > 64 || b->series_index) return QNMFIT_E_SHAPE;
+    FitParams p;
+    fill_params(b, K2_THREADS, eval != 0, &p);
+    p.coef = (const double2 *)b->coef; p.coef_index = b->coef_index; p.n_coef = b->n_coef;
+    p.omega_rows = (const double2 *)b->omega_rows; p.coef_rows = (const double2 *)b->coef_rows;
+    p.fast_mismatch = 0;
+    int TR = 128, TK = 0;
+    for (; TR >= 32; TR /= 2)
+        if (TR >= L) { TK = TR / L > 0 ? TR / L : 1; break; }
+    if (!TK) return QNMFIT_E_SHAPE;
+    std::vector<unsigned char> smem(GeneralSmem::bytes(N, L, TR, TK) + 64);
+    for (int fit = 0; fit < b->n_fits; ++fit)
+        hswarp::run_cta(K2_THREADS, [&](int) { fit_general_kernel(p, TR, TK); }, descending, fit, smem.data());
+    return 0;
+}
+
+// K4: the unmodified kernel function (blocked structured QR); its mma.sync.m8n8k4.f64 is emulated
+// as a warp collective with the PTX fragment layout.
+extern "C" int hostsim_fit_panel(const qnmfit_batch *b, int eval)
+{
+    if (!b || b->struct_size != (int)sizeof(qnmfit_batch)) return QNMFIT_E_ABI;
+    const bool descending = (eval & 2) != 0;
+    eval &= 1;
+    const int N = b->n_modes, L = b->n_series;
+    if (N < 1 || L < 1 || N > 64 || L > 64 || b->coef_rows || b->series_index) return QNMFIT_E_SHAPE;
+    FitParams p;
+    fill_params(b, 1, eval != 0, &p);
+    p.coef = (const double2 *)b->coef; p.coef_index = b->coef_index; p.n_coef = b->n_coef;
+    p.omega_rows = (const double2 *)b->omega_rows;
+    p.fast_mismatch = (!eval && b->uniform_weights && b->dt_nominal > 0.0 && !b->model) ? 1 : 0;
+    std::vector<unsigned char> smem(PanelSmem::bytes(N, L) + 64);
+    for (int fit = 0; fit < b->n_fits; ++fit)
+        hswarp::run_cta(K4_THREADS, [&](int) { fit_panel_kernel(p); }, descending, fit, smem.data());
     return 0;
 }
 

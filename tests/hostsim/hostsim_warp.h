@@ -184,6 +184,36 @@ static inline int __shfl_xor_sync(unsigned, int v, int lane_mask, int width = 32
     const int o = l ^ lane_mask;
     return (o & ~(width - 1)) == (l & ~(width - 1)) ? (int)hswarp::current()->xi[slot + o] : v;
 }
+static inline int __shfl_sync(unsigned, int v, int src, int width = 32)
+{
+    const int l = hswarp::lane_id();
+    const int slot = hswarp::arrive(0x180 + width, 0.0, v);
+    return (int)hswarp::current()->xi[slot + ((l & ~(width - 1)) | (src & (width - 1)))];
+}
+static inline unsigned __shfl_sync(unsigned m, unsigned v, int src, int width = 32)
+{
+    return (unsigned)__shfl_sync(m, (int)v, src, width);
+}
+// mma.sync.aligned.m8n8k4.row.col.f64: D (8 x 8) += A (8 x 4) B (4 x 8) with the PTX fragments
+// a = A[lane >> 2][lane & 3], b = B[lane & 3][lane >> 2], d0 / d1 = D[lane >> 2][2 (lane & 3) + 0 / 1]
+static inline void hs_dmma_m8n8k4(double &d0, double &d1, double a, double b)
+{
+    long long bits;
+    static_assert(sizeof(bits) == sizeof(b), "double is 64 bits");
+    __builtin_memcpy(&bits, &b, sizeof(bits));
+    const int l = hswarp::lane_id();
+    const int slot = hswarp::arrive(0x700, a, bits);
+    const int row = l >> 2, c0 = 2 * (l & 3);
+    const hswarp::Cta *c = hswarp::current();
+    for (int k = 0; k < 4; ++k) {
+        const double ak = c->xd[slot + row * 4 + k];
+        double b0, b1;
+        __builtin_memcpy(&b0, &c->xi[slot + c0 * 4 + k], sizeof(b0));
+        __builtin_memcpy(&b1, &c->xi[slot + (c0 + 1) * 4 + k], sizeof(b1));
+        d0 = __builtin_fma(ak, b0, d0);
+        d1 = __builtin_fma(ak, b1, d1);
+    }
+}
 static inline int __all_sync(unsigned, int pred)
 {
     const int slot = hswarp::arrive(0x300, 0.0, pred != 0);

@@ -19,6 +19,8 @@ def lib():
         _hs.hostsim_fit_small.argtypes = [C.POINTER(_cabi.Batch), C.c_int, C.c_int]
         _hs.hostsim_fit_pair.argtypes = [C.POINTER(_cabi.Batch), C.c_int, C.c_int]
         _hs.hostsim_fit_struct.argtypes = [C.POINTER(_cabi.Batch), C.c_int]
+        _hs.hostsim_fit_panel.argtypes = [C.POINTER(_cabi.Batch), C.c_int]
+        _hs.hostsim_fit_general.argtypes = [C.POINTER(_cabi.Batch), C.c_int]
     return _hs
 
 
@@ -93,8 +95,11 @@ def run(times, data, *, n_fits, n_modes, window, t0, lpf=4, eval_only=False, dt=
 
 
 def run_struct(times, data, *, n_fits, n_modes, window, t0, omega, coef=None, eval_only=False, dt=None,
-               uniform_weights=0, C_in=None, want_model=False, descending=False):
-    """K3 (csrc/fit_struct.cuh): the kernel function itself on an emulated CTA per fit.  ``data`` is
+               uniform_weights=0, C_in=None, want_model=False, descending=False, panel=False, general=False,
+               omega_rows=None, coef_rows=None):
+    """K3 (csrc/fit_struct.cuh) or, with ``panel=True``, K4 (csrc/fit_panel.cuh, its DMMA emulated with the
+    PTX fragment layout) or, with ``general=True``, K2 (csrc/fit_general.cuh): the kernel function itself on an
+    emulated CTA per fit.  ``data`` is
     (L, K_tot); ``omega`` (N,) shared by all fits; ``coef`` (L, N) or None (single series, no table)."""
     times = np.ascontiguousarray(times, dtype=float)
     data = np.ascontiguousarray(np.atleast_2d(data), dtype=complex)
@@ -120,6 +125,14 @@ def run_struct(times, data, *, n_fits, n_modes, window, t0, omega, coef=None, ev
         ci = np.zeros(n_fits, np.int32)
         keep += [cf, ci]
         kw.update(coef=_p(cf), coef_index=_p(ci), n_coef=1)
+    if omega_rows is not None:                       # per-sample frequencies [N][K_tot] (dynamic fits)
+        orows = np.ascontiguousarray(omega_rows, dtype=complex)
+        keep.append(orows)
+        kw.update(omega_rows=_p(orows))
+    if coef_rows is not None:                        # per-sample mixing coefficients [L][N][K_tot] (K2 only)
+        crows = np.ascontiguousarray(coef_rows, dtype=complex)
+        keep.append(crows)
+        kw.update(coef_rows=_p(crows))
     if dt is None:
         dt = nominal_step(times[kw["row_begin_all"]:kw["row_end_all"]], float(np.max(np.abs(om))))
     Mmax = kw["row_end_all"] - kw["row_begin_all"]
@@ -131,6 +144,7 @@ def run_struct(times, data, *, n_fits, n_modes, window, t0, omega, coef=None, ev
                     times=_p(times), data=_p(data), dt_nominal=float(dt), C=_p(Cbuf), mismatch=_p(mm),
                     residual=_p(res), status=_p(st), model=_p(model), model_stride=L * Mmax if want_model else 0,
                     uniform_weights=int(uniform_weights), **kw)
-    rc = lib().hostsim_fit_struct(C.byref(b), (1 if eval_only else 0) | (2 if descending else 0))
+    entry = lib().hostsim_fit_general if general else lib().hostsim_fit_panel if panel else lib().hostsim_fit_struct
+    rc = entry(C.byref(b), (1 if eval_only else 0) | (2 if descending else 0))
     assert rc == 0, rc
     return dict(C=Cbuf, mismatch=mm, residual=res, status=st, model=model, dt=dt)

@@ -332,9 +332,10 @@ def test_pair_kernel_emulated_grid_matches_small_kernel():
 
 
 # ---------------------------------------------------------------------------------------
-# K3 (csrc/fit_struct.cuh): the kernel function itself, one emulated CTA per fit — all threads as
-# fibers, warp shuffles and __syncthreads emulated, the threads resumed in ascending and in
-# descending order between barriers (the stand-in for racecheck, which the GPU pool does not offer).
+# K3 (csrc/fit_struct.cuh) and K4 (csrc/fit_panel.cuh): the kernel functions themselves, one emulated
+# CTA per fit — all threads as fibers, warp shuffles / mma.sync / __syncthreads emulated, the threads
+# resumed in ascending and in descending order between barriers (the stand-in for racecheck, which
+# the GPU pool does not offer).
 
 def _stack(N, L, K_tot, seed, uniform=True):
     rng = np.random.default_rng(seed)
@@ -349,12 +350,16 @@ def _stack(N, L, K_tot, seed, uniform=True):
 
 
 @pytest.mark.parametrize("descending", [False, True])
+@pytest.mark.parametrize("kernel", ["k3", "k4"])
 @pytest.mark.parametrize("N,L,use_coef", [(3, 2, True), (10, 3, True), (12, 1, False), (9, 7, True), (20, 5, True),
-                                          (40, 21, True)])
-def test_struct_kernel_emulated_cta_vs_numpy(N, L, use_coef, descending):
-    """Structured two-phase QR (K3) on uniform grids (fast mismatch and second pass, model output,
+                                          (40, 21, True), (44, 21, True)])
+def test_struct_kernel_emulated_cta_vs_numpy(N, L, use_coef, kernel, descending):
+    """Structured two-phase QR — K3, and K4 (blocked, trailing update on mma.sync.m8n8k4.f64, emulated
+    with the PTX fragment layout) — on uniform grids (fast mismatch and second pass, model output,
     eval-only) and on a non-uniform grid (direct evaluation), against numpy lstsq on the explicit
     stacked matrix."""
+    if kernel == "k3" and N + L > 64:
+        pytest.skip("K3 takes at most 64 columns")
     for uniform in (True, False):
         K_tot = 330 if N < 40 else 200
         times, data, freq, coef = _stack(N, L, K_tot, seed=N * 100 + L, uniform=uniform)
@@ -366,7 +371,7 @@ def test_struct_kernel_emulated_cta_vs_numpy(N, L, use_coef, descending):
         mm_ref = orc.multimode_mismatch(times[rb:re], {i: model[i * K:(i + 1) * K] for i in range(L)},
                                         {i: data[i, rb:re] for i in range(L)})
         kw = dict(n_fits=1, n_modes=N, window=(rb, re), t0=t0, omega=freq, coef=coef if (use_coef or L > 1) else None,
-                  dt=0.1 if uniform else 0.0, descending=descending)
+                  dt=0.1 if uniform else 0.0, descending=descending, panel=kernel == "k4")
         out = hs.run_struct(times, data, want_model=True, **kw)
         assert out["status"][0] == 0
         assert np.max(np.abs(out["C"][0] - C_ref)) / np.max(np.abs(C_ref)) < cases.amp_tol(s), (uniform,)
@@ -381,7 +386,8 @@ def test_struct_kernel_emulated_cta_vs_numpy(N, L, use_coef, descending):
             assert abs(fast["mismatch"][0] - mm_ref) < 1e-10
 
 
-def test_struct_kernel_emulated_sweep_with_ragged_windows():
+@pytest.mark.parametrize("panel", [False, True])
+def test_struct_kernel_emulated_sweep_with_ragged_windows(panel):
     """Several fits, each with its own window and start time (a t0 sweep of a multimode fit)."""
     N, L, B = 10, 3, 6
     times, data, freq, coef = _stack(N, L, 300, seed=7)
@@ -389,7 +395,8 @@ def test_struct_kernel_emulated_sweep_with_ragged_windows():
     rb = rng.integers(0, 40, B).astype(np.int32)
     re = (rb + rng.integers(90, 250, B)).astype(np.int32)
     t0 = times[rb] - 0.03
-    out = hs.run_struct(times, data, n_fits=B, n_modes=N, window=(rb, re), t0=t0, omega=freq, coef=coef, dt=0.1)
+    out = hs.run_struct(times, data, n_fits=B, n_modes=N, window=(rb, re), t0=t0, omega=freq, coef=coef, dt=0.1,
+                        panel=panel)
     for b in range(B):
         sl = slice(rb[b], re[b])
         K = re[b] - rb[b]
@@ -398,3 +405,37 @@ def test_struct_kernel_emulated_sweep_with_ragged_windows():
         mm_ref = orc.multimode_mismatch(times[sl], {i: m_ref[i * K:(i + 1) * K] for i in range(L)},
                                         {i: data[i, sl] for i in range(L)})
         assert abs(out["mismatch"][b] - mm_ref) < 1e-10
+
+
+@pytest.mark.parametrize("descending", [False, True])
+@pytest.mark.parametrize("N,L", [(3, 2), (10, 3), (12, 1), (17, 3)])
+def test_general_kernel_emulated_cta_vs_numpy(N, L, descending):
+    """K2 (streamed dense Householder, csrc/fit_general.cuh) with a constant mixing table, and with
+    per-sample frequencies and mixing coefficients (the dynamic multimode fit, the one case only K2
+    takes), against numpy lstsq on the explicit matrix."""
+    times, data, freq, coef = _stack(N, L, 260, seed=N * 10 + L)
+    rb, re, t0 = 3, 241, float(times[3])
+    K = re - rb
+    a, C_ref, res_ref, rank, s, model = orc.lstsq_fit(times[rb:re], data[:, rb:re].reshape(-1), freq, t0, coef)
+    mm_ref = orc.multimode_mismatch(times[rb:re], {i: model[i * K:(i + 1) * K] for i in range(L)},
+                                    {i: data[i, rb:re] for i in range(L)})
+    out = hs.run_struct(times, data, n_fits=1, n_modes=N, window=(rb, re), t0=t0, omega=freq, coef=coef, dt=0.0,
+                        general=True, descending=descending)
+    assert out["status"][0] == 0
+    assert np.max(np.abs(out["C"][0] - C_ref)) / np.max(np.abs(C_ref)) < cases.amp_tol(s)
+    assert abs(out["mismatch"][0] - mm_ref) < 1e-10
+    # dynamic spectrum: frequencies and coefficients drift with the sample
+    drift = 1.0 + 0.02 * np.exp(-np.arange(len(times)) / 60.0)
+    omega_rows = freq[:, None] * drift[None, :]
+    coef_rows = coef[:, :, None] * (1.0 + 0.05j * (drift[None, None, :] - 1.0))
+    tau = times[rb:re] - t0
+    A = np.concatenate([coef_rows[i][:, rb:re].T * np.exp(-1j * omega_rows[:, rb:re].T * tau[:, None]) for i in range(L)])
+    d = data[:, rb:re].reshape(-1)
+    C_dyn, _, rank, sv = np.linalg.lstsq(A, d, rcond=None)
+    m_dyn = A @ C_dyn
+    mm_dyn = orc.multimode_mismatch(times[rb:re], {i: m_dyn[i * K:(i + 1) * K] for i in range(L)},
+                                    {i: data[i, rb:re] for i in range(L)})
+    dyn = hs.run_struct(times, data, n_fits=1, n_modes=N, window=(rb, re), t0=t0, omega=freq, coef=coef, dt=0.0,
+                        general=True, descending=descending, omega_rows=omega_rows, coef_rows=coef_rows)
+    assert np.max(np.abs(dyn["C"][0] - C_dyn)) / np.max(np.abs(C_dyn)) < cases.amp_tol(sv)
+    assert abs(dyn["mismatch"][0] - mm_dyn) < 1e-10
