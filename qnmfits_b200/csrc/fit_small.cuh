@@ -876,14 +876,13 @@ QF_HD void small_fast_finalize(const FitParams &p, const SmallLane &L, const dou
     peer_publish(p, L.fit, mm);
 }
 
-#ifndef QNMFIT_HOSTSIM
 // ---------------------------------------------------------------------------
 // The kernel.  STAGED: the union of all windows (times + data, 24 B/row) is copied
 // into shared memory once per CTA and reused by every fit the CTA handles.
 template <int N, int THREADS, bool STAGED>
 __global__ void __launch_bounds__(THREADS, 1) fit_small_kernel(const __grid_constant__ FitParams p)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    QF_DYN_SMEM(smem_raw);
     SmallSmem<N, THREADS> sm;
     const int lpf = p.lanes_per_fit;
     const int fpc = THREADS / lpf;
@@ -962,4 +961,3 @@ __global__ void __launch_bounds__(THREADS, 1) fit_small_kernel(const __grid_cons
     }
     small_finalize(p, L, sums, status);
 }
-#endif  // !QNMFIT_HOSTSIM

@@ -131,6 +131,46 @@ static void run(const qnmfit_batch *b, int lpf, bool eval)
     }
 }
 
+// K1 once more, this time the kernel function itself on an emulated CTA (staging of the window,
+// table fill, __syncthreads, R-combine behind __syncwarp, butterflies), threads in either order.
+template <int N>
+static void run_small_cta(const qnmfit_batch *b, int lpf, bool eval, bool staged, bool descending)
+{
+    FitParams p;
+    fill_params(b, lpf, eval, &p);
+    const int fpc = HS_THREADS / lpf;
+    const int ctas = (b->n_fits + fpc - 1) / fpc;
+    const int rows = b->row_end_all - b->row_begin_all;
+    p.stage_begin = b->row_begin_all;
+    p.stage_rows = staged ? rows : 0;
+    std::vector<unsigned char> smem(SmallSmem<N, HS_THREADS>::bytes(fpc, p.stage_rows) + 64);
+    for (int cta = 0; cta < ctas; ++cta) {
+        if (staged) hswarp::run_cta(HS_THREADS, [&](int) { fit_small_kernel<N, HS_THREADS, true>(p); }, descending, cta, smem.data());
+        else hswarp::run_cta(HS_THREADS, [&](int) { fit_small_kernel<N, HS_THREADS, false>(p); }, descending, cta, smem.data());
+    }
+}
+
+// eval: bit 0 eval-only, bit 1 descending thread order, bit 2 staged window
+extern "C" int hostsim_fit_small_cta(const qnmfit_batch *b, int lpf, int eval)
+{
+    if (!b || b->struct_size != (int)sizeof(qnmfit_batch)) return QNMFIT_E_ABI;
+    if (b->n_series != 1 || b->n_modes < 1 || b->n_modes > 8) return QNMFIT_E_SHAPE;
+    if (lpf < 1 || lpf > 32 || (lpf & (lpf - 1))) return QNMFIT_E_SHAPE;
+    const bool descending = (eval & 2) != 0, staged = (eval & 4) != 0 && !b->series_index;
+    const bool ev = (eval & 1) != 0;
+    switch (b->n_modes) {
+    case 1: run_small_cta<1>(b, lpf, ev, staged, descending); break;
+    case 2: run_small_cta<2>(b, lpf, ev, staged, descending); break;
+    case 3: run_small_cta<3>(b, lpf, ev, staged, descending); break;
+    case 4: run_small_cta<4>(b, lpf, ev, staged, descending); break;
+    case 5: run_small_cta<5>(b, lpf, ev, staged, descending); break;
+    case 6: run_small_cta<6>(b, lpf, ev, staged, descending); break;
+    case 7: run_small_cta<7>(b, lpf, ev, staged, descending); break;
+    case 8: run_small_cta<8>(b, lpf, ev, staged, descending); break;
+    }
+    return 0;
+}
+
 // K1p: the CTA's shared memory is set up serially, then each warp runs in lock step.
 #define HSP_THREADS 64
 template <int N>

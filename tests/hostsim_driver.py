@@ -18,6 +18,7 @@ def lib():
         _hs = C.CDLL(os.path.join(ROOT, "tests", "hostsim", "libqnmfit_hostsim.so"))
         _hs.hostsim_fit_small.argtypes = [C.POINTER(_cabi.Batch), C.c_int, C.c_int]
         _hs.hostsim_fit_pair.argtypes = [C.POINTER(_cabi.Batch), C.c_int, C.c_int]
+        _hs.hostsim_fit_small_cta.argtypes = [C.POINTER(_cabi.Batch), C.c_int, C.c_int]
         _hs.hostsim_fit_struct.argtypes = [C.POINTER(_cabi.Batch), C.c_int]
         _hs.hostsim_fit_panel.argtypes = [C.POINTER(_cabi.Batch), C.c_int]
         _hs.hostsim_fit_general.argtypes = [C.POINTER(_cabi.Batch), C.c_int]
@@ -31,9 +32,11 @@ def _p(a):
 def run(times, data, *, n_fits, n_modes, window, t0, lpf=4, eval_only=False, dt=None,
         anchor_rows=0, omega=None, omega_shared=False, table=None, mode_ptr=None, inv_Mf=None,
         delta_factor=None, n_chi=0, n_mf=0, first_fit=0, C_in=None, want_model=False,
-        uniform_weights=0, series_index=None, pair=False, descending=False):
+        uniform_weights=0, series_index=None, pair=False, descending=False, cta=False, staged=False):
     """``pair=True``: the K1p code (csrc/fit_pair.cuh), warps in lock step (``descending``: the lanes
-    of a warp are resumed 31 .. 0 instead of 0 .. 31 between collectives); otherwise K1."""
+    of a warp are resumed 31 .. 0 instead of 0 .. 31 between collectives); ``cta=True``: K1's kernel
+    function itself on an emulated CTA (``staged``: with the window staged in shared memory);
+    otherwise K1's stages called lane by lane."""
     times = np.ascontiguousarray(times, dtype=float)
     data = np.ascontiguousarray(data, dtype=complex)
     keep = [times, data]
@@ -88,8 +91,9 @@ def run(times, data, *, n_fits, n_modes, window, t0, lpf=4, eval_only=False, dt=
                     dt_nominal=float(dt), anchor_rows=anchor_rows, C=_p(Cbuf), mismatch=_p(mm),
                     residual=_p(res), R=_p(R), status=_p(st), model=_p(model),
                     model_stride=Mmax if want_model else 0, uniform_weights=int(uniform_weights), **kw)
-    entry = lib().hostsim_fit_pair if pair else lib().hostsim_fit_small
-    rc = entry(C.byref(b), int(lpf), (1 if eval_only else 0) | (2 if pair and descending else 0))
+    entry = lib().hostsim_fit_pair if pair else lib().hostsim_fit_small_cta if cta else lib().hostsim_fit_small
+    rc = entry(C.byref(b), int(lpf), (1 if eval_only else 0) | (2 if (pair or cta) and descending else 0)
+               | (4 if cta and staged else 0))
     assert rc == 0, rc
     return dict(C=Cbuf, mismatch=mm, residual=res, R=R, status=st, model=model, dt=dt)
 
