@@ -134,7 +134,7 @@ static void run(const qnmfit_batch *b, int lpf, bool eval)
 // K1 once more, this time the kernel function itself on an emulated CTA (staging of the window,
 // table fill, __syncthreads, R-combine behind __syncwarp, butterflies), threads in either order.
 template <int N>
-static void run_small_cta(const qnmfit_batch *b, int lpf, bool eval, bool staged, bool descending)
+static void run_small_cta(const qnmfit_batch *b, int lpf, bool eval, bool staged, int order)
 {
     FitParams p;
     fill_params(b, lpf, eval, &p);
@@ -145,28 +145,30 @@ static void run_small_cta(const qnmfit_batch *b, int lpf, bool eval, bool staged
     p.stage_rows = staged ? rows : 0;
     std::vector<unsigned char> smem(SmallSmem<N, HS_THREADS>::bytes(fpc, p.stage_rows) + 64);
     for (int cta = 0; cta < ctas; ++cta) {
-        if (staged) hswarp::run_cta(HS_THREADS, [&](int) { fit_small_kernel<N, HS_THREADS, true>(p); }, descending, cta, smem.data());
-        else hswarp::run_cta(HS_THREADS, [&](int) { fit_small_kernel<N, HS_THREADS, false>(p); }, descending, cta, smem.data());
+        if (staged) hswarp::run_cta(HS_THREADS, [&](int) { fit_small_kernel<N, HS_THREADS, true>(p); }, order, cta, smem.data());
+        else hswarp::run_cta(HS_THREADS, [&](int) { fit_small_kernel<N, HS_THREADS, false>(p); }, order, cta, smem.data());
     }
 }
 
-// eval: bit 0 eval-only, bit 1 descending thread order, bit 2 staged window
+// eval: bit 0 eval-only, bit 1 staged window, bits 8.. thread order (hostsim_warp.h: 0 ascending,
+// 1 descending, >= 2 seed of a shuffled order)
 extern "C" int hostsim_fit_small_cta(const qnmfit_batch *b, int lpf, int eval)
 {
     if (!b || b->struct_size != (int)sizeof(qnmfit_batch)) return QNMFIT_E_ABI;
     if (b->n_series != 1 || b->n_modes < 1 || b->n_modes > 8) return QNMFIT_E_SHAPE;
     if (lpf < 1 || lpf > 32 || (lpf & (lpf - 1))) return QNMFIT_E_SHAPE;
-    const bool descending = (eval & 2) != 0, staged = (eval & 4) != 0 && !b->series_index;
+    const int order = eval >> 8;
+    const bool staged = (eval & 2) != 0 && !b->series_index;
     const bool ev = (eval & 1) != 0;
     switch (b->n_modes) {
-    case 1: run_small_cta<1>(b, lpf, ev, staged, descending); break;
-    case 2: run_small_cta<2>(b, lpf, ev, staged, descending); break;
-    case 3: run_small_cta<3>(b, lpf, ev, staged, descending); break;
-    case 4: run_small_cta<4>(b, lpf, ev, staged, descending); break;
-    case 5: run_small_cta<5>(b, lpf, ev, staged, descending); break;
-    case 6: run_small_cta<6>(b, lpf, ev, staged, descending); break;
-    case 7: run_small_cta<7>(b, lpf, ev, staged, descending); break;
-    case 8: run_small_cta<8>(b, lpf, ev, staged, descending); break;
+    case 1: run_small_cta<1>(b, lpf, ev, staged, order); break;
+    case 2: run_small_cta<2>(b, lpf, ev, staged, order); break;
+    case 3: run_small_cta<3>(b, lpf, ev, staged, order); break;
+    case 4: run_small_cta<4>(b, lpf, ev, staged, order); break;
+    case 5: run_small_cta<5>(b, lpf, ev, staged, order); break;
+    case 6: run_small_cta<6>(b, lpf, ev, staged, order); break;
+    case 7: run_small_cta<7>(b, lpf, ev, staged, order); break;
+    case 8: run_small_cta<8>(b, lpf, ev, staged, order); break;
     }
     return 0;
 }
@@ -174,7 +176,7 @@ extern "C" int hostsim_fit_small_cta(const qnmfit_batch *b, int lpf, int eval)
 // K1p: the CTA's shared memory is set up serially, then each warp runs in lock step.
 #define HSP_THREADS 64
 template <int N>
-static void run_pair(const qnmfit_batch *b, int lpf, bool eval, bool descending)
+static void run_pair(const qnmfit_batch *b, int lpf, bool eval, int order)
 {
     constexpr int CS = k1p_cs_ct(N), MB = k1p_mb_ct(N);
     typedef PairLayout<N, CS> LY;
@@ -195,28 +197,28 @@ static void run_pair(const qnmfit_batch *b, int lpf, bool eval, bool descending)
                 const int tid = warp * 32 + lane;
                 const SmallLane L = pair_lane_setup<CS>(p, cta, tid, HSP_THREADS, true, MB, 0);
                 pair_lane_body<N, CS, MB, HSP_THREADS>(p, sm, L, tid);
-            }, descending);
+            }, order);
     }
 }
 
 // All pointers in *b are HOST pointers here.  Column counts: a sample of every configuration
 // (2 / 4 / 8 lanes per row slice, 4 / 5 / 6 / 8 rows per block).
-// eval: bit 0 = eval-only launch, bit 1 = resume the lanes of a warp in descending order
+// eval: bit 0 = eval-only launch, bits 8.. thread order
 extern "C" int hostsim_fit_pair(const qnmfit_batch *b, int lpf, int eval)
 {
-    const bool descending = (eval & 2) != 0;
+    const int order = eval >> 8;
     eval &= 1;
     if (!b || b->struct_size != (int)sizeof(qnmfit_batch)) return QNMFIT_E_ABI;
     if (b->n_series != 1) return QNMFIT_E_SHAPE;
     if (lpf < 1 || lpf > 32 || (lpf & (lpf - 1)) || lpf < k1p_cs_ct(b->n_modes)) return QNMFIT_E_SHAPE;
     switch (b->n_modes) {
-    case 9: run_pair<9>(b, lpf, eval, descending); break;
-    case 11: run_pair<11>(b, lpf, eval, descending); break;
-    case 12: run_pair<12>(b, lpf, eval, descending); break;
-    case 14: run_pair<14>(b, lpf, eval, descending); break;
-    case 16: run_pair<16>(b, lpf, eval, descending); break;
-    case 19: run_pair<19>(b, lpf, eval, descending); break;
-    case 24: run_pair<24>(b, lpf, eval, descending); break;
+    case 9: run_pair<9>(b, lpf, eval, order); break;
+    case 11: run_pair<11>(b, lpf, eval, order); break;
+    case 12: run_pair<12>(b, lpf, eval, order); break;
+    case 14: run_pair<14>(b, lpf, eval, order); break;
+    case 16: run_pair<16>(b, lpf, eval, order); break;
+    case 19: run_pair<19>(b, lpf, eval, order); break;
+    case 24: run_pair<24>(b, lpf, eval, order); break;
     default: return QNMFIT_E_SHAPE;
     }
     return 0;
@@ -227,7 +229,7 @@ extern "C" int hostsim_fit_pair(const qnmfit_batch *b, int lpf, int eval)
 extern "C" int hostsim_fit_struct(const qnmfit_batch *b, int eval)
 {
     if (!b || b->struct_size != (int)sizeof(qnmfit_batch)) return QNMFIT_E_ABI;
-    const bool descending = (eval & 2) != 0;
+    const int order = eval >> 8;
     eval &= 1;
     constexpr int G = 4, RPT = 16;
     const int N = b->n_modes, L = b->n_series;
@@ -240,7 +242,7 @@ extern "C" int hostsim_fit_struct(const qnmfit_batch *b, int eval)
     const int threads = G * 32 * ((N + L + 31) / 32);
     std::vector<unsigned char> smem(Struct3Smem::bytes(N, L) + 64);
     for (int fit = 0; fit < b->n_fits; ++fit)
-        hswarp::run_cta(threads, [&](int) { fit_struct3_kernel<G, RPT>(p); }, descending, fit, smem.data());
+        hswarp::run_cta(threads, [&](int) { fit_struct3_kernel<G, RPT>(p); }, order, fit, smem.data());
     return 0;
 }
 
@@ -249,7 +251,7 @@ extern "C" int hostsim_fit_struct(const qnmfit_batch *b, int eval)
 extern "C" int hostsim_fit_general(const qnmfit_batch *b, int eval)
 {
     if (!b || b->struct_size != (int)sizeof(qnmfit_batch)) return QNMFIT_E_ABI;
-    const bool descending = (eval & 2) != 0;
+    const int order = eval >> 8;
     eval &= 1;
     const int N = b->n_modes, L = b->n_series;
     if (N < 1 || L < 1 || N > 64 || b->series_index) return QNMFIT_E_SHAPE;
@@ -264,7 +266,7 @@ extern "C" int hostsim_fit_general(const qnmfit_batch *b, int eval)
     if (!TK) return QNMFIT_E_SHAPE;
     std::vector<unsigned char> smem(GeneralSmem::bytes(N, L, TR, TK) + 64);
     for (int fit = 0; fit < b->n_fits; ++fit)
-        hswarp::run_cta(K2_THREADS, [&](int) { fit_general_kernel(p, TR, TK); }, descending, fit, smem.data());
+        hswarp::run_cta(K2_THREADS, [&](int) { fit_general_kernel(p, TR, TK); }, order, fit, smem.data());
     return 0;
 }
 
@@ -273,7 +275,7 @@ extern "C" int hostsim_fit_general(const qnmfit_batch *b, int eval)
 extern "C" int hostsim_fit_panel(const qnmfit_batch *b, int eval)
 {
     if (!b || b->struct_size != (int)sizeof(qnmfit_batch)) return QNMFIT_E_ABI;
-    const bool descending = (eval & 2) != 0;
+    const int order = eval >> 8;
     eval &= 1;
     const int N = b->n_modes, L = b->n_series;
     if (N < 1 || L < 1 || N > 64 || L > 64 || b->coef_rows || b->series_index) return QNMFIT_E_SHAPE;
@@ -284,7 +286,7 @@ extern "C" int hostsim_fit_panel(const qnmfit_batch *b, int eval)
     p.fast_mismatch = (!eval && b->uniform_weights && b->dt_nominal > 0.0 && !b->model) ? 1 : 0;
     std::vector<unsigned char> smem(PanelSmem::bytes(N, L) + 64);
     for (int fit = 0; fit < b->n_fits; ++fit)
-        hswarp::run_cta(K4_THREADS, [&](int) { fit_panel_kernel(p); }, descending, fit, smem.data());
+        hswarp::run_cta(K4_THREADS, [&](int) { fit_panel_kernel(p); }, order, fit, smem.data());
     return 0;
 }
 

@@ -9,8 +9,9 @@
 // their control flow around shuffles is warp-uniform — and when the CTA dead-locks (a barrier not
 // reached by every thread).
 //
-// Between two collectives a thread runs ALONE, the threads one after another in ascending or
-// descending order.  That is stricter than the hardware about the order of shared-memory
+// Between two collectives a thread runs ALONE, the threads one after another in ascending order,
+// in descending order, or (order >= 2) in a pseudo-random order drawn anew for every pass of the
+// scheduler from the seed `order`.  That is stricter than the hardware about the order of shared-memory
 // accesses of different threads: a load that relies on another thread's earlier store (or must
 // precede another thread's later store) with no barrier in between goes wrong in one of the two
 // orders.  compute-sanitizer's racecheck is not available on the GPU pool of this project; this is
@@ -42,7 +43,7 @@ struct Cta {
     std::vector<int> warp_arrived;
     int cta_arrived;
     int nthreads, cur, block;
-    bool descending;
+    int order;                                    // 0 ascending, 1 descending, >= 2: seed of a shuffled order per pass
     unsigned char *smem;
     const std::function<void(int)> *body;
 };
@@ -111,12 +112,12 @@ inline void trampoline()
 }
 
 // run body(tid) for the nthreads (a multiple of 32) threads of one CTA in lock step
-inline void run_cta(int nthreads, const std::function<void(int)> &body, bool descending = false, int block = 0,
+inline void run_cta(int nthreads, const std::function<void(int)> &body, int order = 0, int block = 0,
                     unsigned char *smem = nullptr)
 {
     if (nthreads % LANES) fail("run_cta: the thread count must be a multiple of 32");
     Cta c;
-    c.nthreads = nthreads; c.body = &body; c.descending = descending; c.block = block; c.smem = smem;
+    c.nthreads = nthreads; c.body = &body; c.order = order; c.block = block; c.smem = smem;
     c.ctx.resize(nthreads);
     c.stacks.reset(new char[(size_t)nthreads * STACK_BYTES]);
     c.done.assign(nthreads, 0); c.wait.assign(nthreads, 0); c.count.assign(nthreads, 0);
@@ -134,10 +135,19 @@ inline void run_cta(int nthreads, const std::function<void(int)> &body, bool des
         c.ctx[t].uc_link = &c.sched;
         makecontext(&c.ctx[t], (void (*)())trampoline, 0);
     }
+    std::vector<int> perm(nthreads);
+    for (int i = 0; i < nthreads; ++i) perm[i] = order == 1 ? nthreads - 1 - i : i;
+    unsigned long long rng = 0x9e3779b97f4a7c15ull * (unsigned long long)(order + 1) + (unsigned long long)block;
     for (;;) {
+        if (order >= 2)                               // Fisher-Yates with a xorshift generator
+            for (int i = nthreads - 1; i > 0; --i) {
+                rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+                const int j = (int)(rng % (unsigned long long)(i + 1));
+                const int tmp = perm[i]; perm[i] = perm[j]; perm[j] = tmp;
+            }
         bool ran = false, all_done = true;
         for (int i = 0; i < nthreads; ++i) {
-            const int t = descending ? nthreads - 1 - i : i;
+            const int t = perm[i];
             if (c.done[t]) continue;
             all_done = false;
             if (c.wait[t]) continue;
@@ -151,9 +161,9 @@ inline void run_cta(int nthreads, const std::function<void(int)> &body, bool des
     current() = outer;
 }
 
-inline void run_warp(const std::function<void(int)> &body, bool descending = false)
+inline void run_warp(const std::function<void(int)> &body, int order = 0)
 {
-    run_cta(LANES, body, descending);
+    run_cta(LANES, body, order);
 }
 
 }  // namespace hswarp

@@ -32,11 +32,11 @@ def _p(a):
 def run(times, data, *, n_fits, n_modes, window, t0, lpf=4, eval_only=False, dt=None,
         anchor_rows=0, omega=None, omega_shared=False, table=None, mode_ptr=None, inv_Mf=None,
         delta_factor=None, n_chi=0, n_mf=0, first_fit=0, C_in=None, want_model=False,
-        uniform_weights=0, series_index=None, pair=False, descending=False, cta=False, staged=False):
-    """``pair=True``: the K1p code (csrc/fit_pair.cuh), warps in lock step (``descending``: the lanes
-    of a warp are resumed 31 .. 0 instead of 0 .. 31 between collectives); ``cta=True``: K1's kernel
-    function itself on an emulated CTA (``staged``: with the window staged in shared memory);
-    otherwise K1's stages called lane by lane."""
+        uniform_weights=0, series_index=None, pair=False, order=0, cta=False, staged=False):
+    """``pair=True``: the K1p code (csrc/fit_pair.cuh), warps in lock step; ``cta=True``: K1's kernel
+    function itself on an emulated CTA (``staged``: with the window staged in shared memory); otherwise
+    K1's stages called lane by lane.  ``order``: how the emulated threads are resumed between
+    collectives — 0 ascending, 1 descending, >= 2 seed of an order shuffled anew for every pass."""
     times = np.ascontiguousarray(times, dtype=float)
     data = np.ascontiguousarray(data, dtype=complex)
     keep = [times, data]
@@ -92,14 +92,14 @@ def run(times, data, *, n_fits, n_modes, window, t0, lpf=4, eval_only=False, dt=
                     residual=_p(res), R=_p(R), status=_p(st), model=_p(model),
                     model_stride=Mmax if want_model else 0, uniform_weights=int(uniform_weights), **kw)
     entry = lib().hostsim_fit_pair if pair else lib().hostsim_fit_small_cta if cta else lib().hostsim_fit_small
-    rc = entry(C.byref(b), int(lpf), (1 if eval_only else 0) | (2 if (pair or cta) and descending else 0)
-               | (4 if cta and staged else 0))
+    rc = entry(C.byref(b), int(lpf), (1 if eval_only else 0) | (2 if cta and staged else 0)
+               | (int(order) << 8 if (pair or cta) else 0))
     assert rc == 0, rc
     return dict(C=Cbuf, mismatch=mm, residual=res, R=R, status=st, model=model, dt=dt)
 
 
 def run_struct(times, data, *, n_fits, n_modes, window, t0, omega, coef=None, eval_only=False, dt=None,
-               uniform_weights=0, C_in=None, want_model=False, descending=False, panel=False, general=False,
+               uniform_weights=0, C_in=None, want_model=False, order=0, panel=False, general=False,
                omega_rows=None, coef_rows=None):
     """K3 (csrc/fit_struct.cuh) or, with ``panel=True``, K4 (csrc/fit_panel.cuh, its DMMA emulated with the
     PTX fragment layout) or, with ``general=True``, K2 (csrc/fit_general.cuh): the kernel function itself on an
@@ -149,6 +149,6 @@ def run_struct(times, data, *, n_fits, n_modes, window, t0, omega, coef=None, ev
                     residual=_p(res), status=_p(st), model=_p(model), model_stride=L * Mmax if want_model else 0,
                     uniform_weights=int(uniform_weights), **kw)
     entry = lib().hostsim_fit_general if general else lib().hostsim_fit_panel if panel else lib().hostsim_fit_struct
-    rc = entry(C.byref(b), (1 if eval_only else 0) | (2 if descending else 0))
+    rc = entry(C.byref(b), (1 if eval_only else 0) | (int(order) << 8))
     assert rc == 0, rc
     return dict(C=Cbuf, mismatch=mm, residual=res, status=st, model=model, dt=dt)

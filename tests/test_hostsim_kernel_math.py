@@ -283,14 +283,14 @@ def _damped_stack(N, S, K_tot, seed):
     return times, data, freq
 
 
-@pytest.mark.parametrize("descending", [False, True])
+@pytest.mark.parametrize("order", [0, 1, 5])
 @pytest.mark.parametrize("N,lpf", [(9, 2), (9, 8), (11, 4), (12, 4), (14, 8), (16, 4), (19, 16), (24, 8), (24, 32)])
-def test_pair_kernel_emulated_in_lock_step_vs_numpy(N, lpf, descending):
+def test_pair_kernel_emulated_in_lock_step_vs_numpy(N, lpf, order):
     """Seven fits sharing warps: windows of different lengths (lanes run blocks they have no rows
     for), per-fit start times and data series; second pass with model output, fast mismatch and
     the eval-only path, each fit against numpy lstsq on its explicit matrix.  Between collectives
-    the lanes run one after another, in ascending and in descending order: a cross-lane
-    shared-memory dependence that no collective orders fails in one of the two."""
+    the lanes run one after another, in ascending, descending and shuffled order: a cross-lane
+    shared-memory dependence that no collective orders fails in one of them."""
     times, data, freq = _damped_stack(N, 2, 360, seed=70 + N)
     rng = np.random.default_rng(N + lpf)
     B = 7
@@ -300,7 +300,7 @@ def test_pair_kernel_emulated_in_lock_step_vs_numpy(N, lpf, descending):
     t0 = times[rb] - 0.03
     which = rng.integers(0, 2, B).astype(np.int32)
     kw = dict(n_fits=B, n_modes=N, window=(rb, re), t0=t0, lpf=lpf, omega=freq.reshape(1, -1), omega_shared=True,
-              series_index=which, pair=True, dt=0.1, descending=descending)
+              series_index=which, pair=True, dt=0.1, order=order)
     out = hs.run(times, data, want_model=True, **kw)
     fast = hs.run(times, data, uniform_weights=1, **kw)
     ev = hs.run(times, data, eval_only=True, C_in=out["C"], **kw)
@@ -348,7 +348,7 @@ def test_pair_kernel_emulated_grid_matches_small_kernel():
 # ---------------------------------------------------------------------------------------
 # K3 (csrc/fit_struct.cuh) and K4 (csrc/fit_panel.cuh): the kernel functions themselves, one emulated
 # CTA per fit — all threads as fibers, warp shuffles / mma.sync / __syncthreads emulated, the threads
-# resumed in ascending and in descending order between barriers (the stand-in for racecheck, which
+# resumed in ascending, descending and shuffled order between barriers (the stand-in for racecheck, which
 # the GPU pool does not offer).
 
 def _stack(N, L, K_tot, seed, uniform=True):
@@ -363,11 +363,11 @@ def _stack(N, L, K_tot, seed, uniform=True):
     return times, data, freq, coef
 
 
-@pytest.mark.parametrize("descending", [False, True])
+@pytest.mark.parametrize("order", [0, 1, 5])
 @pytest.mark.parametrize("kernel", ["k3", "k4"])
 @pytest.mark.parametrize("N,L,use_coef", [(3, 2, True), (10, 3, True), (12, 1, False), (9, 7, True), (20, 5, True),
                                           (40, 21, True), (44, 21, True)])
-def test_struct_kernel_emulated_cta_vs_numpy(N, L, use_coef, kernel, descending):
+def test_struct_kernel_emulated_cta_vs_numpy(N, L, use_coef, kernel, order):
     """Structured two-phase QR — K3, and K4 (blocked, trailing update on mma.sync.m8n8k4.f64, emulated
     with the PTX fragment layout) — on uniform grids (fast mismatch and second pass, model output,
     eval-only) and on a non-uniform grid (direct evaluation), against numpy lstsq on the explicit
@@ -385,7 +385,7 @@ def test_struct_kernel_emulated_cta_vs_numpy(N, L, use_coef, kernel, descending)
         mm_ref = orc.multimode_mismatch(times[rb:re], {i: model[i * K:(i + 1) * K] for i in range(L)},
                                         {i: data[i, rb:re] for i in range(L)})
         kw = dict(n_fits=1, n_modes=N, window=(rb, re), t0=t0, omega=freq, coef=coef if (use_coef or L > 1) else None,
-                  dt=0.1 if uniform else 0.0, descending=descending, panel=kernel == "k4")
+                  dt=0.1 if uniform else 0.0, order=order, panel=kernel == "k4")
         out = hs.run_struct(times, data, want_model=True, **kw)
         assert out["status"][0] == 0
         assert np.max(np.abs(out["C"][0] - C_ref)) / np.max(np.abs(C_ref)) < cases.amp_tol(s), (uniform,)
@@ -421,9 +421,9 @@ def test_struct_kernel_emulated_sweep_with_ragged_windows(panel):
         assert abs(out["mismatch"][b] - mm_ref) < 1e-10
 
 
-@pytest.mark.parametrize("descending", [False, True])
+@pytest.mark.parametrize("order", [0, 1, 5])
 @pytest.mark.parametrize("N,L", [(3, 2), (10, 3), (12, 1), (17, 3)])
-def test_general_kernel_emulated_cta_vs_numpy(N, L, descending):
+def test_general_kernel_emulated_cta_vs_numpy(N, L, order):
     """K2 (streamed dense Householder, csrc/fit_general.cuh) with a constant mixing table, and with
     per-sample frequencies and mixing coefficients (the dynamic multimode fit, the one case only K2
     takes), against numpy lstsq on the explicit matrix."""
@@ -434,7 +434,7 @@ def test_general_kernel_emulated_cta_vs_numpy(N, L, descending):
     mm_ref = orc.multimode_mismatch(times[rb:re], {i: model[i * K:(i + 1) * K] for i in range(L)},
                                     {i: data[i, rb:re] for i in range(L)})
     out = hs.run_struct(times, data, n_fits=1, n_modes=N, window=(rb, re), t0=t0, omega=freq, coef=coef, dt=0.0,
-                        general=True, descending=descending)
+                        general=True, order=order)
     assert out["status"][0] == 0
     assert np.max(np.abs(out["C"][0] - C_ref)) / np.max(np.abs(C_ref)) < cases.amp_tol(s)
     assert abs(out["mismatch"][0] - mm_ref) < 1e-10
@@ -450,15 +450,15 @@ def test_general_kernel_emulated_cta_vs_numpy(N, L, descending):
     mm_dyn = orc.multimode_mismatch(times[rb:re], {i: m_dyn[i * K:(i + 1) * K] for i in range(L)},
                                     {i: data[i, rb:re] for i in range(L)})
     dyn = hs.run_struct(times, data, n_fits=1, n_modes=N, window=(rb, re), t0=t0, omega=freq, coef=coef, dt=0.0,
-                        general=True, descending=descending, omega_rows=omega_rows, coef_rows=coef_rows)
+                        general=True, order=order, omega_rows=omega_rows, coef_rows=coef_rows)
     assert np.max(np.abs(dyn["C"][0] - C_dyn)) / np.max(np.abs(C_dyn)) < cases.amp_tol(sv)
     assert abs(dyn["mismatch"][0] - mm_dyn) < 1e-10
 
 
-@pytest.mark.parametrize("descending", [False, True])
+@pytest.mark.parametrize("order", [0, 1, 5])
 @pytest.mark.parametrize("staged", [False, True])
 @pytest.mark.parametrize("N,lpf", [(1, 1), (5, 8), (8, 4)])
-def test_small_kernel_function_on_emulated_cta(N, lpf, staged, descending):
+def test_small_kernel_function_on_emulated_cta(N, lpf, staged, order):
     """K1's kernel function itself (fit_small_kernel: staging of the window, table fill,
     __syncthreads, R-combine behind __syncwarp, butterflies) on an emulated CTA, threads resumed in
     either order: a sweep with ragged windows must reproduce, bit for bit, what the stage-by-stage
@@ -472,7 +472,7 @@ def test_small_kernel_function_on_emulated_cta(N, lpf, staged, descending):
     kw = dict(n_fits=B, n_modes=N, window=(rb, re), t0=t0, lpf=lpf, omega=freq.reshape(1, -1), omega_shared=True, dt=0.1)
     for fast in (0, 1):
         ref = hs.run(times, data[0], uniform_weights=fast, **kw)
-        out = hs.run(times, data[0], uniform_weights=fast, cta=True, staged=staged, descending=descending, **kw)
+        out = hs.run(times, data[0], uniform_weights=fast, cta=True, staged=staged, order=order, **kw)
         assert np.array_equal(out["mismatch"], ref["mismatch"]) and np.array_equal(out["C"], ref["C"])
         assert np.array_equal(out["status"], ref["status"])
     for b in range(B):
