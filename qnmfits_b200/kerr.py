@@ -28,9 +28,10 @@ memory and, optionally, on disk (``QNMFITS_B200_KERR_CACHE=<dir>``).
 Pinned by ``tests/test_kerr_provider.py`` to literature values (Schwarzschild and Kerr
 frequencies of Leaver 1985 / Berti, Cardoso & Starinets 2009) and to the value the
 reference's own notebook prints, omega_220(chi = 0.7) = 0.53260024 - 0.08079287i
-(golden G2).  Not covered: the n >= 8 overtones of l = 2, whose
-sequences pass through the algebraically special frequency (the reference takes those from
-the Cook-Zalutskiy data files, ``qnm.py:60-122``).
+(golden G2).  Not covered: overtone n = 8 of l = 2, whose sequences
+start at the algebraically special frequency (the reference takes its multiplets from the
+Cook-Zalutskiy data files, ``qnm.py:60-122``); the l = 2 overtones below it (n >= 9, with
+Leaver's and the ``qnm`` package's index) are followed like any other sequence.
 """
 import math
 import os
@@ -226,7 +227,18 @@ def schwarzschild_omegas(s, l, n_max):
     have = _schw_cache.setdefault(key, [])
     while len(have) <= n_max:
         n = len(have)
-        if n == 0:
+        if abs(s) == 2 and l == 2 and n == 8:
+            # the algebraically special frequency (Chandrasekhar 1984; Leaver 1985 lists the
+            # root at 2M omega = -3.998 i): the continued fraction does not converge on the
+            # negative imaginary axis.  Kept as a place holder so that the overtones below it
+            # keep the index the `qnm` package (and Leaver's table) gives them.
+            have.append(complex(0.0, -2.0))
+            continue
+        if abs(s) == 2 and l == 2 and n == 9:
+            # first root past it, from Leaver (1985) table 1 / Berti, Cardoso & Starinets (2009):
+            # 2M omega = 0.126527 - 4.605289 i; Newton refines it on the n = 9 inversion
+            guesses = [complex(0.063263, -2.302645)]
+        elif n == 0:
             # eikonal estimate, accurate to ~10 % at l = 2: (l + 1/2 - i (n + 1/2)) / (3 sqrt 3)
             guesses = [complex((l + 0.5) / math.sqrt(27.0) * 0.78 + 0.1 * (l - 2) * 0.22, -0.5 / math.sqrt(27.0))]
         elif n == 1:
@@ -265,10 +277,11 @@ def compute_sequence(s, l, m, n, spins=SPIN_GRID, tol=INTERP_TOL):
     from scipy.interpolate import UnivariateSpline
     if l < max(abs(m), abs(s)):
         raise KeyError(f"no sequence for s={s}, l={l}, m={m}")
-    if l == 2 and n >= 8:
+    if l == 2 and n == 8:
         raise NotImplementedError(
-            "l = 2, n >= 8: these sequences pass through the algebraically special frequency; the "
-            "reference reads them from the Cook-Zalutskiy data files (qnm.py:60-122)")
+            "l = 2, n = 8: these sequences start at the algebraically special frequency (and split into "
+            "the multiplets {8,0}, {8,1} for m >= 0); the reference reads them from the Cook-Zalutskiy "
+            "data files (qnm.py:60-122)")
     # march in spin with step control: a point is accepted when the solved frequency lies
     # close to the one extrapolated along the sequence, otherwise the step is halved (near
     # avoided crossings two sequences come close and Newton must not change branch)

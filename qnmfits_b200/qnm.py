@@ -65,8 +65,8 @@ def _default_provider():
             import warnings
             warnings.warn(
                 "The 'qnm' package (Kerr QNM tables) is not installed: using the built-in Leaver "
-                "solver qnmfits_b200.kerr (same algorithm; frequencies agree to ~1e-9, overtones "
-                "n >= 8 of l = 2 unavailable).  Call qnmfits_b200.set_table_provider(...) to "
+                "solver qnmfits_b200.kerr (same algorithm; frequencies agree to ~1e-9, overtone "
+                "n = 8 of l = 2 unavailable).  Call qnmfits_b200.set_table_provider(...) to "
                 "install another source.", RuntimeWarning, stacklevel=3)
             _warned_fallback = True
         return kerr.modes_cache

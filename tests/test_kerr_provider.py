@@ -26,6 +26,28 @@ def test_schwarzschild_overtones_match_the_literature():
     assert abs(w0 - SCHWARZSCHILD[2][0]) < 2e-8
 
 
+def test_l2_overtones_beyond_the_algebraically_special_frequency():
+    """l = 2: overtone 8 of Schwarzschild is the algebraically special frequency -2i (M = 1), which the
+    continued fraction cannot reach; the ladder continues below it with the index of Leaver's table
+    (1985, table 1, 2M omega: n = 10 (0.126527, -4.605289), 11 (0.153107, -5.121653),
+    12 (0.165196, -5.630885) in his counting from 1) and of the `qnm` package.  Corotating Kerr
+    sequences of those overtones follow to chi = 0.99; the multiplets of n = 8 are not attempted."""
+    got = kerr.schwarzschild_omegas(-2, 2, 11)
+    assert got[8] == -2j
+    for n, ref in ((9, 0.126527 - 4.605289j), (10, 0.153107 - 5.121653j), (11, 0.165196 - 5.630885j)):
+        assert abs(2 * got[n] - ref) < 2e-6, (n, got[n])
+    seq = kerr.modes_cache(-2, 2, 2, 9)
+    assert seq.a[0] == 0.0 and abs(seq.a[-1] - 0.99) < 1e-12
+    assert abs(seq.omega[0] - got[9]) < 1e-10
+    assert seq.omega[-1].real > 0.8 and np.all(seq.omega.real > 0.06)    # away from the imaginary axis, up to 0.99
+    assert np.all(seq.omega.imag < 0) and np.max(np.abs(np.diff(seq.omega))) < 0.05
+    # the root really is the n = 9 one: it solves the radial equation in ANOTHER inversion too
+    w_check = kerr.solve_mode(-2, 2, 2, 7, float(seq.a[100]), seq.omega[100])[0]
+    assert abs(w_check - seq.omega[100]) < 1e-9
+    with pytest.raises(NotImplementedError):
+        kerr.modes_cache(-2, 2, 2, 8)
+
+
 def test_notebook_value_and_kerr_literature():
     seq = kerr.modes_cache(-2, 2, 2, 0)
     assert seq.a[0] == 0.0 and abs(seq.a[-1] - 0.99) < 1e-12 and np.all(np.diff(seq.a) > 0)
