@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define QNMFIT_ABI_VERSION 6
+#define QNMFIT_ABI_VERSION 7
 
 /* limits of the compiled kernels */
 #define QNMFIT_MAX_MODES_SMALL 12    /* register-resident TSQR kernel (K1): 4-row blocks
@@ -340,6 +340,36 @@ int qnmfit_fp64_peak(qnmfit_ctx *ctx, int kind, int iters, double *tflops);
  *   fast_mismatch = 1:  F = 8 M N^2 + 22 M N + 4 M - (8/3) N^3 - 4 N^2 + 28 N
  *                       (no model pass: ||d||^2 and two end rows instead). */
 double qnmfit_flops_per_fit(int rows, int n_modes, int n_series, int fast_mismatch);
+
+/* ---- lock-step Nelder-Mead (host code; no device is touched) ---------------------------
+ * The reference's free_frequency_fit (qnmfits/qnmfits.py:1992-2041) and calculate_epsilon
+ * (:1520-1560) call scipy.optimize.minimize(method='Nelder-Mead', bounds=...) once per
+ * waveform, one least-squares fit per objective call.  qnmfit_nm_* advances B such searches
+ * together so that every optimiser step is ONE qnmfit_fit_batch launch: the caller loops
+ *
+ *     n = qnmfit_nm_step(nm, NULL, x, idx);
+ *     while (n > 0) { f[0..n) = objective of point x[i*N .. i*N+N) of problem idx[i];
+ *                     n = qnmfit_nm_step(nm, f, x, idx); }
+ *
+ * Each problem follows scipy's bounded Nelder-Mead (scipy 1.18 _minimize_neldermead,
+ * non-adaptive coefficients, start simplex 5 % / 0.00025, clipping to the bounds, xatol and
+ * fatol test, status 0 converged / 1 maxfun / 2 maxiter) operation for operation; idx is
+ * ascending and holds a problem at most once per step.  `order`, when not NULL, is asked for
+ * the sorted order of a simplex's values only when that order is ambiguous (equal values or
+ * NaNs): numpy's argsort is not stable, so the Python wrapper passes numpy's own.  x and idx
+ * must hold n_problems points.  qnmfit_nm_step returns the number of points handed out, 0
+ * when every search has ended, QNMFIT_E_* (< 0) on an argument error. */
+#define QNMFIT_NM_MAX_VARS 64
+typedef struct qnmfit_nm qnmfit_nm;
+typedef void (*qnmfit_nm_order_fn)(const double *values, int n, int64_t *order, void *user);
+int qnmfit_nm_create(int64_t n_problems, int n_vars, const double *x0, const double *lower,
+                     const double *upper, double xatol, double fatol, double maxiter, double maxfun,
+                     qnmfit_nm_order_fn order, void *order_user, qnmfit_nm **out);
+int64_t qnmfit_nm_step(qnmfit_nm *nm, const double *f_prev, double *x_out, int64_t *idx_out);
+/* Any output pointer may be NULL.  x: [n_problems][n_vars] best vertices; fun: their values. */
+int qnmfit_nm_result(const qnmfit_nm *nm, double *x, double *fun, int64_t *nit, int64_t *nfev,
+                     int64_t *status, int64_t *n_calls);
+int qnmfit_nm_destroy(qnmfit_nm *nm);
 
 int qnmfit_abi_version(void);
 

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libqnmfit.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_MODES_SMALL = 12
 MIN_MODES_PAIR, MAX_MODES_PAIR = 9, 24
 MAX_MODES = 64
@@ -98,7 +98,11 @@ EXPORTS = (
     "qnmfit_fit_batch_peers",
     "qnmfit_h2d", "qnmfit_h2d_wait", "qnmfit_d2h", "qnmfit_zero", "qnmfit_stream_sync",
     "qnmfit_run_host",
+    "qnmfit_nm_create", "qnmfit_nm_step", "qnmfit_nm_result", "qnmfit_nm_destroy",
 )
+
+NM_MAX_VARS = 64                     # QNMFIT_NM_MAX_VARS
+NM_ORDER_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int64), C.c_void_p)
 
 _lib = None
 
@@ -162,6 +166,16 @@ def load_library(path=None):
     lib.qnmfit_fp64_peak.restype = C.c_int
     lib.qnmfit_flops_per_fit.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     lib.qnmfit_flops_per_fit.restype = C.c_double
+    lib.qnmfit_nm_create.argtypes = [C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                     C.c_double, C.c_double, C.c_double, NM_ORDER_FN, C.c_void_p,
+                                     C.POINTER(C.c_void_p)]
+    lib.qnmfit_nm_create.restype = C.c_int
+    lib.qnmfit_nm_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.qnmfit_nm_step.restype = C.c_int64
+    lib.qnmfit_nm_result.argtypes = [C.c_void_p] * 7
+    lib.qnmfit_nm_result.restype = C.c_int
+    lib.qnmfit_nm_destroy.argtypes = [C.c_void_p]
+    lib.qnmfit_nm_destroy.restype = C.c_int
     if lib.qnmfit_abi_version() != ABI_VERSION:
         raise ImportError(
             f"{path}: ABI version {lib.qnmfit_abi_version()} != binding {ABI_VERSION}; rebuild")

@@ -16,7 +16,17 @@ exactly scipy's trajectory (tests/test_neldermead.py checks x, fun, nit and nfev
 equality).  The only deliberate difference: when ``maxfun`` is hit in the middle of an
 iteration scipy abandons that iteration through an exception; here the problem simply
 stops before the call.
+
+Two implementations of the same state machine.  ``minimize_lockstep_numpy`` below is the
+specification.  Its bookkeeping costs ~2 ms per optimiser step at B = 4096 (fancy indexing
+over a dozen small arrays), ten times the batched fit it waits for, so ``minimize_lockstep``
+runs the C++ form in libqnmfit.so (``qnmfit_nm_*``, csrc/nm_lockstep.cu: host code, one call
+per optimiser step) whenever the problem has at most ``QNMFIT_NM_MAX_VARS`` variables; the
+tests hold the two to identical results, ties in the simplex order included (the C++ form
+asks numpy's own argsort for the order of equal values, which is not stable).
 """
+import ctypes as C
+
 import numpy as np
 
 RHO, CHI, PSI, SIGMA = 1.0, 2.0, 0.5, 0.5
@@ -51,24 +61,85 @@ def initial_simplex(x0, lower, upper):
     return np.clip(sim, lower, upper)
 
 
-def minimize_lockstep(fun, x0, bounds, xatol=1e-4, fatol=1e-4, maxiter=None, maxfun=None):
-    """Minimise B independent functions of N variables.
-
-    fun(X, idx) -> f : X float64 (n, N) trial points, idx int (n,) the problems they
-    belong to (ascending, at most one point per problem per call); returns float (n,).
-    x0: (B, N) or (N,) start point(s) (then B must be given by idx range = 1).
-    bounds: sequence of N (low, high) pairs.
-    """
-    x0 = np.atleast_2d(np.asarray(x0, dtype=float))
-    B, N = x0.shape
-    lower = np.array([b[0] for b in bounds], dtype=float)
-    upper = np.array([b[1] for b in bounds], dtype=float)
+def _limits(N, maxiter, maxfun):
+    """scipy's defaults for the two budgets."""
     if maxiter is None and maxfun is None:
         maxiter = maxfun = N * 200
     elif maxiter is None:
         maxiter = N * 200 if maxfun == np.inf else np.inf
     elif maxfun is None:
         maxfun = N * 200 if maxiter == np.inf else np.inf
+    return maxiter, maxfun
+
+
+@C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int64), C.c_void_p)
+def _numpy_order(values, n, order, _user):
+    """Order of a simplex whose values hold ties or NaNs: what scipy's ``np.argsort(fsim)`` gives."""
+    got = np.argsort(np.ctypeslib.as_array(values, (n,)))
+    for i in range(n):
+        order[i] = int(got[i])
+
+
+def minimize_lockstep(fun, x0, bounds, xatol=1e-4, fatol=1e-4, maxiter=None, maxfun=None):
+    """Minimise B independent functions of N variables.
+
+    fun(X, idx) -> f : X float64 (n, N) trial points, idx int64 (n,) the problems they
+    belong to (ascending, at most one point per problem per call); returns float (n,).
+    x0: (B, N) or (N,) start point(s) (then B must be given by idx range = 1).
+    bounds: sequence of N (low, high) pairs.
+
+    Runs the state machine of libqnmfit.so (``qnmfit_nm_step``: one C call between two
+    objective calls); more than ``QNMFIT_NM_MAX_VARS`` variables go to the numpy form.
+    """
+    from . import _cabi
+    x0 = np.ascontiguousarray(np.atleast_2d(np.asarray(x0, dtype=float)))
+    B, N = x0.shape
+    if N > _cabi.NM_MAX_VARS:
+        return minimize_lockstep_numpy(fun, x0, bounds, xatol, fatol, maxiter, maxfun)
+    lib = _cabi.load_library()
+    lower = np.array([b[0] for b in bounds], dtype=float)
+    upper = np.array([b[1] for b in bounds], dtype=float)
+    if len(lower) != N:
+        raise ValueError("bounds must hold one (low, high) pair per variable")
+    maxiter, maxfun = _limits(N, maxiter, maxfun)
+    handle = C.c_void_p()
+    rc = lib.qnmfit_nm_create(B, N, x0.ctypes.data, lower.ctypes.data, upper.ctypes.data, float(xatol),
+                              float(fatol), float(maxiter), float(maxfun), _numpy_order, None, C.byref(handle))
+    if rc:
+        raise _cabi.QnmfitError(rc, "qnmfit_nm_create: bad arguments")
+    try:
+        X = np.empty((max(B, 1), N), dtype=np.float64)
+        idx = np.empty(max(B, 1), dtype=np.int64)
+        f = None
+        while True:
+            n = lib.qnmfit_nm_step(handle, None if f is None else f.ctypes.data, X.ctypes.data, idx.ctypes.data)
+            if n <= 0:
+                break
+            # the objective gets its own copies: the next step overwrites X and idx
+            f = np.ascontiguousarray(fun(X[:n].copy(), idx[:n].copy()), dtype=np.float64).reshape(-1)
+            if len(f) != n:
+                raise ValueError(f"the objective returned {len(f)} values for {n} points")
+        if n < 0:
+            raise _cabi.QnmfitError(int(n), "qnmfit_nm_step: bad arguments")
+        x = np.empty((B, N), dtype=np.float64)
+        val = np.empty(B, dtype=np.float64)
+        nit, nfev, status = (np.empty(B, dtype=np.int64) for _ in range(3))
+        n_calls = C.c_int64()
+        lib.qnmfit_nm_result(handle, x.ctypes.data, val.ctypes.data, nit.ctypes.data, nfev.ctypes.data,
+                             status.ctypes.data, C.addressof(n_calls))
+    finally:
+        lib.qnmfit_nm_destroy(handle)
+    return LockstepResult(x, val, nit, nfev, status, int(n_calls.value))
+
+
+def minimize_lockstep_numpy(fun, x0, bounds, xatol=1e-4, fatol=1e-4, maxiter=None, maxfun=None):
+    """The same search written with numpy: the specification of ``qnmfit_nm_*`` (and the form
+    used beyond ``QNMFIT_NM_MAX_VARS`` variables).  Same arguments as ``minimize_lockstep``."""
+    x0 = np.atleast_2d(np.asarray(x0, dtype=float))
+    B, N = x0.shape
+    lower = np.array([b[0] for b in bounds], dtype=float)
+    upper = np.array([b[1] for b in bounds], dtype=float)
+    maxiter, maxfun = _limits(N, maxiter, maxfun)
 
     sim = initial_simplex(x0, lower, upper)
     fsim = np.full((B, N + 1), np.inf)

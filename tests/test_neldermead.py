@@ -72,3 +72,78 @@ def test_initial_simplex_matches_scipy():
             minimize(lambda x: seen.append(np.array(x)) or 0.0, x0[b], method="Nelder-Mead",
                      bounds=list(zip(lower, upper)), options={"maxfev": 3})
         np.testing.assert_array_equal(sim[b], np.array(seen[:3]))
+
+
+def _same(got, want):
+    for key in ("x", "fun", "nit", "nfev", "status"):
+        assert np.array_equal(getattr(got, key), getattr(want, key), equal_nan=True), key
+    assert got.n_calls == want.n_calls
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 5])
+@pytest.mark.parametrize("limits", [{}, {"maxfun": 23}, {"maxiter": 9}, {"maxfun": 3}, {"maxiter": 40, "maxfun": 61}])
+def test_native_state_machine_equals_the_numpy_form(N, limits):
+    """``minimize_lockstep`` (qnmfit_nm_* of libqnmfit.so, host code) against its specification
+    ``minimize_lockstep_numpy``: same requests in the same order, same results to the bit —
+    smooth objectives, plateaus (ties in the simplex order: numpy's argsort decides), NaNs and
+    infinities, budgets that end a search before, inside and after an iteration."""
+    rng = np.random.default_rng(100 + N)
+    B = 64
+    centre = rng.uniform(-0.5, 1.5, (B, N))
+    bounds = [(-1.0 + 0.1 * k, 1.0 + 0.2 * k) for k in range(N)]
+    x0 = rng.uniform(-1.2, 1.6, (B, N))
+    x0[0] = 0.0                                   # zero coordinates
+    x0[1] = [b[1] for b in bounds]                # on the upper bounds
+
+    def smooth(X, idx):
+        d = X - centre[idx]
+        return np.sum(d * d * (1.0 + np.arange(N)), axis=1) + 0.05 * np.sin(7 * X[:, 0])
+
+    def plateau(X, idx):
+        return np.round(np.sum(np.abs(X - centre[idx]), axis=1), 2)
+
+    def rough(X, idx):
+        f = smooth(X, idx)
+        f[(idx % 7 == 3) & (X[:, 0] > 0.5)] = np.nan
+        f[(idx % 5 == 1) & (X[:, 0] < -0.2)] = np.inf
+        return f
+
+    for objective in (smooth, plateau, rough):
+        logs = []
+
+        def make(tag):
+            def fun(X, idx):
+                logs.append((tag, X.copy(), idx.copy()))
+                assert X.dtype == np.float64 and idx.dtype == np.int64 and np.all(np.diff(idx) > 0)
+                return objective(X, idx)
+            return fun
+        got = nm.minimize_lockstep(make("c"), x0, bounds, xatol=1e-6, fatol=1e-5, **limits)
+        want = nm.minimize_lockstep_numpy(make("np"), x0, bounds, xatol=1e-6, fatol=1e-5, **limits)
+        _same(got, want)
+        mine = [entry for entry in logs if entry[0] == "c"]
+        spec = [entry for entry in logs if entry[0] == "np"]
+        assert len(mine) == len(spec) == got.n_calls
+        for (_, Xc, ic), (_, Xn, i_n) in zip(mine, spec):
+            assert np.array_equal(ic, i_n) and np.array_equal(Xc, Xn)
+
+
+def test_native_state_machine_edge_cases():
+    lib_err = pytest.raises(Exception)
+    f = lambda X, idx: np.sum(X * X, axis=1)  # noqa: E731
+    # no problems at all; a single problem given as a flat start point
+    empty = nm.minimize_lockstep(f, np.zeros((0, 2)), [(0, 1), (0, 1)])
+    assert empty.x.shape == (0, 2) and empty.n_calls == 0
+    one = nm.minimize_lockstep(f, [0.5, 0.25], [(-1, 1), (-1, 1)], xatol=1e-9, fatol=1e-12)
+    ref = nm.minimize_lockstep_numpy(f, [0.5, 0.25], [(-1, 1), (-1, 1)], xatol=1e-9, fatol=1e-12)
+    _same(one, ref)
+    assert np.all(np.abs(one.x) < 1e-8) and one.status[0] == 0
+    # an objective that returns the wrong number of values is an error, not a crash
+    with lib_err:
+        nm.minimize_lockstep(lambda X, idx: np.zeros(len(idx) + 1), np.zeros((3, 2)), [(0, 1), (0, 1)])
+    with pytest.raises(ValueError):
+        nm.minimize_lockstep(f, np.zeros((3, 2)), [(0, 1)])
+    # beyond QNMFIT_NM_MAX_VARS variables the numpy form takes over
+    from qnmfits_b200 import _cabi
+    N = _cabi.NM_MAX_VARS + 1
+    big = nm.minimize_lockstep(f, np.full((2, N), 0.3), [(-1, 1)] * N, maxfun=N + 5)
+    assert big.x.shape == (2, N) and np.all(big.nfev <= N + 5)
