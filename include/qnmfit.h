@@ -355,13 +355,16 @@ double qnmfit_flops_per_fit(int rows, int n_modes, int n_series, int fast_mismat
  * non-adaptive coefficients, start simplex 5 % / 0.00025, clipping to the bounds, xatol and
  * fatol test, status 0 converged / 1 maxfun / 2 maxiter) operation for operation; idx is
  * ascending and holds a problem at most once per step.  `order`, when not NULL, is asked for
- * the sorted order of a simplex's values only when that order is ambiguous (equal values or
- * NaNs): numpy's argsort is not stable, so the Python wrapper passes numpy's own.  x and idx
+ * the sorted order of the simplices whose order is ambiguous (equal values or NaNs; all such
+ * rows of a step in one call): numpy's argsort is not stable, so the Python wrapper passes
+ * numpy's own.  x and idx
  * must hold n_problems points.  qnmfit_nm_step returns the number of points handed out, 0
  * when every search has ended, QNMFIT_E_* (< 0) on an argument error. */
 #define QNMFIT_NM_MAX_VARS 64
 typedef struct qnmfit_nm qnmfit_nm;
-typedef void (*qnmfit_nm_order_fn)(const double *values, int n, int64_t *order, void *user);
+/* values: [n_rows][n] simplex values; order: [n_rows][n], to be filled with the permutation that
+ * sorts each row ascending (NaNs last). */
+typedef void (*qnmfit_nm_order_fn)(const double *values, int64_t n_rows, int n, int64_t *order, void *user);
 int qnmfit_nm_create(int64_t n_problems, int n_vars, const double *x0, const double *lower,
                      const double *upper, double xatol, double fatol, double maxiter, double maxfun,
                      qnmfit_nm_order_fn order, void *order_user, qnmfit_nm **out);

@@ -102,7 +102,7 @@ EXPORTS = (
 )
 
 NM_MAX_VARS = 64                     # QNMFIT_NM_MAX_VARS
-NM_ORDER_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int64), C.c_void_p)
+NM_ORDER_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int64, C.c_int, C.POINTER(C.c_int64), C.c_void_p)
 
 _lib = None
 

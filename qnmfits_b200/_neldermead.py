@@ -72,12 +72,12 @@ def _limits(N, maxiter, maxfun):
     return maxiter, maxfun
 
 
-@C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int64), C.c_void_p)
-def _numpy_order(values, n, order, _user):
-    """Order of a simplex whose values hold ties or NaNs: what scipy's ``np.argsort(fsim)`` gives."""
-    got = np.argsort(np.ctypeslib.as_array(values, (n,)))
-    for i in range(n):
-        order[i] = int(got[i])
+@C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int64, C.c_int, C.POINTER(C.c_int64), C.c_void_p)
+def _numpy_order(values, n_rows, n, order, _user):
+    """Order of the simplices whose values hold ties or NaNs: what scipy's ``np.argsort(fsim)``
+    gives for each of them (numpy sorts the rows of a 2-D array with the same routine)."""
+    got = np.argsort(np.ctypeslib.as_array(values, (n_rows, n)), axis=1)
+    np.ctypeslib.as_array(order, (n_rows, n))[...] = got
 
 
 def minimize_lockstep(fun, x0, bounds, xatol=1e-4, fatol=1e-4, maxiter=None, maxfun=None):

@@ -18,8 +18,9 @@
 // returns the same floats.  One point needs care: scipy orders the simplex with np.argsort,
 // whose order of EQUAL values depends on the CPU (numpy dispatches to an unstable SIMD network
 // sort where AVX2 / AVX-512 exist).  A row with distinct values has one sorted order whatever
-// the algorithm; a row with ties or NaNs is handed to the caller's `order` callback (the
-// Python wrapper passes np.argsort itself), or sorted stably when there is none.
+// the algorithm; the rows with ties or NaNs are handed, all rows of a step in one call, to the
+// caller's `order` callback (the Python wrapper passes np.argsort itself), or sorted stably when
+// there is none.  (They are common: a simplex pressed against a bound has coinciding vertices.)
 #include <cmath>
 #include <cstdint>
 #include <limits>
@@ -72,37 +73,71 @@ struct qnmfit_nm {
     std::vector<int64_t> req_pos;             // P_SECOND: position in `a` of each requested point
     std::vector<int64_t> s;                   // problems that shrink
     std::vector<double> tmp_x, tmp_f;
-    std::vector<int64_t> perm;
+    std::vector<int64_t> perm, everyone, amb_rows, amb_order;
+    std::vector<double> amb_values;
 
     double *vertex(int64_t b, int j) { return &sim[(b * (N + 1) + j) * N]; }
     double *values(int64_t b) { return &fsim[b * (N + 1)]; }
     bool has_budget(int64_t b) const { return (double)fcalls[b] < maxfun; }
     void stop(int64_t b) { active[b] = 0; status[b] = 1; }
 
-    void sort_row(int64_t b)
+    void apply_order(int64_t b, const int64_t *pm)
     {
         const int n = N + 1;
-        double *f = values(b);
-        for (int i = 0; i < n; ++i) perm[i] = i;
-        for (int i = 1; i < n; ++i) {         // insertion sort: stable
-            const int64_t p = perm[i];
-            int j = i;
-            while (j > 0 && sorts_before(f[p], f[perm[j - 1]])) { perm[j] = perm[j - 1]; --j; }
-            perm[j] = p;
-        }
-        bool ambiguous = f[perm[n - 1]] != f[perm[n - 1]];
-        for (int i = 1; i < n && !ambiguous; ++i) ambiguous = f[perm[i]] == f[perm[i - 1]];
-        if (ambiguous && order) order(f, n, perm.data(), order_user);
         bool sorted = true;
-        for (int i = 0; i < n; ++i) sorted = sorted && perm[i] == i;
+        for (int i = 0; i < n; ++i) sorted = sorted && pm[i] == i;
         if (sorted) return;
-        double *x = vertex(b, 0);
+        double *f = values(b), *x = vertex(b, 0);
         for (int i = 0; i < n; ++i) {
-            tmp_f[i] = f[perm[i]];
-            for (int c = 0; c < N; ++c) tmp_x[i * N + c] = x[perm[i] * N + c];
+            tmp_f[i] = f[pm[i]];
+            for (int c = 0; c < N; ++c) tmp_x[i * N + c] = x[pm[i] * N + c];
         }
         for (int i = 0; i < n; ++i) f[i] = tmp_f[i];
         for (int i = 0; i < n * N; ++i) x[i] = tmp_x[i];
+    }
+
+    // Order the simplices of `rows` by value.  Rows whose order is ambiguous (equal values,
+    // NaNs) are collected and handed to the caller's `order` in ONE call.
+    void sort_rows(const int64_t *rows, int64_t n_rows)
+    {
+        const int n = N + 1;
+        amb_rows.clear(); amb_values.clear();
+        for (int64_t r = 0; r < n_rows; ++r) {
+            const int64_t b = rows[r];
+            const double *f = values(b);
+            for (int i = 0; i < n; ++i) perm[i] = i;
+            for (int i = 1; i < n; ++i) {         // insertion sort: stable
+                const int64_t p = perm[i];
+                int j = i;
+                while (j > 0 && sorts_before(f[p], f[perm[j - 1]])) { perm[j] = perm[j - 1]; --j; }
+                perm[j] = p;
+            }
+            bool ambiguous = f[perm[n - 1]] != f[perm[n - 1]];
+            for (int i = 1; i < n && !ambiguous; ++i) ambiguous = f[perm[i]] == f[perm[i - 1]];
+            if (ambiguous && order) {
+                amb_rows.push_back(b);
+                amb_values.insert(amb_values.end(), f, f + n);
+            } else {
+                apply_order(b, perm.data());
+            }
+        }
+        if (amb_rows.empty()) return;
+        amb_order.assign(amb_rows.size() * n, 0);
+        order(amb_values.data(), (int64_t)amb_rows.size(), n, amb_order.data(), order_user);
+        for (size_t r = 0; r < amb_rows.size(); ++r) {
+            // a permutation, or the callback is broken: then the row is left as it is
+            const int64_t *pm = &amb_order[r * n];
+            uint64_t seen_lo = 0, seen_hi = 0;
+            bool ok = true;
+            for (int i = 0; i < n && ok; ++i) {
+                if (pm[i] < 0 || pm[i] >= n) { ok = false; break; }
+                uint64_t &word = pm[i] < 64 ? seen_lo : seen_hi;
+                const uint64_t bit = uint64_t(1) << (pm[i] & 63);
+                ok = !(word & bit);
+                word |= bit;
+            }
+            if (ok) apply_order(amb_rows[r], pm);
+        }
     }
 
     void put(double *x_out, int64_t *idx_out, int64_t b, const double *x)
@@ -236,10 +271,9 @@ struct qnmfit_nm {
 
     void end_iteration()
     {
-        for (int64_t b : a) {
+        for (int64_t b : a)
             if (active[b]) iters[b] += 1;
-            sort_row(b);
-        }
+        sort_rows(a.data(), (int64_t)a.size());
     }
 
     int64_t step(const double *f_prev, double *x_out, int64_t *idx_out)
@@ -284,7 +318,9 @@ struct qnmfit_nm {
                     if (!req.empty()) return (int64_t)req.size();
                     continue;
                 }
-                for (int64_t b = 0; b < B; ++b) sort_row(b);
+                everyone.resize(B);
+                for (int64_t b = 0; b < B; ++b) everyone[b] = b;
+                sort_rows(everyone.data(), B);
                 if (!begin_iteration(x_out, idx_out)) { phase = P_DONE; return 0; }
                 phase = P_REFLECT;
                 return (int64_t)req.size();
