@@ -1272,6 +1272,8 @@ class _ResidentData:
         finite = np.isfinite(omega).all()
         wmax = float(np.max(np.abs(omega))) if (n and finite) else np.inf
         dt = self._dt if self._dev * max(wmax, 1.0) <= 4e-10 else 0.0
+        if coef is None and row_end is None and n > 0 and n_series == 1:
+            return self._mismatches_one_call(omega, series_index, dt)
         rb = re = None
         if row_end is not None:
             re = np.ascontiguousarray(row_end, dtype=np.int32)
@@ -1302,6 +1304,55 @@ class _ResidentData:
             flags = raw[1 + n:1 + n + flagged].view(np.int32).reshape(-1, 2) if flagged <= cap else None
             _repair_rank_deficient(eng, batch, n, stream, rb, re, result, flags)
         del keep
+        return result
+
+
+    def _mismatches_one_call(self, omega, series_index, dt):
+        """``mismatches`` for explicit frequencies only (the free-frequency objective: hundreds of
+        launches per search): the frequencies live in a device block that is kept between calls,
+        the launch descriptor is filled once, and upload + launch + download are ONE C call
+        (``qnmfit_run_host``).  Block: [series_index i32[n] | omega c128[n][N] | counter |
+        mismatch f64[cap] | flag list]; the inputs are laid out by n (they travel as one copy),
+        the results by the capacity."""
+        eng = self.eng
+        n, N = omega.shape
+        idx = None if series_index is None else np.ascontiguousarray(series_index, dtype=np.int32)
+        st = getattr(self, "_one_call", None)
+        if st is None or st["N"] != N or st["cap"] < n:
+            cap = max(n, self.S if idx is not None else 1)
+            in_bytes = (4 * cap + 255) // 256 * 256 + 16 * cap * N
+            c_off = (in_bytes + 255) // 256 * 256
+            dev = eng.torch.empty(c_off + 16 + 8 * cap + 8 * FLAG_CAPACITY, dtype=eng.torch.uint8, device=eng.device)
+            base = dev.data_ptr()
+            batch = eng.make_batch(
+                times_d=self.times_p, data_d=self.data_p, n_times=self.K_tot, series_stride=self.K_tot,
+                n_fits=n, n_modes=N, n_series=1, row_begin_all=self.window[0], row_end_all=self.window[1],
+                t0_all=self.t0, omega_d=base, mismatch_d=base + c_off + 16, flagged_d=base + c_off + 8,
+                flag_list_d=base + c_off + 16 + 8 * cap, flag_capacity=FLAG_CAPACITY, plan_fits=n)
+            st = self._one_call = dict(N=N, cap=cap, dev=dev, base=base, result=base + c_off + 8, batch=batch,
+                                       up=(_cabi.Copy * 2)(), stream=eng.stream())
+        b, up, base, stream = st["batch"], st["up"], st["base"], st["stream"]
+        k, omega_p = 0, base
+        if idx is not None:
+            up[0].dst_dev, up[0].src_host, up[0].bytes = base, idx.ctypes.data, idx.nbytes
+            k, omega_p = 1, base + (idx.nbytes + 255) // 256 * 256
+        up[k].dst_dev, up[k].src_host, up[k].bytes = omega_p, omega.ctypes.data, omega.nbytes
+        b.n_fits = b.plan_fits = n
+        b.omega, b.series_index = omega_p, (base if idx is not None else None)
+        b.dt_nominal, b.uniform_weights = dt, 1 if (self.uniform and dt > 0.0) else 0
+        out = np.empty(1 + n, dtype=np.float64)
+        eng.ctx.run_host(b, None, up, k + 1, st["result"], out.ctypes.data, out.nbytes,
+                         _cabi.RUN_COALESCE | _cabi.RUN_ZERO_COUNTER, stream)
+        eng.h2d_bytes += omega.nbytes + (0 if idx is None else idx.nbytes)
+        eng.d2h_bytes += out.nbytes
+        self.launches += 1
+        flagged, result = int(out[0]), out[1:]
+        if flagged:
+            # a trial frequency (numerically) equal to another column: numpy truncates, so do we
+            flags = None
+            if flagged <= FLAG_CAPACITY:
+                flags = eng.download_raw(int(b.flag_list), 8 * flagged, stream=stream).view(np.int32).reshape(-1, 2)
+            _repair_rank_deficient(eng, b, n, stream, None, None, result, flags)
         return result
 
 
