@@ -207,7 +207,24 @@ def _single_fit_on_device(times_m, data_rows, frequencies, t0, coef, omega_rows=
             None if coef_rows is None else np.ascontiguousarray(coef_rows, dtype=np.complex128)]
     n_c, n_r, n_m = 16 * N, 16 * N * (N + 1), 16 * L * K
     out_bytes = n_c + n_r + n_m + 16 + 8
-    keep, ptrs, out = eng.upload_packed(host, out_bytes=out_bytes, stream=stream)
+    one_call = sum(a.nbytes for a in host if a is not None) < eng.DIRECT_BYTES
+    if one_call:
+        # upload, launch, download and synchronisation in ONE C call (qnmfit_run_host): the
+        # inputs are packed 256-byte aligned in front of the result region of one device block
+        offsets, total = [], 0
+        for a in host:
+            offsets.append(None if a is None else total)
+            total += 0 if a is None else (a.nbytes + 255) // 256 * 256
+        keep = eng.torch.empty(total + out_bytes, dtype=eng.torch.uint8, device=eng.device)
+        base = keep.data_ptr()
+        ptrs, out = [None if off is None else base + off for off in offsets], base + total
+        live = [(a, off) for a, off in zip(host, offsets) if a is not None and a.nbytes]
+        uploads = (_cabi.Copy * len(live))()
+        for c, (a, off) in zip(uploads, live):
+            c.dst_dev, c.src_host, c.bytes = base + off, a.ctypes.data, a.nbytes
+        eng.h2d_bytes += sum(a.nbytes for a, _ in live)
+    else:
+        keep, ptrs, out = eng.upload_packed(host, out_bytes=out_bytes, stream=stream)
     C_p, R_p, model_p = out, out + n_c, out + n_c + n_r
     mm_p = model_p + n_m
     common = dict(
@@ -218,16 +235,24 @@ def _single_fit_on_device(times_m, data_rows, frequencies, t0, coef, omega_rows=
         dt_nominal=0.0 if dynamic else nominal_step(times_m, wmax),
         C_d=C_p, mismatch_d=mm_p, residual_d=mm_p + 8, status_d=mm_p + 16,
         model_d=model_p, model_stride=L * K)
-    eng.ctx.fit_batch(eng.make_batch(R_d=R_p, **common), stream)
+    first = None
+    if one_call:
+        first = np.empty(out_bytes, dtype=np.uint8)
+        eng.ctx.run_host(eng.make_batch(R_d=R_p, **common), None, uploads, len(live), out, first.ctypes.data,
+                         out_bytes, _cabi.RUN_COALESCE, stream)
+        eng.d2h_bytes += out_bytes
+    else:
+        eng.ctx.fit_batch(eng.make_batch(R_d=R_p, **common), stream)
 
-    def fetch():
-        raw = eng.download_raw(out, out_bytes, np.uint8, stream=stream)
+    def fetch(raw=None):
+        if raw is None:
+            raw = eng.download_raw(out, out_bytes, np.uint8, stream=stream)
         return (raw[:n_c].view(np.complex128), raw[n_c:n_c + n_r].view(np.complex128).reshape(N, N + 1),
                 raw[n_c + n_r:n_c + n_r + n_m].view(np.complex128).reshape(L, K),
                 raw[n_c + n_r + n_m:n_c + n_r + n_m + 16].view(np.float64),
                 int(raw[n_c + n_r + n_m + 16:n_c + n_r + n_m + 20].view(np.int32)[0]))
 
-    C, R, model, scal, status = fetch()
+    C, R, model, scal, status = fetch(first)
     rank, s = _rank_and_singular_values(R, L * K)
     if rank < N:
         # numpy truncates here: complete the minimum-norm solution from the factor
