@@ -481,6 +481,40 @@ def test_free_frequency_objective_matches_oracle_mismatch(qf, eng, oracle_tables
         assert abs(got[k] - orc.mismatch(wl.times[sel], model, wl.data[b][sel])) < MM_TOL
 
 
+def test_objective_calls_of_changing_size_reuse_the_device_block(qf, eng, oracle_tables):
+    """The explicit-frequency launches keep their device block between calls
+    (``_ResidentData._mismatches_one_call``): calls with fewer, more (the block grows) and again
+    fewer trial points, one of them equal to a fixed mode (flagged, repaired: numpy truncates),
+    and calls without per-fit data rows, all against the numpy objective."""
+    from qnmfits_b200 import qnmfits as api
+    wl = workloads.config5(n_waveforms=12, n_fixed=2)
+    fixed = np.array(qf.qnm.omega_list(wl.modes, wl.chif, wl.Mf))
+    sel = orc.window(wl.times, 0.0, 100, 'geq')
+
+    def want(b, w):
+        a, C, res, rank, s, model = orc.lstsq_fit(wl.times[sel], wl.data[b][sel], np.hstack([fixed, w]), 0.0)
+        return orc.mismatch(wl.times[sel], model, wl.data[b][sel])
+
+    rng = np.random.default_rng(21)
+    obj = api._FreeFrequencyObjective(wl.times, wl.data[:6], 0.0, fixed, 'geq', 100)
+    for idx in (np.array([1, 4]), np.arange(6), np.array([0, 2, 5]), np.array([3])):
+        X = np.column_stack([rng.uniform(0.2, 1.5, len(idx)), rng.uniform(-0.9, -0.05, len(idx))])
+        if len(idx) == 3:
+            X[1] = [fixed[0].real, fixed[0].imag]
+        got = obj(X, idx)
+        for k, b in enumerate(idx):
+            assert abs(got[k] - want(b, X[k, 0] + 1j * X[k, 1])) < MM_TOL, (idx, k)
+    assert obj.launches >= 4
+    # one data row, no series_index: 3 trial points, then 9 (larger than the block), then 1
+    res = api._ResidentData(wl.times, wl.data[7], 0.0, 'geq', 100)
+    for n in (3, 9, 1):
+        w = rng.uniform(0.2, 1.5, n) + 1j * rng.uniform(-0.9, -0.05, n)
+        omega = np.column_stack([np.tile(fixed, (n, 1)), w])
+        got = res.mismatches(omega)
+        for k in range(n):
+            assert abs(got[k] - want(7, w[k])) < MM_TOL, (n, k)
+
+
 def test_omega_grid_vs_reference_golden(qf, eng, golden):
     """mismatch_omega_grid (reference qnmfits.py:1679-1827): orientation [i_im, i_re], no
     fixed modes, and the 'closest' window that loses one sample per grid point."""
