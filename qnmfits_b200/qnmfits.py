@@ -1255,6 +1255,23 @@ def mismatch_M_chi_grid(times, data, modes, Mf_minmax, chif_minmax, t0,
 # --------------------------------------------------------------------------
 # free-frequency search (reference qnmfits.py:1905-2043)
 
+def explicit_block_layout(n, cap, N, with_index):
+    """Byte offsets inside the device block of ``_ResidentData._mismatches_one_call`` (pure
+    arithmetic, unit-tested on the CPU): the inputs of a call with n fits — ``series_index``
+    i32[n] at 0 when there is one, ``omega`` c128[n][N] 256-byte aligned behind it — are laid out
+    by n so that they travel in one copy; the result region, laid out by the capacity, starts
+    at ``c_off``: 8 unused bytes, the counter of flagged fits at c_off + 8, mismatch f64[cap] at
+    c_off + 16, the list of flagged fits behind it.  Returns (omega offset, c_off, block bytes)."""
+    if not 0 <= n <= cap:
+        raise ValueError("n must lie in [0, cap]")
+    def inputs(m):
+        head = (4 * m + 255) // 256 * 256 if with_index else 0
+        return head, head + 16 * m * N
+    omega_off, _ = inputs(n)
+    c_off = (inputs(cap)[1] + 255) // 256 * 256
+    return omega_off, c_off, c_off + 16 + 8 * cap + 8 * FLAG_CAPACITY
+
+
 class _ResidentData:
     """``times`` and S data rows resident on the device for repeated launches with fresh
     frequencies: the objective of the optimiser-driven entry points (free_frequency_fit,
@@ -1345,9 +1362,8 @@ class _ResidentData:
         st = getattr(self, "_one_call", None)
         if st is None or st["N"] != N or st["cap"] < n:
             cap = max(n, self.S if idx is not None else 1)
-            in_bytes = (4 * cap + 255) // 256 * 256 + 16 * cap * N
-            c_off = (in_bytes + 255) // 256 * 256
-            dev = eng.torch.empty(c_off + 16 + 8 * cap + 8 * FLAG_CAPACITY, dtype=eng.torch.uint8, device=eng.device)
+            _, c_off, total = explicit_block_layout(cap, cap, N, True)
+            dev = eng.torch.empty(total, dtype=eng.torch.uint8, device=eng.device)
             base = dev.data_ptr()
             batch = eng.make_batch(
                 times_d=self.times_p, data_d=self.data_p, n_times=self.K_tot, series_stride=self.K_tot,
@@ -1360,7 +1376,7 @@ class _ResidentData:
         k, omega_p = 0, base
         if idx is not None:
             up[0].dst_dev, up[0].src_host, up[0].bytes = base, idx.ctypes.data, idx.nbytes
-            k, omega_p = 1, base + (idx.nbytes + 255) // 256 * 256
+            k, omega_p = 1, base + explicit_block_layout(n, st["cap"], N, True)[0]
         up[k].dst_dev, up[k].src_host, up[k].bytes = omega_p, omega.ctypes.data, omega.nbytes
         b.n_fits = b.plan_fits = n
         b.omega, b.series_index = omega_p, (base if idx is not None else None)

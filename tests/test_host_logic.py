@@ -209,3 +209,21 @@ def test_coef_columns_assemble_like_the_reference_mapping_fit(qf):
         api._coef_table(spherical, modes, chis)
     with pytest.raises(ValueError):
         api._mu_lists(spherical, modes, 0.69, {label: np.ones(3)})
+
+
+def test_explicit_block_layout_keeps_inputs_and_results_apart():
+    """Device block of the explicit-frequency launches (free-frequency objective): whatever the
+    number of fits of a call, its inputs end before the result region, which does not move."""
+    from qnmfits_b200.qnmfits import explicit_block_layout, FLAG_CAPACITY
+    for N in (1, 3, 8, 24):
+        for cap in (1, 7, 64, 4096, 65536):
+            _, c_off, total = explicit_block_layout(cap, cap, N, True)
+            assert c_off % 256 == 0 and total == c_off + 16 + 8 * cap + 8 * FLAG_CAPACITY
+            for with_index in (True, False):
+                for n in sorted({0, 1, cap // 3, cap - 1, cap} & set(range(cap + 1))):
+                    omega_off, c2, t2 = explicit_block_layout(n, cap, N, with_index)
+                    assert omega_off % 256 == 0 and (omega_off >= 4 * n if with_index else omega_off == 0)
+                    assert omega_off + 16 * n * N <= c2 <= c_off      # inputs end before the counter
+                    assert t2 <= total                                 # the block allocated for cap holds it
+    with pytest.raises(ValueError):
+        explicit_block_layout(5, 4, 3, True)
