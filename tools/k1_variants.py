@@ -25,17 +25,13 @@ VARIANTS = {       # leaf-loop pipelining: H columns of the next block refilled 
 
 
 def build():
+    """Every variant is a full library build (all translation units, __graft_entry__.build_library)
+    with the variant's -D switches, into tools/_variants/ with its own object directory."""
+    import __graft_entry__ as ge
     os.makedirs(OUT, exist_ok=True)
-    procs = []
     for name, flags in VARIANTS.items():
-        cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-               "-Xcompiler", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"),
-               "-I" + os.path.join(ROOT, "qnmfits_b200", "csrc"), "-DQNMFIT_ONLY_N8", "-Xptxas", "-v", *flags,
-               "-o", os.path.join(OUT, f"libqnmfit_{name}.so"),
-               os.path.join(ROOT, "qnmfits_b200", "csrc", "qnmfit_api.cu")]
-        procs.append((name, subprocess.Popen(cmd, cwd=ROOT)))
-    for name, p in procs:
-        assert p.wait() == 0, name
+        ge.build_library(force=True, extra_flags=flags, lib=os.path.join(OUT, f"libqnmfit_{name}.so"),
+                         build_dir=os.path.join(ROOT, "build", "variant_" + name))
 
 
 def run(steps=20):
