@@ -920,6 +920,10 @@ __global__ void __launch_bounds__(THREADS, 1) fit_small_kernel(const __grid_cons
     const SmallLane L = small_lane_setup(p, blockIdx.x, tid, THREADS, !STAGED, SmallLayout<N>::MB);
     small_clear<N, THREADS>(sm, tid);
     __syncthreads();
+#ifdef QNMFIT_K1_SKEW_NS   /* developer experiment (profiles/k1_skew_r02.txt): the two warps of a scheduler
+                              started 300 / 1200 ns apart: 2.2418 / 2.2412 ms against 2.2404, no effect */
+    if ((tid >> 5) >= THREADS / 64) __nanosleep(QNMFIT_K1_SKEW_NS);
+#endif
 
     int status = 0;
     SmallAcc acc;

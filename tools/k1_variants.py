@@ -50,7 +50,7 @@ def run(steps=20):
     results = {}
     names = sys.argv[2:] or sorted(f[len('libqnmfit_'):-3] for f in os.listdir(OUT) if f.startswith('libqnmfit_') and f.endswith('.so'))
     for name in names:
-        path = os.path.join(OUT, f"libqnmfit_{name}.so")
+        path = os.path.join(OUT, f"libqnmfit_{name}.so") if name != "default" else _cabi.LIB_PATH
         if not os.path.isfile(path):
             continue
         lib = _cabi.load_library(path)
