@@ -147,3 +147,68 @@ def test_native_state_machine_edge_cases():
     N = _cabi.NM_MAX_VARS + 1
     big = nm.minimize_lockstep(f, np.full((2, N), 0.3), [(-1, 1)] * N, maxfun=N + 5)
     assert big.x.shape == (2, N) and np.all(big.nfev <= N + 5)
+
+
+def test_native_state_machine_random_configurations():
+    """Thirty random problems (1 - 6 variables, 1 - 40 searches, random bounds, tolerances and
+    budgets, objectives quantised to a random grid so that ties are frequent): the C++ form and
+    the numpy form agree to the bit."""
+    rng = np.random.default_rng(2024)
+    for trial in range(30):
+        N = int(rng.integers(1, 7))
+        B = int(rng.integers(1, 41))
+        lo = rng.uniform(-2, 0, N)
+        hi = lo + rng.uniform(0.5, 3, N)
+        bounds = list(zip(lo, hi))
+        x0 = rng.uniform(lo - 0.3, hi + 0.3, (B, N))
+        centre = rng.uniform(lo - 0.5, hi + 0.5, (B, N))
+        scale = rng.uniform(0.2, 5.0, N)
+        quantum = float(rng.choice([0.0, 1e-3, 1e-2, 0.1]))
+        limits = [{}, {"maxfun": int(rng.integers(1, 60))}, {"maxiter": int(rng.integers(1, 30))}][trial % 3]
+
+        def fun(X, idx):
+            f = np.sum(scale * (X - centre[idx]) ** 2, axis=1)
+            return np.round(f / quantum) * quantum if quantum else f
+        kw = dict(xatol=float(rng.choice([1e-8, 1e-4, 1e-2])), fatol=float(rng.choice([1e-10, 1e-4, 1e-1])), **limits)
+        _same(nm.minimize_lockstep(fun, x0, bounds, **kw), nm.minimize_lockstep_numpy(fun, x0, bounds, **kw))
+
+
+def test_native_state_machine_survives_a_broken_order_callback():
+    """The `order` callback is only trusted when it returns permutations: garbage leaves the
+    simplices of that step unsorted (a worse search, not a crash or an out-of-range access);
+    without a callback ties are resolved stably."""
+    import ctypes as C
+    from qnmfits_b200 import _cabi
+    lib = _cabi.load_library()
+
+    @_cabi.NM_ORDER_FN
+    def garbage(values, n_rows, n, order, _user):
+        for i in range(n_rows * n):
+            order[i] = 7 if i % 2 else -3
+
+    for callback in (garbage, _cabi.NM_ORDER_FN()):
+        B, N = 5, 2
+        x0 = np.tile([0.3, 0.6], (B, 1))
+        lower, upper = np.zeros(N), np.ones(N)
+        handle = C.c_void_p()
+        assert lib.qnmfit_nm_create(B, N, x0.ctypes.data, lower.ctypes.data, upper.ctypes.data, 1e-4, 1e-4,
+                                    400.0, 400.0, callback, None, C.byref(handle)) == 0
+        X, idx = np.empty((B, N)), np.empty(B, dtype=np.int64)
+        f, steps = None, 0
+        while True:
+            n = lib.qnmfit_nm_step(handle, None if f is None else f.ctypes.data, X.ctypes.data, idx.ctypes.data)
+            assert 0 <= n <= B
+            if n == 0:
+                break
+            assert np.all((X[:n] >= 0) & (X[:n] <= 1)) and np.all(np.diff(idx[:n]) > 0)
+            f = np.round(np.sum((X[:n] - 0.5) ** 2, axis=1), 2)      # plateaus: ties at every step
+            steps += 1
+            assert steps < 2000
+        x, nfev = np.empty((B, N)), np.empty(B, dtype=np.int64)
+        assert lib.qnmfit_nm_result(handle, x.ctypes.data, None, None, nfev.ctypes.data, None, None) == 0
+        assert np.all((x >= 0) & (x <= 1)) and np.all(nfev <= 400)
+        assert lib.qnmfit_nm_destroy(handle) == 0
+    # argument errors are reported, not dereferenced
+    assert lib.qnmfit_nm_create(1, 0, x0.ctypes.data, lower.ctypes.data, upper.ctypes.data, 1e-4, 1e-4, 1.0, 1.0,
+                                _cabi.NM_ORDER_FN(), None, C.byref(handle)) == -2
+    assert lib.qnmfit_nm_step(None, None, X.ctypes.data, idx.ctypes.data) == -1
