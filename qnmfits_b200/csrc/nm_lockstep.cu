@@ -153,7 +153,9 @@ struct qnmfit_nm {
     bool begin_iteration(double *x_out, int64_t *idx_out)
     {
         req.clear();
-        a.clear(); xbar.clear(); xr.clear();
+        a.clear();
+        xbar.resize((size_t)B * N); xr.resize((size_t)B * N);    // filled by position in `a`
+        const double n_vars = (double)N;
         for (int64_t b = 0; b < B; ++b) {
             if (!active[b]) continue;
             if ((double)fcalls[b] >= maxfun) { stop(b); continue; }
@@ -174,12 +176,11 @@ struct qnmfit_nm {
             if (!nan && size <= xatol && spread <= fatol) { active[b] = 0; continue; }
             if (!has_budget(b)) { stop(b); continue; }      // (cannot happen after the test above)
             const double *worst = vertex(b, N);
-            const size_t at = xbar.size();
-            xbar.resize(at + N); xr.resize(at + N);
+            const size_t at = a.size() * N;
             for (int c = 0; c < N; ++c) {
-                double sum = vertex(b, 0)[c];
-                for (int j = 1; j < N; ++j) sum = sum + vertex(b, j)[c];
-                const double xb = sum / N;
+                double sum = x0[c];
+                for (int j = 1; j < N; ++j) sum = sum + x0[j * N + c];
+                const double xb = sum / n_vars;
                 xbar[at + c] = xb;
                 xr[at + c] = clip((1 + RHO) * xb - RHO * worst[c], lower[c], upper[c]);
             }
